@@ -1,0 +1,166 @@
+/*
+ * ssd_b200.h -- C ABI of libssd_b200.so, the B200 (sm_100a) implementation of
+ * the tf-ssd hot path.
+ *
+ * The reference (FurkanOM/tf-ssd) is pure Python/TensorFlow and has NO native
+ * interface of its own; the boundary it exposes is a set of
+ * Python call signatures.  Every entry point below therefore cites the
+ * reference Python function (file:line under the reference tree) whose
+ * arithmetic it replaces.  The Python modules under tf_ssd_b200/ keep the
+ * reference's names/argument meanings and bind these symbols through ctypes
+ * (tf_ssd_b200/_ffi.py); INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C types only; no torch / C++ types cross this boundary.
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller
+ *     (allocated e.g. as a torch tensor); h_* is a HOST pointer read
+ *     synchronously before the call returns.  The library never frees or
+ *     retains caller memory.
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed
+ *     as void*); calls are re-entrant and safe to capture into a CUDA graph
+ *     (no allocation, no synchronisation, no host<->device copy inside).
+ *   - scratch memory is a caller-provided workspace; query its size with the
+ *     matching ssd_*_workspace_bytes().
+ *   - return value: 0 success; <0 argument error (SSD_ERR_*); >0 cudaError_t.
+ *     ssd_last_error() returns a thread-local description of the last
+ *     non-zero return.
+ *   - boxes are normalised [y1, x1, y2, x2] float32; tensors are dense,
+ *     row-major, in the shapes written next to each argument.
+ */
+#ifndef SSD_B200_H_
+#define SSD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSD_B200_ABI_VERSION 1
+
+#define SSD_OK               0
+#define SSD_ERR_NULL        -1   /* a required pointer is NULL            */
+#define SSD_ERR_SHAPE       -2   /* a size/shape argument is out of range  */
+#define SSD_ERR_WORKSPACE   -3   /* workspace_bytes smaller than required  */
+#define SSD_ERR_UNSUPPORTED -4   /* valid request this build cannot serve  */
+
+#define SSD_MAX_FEATURE_MAPS 8
+#define SSD_MAX_ASPECT_RATIOS 8
+
+typedef void* ssd_stream_t;      /* cudaStream_t */
+
+int         ssd_abi_version(void);
+const char* ssd_last_error(void);
+/* Device the library sees as current: fills name (<= name_len bytes), SM count
+ * and compute capability major*10+minor.  Used by the loader to fail loudly on
+ * a non-sm_100 device. */
+int ssd_device_info(char* h_name, int name_len, int* h_sm_count, int* h_cc);
+
+/* ---------------------------------------------------------------- priors -- */
+/* utils/bbox_utils.py:131-214 generate_prior_boxes (+ :151-176 base boxes,
+ * :131-148 scales).  h_aspect_ratios is the concatenation of the per-map
+ * aspect-ratio lists (h_ar_counts[i] entries for map i); each map gets
+ * h_ar_counts[i]+1 anchors per cell (the extra square box last).
+ * d_out: [n_anchors,4].  n_anchors must equal sum(fm^2 * (count+1)). */
+int ssd_prior_boxes(const int* h_fm_shapes, int n_maps,
+                    const float* h_aspect_ratios, const int* h_ar_counts,
+                    float* d_out, int n_anchors, ssd_stream_t stream);
+int ssd_prior_box_count(const int* h_fm_shapes, int n_maps, const int* h_ar_counts);
+
+/* ------------------------------------------------------------------- IoU -- */
+/* utils/bbox_utils.py:24-55 generate_iou_map.
+ * d_boxes: [N,4] (boxes_batched=0) or [B,N,4] (boxes_batched=1);
+ * d_gt: [B,G,4]; d_out: [B,N,G].  The rank-2 mode of the reference
+ * (transpose_perm=[1,0]) is B=1.  0/0 yields NaN like the reference. */
+int ssd_iou_map(const float* d_boxes, const float* d_gt, int B, int N, int G,
+                int boxes_batched, float* d_out, ssd_stream_t stream);
+
+/* ------------------------------------------------------- target encoding -- */
+/* utils/train_utils.py:102-136 calculate_actual_outputs, fused with
+ * utils/bbox_utils.py:85-128 get_deltas_from_bboxes; the [B,N,G] IoU map is
+ * never materialised.
+ * d_priors [N,4]; d_gt_boxes [B,G,4]; d_gt_labels [B,G] int32 (-1 padding);
+ * h_variances[4].  Outputs: d_deltas [B,N,4]; d_onehot [B,N,L] (may be NULL);
+ * d_label [B,N] int32 and d_match [B,N] int32 = argmax GT index (either may be
+ * NULL).  Positive iff max IoU > iou_threshold (strict); first max wins. */
+int ssd_match_encode(const float* d_priors, const float* d_gt_boxes, const int32_t* d_gt_labels,
+                     int B, int N, int G, int L, float iou_threshold, const float* h_variances,
+                     float* d_deltas, float* d_onehot, int32_t* d_label, int32_t* d_match,
+                     ssd_stream_t stream);
+
+/* utils/bbox_utils.py:85-128 / :58-82 as stand-alone element-wise ops.
+ * priors_batched: 0 -> d_priors [N,4] broadcast over B, 1 -> [B,N,4]. */
+int ssd_encode_deltas(const float* d_priors, const float* d_boxes, int B, int N, int priors_batched,
+                      float* d_deltas, ssd_stream_t stream);
+int ssd_decode_boxes(const float* d_priors, const float* d_deltas, int B, int N, int priors_batched,
+                     float* d_boxes, ssd_stream_t stream);
+
+/* ------------------------------------------------------------------ loss -- */
+/* ssd_loss.py:26-57 CustomLoss.loc_loss_fn + :59-91 CustomLoss.conf_loss_fn
+ * (Huber on positives; categorical CE with hard-negative mining by rank).
+ * d_actual_deltas/d_pred_deltas [B,N,4]; d_actual_labels [B,N,L] one-hot;
+ * d_pred_labels [B,N,L]: probabilities (from_logits=0, the public signature;
+ * Keras renormalise + clip 1e-7 path) or pre-softmax logits (from_logits=1,
+ * what Keras substitutes inside model.fit).
+ * Outputs: d_loc_loss [B], d_conf_loss [B] (per-image, like the reference).
+ * Either half may be skipped by passing NULL for its inputs AND output.
+ * The workspace keeps per-anchor state for ssd_loss_bwd. */
+size_t ssd_loss_workspace_bytes(int B, int N, int L);
+int ssd_loss_fwd(const float* d_actual_deltas, const float* d_pred_deltas,
+                 const float* d_actual_labels, const float* d_pred_labels,
+                 int B, int N, int L, float neg_pos_ratio, float loc_loss_alpha, int from_logits,
+                 float* d_loc_loss, float* d_conf_loss,
+                 void* d_workspace, size_t workspace_bytes, ssd_stream_t stream);
+/* Gradient of  grad_scale * (sum_b loc[b] + sum_b conf[b])  w.r.t. pred_deltas
+ * and the LOGITS (from_logits=1 forward required).  Keras' batch-mean
+ * reduction (trainer.py:91-94) is grad_scale = 1/B.  Must follow ssd_loss_fwd
+ * on the same workspace. */
+int ssd_loss_bwd(const float* d_actual_deltas, const float* d_pred_deltas,
+                 const float* d_actual_labels, const float* d_pred_logits,
+                 int B, int N, int L, float loc_loss_alpha, float grad_scale,
+                 float* d_grad_deltas, float* d_grad_logits,
+                 const void* d_workspace, size_t workspace_bytes, ssd_stream_t stream);
+
+/* --------------------------------------------------------- decode + NMS -- */
+/* models/header.py:88 Activation("softmax") over the last axis: [rows,L]. */
+int ssd_softmax(const float* d_logits, int64_t rows, int L, float* d_probs, ssd_stream_t stream);
+
+/* models/decoder.py:60-93 SSDDecoder.call, fused: deltas*variances (:74),
+ * get_bboxes_from_deltas (:75, utils/bbox_utils.py:58-82), background-row
+ * suppression (:78-83) and tf.image.combined_non_max_suppression (:86-92 via
+ * utils/bbox_utils.py:10-21) with max_output_size_per_class = max_total_size,
+ * clip_boxes, pad_per_class=False.
+ * d_priors [N,4]; d_pred_deltas [B,N,4]; d_pred_labels [B,N,L] probabilities
+ * (from_logits=0) or logits (from_logits=1: softmax fused in).
+ * Outputs (order of the reference's return, decoder.py:93):
+ *   d_boxes [B,T,4] clipped to [0,1], zero padded; d_labels [B,T] float32
+ *   class ids; d_scores [B,T]; d_valid [B] int32 number of detections, or -1
+ *   if that image produced more candidates than max_candidates (overflow).
+ * max_candidates: per-image capacity of the candidate list; 0 -> N (exact for
+ * normalised probabilities with score_threshold >= 0.5). */
+size_t ssd_decode_nms_workspace_bytes(int B, int N, int L, int max_total_size, int max_candidates);
+int ssd_decode_nms(const float* d_priors, const float* d_pred_deltas, const float* d_pred_labels,
+                   int B, int N, int L, const float* h_variances, int from_logits,
+                   float score_threshold, float iou_threshold, int max_total_size, int max_candidates,
+                   float* d_boxes, float* d_labels, float* d_scores, int32_t* d_valid,
+                   void* d_workspace, size_t workspace_bytes, ssd_stream_t stream);
+
+/* utils/bbox_utils.py:10-21 non_max_suppression -> the general
+ * tf.image.combined_non_max_suppression (pad_per_class=False).
+ * d_boxes [B,N,q,4] with q == 1 or q == L; d_scores [B,N,L].
+ * Outputs as TensorFlow returns them: boxes [B,T,4], scores [B,T],
+ * classes [B,T] float32, valid [B] int32 (-1 on candidate overflow).
+ * max_candidates: 0 -> N*L (always sufficient). */
+size_t ssd_combined_nms_workspace_bytes(int B, int N, int L, int max_output_size_per_class,
+                                        int max_total_size, int max_candidates);
+int ssd_combined_nms(const float* d_boxes, const float* d_scores, int B, int N, int q, int L,
+                     int max_output_size_per_class, int max_total_size,
+                     float iou_threshold, float score_threshold, int clip_boxes, int max_candidates,
+                     float* d_out_boxes, float* d_out_scores, float* d_out_classes, int32_t* d_valid,
+                     void* d_workspace, size_t workspace_bytes, ssd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSD_B200_H_ */

@@ -1,0 +1,58 @@
+// Error reporting + device queries shared by every entry point of libssd_b200.so.
+#include "common.cuh"
+
+#include <string.h>
+
+namespace ssd {
+
+static thread_local char g_err[512] = "";
+
+char* last_error_buffer() { return g_err; }
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+    return (int)e;
+}
+
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached = n;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+}  // namespace ssd
+
+extern "C" int ssd_abi_version(void) { return SSD_B200_ABI_VERSION; }
+
+extern "C" const char* ssd_last_error(void) { return ssd::last_error_buffer(); }
+
+extern "C" int ssd_device_info(char* h_name, int name_len, int* h_sm_count, int* h_cc) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return ssd::cuda_fail(e, "ssd_device_info: cudaGetDevice");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) return ssd::cuda_fail(e, "ssd_device_info: cudaGetDeviceProperties");
+    if (h_name && name_len > 0) {
+        strncpy(h_name, prop.name, (size_t)name_len - 1);
+        h_name[name_len - 1] = '\0';
+    }
+    if (h_sm_count) *h_sm_count = prop.multiProcessorCount;
+    if (h_cc) *h_cc = prop.major * 10 + prop.minor;
+    return SSD_OK;
+}

@@ -1,0 +1,473 @@
+// Decode + combined NMS (models/decoder.py:60-93 -> utils/bbox_utils.py:10-21
+// -> tf.image.combined_non_max_suppression) and softmax (models/header.py:88)
+// for sm_100a.  Everything stays on the device: the reference's NMS is a
+// CPU-only TensorFlow kernel that forces a device->host copy of all head
+// outputs.
+//
+// Two kernels per call:
+//   A. candidate pass -- full grid, one thread per (image, anchor); score rows
+//      staged through shared memory; optional fused softmax; background-row
+//      rule; survivors (score > threshold) appended to a per-image list as
+//      64-bit keys  [class:8 | ~order(score):32 | anchor:24].
+//   B. per-image pass -- one CTA per image: bitonic sort of the keys (class
+//      asc, score desc, anchor asc), greedy per-class suppression with one
+//      warp per class, then a second sort of the survivors by (score desc,
+//      class asc, anchor asc) and emission of the first max_total rows.
+// Boxes are never materialised for all anchors: pass B decodes the (few)
+// candidate boxes on demand from priors+deltas with the same arithmetic.
+//
+// Tie order on equal scores follows the oracle rule documented in
+// oracle/box_oracle.py (TensorFlow leaves it implementation-defined).
+
+#include "common.cuh"
+
+namespace ssd {
+
+constexpr int kRowThreadsNms = 128;
+constexpr int kNmsThreads = 1024;
+constexpr uint64_t kPadKey = ~0ull;
+
+__device__ __forceinline__ uint32_t order_bits(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unorder_bits(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
+}
+
+__device__ __forceinline__ void stage_rows(const float* __restrict__ src, int total, float* __restrict__ s) {
+    const int head = min(total, (int)((4 - (((uintptr_t)src >> 2) & 3)) & 3));
+    const int nvec = (total - head) >> 2;
+    for (int e = threadIdx.x; e < head; e += blockDim.x) s[e] = __ldcs(src + e);
+    const float4* v = reinterpret_cast<const float4*>(src + head);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        float4 t = __ldcs(v + i);
+        float* d = s + head + (i << 2);
+        d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+    }
+    for (int e = head + (nvec << 2) + threadIdx.x; e < total; e += blockDim.x) s[e] = __ldcs(src + e);
+}
+
+// ---------------------------------------------------------------- softmax --
+__global__ void __launch_bounds__(kRowThreadsNms)
+softmax_kernel(const float* __restrict__ logits, int64_t rows, int L, float* __restrict__ probs) {
+    extern __shared__ float s_rows[];
+    for (int64_t r0 = (int64_t)blockIdx.x * kRowThreadsNms; r0 < rows; r0 += (int64_t)gridDim.x * kRowThreadsNms) {
+        const int cnt = (int)min((int64_t)kRowThreadsNms, rows - r0);
+        stage_rows(logits + r0 * L, cnt * L, s_rows);
+        __syncthreads();
+        if ((int)threadIdx.x < cnt) {
+            float* z = s_rows + (size_t)threadIdx.x * L;
+            float m = z[0];
+            for (int l = 1; l < L; ++l) m = fmaxf(m, z[l]);
+            float s = 0.0f;
+            for (int l = 0; l < L; ++l) { float e = expf(fsub(z[l], m)); z[l] = e; s = fadd(s, e); }
+            for (int l = 0; l < L; ++l) z[l] = fdiv(z[l], s);
+        }
+        __syncthreads();
+        float* dst = probs + r0 * L;
+        const int total = cnt * L;
+        const int head = min(total, (int)((4 - (((uintptr_t)dst >> 2) & 3)) & 3));
+        const int nvec = (total - head) >> 2;
+        for (int e = threadIdx.x; e < head; e += blockDim.x) dst[e] = s_rows[e];
+        for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+            const float* d = s_rows + head + (i << 2);
+            __stcs(reinterpret_cast<float4*>(dst + head) + i, make_float4(d[0], d[1], d[2], d[3]));
+        }
+        for (int e = head + (nvec << 2) + threadIdx.x; e < total; e += blockDim.x) dst[e] = s_rows[e];
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------- candidate pass --
+// DECODER=true : models/decoder.py:78-83 rule (argmax==0 kills the row).
+// DECODER=false: plain combined NMS, every (anchor, class) above threshold.
+template <bool DECODER, bool FROM_LOGITS>
+__global__ void __launch_bounds__(kRowThreadsNms)
+nms_candidates_kernel(const float* __restrict__ scores, int N, int L, float score_thr, int cap,
+                      uint64_t* __restrict__ keys, int key_stride, int* __restrict__ counts) {
+    extern __shared__ float s_rows[];
+    const int b = blockIdx.y;
+    const int n0 = blockIdx.x * kRowThreadsNms;
+    const int cnt = min(kRowThreadsNms, N - n0);
+    stage_rows(scores + ((size_t)b * N + n0) * L, cnt * L, s_rows);
+    __syncthreads();
+    if ((int)threadIdx.x >= cnt) return;
+    float* p = s_rows + (size_t)threadIdx.x * L;
+    if (FROM_LOGITS) {                                   // models/header.py:88 fused in
+        float m = p[0];
+        for (int l = 1; l < L; ++l) m = fmaxf(m, p[l]);
+        float s = 0.0f;
+        for (int l = 0; l < L; ++l) { float e = expf(fsub(p[l], m)); p[l] = e; s = fadd(s, e); }
+        for (int l = 0; l < L; ++l) p[l] = fdiv(p[l], s);
+    }
+    if (DECODER) {                                       // decoder.py:78-83
+        int am = 0;
+        float best = p[0];
+        for (int l = 1; l < L; ++l)
+            if (p[l] > best) { best = p[l]; am = l; }
+        if (am == 0) return;
+    }
+    const uint32_t anchor = (uint32_t)(n0 + threadIdx.x);
+    for (int l = 0; l < L; ++l) {
+        float sc = p[l];
+        if (sc > score_thr) {                            // strict, like TensorFlow
+            int slot = atomicAdd(counts + b, 1);
+            if (slot < cap)
+                keys[(size_t)b * key_stride + slot] =
+                    ((uint64_t)l << 56) | ((uint64_t)(~order_bits(sc)) << 24) | anchor;
+        }
+    }
+}
+
+// --------------------------------------------------------- per-image pass --
+struct DecodeFetch {          // boxes decoded on demand: decoder.py:74-75
+    const float4* priors; const float4* deltas; float4 var; int N;
+    __device__ __forceinline__ float4 operator()(int b, int anchor, int /*cls*/) const;
+};
+struct DirectFetch {          // boxes given: [B,N,q,4]
+    const float4* boxes; int N; int q;
+    __device__ __forceinline__ float4 operator()(int b, int anchor, int cls) const {
+        return __ldg(boxes + ((size_t)b * N + anchor) * q + (q > 1 ? cls : 0));
+    }
+};
+
+// utils/bbox_utils.py:68-82 (same expression order as box_kernels.cu:decode_one)
+__device__ __forceinline__ float4 DecodeFetch::operator()(int b, int anchor, int) const {
+    float4 p = __ldg(priors + anchor);
+    float4 d = __ldg(deltas + (size_t)b * N + anchor);
+    d.x = fmul(d.x, var.x); d.y = fmul(d.y, var.y); d.z = fmul(d.z, var.z); d.w = fmul(d.w, var.w);
+    float pw = fsub(p.w, p.y), ph = fsub(p.z, p.x);
+    float pcx = fadd(p.y, fmul(0.5f, pw)), pcy = fadd(p.x, fmul(0.5f, ph));
+    float w = fmul(expf(d.w), pw), h = fmul(expf(d.z), ph);
+    float cx = fadd(fmul(d.y, pw), pcx), cy = fadd(fmul(d.x, ph), pcy);
+    float y1 = fsub(cy, fmul(0.5f, h)), x1 = fsub(cx, fmul(0.5f, w));
+    return make_float4(y1, x1, fadd(h, y1), fadd(w, x1));
+}
+
+// [TF-recall] IoU of TensorFlow's non_max_suppression_op.cc: corners
+// canonicalised, 0 if either area <= 0.
+__device__ __forceinline__ float nms_iou(const float4 a, const float4 b) {
+    float aymin = fminf(a.x, a.z), aymax = fmaxf(a.x, a.z), axmin = fminf(a.y, a.w), axmax = fmaxf(a.y, a.w);
+    float bymin = fminf(b.x, b.z), bymax = fmaxf(b.x, b.z), bxmin = fminf(b.y, b.w), bxmax = fmaxf(b.y, b.w);
+    float area_a = fmul(fsub(aymax, aymin), fsub(axmax, axmin));
+    float area_b = fmul(fsub(bymax, bymin), fsub(bxmax, bxmin));
+    if (area_a <= 0.0f || area_b <= 0.0f) return 0.0f;
+    float ih = fmaxf(fsub(fminf(aymax, bymax), fmaxf(aymin, bymin)), 0.0f);
+    float iw = fmaxf(fsub(fminf(axmax, bxmax), fmaxf(axmin, bxmin)), 0.0f);
+    float inter = fmul(ih, iw);
+    return fdiv(inter, fsub(fadd(area_a, area_b), inter));
+}
+
+// In-place ascending bitonic sort of a[0..P) (P a power of two) by the CTA.
+__device__ void bitonic_sort(uint64_t* a, int P) {
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    uint64_t x = a[i], y = a[ixj];
+                    bool up = (i & k) == 0;
+                    if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+__device__ __forceinline__ int pow2_ceil(int v) {
+    int p = 32;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+struct NmsParams {
+    int N, L, per_class, max_total, cap;
+    int key_stride;            // u64 slots per image in `keys` (power of two >= cap)
+    int merge_stride;          // u64 slots per image in `merge` (power of two >= L*per_class)
+    int smem_sort_slots;       // u64 slots of the shared sort buffer
+    int kept_in_smem;          // kept-box cache lives in shared memory (else workspace)
+    float iou_thr;
+    int clip;
+    int labels_first;          // output order: decoder (boxes, labels, scores) vs TF (boxes, scores, classes)
+};
+
+template <typename Fetch>
+__global__ void __launch_bounds__(kNmsThreads)
+nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t* __restrict__ merge,
+                 float4* __restrict__ kept_ws, int* __restrict__ counts,
+                 float4* __restrict__ out_boxes, float* __restrict__ out_a, float* __restrict__ out_b,
+                 int32_t* __restrict__ out_valid) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    uint64_t* s_sort = reinterpret_cast<uint64_t*>(s_raw);
+    float4* s_kept = reinterpret_cast<float4*>(s_raw + (size_t)P.smem_sort_slots * 8);
+    __shared__ int s_seg_start[257];
+    __shared__ int s_mcount;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nwarps = kNmsThreads / 32;
+    const int T = P.max_total;
+    float4* ob = out_boxes + (size_t)b * T;
+    float* oa = out_a + (size_t)b * T;
+    float* oc = out_b + (size_t)b * T;
+
+    const int raw_count = counts[b];
+    if (raw_count > P.cap) {                       // candidate list overflowed: report, emit zeros
+        for (int r = tid; r < T; r += kNmsThreads) { ob[r] = make_float4(0, 0, 0, 0); oa[r] = 0.f; oc[r] = 0.f; }
+        if (tid == 0) out_valid[b] = -1;
+        return;
+    }
+    const int M = raw_count;
+
+    // ---- 1. sort candidates: class asc, score desc, anchor asc -------------
+    const int P1 = pow2_ceil(M);
+    uint64_t* gk = keys + (size_t)b * P.key_stride;
+    uint64_t* cand = (P1 <= P.smem_sort_slots) ? s_sort : gk;
+    if (cand == s_sort) {
+        for (int i = tid; i < P1; i += kNmsThreads) s_sort[i] = (i < M) ? gk[i] : kPadKey;
+    } else {
+        for (int i = M + tid; i < P1; i += kNmsThreads) gk[i] = kPadKey;
+    }
+    for (int i = tid; i < 257; i += kNmsThreads) s_seg_start[i] = -1;
+    if (tid == 0) s_mcount = 0;
+    __syncthreads();
+    if (M > 1) bitonic_sort(cand, P1);
+
+    // ---- 2. class segments ---------------------------------------------------
+    for (int i = tid; i < M; i += kNmsThreads) {
+        int c = (int)(cand[i] >> 56);
+        if (i == 0 || (int)(cand[i - 1] >> 56) != c) s_seg_start[c] = i;
+    }
+    __syncthreads();
+
+    // ---- 3. greedy suppression, one warp per class ---------------------------
+    uint64_t* mk = merge + (size_t)b * P.merge_stride;
+    for (int c = wid; c < P.L; c += nwarps) {
+        int start = s_seg_start[c];
+        if (start < 0) continue;
+        float4* kept = P.kept_in_smem ? s_kept + (size_t)wid * P.per_class
+                                      : kept_ws + ((size_t)b * P.L + c) * P.per_class;
+        int nk = 0;
+        for (int i = start; i < M && nk < P.per_class; ++i) {
+            uint64_t key = cand[i];
+            if ((int)(key >> 56) != c) break;
+            int anchor = (int)(key & 0xFFFFFFu);
+            float4 box = fetch(b, anchor, c);
+            bool sup = false;
+            for (int j = lane; j < nk; j += 32) {
+                float4 kb = P.kept_in_smem ? kept[j] : __ldcg(kept + j);   // workspace copy: bypass L1
+                sup |= nms_iou(box, kb) > P.iou_thr;
+            }
+            sup = __any_sync(0xffffffffu, sup);
+            if (!sup) {
+                if (lane == 0) {
+                    kept[nk] = box;
+                    int slot = atomicAdd(&s_mcount, 1);
+                    uint32_t inv_score = (uint32_t)((key >> 24) & 0xFFFFFFFFu);
+                    mk[slot] = ((uint64_t)inv_score << 32) | ((uint64_t)c << 24) | (uint32_t)anchor;
+                }
+                ++nk;
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 4. merge: score desc, class asc, anchor asc; first max_total --------
+    const int K = s_mcount;
+    const int P2 = pow2_ceil(K);
+    uint64_t* ms = (P2 <= P.smem_sort_slots) ? s_sort : mk;
+    __threadfence_block();
+    if (ms == s_sort) {
+        for (int i = tid; i < P2; i += kNmsThreads) s_sort[i] = (i < K) ? mk[i] : kPadKey;
+    } else {
+        for (int i = K + tid; i < P2; i += kNmsThreads) mk[i] = kPadKey;
+    }
+    __syncthreads();
+    if (K > 1) bitonic_sort(ms, P2);
+    const int V = min(K, T);
+    for (int r = tid; r < T; r += kNmsThreads) {
+        if (r < V) {
+            uint64_t key = ms[r];
+            int anchor = (int)(key & 0xFFFFFFu);
+            int c = (int)((key >> 24) & 0xFFu);
+            float score = unorder_bits(~(uint32_t)(key >> 32));
+            float4 box = fetch(b, anchor, c);
+            if (P.clip) {
+                box.x = fminf(fmaxf(box.x, 0.f), 1.f); box.y = fminf(fmaxf(box.y, 0.f), 1.f);
+                box.z = fminf(fmaxf(box.z, 0.f), 1.f); box.w = fminf(fmaxf(box.w, 0.f), 1.f);
+            }
+            ob[r] = box;
+            if (P.labels_first) { oa[r] = (float)c; oc[r] = score; }
+            else                { oa[r] = score;    oc[r] = (float)c; }
+        } else {
+            ob[r] = make_float4(0, 0, 0, 0); oa[r] = 0.f; oc[r] = 0.f;
+        }
+    }
+    if (tid == 0) out_valid[b] = V;
+}
+
+// ------------------------------------------------------------- host helpers --
+struct NmsWs { int* counts; uint64_t* keys; uint64_t* merge; float4* kept; };
+
+static int host_pow2_ceil(int64_t v) { int64_t p = 32; while (p < v) p <<= 1; return (int)p; }
+
+static size_t nms_ws_layout(int B, int key_stride, int merge_stride, int L, int per_class, NmsWs* w, void* base) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    size_t o_c = take((size_t)B * 4);
+    size_t o_k = take((size_t)B * key_stride * 8);
+    size_t o_m = take((size_t)B * merge_stride * 8);
+    size_t o_b = take((size_t)B * L * per_class * 16);
+    if (w) {
+        char* p = static_cast<char*>(base);
+        w->counts = (int*)(p + o_c); w->keys = (uint64_t*)(p + o_k);
+        w->merge = (uint64_t*)(p + o_m); w->kept = (float4*)(p + o_b);
+    }
+    return off;
+}
+
+struct NmsPlan { NmsParams p; size_t smem; size_t ws_bytes; };
+
+static int make_plan(int B, int N, int L, int per_class, int max_total, int64_t cap64, NmsPlan* plan) {
+    if (B < 0 || N < 1 || L < 1 || L > 255 || per_class < 1 || max_total < 1 || N >= (1 << 24) || B > 65535)
+        return SSD_ERR_SHAPE;
+    if (cap64 < 1 || cap64 > (int64_t)1 << 28) return SSD_ERR_SHAPE;
+    if (per_class > N) per_class = N;               // a class can never keep more boxes than anchors
+    if ((int64_t)L * per_class > (int64_t)1 << 26) return SSD_ERR_SHAPE;
+    NmsParams& p = plan->p;
+    p.N = N; p.L = L; p.per_class = per_class; p.max_total = max_total; p.cap = (int)cap64;
+    p.key_stride = host_pow2_ceil(cap64);
+    p.merge_stride = host_pow2_ceil((int64_t)L * per_class);
+    p.smem_sort_slots = min(8192, max(p.key_stride, p.merge_stride));
+    const int nwarps_active = min(kNmsThreads / 32, L);
+    size_t kept_bytes = (size_t)(kNmsThreads / 32) * per_class * 16;
+    (void)nwarps_active;
+    size_t sort_bytes = (size_t)p.smem_sort_slots * 8;
+    p.kept_in_smem = (sort_bytes + kept_bytes <= 200 * 1024) ? 1 : 0;
+    plan->smem = sort_bytes + (p.kept_in_smem ? kept_bytes : 0);
+    plan->ws_bytes = nms_ws_layout(max(B, 1), p.key_stride, p.merge_stride, L, per_class, nullptr, nullptr);
+    return SSD_OK;
+}
+
+template <typename Fetch>
+static int run_image_pass(const NmsPlan& plan, Fetch fetch, const NmsWs& w, int B, float* d_boxes, float* d_a,
+                          float* d_b, int32_t* d_valid, cudaStream_t st) {
+    auto kern = nms_image_kernel<Fetch>;
+    if (plan.smem > 48 * 1024)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    kern<<<B, kNmsThreads, plan.smem, st>>>(plan.p, fetch, w.keys, w.merge, w.kept, w.counts,
+                                            reinterpret_cast<float4*>(d_boxes), d_a, d_b, d_valid);
+    SSD_CHECK_LAUNCH("nms_image_kernel");
+    return SSD_OK;
+}
+
+}  // namespace ssd
+
+using namespace ssd;
+
+extern "C" int ssd_softmax(const float* d_logits, int64_t rows, int L, float* d_probs, ssd_stream_t stream) {
+    SSD_REQUIRE_PTR(d_logits); SSD_REQUIRE_PTR(d_probs);
+    SSD_REQUIRE(rows >= 0 && L >= 1, SSD_ERR_SHAPE, "ssd_softmax: bad shape rows=%lld L=%d", (long long)rows, L);
+    if (rows == 0) return SSD_OK;
+    size_t smem = (size_t)kRowThreadsNms * L * sizeof(float);
+    SSD_REQUIRE(smem <= 200 * 1024, SSD_ERR_UNSUPPORTED, "ssd_softmax: L=%d too large for row staging", L);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int64_t blocks = (rows + kRowThreadsNms - 1) / kRowThreadsNms;
+    int64_t gcap = (int64_t)sm_count() * 16;
+    int grid = (int)(blocks < gcap ? blocks : gcap);
+    softmax_kernel<<<grid, kRowThreadsNms, smem, as_stream(stream)>>>(d_logits, rows, L, d_probs);
+    SSD_CHECK_LAUNCH("softmax_kernel");
+    return SSD_OK;
+}
+
+extern "C" size_t ssd_decode_nms_workspace_bytes(int B, int N, int L, int max_total_size, int max_candidates) {
+    NmsPlan plan;
+    int64_t cap = max_candidates > 0 ? max_candidates : N;
+    if (make_plan(B, N, L, max_total_size, max_total_size, cap, &plan) != SSD_OK) return 0;
+    return plan.ws_bytes;
+}
+
+extern "C" int ssd_decode_nms(const float* d_priors, const float* d_pred_deltas, const float* d_pred_labels,
+                              int B, int N, int L, const float* h_variances, int from_logits,
+                              float score_threshold, float iou_threshold, int max_total_size, int max_candidates,
+                              float* d_boxes, float* d_labels, float* d_scores, int32_t* d_valid,
+                              void* d_workspace, size_t workspace_bytes, ssd_stream_t stream) {
+    SSD_REQUIRE_PTR(d_priors); SSD_REQUIRE_PTR(d_pred_deltas); SSD_REQUIRE_PTR(d_pred_labels);
+    SSD_REQUIRE_PTR(h_variances); SSD_REQUIRE_PTR(d_boxes); SSD_REQUIRE_PTR(d_labels);
+    SSD_REQUIRE_PTR(d_scores); SSD_REQUIRE_PTR(d_valid);
+    NmsPlan plan;
+    int64_t cap = max_candidates > 0 ? max_candidates : N;
+    SSD_REQUIRE(make_plan(B, N, L, max_total_size, max_total_size, cap, &plan) == SSD_OK, SSD_ERR_SHAPE,
+                "ssd_decode_nms: bad shape B=%d N=%d L=%d max_total=%d cap=%lld", B, N, L, max_total_size,
+                (long long)cap);
+    if (B == 0) return SSD_OK;
+    SSD_REQUIRE_PTR(d_workspace);
+    SSD_REQUIRE(workspace_bytes >= plan.ws_bytes, SSD_ERR_WORKSPACE,
+                "ssd_decode_nms: workspace %zu < required %zu bytes", workspace_bytes, plan.ws_bytes);
+    plan.p.iou_thr = iou_threshold; plan.p.clip = 1; plan.p.labels_first = 1;
+    NmsWs w;
+    nms_ws_layout(B, plan.p.key_stride, plan.p.merge_stride, L, plan.p.per_class, &w, d_workspace);
+    cudaStream_t st = as_stream(stream);
+    cudaError_t e = cudaMemsetAsync(w.counts, 0, (size_t)B * 4, st);
+    if (e != cudaSuccess) return cuda_fail(e, "ssd_decode_nms: memset");
+
+    size_t smem = (size_t)kRowThreadsNms * L * sizeof(float);
+    SSD_REQUIRE(smem <= 200 * 1024, SSD_ERR_UNSUPPORTED, "ssd_decode_nms: L=%d too large", L);
+    dim3 grid(ceil_div(N, kRowThreadsNms), B);
+    auto launch = [&](auto kern) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, kRowThreadsNms, smem, st>>>(d_pred_labels, N, L, score_threshold, plan.p.cap, w.keys,
+                                                 plan.p.key_stride, w.counts);
+    };
+    if (from_logits) launch(nms_candidates_kernel<true, true>); else launch(nms_candidates_kernel<true, false>);
+    SSD_CHECK_LAUNCH("nms_candidates_kernel");
+
+    DecodeFetch fetch{reinterpret_cast<const float4*>(d_priors), reinterpret_cast<const float4*>(d_pred_deltas),
+                      make_float4(h_variances[0], h_variances[1], h_variances[2], h_variances[3]), N};
+    return run_image_pass(plan, fetch, w, B, d_boxes, d_labels, d_scores, d_valid, st);
+}
+
+extern "C" size_t ssd_combined_nms_workspace_bytes(int B, int N, int L, int max_output_size_per_class,
+                                                   int max_total_size, int max_candidates) {
+    NmsPlan plan;
+    int64_t cap = max_candidates > 0 ? max_candidates : (int64_t)N * L;
+    if (make_plan(B, N, L, max_output_size_per_class, max_total_size, cap, &plan) != SSD_OK) return 0;
+    return plan.ws_bytes;
+}
+
+extern "C" int ssd_combined_nms(const float* d_boxes, const float* d_scores, int B, int N, int q, int L,
+                                int max_output_size_per_class, int max_total_size,
+                                float iou_threshold, float score_threshold, int clip_boxes, int max_candidates,
+                                float* d_out_boxes, float* d_out_scores, float* d_out_classes, int32_t* d_valid,
+                                void* d_workspace, size_t workspace_bytes, ssd_stream_t stream) {
+    SSD_REQUIRE_PTR(d_boxes); SSD_REQUIRE_PTR(d_scores); SSD_REQUIRE_PTR(d_out_boxes);
+    SSD_REQUIRE_PTR(d_out_scores); SSD_REQUIRE_PTR(d_out_classes); SSD_REQUIRE_PTR(d_valid);
+    SSD_REQUIRE(q == 1 || q == L, SSD_ERR_SHAPE, "ssd_combined_nms: q=%d must be 1 or L=%d", q, L);
+    NmsPlan plan;
+    int64_t cap = max_candidates > 0 ? max_candidates : (int64_t)N * L;
+    SSD_REQUIRE(make_plan(B, N, L, max_output_size_per_class, max_total_size, cap, &plan) == SSD_OK, SSD_ERR_SHAPE,
+                "ssd_combined_nms: bad shape B=%d N=%d L=%d per_class=%d max_total=%d cap=%lld", B, N, L,
+                max_output_size_per_class, max_total_size, (long long)cap);
+    if (B == 0) return SSD_OK;
+    SSD_REQUIRE_PTR(d_workspace);
+    SSD_REQUIRE(workspace_bytes >= plan.ws_bytes, SSD_ERR_WORKSPACE,
+                "ssd_combined_nms: workspace %zu < required %zu bytes", workspace_bytes, plan.ws_bytes);
+    plan.p.iou_thr = iou_threshold; plan.p.clip = clip_boxes ? 1 : 0; plan.p.labels_first = 0;
+    NmsWs w;
+    nms_ws_layout(B, plan.p.key_stride, plan.p.merge_stride, L, plan.p.per_class, &w, d_workspace);
+    cudaStream_t st = as_stream(stream);
+    cudaError_t e = cudaMemsetAsync(w.counts, 0, (size_t)B * 4, st);
+    if (e != cudaSuccess) return cuda_fail(e, "ssd_combined_nms: memset");
+
+    size_t smem = (size_t)kRowThreadsNms * L * sizeof(float);
+    SSD_REQUIRE(smem <= 200 * 1024, SSD_ERR_UNSUPPORTED, "ssd_combined_nms: L=%d too large", L);
+    dim3 grid(ceil_div(N, kRowThreadsNms), B);
+    auto kern = nms_candidates_kernel<false, false>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, kRowThreadsNms, smem, st>>>(d_scores, N, L, score_threshold, plan.p.cap, w.keys,
+                                             plan.p.key_stride, w.counts);
+    SSD_CHECK_LAUNCH("nms_candidates_kernel");
+    DirectFetch fetch{reinterpret_cast<const float4*>(d_boxes), N, q};
+    return run_image_pass(plan, fetch, w, B, d_out_boxes, d_out_scores, d_out_classes, d_valid, st);
+}
