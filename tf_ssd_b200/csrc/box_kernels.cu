@@ -301,7 +301,7 @@ extern "C" int ssd_iou_map(const float* d_boxes, const float* d_gt, int B, int N
     int cap = max(1, (sm_count() * 8 + B - 1) / B);
     dim3 grid(min(per_img, cap), B);
     auto launch = [&](auto kern) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<grid, 256, smem, as_stream(stream)>>>(reinterpret_cast<const float4*>(d_boxes),
                                                      reinterpret_cast<const float4*>(d_gt), N, G,
                                                      boxes_batched, d_out);
@@ -324,7 +324,7 @@ extern "C" int ssd_match_encode(const float* d_priors, const float* d_gt_boxes, 
     if (B == 0 || N == 0) return SSD_OK;
     size_t smem = (size_t)G * 24 + kMatchThreads * sizeof(int32_t);
     SSD_REQUIRE(smem <= 160 * 1024, SSD_ERR_UNSUPPORTED, "ssd_match_encode: G=%d exceeds shared-memory staging", G);
-    if (smem > 48 * 1024)
+    if (smem > 40 * 1024)
         cudaFuncSetAttribute(match_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(ceil_div(N, kMatchThreads), B);
     float4 var = make_float4(h_variances[0], h_variances[1], h_variances[2], h_variances[3]);

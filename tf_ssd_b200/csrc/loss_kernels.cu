@@ -371,7 +371,7 @@ extern "C" int ssd_loss_fwd(const float* d_actual_deltas, const float* d_pred_de
     SSD_REQUIRE(smem1 <= 200 * 1024, SSD_ERR_UNSUPPORTED, "ssd_loss_fwd: L=%d too large for row staging", L);
     dim3 grid1(ceil_div(N, kRowThreads), B);
     auto launch1 = [&](auto kern) {
-        if (smem1 > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        if (smem1 > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         kern<<<grid1, kRowThreads, smem1, st>>>(
             do_loc ? reinterpret_cast<const float4*>(d_actual_deltas) : nullptr,
             reinterpret_cast<const float4*>(d_pred_deltas),
@@ -383,7 +383,7 @@ extern "C" int ssd_loss_fwd(const float* d_actual_deltas, const float* d_pred_de
     size_t smem2 = do_conf ? (size_t)N * sizeof(uint32_t) : 0;
     SSD_REQUIRE(smem2 <= 200 * 1024, SSD_ERR_UNSUPPORTED,
                 "ssd_loss_fwd: N=%d anchors exceed the per-image shared-memory select (max 51200)", N);
-    if (smem2 > 48 * 1024)
+    if (smem2 > 40 * 1024)
         cudaFuncSetAttribute(loss_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     loss_select_kernel<<<B, kSelThreads, smem2, st>>>(N, neg_pos_ratio, loc_loss_alpha, do_loc, do_conf, w,
                                                       d_loc_loss, d_conf_loss);
@@ -411,7 +411,7 @@ extern "C" int ssd_loss_bwd(const float* d_actual_deltas, const float* d_pred_de
     loss_ws_layout(B, N, &w, const_cast<void*>(d_workspace));
     size_t smem = do_conf ? (size_t)2 * kRowThreads * L * sizeof(float) : 0;
     SSD_REQUIRE(smem <= 200 * 1024, SSD_ERR_UNSUPPORTED, "ssd_loss_bwd: L=%d too large for row staging", L);
-    if (smem > 48 * 1024)
+    if (smem > 40 * 1024)
         cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(ceil_div(N, kRowThreads), B);
     loss_bwd_kernel<<<grid, kRowThreads, smem, as_stream(stream)>>>(

@@ -353,7 +353,7 @@ template <typename Fetch>
 static int run_image_pass(const NmsPlan& plan, Fetch fetch, const NmsWs& w, int B, float* d_boxes, float* d_a,
                           float* d_b, int32_t* d_valid, cudaStream_t st) {
     auto kern = nms_image_kernel<Fetch>;
-    if (plan.smem > 48 * 1024)
+    if (plan.smem > 40 * 1024)
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     kern<<<B, kNmsThreads, plan.smem, st>>>(plan.p, fetch, w.keys, w.merge, w.kept, w.counts,
                                             reinterpret_cast<float4*>(d_boxes), d_a, d_b, d_valid);
@@ -371,7 +371,7 @@ extern "C" int ssd_softmax(const float* d_logits, int64_t rows, int L, float* d_
     if (rows == 0) return SSD_OK;
     size_t smem = (size_t)kRowThreadsNms * L * sizeof(float);
     SSD_REQUIRE(smem <= 200 * 1024, SSD_ERR_UNSUPPORTED, "ssd_softmax: L=%d too large for row staging", L);
-    if (smem > 48 * 1024)
+    if (smem > 40 * 1024)
         cudaFuncSetAttribute(softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int64_t blocks = (rows + kRowThreadsNms - 1) / kRowThreadsNms;
     int64_t gcap = (int64_t)sm_count() * 16;
@@ -416,7 +416,7 @@ extern "C" int ssd_decode_nms(const float* d_priors, const float* d_pred_deltas,
     SSD_REQUIRE(smem <= 200 * 1024, SSD_ERR_UNSUPPORTED, "ssd_decode_nms: L=%d too large", L);
     dim3 grid(ceil_div(N, kRowThreadsNms), B);
     auto launch = [&](auto kern) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<grid, kRowThreadsNms, smem, st>>>(d_pred_labels, N, L, score_threshold, plan.p.cap, w.keys,
                                                  plan.p.key_stride, w.counts);
     };
@@ -464,7 +464,7 @@ extern "C" int ssd_combined_nms(const float* d_boxes, const float* d_scores, int
     SSD_REQUIRE(smem <= 200 * 1024, SSD_ERR_UNSUPPORTED, "ssd_combined_nms: L=%d too large", L);
     dim3 grid(ceil_div(N, kRowThreadsNms), B);
     auto kern = nms_candidates_kernel<false, false>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<grid, kRowThreadsNms, smem, st>>>(d_scores, N, L, score_threshold, plan.p.cap, w.keys,
                                              plan.p.key_stride, w.counts);
     SSD_CHECK_LAUNCH("nms_candidates_kernel");
