@@ -1,0 +1,474 @@
+#!/usr/bin/env python
+"""Benchmark of the tf-ssd hot path on B200 (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One step = one pass of the inference hot path over one synthetic VOC-shaped
+batch: SSD300-MobileNetV2, batch 32 per GPU, forward + softmax + decode + NMS
+(BASELINE.json configs[1]).  Prints ONE JSON line (rank 0).
+
+  value  images/s, whole job, inputs resident in HBM, CUDA events, max over ranks
+  e2e    the same metric through the reference-facing API
+         (get_model -> get_decoder_model -> predict) with HOST batches: pinned
+         H2D of every step's images and D2H of its detections inside the timing
+  roofline / cpu_baseline / box_kernels: see DESIGN.md
+
+``--impl reference`` times the CPU restatement of the reference (oracle/, torch
+CPU + NumPy, all host threads) on the same workload: the reference itself is
+TensorFlow 2.0 and cannot be installed in this image (no wheel, no network).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BACKBONE = "mobilenet_v2"
+BATCH = 32
+WORKLOAD = "SSD300-MobileNetV2 batch=32/GPU inference fwd+softmax+decode+NMS, 2268 anchors, 21 labels, fp16 convs / fp32 boxes"
+METRIC = "SSD300 images/sec (fwd+decode+NMS)"
+UNIT = "images/s"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "tflops_burst": float(p["bf16_tflops"]),
+                "tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def _hyper_params():
+    from tf_ssd_b200.utils import train_utils
+    hp = train_utils.get_hyper_params(BACKBONE)
+    hp["total_labels"] = 21
+    return hp
+
+
+def _calibrated_weights(model, hp, seed=1234):
+    """Random-init weights of the architecture (no checkpoints offline), with the
+    background logit bias shifted so that a detector-like number of anchors
+    (about 200 per image) passes the 0.5 score threshold and reaches NMS."""
+    from tf_ssd_b200 import synth
+    import torch
+    img = synth.make_images(4, hp["img_size"], seed=seed)
+    _, z = model.forward_logits(img)
+    torch.cuda.synchronize()
+    z = z.cpu().numpy().astype(np.float64)
+
+    def candidates(shift):
+        zz = z.copy()
+        zz[..., 0] += shift
+        zz -= zz.max(-1, keepdims=True)
+        p = np.exp(zz)
+        p /= p.sum(-1, keepdims=True)
+        return float(((p[..., 1:].max(-1) > 0.5) & (p.argmax(-1) != 0)).sum() / z.shape[0])
+
+    lo, hi = -50.0, 50.0
+    for _ in range(40):
+        mid = 0.5 * (lo + hi)
+        if candidates(mid) > 200.0:
+            lo = mid
+        else:
+            hi = mid
+    shift = 0.5 * (lo + hi)
+    w = {}
+    for i in range(1, len(hp["feature_map_shapes"]) + 1):
+        b = model.weights[f"{i}_conv_label_output/bias"].copy().reshape(-1, 21)
+        b[:, 0] += np.float32(shift)
+        w[f"{i}_conv_label_output/bias"] = b.reshape(-1)
+    model.set_weights(w)
+    return candidates(shift)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                mask = int(get(self.h))
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.02)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        med = int(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def _physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------ CPU arms --
+def _cpu_reference_step(weights, hp, priors, images):
+    """The reference's inference path restated on the CPU (oracle/): forward in
+    fp32 (torch CPU conv2d), softmax, SSDDecoder (NumPy)."""
+    from oracle import box_oracle as bo
+    from oracle import net_oracle as no
+    d, p = no.forward(BACKBONE, weights, hp, images, mode="fp32")
+    return bo.ssd_decode(priors, hp["variances"], d, p)
+
+
+def cpu_baseline(weights, hp, priors, budget_s=12.0):
+    import torch
+    from tf_ssd_b200 import synth
+    cores = torch.get_num_threads()
+    img = synth.make_images(BATCH, hp["img_size"], seed=77)
+    _cpu_reference_step(weights, hp, priors, img[:4])           # warm-up (thread pools, allocator)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        _cpu_reference_step(weights, hp, priors, img)
+        n += BATCH
+        el = time.perf_counter() - t0
+        if el > budget_s or n >= 8 * BATCH:
+            break
+    return {"value": n / el, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} images (batches of {BATCH}) through oracle/net_oracle.py fp32 forward + oracle/box_oracle.py "
+                      f"ssd_decode in {el:.1f} s; host has {os.cpu_count()} logical CPUs; restated reference, not TensorFlow"}
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement timed with all host threads (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import box_oracle as bo
+    from tf_ssd_b200 import synth
+    from tf_ssd_b200.models.engine import SSDModel
+    hp = _hyper_params()
+    model = SSDModel(BACKBONE, hp, seed=1234)          # host-side variable initialisation only (no GPU use)
+    weights = model.weights
+    priors = bo.prior_boxes(hp["feature_map_shapes"], hp["aspect_ratios"])
+    # bounded sample per step so that steps+warmup stay within minutes
+    img = synth.make_images(BATCH, hp["img_size"], seed=77)
+    t0 = time.perf_counter()
+    _cpu_reference_step(weights, hp, priors, img[:4])
+    per_img = (time.perf_counter() - t0) / 4
+    total_steps = args.steps + args.warmup
+    sample = int(max(1, min(BATCH, 150.0 / max(per_img * total_steps, 1e-9))))
+    for _ in range(args.warmup):
+        _cpu_reference_step(weights, hp, priors, img[:sample])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _cpu_reference_step(weights, hp, priors, img[:sample])
+    el = time.perf_counter() - t0
+    value = args.steps * sample / el
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "images_per_step": sample,
+                   "note": "CPU restatement of the reference (oracle/); TensorFlow 2.0 is not installable in this image"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} images per step x {args.steps} steps, {os.cpu_count()} logical CPUs"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------- GPU arm --
+def _profile_steps(dm, B, iters=5):
+    """Per-launch CUDA-event timing of every kernel of one step (eager launches
+    on the current stream; events recorded on that same stream)."""
+    import torch
+    st = dm._prepare(B, 0)
+    plan = st["plan"]
+    n = plan.n_launches
+    acc = np.zeros(n + 1)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=plan.device)
+    for it in range(iters + 1):
+        flush.zero_()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 2)]
+        evs[0].record()
+        for i in range(n):
+            plan.run(i, i + 1)
+            evs[i + 1].record()
+        st["enqueue_decode"]()
+        evs[n + 1].record()
+        torch.cuda.synchronize()
+        if it:                                          # first pass is warm-up
+            acc += np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(n + 1)])
+    return acc / iters                                  # ms per launch; last entry = decode+NMS (2 kernels)
+
+
+def _box_kernel_rooflines(peaks, hp, iters=10, warmup=3):
+    """BASELINE.json's second metric: anchor-IoU / matching / loss / decode kernels as HBM GB/s at the stress
+    shape of SURVEY.md 8(d) (B=256, N=24564, G=42: working sets far larger than L2)."""
+    import torch
+    from tf_ssd_b200 import _ffi, synth
+    from tf_ssd_b200.utils import bbox_utils, train_utils
+    hp512 = train_utils.get_hyper_params("vgg16_512")
+    hp512["total_labels"] = 21
+    priors = bbox_utils.generate_prior_boxes(hp512["feature_map_shapes"], hp512["aspect_ratios"])
+    B, N, G, L = 256, priors.shape[0], 42, 21
+    gt, lab = synth.make_ground_truth(B, padded=G, max_boxes=G, seed=5)
+    gt_d, lab_d = _ffi.to_dev(gt), _ffi.to_dev(lab, dtype=torch.int32)
+    lib = _ffi.lib()
+    dev = priors.device
+    out = {}
+
+    def timeit(fn, nbytes):
+        for _ in range(warmup):
+            fn()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for a, b in evs:
+            a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        gbs = nbytes / ms / 1e6
+        return {"ms": ms, "bytes": nbytes, "achieved_gbs": gbs, "frac": gbs / peaks["hbm_gbs"]}
+
+    iou = torch.empty((B, N, G), dtype=torch.float32, device=dev)
+    out["generate_iou_map"] = timeit(
+        lambda: _ffi.check(lib.ssd_iou_map(_ffi.ptr(priors), _ffi.ptr(gt_d), B, N, G, 0, _ffi.ptr(iou), _ffi.stream())),
+        4 * B * N * G + 16 * N + 16 * B * G)
+    del iou
+    deltas = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
+    onehot = torch.empty((B, N, L), dtype=torch.float32, device=dev)
+    var = _ffi.f32_array(hp["variances"])
+    out["match_encode"] = timeit(
+        lambda: _ffi.check(lib.ssd_match_encode(_ffi.ptr(priors), _ffi.ptr(gt_d), _ffi.ptr(lab_d), B, N, G, L, 0.5, var,
+                                                _ffi.ptr(deltas), _ffi.ptr(onehot), None, None, _ffi.stream())),
+        16 * N + 20 * B * G + B * N * (16 + 4 * L))
+    pd, logits = synth.make_head_outputs(B, N, L, seed=6)
+    pd_d, z_d = _ffi.to_dev(pd), _ffi.to_dev(logits)
+    ws = _ffi.workspace(lib.ssd_loss_workspace_bytes(B, N, L))
+    loc = torch.empty(B, dtype=torch.float32, device=dev)
+    conf = torch.empty(B, dtype=torch.float32, device=dev)
+    out["ssd_loss_fwd"] = timeit(
+        lambda: _ffi.check(lib.ssd_loss_fwd(_ffi.ptr(deltas), _ffi.ptr(pd_d), _ffi.ptr(onehot), _ffi.ptr(z_d), B, N, L, 3.0,
+                                            1.0, 1, _ffi.ptr(loc), _ffi.ptr(conf), _ffi.ptr(ws), ws.numel(), _ffi.stream())),
+        B * N * (16 + 16 + 4 * L + 4 * L) + 8 * B)
+    T = 200
+    ws2 = _ffi.workspace(lib.ssd_decode_nms_workspace_bytes(B, N, L, T, 0))
+    ob = torch.empty((B, T, 4), dtype=torch.float32, device=dev)
+    ol = torch.empty((B, T), dtype=torch.float32, device=dev)
+    os_ = torch.empty((B, T), dtype=torch.float32, device=dev)
+    ov = torch.empty((B,), dtype=torch.int32, device=dev)
+    out["decode_nms"] = timeit(
+        lambda: _ffi.check(lib.ssd_decode_nms(_ffi.ptr(priors), _ffi.ptr(pd_d), _ffi.ptr(z_d), B, N, L, var, 1, 0.5, 0.5, T,
+                                              0, _ffi.ptr(ob), _ffi.ptr(ol), _ffi.ptr(os_), _ffi.ptr(ov), _ffi.ptr(ws2),
+                                              ws2.numel(), _ffi.stream())),
+        B * N * (16 + 4 * L) + 16 * N + 24 * B * T)
+    return {"shape": {"B": B, "N": N, "G": G, "L": L}, "peak_gbs": peaks["hbm_gbs"], "kernels": out}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU restatement)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from tf_ssd_b200 import _ffi, synth
+    from tf_ssd_b200.models import ssd_mobilenet_v2
+    from tf_ssd_b200.models.decoder import get_decoder_model
+    from tf_ssd_b200.utils import bbox_utils
+    _ffi.check_device()
+    peaks = _peaks()
+    hp = _hyper_params()
+    model = ssd_mobilenet_v2.get_model(hp, seed=1234)
+    cand = _calibrated_weights(model, hp)
+    priors = bbox_utils.generate_prior_boxes(hp["feature_map_shapes"], hp["aspect_ratios"])
+    dm = get_decoder_model(model, priors, hp)
+    B, K, W = BATCH, args.steps, max(args.warmup, 3)
+    S = hp["img_size"]
+
+    # distinct synthetic batches per rank (inference shards are independent: no data-path collective)
+    host_batches = [torch.from_numpy(synth.make_images(B, S, seed=1000 + 17 * rank + i)).pin_memory() for i in range(4)]
+    st = dm._prepare(B, 0)
+    plan = st["plan"]
+    st["enqueue_decode"] = lambda: _decode_only(dm, st, B)
+    plan.image.copy_(host_batches[0], non_blocking=False)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=plan.device)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") -------------------------------
+    for _ in range(W):
+        dm.run_resident(B, 0)
+    barrier()
+    sampler = ClockSampler(_physical_gpu_index(local_rank))
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for a, b in evs:
+        flush.zero_()                       # L2 flush between timed steps, outside the event pair
+        a.record()
+        dm.run_resident(B, 0)
+        b.record()
+    barrier()
+    clocks = sampler.finish()
+    dev_ms = float(sum(a.elapsed_time(b) for a, b in evs))
+    valid = st["valid"].cpu().numpy()
+
+    # ---- end-to-end through the public API ("e2e") --------------------------
+    def host_iter(n):
+        for i in range(n):
+            yield host_batches[i % len(host_batches)]
+    dm.predict(host_iter(W), steps=W)
+    barrier()
+    t0 = time.perf_counter()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = dm.predict(host_iter(K), steps=K)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = max(float(e0.elapsed_time(e1)), 1e3 * (time.perf_counter() - t0))
+    assert res[0].shape == (K * B, 200, 4)
+    barrier()
+
+    times = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(times[0]), float(times[1])
+
+    if rank == 0:
+        total_images = world * B * K
+        value = total_images / (dev_ms / 1e3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"independent inference shards x{world}",
+                       "weights": "random-init, BN folded, background bias calibrated",
+                       "nms_candidates_per_image": round(cand, 1), "valid_detections_mean": float(valid.mean()),
+                       "l2": "256 MiB memset between timed steps (outside the event pairs)",
+                       "cuda_graph": True, "peaks": peaks["source"]},
+            "clocks": clocks,
+            "e2e": {"value": total_images / (e2e_ms / 1e3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(B * S * S * 3 * 4), "d2h_bytes_per_step": int(B * 200 * 6 * 4),
+                    "api": "get_decoder_model(...).predict(host batches): pinned H2D + graph replay + D2H, 2 slots in flight"},
+            "gpu_launches": K * dm.launches_per_batch(B),
+        }
+        if world == 1:
+            per = _profile_steps(dm, B)
+            steps = plan.steps
+            groups = {}
+            for s, ms in zip(steps, per[:-1]):
+                g = groups.setdefault(s.kind, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+                g["ms"] += ms; g["flops"] += s.flops; g["bytes"] += s.bytes; g["launches"] += 1
+            groups["decode_nms"] = {"ms": float(per[-1]), "flops": 0.0, "launches": 2,
+                                    "bytes": float(B * model.n_anchors * (16 + 4 * 21) + 16 * model.n_anchors + 24 * B * 200)}
+            total = sum(g["ms"] for g in groups.values())
+            top = max(groups, key=lambda k: groups[k]["ms"])
+            g = groups[top]
+            t_flop = g["flops"] / (peaks["tflops_burst"] * 1e12)
+            t_mem = g["bytes"] / (peaks["hbm_gbs"] * 1e9)
+            if t_flop > t_mem:
+                ach = g["flops"] / (g["ms"] * 1e-3) / 1e12
+                roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
+                        "frac": ach / peaks["tflops_burst"]}
+            else:
+                ach = g["bytes"] / (g["ms"] * 1e-3) / 1e9
+                roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]}
+            roof.update({"traffic": None, "kernel": {"conv": "conv_igemm_kernel (all Conv2D launches of the step)",
+                                                     "dw": "depthwise3x3_kernel", "decode_nms": "nms_candidates+nms_image"}.get(top, top),
+                         "launches_per_step": g["launches"], "ms_per_step": g["ms"], "share_of_step": g["ms"] / total,
+                         "algorithmic_bytes_per_step": g["bytes"], "flops_per_step": g["flops"], "peak_source": peaks["source"],
+                         "by_kind_ms": {k: round(v["ms"], 4) for k, v in groups.items()}})
+            line["roofline"] = roof
+            worst = sorted(zip(per[:-1], steps), key=lambda t: -t[0])[:8]
+            line["top_launches"] = [{"name": s.name, "kind": s.kind, "ms": round(float(ms), 4),
+                                     "tflops": round(s.flops / (ms * 1e-3) / 1e12, 2), "gbs": round(s.bytes / (ms * 1e-3) / 1e9, 1)}
+                                    for ms, s in worst]
+            if not args.skip_box:
+                line["box_kernels"] = _box_kernel_rooflines(peaks, hp)
+            if not args.skip_cpu:
+                from oracle import box_oracle as bo
+                line["cpu_baseline"] = cpu_baseline(model.weights, hp, bo.prior_boxes(hp["feature_map_shapes"], hp["aspect_ratios"]))
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _decode_only(dm, st, B):
+    from tf_ssd_b200 import _ffi
+    dec, lib, plan, m = dm.decoder, _ffi.lib(), st["plan"], dm.base_model
+    _ffi.check(lib.ssd_decode_nms(_ffi.ptr(dec._priors()), _ffi.ptr(plan.deltas), _ffi.ptr(plan.logits), B, m.n_anchors,
+                                  m.total_labels, _ffi.f32_array(dec.variances), 1, dec.score_threshold, dec.iou_threshold,
+                                  dec.max_total_size, 0, _ffi.ptr(st["boxes"]), _ffi.ptr(st["labels"]), _ffi.ptr(st["scores"]),
+                                  _ffi.ptr(st["valid"]), _ffi.ptr(st["ws"]), st["ws"].numel(), _ffi.stream()), "ssd_decode_nms")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--skip-box", action="store_true", help="omit the box-kernel stress rooflines")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -160,6 +160,72 @@ int ssd_combined_nms(const float* d_boxes, const float* d_scores, int B, int N, 
                      float* d_out_boxes, float* d_out_scores, float* d_out_classes, int32_t* d_valid,
                      void* d_workspace, size_t workspace_bytes, ssd_stream_t stream);
 
+/* ===================================================== network forward ==== */
+/* The SSD forward pass (models/ssd_mobilenet_v2.py:15-47, models/ssd_vgg16.py:
+ * 66-121, models/header.py:54-90) as NHWC fp16 tensors with fp32 accumulation.
+ * The reference builds these layers from Keras (Conv2D / DepthwiseConv2D /
+ * BatchNormalization / ReLU / MaxPool2D / L2Normalization); each entry below
+ * replaces the Keras layer call sites cited.  BatchNormalization is folded
+ * into the preceding kernel+bias by the host code (inference). */
+
+#define SSD_ACT_NONE  0
+#define SSD_ACT_RELU  1
+#define SSD_ACT_RELU6 2
+
+/* One convolution (Keras Conv2D call sites: models/ssd_vgg16.py:80-113,
+ * models/ssd_mobilenet_v2.py:31-41, models/header.py:71-85, and the 1x1/3x3
+ * convolutions inside keras_applications MobileNetV2 at ssd_mobilenet_v2.py:25).
+ *   in      [B,H,W,Cin]   fp16 NHWC, Cin % 8 == 0
+ *   weight  [Cout,KH,KW,Cin] fp16 ("OHWI": K-major for the tensor cores)
+ *   bias    [Cout] fp32 (may be NULL)
+ *   residual: optional fp16 tensor added AFTER bias+activation, addressed like
+ *             output segment 0 (MobileNetV2 block_i_add).
+ * Output pixel (b,oy,ox) = row m = (b*Ho+oy)*Wo+ox.  Channels [0,split) go to
+ * out0, [split,Cout) to out1 (split == Cout: single output).  Element address
+ * of segment s: out_s + b*img_stride_s + (oy*Wo+ox)*pix_stride_s + (c - begin_s)
+ * in elements -- this is how the head convolutions write straight into the
+ * concatenated [B,N_anchors,L] / [B,N_anchors,4] tensors (header.py:46-51).
+ * out_f32: 0 -> fp16 outputs, 1 -> fp32 outputs. */
+typedef struct ssd_conv_desc {
+    const void*  in;
+    const void*  weight;
+    const float* bias;
+    const void*  residual;
+    void*        out0;
+    void*        out1;
+    int32_t B, H, W, Cin;
+    int32_t Ho, Wo, Cout;
+    int32_t KH, KW, stride, dilation, pad_top, pad_left;
+    int32_t act;
+    int32_t out_f32;
+    int32_t split;
+    int32_t reserved;
+    int64_t img_stride0, pix_stride0;
+    int64_t img_stride1, pix_stride1;
+} ssd_conv_desc;
+
+int ssd_conv2d(const ssd_conv_desc* h_desc, ssd_stream_t stream);
+
+/* Keras DepthwiseConv2D 3x3 (+ folded BN + ReLU6) inside MobileNetV2
+ * (ssd_mobilenet_v2.py:25).  in [B,H,W,C] fp16, weight [3,3,C] fp16,
+ * bias [C] fp32, out [B,Ho,Wo,C] fp16; C % 8 == 0. */
+int ssd_depthwise3x3(const void* d_in, const void* d_weight, const float* d_bias, void* d_out,
+                     int B, int H, int W, int C, int Ho, int Wo, int stride, int pad_top, int pad_left,
+                     int act, ssd_stream_t stream);
+
+/* fp32 NHWC image [B,H,W,3] (utils/data_utils.py:36 convert_image_dtype output)
+ * -> fp16 NHWC with the channel dimension zero-padded to 8. */
+int ssd_image_to_f16c8(const float* d_img, void* d_out, int64_t n_pixels, ssd_stream_t stream);
+
+/* Keras MaxPool2D(padding="same") (models/ssd_vgg16.py:82-101): window k,
+ * stride s, TensorFlow SAME padding (odd pixel after, -inf padded). fp16 NHWC. */
+int ssd_maxpool(const void* d_in, void* d_out, int B, int H, int W, int C, int Ho, int Wo,
+                int k, int stride, int pad_top, int pad_left, ssd_stream_t stream);
+
+/* L2Normalization.call (models/ssd_vgg16.py:63): x * rsqrt(max(sum_c x^2, 1e-12))
+ * * scale[c].  in/out [rows,C] fp16, scale [C] fp32. */
+int ssd_l2norm(const void* d_in, const float* d_scale, void* d_out, int64_t rows, int C, ssd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,304 @@
+"""Parity of the forward engine (C-ABI conv / depthwise / pool / l2norm kernels and the
+two SSD graphs) against the torch-CPU oracle.
+
+Tolerances: the product computes with fp16 storage and fp32 accumulation
+(BASELINE.json config 2: "fp16 convs / fp32 boxes").  Against the oracle's
+``fp16sim`` mode (same roundings, different summation order) the bound is
+5e-3 of the tensor's max magnitude; against the reference's fp32 arithmetic it
+is 3e-2 of the max magnitude (fp16 storage error through up to 54 layers)."""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import box_oracle as bo
+from oracle import net_oracle as no
+
+pytestmark = pytest.mark.gpu
+
+TOL_SIM = 5e-3
+TOL_FP32 = 3e-2
+
+
+def _randomise(model, seed):
+    """Non-trivial BatchNorm statistics, biases and L2-norm scales (the initialiser leaves them at identity)."""
+    rng = np.random.default_rng(seed)
+    w = {}
+    for k, v in model.weights.items():
+        if k.endswith("/bias") or k.endswith("/beta") or k.endswith("/moving_mean"):
+            w[k] = rng.normal(0, 0.1, v.shape).astype(np.float32)
+        elif k.endswith("/gamma") or k.endswith("/moving_variance"):
+            w[k] = rng.uniform(0.5, 1.5, v.shape).astype(np.float32)
+        elif k.endswith("/scale"):
+            w[k] = rng.uniform(10, 30, v.shape).astype(np.float32)
+    model.set_weights(w)
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-6))
+
+
+def _conv_case(B, H, W, Cin, Cout, k, stride, dil, pads, act, residual, seed, split=None, out_f32=False):
+    from tf_ssd_b200 import _ffi
+    from tf_ssd_b200._ffi_conv import ConvDesc
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, H, W, Cin)).astype(np.float16)
+    w = (rng.standard_normal((Cout, k, k, Cin)) / np.sqrt(k * k * Cin)).astype(np.float16)
+    bias = rng.standard_normal(Cout).astype(np.float32)
+    (pt, pb), (pl, pr) = pads
+    Ho = (H + pt + pb - ((k - 1) * dil + 1)) // stride + 1
+    Wo = (W + pl + pr - ((k - 1) * dil + 1)) // stride + 1
+    res = rng.standard_normal((B, Ho, Wo, Cout)).astype(np.float16) if residual else None
+    # reference: torch CPU fp32 conv on the fp16-rounded operands
+    xt = torch.from_numpy(x.astype(np.float32)).permute(0, 3, 1, 2)
+    wt = torch.from_numpy(w.astype(np.float32)).permute(0, 3, 1, 2)
+    y = F.conv2d(F.pad(xt, (pl, pr, pt, pb)), wt, torch.from_numpy(bias), stride=stride, dilation=dil)
+    if act == 1:
+        y = torch.relu(y)
+    elif act == 2:
+        y = torch.clamp(y, 0, 6)
+    y = y.permute(0, 2, 3, 1).numpy()
+    if res is not None:
+        y = y + res.astype(np.float32)
+
+    dev = torch.device("cuda")
+    xd, wd, bd = torch.from_numpy(x).to(dev), torch.from_numpy(w).to(dev), torch.from_numpy(bias).to(dev)
+    rd = torch.from_numpy(res).to(dev) if res is not None else None
+    odt = torch.float32 if out_f32 else torch.float16
+    sp = Cout if split is None else split
+    out0 = torch.zeros((B, Ho, Wo, sp), dtype=odt, device=dev)
+    out1 = torch.zeros((B, Ho, Wo, max(Cout - sp, 1)), dtype=odt, device=dev)
+    d = ConvDesc()
+    d.inp, d.weight, d.bias = xd.data_ptr(), wd.data_ptr(), bd.data_ptr()
+    d.residual = rd.data_ptr() if rd is not None else None
+    d.out0, d.out1 = out0.data_ptr(), out1.data_ptr()
+    d.B, d.H, d.W, d.Cin, d.Ho, d.Wo, d.Cout = B, H, W, Cin, Ho, Wo, Cout
+    d.KH = d.KW = k
+    d.stride, d.dilation, d.pad_top, d.pad_left, d.act, d.out_f32, d.split = stride, dil, pt, pl, act, int(out_f32), sp
+    d.img_stride0, d.pix_stride0 = Ho * Wo * sp, sp
+    d.img_stride1, d.pix_stride1 = Ho * Wo * (Cout - sp), Cout - sp
+    _ffi.check(_ffi.lib().ssd_conv2d(C.byref(d), _ffi.stream()), "ssd_conv2d")
+    torch.cuda.synchronize()
+    got = out0.float().cpu().numpy()
+    if sp < Cout:
+        got = np.concatenate([got, out1.float().cpu().numpy()], axis=-1)
+    return got, y
+
+
+@pytest.mark.parametrize("case", [
+    # B, H, W, Cin, Cout, k, stride, dil, pads, act, residual
+    (2, 19, 19, 64, 384, 1, 1, 1, ((0, 0), (0, 0)), 2, False),      # MobileNetV2 expand
+    (2, 19, 19, 384, 64, 1, 1, 1, ((0, 0), (0, 0)), 0, True),       # project + residual add
+    (1, 150, 150, 32, 16, 1, 1, 1, ((0, 0), (0, 0)), 0, False),     # thin projection, many rows
+    (3, 10, 10, 1280, 256, 1, 1, 1, ((0, 0), (0, 0)), 1, False),    # extra1_1
+    (2, 10, 10, 256, 512, 3, 2, 1, ((0, 1), (0, 1)), 1, False),     # extra1_2, SAME stride 2 even input
+    (2, 5, 5, 128, 256, 3, 2, 1, ((1, 1), (1, 1)), 1, False),       # extra2_2, odd input
+    (1, 31, 29, 8, 32, 3, 2, 1, ((0, 1), (1, 1)), 2, False),        # stem-like, Cin padded to 8
+    (1, 19, 19, 64, 96, 3, 1, 6, ((6, 6), (6, 6)), 1, False),       # conv6-like dilation 6
+    (1, 5, 5, 128, 256, 3, 1, 1, ((0, 0), (0, 0)), 1, False),       # conv10_2 VALID
+    (2, 38, 38, 128, 128, 3, 1, 1, ((1, 1), (1, 1)), 1, False),     # VGG body
+    (1, 7, 9, 24, 40, 1, 1, 1, ((0, 0), (0, 0)), 0, False),         # ragged K (24) and N (40)
+])
+def test_conv2d_against_torch(case):
+    got, ref = _conv_case(*case, seed=hash(case) % 1000)
+    assert got.shape == ref.shape
+    assert _rel(got, ref) < 2e-3                       # fp16 output rounding only
+
+
+def test_conv2d_head_split_fp32():
+    # head-style: two fp32 segments (A*L = 84 label channels, A*4 = 16 box channels)
+    got, ref = _conv_case(2, 10, 10, 64, 100, 3, 1, 1, ((1, 1), (1, 1)), 0, False, seed=5, split=84, out_f32=True)
+    assert _rel(got, ref) < 1e-4
+
+
+def test_conv2d_rejects_bad_arguments():
+    from tf_ssd_b200 import _ffi
+    from tf_ssd_b200._ffi_conv import ConvDesc
+    d = ConvDesc()
+    assert _ffi.lib().ssd_conv2d(C.byref(d), None) == -1            # SSD_ERR_NULL
+    assert b"NULL" in _ffi.lib().ssd_last_error()
+
+
+@pytest.mark.parametrize("stride,H,W,C", [(1, 19, 19, 384), (2, 38, 38, 192), (2, 75, 75, 144), (1, 7, 5, 8), (2, 150, 150, 96)])
+def test_depthwise_against_torch(stride, H, W, C):
+    from tf_ssd_b200 import _ffi
+    from tf_ssd_b200.models.engine import _out_size, _resolve_pads
+    rng = np.random.default_rng(C + H)
+    B = 2
+    x = rng.standard_normal((B, H, W, C)).astype(np.float16)
+    w = (rng.standard_normal((3, 3, C)) / 3).astype(np.float16)
+    bias = rng.standard_normal(C).astype(np.float32)
+    ph, pw = _resolve_pads(H, W, 3, stride, 1, "same" if stride == 1 else "correct")
+    assert (ph, pw) == ((no.same_pad(H, 3, 1), no.same_pad(W, 3, 1)) if stride == 1 else (no.correct_pad(H), no.correct_pad(W)))
+    Ho, Wo = _out_size(H, 3, stride, 1, ph), _out_size(W, 3, stride, 1, pw)
+    xt = torch.from_numpy(x.astype(np.float32)).permute(0, 3, 1, 2)
+    wt = torch.from_numpy(w.astype(np.float32)).permute(2, 0, 1).unsqueeze(1)
+    y = F.conv2d(F.pad(xt, (pw[0], pw[1], ph[0], ph[1])), wt, torch.from_numpy(bias), stride=stride, groups=C)
+    y = torch.clamp(y, 0, 6).permute(0, 2, 3, 1).numpy()
+    dev = torch.device("cuda")
+    xd, wd, bd = torch.from_numpy(x).to(dev), torch.from_numpy(w).to(dev), torch.from_numpy(bias).to(dev)
+    out = torch.zeros((B, Ho, Wo, C), dtype=torch.float16, device=dev)
+    _ffi.check(_ffi.lib().ssd_depthwise3x3(_ffi.ptr(xd), _ffi.ptr(wd), _ffi.ptr(bd), _ffi.ptr(out), B, H, W, C, Ho, Wo,
+                                           stride, ph[0], pw[0], 2, _ffi.stream()), "ssd_depthwise3x3")
+    assert _rel(out.float().cpu().numpy(), y) < 2e-3
+
+
+@pytest.mark.parametrize("k,s,H", [(2, 2, 75), (2, 2, 38), (3, 1, 19)])
+def test_maxpool_and_l2norm(k, s, H):
+    from tf_ssd_b200 import _ffi
+    rng = np.random.default_rng(H)
+    B, C_ = 2, 64
+    x = rng.standard_normal((B, H, H, C_)).astype(np.float16)
+    pads = no.same_pad(H, k, s)
+    Ho = -(-H // s)
+    xt = torch.from_numpy(x.astype(np.float32)).permute(0, 3, 1, 2)
+    y = F.max_pool2d(F.pad(xt, (pads[0], pads[1], pads[0], pads[1]), value=float("-inf")), k, s).permute(0, 2, 3, 1).numpy()
+    dev = torch.device("cuda")
+    xd = torch.from_numpy(x).to(dev)
+    out = torch.zeros((B, Ho, Ho, C_), dtype=torch.float16, device=dev)
+    _ffi.check(_ffi.lib().ssd_maxpool(_ffi.ptr(xd), _ffi.ptr(out), B, H, H, C_, Ho, Ho, k, s, pads[0], pads[0], _ffi.stream()))
+    assert np.array_equal(out.float().cpu().numpy(), y)             # max is exact
+
+    scale = rng.uniform(10, 30, C_).astype(np.float32)
+    xf = x.astype(np.float32)
+    ref = xf / np.sqrt(np.maximum((xf * xf).sum(-1, keepdims=True), 1e-12)) * scale
+    sd = torch.from_numpy(scale).to(dev)
+    out2 = torch.zeros_like(xd)
+    _ffi.check(_ffi.lib().ssd_l2norm(_ffi.ptr(xd), _ffi.ptr(sd), _ffi.ptr(out2), B * H * H, C_, _ffi.stream()))
+    assert _rel(out2.float().cpu().numpy(), ref) < 2e-3
+
+
+def _model(backbone, seed=3):
+    from tf_ssd_b200.models import ssd_mobilenet_v2, ssd_vgg16
+    from tf_ssd_b200.utils import train_utils
+    hp = train_utils.get_hyper_params(backbone)
+    hp["total_labels"] = 21
+    mod = ssd_mobilenet_v2 if backbone == "mobilenet_v2" else ssd_vgg16
+    m = mod.get_model(hp, seed=seed)
+    _randomise(m, seed + 1)
+    return m, hp
+
+
+def _rms(a, b):
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-12))
+
+
+@pytest.mark.parametrize("backbone,B", [("mobilenet_v2", 2), ("vgg16", 1), ("vgg16_512", 1)])
+def test_every_layer_in_situ(backbone, B):
+    """Each launch of the plan is checked against torch-CPU on the launch's ACTUAL device
+    input buffer (read back after the forward), with the geometry the graph gave it.  This
+    pins every layer's padding / stride / dilation / fusion independently of how rounding
+    differences propagate through the (random-weight, error-amplifying) network."""
+    from tf_ssd_b200 import synth
+    m, hp = _model(backbone)
+    img = synth.make_images(B, hp["img_size"], seed=9)
+    m.forward_logits(img)
+    torch.cuda.synchronize()
+    plan = m.plan(B)
+    f32 = lambda t: t.float().cpu()
+    checked = 0
+    for s in plan.steps:
+        mt = s.meta
+        if s.kind == "conv":
+            x = f32(mt["x"]).permute(0, 3, 1, 2)
+            w = f32(mt["w"]).permute(0, 3, 1, 2)
+            (pt, pb), (pl, pr) = mt["ph"], mt["pw"]
+            y = F.conv2d(F.pad(x, (pl, pr, pt, pb)), w, f32(mt["bias"]), stride=mt["stride"], dilation=mt["dilation"])
+            y = torch.relu(y) if mt["act"] == 1 else torch.clamp(y, 0, 6) if mt["act"] == 2 else y
+            y = y.permute(0, 2, 3, 1)
+            if mt["res"] is not None:
+                y = y + f32(mt["res"])
+            y = y.numpy()
+            assert y.shape[1:3] == (mt["Ho"], mt["Wo"])
+            if "head" in mt:
+                off, cnt, A = mt["head"]
+                lab = plan.logits[:, off:off + cnt].cpu().numpy().reshape(B, mt["Ho"], mt["Wo"], A * 21)
+                box = plan.deltas[:, off:off + cnt].cpu().numpy().reshape(B, mt["Ho"], mt["Wo"], A * 4)
+                got, tol = np.concatenate([lab, box], -1), 2e-4
+            else:
+                got, tol = f32(mt["out0"]).numpy(), 2e-3
+            assert _rel(got, y) < tol, f"{s.name}: {_rel(got, y)}"
+        elif s.kind == "dw":
+            x = f32(mt["x"]).permute(0, 3, 1, 2)
+            w = f32(mt["w"]).permute(2, 0, 1).unsqueeze(1)
+            (pt, pb), (pl, pr) = mt["ph"], mt["pw"]
+            y = F.conv2d(F.pad(x, (pl, pr, pt, pb)), w, f32(mt["bias"]), stride=mt["stride"], groups=w.shape[0])
+            y = torch.clamp(y, 0, 6).permute(0, 2, 3, 1).numpy()
+            assert _rel(f32(mt["out"]).numpy(), y) < 2e-3, s.name
+        elif s.kind == "pool":
+            x = f32(mt["x"]).permute(0, 3, 1, 2)
+            (pt, pb), (pl, pr) = mt["ph"], mt["pw"]
+            y = F.max_pool2d(F.pad(x, (pl, pr, pt, pb), value=float("-inf")), mt["k"], mt["stride"]).permute(0, 2, 3, 1)
+            assert np.array_equal(f32(mt["out"]).numpy(), y.numpy()), s.name
+        elif s.kind == "l2norm":
+            x = f32(mt["x"]).numpy()
+            y = x / np.sqrt(np.maximum((x * x).sum(-1, keepdims=True), 1e-12)) * f32(mt["scale"]).numpy()
+            assert _rel(f32(mt["out"]).numpy(), y) < 2e-3, s.name
+        else:
+            assert s.kind == "cast"
+            continue
+        checked += 1
+    assert checked == plan.n_launches - 1
+
+
+@pytest.mark.parametrize("backbone,B", [("mobilenet_v2", 2), ("vgg16", 1)])
+def test_forward_parity(backbone, B):
+    """Whole-graph parity.  The random-weight networks amplify rounding differences, so the
+    yardstick is the oracle's own fp16-storage error: our distance to the reference's fp32
+    arithmetic must not exceed 1.5x the distance of the oracle's fp16sim mode to it."""
+    from tf_ssd_b200 import synth
+    m, hp = _model(backbone)
+    img = synth.make_images(B, hp["img_size"], seed=9)
+    d, z = m.forward_logits(img)
+    torch.cuda.synchronize()
+    d, z = d.cpu().numpy(), z.cpu().numpy()
+    assert d.shape == (B, m.n_anchors, 4) and z.shape == (B, m.n_anchors, 21)
+    (sd, sz), staps = no.forward(backbone, m.weights, hp, img, mode="fp16sim", return_logits=True, return_taps=True)
+    (fd, fz), ftaps = no.forward(backbone, m.weights, hp, img, mode="fp32", return_logits=True, return_taps=True)
+    taps = [t.t.float().cpu().numpy() for t in m.plan(B).taps]
+    for i, (a, s_, f_) in enumerate(zip(taps, staps, ftaps)):
+        assert a.shape == f_.shape, f"tap {i}"
+        inherent = _rms(s_, f_)
+        assert _rms(a, f_) < 1.5 * inherent + 1e-3, f"tap {i}: {_rms(a, f_)} vs inherent {inherent}"
+        assert _rms(a, s_) < 1.5 * inherent + 1e-3, f"tap {i}: {_rms(a, s_)} vs inherent {inherent}"
+    for a, s_, f_ in ((d, sd, fd), (z, sz, fz)):
+        inherent = _rms(s_, f_)
+        assert _rms(a, f_) < 1.5 * inherent + 1e-3 and _rms(a, s_) < 1.5 * inherent + 1e-3
+    # public signature: model(x) -> (deltas, softmax probabilities)
+    pd, pp = m(img)
+    assert np.allclose(pp.cpu().numpy(), bo.softmax(z), rtol=1e-5, atol=1e-7)
+    assert np.array_equal(pd.cpu().numpy(), d)
+
+
+def test_decoder_model_end_to_end():
+    """predictor.py:80-97 flow: get_model -> get_decoder_model -> predict; the fused graph
+    (forward + softmax + decode + NMS) must equal the oracle's decoder run on the
+    model's own head outputs, selection order included."""
+    from tf_ssd_b200 import synth
+    from tf_ssd_b200.models.decoder import get_decoder_model
+    from tf_ssd_b200.utils import bbox_utils
+    m, hp = _model("mobilenet_v2", seed=11)
+    # make the random-weight head confident somewhere so NMS has work: boost the label biases
+    w = {}
+    rng = np.random.default_rng(0)
+    for i in range(1, 7):
+        b = m.weights[f"{i}_conv_label_output/bias"].copy().reshape(-1, 21)
+        b += rng.normal(0, 2.5, b.shape).astype(np.float32)
+        w[f"{i}_conv_label_output/bias"] = b.reshape(-1)
+    m.set_weights(w)
+    priors = bbox_utils.generate_prior_boxes(hp["feature_map_shapes"], hp["aspect_ratios"])
+    dm = get_decoder_model(m, priors, hp)
+    B = 4
+    batches = [synth.make_images(B, 300, seed=s) for s in (1, 2)]
+    boxes, labels, scores = dm.predict(batches, steps=2)
+    assert boxes.shape == (2 * B, 200, 4) and labels.shape == (2 * B, 200) and scores.shape == (2 * B, 200)
+    for i, img in enumerate(batches):
+        d, z = m.forward_logits(img)
+        rb, rl, rs = bo.ssd_decode(priors.cpu().numpy(), hp["variances"], d.cpu().numpy(), bo.softmax(z.cpu().numpy()))
+        sl = slice(i * B, (i + 1) * B)
+        assert (rs > 0).sum() > 0
+        assert np.array_equal(labels[sl], rl) and np.allclose(scores[sl], rs, rtol=1e-6, atol=0)
+        assert np.allclose(boxes[sl], rb, rtol=1e-5, atol=1e-6)

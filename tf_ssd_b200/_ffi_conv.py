@@ -1,0 +1,32 @@
+"""ctypes declarations of the network-forward entry points of ``include/ssd_b200.h``
+(``ssd_conv2d`` and the HBM-bound layer kernels)."""
+
+from __future__ import annotations
+
+import ctypes as C
+
+i, f, vp, i64 = C.c_int, C.c_float, C.c_void_p, C.c_int64
+
+ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
+
+
+class ConvDesc(C.Structure):
+    """``struct ssd_conv_desc`` (include/ssd_b200.h)."""
+    _fields_ = [
+        ("inp", vp), ("weight", vp), ("bias", vp), ("residual", vp), ("out0", vp), ("out1", vp),
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32),
+        ("Ho", C.c_int32), ("Wo", C.c_int32), ("Cout", C.c_int32),
+        ("KH", C.c_int32), ("KW", C.c_int32), ("stride", C.c_int32), ("dilation", C.c_int32),
+        ("pad_top", C.c_int32), ("pad_left", C.c_int32),
+        ("act", C.c_int32), ("out_f32", C.c_int32), ("split", C.c_int32), ("reserved", C.c_int32),
+        ("img_stride0", i64), ("pix_stride0", i64), ("img_stride1", i64), ("pix_stride1", i64),
+    ]
+
+
+SIGNATURES = {
+    "ssd_conv2d": (i, [C.POINTER(ConvDesc), vp]),
+    "ssd_depthwise3x3": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),
+    "ssd_image_to_f16c8": (i, [vp, vp, i64, vp]),
+    "ssd_maxpool": (i, [vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),
+    "ssd_l2norm": (i, [vp, vp, vp, i64, i, vp]),
+}

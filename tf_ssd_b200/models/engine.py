@@ -1,0 +1,675 @@
+"""Forward engine behind ``get_model`` (models/ssd_mobilenet_v2.py:15-47,
+models/ssd_vgg16.py:66-121, models/header.py:54-90 of the reference).
+
+The reference builds Keras graphs; here each graph is written once against a
+small "net" interface and interpreted twice:
+
+* ``_ParamTracer``  walks it to enumerate the trainable variables (Keras layer
+  names, Keras layouts) and to initialise them;
+* ``_PlanBuilder``  walks it for a concrete batch size and emits a flat list
+  of C-ABI kernel launches (``ssd_conv2d``, ``ssd_depthwise3x3``, ...) over
+  preallocated NHWC fp16 device buffers.  A plan allocates nothing and never
+  synchronises when it runs, so it is captured once into a CUDA graph and
+  replayed.
+
+torch is used for device buffers, streams and graph capture only -- no
+``torch.nn`` and no torch arithmetic on the activation path.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from tf_ssd_b200 import _ffi
+from tf_ssd_b200._ffi_conv import ACT_NONE, ACT_RELU, ACT_RELU6, ConvDesc
+
+BN_EPS = 1e-3        # keras_applications.mobilenet_v2: BatchNormalization(epsilon=1e-3, momentum=0.999)
+
+# (expansion, out channels, stride) of inverted-residual blocks 0..16, alpha = 1.0
+MNV2_BLOCKS: List[Tuple[int, int, int]] = [
+    (1, 16, 1),
+    (6, 24, 2), (6, 24, 1),
+    (6, 32, 2), (6, 32, 1), (6, 32, 1),
+    (6, 64, 2), (6, 64, 1), (6, 64, 1), (6, 64, 1),
+    (6, 96, 1), (6, 96, 1), (6, 96, 1),
+    (6, 160, 2), (6, 160, 1), (6, 160, 1),
+    (6, 320, 1),
+]
+
+
+# ------------------------------------------------------------------ geometry --
+def same_pad(size: int, k: int, s: int, d: int = 1) -> Tuple[int, int]:
+    """TensorFlow ``padding="same"``: total padding split with the odd pixel AFTER."""
+    out = -(-size // s)
+    total = max((out - 1) * s + (k - 1) * d + 1 - size, 0)
+    return total // 2, total - total // 2
+
+
+def correct_pad(size: int, k: int = 3) -> Tuple[int, int]:
+    """keras_applications ``correct_pad`` (ZeroPadding2D before the stride-2 VALID convs)."""
+    return k // 2 - (1 - size % 2), k // 2
+
+
+def _out_size(size: int, k: int, s: int, d: int, pads: Tuple[int, int]) -> int:
+    return (size + pads[0] + pads[1] - ((k - 1) * d + 1)) // s + 1
+
+
+def _resolve_pads(H: int, W: int, k: int, s: int, d: int, pad: str):
+    if pad == "same":
+        return same_pad(H, k, s, d), same_pad(W, k, s, d)
+    if pad == "correct":
+        return correct_pad(H, k), correct_pad(W, k)
+    if pad == "valid":
+        return (0, 0), (0, 0)
+    raise ValueError(f"unknown padding {pad!r}")
+
+
+# ---------------------------------------------------------------- the graphs --
+@dataclass
+class Act:
+    """An NHWC activation: device buffer (None while tracing) + logical shape."""
+    t: Optional[torch.Tensor]
+    H: int
+    W: int
+    C: int
+
+
+def mobilenet_v2_graph(n: Any, x: Act, hp: Dict[str, Any]) -> List[Act]:
+    """models/ssd_mobilenet_v2.py:24-46 over keras_applications MobileNetV2
+    (alpha 1.0, include_top=False): returns the six head taps."""
+    x = n.conv(x, "Conv1", 32, k=3, stride=2, pad="correct", act=ACT_RELU6, bn="bn_Conv1", use_bias=False)
+    taps: List[Act] = []
+    for bid, (t, c, s) in enumerate(MNV2_BLOCKS):
+        prefix = f"block_{bid}_" if bid else "expanded_conv_"
+        inp = x
+        if bid:
+            x = n.conv(x, prefix + "expand", t * inp.C, act=ACT_RELU6, bn=prefix + "expand_BN", use_bias=False)
+            if bid == 13:
+                taps.append(x)                                  # block_13_expand_relu   :27
+        x = n.dw(x, prefix + "depthwise", stride=s, act=ACT_RELU6, bn=prefix + "depthwise_BN")
+        res = inp if (s == 1 and inp.C == c) else None          # block_i_add
+        x = n.conv(x, prefix + "project", c, act=ACT_NONE, bn=prefix + "project_BN", use_bias=False, residual=res)
+    x = n.conv(x, "Conv_1", 1280, act=ACT_RELU6, bn="Conv_1_bn", use_bias=False)
+    taps.append(x)                                              # out_relu   :28
+    for i, (c1, c2) in enumerate([(256, 512), (128, 256), (128, 256), (128, 256)], start=1):   # :31-41
+        x = n.conv(x, f"extra{i}_1", c1, pad="valid", act=ACT_RELU)
+        x = n.conv(x, f"extra{i}_2", c2, k=3, stride=2, pad="same", act=ACT_RELU)
+        taps.append(x)
+    return taps
+
+
+def vgg16_graph(n: Any, x: Act, hp: Dict[str, Any]) -> List[Act]:
+    """models/ssd_vgg16.py:78-119.  With seven feature maps the SSD512 extension
+    (not in the reference) is built instead."""
+    ssd512 = len(hp["feature_map_shapes"]) == 7
+    kw = dict(k=3, act=ACT_RELU, init="glorot_normal", l2=True)
+    conv4_3 = None
+    for bname, reps, cout in [("conv1", 2, 64), ("conv2", 2, 128), ("conv3", 3, 256), ("conv4", 3, 512),
+                              ("conv5", 3, 512)]:
+        for r in range(1, reps + 1):
+            x = n.conv(x, f"{bname}_{r}", cout, **kw)
+        if bname == "conv4":
+            conv4_3 = x
+        x = n.maxpool(x, 2, 2) if bname != "conv5" else n.maxpool(x, 3, 1)      # :82-101
+    x = n.conv(x, "conv6", 1024, dilation=6, **kw)                              # :103
+    kw1 = dict(kw, k=1)
+    conv7 = n.conv(x, "conv7", 1024, **kw1)                                     # :104
+    x = n.conv(conv7, "conv8_1", 256, pad="valid", **kw1)
+    conv8_2 = n.conv(x, "conv8_2", 512, stride=2, **kw)
+    x = n.conv(conv8_2, "conv9_1", 128, pad="valid", **kw1)
+    conv9_2 = n.conv(x, "conv9_2", 256, stride=2, **kw)
+    x = n.conv(conv9_2, "conv10_1", 128, pad="valid", **kw1)
+    if ssd512:
+        conv10_2 = n.conv(x, "conv10_2", 256, stride=2, **kw)
+        x = n.conv(conv10_2, "conv11_1", 128, pad="valid", **kw1)
+        conv11_2 = n.conv(x, "conv11_2", 256, stride=2, **kw)
+        x = n.conv(conv11_2, "conv12_1", 128, pad="valid", **kw1)
+        conv12_2 = n.conv(x, "conv12_2", 256, stride=2, **kw)
+    else:
+        conv10_2 = n.conv(x, "conv10_2", 256, pad="valid", **kw)                # :111
+        x = n.conv(conv10_2, "conv11_1", 128, pad="valid", **kw1)
+        conv11_2 = n.conv(x, "conv11_2", 256, pad="valid", **kw)                # :113
+    norm = n.l2norm(conv4_3, "l2_normalization")                                # :116
+    return [norm, conv7, conv8_2, conv9_2, conv10_2, conv11_2] + ([conv12_2] if ssd512 else [])
+
+
+GRAPHS: Dict[str, Callable[[Any, Act, Dict[str, Any]], List[Act]]] = {
+    "mobilenet_v2": mobilenet_v2_graph,
+    "vgg16": vgg16_graph,
+}
+
+
+# ------------------------------------------------------- parameter enumeration --
+class _ParamTracer:
+    """Walks a graph with shapes only and creates the Keras-named variables."""
+
+    def __init__(self, rng: np.random.Generator):
+        self.rng = rng
+        self.weights: Dict[str, np.ndarray] = {}
+        self.l2_kernels: List[str] = []          # kernels carrying l2(5e-4) (ssd_vgg16.py:76)
+        self.macs = 0                            # multiply-accumulates per image
+
+    def _kernel(self, shape, fan_in, fan_out, init):
+        if init == "glorot_normal":              # Keras: truncated normal, std = sqrt(2/(fan_in+fan_out))/.8796
+            std = math.sqrt(2.0 / (fan_in + fan_out))
+            return np.clip(self.rng.standard_normal(shape), -2, 2).astype(np.float32) * np.float32(std / 0.87962566)
+        if init == "he_normal":
+            return (self.rng.standard_normal(shape) * math.sqrt(2.0 / fan_in)).astype(np.float32)
+        lim = math.sqrt(6.0 / (fan_in + fan_out))            # glorot_uniform, the Keras default
+        return self.rng.uniform(-lim, lim, shape).astype(np.float32)
+
+    def _bn(self, name, c):
+        self.weights[name + "/gamma"] = np.ones(c, np.float32)
+        self.weights[name + "/beta"] = np.zeros(c, np.float32)
+        self.weights[name + "/moving_mean"] = np.zeros(c, np.float32)
+        self.weights[name + "/moving_variance"] = np.ones(c, np.float32)
+
+    def conv(self, x, name, cout, k=1, stride=1, pad="same", dilation=1, act=ACT_NONE, bn=None, use_bias=True,
+             residual=None, init="he_normal", l2=False):
+        ph, pw = _resolve_pads(x.H, x.W, k, stride, dilation, pad)
+        Ho, Wo = _out_size(x.H, k, stride, dilation, ph), _out_size(x.W, k, stride, dilation, pw)
+        self.weights[name + "/kernel"] = self._kernel((k, k, x.C, cout), k * k * x.C, k * k * cout, init)
+        if use_bias:
+            self.weights[name + "/bias"] = np.zeros(cout, np.float32)
+        if bn:
+            self._bn(bn, cout)
+        if l2:
+            self.l2_kernels.append(name + "/kernel")
+        self.macs += Ho * Wo * k * k * x.C * cout
+        return Act(None, Ho, Wo, cout)
+
+    def dw(self, x, name, stride=1, act=ACT_RELU6, bn=None):
+        ph, pw = _resolve_pads(x.H, x.W, 3, stride, 1, "same" if stride == 1 else "correct")
+        Ho, Wo = _out_size(x.H, 3, stride, 1, ph), _out_size(x.W, 3, stride, 1, pw)
+        self.weights[name + "/depthwise_kernel"] = self._kernel((3, 3, x.C, 1), 9, 9, "he_normal")
+        if bn:
+            self._bn(bn, x.C)
+        self.macs += Ho * Wo * 9 * x.C
+        return Act(None, Ho, Wo, x.C)
+
+    def maxpool(self, x, k, s):
+        ph, pw = same_pad(x.H, k, s), same_pad(x.W, k, s)
+        return Act(None, _out_size(x.H, k, s, 1, ph), _out_size(x.W, k, s, 1, pw), x.C)
+
+    def l2norm(self, x, name, scale_factor=20.0):
+        self.weights[name + "/scale"] = np.full(x.C, scale_factor, np.float32)      # ssd_vgg16.py:38-44
+        return x
+
+    def head(self, taps, hp):
+        L = int(hp["total_labels"])
+        for i, t in enumerate(taps):
+            A = len(hp["aspect_ratios"][i]) + 1
+            for nm, c in ((f"{i + 1}_conv_label_output", A * L), (f"{i + 1}_conv_boxes_output", A * 4)):
+                self.weights[nm + "/kernel"] = self._kernel((3, 3, t.C, c), 9 * t.C, 9 * c, "glorot_uniform")
+                self.weights[nm + "/bias"] = np.zeros(c, np.float32)
+                self.macs += t.H * t.W * 9 * t.C * c
+
+
+# ------------------------------------------------------------------ the plan --
+@dataclass
+class Step:
+    name: str
+    kind: str               # conv | dw | pool | l2norm | cast | softmax
+    fn: Any
+    args: tuple             # everything but the trailing stream argument
+    flops: float            # 2 * MACs for the whole batch
+    bytes: float            # algorithmic bytes: inputs + weights + outputs, once each
+    keep: tuple = ()        # objects that must outlive the plan (descs, tensors)
+    meta: Optional[Dict[str, Any]] = None   # tensors + geometry of the launch (tests check every layer in situ)
+
+
+class Plan:
+    """A flat, allocation-free launch list for one (backbone, batch) pair."""
+
+    def __init__(self, B: int, img_size: int, device: torch.device):
+        self.B, self.img_size, self.device = B, img_size, device
+        self.steps: List[Step] = []
+        self.image = torch.zeros((B, img_size, img_size, 3), dtype=torch.float32, device=device)
+        self.logits: Optional[torch.Tensor] = None
+        self.deltas: Optional[torch.Tensor] = None
+        self.taps: List[Act] = []
+
+    def run(self, first: int = 0, last: Optional[int] = None) -> None:
+        st = _ffi.stream()
+        for s in self.steps[first:last]:
+            rc = s.fn(*s.args, st)
+            if rc != 0:
+                _ffi.check(rc, f"{s.fn.__name__} [{s.name}]")
+
+    @property
+    def n_launches(self) -> int:
+        return len(self.steps)
+
+
+class _PlanBuilder:
+    def __init__(self, model: "SSDModel", B: int):
+        self.m = model
+        self.B = B
+        self.dev = _ffi.require_cuda()
+        self.lib = _ffi.lib()
+        self.plan = Plan(B, model.img_size, self.dev)
+
+    def _buf(self, H, W, C) -> torch.Tensor:
+        return torch.empty((self.B, H, W, C), dtype=torch.float16, device=self.dev)
+
+    def input(self) -> Act:
+        S = self.m.img_size
+        x = self._buf(S, S, 8)
+        npx = self.B * S * S
+        self.plan.steps.append(Step("input_cast", "cast", self.lib.ssd_image_to_f16c8,
+                                    (_ffi.ptr(self.plan.image), _ffi.ptr(x), npx), 0.0, npx * (12 + 16), (x,)))
+        return Act(x, S, S, 8)
+
+    def _emit_conv(self, name, x: Act, w: torch.Tensor, bias, cout, k, stride, dilation, ph, pw, act,
+                   residual: Optional[Act], out0, out1=None, out_f32=0, split=None, strides=None, real_cin=None):
+        Ho, Wo = _out_size(x.H, k, stride, dilation, ph), _out_size(x.W, k, stride, dilation, pw)
+        d = ConvDesc()
+        d.inp, d.weight, d.bias = x.t.data_ptr(), w.data_ptr(), (bias.data_ptr() if bias is not None else None)
+        d.residual = residual.t.data_ptr() if residual is not None else None
+        d.out0, d.out1 = out0.data_ptr() if isinstance(out0, torch.Tensor) else out0, out1
+        d.B, d.H, d.W, d.Cin = self.B, x.H, x.W, x.C
+        d.Ho, d.Wo, d.Cout = Ho, Wo, cout
+        d.KH = d.KW = k
+        d.stride, d.dilation, d.pad_top, d.pad_left = stride, dilation, ph[0], pw[0]
+        d.act, d.out_f32 = act, out_f32
+        d.split = cout if split is None else split
+        if strides is None:
+            strides = (Ho * Wo * cout, cout, 0, 0)
+        d.img_stride0, d.pix_stride0, d.img_stride1, d.pix_stride1 = strides
+        cin = real_cin or x.C
+        macs = self.B * Ho * Wo * k * k * cin * cout
+        nbytes = self.B * x.H * x.W * cin * 2 + k * k * cin * cout * 2 + \
+            self.B * Ho * Wo * cout * (4 if out_f32 else 2) + (self.B * Ho * Wo * cout * 2 if residual is not None else 0)
+        meta = dict(x=x.t, w=w, bias=bias, res=residual.t if residual is not None else None, out0=out0, out1=out1,
+                    k=k, stride=stride, dilation=dilation, ph=ph, pw=pw, act=act, Ho=Ho, Wo=Wo, cout=cout,
+                    split=d.split, out_f32=out_f32, strides=strides)
+        self.plan.steps.append(Step(name, "conv", self.lib.ssd_conv2d, (C.byref(d),), 2.0 * macs, nbytes,
+                                    (d, w, bias, x.t, out0), meta))
+        return Ho, Wo
+
+    def conv(self, x, name, cout, k=1, stride=1, pad="same", dilation=1, act=ACT_NONE, bn=None, use_bias=True,
+             residual=None, init=None, l2=False):
+        ph, pw = _resolve_pads(x.H, x.W, k, stride, dilation, pad)
+        w, b = self.m._packed_conv(name, bn, x.C)
+        Ho, Wo = _out_size(x.H, k, stride, dilation, ph), _out_size(x.W, k, stride, dilation, pw)
+        out = self._buf(Ho, Wo, cout)
+        real_cin = self.m.weights[name + "/kernel"].shape[2]
+        self._emit_conv(name, x, w, b, cout, k, stride, dilation, ph, pw, act, residual, out, real_cin=real_cin)
+        return Act(out, Ho, Wo, cout)
+
+    def dw(self, x, name, stride=1, act=ACT_RELU6, bn=None):
+        ph, pw = _resolve_pads(x.H, x.W, 3, stride, 1, "same" if stride == 1 else "correct")
+        Ho, Wo = _out_size(x.H, 3, stride, 1, ph), _out_size(x.W, 3, stride, 1, pw)
+        w, b = self.m._packed_dw(name, bn)
+        out = self._buf(Ho, Wo, x.C)
+        args = (_ffi.ptr(x.t), _ffi.ptr(w), _ffi.ptr(b), _ffi.ptr(out), self.B, x.H, x.W, x.C, Ho, Wo, stride,
+                ph[0], pw[0], act)
+        nbytes = self.B * (x.H * x.W + Ho * Wo) * x.C * 2 + 9 * x.C * 2
+        self.plan.steps.append(Step(name, "dw", self.lib.ssd_depthwise3x3, args, 2.0 * self.B * Ho * Wo * 9 * x.C,
+                                    nbytes, (w, b, x.t, out),
+                                    dict(x=x.t, w=w, bias=b, out=out, stride=stride, ph=ph, pw=pw, act=act)))
+        return Act(out, Ho, Wo, x.C)
+
+    def maxpool(self, x, k, s):
+        ph, pw = same_pad(x.H, k, s), same_pad(x.W, k, s)
+        Ho, Wo = _out_size(x.H, k, s, 1, ph), _out_size(x.W, k, s, 1, pw)
+        out = self._buf(Ho, Wo, x.C)
+        args = (_ffi.ptr(x.t), _ffi.ptr(out), self.B, x.H, x.W, x.C, Ho, Wo, k, s, ph[0], pw[0])
+        self.plan.steps.append(Step(f"pool{k}x{k}s{s}_{x.H}", "pool", self.lib.ssd_maxpool, args, 0.0,
+                                    self.B * (x.H * x.W + Ho * Wo) * x.C * 2, (x.t, out),
+                                    dict(x=x.t, out=out, k=k, stride=s, ph=ph, pw=pw)))
+        return Act(out, Ho, Wo, x.C)
+
+    def l2norm(self, x, name, scale_factor=20.0):
+        scale = self.m._dev_f32(name + "/scale")
+        out = self._buf(x.H, x.W, x.C)
+        rows = self.B * x.H * x.W
+        self.plan.steps.append(Step(name, "l2norm", self.lib.ssd_l2norm,
+                                    (_ffi.ptr(x.t), _ffi.ptr(scale), _ffi.ptr(out), rows, x.C), 0.0,
+                                    rows * x.C * 4, (scale, x.t, out), dict(x=x.t, scale=scale, out=out)))
+        return Act(out, x.H, x.W, x.C)
+
+    def head(self, taps: Sequence[Act], hp):
+        """models/header.py:54-90: per tap ONE 3x3 SAME convolution producing the
+        label and box channels together, written straight into the concatenated
+        ``[B,N,L]`` logits and ``[B,N,4]`` deltas (HeadWrapper :46-51 is free)."""
+        L = int(hp["total_labels"])
+        counts = [t.H * t.W * (len(hp["aspect_ratios"][i]) + 1) for i, t in enumerate(taps)]
+        N = sum(counts)
+        logits = torch.empty((self.B, N, L), dtype=torch.float32, device=self.dev)
+        deltas = torch.empty((self.B, N, 4), dtype=torch.float32, device=self.dev)
+        off = 0
+        for i, t in enumerate(taps):
+            A = len(hp["aspect_ratios"][i]) + 1
+            w, b = self.m._packed_head(i + 1, t.C)
+            ph, pw = same_pad(t.H, 3, 1), same_pad(t.W, 3, 1)
+            out0 = logits.data_ptr() + off * L * 4
+            out1 = deltas.data_ptr() + off * 4 * 4
+            self._emit_conv(f"{i + 1}_conv_head", t, w, b, A * (L + 4), 3, 1, 1, ph, pw, ACT_NONE, None, out0, out1,
+                            out_f32=1, split=A * L, strides=(N * L, A * L, N * 4, A * 4))
+            self.plan.steps[-1].meta["head"] = (off, counts[i], A)
+            off += counts[i]
+        self.plan.logits, self.plan.deltas, self.plan.taps = logits, deltas, list(taps)
+        return deltas, logits
+
+
+# ----------------------------------------------------------------- the model --
+class SSDModel(object):
+    """What ``get_model(hyper_params)`` returns: the object ``trainer.py`` /
+    ``predictor.py`` call (``model(x)``, ``load_weights``, ``predict``).
+
+    ``model(images)`` -> ``(pred_deltas [B,N,4], pred_labels [B,N,L])`` with
+    ``pred_labels`` the softmax probabilities (header.py:88-90), both float32
+    CUDA tensors.  Weights live in ``self.weights`` as float32 NumPy arrays in
+    Keras layouts under Keras variable names, so a converted ``.h5`` drops in.
+    Inference arithmetic: BatchNorm folded into the preceding kernel, fp16
+    storage, fp32 accumulation, fp32 head outputs."""
+
+    def __init__(self, backbone: str, hyper_params: Dict[str, Any], seed: int = 0):
+        if "total_labels" not in hyper_params:
+            raise KeyError("hyper_params['total_labels'] must be set by the caller (trainer.py:63-64)")
+        self.backbone = "vgg16" if backbone.startswith("vgg16") else backbone
+        self.hyper_params = hyper_params
+        self.img_size = int(hyper_params["img_size"])
+        self.total_labels = int(hyper_params["total_labels"])
+        tr = _ParamTracer(np.random.default_rng(seed))
+        taps = GRAPHS[self.backbone](tr, Act(None, self.img_size, self.img_size, 3), hyper_params)
+        fm = [t.H for t in taps]
+        if fm != list(hyper_params["feature_map_shapes"]):
+            raise ValueError(f"graph yields feature maps {fm}, hyper_params say {hyper_params['feature_map_shapes']}")
+        tr.head(taps, hyper_params)
+        self.weights: Dict[str, np.ndarray] = tr.weights
+        self.l2_kernels = tr.l2_kernels
+        self.macs_per_image = tr.macs
+        self.n_anchors = sum(t.H * t.W * (len(hyper_params["aspect_ratios"][i]) + 1) for i, t in enumerate(taps))
+        self._packed: Dict[str, Tuple[torch.Tensor, Optional[torch.Tensor]]] = {}
+        self._plans: Dict[Tuple[int, int], Plan] = {}
+
+    # -- weights ---------------------------------------------------------------
+    def set_weights(self, weights: Dict[str, np.ndarray]) -> None:
+        for k, v in weights.items():
+            if k not in self.weights:
+                raise KeyError(f"unknown variable {k!r}")
+            if tuple(v.shape) != tuple(self.weights[k].shape):
+                raise ValueError(f"{k}: shape {v.shape} != {self.weights[k].shape}")
+            self.weights[k] = np.ascontiguousarray(v, dtype=np.float32)
+        self._invalidate()
+
+    def get_weights(self) -> Dict[str, np.ndarray]:
+        return dict(self.weights)
+
+    def save_weights(self, path: str) -> None:
+        np.savez(path, **self.weights)
+
+    def load_weights(self, path: str) -> None:
+        """``model.load_weights`` (trainer.py:99, predictor.py:83).  ``.npz`` keyed
+        by Keras variable names; ``h5py`` is not available in this image."""
+        with np.load(path) as z:
+            self.set_weights({k: z[k] for k in z.files})
+
+    def _invalidate(self) -> None:
+        self._packed.clear()
+        self._plans.clear()
+
+    def _bn_fold(self, bn: Optional[str], cout: int, bias: Optional[np.ndarray]):
+        b = bias if bias is not None else np.zeros(cout, np.float32)
+        if bn is None:
+            return np.ones(cout, np.float32), b
+        w = self.weights
+        scale = w[bn + "/gamma"] / np.sqrt(w[bn + "/moving_variance"] + np.float32(BN_EPS))
+        return scale.astype(np.float32), (b * scale + (w[bn + "/beta"] - w[bn + "/moving_mean"] * scale)).astype(np.float32)
+
+    def _upload(self, key, kernel_ohwi: np.ndarray, bias: np.ndarray):
+        dev = _ffi.require_cuda()
+        wt = torch.from_numpy(np.ascontiguousarray(kernel_ohwi)).to(dev).to(torch.float16).contiguous()
+        bt = torch.from_numpy(np.ascontiguousarray(bias, dtype=np.float32)).to(dev)
+        self._packed[key] = (wt, bt)
+        return wt, bt
+
+    def _packed_conv(self, name: str, bn: Optional[str], cin_buf: int):
+        """HWIO float32 -> BN-folded OHWI fp16 (Cin zero-padded to the buffer's channel count)."""
+        if name in self._packed:
+            return self._packed[name]
+        k = self.weights[name + "/kernel"]                          # [kh,kw,Cin,Cout]
+        scale, bias = self._bn_fold(bn, k.shape[3], self.weights.get(name + "/bias"))
+        k = k * scale.reshape(1, 1, 1, -1)
+        if cin_buf != k.shape[2]:
+            k = np.concatenate([k, np.zeros(k.shape[:2] + (cin_buf - k.shape[2], k.shape[3]), np.float32)], axis=2)
+        return self._upload(name, k.transpose(3, 0, 1, 2), bias)
+
+    def _packed_dw(self, name: str, bn: Optional[str]):
+        if name in self._packed:
+            return self._packed[name]
+        k = self.weights[name + "/depthwise_kernel"][:, :, :, 0]    # [3,3,C]
+        scale, bias = self._bn_fold(bn, k.shape[2], None)
+        return self._upload(name, k * scale.reshape(1, 1, -1), bias)
+
+    def _packed_head(self, index: int, cin_buf: int):
+        key = f"{index}_conv_head"
+        if key in self._packed:
+            return self._packed[key]
+        kl, kb = self.weights[f"{index}_conv_label_output/kernel"], self.weights[f"{index}_conv_boxes_output/kernel"]
+        k = np.concatenate([kl, kb], axis=3)
+        bias = np.concatenate([self.weights[f"{index}_conv_label_output/bias"],
+                               self.weights[f"{index}_conv_boxes_output/bias"]])
+        return self._upload(key, k.transpose(3, 0, 1, 2), bias)
+
+    def _dev_f32(self, key: str) -> torch.Tensor:
+        if key not in self._packed:
+            self._packed[key] = (torch.from_numpy(self.weights[key]).to(_ffi.require_cuda()), None)
+        return self._packed[key][0]
+
+    # -- plans -----------------------------------------------------------------
+    def plan(self, B: int, slot: int = 0) -> Plan:
+        """Launch plan for batch size ``B``.  ``slot`` selects an independent set of
+        activation buffers (double-buffered pipelines keep two in flight)."""
+        if (B, slot) not in self._plans:
+            _ffi.check_device()
+            pb = _PlanBuilder(self, B)
+            taps = GRAPHS[self.backbone](pb, pb.input(), self.hyper_params)
+            pb.head(taps, self.hyper_params)
+            self._plans[(B, slot)] = pb.plan
+        return self._plans[(B, slot)]
+
+    def _to_image_buffer(self, plan: Plan, images: Any) -> None:
+        x = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images, np.float32))
+        if tuple(x.shape) != tuple(plan.image.shape):
+            raise ValueError(f"expected images {tuple(plan.image.shape)} (NHWC float32), got {tuple(x.shape)}")
+        plan.image.copy_(x.to(torch.float32), non_blocking=True)
+
+    def forward_logits(self, images: Any) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``(pred_deltas, logits)`` -- the pre-softmax head outputs (what Keras feeds
+        the cross-entropy inside ``fit`` and what the fused decoder consumes)."""
+        B = int(images.shape[0])
+        plan = self.plan(B)
+        self._to_image_buffer(plan, images)
+        plan.run()
+        return plan.deltas, plan.logits
+
+    def __call__(self, images: Any, training: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+        deltas, logits = self.forward_logits(images)
+        B, N, L = logits.shape
+        probs = torch.empty_like(logits)
+        _ffi.check(_ffi.lib().ssd_softmax(_ffi.ptr(logits), B * N, L, _ffi.ptr(probs), _ffi.stream()), "ssd_softmax")
+        return deltas.clone(), probs
+
+    def predict(self, data: Iterable[Any], steps: Optional[int] = None, verbose: int = 0):
+        outs_d, outs_p = [], []
+        for i, batch in enumerate(data):
+            if steps is not None and i >= steps:
+                break
+            img = batch[0] if isinstance(batch, (tuple, list)) else batch
+            d, p = self(img)
+            outs_d.append(d.cpu().numpy())
+            outs_p.append(p.cpu().numpy())
+        return np.concatenate(outs_d, 0), np.concatenate(outs_p, 0)
+
+
+class DecoderModel(object):
+    """``get_decoder_model`` result (models/decoder.py:96-108): images ->
+    ``(boxes [B,200,4], labels [B,200], scores [B,200])``.
+
+    The forward plan and the fused softmax+decode+NMS are captured into one
+    CUDA graph per (batch size, slot).  ``predict`` keeps two slots in flight:
+    the host->device image copy of batch i+1 and the device->host copy of
+    batch i-1's detections overlap batch i's graph replay."""
+
+    N_SLOTS = 2
+
+    def __init__(self, base_model: SSDModel, decoder: Any, use_cuda_graph: bool = True):
+        self.base_model = base_model
+        self.decoder = decoder
+        self.use_cuda_graph = use_cuda_graph
+        self._state: Dict[Tuple[int, int], Dict[str, Any]] = {}
+        self._copy_stream: Optional[Tuple[torch.cuda.Stream, torch.cuda.Stream]] = None
+
+    def _prepare(self, B: int, slot: int = 0) -> Dict[str, Any]:
+        if (B, slot) in self._state:
+            return self._state[(B, slot)]
+        plan = self.base_model.plan(B, slot)
+        dev, T = plan.device, self.decoder.max_total_size
+        st: Dict[str, Any] = {
+            "plan": plan,
+            # one packed result buffer so a single D2H brings everything back:
+            # [B, T, 6] = boxes(4) | labels | scores, then the int32 valid counts
+            "boxes": torch.empty((B, T, 4), dtype=torch.float32, device=dev),
+            "labels": torch.empty((B, T), dtype=torch.float32, device=dev),
+            "scores": torch.empty((B, T), dtype=torch.float32, device=dev),
+            "valid": torch.empty((B,), dtype=torch.int32, device=dev),
+            "graph": None,
+            "ws": _ffi.workspace(_ffi.lib().ssd_decode_nms_workspace_bytes(B, self.base_model.n_anchors,
+                                                                            self.base_model.total_labels, T, 0)),
+        }
+        dec, lib = self.decoder, _ffi.lib()
+        var = _ffi.f32_array(dec.variances)
+        priors = dec._priors()
+        N, L = self.base_model.n_anchors, self.base_model.total_labels
+
+        def enqueue():
+            plan.run()
+            _ffi.check(lib.ssd_decode_nms(_ffi.ptr(priors), _ffi.ptr(plan.deltas), _ffi.ptr(plan.logits), B, N, L, var, 1,
+                                          dec.score_threshold, dec.iou_threshold, T, 0, _ffi.ptr(st["boxes"]),
+                                          _ffi.ptr(st["labels"]), _ffi.ptr(st["scores"]), _ffi.ptr(st["valid"]),
+                                          _ffi.ptr(st["ws"]), st["ws"].numel(), _ffi.stream()), "ssd_decode_nms")
+
+        st["enqueue"] = enqueue
+        if self.use_cuda_graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                      # warm-up: function attributes, lazy module load
+                    enqueue()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                enqueue()
+            st["graph"] = g
+        self._state[(B, slot)] = st
+        return st
+
+    def launches_per_batch(self, B: int) -> int:
+        """libssd_b200 kernels per forward+decode: plan steps + candidate pass + per-image NMS."""
+        return self.base_model.plan(B).n_launches + 2
+
+    def run_resident(self, B: int, slot: int = 0) -> Dict[str, Any]:
+        """Replay on whatever already sits in the slot's image buffer (device-resident timing)."""
+        st = self._prepare(B, slot)
+        if st["graph"] is not None:
+            st["graph"].replay()
+        else:
+            st["enqueue"]()
+        return st
+
+    def __call__(self, images: Any):
+        B = int(images.shape[0])
+        st = self._prepare(B)
+        self.base_model._to_image_buffer(st["plan"], images)
+        self.run_resident(B)
+        self.decoder.last_valid_detections = st["valid"]
+        return st["boxes"].clone(), st["labels"].clone(), st["scores"].clone()
+
+    def predict(self, data: Iterable[Any], steps: Optional[int] = None, verbose: int = 0):
+        """predictor.py:93-97: three NumPy arrays concatenated over the batches.
+        Host batches go through pinned staging buffers; copies run on a second
+        stream and overlap the neighbouring batches' compute."""
+        dev = _ffi.require_cuda()
+        if self._copy_stream is None:
+            self._copy_stream = (torch.cuda.Stream(), torch.cuda.Stream())      # H2D, D2H
+        (cs, ds), ms = self._copy_stream, torch.cuda.current_stream()
+        T = self.decoder.max_total_size
+        ob, ol, os_ = [], [], []
+        pending: List[Tuple[Dict[str, Any], torch.cuda.Event]] = []
+        host: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}
+
+        def drain(entry):
+            st, hb, done = entry
+            done.synchronize()
+            ob.append(hb["boxes"].numpy().copy()); ol.append(hb["labels"].numpy().copy())
+            os_.append(hb["scores"].numpy().copy())
+
+        for i, batch in enumerate(data):
+            if steps is not None and i >= steps:
+                break
+            img = batch[0] if isinstance(batch, (tuple, list)) else batch
+            B = int(img.shape[0])
+            slot = i % self.N_SLOTS
+            st = self._prepare(B, slot)
+            if len(pending) >= self.N_SLOTS:           # the slot's previous user must be fully drained
+                drain(pending.pop(0))
+            hb = host.get((B, slot))
+            if hb is None:
+                hb = {"img": torch.empty(tuple(st["plan"].image.shape), dtype=torch.float32, pin_memory=True),
+                      "boxes": torch.empty((B, T, 4), dtype=torch.float32, pin_memory=True),
+                      "labels": torch.empty((B, T), dtype=torch.float32, pin_memory=True),
+                      "scores": torch.empty((B, T), dtype=torch.float32, pin_memory=True)}
+                host[(B, slot)] = hb
+            if isinstance(img, torch.Tensor) and img.is_cuda:
+                with torch.cuda.stream(cs):
+                    cs.wait_stream(ms)
+                    st["plan"].image.copy_(img.to(torch.float32), non_blocking=True)
+            else:
+                src = img if isinstance(img, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(img, np.float32))
+                if tuple(src.shape) != tuple(hb["img"].shape):
+                    raise ValueError(f"expected images {tuple(hb['img'].shape)} (NHWC float32), got {tuple(src.shape)}")
+                if not src.is_pinned():
+                    hb["img"].copy_(src)
+                    src = hb["img"]
+                with torch.cuda.stream(cs):
+                    st["plan"].image.copy_(src, non_blocking=True)
+            ms.wait_stream(cs)
+            self.run_resident(B, slot)
+            ds.wait_stream(ms)
+            with torch.cuda.stream(ds):
+                hb["boxes"].copy_(st["boxes"], non_blocking=True)
+                hb["labels"].copy_(st["labels"], non_blocking=True)
+                hb["scores"].copy_(st["scores"], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(ds)
+            pending.append((st, hb, done))
+        while pending:
+            drain(pending.pop(0))
+        if not ob:
+            z = np.zeros((0, T), np.float32)
+            return np.zeros((0, T, 4), np.float32), z, z.copy()
+        return np.concatenate(ob, 0), np.concatenate(ol, 0), np.concatenate(os_, 0)
+
+
+def smoke_forward() -> None:
+    """Tiny forward of both graphs (used by ``__graft_entry__.smoke``)."""
+    from tf_ssd_b200.utils import train_utils
+    for backbone in ("mobilenet_v2",):
+        hp = train_utils.get_hyper_params(backbone)
+        hp["total_labels"] = 21
+        model = SSDModel(backbone, hp, seed=1)
+        x = np.random.default_rng(0).random((1, hp["img_size"], hp["img_size"], 3), dtype=np.float32)
+        d, p = model(x)
+        torch.cuda.synchronize()
+        assert d.shape == (1, model.n_anchors, 4) and p.shape == (1, model.n_anchors, 21)
+        assert bool(torch.isfinite(d).all()) and bool(torch.isfinite(p).all())
