@@ -2,10 +2,10 @@
 two SSD graphs) against the torch-CPU oracle.
 
 Tolerances: the product computes with fp16 storage and fp32 accumulation
-(BASELINE.json config 2: "fp16 convs / fp32 boxes").  Against the oracle's
-``fp16sim`` mode (same roundings, different summation order) the bound is
-5e-3 of the tensor's max magnitude; against the reference's fp32 arithmetic it
-is 3e-2 of the max magnitude (fp16 storage error through up to 54 layers)."""
+(BASELINE.json config 2: "fp16 convs / fp32 boxes").  Single launches are
+checked at 2e-3 of the tensor's max magnitude (one fp16 output rounding) against
+torch-CPU fp32 on the same fp16 operands; whole graphs are checked relative to
+the oracle's own fp16-storage error (see ``test_forward_parity``)."""
 
 import ctypes as C
 
@@ -288,6 +288,9 @@ def test_decoder_model_end_to_end():
         b = m.weights[f"{i}_conv_label_output/bias"].copy().reshape(-1, 21)
         b += rng.normal(0, 2.5, b.shape).astype(np.float32)
         w[f"{i}_conv_label_output/bias"] = b.reshape(-1)
+        # keep the regression outputs in a trained detector's range (|delta| of a few units): exp() of the
+        # raw random-weight outputs overflows and inf - inf = NaN has no defined clip in either implementation
+        w[f"{i}_conv_boxes_output/kernel"] = m.weights[f"{i}_conv_boxes_output/kernel"] * np.float32(0.02)
     m.set_weights(w)
     priors = bbox_utils.generate_prior_boxes(hp["feature_map_shapes"], hp["aspect_ratios"])
     dm = get_decoder_model(m, priors, hp)
@@ -301,4 +304,6 @@ def test_decoder_model_end_to_end():
         sl = slice(i * B, (i + 1) * B)
         assert (rs > 0).sum() > 0
         assert np.array_equal(labels[sl], rl) and np.allclose(scores[sl], rs, rtol=1e-6, atol=0)
-        assert np.allclose(boxes[sl], rb, rtol=1e-5, atol=1e-6)
+        # random-weight deltas are large: y1 = cy - h/2 cancels, so the bound is absolute (boxes live in [0,1])
+        assert np.isfinite(rb).all()
+        np.testing.assert_allclose(boxes[sl], rb, rtol=1e-5, atol=2e-5)

@@ -118,6 +118,96 @@ iou_map_kernel(const float4* __restrict__ boxes, const float4* __restrict__ gt, 
     }
 }
 
+// Warp-tile variant for G <= kIouTileMaxG: a warp owns 32 consecutive anchors and
+// all G ground-truth boxes.  Ground-truth boxes that cannot overlap ANY of the
+// warp's anchors (tested against the warp's bounding box, one ballot per 32
+// boxes) are known to give IoU = +0 and skip the arithmetic entirely, so the
+// kernel does ~26 instructions only for (warp, box) pairs that can intersect
+// and is otherwise a pure streaming write.  The [32][G] tile is transposed
+// through shared memory so the global stores are contiguous 16-byte vectors.
+constexpr int kIouTileMaxG = 128;
+constexpr int kIouTileWarps = 8;
+
+__device__ __forceinline__ float warp_min_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// true when ground-truth box q provably has zero intersection with every box inside
+// the bounding box (y1,x1,y2,x2) AND the reference formula then yields exactly +0
+// (needs union > 0: anchors with positive area, ground truth with non-negative area).
+// Any NaN makes the test false, i.e. the pair is computed exactly.
+__device__ __forceinline__ bool gt_culled(const float4 q, float q_area, float wy1, float wx1, float wy2, float wx2) {
+    return (q.z <= wy1 || q.x >= wy2 || q.w <= wx1 || q.y >= wx2) && q_area >= 0.0f;
+}
+
+__global__ void __launch_bounds__(kIouTileWarps * 32)
+iou_map_tile_kernel(const float4* __restrict__ boxes, const float4* __restrict__ gt, int N, int G, int pitch,
+                    int boxes_batched, float* __restrict__ out) {
+    extern __shared__ float4 s_gt[];                 // [G] boxes | [G] areas | per-warp [32][pitch] tiles
+    float* s_area = reinterpret_cast<float*>(s_gt + G);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* tile = s_area + G + (size_t)warp * 32 * pitch;
+    const int b = blockIdx.y;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        float4 v = gt[(size_t)b * G + g];
+        s_gt[g] = v;
+        s_area[g] = box_area(v);
+    }
+    __syncthreads();
+    const float4* bx = boxes + (boxes_batched ? (size_t)b * N : 0);
+    float* o = out + (size_t)b * N * G;
+    const int ntiles = (N + 31) >> 5;
+    const float inf = __int_as_float(0x7f800000);
+    for (int t = blockIdx.x * kIouTileWarps + warp; t < ntiles; t += gridDim.x * kIouTileWarps) {
+        const int n0 = t << 5, n = n0 + lane;
+        const bool valid = n < N;
+        const float4 p = valid ? __ldg(bx + n) : make_float4(inf, inf, -inf, -inf);
+        const float pa = box_area(p);
+        const float wy1 = warp_min_f(p.x), wx1 = warp_min_f(p.y), wy2 = warp_max_f(p.z), wx2 = warp_max_f(p.w);
+        const bool can_cull = __all_sync(0xffffffffu, !valid || pa > 0.0f);
+        float* row = tile + lane * pitch;
+        uint32_t hitmask[kIouTileMaxG / 32];             // warp-uniform: which boxes were evaluated
+#pragma unroll
+        for (int k = 0; k < kIouTileMaxG / 32; ++k) {
+            hitmask[k] = 0u;
+            const int g0 = k << 5;
+            if (g0 < G) {
+                const int g = g0 + lane;
+                bool hit = g < G;
+                if (can_cull && hit) hit = !gt_culled(s_gt[g], s_area[g], wy1, wx1, wy2, wx2);
+                uint32_t m = __ballot_sync(0xffffffffu, hit);
+                hitmask[k] = m;
+                while (m) {
+                    const int gg = g0 + __ffs(m) - 1;
+                    m &= m - 1;
+                    row[gg] = iou_ref(p, pa, s_gt[gg], s_area[gg]);
+                }
+            }
+        }
+        __syncwarp();
+        // row by row: lanes cover consecutive columns, so every store instruction writes one
+        // contiguous run of the output; culled columns are +0 without touching shared memory
+        const int rows = min(32, N - n0);
+        float* dst = o + (size_t)n0 * G;
+        for (int r = 0; r < rows; ++r) {
+            const float* trow = tile + r * pitch;
+            float* drow = dst + (size_t)r * G;
+#pragma unroll
+            for (int k = 0; k < kIouTileMaxG / 32; ++k) {
+                const int c = (k << 5) + lane;
+                if (c < G) __stcs(drow + c, ((hitmask[k] >> lane) & 1u) ? trow[c] : 0.0f);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------- encode / decode --
 // utils/bbox_utils.py:95-128 for one (prior, matched gt) pair -> [dy,dx,dh,dw]
 __device__ __forceinline__ float4 encode_one(const float4 p, const float4 g) {
@@ -192,25 +282,52 @@ match_encode_kernel(const float4* __restrict__ priors, const float4* __restrict_
 
     const int n0 = blockIdx.x * kMatchThreads;
     const int n = n0 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool valid = n < N;
+    const float inf = __int_as_float(0x7f800000);
     int label = 0;
-    if (n < N) {
-        float4 p = __ldg(priors + n);
-        float pa = box_area(p);
-        float best = iou_ref(p, pa, s_gt[0], s_area[0]);
+    {
+        // Ground-truth boxes that cannot overlap any anchor of this warp (tested against
+        // the warp's bounding box) have IoU = +0 for all 32 anchors and can never win the
+        // strict ">" of the arg-max, so only the boxes that pass the ballot are evaluated.
+        const float4 p = valid ? __ldg(priors + n) : make_float4(inf, inf, -inf, -inf);
+        const float pa = box_area(p);
+        const float wy1 = warp_min_f(p.x), wx1 = warp_min_f(p.y), wy2 = warp_max_f(p.z), wx2 = warp_max_f(p.w);
+        const bool can_cull = __all_sync(0xffffffffu, !valid || pa > 0.0f);
+        float best;
         int idx = 0;
-        for (int g = 1; g < G; ++g) {                              // first maximum wins (:124)
-            float v = iou_ref(p, pa, s_gt[g], s_area[g]);
-            if (v > best) { best = v; idx = g; }
+        if (can_cull) {
+            best = 0.0f;                                           // == IoU of every culled box
+            for (int g0 = 0; g0 < G; g0 += 32) {
+                const int g = g0 + lane;
+                bool hit = false;
+                if (g < G) hit = !gt_culled(s_gt[g], s_area[g], wy1, wx1, wy2, wx2);
+                unsigned mask = __ballot_sync(0xffffffffu, hit);
+                while (mask) {
+                    const int gg = g0 + __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    float v = iou_ref(p, pa, s_gt[gg], s_area[gg]);
+                    if (v > best) { best = v; idx = gg; }          // ascending g: first maximum wins (:124)
+                }
+            }
+        } else {                                                   // degenerate anchors: plain scan (0/0 = NaN semantics)
+            best = iou_ref(p, pa, s_gt[0], s_area[0]);
+            for (int g = 1; g < G; ++g) {
+                float v = iou_ref(p, pa, s_gt[g], s_area[g]);
+                if (v > best) { best = v; idx = g; }
+            }
         }
-        const bool pos = best > iou_thr;                           // strict (:126)
-        float4 g4 = pos ? s_gt[idx] : make_float4(0.f, 0.f, 0.f, 0.f);   // :129-130
-        float4 d = encode_one(p, g4);
-        d.x = fdiv(d.x, variances.x); d.y = fdiv(d.y, variances.y);      // :131
-        d.z = fdiv(d.z, variances.z); d.w = fdiv(d.w, variances.w);
-        __stcs(out_deltas + (size_t)b * N + n, d);
-        label = pos ? s_glab[idx] : 0;                             // :133-134
-        if (out_label) out_label[(size_t)b * N + n] = label;
-        if (out_match) out_match[(size_t)b * N + n] = idx;
+        if (valid) {
+            const bool pos = best > iou_thr;                           // strict (:126)
+            float4 g4 = pos ? s_gt[idx] : make_float4(0.f, 0.f, 0.f, 0.f);   // :129-130
+            float4 d = encode_one(p, g4);
+            d.x = fdiv(d.x, variances.x); d.y = fdiv(d.y, variances.y);      // :131
+            d.z = fdiv(d.z, variances.z); d.w = fdiv(d.w, variances.w);
+            __stcs(out_deltas + (size_t)b * N + n, d);
+            label = pos ? s_glab[idx] : 0;                             // :133-134
+            if (out_label) out_label[(size_t)b * N + n] = label;
+            if (out_match) out_match[(size_t)b * N + n] = idx;
+        }
     }
     if (out_onehot == nullptr) return;
     s_lab[threadIdx.x] = label;
@@ -227,16 +344,24 @@ match_encode_kernel(const float4* __restrict__ priors, const float4* __restrict_
         int a = e / L;
         dst[e] = (s_lab[a] == e - a * L) ? 1.0f : 0.0f;
     }
-    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
-        int e = head + (v << 2);
+    {
+        // (anchor, label) of the thread's first element by one division, then advanced
+        // incrementally by the block stride (4 * blockDim.x elements per step)
+        const int step = kMatchThreads * 4, step_a = step / L, step_l = step - step_a * L;
+        int e = head + (threadIdx.x << 2);
         int a = e / L, l = e - a * L;
-        float r[4];
+        for (int v = threadIdx.x; v < nvec; v += kMatchThreads) {
+            float r[4];
+            int aa = a, ll = l;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            r[k] = (s_lab[a] == l) ? 1.0f : 0.0f;
-            if (++l == L) { l = 0; ++a; }
+            for (int k = 0; k < 4; ++k) {
+                r[k] = (s_lab[aa] == ll) ? 1.0f : 0.0f;
+                if (++ll == L) { ll = 0; ++aa; }
+            }
+            __stcs(reinterpret_cast<float4*>(dst + e), make_float4(r[0], r[1], r[2], r[3]));
+            e += step; a += step_a; l += step_l;
+            if (l >= L) { l -= L; ++a; }
         }
-        __stcs(reinterpret_cast<float4*>(dst + e), make_float4(r[0], r[1], r[2], r[3]));
     }
     for (int e = head + (nvec << 2) + threadIdx.x; e < total; e += blockDim.x) {
         int a = e / L;
@@ -291,6 +416,21 @@ extern "C" int ssd_iou_map(const float* d_boxes, const float* d_gt, int B, int N
     SSD_REQUIRE(B >= 0 && N >= 0 && G >= 0 && B <= 65535, SSD_ERR_SHAPE,
                 "ssd_iou_map: bad shape B=%d N=%d G=%d", B, N, G);
     if (B == 0 || N == 0 || G == 0) return SSD_OK;
+    if (G <= kIouTileMaxG) {
+        const int pitch = G | 1;                                   // odd pitch: conflict-free column writes
+        size_t smem_t = (size_t)G * 20 + (size_t)kIouTileWarps * 32 * pitch * sizeof(float);
+        if (smem_t > 40 * 1024)
+            cudaFuncSetAttribute(iou_map_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+        const int ntiles = (N + 31) / 32;
+        const int per_img = (ntiles + kIouTileWarps - 1) / kIouTileWarps;
+        const int cap = max(1, (sm_count() * 16 + B - 1) / B);
+        dim3 grid(min(per_img, cap), B);
+        iou_map_tile_kernel<<<grid, kIouTileWarps * 32, smem_t, as_stream(stream)>>>(
+            reinterpret_cast<const float4*>(d_boxes), reinterpret_cast<const float4*>(d_gt), N, G, pitch,
+            boxes_batched, d_out);
+        SSD_CHECK_LAUNCH("iou_map_tile_kernel");
+        return SSD_OK;
+    }
     size_t smem = (size_t)G * 20;
     SSD_REQUIRE(smem <= 160 * 1024, SSD_ERR_UNSUPPORTED, "ssd_iou_map: G=%d exceeds shared-memory staging", G);
     const bool aligned = (((uintptr_t)d_out) & 15) == 0;

@@ -55,4 +55,37 @@ __device__ __forceinline__ int warp_sum_i(int v) {
     return v;
 }
 
+// Cooperative copy of `total` consecutive floats between global memory and a shared
+// staging region with 16-byte global accesses AND 16-byte shared accesses: the data is
+// placed in shared memory at the same misalignment (mod 4 floats) as in global memory,
+// so both sides of every vector move are aligned.  `region` must be 16-byte aligned and
+// hold total + 3 floats.  Returns the pointer p with p[e] == src[e].
+__device__ __forceinline__ float* stage_rows_in(const float* __restrict__ src, int total, float* __restrict__ region) {
+    const int mis = (int)(((uintptr_t)src >> 2) & 3);          // floats past a 16-byte boundary
+    float* s = region + mis;
+    const int head = min(total, (4 - mis) & 3);
+    const int nvec = (total - head) >> 2;
+    for (int e = threadIdx.x; e < head; e += blockDim.x) s[e] = __ldcs(src + e);
+    const float4* v = reinterpret_cast<const float4*>(src + head);
+    float4* d = reinterpret_cast<float4*>(s + head);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) d[i] = __ldcs(v + i);
+    for (int e = head + (nvec << 2) + threadIdx.x; e < total; e += blockDim.x) s[e] = __ldcs(src + e);
+    return s;
+}
+// The reverse: s must have been laid out with the destination's misalignment, i.e.
+// s == region + ((uintptr_t)dst >> 2 & 3).
+__device__ __forceinline__ float* stage_rows_ptr(const float* dst, float* region) {
+    return region + (int)(((uintptr_t)dst >> 2) & 3);
+}
+__device__ __forceinline__ void stage_rows_out(float* __restrict__ dst, int total, const float* __restrict__ s) {
+    const int mis = (int)(((uintptr_t)dst >> 2) & 3);
+    const int head = min(total, (4 - mis) & 3);
+    const int nvec = (total - head) >> 2;
+    for (int e = threadIdx.x; e < head; e += blockDim.x) __stcs(dst + e, s[e]);
+    float4* v = reinterpret_cast<float4*>(dst + head);
+    const float4* d = reinterpret_cast<const float4*>(s + head);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) __stcs(v + i, d[i]);
+    for (int e = head + (nvec << 2) + threadIdx.x; e < total; e += blockDim.x) __stcs(dst + e, s[e]);
+}
+
 }  // namespace ssd

@@ -18,32 +18,6 @@ namespace ssd {
 constexpr int kRowThreads = 128;      // anchors per CTA in the row-staged kernels
 constexpr int kSelThreads = 1024;
 
-// Cooperative copy of `total` consecutive floats src[0..total) into shared
-// memory: float4 body, scalar head/tail for arbitrary alignment.
-__device__ __forceinline__ void stage_in(const float* __restrict__ src, int total, float* __restrict__ s) {
-    const int head = min(total, (int)((4 - (((uintptr_t)src >> 2) & 3)) & 3));
-    const int nvec = (total - head) >> 2;
-    for (int e = threadIdx.x; e < head; e += blockDim.x) s[e] = __ldcs(src + e);
-    const float4* v = reinterpret_cast<const float4*>(src + head);
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        float4 t = __ldcs(v + i);
-        float* d = s + head + (i << 2);
-        d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
-    }
-    for (int e = head + (nvec << 2) + threadIdx.x; e < total; e += blockDim.x) s[e] = __ldcs(src + e);
-}
-__device__ __forceinline__ void stage_out(float* __restrict__ dst, int total, const float* __restrict__ s) {
-    const int head = min(total, (int)((4 - (((uintptr_t)dst >> 2) & 3)) & 3));
-    const int nvec = (total - head) >> 2;
-    for (int e = threadIdx.x; e < head; e += blockDim.x) __stcs(dst + e, s[e]);
-    float4* v = reinterpret_cast<float4*>(dst + head);
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const float* d = s + head + (i << 2);
-        __stcs(v + i, make_float4(d[0], d[1], d[2], d[3]));
-    }
-    for (int e = head + (nvec << 2) + threadIdx.x; e < total; e += blockDim.x) __stcs(dst + e, s[e]);
-}
-
 struct LossWs {            // views into the caller's workspace
     float*   ce;           // [B,N] per-anchor cross entropy
     float*   masked;       // [B,N] ce * y[...,0]           (ssd_loss.py:78)
@@ -74,17 +48,18 @@ __global__ void __launch_bounds__(kRowThreads)
 loss_anchor_kernel(const float4* __restrict__ act_d, const float4* __restrict__ pred_d,
                    const float* __restrict__ act_l, const float* __restrict__ pred_l,
                    int N, int L, LossWs w) {
-    extern __shared__ float s_rows[];                 // [cnt*L] labels, [cnt*L] predictions
+    extern __shared__ __align__(16) float s_rows[];   // [cnt*L + 4] labels, [cnt*L + 4] predictions
     const int b = blockIdx.y;
     const int n0 = blockIdx.x * kRowThreads;
     const int cnt = min(kRowThreads, N - n0);
     const size_t row0 = (size_t)b * N + n0;
+    const int region = kRowThreads * L + 4;               // floats per staging region (multiple of 4)
     float* s_y = s_rows;
-    float* s_p = s_rows + (size_t)kRowThreads * L;
+    float* s_p = s_rows + region;
     const bool do_conf = act_l != nullptr;
     if (do_conf) {
-        stage_in(act_l + row0 * L, cnt * L, s_y);
-        stage_in(pred_l + row0 * L, cnt * L, s_p);
+        s_y = stage_rows_in(act_l + row0 * L, cnt * L, s_rows);
+        s_p = stage_rows_in(pred_l + row0 * L, cnt * L, s_rows + region);
         __syncthreads();
     }
     if ((int)threadIdx.x >= cnt) return;
@@ -166,36 +141,56 @@ __device__ float block_sum(float v, float* s_red) {           // deterministic t
     return r;
 }
 
+// Three block sums at once (deterministic tree).
+__device__ float3 block_sum3(float3 v, float3* s_red3) {
+    v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) s_red3[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        float3 t = (lane < (int)(blockDim.x >> 5)) ? s_red3[lane] : make_float3(0.f, 0.f, 0.f);
+        t.x = warp_sum(t.x); t.y = warp_sum(t.y); t.z = warp_sum(t.z);
+        if (lane == 0) s_red3[0] = t;
+    }
+    __syncthreads();
+    float3 r = s_red3[0];
+    __syncthreads();
+    return r;
+}
+
 __global__ void __launch_bounds__(kSelThreads)
 loss_select_kernel(int N, float neg_pos_ratio, float alpha, bool do_loc, bool do_conf, LossWs w,
                    float* __restrict__ out_loc, float* __restrict__ out_conf) {
-    extern __shared__ uint32_t s_key[];               // [N]
+    extern __shared__ uint32_t s_key[];               // [N] keys, then [N] flag bytes
+    uint8_t* s_flag = reinterpret_cast<uint8_t*>(s_key + N);
     __shared__ float s_red[32];
+    __shared__ float3 s_red3[32];
     __shared__ int s_hist[256];
     __shared__ int s_scan[kSelThreads / 32];
     __shared__ uint32_t s_prefix;
     __shared__ int s_remaining;
     const int b = blockIdx.x, tid = threadIdx.x;
+    const int lane = tid & 31, wid = tid >> 5;
     const size_t base = (size_t)b * N;
     const int chunk = (N + kSelThreads - 1) / kSelThreads;
     const int lo = min(N, tid * chunk), hi = min(N, lo + chunk);
 
     // counts (exact in float while N < 2^24, like the reference's float sums)
-    float c_loc = 0.0f, c_conf = 0.0f, hsum = 0.0f;
+    float3 acc = make_float3(0.f, 0.f, 0.f);          // n_pos_loc, n_pos_conf, huber sum
     for (int i = tid; i < N; i += kSelThreads) {
         uint8_t f = w.flags[base + i];
-        c_loc += (f & 1) ? 1.0f : 0.0f;
-        c_conf += (f & 2) ? 1.0f : 0.0f;
-        if (do_loc) hsum += w.hub[base + i];
+        s_flag[i] = f;
+        acc.x += (f & 1) ? 1.0f : 0.0f;
+        acc.y += (f & 2) ? 1.0f : 0.0f;
+        if (do_loc) acc.z += w.hub[base + i];
         if (do_conf) s_key[i] = order_key(w.masked[base + i]);
     }
-    const float n_pos_loc = block_sum(c_loc, s_red);
-    const float n_pos_conf = block_sum(c_conf, s_red);
+    acc = block_sum3(acc, s_red3);
+    const float n_pos_loc = acc.x, n_pos_conf = acc.y;
     if (do_loc) {
-        float total = block_sum(hsum, s_red);
         float div = (n_pos_loc == 0.0f) ? 1.0f : n_pos_loc;       // :51-55
         if (tid == 0) {
-            out_loc[b] = fmul(fdiv(total, div), alpha);            // :56-57
+            out_loc[b] = fmul(fdiv(acc.z, div), alpha);            // :56-57
             w.npos_loc[b] = div;
         }
     }
@@ -220,17 +215,38 @@ loss_select_kernel(int N, float neg_pos_ratio, float alpha, bool do_loc, bool do
                 uint32_t digit = in ? ((s_key[i] >> shift) & 255u) : 256u;
                 // warp-aggregated histogram update
                 uint32_t peers = __match_any_sync(0xffffffffu, digit);
-                if (in && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[digit], __popc(peers));
+                if (in && lane == __ffs(peers) - 1) atomicAdd(&s_hist[digit], __popc(peers));
             }
             __syncthreads();
-            if (tid == 0) {
-                int rem = s_remaining, d = 255, acc = 0;
-                for (; d > 0; --d) {
-                    if (acc + s_hist[d] >= rem) break;
-                    acc += s_hist[d];
+            if (wid == 0) {
+                // bins from the top: lane l owns bins 255-8l .. 248-8l; suffix counts by shuffle scan
+                const int rem = s_remaining;
+                int h[8], t = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { h[q] = s_hist[255 - 8 * lane - q]; t += h[q]; }
+                int incl = t;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int u = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += u;
                 }
-                s_remaining = rem - acc;
-                s_prefix = prefix | ((uint32_t)d << shift);
+                const int before = incl - t;          // keys in strictly higher bins than this lane's
+                // the digit d is the highest bin with (count of keys in bins > d) + hist[d] >= rem;
+                // if no bin satisfies it the digit is 0 (cannot happen while rem <= matching keys)
+                const bool owner = before < rem && incl >= rem;
+                const bool none = __ballot_sync(0xffffffffu, owner) == 0u;
+                if (owner) {
+                    int a = before, d = 255 - 8 * lane;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (a + h[q] >= rem) { d = 255 - 8 * lane - q; break; }
+                        a += h[q];
+                    }
+                    s_remaining = rem - a;
+                    s_prefix = prefix | ((uint32_t)d << shift);
+                } else if (none && lane == 0) {
+                    s_prefix = prefix;                // unreachable (rem never exceeds the matching keys): digit 0
+                }
             }
             mask |= 255u << shift;
             __syncthreads();
@@ -246,7 +262,6 @@ loss_select_kernel(int N, float neg_pos_ratio, float alpha, bool do_loc, bool do
     if (k > 0 && k < N)
         for (int i = lo; i < hi; ++i) my_eq += (s_key[i] == T);
     int incl = my_eq;
-    const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         int t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -275,7 +290,7 @@ loss_select_kernel(int N, float neg_pos_ratio, float alpha, bool do_loc, bool do
             uint32_t key = s_key[i];
             neg = key > T ? 1 : (key == T ? (eq_rank++ < need_eq ? 1 : 0) : 0);
         }
-        int fm = neg + ((w.flags[base + i] & 2) ? 1 : 0);         // :84
+        int fm = neg + ((s_flag[i] & 2) ? 1 : 0);                  // :84
         w.fmask[base + i] = (uint8_t)fm;
         if (fm) total = fadd(total, fmul((float)fm, w.ce[base + i]));    // :85
     }
@@ -293,17 +308,18 @@ loss_bwd_kernel(const float4* __restrict__ act_d, const float4* __restrict__ pre
                 const float* __restrict__ act_l, const float* __restrict__ logits,
                 int N, int L, float alpha, float gscale, LossWs w,
                 float4* __restrict__ g_d, float* __restrict__ g_z) {
-    extern __shared__ float s_rows[];
+    extern __shared__ __align__(16) float s_rows[];
     const int b = blockIdx.y;
     const int n0 = blockIdx.x * kRowThreads;
     const int cnt = min(kRowThreads, N - n0);
     const size_t row0 = (size_t)b * N + n0;
+    const int region = kRowThreads * L + 4;
     float* s_y = s_rows;
-    float* s_z = s_rows + (size_t)kRowThreads * L;
+    float* s_z = s_rows + region;
     const bool do_conf = g_z != nullptr;
     if (do_conf) {
-        stage_in(act_l + row0 * L, cnt * L, s_y);
-        stage_in(logits + row0 * L, cnt * L, s_z);
+        s_y = stage_rows_in(act_l + row0 * L, cnt * L, s_rows);
+        s_z = stage_rows_in(logits + row0 * L, cnt * L, s_rows + region);   // g_z + row0*L is misaligned like logits
         __syncthreads();
     }
     if ((int)threadIdx.x < cnt) {
@@ -332,7 +348,12 @@ loss_bwd_kernel(const float4* __restrict__ act_d, const float4* __restrict__ pre
     }
     if (do_conf) {
         __syncthreads();
-        stage_out(g_z + row0 * L, cnt * L, s_z);
+        float* dst = g_z + row0 * L;
+        if (stage_rows_ptr(dst, s_rows + region) == s_z) {
+            stage_rows_out(dst, cnt * L, s_z);
+        } else {
+            for (int e = threadIdx.x; e < cnt * L; e += blockDim.x) __stcs(dst + e, s_z[e]);
+        }
     }
 }
 
@@ -367,7 +388,7 @@ extern "C" int ssd_loss_fwd(const float* d_actual_deltas, const float* d_pred_de
     loss_ws_layout(B, N, &w, d_workspace);
     cudaStream_t st = as_stream(stream);
 
-    size_t smem1 = do_conf ? (size_t)2 * kRowThreads * L * sizeof(float) : 0;
+    size_t smem1 = do_conf ? (size_t)2 * (kRowThreads * L + 4) * sizeof(float) : 0;
     SSD_REQUIRE(smem1 <= 200 * 1024, SSD_ERR_UNSUPPORTED, "ssd_loss_fwd: L=%d too large for row staging", L);
     dim3 grid1(ceil_div(N, kRowThreads), B);
     auto launch1 = [&](auto kern) {
@@ -380,9 +401,9 @@ extern "C" int ssd_loss_fwd(const float* d_actual_deltas, const float* d_pred_de
     if (from_logits) launch1(loss_anchor_kernel<true>); else launch1(loss_anchor_kernel<false>);
     SSD_CHECK_LAUNCH("loss_anchor_kernel");
 
-    size_t smem2 = do_conf ? (size_t)N * sizeof(uint32_t) : 0;
+    size_t smem2 = (size_t)N * (sizeof(uint32_t) + 1) + 16;
     SSD_REQUIRE(smem2 <= 200 * 1024, SSD_ERR_UNSUPPORTED,
-                "ssd_loss_fwd: N=%d anchors exceed the per-image shared-memory select (max 51200)", N);
+                "ssd_loss_fwd: N=%d anchors exceed the per-image shared-memory select (max 40000)", N);
     if (smem2 > 40 * 1024)
         cudaFuncSetAttribute(loss_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     loss_select_kernel<<<B, kSelThreads, smem2, st>>>(N, neg_pos_ratio, loc_loss_alpha, do_loc, do_conf, w,
@@ -409,7 +430,7 @@ extern "C" int ssd_loss_bwd(const float* d_actual_deltas, const float* d_pred_de
                 "ssd_loss_bwd: workspace %zu < required %zu bytes", workspace_bytes, need);
     LossWs w;
     loss_ws_layout(B, N, &w, const_cast<void*>(d_workspace));
-    size_t smem = do_conf ? (size_t)2 * kRowThreads * L * sizeof(float) : 0;
+    size_t smem = do_conf ? (size_t)2 * (kRowThreads * L + 4) * sizeof(float) : 0;
     SSD_REQUIRE(smem <= 200 * 1024, SSD_ERR_UNSUPPORTED, "ssd_loss_bwd: L=%d too large for row staging", L);
     if (smem > 40 * 1024)
         cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

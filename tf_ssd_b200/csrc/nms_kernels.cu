@@ -35,29 +35,16 @@ __device__ __forceinline__ float unorder_bits(uint32_t o) {
     return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
 }
 
-__device__ __forceinline__ void stage_rows(const float* __restrict__ src, int total, float* __restrict__ s) {
-    const int head = min(total, (int)((4 - (((uintptr_t)src >> 2) & 3)) & 3));
-    const int nvec = (total - head) >> 2;
-    for (int e = threadIdx.x; e < head; e += blockDim.x) s[e] = __ldcs(src + e);
-    const float4* v = reinterpret_cast<const float4*>(src + head);
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        float4 t = __ldcs(v + i);
-        float* d = s + head + (i << 2);
-        d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
-    }
-    for (int e = head + (nvec << 2) + threadIdx.x; e < total; e += blockDim.x) s[e] = __ldcs(src + e);
-}
-
 // ---------------------------------------------------------------- softmax --
 __global__ void __launch_bounds__(kRowThreadsNms)
 softmax_kernel(const float* __restrict__ logits, int64_t rows, int L, float* __restrict__ probs) {
-    extern __shared__ float s_rows[];
+    extern __shared__ __align__(16) float s_rows[];
     for (int64_t r0 = (int64_t)blockIdx.x * kRowThreadsNms; r0 < rows; r0 += (int64_t)gridDim.x * kRowThreadsNms) {
         const int cnt = (int)min((int64_t)kRowThreadsNms, rows - r0);
-        stage_rows(logits + r0 * L, cnt * L, s_rows);
+        float* rows = stage_rows_in(logits + r0 * L, cnt * L, s_rows);   // probs + r0*L has the same misalignment
         __syncthreads();
         if ((int)threadIdx.x < cnt) {
-            float* z = s_rows + (size_t)threadIdx.x * L;
+            float* z = rows + (size_t)threadIdx.x * L;
             float m = z[0];
             for (int l = 1; l < L; ++l) m = fmaxf(m, z[l]);
             float s = 0.0f;
@@ -66,15 +53,11 @@ softmax_kernel(const float* __restrict__ logits, int64_t rows, int L, float* __r
         }
         __syncthreads();
         float* dst = probs + r0 * L;
-        const int total = cnt * L;
-        const int head = min(total, (int)((4 - (((uintptr_t)dst >> 2) & 3)) & 3));
-        const int nvec = (total - head) >> 2;
-        for (int e = threadIdx.x; e < head; e += blockDim.x) dst[e] = s_rows[e];
-        for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-            const float* d = s_rows + head + (i << 2);
-            __stcs(reinterpret_cast<float4*>(dst + head) + i, make_float4(d[0], d[1], d[2], d[3]));
+        if (stage_rows_ptr(dst, s_rows) == rows) {
+            stage_rows_out(dst, cnt * L, rows);
+        } else {                                          // input and output misaligned differently: scalar stores
+            for (int e = threadIdx.x; e < cnt * L; e += blockDim.x) __stcs(dst + e, rows[e]);
         }
-        for (int e = head + (nvec << 2) + threadIdx.x; e < total; e += blockDim.x) dst[e] = s_rows[e];
         __syncthreads();
     }
 }
@@ -86,36 +69,63 @@ template <bool DECODER, bool FROM_LOGITS>
 __global__ void __launch_bounds__(kRowThreadsNms)
 nms_candidates_kernel(const float* __restrict__ scores, int N, int L, float score_thr, int cap,
                       uint64_t* __restrict__ keys, int key_stride, int* __restrict__ counts) {
-    extern __shared__ float s_rows[];
+    extern __shared__ __align__(16) float s_rows[];
+    __shared__ int s_warp_tot[kRowThreadsNms / 32];
+    __shared__ int s_base;
     const int b = blockIdx.y;
     const int n0 = blockIdx.x * kRowThreadsNms;
     const int cnt = min(kRowThreadsNms, N - n0);
-    stage_rows(scores + ((size_t)b * N + n0) * L, cnt * L, s_rows);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* rows = stage_rows_in(scores + ((size_t)b * N + n0) * L, cnt * L, s_rows);
     __syncthreads();
-    if ((int)threadIdx.x >= cnt) return;
-    float* p = s_rows + (size_t)threadIdx.x * L;
-    if (FROM_LOGITS) {                                   // models/header.py:88 fused in
-        float m = p[0];
-        for (int l = 1; l < L; ++l) m = fmaxf(m, p[l]);
-        float s = 0.0f;
-        for (int l = 0; l < L; ++l) { float e = expf(fsub(p[l], m)); p[l] = e; s = fadd(s, e); }
-        for (int l = 0; l < L; ++l) p[l] = fdiv(p[l], s);
+    float* p = rows + (size_t)threadIdx.x * L;
+    int mine = 0;                                        // candidates of this anchor
+    if ((int)threadIdx.x < cnt) {
+        if (FROM_LOGITS) {                               // models/header.py:88 fused in
+            float m = p[0];
+            for (int l = 1; l < L; ++l) m = fmaxf(m, p[l]);
+            float s = 0.0f;
+            for (int l = 0; l < L; ++l) { float e = expf(fsub(p[l], m)); p[l] = e; s = fadd(s, e); }
+            for (int l = 0; l < L; ++l) p[l] = fdiv(p[l], s);
+        }
+        bool alive = true;
+        if (DECODER) {                                   // decoder.py:78-83: argmax == 0 zeroes the row
+            int am = 0;
+            float best = p[0];
+            for (int l = 1; l < L; ++l)
+                if (p[l] > best) { best = p[l]; am = l; }
+            alive = am != 0;
+        }
+        if (alive)
+            for (int l = 0; l < L; ++l) mine += (p[l] > score_thr) ? 1 : 0;      // strict, like TensorFlow
     }
-    if (DECODER) {                                       // decoder.py:78-83
-        int am = 0;
-        float best = p[0];
-        for (int l = 1; l < L; ++l)
-            if (p[l] > best) { best = p[l]; am = l; }
-        if (am == 0) return;
+    // One global reservation per CTA: exclusive scan of the per-anchor counts, a single
+    // atomicAdd for the CTA's total (the previous per-candidate atomics serialised on one
+    // address per image and stalled every warp for a full L2 round trip each).
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
     }
+    if (lane == 31) s_warp_tot[wid] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < kRowThreadsNms / 32; ++w) { int t = s_warp_tot[w]; s_warp_tot[w] = tot; tot += t; }
+        s_base = tot ? atomicAdd(counts + b, tot) : 0;
+    }
+    __syncthreads();
+    if (mine == 0) return;
+    int slot = s_base + s_warp_tot[wid] + incl - mine;
     const uint32_t anchor = (uint32_t)(n0 + threadIdx.x);
+    uint64_t* dst = keys + (size_t)b * key_stride;
     for (int l = 0; l < L; ++l) {
         float sc = p[l];
-        if (sc > score_thr) {                            // strict, like TensorFlow
-            int slot = atomicAdd(counts + b, 1);
-            if (slot < cap)
-                keys[(size_t)b * key_stride + slot] =
-                    ((uint64_t)l << 56) | ((uint64_t)(~order_bits(sc)) << 24) | anchor;
+        if (sc > score_thr) {
+            if (slot < cap) dst[slot] = ((uint64_t)l << 56) | ((uint64_t)(~order_bits(sc)) << 24) | anchor;
+            ++slot;
         }
     }
 }
@@ -186,12 +196,17 @@ struct NmsParams {
     int key_stride;            // u64 slots per image in `keys` (power of two >= cap)
     int merge_stride;          // u64 slots per image in `merge` (power of two >= L*per_class)
     int smem_sort_slots;       // u64 slots of the shared sort buffer
-    int kept_in_smem;          // kept-box cache lives in shared memory (else workspace)
+    int fast_slots;            // > 0: shared box cache (float4 per candidate) + u16 kept lists are available
     float iou_thr;
     int clip;
     int labels_first;          // output order: decoder (boxes, labels, scores) vs TF (boxes, scores, classes)
 };
 
+// One CTA per image.  Fast path (candidate count <= fast_slots): keys, the decoded
+// candidate boxes (decoded once, cooperatively, in sorted order) and the per-class kept
+// lists all live in shared memory, so the serial greedy loop of a class touches no
+// global memory.  Slow path (rare overflow): keys sorted in the global workspace, boxes
+// fetched on demand, kept boxes in the workspace.
 template <typename Fetch>
 __global__ void __launch_bounds__(kNmsThreads)
 nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t* __restrict__ merge,
@@ -200,7 +215,8 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
                  int32_t* __restrict__ out_valid) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     uint64_t* s_sort = reinterpret_cast<uint64_t*>(s_raw);
-    float4* s_kept = reinterpret_cast<float4*>(s_raw + (size_t)P.smem_sort_slots * 8);
+    float4*   s_box  = reinterpret_cast<float4*>(s_raw + (size_t)P.smem_sort_slots * 8);
+    uint16_t* s_kidx = reinterpret_cast<uint16_t*>(s_raw + (size_t)P.smem_sort_slots * 8 + (size_t)P.fast_slots * 16);
     __shared__ int s_seg_start[257];
     __shared__ int s_mcount;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -222,6 +238,7 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
     const int P1 = pow2_ceil(M);
     uint64_t* gk = keys + (size_t)b * P.key_stride;
     uint64_t* cand = (P1 <= P.smem_sort_slots) ? s_sort : gk;
+    const bool fast = P1 <= P.fast_slots;
     if (cand == s_sort) {
         for (int i = tid; i < P1; i += kNmsThreads) s_sort[i] = (i < M) ? gk[i] : kPadKey;
     } else {
@@ -232,53 +249,71 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
     __syncthreads();
     if (M > 1) bitonic_sort(cand, P1);
 
-    // ---- 2. class segments ---------------------------------------------------
+    // ---- 2. class segments; decode every candidate box once (fast path) ------
     for (int i = tid; i < M; i += kNmsThreads) {
-        int c = (int)(cand[i] >> 56);
+        const uint64_t key = cand[i];
+        const int c = (int)(key >> 56);
         if (i == 0 || (int)(cand[i - 1] >> 56) != c) s_seg_start[c] = i;
+        if (fast) s_box[i] = fetch(b, (int)(key & 0xFFFFFFu), c);
     }
     __syncthreads();
 
     // ---- 3. greedy suppression, one warp per class ---------------------------
     uint64_t* mk = merge + (size_t)b * P.merge_stride;
     for (int c = wid; c < P.L; c += nwarps) {
-        int start = s_seg_start[c];
+        const int start = s_seg_start[c];
         if (start < 0) continue;
-        float4* kept = P.kept_in_smem ? s_kept + (size_t)wid * P.per_class
-                                      : kept_ws + ((size_t)b * P.L + c) * P.per_class;
         int nk = 0;
-        for (int i = start; i < M && nk < P.per_class; ++i) {
-            uint64_t key = cand[i];
-            if ((int)(key >> 56) != c) break;
-            int anchor = (int)(key & 0xFFFFFFu);
-            float4 box = fetch(b, anchor, c);
-            bool sup = false;
-            for (int j = lane; j < nk; j += 32) {
-                float4 kb = P.kept_in_smem ? kept[j] : __ldcg(kept + j);   // workspace copy: bypass L1
-                sup |= nms_iou(box, kb) > P.iou_thr;
-            }
-            sup = __any_sync(0xffffffffu, sup);
-            if (!sup) {
-                if (lane == 0) {
-                    kept[nk] = box;
-                    int slot = atomicAdd(&s_mcount, 1);
-                    uint32_t inv_score = (uint32_t)((key >> 24) & 0xFFFFFFFFu);
-                    mk[slot] = ((uint64_t)inv_score << 32) | ((uint64_t)c << 24) | (uint32_t)anchor;
+        if (fast) {
+            uint16_t* kidx = s_kidx + (size_t)wid * P.per_class;
+            for (int i = start; i < M && nk < P.per_class; ++i) {
+                const uint64_t key = cand[i];
+                if ((int)(key >> 56) != c) break;
+                const float4 box = s_box[i];
+                bool sup = false;
+                for (int j = lane; j < nk; j += 32) sup |= nms_iou(box, s_box[kidx[j]]) > P.iou_thr;
+                if (!__any_sync(0xffffffffu, sup)) {
+                    if (lane == 0) {
+                        kidx[nk] = (uint16_t)i;
+                        const int slot = atomicAdd(&s_mcount, 1);
+                        const uint32_t inv_score = (uint32_t)((key >> 24) & 0xFFFFFFFFu);
+                        mk[slot] = ((uint64_t)inv_score << 32) | ((uint64_t)c << 24) | (uint32_t)(key & 0xFFFFFFu);
+                    }
+                    ++nk;
+                    __syncwarp();
                 }
-                ++nk;
-                __syncwarp();
+            }
+        } else {
+            float4* kept = kept_ws + ((size_t)b * P.L + c) * P.per_class;
+            for (int i = start; i < M && nk < P.per_class; ++i) {
+                const uint64_t key = cand[i];
+                if ((int)(key >> 56) != c) break;
+                const int anchor = (int)(key & 0xFFFFFFu);
+                const float4 box = fetch(b, anchor, c);
+                bool sup = false;
+                for (int j = lane; j < nk; j += 32) sup |= nms_iou(box, __ldcg(kept + j)) > P.iou_thr;   // bypass L1
+                if (!__any_sync(0xffffffffu, sup)) {
+                    if (lane == 0) {
+                        kept[nk] = box;
+                        const int slot = atomicAdd(&s_mcount, 1);
+                        const uint32_t inv_score = (uint32_t)((key >> 24) & 0xFFFFFFFFu);
+                        mk[slot] = ((uint64_t)inv_score << 32) | ((uint64_t)c << 24) | (uint32_t)anchor;
+                    }
+                    ++nk;
+                    __syncwarp();
+                }
             }
         }
     }
+    __threadfence_block();
     __syncthreads();
 
     // ---- 4. merge: score desc, class asc, anchor asc; first max_total --------
     const int K = s_mcount;
     const int P2 = pow2_ceil(K);
     uint64_t* ms = (P2 <= P.smem_sort_slots) ? s_sort : mk;
-    __threadfence_block();
     if (ms == s_sort) {
-        for (int i = tid; i < P2; i += kNmsThreads) s_sort[i] = (i < K) ? mk[i] : kPadKey;
+        for (int i = tid; i < P2; i += kNmsThreads) s_sort[i] = (i < K) ? __ldcg(mk + i) : kPadKey;
     } else {
         for (int i = K + tid; i < P2; i += kNmsThreads) mk[i] = kPadKey;
     }
@@ -338,13 +373,12 @@ static int make_plan(int B, int N, int L, int per_class, int max_total, int64_t 
     p.N = N; p.L = L; p.per_class = per_class; p.max_total = max_total; p.cap = (int)cap64;
     p.key_stride = host_pow2_ceil(cap64);
     p.merge_stride = host_pow2_ceil((int64_t)L * per_class);
-    p.smem_sort_slots = min(8192, max(p.key_stride, p.merge_stride));
-    const int nwarps_active = min(kNmsThreads / 32, L);
-    size_t kept_bytes = (size_t)(kNmsThreads / 32) * per_class * 16;
-    (void)nwarps_active;
-    size_t sort_bytes = (size_t)p.smem_sort_slots * 8;
-    p.kept_in_smem = (sort_bytes + kept_bytes <= 200 * 1024) ? 1 : 0;
-    plan->smem = sort_bytes + (p.kept_in_smem ? kept_bytes : 0);
+    p.smem_sort_slots = min(4096, max(p.key_stride, p.merge_stride));
+    // fast path: 8 B key + 16 B box per slot + u16 kept lists; 4096 slots with per_class = 200 is
+    // 109 KB, i.e. two resident CTAs per SM
+    p.fast_slots = (per_class <= 256) ? p.smem_sort_slots : 0;
+    plan->smem = (size_t)p.smem_sort_slots * 8 + (size_t)p.fast_slots * 16 +
+                 (p.fast_slots ? (size_t)(kNmsThreads / 32) * per_class * 2 : 0);
     plan->ws_bytes = nms_ws_layout(max(B, 1), p.key_stride, p.merge_stride, L, per_class, nullptr, nullptr);
     return SSD_OK;
 }
@@ -369,7 +403,7 @@ extern "C" int ssd_softmax(const float* d_logits, int64_t rows, int L, float* d_
     SSD_REQUIRE_PTR(d_logits); SSD_REQUIRE_PTR(d_probs);
     SSD_REQUIRE(rows >= 0 && L >= 1, SSD_ERR_SHAPE, "ssd_softmax: bad shape rows=%lld L=%d", (long long)rows, L);
     if (rows == 0) return SSD_OK;
-    size_t smem = (size_t)kRowThreadsNms * L * sizeof(float);
+    size_t smem = ((size_t)kRowThreadsNms * L + 4) * sizeof(float);
     SSD_REQUIRE(smem <= 200 * 1024, SSD_ERR_UNSUPPORTED, "ssd_softmax: L=%d too large for row staging", L);
     if (smem > 40 * 1024)
         cudaFuncSetAttribute(softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -412,7 +446,7 @@ extern "C" int ssd_decode_nms(const float* d_priors, const float* d_pred_deltas,
     cudaError_t e = cudaMemsetAsync(w.counts, 0, (size_t)B * 4, st);
     if (e != cudaSuccess) return cuda_fail(e, "ssd_decode_nms: memset");
 
-    size_t smem = (size_t)kRowThreadsNms * L * sizeof(float);
+    size_t smem = ((size_t)kRowThreadsNms * L + 4) * sizeof(float);
     SSD_REQUIRE(smem <= 200 * 1024, SSD_ERR_UNSUPPORTED, "ssd_decode_nms: L=%d too large", L);
     dim3 grid(ceil_div(N, kRowThreadsNms), B);
     auto launch = [&](auto kern) {
@@ -460,7 +494,7 @@ extern "C" int ssd_combined_nms(const float* d_boxes, const float* d_scores, int
     cudaError_t e = cudaMemsetAsync(w.counts, 0, (size_t)B * 4, st);
     if (e != cudaSuccess) return cuda_fail(e, "ssd_combined_nms: memset");
 
-    size_t smem = (size_t)kRowThreadsNms * L * sizeof(float);
+    size_t smem = ((size_t)kRowThreadsNms * L + 4) * sizeof(float);
     SSD_REQUIRE(smem <= 200 * 1024, SSD_ERR_UNSUPPORTED, "ssd_combined_nms: L=%d too large", L);
     dim3 grid(ceil_div(N, kRowThreadsNms), B);
     auto kern = nms_candidates_kernel<false, false>;

@@ -47,7 +47,7 @@ def make_ground_truth(batch: int, padded: int = 16, max_boxes: int = 8, n_classe
 
 
 def make_head_outputs(batch: int, n_anchors: int, n_labels: int = 21, seed: int = 1234, hot_fraction: float = 0.02,
-                      hot_boost: float = 8.0) -> Tuple[np.ndarray, np.ndarray]:
+                      hot_boost: float = 8.0, background_bias: float = 0.0) -> Tuple[np.ndarray, np.ndarray]:
     """``(pred_deltas [B,N,4], logits [B,N,L])``: logits N(0, 2^2) with
     ``hot_fraction`` of the anchors boosted on one random foreground class so a
     realistic number of NMS candidates (tens to hundreds per image) appears."""
@@ -58,4 +58,8 @@ def make_head_outputs(batch: int, n_anchors: int, n_labels: int = 21, seed: int 
     cls = rng.integers(1, n_labels, (batch, n_anchors))
     bi, ni = np.nonzero(hot)
     logits[bi, ni, cls[bi, ni]] += np.float32(hot_boost)
+    if background_bias:
+        # detector-like: background dominates everywhere but on the hot anchors
+        logits[..., 0] += np.float32(background_bias)
+        logits[bi, ni, 0] -= np.float32(background_bias)
     return deltas, logits

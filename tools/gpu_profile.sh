@@ -1,0 +1,29 @@
+#!/bin/bash
+# Runs on the GPU box (via gpurun): ncu captures -> small CSV summaries in gpurun_out/.
+# usage: tools/gpu_profile.sh <tag> [box] [launches] [conv]
+set -u
+tag=$1; shift
+OUT=gpurun_out
+mkdir -p $OUT
+METRICS='gpu__time_duration.sum|dram__bytes_read.sum |dram__bytes_write.sum |dram__throughput.avg.pct_of_peak_sustained_elapsed|sm__throughput.avg.pct_of_peak_sustained_elapsed|sm__warps_active.avg.pct_of_peak_sustained_active|launch__registers_per_thread|launch__grid_size|launch__block_size|sm__pipe_tensor_cycles_active|sm__inst_executed_pipe_tensor|smsp__cycles_active.avg|l1tex__t_bytes|lts__t_bytes.sum |launch__occupancy_limit|smsp__average_warp.*_per_issue_active|sm__pipe_tensor_op_hmma_cycles_active'
+for what in "$@"; do
+  case $what in
+    box)
+      ncu --set full --clock-control none --import-source on -k regex:"iou_map|match_encode|loss_|nms_" \
+          -o $OUT/box_$tag python tools/prof_box.py > $OUT/prof_box_$tag.log 2>&1
+      ncu -i $OUT/box_$tag.ncu-rep --page raw --csv > $OUT/box_${tag}_raw.csv 2>/dev/null
+      ncu -i $OUT/box_$tag.ncu-rep --page details --csv > $OUT/box_${tag}_details.csv 2>/dev/null
+      ;;
+    launches)
+      ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$tag.csv \
+          python bench.py --steps 2 --warmup 3 --skip-cpu --skip-box > $OUT/launches_$tag.log 2>&1
+      ;;
+    conv)
+      ncu --set full --clock-control none --import-source on -k regex:"conv_|gemm_|depthwise" -s 138 -c 69 \
+          -o $OUT/conv_$tag python bench.py --steps 1 --warmup 3 --skip-cpu --skip-box > $OUT/conv_$tag.log 2>&1
+      ncu -i $OUT/conv_$tag.ncu-rep --page raw --csv > $OUT/conv_${tag}_raw.csv 2>/dev/null
+      rm -f $OUT/conv_$tag.ncu-rep
+      ;;
+  esac
+done
+ls -la $OUT; du -sh $OUT
