@@ -146,6 +146,7 @@ __device__ __forceinline__ bool gt_culled(const float4 q, float q_area, float wy
     return (q.z <= wy1 || q.x >= wy2 || q.w <= wx1 || q.y >= wx2) && q_area >= 0.0f;
 }
 
+template <int NCH>                                   // NCH = ceil(G / 32) chunks of ground-truth boxes
 __global__ void __launch_bounds__(kIouTileWarps * 32)
 iou_map_tile_kernel(const float4* __restrict__ boxes, const float4* __restrict__ gt, int N, int G, int pitch,
                     int boxes_batched, float* __restrict__ out) {
@@ -172,37 +173,36 @@ iou_map_tile_kernel(const float4* __restrict__ boxes, const float4* __restrict__
         const float wy1 = warp_min_f(p.x), wx1 = warp_min_f(p.y), wy2 = warp_max_f(p.z), wx2 = warp_max_f(p.w);
         const bool can_cull = __all_sync(0xffffffffu, !valid || pa > 0.0f);
         float* row = tile + lane * pitch;
-        uint32_t hitmask[kIouTileMaxG / 32];             // warp-uniform: which boxes were evaluated
+        uint32_t hitmask[NCH];                           // warp-uniform: which boxes were evaluated
 #pragma unroll
-        for (int k = 0; k < kIouTileMaxG / 32; ++k) {
-            hitmask[k] = 0u;
+        for (int k = 0; k < NCH; ++k) {
             const int g0 = k << 5;
-            if (g0 < G) {
-                const int g = g0 + lane;
-                bool hit = g < G;
-                if (can_cull && hit) hit = !gt_culled(s_gt[g], s_area[g], wy1, wx1, wy2, wx2);
-                uint32_t m = __ballot_sync(0xffffffffu, hit);
-                hitmask[k] = m;
-                while (m) {
-                    const int gg = g0 + __ffs(m) - 1;
-                    m &= m - 1;
-                    row[gg] = iou_ref(p, pa, s_gt[gg], s_area[gg]);
-                }
+            const int g = g0 + lane;
+            bool hit = g < G;
+            if (can_cull && hit) hit = !gt_culled(s_gt[g], s_area[g], wy1, wx1, wy2, wx2);
+            uint32_t m = __ballot_sync(0xffffffffu, hit);
+            hitmask[k] = m;
+            while (m) {
+                const int gg = g0 + __ffs(m) - 1;
+                m &= m - 1;
+                row[gg] = iou_ref(p, pa, s_gt[gg], s_area[gg]);
             }
         }
         __syncwarp();
-        // row by row: lanes cover consecutive columns, so every store instruction writes one
-        // contiguous run of the output; culled columns are +0 without touching shared memory
-        const int rows = min(32, N - n0);
+        // The tile's outputs are one contiguous run of rows*G floats: lane f, f+32, ... so every
+        // store instruction writes 128 contiguous bytes; (row, column) advance incrementally and
+        // culled columns are +0 without touching shared memory.
+        const int total = min(32, N - n0) * G;
         float* dst = o + (size_t)n0 * G;
-        for (int r = 0; r < rows; ++r) {
-            const float* trow = tile + r * pitch;
-            float* drow = dst + (size_t)r * G;
+        const int dr = 32 / G, dc = 32 - dr * G;
+        int r = lane / G, c = lane - r * G;
+        for (int f = lane; f < total; f += 32) {
+            uint32_t hm = hitmask[0];
 #pragma unroll
-            for (int k = 0; k < kIouTileMaxG / 32; ++k) {
-                const int c = (k << 5) + lane;
-                if (c < G) __stcs(drow + c, ((hitmask[k] >> lane) & 1u) ? trow[c] : 0.0f);
-            }
+            for (int k = 1; k < NCH; ++k) hm = (c >> 5) == k ? hitmask[k] : hm;
+            __stcs(dst + f, ((hm >> (c & 31)) & 1u) ? tile[r * pitch + c] : 0.0f);
+            r += dr; c += dc;
+            if (c >= G) { c -= G; ++r; }
         }
         __syncwarp();
     }
@@ -419,13 +419,16 @@ extern "C" int ssd_iou_map(const float* d_boxes, const float* d_gt, int B, int N
     if (G <= kIouTileMaxG) {
         const int pitch = G | 1;                                   // odd pitch: conflict-free column writes
         size_t smem_t = (size_t)G * 20 + (size_t)kIouTileWarps * 32 * pitch * sizeof(float);
+        const int nch = (G + 31) / 32;
+        auto kern = nch == 1 ? iou_map_tile_kernel<1> : nch == 2 ? iou_map_tile_kernel<2>
+                  : nch == 3 ? iou_map_tile_kernel<3> : iou_map_tile_kernel<4>;
         if (smem_t > 40 * 1024)
-            cudaFuncSetAttribute(iou_map_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
         const int ntiles = (N + 31) / 32;
         const int per_img = (ntiles + kIouTileWarps - 1) / kIouTileWarps;
         const int cap = max(1, (sm_count() * 16 + B - 1) / B);
         dim3 grid(min(per_img, cap), B);
-        iou_map_tile_kernel<<<grid, kIouTileWarps * 32, smem_t, as_stream(stream)>>>(
+        kern<<<grid, kIouTileWarps * 32, smem_t, as_stream(stream)>>>(
             reinterpret_cast<const float4*>(d_boxes), reinterpret_cast<const float4*>(d_gt), N, G, pitch,
             boxes_batched, d_out);
         SSD_CHECK_LAUNCH("iou_map_tile_kernel");

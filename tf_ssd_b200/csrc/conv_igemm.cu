@@ -13,6 +13,9 @@
 
 #include "common.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
 namespace ssd {
 
 constexpr int BK = 32;            // k-chunk: 32 halfs = 64 B per row = 4 x 16-byte pieces
@@ -251,6 +254,20 @@ static int launch_conv(const ConvK& k, cudaStream_t st) {
     return SSD_OK;
 }
 
+// conv_tcgen05.cu
+bool conv_tcgen05_supported(const ssd_conv_desc* d);
+int  conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st);
+
+// SSD_B200_CONV=legacy forces the mma.sync kernel for every convolution (A/B measurements, cross-checks).
+static bool force_legacy_conv() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SSD_B200_CONV");
+        v = (e && strcmp(e, "legacy") == 0) ? 1 : 0;
+    }
+    return v == 1;
+}
+
 }  // namespace ssd
 
 using namespace ssd;
@@ -278,6 +295,7 @@ extern "C" int ssd_conv2d(const ssd_conv_desc* d, ssd_stream_t stream) {
     k.chunks_per_tap = (d->Cin + BK - 1) / BK;
     k.n_chunks = k.chunks_per_tap * d->KH * d->KW;
     cudaStream_t st = as_stream(stream);
+    if (!force_legacy_conv() && conv_tcgen05_supported(d)) return conv_tcgen05_launch(d, st);
 
     // Tile choice: narrow N tiles for the thin MobileNetV2 projections, smaller M
     // tiles when the grid would not cover the 148 SMs.

@@ -1,0 +1,471 @@
+// Blackwell-native convolution for sm_100a: implicit GEMM on the 5th-generation
+// tensor cores.
+//
+//   * operands staged by TMA (cp.async.bulk.tensor) into 128-byte-swizzled
+//     shared-memory tiles; the im2col gather of a 3x3 / dilated convolution is
+//     done BY the TMA unit: a 4-D tensor map over the NHWC activation is read
+//     with the tap's (dy, dx) added to the box coordinates, and out-of-bounds
+//     (padding) elements arrive as zeros;
+//   * tcgen05.mma (kind::f16, M = 128, N = 16..256) issued by one elected
+//     thread, fp32 accumulators in tensor memory (TMEM);
+//   * a 4-stage mbarrier producer/consumer ring (TMA warp -> MMA warp), and a
+//     TMEM-full barrier (MMA warp -> 4 epilogue warps);
+//   * epilogue: tcgen05.ld -> registers -> bias / BatchNorm-folded bias, ReLU /
+//     ReLU6, residual add, fp16 or fp32 stores, optional two-segment strided
+//     output (the multibox head writes straight into the concatenated tensors);
+//   * split-K across blockIdx.z for the head convolutions (tiny M, K up to
+//     11 520): fp32 partials in a workspace + a deterministic fixed-order
+//     reduction kernel that applies the epilogue.
+//
+// Handles every stride-1 Conv2D of the two graphs (1x1, 3x3, dilation 6, SAME /
+// VALID).  Stride-2 convolutions stay on the mma.sync kernel (conv_igemm.cu).
+
+#include "common.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace ssd {
+
+constexpr int TC_BM = 128;           // UMMA M (one CTA, cta_group::1)
+constexpr int TC_BK = 64;            // 64 fp16 = 128 B = one swizzle row
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 192;      // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+
+struct TcParams {
+    int mode4d;                      // 0: A is a 2-D [M, K] matrix (1x1 conv); 1: 4-D im2col boxes
+    int M;                           // B*Ho*Wo
+    int B, Ho, Wo, HoWo;
+    int bw, bh, bb;                  // output-pixel box of one M tile (4-D mode), bw*bh*bb <= 128
+    int tiles_w, tiles_h;            // tiles per image row / column
+    int Cin, KW, dil, pad_t, pad_l;
+    int kb_per_tap;                  // ceil(Cin / 64)
+    int n_kblocks;                   // taps * kb_per_tap
+    int kb_per_split;                // k-blocks handled by one blockIdx.z
+    int Cout, BN;
+    uint32_t a_bytes, b_bytes;       // TMA transaction bytes per stage
+    uint32_t idesc;                  // tcgen05 instruction descriptor
+    uint32_t tmem_cols;
+    // epilogue
+    const float* bias; const __half* res; void* out0; void* out1;
+    int act, out_f32, split;
+    long long img0, pix0, img1, pix1;
+    float* partial;                  // split-K workspace [splits][tiles_m*128][ldp] or nullptr
+    int splits, ldp;
+};
+
+// ------------------------------------------------------------------ PTX glue --
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == SSD_ACT_RELU) return fmaxf(v, 0.0f);
+    if (act == SSD_ACT_RELU6) return fminf(fmaxf(v, 0.0f), 6.0f);
+    return v;
+}
+
+// Output location of tile row r: returns false when the row is padding of the tile.
+__device__ __forceinline__ bool tc_row_to_pixel(const TcParams& p, int tile, int r, int& b, int& pix) {
+    if (!p.mode4d) {
+        int m = tile * TC_BM + r;
+        if (m >= p.M) return false;
+        b = m / p.HoWo;
+        pix = m - b * p.HoWo;
+        return true;
+    }
+    const int per_img = p.tiles_w * p.tiles_h;
+    const int tb = tile / per_img, tr = tile - tb * per_img;
+    const int th = tr / p.tiles_w, tw = tr - th * p.tiles_w;
+    const int dx = r % p.bw, q = r / p.bw, dy = q % p.bh, db = q / p.bh;
+    if (db >= p.bb) return false;
+    b = tb * p.bb + db;
+    const int oy = th * p.bh + dy, ox = tw * p.bw + dx;
+    if (b >= p.B || oy >= p.Ho || ox >= p.Wo) return false;
+    pix = oy * p.Wo + ox;
+    return true;
+}
+
+// Final epilogue for one element (shared by the fused epilogue's generic path and the split-K reduction).
+__device__ __forceinline__ void tc_store_one(const TcParams& p, int b, int pix, int n, float v) {
+    if (p.bias) v += __ldg(p.bias + n);
+    v = apply_act(v, p.act);
+    const bool seg1 = n >= p.split;
+    const size_t off = seg1 ? (size_t)b * p.img1 + (size_t)pix * p.pix1 + (n - p.split)
+                            : (size_t)b * p.img0 + (size_t)pix * p.pix0 + n;
+    void* base = seg1 ? p.out1 : p.out0;
+    if (p.res && !seg1) v += __half2float(p.res[off]);
+    if (p.out_f32) reinterpret_cast<float*>(base)[off] = v;
+    else reinterpret_cast<__half*>(base)[off] = __float2half_rn(v);
+}
+
+// ------------------------------------------------------------------- kernel --
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const TcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // 1024-byte alignment for the 128-byte swizzle atoms
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_stage = TC_BM * TC_BK * 2;                 // 16 KB
+    const uint32_t b_stage = (uint32_t)p.BN * TC_BK * 2;
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + TC_STAGES * a_stage;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + TC_STAGES * b_stage);   // full[S], empty[S], tmem_full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_m = blockIdx.x, n0 = blockIdx.y * p.BN;
+    const int kb0 = blockIdx.z * p.kb_per_split;
+    const int kb1 = min(p.n_kblocks, kb0 + p.kb_per_split);
+    const int nkb = kb1 - kb0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(smem_addr(bars + s), 1);                   // full: one arrive.expect_tx (+ TMA bytes)
+            mbar_init(smem_addr(bars + TC_STAGES + s), 1);       // empty: one tcgen05.commit
+        }
+        mbar_init(smem_addr(bars + 2 * TC_STAGES), 1);           // accumulator ready
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {                                             // this warp owns the TMEM allocation
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_addr(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one elected lane) =====================
+        if (lane == 0) {
+            int b0 = 0, oy0 = 0, ox0 = 0;
+            if (p.mode4d) {
+                const int per_img = p.tiles_w * p.tiles_h;
+                const int tb = tile_m / per_img, tr = tile_m - tb * per_img;
+                const int th = tr / p.tiles_w, tw = tr - th * p.tiles_w;
+                b0 = tb * p.bb; oy0 = th * p.bh; ox0 = tw * p.bw;
+            }
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % TC_STAGES;
+                const uint32_t full = smem_addr(bars + s), empty = smem_addr(bars + TC_STAGES + s);
+                if (i >= TC_STAGES) mbar_wait(empty, ((i / TC_STAGES) - 1) & 1);
+                const int kb = kb0 + i;
+                const int tap = kb / p.kb_per_tap, c0 = (kb - tap * p.kb_per_tap) * TC_BK;
+                mbar_expect_tx(full, p.a_bytes + p.b_bytes);
+                const uint32_t dst_a = smem_addr(sA + (size_t)s * a_stage), dst_b = smem_addr(sB + (size_t)s * b_stage);
+                if (p.mode4d) {
+                    const int ky = tap / p.KW, kx = tap - ky * p.KW;
+                    tma_load_4d(dst_a, &map_a, full, c0, ox0 + kx * p.dil - p.pad_l, oy0 + ky * p.dil - p.pad_t, b0);
+                } else {
+                    tma_load_2d(dst_a, &map_a, full, c0, tile_m * TC_BM);
+                }
+                tma_load_2d(dst_b, &map_b, full, tap * p.Cin + c0, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one elected lane) =====================
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % TC_STAGES;
+                mbar_wait(smem_addr(bars + s), (i / TC_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t da = umma_desc_sw128(smem_addr(sA + (size_t)s * a_stage));
+                const uint64_t db = umma_desc_sw128(smem_addr(sB + (size_t)s * b_stage));
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k)             // UMMA_K = 16: +32 bytes along K inside the swizzle row
+                    umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (i | k) != 0);
+                umma_commit(smem_addr(bars + TC_STAGES + s));    // frees the stage when these MMAs retire
+            }
+            umma_commit(smem_addr(bars + 2 * TC_STAGES));        // accumulator complete
+        }
+    } else {
+        // ===================== epilogue: 4 warps, one TMEM lane quarter each =====================
+        const int q = warp & 3;                                  // tcgen05.ld: warp w may touch lanes 32*(w%4)..+31
+        const int r = q * 32 + lane;
+        mbar_wait(smem_addr(bars + 2 * TC_STAGES), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        int b = 0, pix = 0;
+        const bool row_ok = tc_row_to_pixel(p, tile_m, r, b, pix);
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool fast16 = !p.partial && !p.out_f32 && p.split >= p.Cout && (p.Cout & 7) == 0 && (p.pix0 & 7) == 0 &&
+                            (p.img0 & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.out0) & 15) == 0) &&
+                            (p.res == nullptr || (reinterpret_cast<uintptr_t>(p.res) & 15) == 0);
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+            if (n0 + c0 >= p.Cout) break;                        // warp-uniform
+            uint32_t acc[16];
+            tmem_ld16(trow + (uint32_t)c0, acc);                 // all 32 lanes must execute (sync.aligned)
+            if (!row_ok) continue;
+            if (p.partial) {
+                float* dst = p.partial + ((size_t)blockIdx.z * gridDim.x * TC_BM + (size_t)tile_m * TC_BM + r) * p.ldp + n0 + c0;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
+                                                                      __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
+            } else if (fast16) {
+                const int n = n0 + c0;
+                const size_t off = (size_t)b * p.img0 + (size_t)pix * p.pix0 + n;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (n + h * 8 >= p.Cout) break;
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        v[j] = __uint_as_float(acc[h * 8 + j]);
+                        if (p.bias) v[j] += __ldg(p.bias + n + h * 8 + j);
+                        v[j] = apply_act(v[j], p.act);
+                    }
+                    if (p.res) {
+                        const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + off + h * 8));
+                        const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 f = __half22float2(rh[j]);
+                            v[2 * j] += f.x; v[2 * j + 1] += f.y;
+                        }
+                    }
+                    uint4 o;
+                    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out0) + off + h * 8) = o;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n0 + c0 + j;
+                    if (n < p.Cout) tc_store_one(p, b, pix, n, __uint_as_float(acc[j]));
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// Deterministic split-K reduction + epilogue: partial[z][row][n] summed for z = 0..splits-1 in order.
+__global__ void __launch_bounds__(256)
+conv_splitk_reduce_kernel(const TcParams p, int rows_total) {
+    const int64_t total = (int64_t)rows_total * p.Cout;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(e / p.Cout), n = (int)(e - (int64_t)row * p.Cout);
+        int b, pix;
+        if (!tc_row_to_pixel(p, row / TC_BM, row % TC_BM, b, pix)) continue;
+        float v = 0.0f;
+        for (int z = 0; z < p.splits; ++z) v += p.partial[((size_t)z * rows_total + row) * p.ldp + n];
+        tc_store_one(p, b, pix, n, v);
+    }
+}
+
+// ------------------------------------------------------------------- host side --
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(sym);
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+    auto enc = tensor_map_encoder();
+    if (!enc) return fail(SSD_ERR_UNSUPPORTED, "conv_tcgen05: cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t gdim[4], gstr[3];
+    cuuint32_t bx[4], es[4];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SSD_ERR_UNSUPPORTED, "conv_tcgen05: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return SSD_OK;
+}
+
+// split-K workspace: grown on demand, owned by the library, per device (the only allocation the
+// library makes; it happens outside stream capture because plans are warmed up before capture)
+static float* g_partial[16] = {nullptr};
+static size_t g_partial_bytes[16] = {0};
+
+static int partial_workspace(size_t bytes, float** out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16) return fail(SSD_ERR_UNSUPPORTED, "conv_tcgen05: device index %d out of range", dev);
+    if (g_partial_bytes[dev] < bytes) {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        (void)st;
+        if (g_partial[dev]) cudaFree(g_partial[dev]);
+        size_t want = bytes < ((size_t)64 << 20) ? ((size_t)64 << 20) : bytes;
+        cudaError_t e = cudaMalloc(&g_partial[dev], want);
+        if (e != cudaSuccess) { g_partial[dev] = nullptr; g_partial_bytes[dev] = 0; return cuda_fail(e, "conv_tcgen05: split-K workspace"); }
+        g_partial_bytes[dev] = want;
+    }
+    *out = g_partial[dev];
+    return SSD_OK;
+}
+
+bool conv_tcgen05_supported(const ssd_conv_desc* d) {
+    return d->stride == 1 && d->Cin % 8 == 0 && d->KH == d->KW && d->KH * d->KW <= 49 &&
+           (reinterpret_cast<uintptr_t>(d->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0;
+}
+
+int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    const int taps = d->KH * d->KW;
+    p.mode4d = !(taps == 1 && d->pad_top == 0 && d->pad_left == 0 && d->Ho == d->H && d->Wo == d->W);
+    p.B = d->B; p.Ho = d->Ho; p.Wo = d->Wo; p.HoWo = d->Ho * d->Wo; p.M = d->B * p.HoWo;
+    p.Cin = d->Cin; p.KW = d->KW; p.dil = d->dilation; p.pad_t = d->pad_top; p.pad_l = d->pad_left;
+    p.kb_per_tap = (d->Cin + TC_BK - 1) / TC_BK;
+    p.n_kblocks = taps * p.kb_per_tap;
+    p.Cout = d->Cout;
+    p.bias = d->bias; p.res = (const __half*)d->residual; p.out0 = d->out0; p.out1 = d->out1;
+    p.act = d->act; p.out_f32 = d->out_f32; p.split = d->split;
+    p.img0 = d->img_stride0; p.pix0 = d->pix_stride0; p.img1 = d->img_stride1; p.pix1 = d->pix_stride1;
+
+    // N tile: whole Cout when it fits one UMMA (<= 256, multiple of 16), else 128-wide tiles
+    const int cout16 = (d->Cout + 15) / 16 * 16;
+    p.BN = cout16 <= 256 ? cout16 : 128;
+    const int tiles_n = (d->Cout + p.BN - 1) / p.BN;
+    p.tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+    p.idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // f16 x f16 -> f32, K-major A and B
+
+    int tiles_m;
+    CUtensorMap map_a, map_b;
+    if (!p.mode4d) {
+        tiles_m = (p.M + TC_BM - 1) / TC_BM;
+        uint64_t dims[2] = {(uint64_t)d->Cin, (uint64_t)p.M};
+        uint64_t str[1] = {(uint64_t)d->Cin * 2};
+        uint32_t box[2] = {TC_BK, TC_BM};
+        int rc = make_map(&map_a, d->in, 2, dims, str, box);
+        if (rc) return rc;
+        p.a_bytes = TC_BM * TC_BK * 2;
+    } else {
+        // choose the output-pixel box (bw x bh x bb <= 128) that wastes the fewest MMA rows
+        double best = -1.0;
+        for (int bw = 1; bw <= min(d->Wo, TC_BM); ++bw) {
+            const int tw = (d->Wo + bw - 1) / bw;
+            for (int bh = 1; bh <= min(d->Ho, TC_BM / bw); ++bh) {
+                const int th = (d->Ho + bh - 1) / bh;
+                int bb = 1;
+                if (bw == d->Wo && bh == d->Ho) bb = max(1, min(d->B, TC_BM / (bw * bh)));
+                const int tb = (d->B + bb - 1) / bb;
+                const double eff = (double)p.M / ((double)tw * th * tb * TC_BM) + 1e-6 * bw;
+                if (eff > best) { best = eff; p.bw = bw; p.bh = bh; p.bb = bb; p.tiles_w = tw; p.tiles_h = th; }
+            }
+        }
+        tiles_m = p.tiles_w * p.tiles_h * ((d->B + p.bb - 1) / p.bb);
+        uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+        uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
+        uint32_t box[4] = {TC_BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bb};
+        int rc = make_map(&map_a, d->in, 4, dims, str, box);
+        if (rc) return rc;
+        p.a_bytes = (uint32_t)(p.bw * p.bh * p.bb) * TC_BK * 2;
+    }
+    {
+        const uint64_t ktot = (uint64_t)taps * d->Cin;
+        uint64_t dims[2] = {ktot, (uint64_t)d->Cout};
+        uint64_t str[1] = {ktot * 2};
+        uint32_t box[2] = {TC_BK, (uint32_t)p.BN};
+        int rc = make_map(&map_b, d->weight, 2, dims, str, box);
+        if (rc) return rc;
+        p.b_bytes = (uint32_t)p.BN * TC_BK * 2;
+    }
+
+    // split-K when the tile grid cannot fill the SMs and K is deep (the multibox head)
+    const int sms = sm_count();
+    int splits = 1;
+    const int ctas = tiles_m * tiles_n;
+    if (ctas * 2 <= sms && p.n_kblocks >= 8) {
+        splits = min(min((sms + ctas - 1) / ctas, p.n_kblocks / 4), 32);
+        if (splits < 1) splits = 1;
+    }
+    p.kb_per_split = (p.n_kblocks + splits - 1) / splits;
+    splits = (p.n_kblocks + p.kb_per_split - 1) / p.kb_per_split;
+    p.splits = splits;
+    const int rows_total = tiles_m * TC_BM;
+    if (splits > 1) {
+        p.ldp = tiles_n * p.BN;
+        int rc = partial_workspace((size_t)splits * rows_total * p.ldp * sizeof(float), &p.partial);
+        if (rc) return rc;
+    }
+
+    const size_t smem = (size_t)TC_STAGES * (TC_BM * TC_BK * 2 + (size_t)p.BN * TC_BK * 2) + (2 * TC_STAGES + 1) * 8 + 16 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "conv_tcgen05: cudaFuncSetAttribute");
+    dim3 grid(tiles_m, tiles_n, splits);
+    conv_tcgen05_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+    SSD_CHECK_LAUNCH("conv_tcgen05_kernel");
+    if (splits > 1) {
+        const int64_t total = (int64_t)rows_total * p.Cout;
+        const int64_t want = (total + 255) / 256, cap = (int64_t)sms * 8;
+        int blocks = (int)(want < cap ? want : cap);
+        conv_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p, rows_total);
+        SSD_CHECK_LAUNCH("conv_splitk_reduce_kernel");
+    }
+    return SSD_OK;
+}
+
+}  // namespace ssd
