@@ -8,11 +8,16 @@
 //     (padding) elements arrive as zeros;
 //   * tcgen05.mma (kind::f16, M = 128, N = 16..256) issued by one elected
 //     thread, fp32 accumulators in tensor memory (TMEM);
-//   * a 4-stage mbarrier producer/consumer ring (TMA warp -> MMA warp), and a
-//     TMEM-full barrier (MMA warp -> 4 epilogue warps);
-//   * epilogue: tcgen05.ld -> registers -> bias / BatchNorm-folded bias, ReLU /
-//     ReLU6, residual add, fp16 or fp32 stores, optional two-segment strided
-//     output (the multibox head writes straight into the concatenated tensors);
+//   * PERSISTENT CTAs (one per SM) loop over output tiles; a 4-stage mbarrier
+//     producer/consumer ring (TMA warp -> MMA warp) runs ahead across tiles and
+//     the accumulator is double-buffered in TMEM (tmem_full / tmem_empty
+//     barriers), so the epilogue of tile i overlaps the loads and MMAs of
+//     tile i+1;
+//   * epilogue (8 warps): tcgen05.ld -> registers -> bias / BatchNorm-folded
+//     bias, ReLU / ReLU6, residual add -> fp16 -> per-warp shared-memory staging
+//     -> fully coalesced 16-byte global stores; fp32 / two-segment strided
+//     outputs (the multibox head writes straight into the concatenated tensors)
+//     take a generic path;
 //   * split-K across blockIdx.z for the head convolutions (tiny M, K up to
 //     11 520): fp32 partials in a workspace + a deterministic fixed-order
 //     reduction kernel that applies the epilogue.
@@ -32,7 +37,11 @@ namespace ssd {
 constexpr int TC_BM = 128;           // UMMA M (one CTA, cta_group::1)
 constexpr int TC_BK = 64;            // 64 fp16 = 128 B = one swizzle row
 constexpr int TC_STAGES = 4;
-constexpr int TC_THREADS = 192;      // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+constexpr int TC_EPI_WARPS = 8;      // two warps per TMEM lane quarter (they split the column chunks)
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..9: epilogue
+constexpr int TC_CHUNK = 32;         // epilogue column chunk (fp16: 64 B per row)
+constexpr int TC_STAGE_PITCH = TC_CHUNK * 2 + 16;    // bytes per staged row: conflict-free 16-byte accesses
+constexpr int TC_STAGE_WARP = 32 * TC_STAGE_PITCH + TC_CHUNK * 4;   // per-warp staging: 32 rows + the chunk's bias
 
 struct TcParams {
     int mode4d;                      // 0: A is a 2-D [M, K] matrix (1x1 conv); 1: 4-D im2col boxes
@@ -47,7 +56,9 @@ struct TcParams {
     int Cout, BN;
     uint32_t a_bytes, b_bytes;       // TMA transaction bytes per stage
     uint32_t idesc;                  // tcgen05 instruction descriptor
-    uint32_t tmem_cols;
+    uint32_t tmem_cols;              // allocated columns = 2 accumulators
+    uint32_t acc_cols;               // column offset between the two accumulators
+    int tiles_m, tiles_n, n_tiles;   // n_tiles = tiles_m * tiles_n * splits
     // epilogue
     const float* bias; const __half* res; void* out0; void* out1;
     int act, out_f32, split;
@@ -152,6 +163,10 @@ __device__ __forceinline__ void tc_store_one(const TcParams& p, int b, int pix, 
 }
 
 // ------------------------------------------------------------------- kernel --
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const TcParams p) {
@@ -162,23 +177,26 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const uint32_t b_stage = (uint32_t)p.BN * TC_BK * 2;
     unsigned char* sA = smem;
     unsigned char* sB = smem + TC_STAGES * a_stage;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + TC_STAGES * b_stage);   // full[S], empty[S], tmem_full
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+    unsigned char* sStage = sB + TC_STAGES * b_stage;            // [TC_EPI_WARPS][32][TC_STAGE_PITCH]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + TC_EPI_WARPS * TC_STAGE_WARP);
+    // bars: full[S] | empty[S] | tmem_full[2] | tmem_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile_m = blockIdx.x, n0 = blockIdx.y * p.BN;
-    const int kb0 = blockIdx.z * p.kb_per_split;
-    const int kb1 = min(p.n_kblocks, kb0 + p.kb_per_split);
-    const int nkb = kb1 - kb0;
+    const uint32_t bar_full = smem_addr(bars), bar_empty = smem_addr(bars + TC_STAGES);
+    const uint32_t bar_tfull = smem_addr(bars + 2 * TC_STAGES), bar_tempty = smem_addr(bars + 2 * TC_STAGES + 2);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(smem_addr(bars + s), 1);                   // full: one arrive.expect_tx (+ TMA bytes)
-            mbar_init(smem_addr(bars + TC_STAGES + s), 1);       // empty: one tcgen05.commit
+            mbar_init(bar_full + 8 * s, 1);                      // one arrive.expect_tx (+ TMA bytes)
+            mbar_init(bar_empty + 8 * s, 1);                     // one tcgen05.commit
         }
-        mbar_init(smem_addr(bars + 2 * TC_STAGES), 1);           // accumulator ready
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);                     // one tcgen05.commit
+            mbar_init(bar_tempty + 8 * a, TC_EPI_WARPS);         // one arrive per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {                                             // this warp owns the TMEM allocation
@@ -190,110 +208,157 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    const int tiles_mn = p.tiles_m * p.tiles_n;
 
     if (warp == 0) {
         // ===================== TMA producer (one elected lane) =====================
         if (lane == 0) {
-            int b0 = 0, oy0 = 0, ox0 = 0;
-            if (p.mode4d) {
-                const int per_img = p.tiles_w * p.tiles_h;
-                const int tb = tile_m / per_img, tr = tile_m - tb * per_img;
-                const int th = tr / p.tiles_w, tw = tr - th * p.tiles_w;
-                b0 = tb * p.bb; oy0 = th * p.bh; ox0 = tw * p.bw;
-            }
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % TC_STAGES;
-                const uint32_t full = smem_addr(bars + s), empty = smem_addr(bars + TC_STAGES + s);
-                if (i >= TC_STAGES) mbar_wait(empty, ((i / TC_STAGES) - 1) & 1);
-                const int kb = kb0 + i;
-                const int tap = kb / p.kb_per_tap, c0 = (kb - tap * p.kb_per_tap) * TC_BK;
-                mbar_expect_tx(full, p.a_bytes + p.b_bytes);
-                const uint32_t dst_a = smem_addr(sA + (size_t)s * a_stage), dst_b = smem_addr(sB + (size_t)s * b_stage);
+            int it = 0;                                          // k-block counter across all tiles of this CTA
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+                const int z = t / tiles_mn, tm_ = (t - z * tiles_mn) / p.tiles_n, tn = t - z * tiles_mn - tm_ * p.tiles_n;
+                const int kb0 = z * p.kb_per_split, kb1 = min(p.n_kblocks, kb0 + p.kb_per_split);
+                int b0 = 0, oy0 = 0, ox0 = 0;
                 if (p.mode4d) {
-                    const int ky = tap / p.KW, kx = tap - ky * p.KW;
-                    tma_load_4d(dst_a, &map_a, full, c0, ox0 + kx * p.dil - p.pad_l, oy0 + ky * p.dil - p.pad_t, b0);
-                } else {
-                    tma_load_2d(dst_a, &map_a, full, c0, tile_m * TC_BM);
+                    const int per_img = p.tiles_w * p.tiles_h;
+                    const int tb = tm_ / per_img, tr = tm_ - tb * per_img;
+                    const int th = tr / p.tiles_w, tw = tr - th * p.tiles_w;
+                    b0 = tb * p.bb; oy0 = th * p.bh; ox0 = tw * p.bw;
                 }
-                tma_load_2d(dst_b, &map_b, full, tap * p.Cin + c0, n0);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % TC_STAGES;
+                    if (it >= TC_STAGES) mbar_wait(bar_empty + 8 * s, ((it / TC_STAGES) - 1) & 1);
+                    const int tap = kb / p.kb_per_tap, c0 = (kb - tap * p.kb_per_tap) * TC_BK;
+                    mbar_expect_tx(bar_full + 8 * s, p.a_bytes + p.b_bytes);
+                    const uint32_t dst_a = smem_addr(sA + (size_t)s * a_stage), dst_b = smem_addr(sB + (size_t)s * b_stage);
+                    if (p.mode4d) {
+                        const int ky = tap / p.KW, kx = tap - ky * p.KW;
+                        tma_load_4d(dst_a, &map_a, bar_full + 8 * s, c0, ox0 + kx * p.dil - p.pad_l,
+                                    oy0 + ky * p.dil - p.pad_t, b0);
+                    } else {
+                        tma_load_2d(dst_a, &map_a, bar_full + 8 * s, c0, tm_ * TC_BM);
+                    }
+                    tma_load_2d(dst_b, &map_b, bar_full + 8 * s, tap * p.Cin + c0, tn * p.BN);
+                }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one elected lane) =====================
         if (lane == 0) {
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % TC_STAGES;
-                mbar_wait(smem_addr(bars + s), (i / TC_STAGES) & 1);
+            int it = 0, j = 0;
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++j) {
+                const int z = t / tiles_mn;
+                const int kb0 = z * p.kb_per_split, kb1 = min(p.n_kblocks, kb0 + p.kb_per_split);
+                const int a = j & 1;
+                if (j >= 2) mbar_wait(bar_tempty + 8 * a, ((j >> 1) - 1) & 1);      // epilogue drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t da = umma_desc_sw128(smem_addr(sA + (size_t)s * a_stage));
-                const uint64_t db = umma_desc_sw128(smem_addr(sB + (size_t)s * b_stage));
+                const uint32_t tacc = tmem_base + (uint32_t)a * p.acc_cols;
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % TC_STAGES;
+                    mbar_wait(bar_full + 8 * s, (it / TC_STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t da = umma_desc_sw128(smem_addr(sA + (size_t)s * a_stage));
+                    const uint64_t db = umma_desc_sw128(smem_addr(sB + (size_t)s * b_stage));
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k)             // UMMA_K = 16: +32 bytes along K inside the swizzle row
-                    umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (i | k) != 0);
-                umma_commit(smem_addr(bars + TC_STAGES + s));    // frees the stage when these MMAs retire
+                    for (int k = 0; k < TC_BK / 16; ++k)         // UMMA_K = 16: +32 bytes along K inside the swizzle row
+                        umma_f16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (kb > kb0) || k > 0);
+                    umma_commit(bar_empty + 8 * s);              // frees the stage when these MMAs retire
+                }
+                umma_commit(bar_tfull + 8 * a);                  // accumulator complete
             }
-            umma_commit(smem_addr(bars + 2 * TC_STAGES));        // accumulator complete
         }
     } else {
-        // ===================== epilogue: 4 warps, one TMEM lane quarter each =====================
+        // ===================== epilogue: 8 warps, two per TMEM lane quarter =====================
+        const int ew = warp - 2;
         const int q = warp & 3;                                  // tcgen05.ld: warp w may touch lanes 32*(w%4)..+31
+        const int half = ew >> 2;                                // which half of the column chunks this warp takes
         const int r = q * 32 + lane;
-        mbar_wait(smem_addr(bars + 2 * TC_STAGES), 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        int b = 0, pix = 0;
-        const bool row_ok = tc_row_to_pixel(p, tile_m, r, b, pix);
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        unsigned char* stage = sStage + (size_t)ew * TC_STAGE_WARP;
         const bool fast16 = !p.partial && !p.out_f32 && p.split >= p.Cout && (p.Cout & 7) == 0 && (p.pix0 & 7) == 0 &&
                             (p.img0 & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.out0) & 15) == 0) &&
                             (p.res == nullptr || (reinterpret_cast<uintptr_t>(p.res) & 15) == 0);
-        for (int c0 = 0; c0 < p.BN; c0 += 16) {
-            if (n0 + c0 >= p.Cout) break;                        // warp-uniform
-            uint32_t acc[16];
-            tmem_ld16(trow + (uint32_t)c0, acc);                 // all 32 lanes must execute (sync.aligned)
-            if (!row_ok) continue;
-            if (p.partial) {
-                float* dst = p.partial + ((size_t)blockIdx.z * gridDim.x * TC_BM + (size_t)tile_m * TC_BM + r) * p.ldp + n0 + c0;
+        const float act_lo = p.act == SSD_ACT_NONE ? -__int_as_float(0x7f800000) : 0.0f;
+        const float act_hi = p.act == SSD_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
+        int j = 0;
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++j) {
+            const int z = t / tiles_mn, tm_ = (t - z * tiles_mn) / p.tiles_n, tn = t - z * tiles_mn - tm_ * p.tiles_n;
+            const int n0 = tn * p.BN;
+            const int a = j & 1;
+            mbar_wait(bar_tfull + 8 * a, (j >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            int b = 0, pix = 0;
+            const bool row_ok = tc_row_to_pixel(p, tm_, r, b, pix);
+            const unsigned ok_mask = __ballot_sync(0xffffffffu, row_ok);
+            const long long row_off = (long long)b * p.img0 + (long long)pix * p.pix0;     // element offset of the row (segment 0)
+            const uint32_t trow = tmem_base + (uint32_t)a * p.acc_cols + ((uint32_t)(q * 32) << 16);
+            for (int c0 = half * TC_CHUNK; c0 < p.BN; c0 += 2 * TC_CHUNK) {
+                if (n0 + c0 >= p.Cout) break;                    // warp-uniform
+                uint32_t acc[TC_CHUNK];
+                tmem_ld16(trow + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));      // all lanes (sync.aligned)
+                if (c0 + 16 < p.BN) tmem_ld16(trow + (uint32_t)c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
+                const int ncols = min(min(TC_CHUNK, p.BN - c0), p.Cout - (n0 + c0));    // valid columns of this chunk
+                if (p.partial) {
+                    if (row_ok) {
+                        float* dst = p.partial + ((size_t)z * p.tiles_m * TC_BM + (size_t)tm_ * TC_BM + r) * p.ldp + n0 + c0;
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
-                                                                      __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
-            } else if (fast16) {
-                const int n = n0 + c0;
-                const size_t off = (size_t)b * p.img0 + (size_t)pix * p.pix0 + n;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (n + h * 8 >= p.Cout) break;
-                    float v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        v[j] = __uint_as_float(acc[h * 8 + j]);
-                        if (p.bias) v[j] += __ldg(p.bias + n + h * 8 + j);
-                        v[j] = apply_act(v[j], p.act);
+                        for (int jj = 0; jj < TC_CHUNK; jj += 4)
+                            if (jj < p.BN - c0)
+                                *reinterpret_cast<float4*>(dst + jj) = make_float4(__uint_as_float(acc[jj]), __uint_as_float(acc[jj + 1]),
+                                                                                   __uint_as_float(acc[jj + 2]), __uint_as_float(acc[jj + 3]));
                     }
-                    if (p.res) {
-                        const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + off + h * 8));
-                        const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+                } else if (fast16) {
+                    const int n = n0 + c0;
+                    // 0. this chunk's 32 bias values -> the warp's private smem row (one coalesced load)
+                    float* sbias = reinterpret_cast<float*>(stage + 32 * TC_STAGE_PITCH);
+                    sbias[lane] = (p.bias && lane < ncols) ? __ldg(p.bias + n + lane) : 0.0f;
+                    __syncwarp();
+                    // 1. per-row math in registers (this thread owns tile row r, 32 channels); the
+                    //    activation is a branch-free clamp to [act_lo, act_hi]
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 f = __half22float2(rh[j]);
-                            v[2 * j] += f.x; v[2 * j + 1] += f.y;
+                    for (int h = 0; h < TC_CHUNK / 8; ++h) {
+                        const float4 b0 = *reinterpret_cast<const float4*>(sbias + h * 8);
+                        const float4 b1 = *reinterpret_cast<const float4*>(sbias + h * 8 + 4);
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        float v[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            v[e] = fminf(fmaxf(__uint_as_float(acc[h * 8 + e]) + bb[e], act_lo), act_hi);
+                        if (p.res && row_ok && h * 8 < ncols) {
+                            const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + row_off + n + h * 8));
+                            const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __half22float2(rh[e]);
+                                v[2 * e] += f.x; v[2 * e + 1] += f.y;
+                            }
+                        }
+                        uint4 o;
+                        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                        *reinterpret_cast<uint4*>(stage + lane * TC_STAGE_PITCH + h * 16) = o;
+                    }
+                    __syncwarp();
+                    // 2. coalesced write-out: 32 rows x 4 pieces of 16 B; 4 consecutive lanes cover one row's 64 B
+#pragma unroll
+                    for (int itw = 0; itw < (32 * (TC_CHUNK / 8)) / 32; ++itw) {
+                        const int idx = itw * 32 + lane, rr_ = idx >> 2, piece = idx & 3;
+                        const long long off = __shfl_sync(0xffffffffu, row_off, rr_);
+                        if (((ok_mask >> rr_) & 1u) && piece * 8 < ncols) {
+                            const uint4 o = *reinterpret_cast<const uint4*>(stage + rr_ * TC_STAGE_PITCH + piece * 16);
+                            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out0) + off + n + piece * 8) = o;
                         }
                     }
-                    uint4 o;
-                    __half2* oh = reinterpret_cast<__half2*>(&o);
+                    __syncwarp();
+                } else if (row_ok) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-                    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out0) + off + h * 8) = o;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = n0 + c0 + j;
-                    if (n < p.Cout) tc_store_one(p, b, pix, n, __uint_as_float(acc[j]));
+                    for (int jj = 0; jj < TC_CHUNK; ++jj)
+                        if (jj < ncols) tc_store_one(p, b, pix, n0 + c0 + jj, __uint_as_float(acc[jj]));
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * a);      // this warp is done reading accumulator a
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
     if (warp == 1) {
@@ -385,11 +450,14 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
     p.act = d->act; p.out_f32 = d->out_f32; p.split = d->split;
     p.img0 = d->img_stride0; p.pix0 = d->pix_stride0; p.img1 = d->img_stride1; p.pix1 = d->pix_stride1;
 
-    // N tile: whole Cout when it fits one UMMA (<= 256, multiple of 16), else 128-wide tiles
+    // N tile: the largest multiple of 16 (<= 256) that tiles Cout evenly; whole Cout when it fits one UMMA
     const int cout16 = (d->Cout + 15) / 16 * 16;
-    p.BN = cout16 <= 256 ? cout16 : 128;
+    p.BN = 128;
+    if (cout16 <= 256) p.BN = cout16;
+    else for (int bn = 256; bn >= 96; bn -= 16) if (cout16 % bn == 0) { p.BN = bn; break; }
     const int tiles_n = (d->Cout + p.BN - 1) / p.BN;
-    p.tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+    p.acc_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+    p.tmem_cols = 2 * p.acc_cols;                                  // double-buffered accumulator (<= 512 columns)
     p.idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // f16 x f16 -> f32, K-major A and B
 
     int tiles_m;
@@ -452,10 +520,13 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
         if (rc) return rc;
     }
 
-    const size_t smem = (size_t)TC_STAGES * (TC_BM * TC_BK * 2 + (size_t)p.BN * TC_BK * 2) + (2 * TC_STAGES + 1) * 8 + 16 + 1024;
+    p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.n_tiles = tiles_m * tiles_n * splits;
+    const size_t smem = (size_t)TC_STAGES * (TC_BM * TC_BK * 2 + (size_t)p.BN * TC_BK * 2) +
+                        (size_t)TC_EPI_WARPS * TC_STAGE_WARP + (2 * TC_STAGES + 4) * 8 + 16 + 1024;
     cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "conv_tcgen05: cudaFuncSetAttribute");
-    dim3 grid(tiles_m, tiles_n, splits);
+    // persistent: one CTA per SM (512 TMEM columns and ~100-215 KB of shared memory per CTA)
+    dim3 grid(min(p.n_tiles, sms), 1, 1);
     conv_tcgen05_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
     SSD_CHECK_LAUNCH("conv_tcgen05_kernel");
     if (splits > 1) {
