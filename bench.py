@@ -232,7 +232,11 @@ def _profile_steps(dm, B, iters=5):
     n = plan.n_launches
     acc = np.zeros(n + 1)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=plan.device)
+    all_evs = []
+    # everything is queued without host synchronisation so that the GPU never waits for the host
+    # between the short launches (an idle gap would be attributed to the following kernel)
     for it in range(iters + 1):
+        flush.zero_()
         flush.zero_()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 2)]
         evs[0].record()
@@ -241,9 +245,10 @@ def _profile_steps(dm, B, iters=5):
             evs[i + 1].record()
         st["enqueue_decode"]()
         evs[n + 1].record()
-        torch.cuda.synchronize()
-        if it:                                          # first pass is warm-up
-            acc += np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(n + 1)])
+        all_evs.append(evs)
+    torch.cuda.synchronize()
+    for evs in all_evs[1:]:                             # first pass is warm-up
+        acc += np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(n + 1)])
     return acc / iters                                  # ms per launch; last entry = decode+NMS (2 kernels)
 
 

@@ -213,6 +213,14 @@ int ssd_depthwise3x3(const void* d_in, const void* d_weight, const float* d_bias
                      int B, int H, int W, int C, int Ho, int Wo, int stride, int pad_top, int pad_left,
                      int act, ssd_stream_t stream);
 
+/* MobileNetV2 stem: keras_applications Conv1_pad + Conv1 (3x3, stride 2, Cin = 3) + bn_Conv1 +
+ * Conv1_relu (models/ssd_mobilenet_v2.py:25), computed straight from the fp32 NHWC image
+ * [B,H,W,3] (the fp32->fp16 input rounding of the pipeline is fused in).
+ * weight [Cout,3,3,3] fp16 (BN folded), bias [Cout] fp32, out [B,Ho,Wo,Cout] fp16; Cout == 32. */
+int ssd_stem_conv3x3s2(const float* d_img, const void* d_weight, const float* d_bias, void* d_out,
+                       int B, int H, int W, int Cout, int Ho, int Wo, int pad_top, int pad_left, int act,
+                       ssd_stream_t stream);
+
 /* fp32 NHWC image [B,H,W,3] (utils/data_utils.py:36 convert_image_dtype output)
  * -> fp16 NHWC with the channel dimension zero-padded to 8. */
 int ssd_image_to_f16c8(const float* d_img, void* d_out, int64_t n_pixels, ssd_stream_t stream);

@@ -32,6 +32,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <unordered_map>
+
 namespace ssd {
 
 constexpr int TC_BM = 128;           // UMMA M (one CTA, cta_group::1)
@@ -409,6 +412,41 @@ static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t
     return SSD_OK;
 }
 
+// Encoded tensor maps are cached per (pointer, geometry): cuTensorMapEncodeTiled costs a few
+// microseconds of host time, which would otherwise dominate eager launches of small layers.
+struct MapKey {
+    const void* base; uint64_t dims[4]; uint64_t strides[3]; uint32_t box[4]; int rank;
+    bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(&k);
+        size_t h = 1469598103934665603ull;
+        for (size_t i = 0; i < sizeof(MapKey); ++i) h = (h ^ p[i]) * 1099511628211ull;
+        return h;
+    }
+};
+static std::mutex g_map_mutex;
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+
+static int cached_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+    MapKey k;
+    memset(&k, 0, sizeof(k));
+    k.base = base; k.rank = rank;
+    for (int i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) k.strides[i] = strides_bytes[i];
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    auto it = g_map_cache.find(k);
+    if (it != g_map_cache.end()) { *map = it->second; return SSD_OK; }
+    int rc = make_map(map, base, rank, dims, strides_bytes, box);
+    if (rc == SSD_OK) {
+        if (g_map_cache.size() > 4096) g_map_cache.clear();
+        g_map_cache.emplace(k, *map);
+    }
+    return rc;
+}
+
 // split-K workspace: grown on demand, owned by the library, per device (the only allocation the
 // library makes; it happens outside stream capture because plans are warmed up before capture)
 static float* g_partial[16] = {nullptr};
@@ -467,7 +505,7 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
         uint64_t dims[2] = {(uint64_t)d->Cin, (uint64_t)p.M};
         uint64_t str[1] = {(uint64_t)d->Cin * 2};
         uint32_t box[2] = {TC_BK, TC_BM};
-        int rc = make_map(&map_a, d->in, 2, dims, str, box);
+        int rc = cached_map(&map_a, d->in, 2, dims, str, box);
         if (rc) return rc;
         p.a_bytes = TC_BM * TC_BK * 2;
     } else {
@@ -488,7 +526,7 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
         uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
         uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
         uint32_t box[4] = {TC_BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bb};
-        int rc = make_map(&map_a, d->in, 4, dims, str, box);
+        int rc = cached_map(&map_a, d->in, 4, dims, str, box);
         if (rc) return rc;
         p.a_bytes = (uint32_t)(p.bw * p.bh * p.bb) * TC_BK * 2;
     }
@@ -497,7 +535,7 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
         uint64_t dims[2] = {ktot, (uint64_t)d->Cout};
         uint64_t str[1] = {ktot * 2};
         uint32_t box[2] = {TC_BK, (uint32_t)p.BN};
-        int rc = make_map(&map_b, d->weight, 2, dims, str, box);
+        int rc = cached_map(&map_b, d->weight, 2, dims, str, box);
         if (rc) return rc;
         p.b_bytes = (uint32_t)p.BN * TC_BK * 2;
     }
@@ -523,8 +561,14 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
     p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.n_tiles = tiles_m * tiles_n * splits;
     const size_t smem = (size_t)TC_STAGES * (TC_BM * TC_BK * 2 + (size_t)p.BN * TC_BK * 2) +
                         (size_t)TC_EPI_WARPS * TC_STAGE_WARP + (2 * TC_STAGES + 4) * 8 + 16 + 1024;
-    cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "conv_tcgen05: cudaFuncSetAttribute");
+    static thread_local int attr_dev = -1;                       // opt-in once per (thread, device): maximum footprint
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (attr_dev != cur_dev) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "conv_tcgen05: cudaFuncSetAttribute");
+        attr_dev = cur_dev;
+    }
     // persistent: one CTA per SM (512 TMEM columns and ~100-215 KB of shared memory per CTA)
     dim3 grid(min(p.n_tiles, sms), 1, 1);
     conv_tcgen05_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);

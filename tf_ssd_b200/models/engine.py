@@ -259,12 +259,30 @@ class _PlanBuilder:
         return torch.empty((self.B, H, W, C), dtype=torch.float16, device=self.dev)
 
     def input(self) -> Act:
+        """The fp32 NHWC image buffer itself (t is None): the first layer decides how to
+        consume it -- the MobileNetV2 stem reads it directly, anything else gets an fp16 copy."""
+        S = self.m.img_size
+        return Act(None, S, S, 3)
+
+    def _image_as_f16(self) -> Act:
         S = self.m.img_size
         x = self._buf(S, S, 8)
         npx = self.B * S * S
         self.plan.steps.append(Step("input_cast", "cast", self.lib.ssd_image_to_f16c8,
                                     (_ffi.ptr(self.plan.image), _ffi.ptr(x), npx), 0.0, npx * (12 + 16), (x,)))
         return Act(x, S, S, 8)
+
+    def _stem(self, x, name, cout, ph, pw, act, bn):
+        Ho, Wo = _out_size(x.H, 3, 2, 1, ph), _out_size(x.W, 3, 2, 1, pw)
+        w, b = self.m._packed_conv(name, bn, 3)
+        out = self._buf(Ho, Wo, cout)
+        args = (_ffi.ptr(self.plan.image), _ffi.ptr(w), _ffi.ptr(b), _ffi.ptr(out), self.B, x.H, x.W, cout, Ho, Wo,
+                ph[0], pw[0], act)
+        nbytes = self.B * (x.H * x.W * 3 * 4 + Ho * Wo * cout * 2) + 27 * cout * 2
+        self.plan.steps.append(Step(name, "stem", self.lib.ssd_stem_conv3x3s2, args, 2.0 * self.B * Ho * Wo * 27 * cout,
+                                    nbytes, (w, b, out),
+                                    dict(x=self.plan.image, w=w, bias=b, out=out, ph=ph, pw=pw, act=act)))
+        return Act(out, Ho, Wo, cout)
 
     def _emit_conv(self, name, x: Act, w: torch.Tensor, bias, cout, k, stride, dilation, ph, pw, act,
                    residual: Optional[Act], out0, out1=None, out_f32=0, split=None, strides=None, real_cin=None):
@@ -296,6 +314,10 @@ class _PlanBuilder:
     def conv(self, x, name, cout, k=1, stride=1, pad="same", dilation=1, act=ACT_NONE, bn=None, use_bias=True,
              residual=None, init=None, l2=False):
         ph, pw = _resolve_pads(x.H, x.W, k, stride, dilation, pad)
+        if x.t is None:                                  # first layer, fed by the fp32 image
+            if k == 3 and stride == 2 and dilation == 1 and cout == 32 and residual is None:
+                return self._stem(x, name, cout, ph, pw, act, bn)
+            x = self._image_as_f16()
         w, b = self.m._packed_conv(name, bn, x.C)
         Ho, Wo = _out_size(x.H, k, stride, dilation, ph), _out_size(x.W, k, stride, dilation, pw)
         out = self._buf(Ho, Wo, cout)
