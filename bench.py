@@ -318,14 +318,12 @@ def _box_kernel_rooflines(peaks, hp, iters=10, warmup=3):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from tf_ssd_b200 import dist_utils
+    rank, local_rank, world = dist_utils.env_rank()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU restatement)")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dist_utils.init_from_env("nccl")
 
     from tf_ssd_b200 import _ffi, synth
     from tf_ssd_b200.models import ssd_mobilenet_v2
@@ -350,8 +348,7 @@ def run_b200(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=plan.device)      # > 126 MB L2
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        dist_utils.barrier()
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value") -------------------------------
@@ -387,10 +384,8 @@ def run_b200(args):
     assert res[0].shape == (K * B, 200, 4)
     barrier()
 
-    times = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(times[0]), float(times[1])
+    dev_ms = dist_utils.max_over_ranks(dev_ms, plan.device)        # slowest rank
+    e2e_ms = dist_utils.max_over_ranks(e2e_ms, plan.device)
 
     if rank == 0:
         total_images = world * B * K
