@@ -189,6 +189,7 @@ def run_reference(args):
     from oracle import box_oracle as bo
     from tf_ssd_b200 import synth
     from tf_ssd_b200.models.engine import SSDModel
+    torch.set_num_threads(os.cpu_count() or 1)         # torchrun exports OMP_NUM_THREADS=1: use every host core
     hp = _hyper_params()
     model = SSDModel(BACKBONE, hp, seed=1234)          # host-side variable initialisation only (no GPU use)
     weights = model.weights

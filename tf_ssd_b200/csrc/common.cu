@@ -1,6 +1,7 @@
 // Error reporting + device queries shared by every entry point of libssd_b200.so.
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace ssd {
@@ -20,6 +21,15 @@ int fail(int code, const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
     snprintf(g_err, sizeof(g_err), "%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
     return (int)e;
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SSD_B200_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 int sm_count() {

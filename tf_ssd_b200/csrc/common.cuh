@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <string.h>
 
 #include "../../include/ssd_b200.h"
 
@@ -31,6 +32,33 @@ int   cuda_fail(cudaError_t e, const char* what);
 static inline cudaStream_t as_stream(ssd_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int sm_count();      // cached multiProcessorCount of the current device
+
+// ---- programmatic dependent launch (PDL) -------------------------------------
+// Consecutive kernels of a plan are launched with programmatic stream serialisation:
+// kernel N+1 may start its prologue (barrier init, TMEM allocation, descriptor
+// prefetch, shared-memory weight staging) while kernel N drains.  Every kernel
+// launched through launch_pdl() MUST call pdl_wait() before it touches global memory
+// written or read by its predecessors; pdl_trigger() (at kernel entry) lets the
+// successor be scheduled as soon as all CTAs of this grid have started.
+// SSD_B200_PDL=0 disables the attribute (plain stream order).
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+__device__ __forceinline__ void pdl_wait()    { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int    ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -70,6 +70,8 @@ conv_igemm_kernel(const ConvK p) {
     unsigned char* sB = smem + STAGES * A_STAGE;
     float* sOut = reinterpret_cast<float*>(smem);          // reused after the main loop
 
+    pdl_trigger();
+    pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int warp_m = warp % WARPS_M, warp_n = warp / WARPS_M;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -249,8 +251,8 @@ static int launch_conv(const ConvK& k, cudaStream_t st) {
         configured = true;
     }
     dim3 grid(ceil_div(k.M, BM), ceil_div(k.Cout, BN));
-    kern<<<grid, NT, smem, st>>>(k);
-    SSD_CHECK_LAUNCH("conv_igemm_kernel");
+    cudaError_t le = launch_pdl(kern, grid, dim3(NT), smem, st, k);
+    if (le != cudaSuccess) return cuda_fail(le, "conv_igemm_kernel");
     return SSD_OK;
 }
 

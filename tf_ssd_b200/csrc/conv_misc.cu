@@ -36,6 +36,8 @@ depthwise3x3_kernel(const uint4* __restrict__ in, const uint4* __restrict__ w, c
                     uint4* __restrict__ out, int H, int W, int C8, int Ho, int Wo, int pad_t, int pad_l,
                     int act, int64_t total) {
     constexpr int COLS = (PX - 1) * STRIDE + 3;
+    pdl_trigger();
+    pdl_wait();
     const int wgroups = (Wo + PX - 1) / PX;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * blockDim.x) {
@@ -125,6 +127,8 @@ stem_conv3x3s2_kernel(const float* __restrict__ img, const __half* __restrict__ 
                       int64_t total) {
     __shared__ __align__(16) float sw[27][COUT];
     __shared__ float sb[COUT];
+    pdl_trigger();
+    pdl_wait();
     for (int e = threadIdx.x; e < 27 * COUT; e += blockDim.x) {
         const int c = e / 27, k = e - c * 27;
         sw[k][c] = __half2float(w[e]);
@@ -261,12 +265,12 @@ extern "C" int ssd_depthwise3x3(const void* d_in, const void* d_weight, const fl
     constexpr int PX = 2;
     const int64_t total = (int64_t)B * Ho * ((Wo + PX - 1) / PX) * C8;
     auto args = [&](auto kern) {
-        kern<<<grid_for(total, 16), 256, 0, as_stream(stream)>>>(
-            reinterpret_cast<const uint4*>(d_in), reinterpret_cast<const uint4*>(d_weight), d_bias,
-            reinterpret_cast<uint4*>(d_out), H, W, C8, Ho, Wo, pad_top, pad_left, act, total);
+        return launch_pdl(kern, dim3(grid_for(total, 16)), dim3(256), 0, as_stream(stream),
+                          reinterpret_cast<const uint4*>(d_in), reinterpret_cast<const uint4*>(d_weight), d_bias,
+                          reinterpret_cast<uint4*>(d_out), H, W, C8, Ho, Wo, pad_top, pad_left, act, total);
     };
-    if (stride == 1) args(depthwise3x3_kernel<1, PX>); else args(depthwise3x3_kernel<2, PX>);
-    SSD_CHECK_LAUNCH("depthwise3x3_kernel");
+    cudaError_t le = (stride == 1) ? args(depthwise3x3_kernel<1, PX>) : args(depthwise3x3_kernel<2, PX>);
+    if (le != cudaSuccess) return cuda_fail(le, "depthwise3x3_kernel");
     return SSD_OK;
 }
 
@@ -279,10 +283,10 @@ extern "C" int ssd_stem_conv3x3s2(const float* d_img, const void* d_weight, cons
     SSD_REQUIRE(Cout == 32, SSD_ERR_UNSUPPORTED, "ssd_stem_conv3x3s2: Cout=%d (this build instantiates Cout == 32)", Cout);
     const int64_t total = (int64_t)B * Ho * Wo;
     const int64_t blocks = (total + 127) / 128, cap = (int64_t)sm_count() * 16;
-    stem_conv3x3s2_kernel<32><<<(int)(blocks < cap ? blocks : cap), 128, 0, as_stream(stream)>>>(
-        d_img, reinterpret_cast<const __half*>(d_weight), d_bias, reinterpret_cast<__half*>(d_out), H, W, Ho, Wo,
-        pad_top, pad_left, act, total);
-    SSD_CHECK_LAUNCH("stem_conv3x3s2_kernel");
+    cudaError_t le = launch_pdl(stem_conv3x3s2_kernel<32>, dim3((int)(blocks < cap ? blocks : cap)), dim3(128), 0,
+                                as_stream(stream), d_img, reinterpret_cast<const __half*>(d_weight), d_bias,
+                                reinterpret_cast<__half*>(d_out), H, W, Ho, Wo, pad_top, pad_left, act, total);
+    if (le != cudaSuccess) return cuda_fail(le, "stem_conv3x3s2_kernel");
     return SSD_OK;
 }
 

@@ -185,6 +185,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // bars: full[S] | empty[S] | tmem_full[2] | tmem_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
 
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_full = smem_addr(bars), bar_empty = smem_addr(bars + TC_STAGES);
     const uint32_t bar_tfull = smem_addr(bars + 2 * TC_STAGES), bar_tempty = smem_addr(bars + 2 * TC_STAGES + 2);
@@ -212,6 +213,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const int tiles_mn = p.tiles_m * p.tiles_n;
+    pdl_wait();                                                  // predecessors' outputs are visible from here on
 
     if (warp == 0) {
         // ===================== TMA producer (one elected lane) =====================
@@ -373,6 +375,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // Deterministic split-K reduction + epilogue: partial[z][row][n] summed for z = 0..splits-1 in order.
 __global__ void __launch_bounds__(256)
 conv_splitk_reduce_kernel(const TcParams p, int rows_total) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t total = (int64_t)rows_total * p.Cout;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int row = (int)(e / p.Cout), n = (int)(e - (int64_t)row * p.Cout);
@@ -571,14 +575,16 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
     }
     // persistent: one CTA per SM (512 TMEM columns and ~100-215 KB of shared memory per CTA)
     dim3 grid(min(p.n_tiles, sms), 1, 1);
-    conv_tcgen05_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
-    SSD_CHECK_LAUNCH("conv_tcgen05_kernel");
+    {
+        cudaError_t le = launch_pdl(conv_tcgen05_kernel, grid, dim3(TC_THREADS), smem, st, map_a, map_b, p);
+        if (le != cudaSuccess) return cuda_fail(le, "conv_tcgen05_kernel");
+    }
     if (splits > 1) {
         const int64_t total = (int64_t)rows_total * p.Cout;
         const int64_t want = (total + 255) / 256, cap = (int64_t)sms * 8;
         int blocks = (int)(want < cap ? want : cap);
-        conv_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p, rows_total);
-        SSD_CHECK_LAUNCH("conv_splitk_reduce_kernel");
+        cudaError_t le = launch_pdl(conv_splitk_reduce_kernel, dim3(blocks), dim3(256), 0, st, p, rows_total);
+        if (le != cudaSuccess) return cuda_fail(le, "conv_splitk_reduce_kernel");
     }
     return SSD_OK;
 }
