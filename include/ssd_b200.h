@@ -234,6 +234,50 @@ int ssd_maxpool(const void* d_in, void* d_out, int B, int H, int W, int C, int H
  * * scale[c].  in/out [rows,C] fp16, scale [C] fp32. */
 int ssd_l2norm(const void* d_in, const float* d_scale, void* d_out, int64_t rows, int C, ssd_stream_t stream);
 
+/* ============================================================ training ==== */
+/* The reference trains through Keras: model.compile(Adam(1e-3), loss=[loc, conf]) and model.fit
+ * (trainer.py:86-127) -- forward, loss, backward and the optimizer step are all inside TensorFlow.
+ * The entries below are the pieces of that step that are not already covered by ssd_conv2d /
+ * ssd_loss_bwd.  Gradients w.r.t. activations are fp16 NHWC tensors (loss-scaled by the caller),
+ * gradients w.r.t. variables are fp32 and ACCUMULATE into their buffers (zero them per step).
+ *
+ * Data gradient of a convolution: for stride 1 it is ssd_conv2d itself applied to dY with the
+ * filter produced by ssd_filter_flip_transpose and pad' = (k-1)*dilation - pad; for stride s the
+ * caller first spreads dY with ssd_upsample_zero. */
+
+/* Filter gradient of the Keras Conv2D described by *h_desc (same geometry fields as the forward
+ * call; out0/out1/weight/bias are ignored):  dW[co][ky][kx][ci] += sum dY[b,oy,ox,co] * X[b,iy,ix,ci].
+ * d_dy [B*Ho*Wo, ldy] fp16 (ldy >= Cout, multiple of 8); d_dw [Cout,KH,KW,Cin] fp32. */
+int ssd_conv2d_wgrad(const ssd_conv_desc* h_desc, const void* d_dy, int ldy, float* d_dw, ssd_stream_t stream);
+
+/* d_dy[i] = y[i] > 0 ? d_dy[i] : 0  (ReLU / the lower knee of ReLU6), fp16, n % 8 == 0. */
+int ssd_relu_bwd(void* d_dy, const void* d_y, int64_t n, ssd_stream_t stream);
+/* d_db[c] += sum over rows of d_dy[row][c], c < C; d_dy [rows, ld] fp16. */
+int ssd_bias_grad(const void* d_dy, float* d_db, int64_t rows, int ld, int C, ssd_stream_t stream);
+/* d_wt[ci][KH-1-ky][KW-1-kx][co] = d_w[co][ky][kx][ci], co padded with zeros to ldo (fp16). */
+int ssd_filter_flip_transpose(const void* d_w, void* d_wt, int Cout, int KH, int KW, int Cin, int ldo,
+                              ssd_stream_t stream);
+/* d_out[b][oy*s][ox*s][:] = d_in[b][oy][ox][:]; every other element of d_out must already be zero. */
+int ssd_upsample_zero(const void* d_in, void* d_out, int B, int Ho, int Wo, int C, int Hu, int Wu, int s,
+                      ssd_stream_t stream);
+/* Keras MaxPool2D backward (models/ssd_vgg16.py:82-101): the first maximum of each window (scan
+ * order) receives the window's gradient.  accumulate != 0 adds to d_dx. */
+int ssd_maxpool_bwd(const void* d_x, const void* d_y, const void* d_dy, void* d_dx, int B, int H, int W, int C,
+                    int Ho, int Wo, int k, int stride, int pad_top, int pad_left, int accumulate, ssd_stream_t stream);
+/* L2Normalization backward (models/ssd_vgg16.py:63): d_dx [rows,C] fp16, d_dscale[C] += ... (fp32). */
+int ssd_l2norm_bwd(const void* d_x, const float* d_scale, const void* d_dy, void* d_dx, float* d_dscale,
+                   int64_t rows, int C, int accumulate, ssd_stream_t stream);
+/* Gradient of one head convolution's output from the concatenated loss gradients (inverse of the
+ * head's two-segment store, models/header.py:46-51): d_dy [B, HW, ld] fp16 = [g_logits | g_deltas | 0]. */
+int ssd_head_grad_gather(const float* d_g_logits, const float* d_g_deltas, void* d_dy, int B, int N, int L,
+                         int anchor_offset, int HW, int A, int ld, ssd_stream_t stream);
+/* Keras Adam (trainer.py:92; beta1 0.9, beta2 0.999, epsilon 1e-7), fused with the loss-scale removal
+ * (inv_scale), the l2 kernel regulariser gradient (l2 = 2*5e-4 for ssd_vgg16.py:76 kernels, else 0), the
+ * fp16 working-copy refresh (d_w16 may be NULL) and sum(w^2) of the pre-update weights (d_sumsq may be NULL).
+ * lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t). */
+int ssd_adam_step(float* d_w, float* d_m, float* d_v, const float* d_grad, void* d_w16, int64_t n, float lr_t,
+                  float beta1, float beta2, float eps, float inv_scale, float l2, float* d_sumsq, ssd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

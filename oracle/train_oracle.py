@@ -1,0 +1,115 @@
+"""torch-CPU autograd restatement of one Keras training step of the reference
+(trainer.py:86-127): forward (models/ssd_vgg16.py), the two CustomLoss terms
+(ssd_loss.py:26-91) reduced like Keras ``compile(loss=[...])`` does (mean over the batch, summed),
+the l2(5e-4) kernel regulariser (ssd_vgg16.py:76) and Adam (trainer.py:92, Keras defaults).
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  PARITY UNPINNED against TensorFlow:
+the reduction rule, the regulariser placement and Adam's epsilon handling are ``[TF-recall]``.
+The hard-negative mask is taken from ``box_oracle`` (it is not differentiable); everything else is
+differentiated by torch autograd in float32.
+"""
+
+from __future__ import annotations
+
+from typing import Dict, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle import box_oracle as bo
+from oracle.net_oracle import same_pad
+
+L2_REG = 5e-4
+
+
+def _conv(x, w, name, stride=1, padding="same", dilation=1, relu=True):
+    k = w[name + "/kernel"]                                   # HWIO
+    wt = k.permute(3, 2, 0, 1)
+    kh = wt.shape[2]
+    if padding == "same":
+        ph, pw = same_pad(x.shape[2], kh, stride, dilation), same_pad(x.shape[3], kh, stride, dilation)
+        x = F.pad(x, (pw[0], pw[1], ph[0], ph[1]))
+    y = F.conv2d(x, wt, w[name + "/bias"], stride=stride, dilation=dilation)
+    return torch.relu(y) if relu else y
+
+
+def _pool(x, k, s):
+    ph, pw = same_pad(x.shape[2], k, s), same_pad(x.shape[3], k, s)
+    return F.max_pool2d(F.pad(x, (pw[0], pw[1], ph[0], ph[1]), value=float("-inf")), k, s)
+
+
+def vgg16_forward_torch(w: Dict[str, torch.Tensor], hyper_params, images: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """models/ssd_vgg16.py:78-121, differentiable; returns (pred_deltas, logits)."""
+    x = images.permute(0, 3, 1, 2)
+    conv4_3 = None
+    for bname, reps in [("conv1", 2), ("conv2", 2), ("conv3", 3), ("conv4", 3), ("conv5", 3)]:
+        for r in range(1, reps + 1):
+            x = _conv(x, w, f"{bname}_{r}")
+        if bname == "conv4":
+            conv4_3 = x
+        x = _pool(x, 2, 2) if bname != "conv5" else _pool(x, 3, 1)
+    x = _conv(x, w, "conv6", dilation=6)
+    conv7 = _conv(x, w, "conv7")
+    x = _conv(conv7, w, "conv8_1", padding="valid")
+    conv8_2 = _conv(x, w, "conv8_2", stride=2)
+    x = _conv(conv8_2, w, "conv9_1", padding="valid")
+    conv9_2 = _conv(x, w, "conv9_2", stride=2)
+    x = _conv(conv9_2, w, "conv10_1", padding="valid")
+    conv10_2 = _conv(x, w, "conv10_2", padding="valid")
+    x = _conv(conv10_2, w, "conv11_1", padding="valid")
+    conv11_2 = _conv(x, w, "conv11_2", padding="valid")
+    ss = torch.sum(conv4_3 * conv4_3, dim=1, keepdim=True)
+    norm = conv4_3 * torch.rsqrt(torch.clamp(ss, min=1e-12)) * w["l2_normalization/scale"].view(1, -1, 1, 1)
+    L = hyper_params["total_labels"]
+    labels, boxes = [], []
+    for i, t in enumerate([norm, conv7, conv8_2, conv9_2, conv10_2, conv11_2]):
+        lab = _conv(t, w, f"{i + 1}_conv_label_output", relu=False)
+        box = _conv(t, w, f"{i + 1}_conv_boxes_output", relu=False)
+        B = t.shape[0]
+        labels.append(lab.permute(0, 2, 3, 1).reshape(B, -1, L))
+        boxes.append(box.permute(0, 2, 3, 1).reshape(B, -1, 4))
+    return torch.cat(boxes, 1), torch.cat(labels, 1)
+
+
+def losses_torch(actual_deltas, actual_labels, pred_deltas, logits, neg_pos_ratio=3.0, alpha=1.0):
+    """ssd_loss.py:26-91 on tensors (from logits); per-image ``(loc [B], conf [B])``."""
+    ad, al = torch.as_tensor(actual_deltas), torch.as_tensor(actual_labels)
+    e = (pred_deltas - ad).abs()
+    hub = torch.where(e <= 1.0, 0.5 * e * e, e - 0.5).sum(-1)                      # Huber mean * 4 == sum over coords
+    pos = (ad != 0).any(-1).float()
+    n_pos = pos.sum(1)
+    loc = (hub * pos).sum(1) / torch.where(n_pos == 0, torch.ones_like(n_pos), n_pos) * alpha
+    ce = -(al * torch.log_softmax(logits, -1)).sum(-1)
+    # the hard-negative selection is a constant of the step (argsort ranks, ssd_loss.py:78-84)
+    with torch.no_grad():
+        masked = (ce * al[..., 0]).numpy()
+        posc = (al[..., 1:] != 0).any(-1).numpy().astype(np.float32)
+        n_posc = posc.sum(1)
+        n_neg = (n_posc * np.float32(neg_pos_ratio)).astype(np.int32)
+        neg = np.stack([(bo.hard_negative_rank(masked[b]) < n_neg[b]) for b in range(masked.shape[0])]).astype(np.float32)
+        final = torch.from_numpy(posc + neg)
+        div = torch.from_numpy(np.where(n_posc == 0, 1.0, n_posc).astype(np.float32))
+    conf = (final * ce).sum(1) / div
+    return loc, conf
+
+
+def train_step(weights: Dict[str, np.ndarray], hyper_params, images: np.ndarray, actual_deltas: np.ndarray,
+               actual_labels: np.ndarray, l2_kernels: Sequence[str], neg_pos_ratio=3.0, alpha=1.0):
+    """Returns ``(loss dict, grads dict)`` -- gradients of mean_B(loc) + mean_B(conf) + reg w.r.t. every variable."""
+    w = {k: torch.tensor(v, dtype=torch.float32, requires_grad=True) for k, v in weights.items()}
+    pd, z = vgg16_forward_torch(w, hyper_params, torch.from_numpy(np.ascontiguousarray(images, np.float32)))
+    loc, conf = losses_torch(actual_deltas, actual_labels, pd, z, neg_pos_ratio, alpha)
+    reg = sum(L2_REG * (w[k] ** 2).sum() for k in l2_kernels)
+    total = loc.mean() + conf.mean() + reg
+    total.backward()
+    grads = {k: (v.grad.numpy() if v.grad is not None else np.zeros_like(weights[k])) for k, v in w.items()}
+    return dict(loss=float(total.detach()), loc=loc.detach().numpy(), conf=conf.detach().numpy(), reg=float(reg.detach())), grads
+
+
+def adam_update(w, g, m, v, t, lr=1e-3, b1=0.9, b2=0.999, eps=1e-7):
+    """[TF-recall] Keras Adam: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); w -= lr_t * m / (sqrt(v) + eps)."""
+    m = b1 * m + (1 - b1) * g
+    v = b2 * v + (1 - b2) * g * g
+    lr_t = lr * np.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+    return w - lr_t * m / (np.sqrt(v) + eps), m, v

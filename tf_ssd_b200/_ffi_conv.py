@@ -30,4 +30,14 @@ SIGNATURES = {
     "ssd_image_to_f16c8": (i, [vp, vp, i64, vp]),
     "ssd_maxpool": (i, [vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),
     "ssd_l2norm": (i, [vp, vp, vp, i64, i, vp]),
+    # training
+    "ssd_conv2d_wgrad": (i, [C.POINTER(ConvDesc), vp, i, vp, vp]),
+    "ssd_relu_bwd": (i, [vp, vp, i64, vp]),
+    "ssd_bias_grad": (i, [vp, vp, i64, i, i, vp]),
+    "ssd_filter_flip_transpose": (i, [vp, vp, i, i, i, i, i, vp]),
+    "ssd_upsample_zero": (i, [vp, vp, i, i, i, i, i, i, i, vp]),
+    "ssd_maxpool_bwd": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, i, vp]),
+    "ssd_l2norm_bwd": (i, [vp, vp, vp, vp, vp, i64, i, i, vp]),
+    "ssd_head_grad_gather": (i, [vp, vp, vp, i, i, i, i, i, i, i, vp]),
+    "ssd_adam_step": (i, [vp, vp, vp, vp, vp, i64, f, f, f, f, f, f, vp, vp]),
 }

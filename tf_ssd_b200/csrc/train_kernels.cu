@@ -1,0 +1,438 @@
+// Training-side kernels of the tf-ssd hot path (trainer.py:86-127: Keras fit =
+// forward + loss + backward + Adam) for sm_100a.
+//
+//   * conv_wgrad_kernel      filter gradient as a split-K implicit GEMM on the tensor
+//                            cores: dW[co, tap, ci] = sum_pixels dY[pix, co] * X[pix+tap, ci]
+//                            (both operands are pixel-major in memory, so fragments come
+//                            from ldmatrix.trans; fp32 atomics combine the K splits)
+//   * data gradient          is NOT here: for stride 1 it is the forward convolution of dY
+//                            with the flipped / transposed filter, so it runs on the
+//                            tcgen05 kernel (conv_tcgen05.cu); stride 2 zero-upsamples dY first
+//   * element-wise / reduction helpers: ReLU mask, bias gradient, filter flip-transpose,
+//     zero-upsample, max-pool backward, L2Normalization backward, head gradient gather,
+//     fused Adam (fp32 master + fp16 working copy, L2 regulariser, loss-scale removal).
+
+#include "common.cuh"
+
+namespace ssd {
+
+__device__ __forceinline__ uint32_t smem_u32t(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16t(uint32_t dst, const void* src, bool valid) {
+    int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816t(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// ------------------------------------------------------------------ wgrad --
+constexpr int WG_BM = 128, WG_BN = 128, WG_BK = 32, WG_STAGES = 4, WG_THREADS = 256;
+
+struct WgradK {
+    const __half* x; const __half* dy; float* dw;
+    int B, H, W, Cin, Ho, Wo, Cout, KW, stride, dil, pad_t, pad_l;
+    int M, HoWo, ldy, taps;
+    int chunks_total, chunks_per_split, tiles_n;
+};
+
+// byte offset of 16-byte piece p (0..15) of pixel row k inside a [32][128] half tile (XOR swizzle)
+__device__ __forceinline__ uint32_t wg_off(int k, int p) { return (uint32_t)(k * 256 + ((p ^ (k & 7)) << 4)); }
+
+__global__ void __launch_bounds__(WG_THREADS)
+conv_wgrad_kernel(const WgradK p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int A_STAGE = WG_BK * WG_BM * 2, B_STAGE = WG_BK * WG_BN * 2;
+    unsigned char* sA = smem;                              // dY tile  [pix][co]
+    unsigned char* sB = smem + WG_STAGES * A_STAGE;        // X tile   [pix][ci]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int warp_m = warp & 1, warp_n = warp >> 1;       // 2 x 4 warps, warp tile 64 (co) x 32 (ci)
+    const int tile_m = blockIdx.x / p.tiles_n, tile_n = blockIdx.x - tile_m * p.tiles_n;
+    const int co0 = tile_m * WG_BM, ci0 = tile_n * WG_BN;
+    const int tap = blockIdx.y, ky = tap / p.KW, kx = tap - ky * p.KW;
+    const int c_begin = blockIdx.z * p.chunks_per_split;
+    const int c_end = min(p.chunks_total, c_begin + p.chunks_per_split);
+
+    auto load_chunk = [&](int chunk, int stage) {
+        const uint32_t a_dst = smem_u32t(sA + stage * A_STAGE), b_dst = smem_u32t(sB + stage * B_STAGE);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int q = tid + i * WG_THREADS, k = q >> 4, pc = q & 15;
+            const int m = chunk * WG_BK + k;
+            const bool mv = m < p.M;
+            const int mm = mv ? m : 0;
+            // dY piece
+            const int co = co0 + pc * 8;
+            const bool va = mv && co < p.ldy;
+            cp_async16t(a_dst + wg_off(k, pc), va ? p.dy + (size_t)mm * p.ldy + co : p.dy, va);
+            // X piece (im2col gather for this tap)
+            const int b = mm / p.HoWo, pix = mm - b * p.HoWo, oy = pix / p.Wo, ox = pix - oy * p.Wo;
+            const int iy = oy * p.stride - p.pad_t + ky * p.dil, ix = ox * p.stride - p.pad_l + kx * p.dil;
+            const int ci = ci0 + pc * 8;
+            const bool vb = mv && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W && ci < p.Cin;
+            cp_async16t(b_dst + wg_off(k, pc), vb ? p.x + (((size_t)b * p.H + iy) * p.W + ix) * p.Cin + ci : p.x, vb);
+        }
+    };
+
+    float acc[4][4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.0f;
+
+    const int n_chunks = c_end - c_begin;
+#pragma unroll
+    for (int s = 0; s < WG_STAGES - 1; ++s) {
+        if (s < n_chunks) load_chunk(c_begin + s, s);
+        asm volatile("cp.async.commit_group;\n" ::);
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(WG_STAGES - 2));
+        __syncthreads();
+        const int nxt = c + WG_STAGES - 1;
+        if (nxt < n_chunks) load_chunk(c_begin + nxt, nxt % WG_STAGES);
+        asm volatile("cp.async.commit_group;\n" ::);
+        const int stage = c % WG_STAGES;
+        const uint32_t a_s = smem_u32t(sA + stage * A_STAGE), b_s = smem_u32t(sB + stage * B_STAGE);
+#pragma unroll
+        for (int ks = 0; ks < WG_BK / 16; ++ks) {
+            uint32_t af[4][4], bf[2][4];
+            const int mi = lane >> 3, r = lane & 7;
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {               // A stored [k][m]: matrices (k0-7,m0-7)(k0-7,m8-15)(k8-15,m0-7)(k8-15,m8-15)
+                const int k = ks * 16 + (mi >> 1) * 8 + r;
+                const int mcol = warp_m * 64 + mt * 16 + (mi & 1) * 8;
+                ldmatrix_x4_trans(af[mt], a_s + wg_off(k, mcol >> 3));
+            }
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {               // B stored [k][n]: (k0-7,n0-7)(k8-15,n0-7)(k0-7,n8-15)(k8-15,n8-15)
+                const int k = ks * 16 + (mi & 1) * 8 + r;
+                const int ncol = warp_n * 32 + np * 16 + (mi >> 1) * 8;
+                ldmatrix_x4_trans(bf[np], b_s + wg_off(k, ncol >> 3));
+            }
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+                    mma16816t(acc[mt][nt], af[mt], bf[nt >> 1][(nt & 1) * 2], bf[nt >> 1][(nt & 1) * 2 + 1]);
+        }
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::);
+
+    // fp32 atomics combine the K splits (and, for shared filters, several calls)
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int co = co0 + warp_m * 64 + mt * 16 + (lane >> 2) + h * 8;
+                const int ci = ci0 + warp_n * 32 + nt * 8 + (lane & 3) * 2;
+                if (co < p.Cout) {
+                    float* dst = p.dw + ((size_t)co * p.taps + tap) * p.Cin + ci;
+                    if (ci < p.Cin) atomicAdd(dst, acc[mt][nt][h * 2]);
+                    if (ci + 1 < p.Cin) atomicAdd(dst + 1, acc[mt][nt][h * 2 + 1]);
+                }
+            }
+}
+
+// ---------------------------------------------------------------- helpers --
+// dY *= (Y > 0): ReLU backward, in place, 8 halfs per thread.
+__global__ void __launch_bounds__(256)
+relu_bwd_kernel(uint4* __restrict__ dy, const uint4* __restrict__ y, int64_t n8) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        uint4 g = dy[i];
+        const uint4 v = __ldg(y + i);
+        __half2* gh = reinterpret_cast<__half2*>(&g);
+        const __half2* vh = reinterpret_cast<const __half2*>(&v);
+        const __half2 zero = __float2half2_rn(0.0f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gh[k] = __hmul2(gh[k], __hgt2(vh[k], zero));
+        dy[i] = g;
+    }
+}
+
+// db[c] += sum_rows dY[row][c]   (dY [rows][ld] fp16, first C columns)
+__global__ void __launch_bounds__(256)
+bias_grad_kernel(const __half* __restrict__ dy, float* __restrict__ db, int64_t rows, int ld, int C) {
+    const int c8 = blockIdx.x * 32 + (threadIdx.x & 31);             // channel group of 8
+    const int slice = threadIdx.x >> 5;                               // 8 row slices per block
+    if (c8 * 8 >= C) return;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t r = (int64_t)blockIdx.y * 8 + slice; r < rows; r += (int64_t)gridDim.y * 8) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(dy + r * ld) + c8);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(h[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (c8 * 8 + k < C) atomicAdd(db + c8 * 8 + k, acc[k]);
+}
+
+// wt[ci][KH-1-ky][KW-1-kx][co (padded to ldo)] = w[co][ky][kx][ci]
+__global__ void __launch_bounds__(256)
+filter_flip_transpose_kernel(const __half* __restrict__ w, __half* __restrict__ wt, int Cout, int KH, int KW, int Cin, int ldo) {
+    const int64_t total = (int64_t)Cin * KH * KW * ldo;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int co = (int)(e % ldo);
+        int64_t r = e / ldo;
+        const int kx = (int)(r % KW); r /= KW;
+        const int ky = (int)(r % KH);
+        const int ci = (int)(r / KH);
+        wt[e] = co < Cout ? w[(((size_t)co * KH + (KH - 1 - ky)) * KW + (KW - 1 - kx)) * Cin + ci] : __float2half_rn(0.0f);
+    }
+}
+
+// out[b][oy*s][ox*s][:] = in[b][oy][ox][:], zeros elsewhere  (out must be pre-zeroed once; written positions are fixed)
+__global__ void __launch_bounds__(256)
+upsample_zero_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int Ho, int Wo, int C8, int Hu, int Wu, int s, int64_t total) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(t % C8);
+        int64_t r = t / C8;
+        const int ox = (int)(r % Wo); r /= Wo;
+        const int oy = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        out[(((size_t)b * Hu + oy * s) * Wu + ox * s) * C8 + c8] = in[t];
+    }
+}
+
+// MaxPool2D backward: each input pixel gathers dY from the windows whose FIRST maximum (scan order ky, kx) it is.
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const __half* __restrict__ x, const __half* __restrict__ y, const __half* __restrict__ dy,
+                   __half* __restrict__ dx, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad_t, int pad_l,
+                   int accumulate, int64_t total) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(t % C);
+        int64_t r = t / C;
+        const int ix = (int)(r % W); r /= W;
+        const int iy = (int)(r % H);
+        const int b = (int)(r / H);
+        const float xv = __half2float(x[t]);
+        float g = 0.0f;
+        // windows (oy, ox) that contain (iy, ix)
+        for (int oy = max(0, (iy + pad_t - k + stride) / stride); oy <= min(Ho - 1, (iy + pad_t) / stride); ++oy)
+            for (int ox = max(0, (ix + pad_l - k + stride) / stride); ox <= min(Wo - 1, (ix + pad_l) / stride); ++ox) {
+                const size_t o = (((size_t)b * Ho + oy) * Wo + ox) * C + c;
+                if (__half2float(y[o]) != xv) continue;
+                // first maximum in scan order wins: any earlier element of the window equal to the max?
+                bool first = true;
+                for (int ky = 0; ky < k && first; ++ky)
+                    for (int kx = 0; kx < k; ++kx) {
+                        const int yy = oy * stride - pad_t + ky, xx = ox * stride - pad_l + kx;
+                        if (yy == iy && xx == ix) { ky = k; break; }
+                        if ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W &&
+                            __half2float(x[(((size_t)b * H + yy) * W + xx) * C + c]) == xv) { first = false; break; }
+                    }
+                if (first) g += __half2float(dy[o]);
+            }
+        dx[t] = __float2half_rn(accumulate ? g + __half2float(dx[t]) : g);
+    }
+}
+
+// L2Normalization backward (models/ssd_vgg16.py:63): y = x * r * s,  r = rsqrt(max(sum x^2, eps)).
+// dx = s*r*dy - x * r^3 * sum_c(dy*s*x)   (when sum x^2 > eps);  dscale[c] += sum_rows dy * x * r.
+__global__ void __launch_bounds__(256)
+l2norm_bwd_kernel(const __half* __restrict__ x, const float* __restrict__ scale, const __half* __restrict__ dy,
+                  __half* __restrict__ dx, float* __restrict__ dscale, int64_t rows, int C, int accumulate) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        const __half* xr = x + r * C;
+        const __half* gr = dy + r * C;
+        float ss = 0.0f, dot = 0.0f;
+        for (int c = lane; c < C; c += 32) {
+            const float xv = __half2float(xr[c]), gv = __half2float(gr[c]);
+            ss = fmaf(xv, xv, ss);
+            dot = fmaf(gv * __ldg(scale + c), xv, dot);
+        }
+        ss = warp_sum(ss); dot = warp_sum(dot);
+        const bool clamped = ss < 1e-12f;
+        const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+        const float coef = clamped ? 0.0f : dot * inv * inv * inv;
+        for (int c = lane; c < C; c += 32) {
+            const float xv = __half2float(xr[c]), gv = __half2float(gr[c]);
+            float g = gv * __ldg(scale + c) * inv - xv * coef;
+            if (accumulate) g += __half2float(dx[r * C + c]);
+            dx[r * C + c] = __float2half_rn(g);
+            atomicAdd(dscale + c, gv * xv * inv);
+        }
+    }
+}
+
+// Head gradient gather: dY[b][pix][0..A*L) <- g_logits, [A*L .. A*(L+4)) <- g_deltas, zero padding to ld.
+__global__ void __launch_bounds__(256)
+head_grad_gather_kernel(const float* __restrict__ g_logits, const float* __restrict__ g_deltas, __half* __restrict__ dy,
+                        int N, int L, int off, int HW, int A, int ld, int64_t total) {
+    const int AL = A * L, A4 = A * 4;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(t % ld);
+        const int64_t r = t / ld;
+        const int pix = (int)(r % HW), b = (int)(r / HW);
+        float v = 0.0f;
+        if (c < AL) v = g_logits[((size_t)b * N + off) * L + (size_t)pix * AL + c];
+        else if (c < AL + A4) v = g_deltas[((size_t)b * N + off) * 4 + (size_t)pix * A4 + (c - AL)];
+        dy[t] = __float2half_rn(v);
+    }
+}
+
+// Fused Adam (Keras defaults, trainer.py:92): g = grad * inv_scale + l2 * w;  m, v update;  w -= lr_t * m / (sqrt(v) + eps).
+// Also refreshes the fp16 working copy and accumulates sum(w^2) of the pre-update weights (regulariser loss).
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
+            __half* __restrict__ w16, int64_t n, float lr_t, float b1, float b2, float eps, float inv_scale, float l2,
+            float* __restrict__ sumsq) {
+    float local = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float wv = w[i];
+        const float gv = g[i] * inv_scale + l2 * wv;
+        const float mv = b1 * m[i] + (1.0f - b1) * gv;
+        const float vv = b2 * v[i] + (1.0f - b2) * gv * gv;
+        const float nw = wv - lr_t * mv / (sqrtf(vv) + eps);
+        m[i] = mv; v[i] = vv; w[i] = nw;
+        if (w16) w16[i] = __float2half_rn(nw);
+        local += wv * wv;
+    }
+    if (sumsq) {
+        local = warp_sum(local);
+        if ((threadIdx.x & 31) == 0 && local != 0.0f) atomicAdd(sumsq, local);
+    }
+}
+
+static int grid1d(int64_t threads, int per_sm = 8) {
+    int64_t blocks = (threads + 255) / 256, cap = (int64_t)sm_count() * per_sm;
+    return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+}  // namespace ssd
+
+using namespace ssd;
+
+extern "C" int ssd_conv2d_wgrad(const ssd_conv_desc* d, const void* d_dy, int ldy, float* d_dw, ssd_stream_t stream) {
+    SSD_REQUIRE_PTR(d); SSD_REQUIRE_PTR(d->in); SSD_REQUIRE_PTR(d_dy); SSD_REQUIRE_PTR(d_dw);
+    SSD_REQUIRE(d->B >= 1 && d->H >= 1 && d->W >= 1 && d->Cin >= 8 && d->Cin % 8 == 0 && d->Cout >= 1 && d->Ho >= 1 &&
+                d->Wo >= 1 && d->KH >= 1 && d->KW >= 1 && d->stride >= 1 && d->dilation >= 1 && ldy >= d->Cout && ldy % 8 == 0,
+                SSD_ERR_SHAPE, "ssd_conv2d_wgrad: bad shape (Cin=%d Cout=%d ldy=%d; Cin and ldy must be multiples of 8)",
+                d->Cin, d->Cout, ldy);
+    WgradK k;
+    k.x = (const __half*)d->in; k.dy = (const __half*)d_dy; k.dw = d_dw;
+    k.B = d->B; k.H = d->H; k.W = d->W; k.Cin = d->Cin; k.Ho = d->Ho; k.Wo = d->Wo; k.Cout = d->Cout; k.KW = d->KW;
+    k.stride = d->stride; k.dil = d->dilation; k.pad_t = d->pad_top; k.pad_l = d->pad_left;
+    k.HoWo = d->Ho * d->Wo; k.M = d->B * k.HoWo; k.ldy = ldy; k.taps = d->KH * d->KW;
+    k.chunks_total = (k.M + WG_BK - 1) / WG_BK;
+    const int tiles_m = (d->Cout + WG_BM - 1) / WG_BM;
+    k.tiles_n = (d->Cin + WG_BN - 1) / WG_BN;
+    const int base = tiles_m * k.tiles_n * k.taps;
+    int splits = (sm_count() * 2 + base - 1) / base;                       // ~2 CTAs per SM overall
+    splits = max(1, min(splits, (k.chunks_total + 7) / 8));
+    k.chunks_per_split = (k.chunks_total + splits - 1) / splits;
+    splits = (k.chunks_total + k.chunks_per_split - 1) / k.chunks_per_split;
+    const size_t smem = (size_t)WG_STAGES * WG_BK * (WG_BM + WG_BN) * 2;
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "ssd_conv2d_wgrad: cudaFuncSetAttribute");
+    dim3 grid(tiles_m * k.tiles_n, k.taps, splits);
+    conv_wgrad_kernel<<<grid, WG_THREADS, smem, as_stream(stream)>>>(k);
+    SSD_CHECK_LAUNCH("conv_wgrad_kernel");
+    return SSD_OK;
+}
+
+extern "C" int ssd_relu_bwd(void* d_dy, const void* d_y, int64_t n, ssd_stream_t stream) {
+    SSD_REQUIRE_PTR(d_dy); SSD_REQUIRE_PTR(d_y);
+    SSD_REQUIRE(n >= 0 && n % 8 == 0, SSD_ERR_SHAPE, "ssd_relu_bwd: n=%lld must be a multiple of 8", (long long)n);
+    if (n == 0) return SSD_OK;
+    relu_bwd_kernel<<<grid1d(n / 8, 16), 256, 0, as_stream(stream)>>>(reinterpret_cast<uint4*>(d_dy),
+                                                                      reinterpret_cast<const uint4*>(d_y), n / 8);
+    SSD_CHECK_LAUNCH("relu_bwd_kernel");
+    return SSD_OK;
+}
+
+extern "C" int ssd_bias_grad(const void* d_dy, float* d_db, int64_t rows, int ld, int C, ssd_stream_t stream) {
+    SSD_REQUIRE_PTR(d_dy); SSD_REQUIRE_PTR(d_db);
+    SSD_REQUIRE(rows >= 0 && ld % 8 == 0 && C >= 1 && C <= ld, SSD_ERR_SHAPE, "ssd_bias_grad: bad shape rows=%lld ld=%d C=%d",
+                (long long)rows, ld, C);
+    if (rows == 0) return SSD_OK;
+    const int gx = (C + 255) / 256;
+    const int64_t want_y = (rows + 7) / 8, cap_y = max(1, sm_count() * 4 / gx);
+    const int gy = (int)(want_y < cap_y ? want_y : cap_y);
+    bias_grad_kernel<<<dim3(gx, gy), 256, 0, as_stream(stream)>>>((const __half*)d_dy, d_db, rows, ld, C);
+    SSD_CHECK_LAUNCH("bias_grad_kernel");
+    return SSD_OK;
+}
+
+extern "C" int ssd_filter_flip_transpose(const void* d_w, void* d_wt, int Cout, int KH, int KW, int Cin, int ldo,
+                                         ssd_stream_t stream) {
+    SSD_REQUIRE_PTR(d_w); SSD_REQUIRE_PTR(d_wt);
+    SSD_REQUIRE(Cout >= 1 && KH >= 1 && KW >= 1 && Cin >= 1 && ldo >= Cout, SSD_ERR_SHAPE, "ssd_filter_flip_transpose: bad shape");
+    filter_flip_transpose_kernel<<<grid1d((int64_t)Cin * KH * KW * ldo, 8), 256, 0, as_stream(stream)>>>(
+        (const __half*)d_w, (__half*)d_wt, Cout, KH, KW, Cin, ldo);
+    SSD_CHECK_LAUNCH("filter_flip_transpose_kernel");
+    return SSD_OK;
+}
+
+extern "C" int ssd_upsample_zero(const void* d_in, void* d_out, int B, int Ho, int Wo, int C, int Hu, int Wu, int s,
+                                 ssd_stream_t stream) {
+    SSD_REQUIRE_PTR(d_in); SSD_REQUIRE_PTR(d_out);
+    SSD_REQUIRE(B >= 1 && Ho >= 1 && Wo >= 1 && C % 8 == 0 && s >= 1 && Hu >= (Ho - 1) * s + 1 && Wu >= (Wo - 1) * s + 1,
+                SSD_ERR_SHAPE, "ssd_upsample_zero: bad shape");
+    const int64_t total = (int64_t)B * Ho * Wo * (C / 8);
+    upsample_zero_kernel<<<grid1d(total, 8), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const uint4*>(d_in), reinterpret_cast<uint4*>(d_out), Ho, Wo, C / 8, Hu, Wu, s, total);
+    SSD_CHECK_LAUNCH("upsample_zero_kernel");
+    return SSD_OK;
+}
+
+extern "C" int ssd_maxpool_bwd(const void* d_x, const void* d_y, const void* d_dy, void* d_dx, int B, int H, int W, int C,
+                               int Ho, int Wo, int k, int stride, int pad_top, int pad_left, int accumulate,
+                               ssd_stream_t stream) {
+    SSD_REQUIRE_PTR(d_x); SSD_REQUIRE_PTR(d_y); SSD_REQUIRE_PTR(d_dy); SSD_REQUIRE_PTR(d_dx);
+    SSD_REQUIRE(B >= 1 && H >= 1 && W >= 1 && C >= 1 && k >= 1 && k <= 7 && stride >= 1, SSD_ERR_SHAPE, "ssd_maxpool_bwd: bad shape");
+    const int64_t total = (int64_t)B * H * W * C;
+    maxpool_bwd_kernel<<<grid1d(total, 16), 256, 0, as_stream(stream)>>>(
+        (const __half*)d_x, (const __half*)d_y, (const __half*)d_dy, (__half*)d_dx, H, W, C, Ho, Wo, k, stride, pad_top,
+        pad_left, accumulate, total);
+    SSD_CHECK_LAUNCH("maxpool_bwd_kernel");
+    return SSD_OK;
+}
+
+extern "C" int ssd_l2norm_bwd(const void* d_x, const float* d_scale, const void* d_dy, void* d_dx, float* d_dscale,
+                              int64_t rows, int C, int accumulate, ssd_stream_t stream) {
+    SSD_REQUIRE_PTR(d_x); SSD_REQUIRE_PTR(d_scale); SSD_REQUIRE_PTR(d_dy); SSD_REQUIRE_PTR(d_dx); SSD_REQUIRE_PTR(d_dscale);
+    SSD_REQUIRE(rows >= 0 && C >= 1, SSD_ERR_SHAPE, "ssd_l2norm_bwd: bad shape");
+    if (rows == 0) return SSD_OK;
+    l2norm_bwd_kernel<<<grid1d(rows * 32, 8), 256, 0, as_stream(stream)>>>(
+        (const __half*)d_x, d_scale, (const __half*)d_dy, (__half*)d_dx, d_dscale, rows, C, accumulate);
+    SSD_CHECK_LAUNCH("l2norm_bwd_kernel");
+    return SSD_OK;
+}
+
+extern "C" int ssd_head_grad_gather(const float* d_g_logits, const float* d_g_deltas, void* d_dy, int B, int N, int L,
+                                    int anchor_offset, int HW, int A, int ld, ssd_stream_t stream) {
+    SSD_REQUIRE_PTR(d_g_logits); SSD_REQUIRE_PTR(d_g_deltas); SSD_REQUIRE_PTR(d_dy);
+    SSD_REQUIRE(B >= 1 && N >= 1 && L >= 1 && HW >= 1 && A >= 1 && ld >= A * (L + 4) && anchor_offset >= 0 &&
+                anchor_offset + HW * A <= N, SSD_ERR_SHAPE, "ssd_head_grad_gather: bad shape");
+    const int64_t total = (int64_t)B * HW * ld;
+    head_grad_gather_kernel<<<grid1d(total, 8), 256, 0, as_stream(stream)>>>(d_g_logits, d_g_deltas, (__half*)d_dy, N, L,
+                                                                             anchor_offset, HW, A, ld, total);
+    SSD_CHECK_LAUNCH("head_grad_gather_kernel");
+    return SSD_OK;
+}
+
+extern "C" int ssd_adam_step(float* d_w, float* d_m, float* d_v, const float* d_grad, void* d_w16, int64_t n, float lr_t,
+                             float beta1, float beta2, float eps, float inv_scale, float l2, float* d_sumsq,
+                             ssd_stream_t stream) {
+    SSD_REQUIRE_PTR(d_w); SSD_REQUIRE_PTR(d_m); SSD_REQUIRE_PTR(d_v); SSD_REQUIRE_PTR(d_grad);
+    SSD_REQUIRE(n >= 0, SSD_ERR_SHAPE, "ssd_adam_step: n=%lld", (long long)n);
+    if (n == 0) return SSD_OK;
+    adam_kernel<<<grid1d(n, 8), 256, 0, as_stream(stream)>>>(d_w, d_m, d_v, d_grad, (__half*)d_w16, n, lr_t, beta1, beta2, eps,
+                                                            inv_scale, l2, d_sumsq);
+    SSD_CHECK_LAUNCH("adam_kernel");
+    return SSD_OK;
+}

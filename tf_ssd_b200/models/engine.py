@@ -521,6 +521,66 @@ class SSDModel(object):
         _ffi.check(_ffi.lib().ssd_softmax(_ffi.ptr(logits), B * N, L, _ffi.ptr(probs), _ffi.stream()), "ssd_softmax")
         return deltas.clone(), probs
 
+    # -- training (trainer.py:91-127) ------------------------------------------
+    def compile(self, optimizer: Any = None, loss: Any = None, **kwargs: Any) -> None:
+        """``model.compile(optimizer=Adam(learning_rate=1e-3), loss=[loc_loss_fn, conf_loss_fn])``
+        (trainer.py:91-94).  ``loss`` are the bound methods of a ``CustomLoss``; its
+        ``neg_pos_ratio`` / ``loc_loss_alpha`` parameterise the fused loss kernels."""
+        from tf_ssd_b200.models.train_engine import Trainer
+        lr = float(getattr(optimizer, "learning_rate", 1e-3) if optimizer is not None else 1e-3)
+        owner = getattr(loss[0], "__self__", None) if loss else None
+        ratio = float(getattr(owner, "neg_pos_ratio", 3.0))
+        alpha = float(getattr(owner, "loc_loss_alpha", 1.0))
+        self.trainer = Trainer(self, learning_rate=lr, neg_pos_ratio=ratio, loc_loss_alpha=alpha,
+                               beta_1=float(getattr(optimizer, "beta_1", 0.9)), beta_2=float(getattr(optimizer, "beta_2", 0.999)),
+                               epsilon=float(getattr(optimizer, "epsilon", 1e-7)))
+
+    def train_on_batch(self, x: Any, y: Tuple[Any, Any], learning_rate: Optional[float] = None) -> Dict[str, float]:
+        if getattr(self, "trainer", None) is None:
+            raise RuntimeError("call model.compile(optimizer=..., loss=[...]) first")
+        return self.trainer.train_on_batch(x, y, learning_rate)
+
+    def fit(self, data: Iterable[Any], steps_per_epoch: Optional[int] = None, validation_data: Optional[Iterable[Any]] = None,
+            validation_steps: Optional[int] = None, epochs: int = 1, callbacks: Optional[Sequence[Any]] = None,
+            verbose: int = 0) -> Dict[str, List[float]]:
+        """``model.fit(generator, steps_per_epoch=, validation_data=, validation_steps=, epochs=, callbacks=)``
+        (trainer.py:120-127).  ``data`` yields ``(img, (actual_deltas, actual_labels))`` like
+        ``train_utils.generator``.  Callbacks may implement ``on_epoch_begin(epoch, logs)`` returning a
+        learning rate (the reference's ``LearningRateScheduler(scheduler)``) and ``on_epoch_end(epoch, logs)``."""
+        if getattr(self, "trainer", None) is None:
+            raise RuntimeError("call model.compile(optimizer=..., loss=[...]) first")
+        history: Dict[str, List[float]] = {"loss": [], "val_loss": []}
+        it = iter(data)
+        vit = iter(validation_data) if validation_data is not None else None
+        for epoch in range(epochs):
+            lr = None
+            for cb in callbacks or ():
+                hook = getattr(cb, "on_epoch_begin", None)
+                r = hook(epoch, {}) if hook else None
+                if isinstance(r, float):
+                    lr = r
+            tot, n = 0.0, 0
+            for _ in range(steps_per_epoch or 1):
+                img, targets = next(it)
+                tot += self.trainer.train_on_batch(img, targets, lr)["loss"]
+                n += 1
+            logs = {"loss": tot / max(n, 1)}
+            if vit is not None:
+                vt, vn = 0.0, 0
+                for _ in range(validation_steps or 1):
+                    img, targets = next(vit)
+                    out = self.trainer.evaluate_batch(img, targets)
+                    vt += out["loss"]; vn += 1
+                logs["val_loss"] = vt / max(vn, 1)
+                history["val_loss"].append(logs["val_loss"])
+            history["loss"].append(logs["loss"])
+            for cb in callbacks or ():
+                hook = getattr(cb, "on_epoch_end", None)
+                if hook:
+                    hook(epoch, logs)
+        self.trainer.sync_weights_to_host()
+        return history
+
     def predict(self, data: Iterable[Any], steps: Optional[int] = None, verbose: int = 0):
         outs_d, outs_p = [], []
         for i, batch in enumerate(data):

@@ -1,0 +1,299 @@
+"""Training step behind ``model.compile(...)`` / ``model.fit(...)``
+(trainer.py:86-127 of the reference: Keras compile + fit with ``Adam(1e-3)`` and the two
+``CustomLoss`` callables).
+
+One step = forward plan (the inference launch list, activations kept) -> fused SSD loss forward
+and backward (``ssd_loss_fwd/bwd``, from logits) -> backward launch list derived by walking the
+forward plan in reverse -> optional gradient all-reduce (``dist_utils.GradBuckets``) -> fused
+Adam on fp32 master weights that also refreshes the fp16 working copies the plans point at.
+
+Mixed precision: activations and activation gradients are fp16 (loss-scaled), variable gradients,
+master weights and Adam moments are fp32.
+
+Scope: graphs without BatchNorm / depthwise layers (SSD300-VGG16, BASELINE.json config 3, and the
+``vgg16_512`` extension).  MobileNetV2 training additionally needs BatchNorm in training mode and
+the depthwise backward kernels, which are not built yet: ``Trainer`` raises for that backbone.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from tf_ssd_b200 import _ffi, dist_utils
+from tf_ssd_b200._ffi_conv import ACT_NONE, ConvDesc
+from tf_ssd_b200.models.engine import SSDModel, Step
+
+L2_REG = 5e-4                  # models/ssd_vgg16.py:76  reg_factor
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class Adam(object):
+    """Stand-in for ``tensorflow.keras.optimizers.Adam`` (trainer.py:8,92): a bag of hyper-parameters
+    consumed by ``model.compile``; the update itself is the fused ``ssd_adam_step`` kernel."""
+
+    def __init__(self, learning_rate: float = 1e-3, beta_1: float = 0.9, beta_2: float = 0.999, epsilon: float = 1e-7):
+        self.learning_rate, self.beta_1, self.beta_2, self.epsilon = learning_rate, beta_1, beta_2, epsilon
+
+
+class LearningRateScheduler(object):
+    """``tensorflow.keras.callbacks.LearningRateScheduler(schedule)`` (trainer.py:7,116)."""
+
+    def __init__(self, schedule):
+        self.schedule = schedule
+
+    def on_epoch_begin(self, epoch, logs=None):
+        return float(self.schedule(epoch))
+
+
+class Trainer(object):
+    """Owns the master weights, Adam state, gradient buffers and the backward launch list."""
+
+    def __init__(self, model: SSDModel, learning_rate: float = 1e-3, neg_pos_ratio: float = 3.0, loc_loss_alpha: float = 1.0,
+                 beta_1: float = 0.9, beta_2: float = 0.999, epsilon: float = 1e-7, loss_scale: float = 1024.0):
+        if model.backbone != "vgg16":
+            raise NotImplementedError(
+                "training is implemented for the BatchNorm-free VGG16 graphs only; MobileNetV2 needs BatchNorm in "
+                "training mode and depthwise backward kernels (not built yet)")
+        _ffi.check_device()
+        self.model = model
+        self.lib = _ffi.lib()
+        self.dev = _ffi.require_cuda()
+        self.lr, self.b1, self.b2, self.eps = float(learning_rate), float(beta_1), float(beta_2), float(epsilon)
+        self.neg_pos_ratio, self.alpha = float(neg_pos_ratio), float(loc_loss_alpha)
+        self.loss_scale = float(loss_scale)
+        self.t = 0
+        self._bwd: Dict[int, List[Tuple[Any, tuple, tuple]]] = {}
+        self._state: Dict[int, Dict[str, Any]] = {}
+        self._build_variables()
+
+    # -- variables: fp32 masters in the kernels' layouts, views into flat gradient buckets ---------------------
+    def _build_variables(self) -> None:
+        m = self.model
+        plan = m.plan(1)                              # forces every packed (fp16, OHWI) tensor into existence
+        self.vars: Dict[str, Dict[str, Any]] = {}
+        shapes = []
+        for s in plan.steps:
+            if s.kind == "conv":
+                w16, b32 = s.meta["w"], s.meta["bias"]
+                self.vars[s.name + "/kernel"] = dict(w16=w16, master=w16.float().clone(), l2=0.0)
+                self.vars[s.name + "/bias"] = dict(w16=None, master=b32, l2=0.0)        # bias buffers are fp32 already
+                shapes += [(s.name + "/kernel", tuple(w16.shape)), (s.name + "/bias", tuple(b32.shape))]
+            elif s.kind == "l2norm":
+                sc = s.meta["scale"]
+                self.vars[s.name + "/scale"] = dict(w16=None, master=sc, l2=0.0)
+                shapes.append((s.name + "/scale", tuple(sc.shape)))
+        for k in m.l2_kernels:                        # Keras name "<layer>/kernel" == step name + "/kernel"
+            if k in self.vars:
+                self.vars[k]["l2"] = 2.0 * L2_REG
+        self.grads = dist_utils.GradBuckets(shapes, self.dev)
+        for name, v in self.vars.items():
+            v["grad"] = self.grads.views[name]
+            v["m"] = torch.zeros_like(v["master"])
+            v["v"] = torch.zeros_like(v["master"])
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=self.dev)
+
+    def sync_weights_to_host(self) -> None:
+        """Write the trained variables back into ``model.weights`` (Keras names / layouts)."""
+        m = self.model
+        for name, v in self.vars.items():
+            arr = v["master"].detach().cpu().numpy()
+            layer, var = name.rsplit("/", 1)
+            if layer.endswith("_conv_head"):
+                idx = layer.split("_")[0]
+                nl = m.weights[f"{idx}_conv_label_output/bias"].shape[0]
+                if var == "kernel":
+                    hwio = arr.transpose(1, 2, 3, 0)
+                    m.weights[f"{idx}_conv_label_output/kernel"] = np.ascontiguousarray(hwio[..., :nl])
+                    m.weights[f"{idx}_conv_boxes_output/kernel"] = np.ascontiguousarray(hwio[..., nl:])
+                else:
+                    m.weights[f"{idx}_conv_label_output/bias"] = arr[:nl].copy()
+                    m.weights[f"{idx}_conv_boxes_output/bias"] = arr[nl:].copy()
+            elif var == "kernel":
+                cin = m.weights[name].shape[2]
+                m.weights[name] = np.ascontiguousarray(arr.transpose(1, 2, 3, 0)[:, :, :cin, :])
+            else:
+                m.weights[name] = arr.copy()
+
+    # -- backward launch list ---------------------------------------------------------------------------------
+    def _prepare(self, B: int) -> Dict[str, Any]:
+        if B in self._state:
+            return self._state[B]
+        m, lib, dev = self.model, self.lib, self.dev
+        plan = m.plan(B)
+        N, L = m.n_anchors, m.total_labels
+        st: Dict[str, Any] = dict(plan=plan)
+        st["g_deltas"] = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
+        st["g_logits"] = torch.empty((B, N, L), dtype=torch.float32, device=dev)
+        st["loc"] = torch.empty((B,), dtype=torch.float32, device=dev)
+        st["conf"] = torch.empty((B,), dtype=torch.float32, device=dev)
+        st["ws"] = _ffi.workspace(lib.ssd_loss_workspace_bytes(B, N, L))
+        keep: List[Any] = []
+        launches: List[Tuple[Any, tuple, str]] = []
+        grad_of: Dict[int, torch.Tensor] = {}       # activation data_ptr -> fp16 gradient buffer
+        written: Dict[int, bool] = {}
+
+        def grad_buf(t: torch.Tensor) -> torch.Tensor:
+            if t.data_ptr() not in grad_of:
+                grad_of[t.data_ptr()] = torch.zeros_like(t)
+                written[t.data_ptr()] = False
+            return grad_of[t.data_ptr()]
+
+        def add(fn, args, what):
+            launches.append((fn, args, what))
+
+        first_conv_input = None
+        for s in plan.steps:
+            if s.kind == "cast":
+                first_conv_input = s.keep[0].data_ptr()
+
+        for s in reversed(plan.steps):
+            mt = s.meta
+            if s.kind == "conv":
+                x, w16 = mt["x"], mt["w"]
+                cout, k, stride, dil = mt["cout"], mt["k"], mt["stride"], mt["dilation"]
+                Ho, Wo = mt["Ho"], mt["Wo"]
+                H, W, cin = x.shape[1], x.shape[2], x.shape[3]
+                ldy = _pad8(cout)
+                if "head" in mt:
+                    off, cnt, A = mt["head"]
+                    dy = torch.zeros((B, Ho, Wo, ldy), dtype=torch.float16, device=dev)
+                    add(lib.ssd_head_grad_gather, (_ffi.ptr(st["g_logits"]), _ffi.ptr(st["g_deltas"]), _ffi.ptr(dy), B, N, L,
+                                                   off, Ho * Wo, A, ldy), s.name + ":gather")
+                else:
+                    out = mt["out0"]
+                    dy = grad_of[out.data_ptr()]
+                    assert written[out.data_ptr()], s.name
+                    if mt["act"] != ACT_NONE:
+                        add(lib.ssd_relu_bwd, (_ffi.ptr(dy), _ffi.ptr(out), out.numel()), s.name + ":relu")
+                keep.append(dy)
+                # filter + bias gradients
+                d = ConvDesc()
+                d.inp = x.data_ptr()
+                d.B, d.H, d.W, d.Cin, d.Ho, d.Wo, d.Cout = B, H, W, cin, Ho, Wo, cout
+                d.KH = d.KW = k
+                d.stride, d.dilation, d.pad_top, d.pad_left = stride, dil, mt["ph"][0], mt["pw"][0]
+                keep.append(d)
+                add(lib.ssd_conv2d_wgrad, (C.byref(d), _ffi.ptr(dy), ldy, _ffi.ptr(self.vars[s.name + "/kernel"]["grad"])),
+                    s.name + ":wgrad")
+                add(lib.ssd_bias_grad, (_ffi.ptr(dy), _ffi.ptr(self.vars[s.name + "/bias"]["grad"]), B * Ho * Wo, ldy, cout),
+                    s.name + ":bgrad")
+                # data gradient (not needed for the layer fed by the image)
+                if x.data_ptr() == first_conv_input:
+                    continue
+                wt = torch.zeros((cin, k, k, ldy), dtype=torch.float16, device=dev)
+                add(lib.ssd_filter_flip_transpose, (_ffi.ptr(w16), _ffi.ptr(wt), cout, k, k, cin, ldy), s.name + ":flip")
+                src, Hs, Ws = dy, Ho, Wo
+                if stride > 1:
+                    Hs, Ws = (Ho - 1) * stride + 1, (Wo - 1) * stride + 1
+                    src = torch.zeros((B, Hs, Ws, ldy), dtype=torch.float16, device=dev)
+                    add(lib.ssd_upsample_zero, (_ffi.ptr(dy), _ffi.ptr(src), B, Ho, Wo, ldy, Hs, Ws, stride), s.name + ":up")
+                dx = grad_buf(x)
+                acc = written[x.data_ptr()]
+                g = ConvDesc()
+                g.inp, g.weight, g.bias = src.data_ptr(), wt.data_ptr(), None
+                g.residual = dx.data_ptr() if acc else None
+                g.out0 = dx.data_ptr()
+                g.B, g.H, g.W, g.Cin, g.Ho, g.Wo, g.Cout = B, Hs, Ws, ldy, H, W, cin
+                g.KH = g.KW = k
+                g.stride, g.dilation = 1, dil
+                g.pad_top, g.pad_left = (k - 1) * dil - mt["ph"][0], (k - 1) * dil - mt["pw"][0]
+                g.act, g.out_f32, g.split = ACT_NONE, 0, cin
+                g.img_stride0, g.pix_stride0 = H * W * cin, cin
+                keep += [wt, src, g]
+                add(lib.ssd_conv2d, (C.byref(g),), s.name + ":dgrad")
+                written[x.data_ptr()] = True
+            elif s.kind == "pool":
+                x, out = mt["x"], mt["out"]
+                dy = grad_of[out.data_ptr()]
+                dx = grad_buf(x)
+                acc = written[x.data_ptr()]
+                add(lib.ssd_maxpool_bwd, (_ffi.ptr(x), _ffi.ptr(out), _ffi.ptr(dy), _ffi.ptr(dx), B, x.shape[1], x.shape[2],
+                                          x.shape[3], out.shape[1], out.shape[2], mt["k"], mt["stride"], mt["ph"][0],
+                                          mt["pw"][0], int(acc)), s.name + ":pool")
+                written[x.data_ptr()] = True
+            elif s.kind == "l2norm":
+                x, out = mt["x"], mt["out"]
+                dy = grad_of[out.data_ptr()]
+                dx = grad_buf(x)
+                acc = written[x.data_ptr()]
+                add(lib.ssd_l2norm_bwd, (_ffi.ptr(x), _ffi.ptr(mt["scale"]), _ffi.ptr(dy), _ffi.ptr(dx),
+                                         _ffi.ptr(self.vars[s.name + "/scale"]["grad"]), B * x.shape[1] * x.shape[2],
+                                         x.shape[3], int(acc)), s.name + ":l2norm")
+                written[x.data_ptr()] = True
+        st["launches"], st["keep"], st["grad_of"] = launches, keep, grad_of
+        self._state[B] = st
+        return st
+
+    # -- one step ---------------------------------------------------------------------------------------------
+    def forward_backward(self, images: Any, actual_deltas: Any, actual_labels: Any) -> Dict[str, torch.Tensor]:
+        """Forward, loss, backward: fills the gradient buckets (loss-scaled) and returns the per-image losses."""
+        m, lib = self.model, self.lib
+        B = int(images.shape[0])
+        st = self._prepare(B)
+        plan = st["plan"]
+        N, L = m.n_anchors, m.total_labels
+        ad, al = _ffi.to_dev(actual_deltas), _ffi.to_dev(actual_labels)
+        m._to_image_buffer(plan, images)
+        plan.run()
+        stream = _ffi.stream()
+        _ffi.check(lib.ssd_loss_fwd(_ffi.ptr(ad), _ffi.ptr(plan.deltas), _ffi.ptr(al), _ffi.ptr(plan.logits), B, N, L,
+                                    self.neg_pos_ratio, self.alpha, 1, _ffi.ptr(st["loc"]), _ffi.ptr(st["conf"]),
+                                    _ffi.ptr(st["ws"]), st["ws"].numel(), stream), "ssd_loss_fwd")
+        # Keras reduces each loss with SUM_OVER_BATCH_SIZE (mean over the batch) and sums the two (trainer.py:91-94)
+        _ffi.check(lib.ssd_loss_bwd(_ffi.ptr(ad), _ffi.ptr(plan.deltas), _ffi.ptr(al), _ffi.ptr(plan.logits), B, N, L,
+                                    self.alpha, self.loss_scale / B, _ffi.ptr(st["g_deltas"]), _ffi.ptr(st["g_logits"]),
+                                    _ffi.ptr(st["ws"]), st["ws"].numel(), stream), "ssd_loss_bwd")
+        self.grads.zero_()
+        for fn, args, what in st["launches"]:
+            rc = fn(*args, stream)
+            if rc != 0:
+                _ffi.check(rc, what)
+        return dict(loc=st["loc"], conf=st["conf"])
+
+    def apply_gradients(self, learning_rate: Optional[float] = None) -> None:
+        """Mean over ranks (one all-reduce per bucket), then fused Adam on every variable."""
+        self.grads.allreduce_mean_()
+        self.t += 1
+        lr = self.lr if learning_rate is None else float(learning_rate)
+        lr_t = lr * math.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
+        self.sumsq.zero_()
+        stream = _ffi.stream()
+        for name, v in self.vars.items():
+            w16 = v["w16"]
+            _ffi.check(self.lib.ssd_adam_step(_ffi.ptr(v["master"]), _ffi.ptr(v["m"]), _ffi.ptr(v["v"]), _ffi.ptr(v["grad"]),
+                                              _ffi.ptr(w16), v["master"].numel(), lr_t, self.b1, self.b2, self.eps,
+                                              1.0 / self.loss_scale, v["l2"], _ffi.ptr(self.sumsq) if v["l2"] else None,
+                                              stream), "ssd_adam_step")
+
+    def evaluate_batch(self, images: Any, targets: Tuple[Any, Any]) -> Dict[str, float]:
+        """Validation loss of one batch (no gradient, no update): mean loc + mean conf (+ the regulariser of the
+        last training step, like Keras adds ``model.losses`` to ``val_loss``)."""
+        m, lib = self.model, self.lib
+        B = int(images.shape[0])
+        st = self._prepare(B)
+        plan = st["plan"]
+        ad, al = _ffi.to_dev(targets[0]), _ffi.to_dev(targets[1])
+        m._to_image_buffer(plan, images)
+        plan.run()
+        _ffi.check(lib.ssd_loss_fwd(_ffi.ptr(ad), _ffi.ptr(plan.deltas), _ffi.ptr(al), _ffi.ptr(plan.logits), B, m.n_anchors,
+                                    m.total_labels, self.neg_pos_ratio, self.alpha, 1, _ffi.ptr(st["loc"]), _ffi.ptr(st["conf"]),
+                                    _ffi.ptr(st["ws"]), st["ws"].numel(), _ffi.stream()), "ssd_loss_fwd")
+        loc, conf = float(st["loc"].mean()), float(st["conf"].mean())
+        reg = L2_REG * float(self.sumsq)
+        return dict(loss=loc + conf + reg, loc_loss=loc, conf_loss=conf, reg_loss=reg)
+
+    def train_on_batch(self, images: Any, targets: Tuple[Any, Any], learning_rate: Optional[float] = None) -> Dict[str, float]:
+        """One optimisation step; ``targets = (actual_deltas, actual_labels)`` as ``train_utils.generator`` yields."""
+        out = self.forward_backward(images, targets[0], targets[1])
+        self.apply_gradients(learning_rate)
+        loc, conf = float(out["loc"].mean()), float(out["conf"].mean())
+        reg = L2_REG * float(self.sumsq)
+        return dict(loss=loc + conf + reg, loc_loss=loc, conf_loss=conf, reg_loss=reg)
