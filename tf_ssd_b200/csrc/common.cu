@@ -27,7 +27,7 @@ bool pdl_enabled() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("SSD_B200_PDL");
-        v = (e && e[0] == '0') ? 0 : 1;
+        v = (e && e[0] == '1') ? 1 : 0;      // opt-in: +1.3 % on the MobileNetV2 step, but ncu cannot serialise PDL chains
     }
     return v == 1;
 }

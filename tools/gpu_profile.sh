@@ -2,6 +2,7 @@
 # Runs on the GPU box (via gpurun): ncu captures -> small CSV summaries in gpurun_out/.
 # usage: tools/gpu_profile.sh <tag> [box] [launches] [conv]
 set -u
+export SSD_B200_PDL=0
 tag=$1; shift
 OUT=gpurun_out
 mkdir -p $OUT

@@ -1,0 +1,115 @@
+"""Config-3 measurement helper (BASELINE.json configs[2]): SSD300-VGG16, batch 32 per GPU, one full
+training step = IoU match + target encode -> forward -> hard-negative-mining loss -> backward ->
+(all-reduce) -> Adam.  Used by bench.py (``training`` key) and runnable on its own / under torchrun.
+
+    python tools/train_bench.py [--steps K] [--warmup W] [--batch B] [--check-dp]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def build(batch, seed=1234):
+    import torch
+    from tf_ssd_b200 import synth
+    from tf_ssd_b200.models import ssd_vgg16
+    from tf_ssd_b200.models.train_engine import Trainer
+    from tf_ssd_b200.utils import bbox_utils, train_utils
+    hp = train_utils.get_hyper_params("vgg16")
+    hp["total_labels"] = 21
+    model = ssd_vgg16.get_model(hp, seed=seed)
+    trainer = Trainer(model)
+    priors = bbox_utils.generate_prior_boxes(hp["feature_map_shapes"], hp["aspect_ratios"])
+    return hp, model, trainer, priors
+
+
+def make_batch(batch, hp, seed):
+    import torch
+    from tf_ssd_b200 import synth
+    img = torch.from_numpy(synth.make_images(batch, hp["img_size"], seed=seed)).cuda()
+    gt, lab = synth.make_ground_truth(batch, padded=16, seed=seed + 1)
+    return img, torch.from_numpy(gt).cuda(), torch.from_numpy(lab).cuda()
+
+
+def train_step(trainer, priors, hp, img, gt, lab):
+    from tf_ssd_b200.utils import train_utils
+    deltas, onehot = train_utils.calculate_actual_outputs(priors, gt, lab, hp)       # IoU match + encode (fused kernel)
+    trainer.forward_backward(img, deltas, onehot)
+    trainer.apply_gradients()
+
+
+def measure(steps=10, warmup=3, batch=32):
+    """Returns a dict with images/s (whole job) for the training step; call under torchrun for N > 1."""
+    import torch
+    from tf_ssd_b200 import dist_utils
+    rank, local_rank, world = dist_utils.env_rank()
+    torch.cuda.set_device(local_rank)
+    dist_utils.init_from_env("nccl")
+    hp, model, trainer, priors = build(batch)
+    data = [make_batch(batch, hp, 100 + 10 * rank + i) for i in range(2)]
+    for i in range(warmup):
+        train_step(trainer, priors, hp, *data[i % 2])
+    dist_utils.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        train_step(trainer, priors, hp, *data[i % 2])
+    e1.record()
+    dist_utils.barrier()
+    torch.cuda.synchronize()
+    ms = dist_utils.max_over_ranks(float(e0.elapsed_time(e1)), torch.device("cuda", local_rank))
+    flops = 3 * 2.0 * model.macs_per_image * batch                        # fwd + dgrad + wgrad
+    return {"workload": "SSD300-VGG16 batch=32/GPU training step (IoU match + encode, forward, hard-negative loss, backward, "
+                        "grad all-reduce, Adam), fp16 activations / fp32 master weights",
+            "value": world * batch * steps / (ms / 1e3), "unit": "images/s", "ms_per_step": ms / steps, "n_gpus": world,
+            "steps": steps, "conv_tflops": world * flops * steps / (ms / 1e3) / 1e12,
+            "grad_allreduce_bytes": int(sum(b.numel() for b in trainer.grads.buckets) * 4)}
+
+
+def check_dp():
+    """2 ranks x B=2 must produce the same averaged gradients as 1 process on the concatenated batch of 4."""
+    import torch
+    from tf_ssd_b200 import dist_utils
+    from tf_ssd_b200.utils import train_utils
+    rank, local_rank, world = dist_utils.env_rank()
+    torch.cuda.set_device(local_rank)
+    dist_utils.init_from_env("nccl")
+    hp, model, trainer, priors = build(2)
+    img, gt, lab = make_batch(2 * world, hp, 7)
+    b, e = dist_utils.shard_range(2 * world, rank, world)
+    d, oh = train_utils.calculate_actual_outputs(priors, gt[b:e], lab[b:e], hp)
+    trainer.forward_backward(img[b:e], d, oh)
+    trainer.grads.allreduce_mean_()
+    torch.cuda.synchronize()
+    mine = torch.cat([bk.flatten() for bk in trainer.grads.buckets])
+    if rank == 0:
+        hp1, model1, trainer1, _ = build(2 * world)
+        d1, oh1 = train_utils.calculate_actual_outputs(priors, gt, lab, hp1)
+        trainer1.forward_backward(img, d1, oh1)
+        torch.cuda.synchronize()
+        ref = torch.cat([bk.flatten() for bk in trainer1.grads.buckets])
+        rel = float((mine - ref).norm() / ref.norm())
+        print(json.dumps({"dp_equivalence_rel_l2": rel, "world": world, "ok": rel < 2e-3}))
+        assert rel < 2e-3, rel
+    dist_utils.barrier()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--check-dp", action="store_true")
+    a = ap.parse_args()
+    if a.check_dp:
+        check_dp()
+    else:
+        out = measure(a.steps, a.warmup, a.batch)
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps(out))
