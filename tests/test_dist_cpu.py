@@ -33,7 +33,7 @@ def _worker(rank, world, port, out_dir):
     # timing: the slowest rank wins
     assert dist_utils.max_over_ranks(1.0 + rank, dev) == float(world)
     # gradient buckets: mean over ranks, small bucket size to force several buckets
-    shapes = [("a/kernel", (3, 3, 8, 16)), ("a/bias", (16,)), ("b/kernel", (1, 1, 16, 5)), ("c/kernel", (7,))]
+    shapes = [("a/kernel", (3, 3, 8, 16)), ("a/bias", (150,)), ("b/kernel", (1, 1, 16, 5)), ("c/kernel", (7,)), ("d/bias", (3,))]
     gb = dist_utils.GradBuckets(shapes, dev, bucket_bytes=2048)
     assert len(gb.buckets) >= 2
     rng = np.random.default_rng(5)          # same stream on every rank

@@ -589,4 +589,196 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
     return SSD_OK;
 }
 
+// ======================================================================================
+// Filter gradient on tcgen05:  dW[co, tap, ci] += sum_pixels dY[pix, co] * X[pix (+) tap, ci]
+//
+// Both operands are pixel-major in memory (NHWC), i.e. "MN-major" for the tensor core: the
+// reduction dimension K (pixels) is the ROW index of both shared-memory tiles.  A pixel tile is a
+// (bw x bh) box of one image; TMA loads dY[box, 64 co] and X[box shifted by the tap, 64 ci] as
+// [64 pixels][128 B] swizzled tiles (out-of-image pixels are zero-filled, which is exactly the
+// convolution padding), one tile per 64-channel group.  UMMA descriptors: MN-major, SWIZZLE_128B,
+// SBO = 1024 B (next 8 pixel rows), LBO = 64*128 B (next 64-channel group), +2048 B per UMMA_K = 16.
+// Accumulator 128 (co) x BN (ci) fp32 in TMEM; split-K over pixel tiles across blockIdx.z,
+// combined with vector fp32 atomics.
+constexpr int WG5_KP = 64;            // pixels per k-block
+constexpr int WG5_STAGES = 4;
+constexpr int WG5_THREADS = 192;      // warp 0 TMA, warp 1 MMA/TMEM, warps 2-5 epilogue
+
+struct Wg5Params {
+    int Cout, Cin, taps, KW, dil, pad_t, pad_l;
+    int bw, bh, tiles_w, tiles_h, B;          // pixel tiles: (tiles_w * tiles_h) per image
+    int n_ptiles, ptiles_per_split;
+    int BN, n_groups;                         // ci tile (multiple of 64), groups of 64
+    int tiles_n;
+    uint32_t idesc, tmem_cols, a_bytes, b_bytes;
+    float* dw;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__global__ void __launch_bounds__(WG5_THREADS, 1)
+conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                          const Wg5Params p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t grp = WG5_KP * 128;                           // one [64 px][128 B] tile = 8 KB
+    const uint32_t a_stage = 2 * grp, b_stage = (uint32_t)p.n_groups * grp;
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + WG5_STAGES * a_stage;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + WG5_STAGES * b_stage);     // full[S] | empty[S] | done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG5_STAGES + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = smem_addr(bars), bar_empty = smem_addr(bars + WG5_STAGES), bar_done = smem_addr(bars + 2 * WG5_STAGES);
+
+    const int tile_m = blockIdx.x / p.tiles_n, tile_n = blockIdx.x - tile_m * p.tiles_n;
+    const int co0 = tile_m * 128, ci0 = tile_n * p.BN;
+    const int tap = blockIdx.y, ky = tap / p.KW, kx = tap - ky * p.KW;
+    const int pt0 = blockIdx.z * p.ptiles_per_split, pt1 = min(p.n_ptiles, pt0 + p.ptiles_per_split);
+    const int nkb = pt1 - pt0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_dy);
+        tma_prefetch_desc(&map_x);
+        for (int s = 0; s < WG5_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_addr(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int per_img = p.tiles_w * p.tiles_h;
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % WG5_STAGES;
+                if (i >= WG5_STAGES) mbar_wait(bar_empty + 8 * s, ((i / WG5_STAGES) - 1) & 1);
+                const int pt = pt0 + i;
+                const int b = pt / per_img, tr = pt - b * per_img, th = tr / p.tiles_w, tw = tr - th * p.tiles_w;
+                const int oy0 = th * p.bh, ox0 = tw * p.bw;
+                mbar_expect_tx(bar_full + 8 * s, p.a_bytes + p.b_bytes);
+                const uint32_t dst_a = smem_addr(sA + (size_t)s * a_stage), dst_b = smem_addr(sB + (size_t)s * b_stage);
+                tma_load_4d(dst_a, &map_dy, bar_full + 8 * s, co0, ox0, oy0, b);
+                tma_load_4d(dst_a + grp, &map_dy, bar_full + 8 * s, co0 + 64, ox0, oy0, b);
+                for (int g = 0; g < p.n_groups; ++g)
+                    tma_load_4d(dst_b + g * grp, &map_x, bar_full + 8 * s, ci0 + g * 64, ox0 + kx * p.dil - p.pad_l,
+                                oy0 + ky * p.dil - p.pad_t, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % WG5_STAGES;
+                mbar_wait(bar_full + 8 * s, (i / WG5_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t da = umma_desc_mn_sw128(smem_addr(sA + (size_t)s * a_stage), grp);
+                const uint64_t db = umma_desc_mn_sw128(smem_addr(sB + (size_t)s * b_stage), grp);
+#pragma unroll
+                for (int k = 0; k < WG5_KP / 16; ++k)            // 16 pixel rows = 2048 B per UMMA_K
+                    umma_f16(tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), p.idesc, (i | k) != 0);
+                umma_commit(bar_empty + 8 * s);
+            }
+            umma_commit(bar_done);
+        }
+    } else {
+        const int q = warp & 3;
+        const int co = co0 + q * 32 + lane;
+        mbar_wait(bar_done, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+            if (ci0 + c0 >= p.Cin) break;
+            uint32_t acc[16];
+            tmem_ld16(trow + (uint32_t)c0, acc);
+            if (co < p.Cout) {
+                float* dst = p.dw + ((size_t)co * p.taps + tap) * p.Cin + ci0 + c0;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    if (ci0 + c0 + j < p.Cin)
+                        atomicAdd(reinterpret_cast<float4*>(dst + j),
+                                  make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
+                                              __uint_as_float(acc[j + 3])));
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+bool conv_wgrad_tcgen05_supported(const ssd_conv_desc* d, int ldy) {
+    return d->stride == 1 && d->Cin % 64 == 0 && d->KH == d->KW && ldy % 8 == 0 &&
+           (reinterpret_cast<uintptr_t>(d->in) & 15) == 0;
+}
+
+int conv_wgrad_tcgen05_launch(const ssd_conv_desc* d, const void* d_dy, int ldy, float* d_dw, cudaStream_t st) {
+    Wg5Params p;
+    memset(&p, 0, sizeof(p));
+    p.Cout = d->Cout; p.Cin = d->Cin; p.taps = d->KH * d->KW; p.KW = d->KW; p.dil = d->dilation;
+    p.pad_t = d->pad_top; p.pad_l = d->pad_left; p.B = d->B; p.dw = d_dw;
+    // pixel box of 64 output pixels with the least out-of-image waste
+    double best = -1.0;
+    for (int bw = 1; bw <= WG5_KP; bw *= 2) {
+        const int bh = WG5_KP / bw;
+        const int tw = (d->Wo + bw - 1) / bw, th = (d->Ho + bh - 1) / bh;
+        const double eff = (double)d->Wo * d->Ho / ((double)tw * bw * th * bh) + 1e-6 * bw;
+        if (eff > best) { best = eff; p.bw = bw; p.bh = bh; p.tiles_w = tw; p.tiles_h = th; }
+    }
+    p.n_ptiles = p.tiles_w * p.tiles_h * d->B;
+    p.BN = d->Cin >= 256 ? 256 : d->Cin;                       // Cin is a multiple of 64
+    p.n_groups = p.BN / 64;
+    p.tiles_n = (d->Cin + p.BN - 1) / p.BN;
+    const int tiles_m = (d->Cout + 127) / 128;
+    p.tmem_cols = p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+    p.idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // MN-major A and B
+    p.a_bytes = 2 * WG5_KP * 128;
+    p.b_bytes = (uint32_t)p.n_groups * WG5_KP * 128;
+
+    CUtensorMap map_dy, map_x;
+    {
+        uint64_t dims[4] = {(uint64_t)ldy, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->B};
+        uint64_t str[3] = {(uint64_t)ldy * 2, (uint64_t)d->Wo * ldy * 2, (uint64_t)d->Ho * d->Wo * ldy * 2};
+        uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, 1};
+        int rc = cached_map(&map_dy, d_dy, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+        uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
+        uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, 1};
+        int rc = cached_map(&map_x, d->in, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    const int sms = sm_count();
+    const int base = tiles_m * p.tiles_n * p.taps;
+    int splits = max(1, min((2 * sms + base - 1) / base, (p.n_ptiles + 7) / 8));
+    p.ptiles_per_split = (p.n_ptiles + splits - 1) / splits;
+    splits = (p.n_ptiles + p.ptiles_per_split - 1) / p.ptiles_per_split;
+    const size_t smem = (size_t)WG5_STAGES * (p.a_bytes + p.b_bytes) + (2 * WG5_STAGES + 1) * 8 + 16 + 1024;
+    static thread_local int attr_dev = -1;
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (attr_dev != cur_dev) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "conv_wgrad_tcgen05: cudaFuncSetAttribute");
+        attr_dev = cur_dev;
+    }
+    dim3 grid(tiles_m * p.tiles_n, p.taps, splits);
+    conv_wgrad_tcgen05_kernel<<<grid, WG5_THREADS, smem, st>>>(map_dy, map_x, p);
+    SSD_CHECK_LAUNCH("conv_wgrad_tcgen05_kernel");
+    return SSD_OK;
+}
+
 }  // namespace ssd

@@ -14,6 +14,9 @@
 
 #include "common.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
 namespace ssd {
 
 __device__ __forceinline__ uint32_t smem_u32t(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -52,11 +55,27 @@ conv_wgrad_kernel(const WgradK p) {
     unsigned char* sB = smem + WG_STAGES * A_STAGE;        // X tile   [pix][ci]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int warp_m = warp & 1, warp_n = warp >> 1;       // 2 x 4 warps, warp tile 64 (co) x 32 (ci)
+    // The GEMM N dimension is the merged (tap, ci) index n = tap*Cin + ci -- dW[co][tap][ci] is contiguous in n --
+    // so a dY tile is read once per 128 merged columns instead of once per tap (Cin = 8: one tile for all 9 taps).
     const int tile_m = blockIdx.x / p.tiles_n, tile_n = blockIdx.x - tile_m * p.tiles_n;
-    const int co0 = tile_m * WG_BM, ci0 = tile_n * WG_BN;
-    const int tap = blockIdx.y, ky = tap / p.KW, kx = tap - ky * p.KW;
+    const int co0 = tile_m * WG_BM, n0 = tile_n * WG_BN;
+    const int NT = p.taps * p.Cin;
     const int c_begin = blockIdx.z * p.chunks_per_split;
     const int c_end = min(p.chunks_total, c_begin + p.chunks_per_split);
+    // the two 16-byte pieces this thread gathers per chunk have a fixed (tap, ci)
+    int pk_ci[2], pk_dy[2], pk_dx[2];
+    bool pk_ok[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int pc = (tid + i * WG_THREADS) & 15;
+        const int n = n0 + pc * 8;
+        pk_ok[i] = n < NT;
+        const int tap = pk_ok[i] ? n / p.Cin : 0;
+        pk_ci[i] = n - tap * p.Cin;
+        const int ky = tap / p.KW, kx = tap - ky * p.KW;
+        pk_dy[i] = ky * p.dil - p.pad_t;
+        pk_dx[i] = kx * p.dil - p.pad_l;
+    }
 
     auto load_chunk = [&](int chunk, int stage) {
         const uint32_t a_dst = smem_u32t(sA + stage * A_STAGE), b_dst = smem_u32t(sB + stage * B_STAGE);
@@ -72,9 +91,9 @@ conv_wgrad_kernel(const WgradK p) {
             cp_async16t(a_dst + wg_off(k, pc), va ? p.dy + (size_t)mm * p.ldy + co : p.dy, va);
             // X piece (im2col gather for this tap)
             const int b = mm / p.HoWo, pix = mm - b * p.HoWo, oy = pix / p.Wo, ox = pix - oy * p.Wo;
-            const int iy = oy * p.stride - p.pad_t + ky * p.dil, ix = ox * p.stride - p.pad_l + kx * p.dil;
-            const int ci = ci0 + pc * 8;
-            const bool vb = mv && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W && ci < p.Cin;
+            const int iy = oy * p.stride + pk_dy[i], ix = ox * p.stride + pk_dx[i];
+            const int ci = pk_ci[i];
+            const bool vb = mv && pk_ok[i] && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
             cp_async16t(b_dst + wg_off(k, pc), vb ? p.x + (((size_t)b * p.H + iy) * p.W + ix) * p.Cin + ci : p.x, vb);
         }
     };
@@ -134,11 +153,11 @@ conv_wgrad_kernel(const WgradK p) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int co = co0 + warp_m * 64 + mt * 16 + (lane >> 2) + h * 8;
-                const int ci = ci0 + warp_n * 32 + nt * 8 + (lane & 3) * 2;
+                const int n = n0 + warp_n * 32 + nt * 8 + (lane & 3) * 2;
                 if (co < p.Cout) {
-                    float* dst = p.dw + ((size_t)co * p.taps + tap) * p.Cin + ci;
-                    if (ci < p.Cin) atomicAdd(dst, acc[mt][nt][h * 2]);
-                    if (ci + 1 < p.Cin) atomicAdd(dst + 1, acc[mt][nt][h * 2 + 1]);
+                    float* dst = p.dw + (size_t)co * NT + n;
+                    if (n < NT) atomicAdd(dst, acc[mt][nt][h * 2]);
+                    if (n + 1 < NT) atomicAdd(dst + 1, acc[mt][nt][h * 2 + 1]);
                 }
             }
 }
@@ -159,22 +178,32 @@ relu_bwd_kernel(uint4* __restrict__ dy, const uint4* __restrict__ y, int64_t n8)
     }
 }
 
-// db[c] += sum_rows dY[row][c]   (dY [rows][ld] fp16, first C columns)
+// db[c] += sum_rows dY[row][c]   (dY [rows][ld] fp16, first C columns).
+// Threads map to (row slice, channel group of 8) with the channel group fastest, so a warp reads
+// contiguous 16-byte pieces; slices of one block are combined in shared memory before the atomics.
 __global__ void __launch_bounds__(256)
 bias_grad_kernel(const __half* __restrict__ dy, float* __restrict__ db, int64_t rows, int ld, int C) {
-    const int c8 = blockIdx.x * 32 + (threadIdx.x & 31);             // channel group of 8
-    const int slice = threadIdx.x >> 5;                               // 8 row slices per block
-    if (c8 * 8 >= C) return;
+    extern __shared__ float s_part[];                                 // [slices][ld]
+    const int G = ld >> 3;                                            // channel groups per row
+    const int slices = blockDim.x / G;                                // host guarantees G <= 256
+    const int g = threadIdx.x % G, slice = threadIdx.x / G;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int64_t r = (int64_t)blockIdx.y * 8 + slice; r < rows; r += (int64_t)gridDim.y * 8) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(dy + r * ld) + c8);
-        const __half2* h = reinterpret_cast<const __half2*>(&v);
+    if (slice < slices) {
+        for (int64_t r = (int64_t)blockIdx.x * slices + slice; r < rows; r += (int64_t)gridDim.x * slices) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(dy + r * ld) + g);
+            const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(h[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+            for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(h[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s_part[slice * ld + g * 8 + k] = acc[k];
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-        if (c8 * 8 + k < C) atomicAdd(db + c8 * 8 + k, acc[k]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float t = 0.0f;
+        for (int sl = 0; sl < slices; ++sl) t += s_part[sl * ld + c];
+        atomicAdd(db + c, t);
+    }
 }
 
 // wt[ci][KH-1-ky][KW-1-kx][co (padded to ldo)] = w[co][ky][kx][ci]
@@ -234,6 +263,67 @@ maxpool_bwd_kernel(const __half* __restrict__ x, const __half* __restrict__ y, c
                 if (first) g += __half2float(dy[o]);
             }
         dx[t] = __float2half_rn(accumulate ? g + __half2float(dx[t]) : g);
+    }
+}
+
+// Non-overlapping windows (k == stride, the four 2x2/2 pools): one thread per output window and 8
+// channels; the first maximum of the window (scan order) receives dY, every other input of the
+// window receives 0, so each dX element is written exactly once with 16-byte accesses.
+template <int K>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_disjoint_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ dx,
+                            int H, int W, int C8, int Ho, int Wo, int pad_t, int pad_l, int accumulate, int64_t total) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(t % C8);
+        int64_t r = t / C8;
+        const int ox = (int)(r % Wo); r /= Wo;
+        const int oy = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        const uint4 gv = __ldg(dy + t);
+        const __half* gh = reinterpret_cast<const __half*>(&gv);
+        uint4 xv[K * K];
+        bool ok[K * K];
+        float best[8];
+        int arg[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; arg[e] = -1; }
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const int iy = oy * K - pad_t + ky, ix = ox * K - pad_l + kx;
+                const int q = ky * K + kx;
+                ok[q] = (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
+                if (ok[q]) {
+                    xv[q] = __ldg(x + (((size_t)b * H + iy) * W + ix) * C8 + c8);
+                    const __half* xh = reinterpret_cast<const __half*>(&xv[q]);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float v = __half2float(xh[e]);
+                        if (v > best[e]) { best[e] = v; arg[e] = q; }        // strict: the first maximum wins
+                    }
+                }
+            }
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const int q = ky * K + kx;
+                if (!ok[q]) continue;
+                const int iy = oy * K - pad_t + ky, ix = ox * K - pad_l + kx;
+                uint4* dst = dx + (((size_t)b * H + iy) * W + ix) * C8 + c8;
+                uint4 o;
+                __half* oh = reinterpret_cast<__half*>(&o);
+                uint4 prev = make_uint4(0, 0, 0, 0);
+                if (accumulate) prev = *dst;
+                const __half* ph = reinterpret_cast<const __half*>(&prev);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float g = arg[e] == q ? __half2float(gh[e]) : 0.0f;
+                    oh[e] = __float2half_rn(accumulate ? g + __half2float(ph[e]) : g);
+                }
+                *dst = o;
+            }
     }
 }
 
@@ -307,6 +397,19 @@ adam_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
     }
 }
 
+// conv_tcgen05.cu
+bool conv_wgrad_tcgen05_supported(const ssd_conv_desc* d, int ldy);
+int  conv_wgrad_tcgen05_launch(const ssd_conv_desc* d, const void* d_dy, int ldy, float* d_dw, cudaStream_t st);
+
+static bool force_legacy_wgrad() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SSD_B200_CONV");
+        v = (e && strcmp(e, "legacy") == 0) ? 1 : 0;
+    }
+    return v == 1;
+}
+
 static int grid1d(int64_t threads, int per_sm = 8) {
     int64_t blocks = (threads + 255) / 256, cap = (int64_t)sm_count() * per_sm;
     return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
@@ -322,6 +425,8 @@ extern "C" int ssd_conv2d_wgrad(const ssd_conv_desc* d, const void* d_dy, int ld
                 d->Wo >= 1 && d->KH >= 1 && d->KW >= 1 && d->stride >= 1 && d->dilation >= 1 && ldy >= d->Cout && ldy % 8 == 0,
                 SSD_ERR_SHAPE, "ssd_conv2d_wgrad: bad shape (Cin=%d Cout=%d ldy=%d; Cin and ldy must be multiples of 8)",
                 d->Cin, d->Cout, ldy);
+    if (!force_legacy_wgrad() && conv_wgrad_tcgen05_supported(d, ldy))
+        return conv_wgrad_tcgen05_launch(d, d_dy, ldy, d_dw, as_stream(stream));
     WgradK k;
     k.x = (const __half*)d->in; k.dy = (const __half*)d_dy; k.dw = d_dw;
     k.B = d->B; k.H = d->H; k.W = d->W; k.Cin = d->Cin; k.Ho = d->Ho; k.Wo = d->Wo; k.Cout = d->Cout; k.KW = d->KW;
@@ -329,8 +434,8 @@ extern "C" int ssd_conv2d_wgrad(const ssd_conv_desc* d, const void* d_dy, int ld
     k.HoWo = d->Ho * d->Wo; k.M = d->B * k.HoWo; k.ldy = ldy; k.taps = d->KH * d->KW;
     k.chunks_total = (k.M + WG_BK - 1) / WG_BK;
     const int tiles_m = (d->Cout + WG_BM - 1) / WG_BM;
-    k.tiles_n = (d->Cin + WG_BN - 1) / WG_BN;
-    const int base = tiles_m * k.tiles_n * k.taps;
+    k.tiles_n = (k.taps * d->Cin + WG_BN - 1) / WG_BN;
+    const int base = tiles_m * k.tiles_n;
     int splits = (sm_count() * 2 + base - 1) / base;                       // ~2 CTAs per SM overall
     splits = max(1, min(splits, (k.chunks_total + 7) / 8));
     k.chunks_per_split = (k.chunks_total + splits - 1) / splits;
@@ -338,7 +443,7 @@ extern "C" int ssd_conv2d_wgrad(const ssd_conv_desc* d, const void* d_dy, int ld
     const size_t smem = (size_t)WG_STAGES * WG_BK * (WG_BM + WG_BN) * 2;
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "ssd_conv2d_wgrad: cudaFuncSetAttribute");
-    dim3 grid(tiles_m * k.tiles_n, k.taps, splits);
+    dim3 grid(tiles_m * k.tiles_n, 1, splits);
     conv_wgrad_kernel<<<grid, WG_THREADS, smem, as_stream(stream)>>>(k);
     SSD_CHECK_LAUNCH("conv_wgrad_kernel");
     return SSD_OK;
@@ -359,10 +464,11 @@ extern "C" int ssd_bias_grad(const void* d_dy, float* d_db, int64_t rows, int ld
     SSD_REQUIRE(rows >= 0 && ld % 8 == 0 && C >= 1 && C <= ld, SSD_ERR_SHAPE, "ssd_bias_grad: bad shape rows=%lld ld=%d C=%d",
                 (long long)rows, ld, C);
     if (rows == 0) return SSD_OK;
-    const int gx = (C + 255) / 256;
-    const int64_t want_y = (rows + 7) / 8, cap_y = max(1, sm_count() * 4 / gx);
-    const int gy = (int)(want_y < cap_y ? want_y : cap_y);
-    bias_grad_kernel<<<dim3(gx, gy), 256, 0, as_stream(stream)>>>((const __half*)d_dy, d_db, rows, ld, C);
+    SSD_REQUIRE(ld <= 2048, SSD_ERR_UNSUPPORTED, "ssd_bias_grad: ld=%d > 2048", ld);
+    const int G = ld / 8, slices = 256 / G;
+    const int64_t want = (rows + slices - 1) / slices, cap = (int64_t)sm_count() * 8;
+    const size_t smem = (size_t)slices * ld * sizeof(float);
+    bias_grad_kernel<<<(int)(want < cap ? want : cap), 256, smem, as_stream(stream)>>>((const __half*)d_dy, d_db, rows, ld, C);
     SSD_CHECK_LAUNCH("bias_grad_kernel");
     return SSD_OK;
 }
@@ -394,6 +500,15 @@ extern "C" int ssd_maxpool_bwd(const void* d_x, const void* d_y, const void* d_d
                                ssd_stream_t stream) {
     SSD_REQUIRE_PTR(d_x); SSD_REQUIRE_PTR(d_y); SSD_REQUIRE_PTR(d_dy); SSD_REQUIRE_PTR(d_dx);
     SSD_REQUIRE(B >= 1 && H >= 1 && W >= 1 && C >= 1 && k >= 1 && k <= 7 && stride >= 1, SSD_ERR_SHAPE, "ssd_maxpool_bwd: bad shape");
+    // disjoint windows that cover every input pixel: vectorised single-pass kernel
+    if (k == stride && k == 2 && C % 8 == 0 && Ho * k - pad_top >= H && Wo * k - pad_left >= W && pad_top >= 0 && pad_left >= 0) {
+        const int64_t total8 = (int64_t)B * Ho * Wo * (C / 8);
+        maxpool_bwd_disjoint_kernel<2><<<grid1d(total8, 16), 256, 0, as_stream(stream)>>>(
+            reinterpret_cast<const uint4*>(d_x), reinterpret_cast<const uint4*>(d_dy), reinterpret_cast<uint4*>(d_dx),
+            H, W, C / 8, Ho, Wo, pad_top, pad_left, accumulate, total8);
+        SSD_CHECK_LAUNCH("maxpool_bwd_disjoint_kernel");
+        return SSD_OK;
+    }
     const int64_t total = (int64_t)B * H * W * C;
     maxpool_bwd_kernel<<<grid1d(total, 16), 256, 0, as_stream(stream)>>>(
         (const __half*)d_x, (const __half*)d_y, (const __half*)d_dy, (__half*)d_dx, H, W, C, Ho, Wo, k, stride, pad_top,

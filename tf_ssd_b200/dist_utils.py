@@ -76,7 +76,7 @@ class GradBuckets(object):
             off = 0
             for name, shape, n in cur:
                 self.views[name] = buf[off:off + n].view(*shape)
-                off += n
+                off += (n + 3) // 4 * 4                    # every view starts on a 16-byte boundary
             self.buckets.append(buf)
             cur, cur_elems = [], 0
 

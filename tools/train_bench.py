@@ -72,6 +72,60 @@ def measure(steps=10, warmup=3, batch=32):
             "grad_allreduce_bytes": int(sum(b.numel() for b in trainer.grads.buckets) * 4)}
 
 
+def breakdown(batch=32):
+    """Per-category CUDA-event timing of one training step (no profiler needed)."""
+    import collections
+    import torch
+    from tf_ssd_b200 import _ffi
+    from tf_ssd_b200.utils import train_utils
+    torch.cuda.set_device(0)
+    hp, model, trainer, priors = build(batch)
+    img, gt, lab = make_batch(batch, hp, 5)
+    for _ in range(2):
+        train_step(trainer, priors, hp, img, gt, lab)
+    torch.cuda.synchronize()
+    st = trainer._prepare(batch)
+    plan = st["plan"]
+    evs = []
+
+    def mark(tag):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        evs.append((tag, e))
+
+    mark("start")
+    d, oh = train_utils.calculate_actual_outputs(priors, gt, lab, hp); mark("match_encode")
+    model._to_image_buffer(plan, img)
+    for i, s_ in enumerate(plan.steps):
+        plan.run(i, i + 1); mark("fwd:" + s_.kind)
+    stream = _ffi.stream()
+    lib = trainer.lib
+    N, L = model.n_anchors, model.total_labels
+    _ffi.check(lib.ssd_loss_fwd(_ffi.ptr(d), _ffi.ptr(plan.deltas), _ffi.ptr(oh), _ffi.ptr(plan.logits), batch, N, L, 3.0, 1.0, 1,
+                                _ffi.ptr(st["loc"]), _ffi.ptr(st["conf"]), _ffi.ptr(st["ws"]), st["ws"].numel(), stream)); mark("loss_fwd")
+    _ffi.check(lib.ssd_loss_bwd(_ffi.ptr(d), _ffi.ptr(plan.deltas), _ffi.ptr(oh), _ffi.ptr(plan.logits), batch, N, L, 1.0,
+                                trainer.loss_scale / batch, _ffi.ptr(st["g_deltas"]), _ffi.ptr(st["g_logits"]), _ffi.ptr(st["ws"]),
+                                st["ws"].numel(), stream)); mark("loss_bwd")
+    trainer.grads.zero_(); mark("zero_grads")
+    per_layer = []
+    for fn, args, what in st["launches"]:
+        _ffi.check(fn(*args, stream), what); mark("bwd:" + what.split(":")[1])
+        per_layer.append(what)
+    trainer.apply_gradients(); mark("adam")
+    torch.cuda.synchronize()
+    agg = collections.OrderedDict()
+    detail = []
+    for (t0, e0), (t1, e1) in zip(evs[:-1], evs[1:]):
+        ms = e0.elapsed_time(e1)
+        agg[t1] = agg.get(t1, 0.0) + ms
+        detail.append((t1, ms))
+    total = sum(agg.values())
+    print(json.dumps({"total_ms": total, "by_category_ms": {k: round(v, 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])}}))
+    bw = [(w, ms) for (w, (t, ms)) in zip(per_layer, [d_ for d_ in detail if d_[0].startswith("bwd:")])]
+    top = sorted(bw, key=lambda t: -t[1])[:14]
+    print(json.dumps({"top_backward_launches_ms": [(w, round(ms, 3)) for w, ms in top]}))
+
+
 def check_dp():
     """2 ranks x B=2 must produce the same averaged gradients as 1 process on the concatenated batch of 4."""
     import torch
@@ -106,8 +160,11 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--check-dp", action="store_true")
+    ap.add_argument("--breakdown", action="store_true")
     a = ap.parse_args()
-    if a.check_dp:
+    if a.breakdown:
+        breakdown(a.batch)
+    elif a.check_dp:
         check_dp()
     else:
         out = measure(a.steps, a.warmup, a.batch)
