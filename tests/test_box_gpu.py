@@ -92,6 +92,36 @@ def test_match_encode_parity(api, name, B, G, snap):
     assert torch.equal(d2, d) and torch.equal(oh2, oh)
 
 
+def test_iou_map_misaligned_rows(api):
+    """M*G odd: every image after the first starts at a 4-byte (not 16-byte) aligned address,
+    tiles end mid-vector, and some warps see no overlapping ground truth at all."""
+    bbox_utils, _, synth = api
+    rng = np.random.default_rng(17)
+    for M, G in [(203, 7), (33, 3), (31, 1), (1000, 45), (64, 128), (70, 130)]:
+        gt, _ = synth.make_ground_truth(3, padded=G, max_boxes=min(G, 8), seed=M + G)
+        boxes = np.sort(rng.random((3, M, 2, 2)).astype(np.float32) * 0.2 + rng.random((3, M, 1, 2)).astype(np.float32) * 0.8,
+                        axis=2).reshape(3, M, 4)
+        boxes = boxes[:, np.argsort(boxes[0, :, 0])]                   # spatially sorted: tight warp bounding boxes
+        got = _np(bbox_utils.generate_iou_map(boxes, gt))
+        np.testing.assert_array_equal(got.view(np.uint32), bo.iou_map(boxes, gt).view(np.uint32))
+
+
+def test_match_encode_misaligned_onehot(api):
+    """N odd and L = 21 / 5 / 3: the one-hot block of a CTA starts off a 16-byte boundary."""
+    _, train_utils, synth = api
+    priors = bo.prior_boxes(*CONFIGS["mobilenet_v2"][:2])[:2267]
+    gt, lab = synth.make_ground_truth(3, padded=9, max_boxes=8, seed=5)
+    for L in (21, 5, 3):
+        labc = np.where(lab > 0, 1 + (lab - 1) % (L - 1), lab).astype(np.int32)
+        hp = {"total_labels": L, "iou_threshold": 0.5, "variances": VARIANCES}
+        d, oh = train_utils.calculate_actual_outputs(priors, gt, labc, hp)
+        rd, roh = bo.match_encode(priors, gt, labc, L, 0.5, VARIANCES)
+        np.testing.assert_array_equal(_np(oh), roh)
+        np.testing.assert_array_equal(_np(d) == 0, rd == 0)
+        np.testing.assert_allclose(_np(d), rd, rtol=1e-4, atol=1e-6)
+        assert (roh[..., 1:] == 1).any()
+
+
 def test_match_encode_edge_cases(api):
     _, train_utils, _ = api
     priors = bo.prior_boxes(*CONFIGS["mobilenet_v2"][:2])
@@ -159,6 +189,14 @@ def test_full_size_properties(api):
     assert torch.equal(oh.sum(-1), torch.ones_like(best))
     assert torch.equal(oh.argmax(-1).to(torch.int32), l)
     assert not d[~pos].any()
+    # the index-free variant (threshold culling) produces the same targets
+    d2, oh2 = train_utils.calculate_actual_outputs(priors, gt, lab, hp)
+    assert torch.equal(d2, d) and torch.equal(oh2, oh)
+    for thr in (0.3, 0.7):
+        hpt = dict(hp, iou_threshold=thr)
+        d3, oh3, _, _ = train_utils.calculate_actual_outputs(priors, gt, lab, hpt, return_indices=True)
+        d4, oh4 = train_utils.calculate_actual_outputs(priors, gt, lab, hpt)
+        assert torch.equal(d3, d4) and torch.equal(oh3, oh4)
     # padded ground truth never matches
     gtl = torch.from_numpy(lab).cuda()
     assert (torch.gather(gtl, 1, idx.long())[pos] > 0).all()

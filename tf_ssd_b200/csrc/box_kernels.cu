@@ -128,15 +128,17 @@ iou_map_kernel(const float4* __restrict__ boxes, const float4* __restrict__ gt, 
 constexpr int kIouTileMaxG = 128;
 constexpr int kIouTileWarps = 8;
 
+// warp-wide float min/max in ONE instruction: sm_100a has redux.sync on f32 (CREDUX.MIN/MAX.F32);
+// NaN inputs are ignored like fminf/fmaxf.
 __device__ __forceinline__ float warp_min_f(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
+    float r;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
 }
 __device__ __forceinline__ float warp_max_f(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
 }
 // true when ground-truth box q provably has zero intersection with every box inside
 // the bounding box (y1,x1,y2,x2) AND the reference formula then yields exactly +0
@@ -146,14 +148,20 @@ __device__ __forceinline__ bool gt_culled(const float4 q, float q_area, float wy
     return (q.z <= wy1 || q.x >= wy2 || q.w <= wx1 || q.y >= wx2) && q_area >= 0.0f;
 }
 
+// Shared-memory tile of a warp: the [rows][G] block of IoUs in the SAME flat order as global
+// memory (so the write-out is a straight 16-byte copy), shifted by `mis` floats so that shared
+// and global 16-byte groups coincide, and XOR-swizzled at 16-byte granularity so that the
+// column writes of the compute phase (lane stride = G floats) spread over the banks.
+__device__ __forceinline__ int tile_swz(int i) { return i ^ (((i >> 5) & 7) << 2); }
+
 template <int NCH>                                   // NCH = ceil(G / 32) chunks of ground-truth boxes
 __global__ void __launch_bounds__(kIouTileWarps * 32)
-iou_map_tile_kernel(const float4* __restrict__ boxes, const float4* __restrict__ gt, int N, int G, int pitch,
+iou_map_tile_kernel(const float4* __restrict__ boxes, const float4* __restrict__ gt, int N, int G, int tile_floats,
                     int boxes_batched, float* __restrict__ out) {
-    extern __shared__ float4 s_gt[];                 // [G] boxes | [G] areas | per-warp [32][pitch] tiles
+    extern __shared__ float4 s_gt[];                 // [G] boxes | [G] areas (padded to 16 B) | per-warp tiles
     float* s_area = reinterpret_cast<float*>(s_gt + G);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* tile = s_area + G + (size_t)warp * 32 * pitch;
+    float* tile = s_area + ((G + 3) & ~3) + (size_t)warp * tile_floats;
     const int b = blockIdx.y;
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         float4 v = gt[(size_t)b * G + g];
@@ -165,6 +173,7 @@ iou_map_tile_kernel(const float4* __restrict__ boxes, const float4* __restrict__
     float* o = out + (size_t)b * N * G;
     const int ntiles = (N + 31) >> 5;
     const float inf = __int_as_float(0x7f800000);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int t = blockIdx.x * kIouTileWarps + warp; t < ntiles; t += gridDim.x * kIouTileWarps) {
         const int n0 = t << 5, n = n0 + lane;
         const bool valid = n < N;
@@ -172,38 +181,53 @@ iou_map_tile_kernel(const float4* __restrict__ boxes, const float4* __restrict__
         const float pa = box_area(p);
         const float wy1 = warp_min_f(p.x), wx1 = warp_min_f(p.y), wy2 = warp_max_f(p.z), wx2 = warp_max_f(p.w);
         const bool can_cull = __all_sync(0xffffffffu, !valid || pa > 0.0f);
-        float* row = tile + lane * pitch;
-        uint32_t hitmask[NCH];                           // warp-uniform: which boxes were evaluated
+        uint32_t hitmask[NCH];                           // warp-uniform: which boxes must be evaluated
+        uint32_t any = 0;
 #pragma unroll
         for (int k = 0; k < NCH; ++k) {
-            const int g0 = k << 5;
-            const int g = g0 + lane;
+            const int g = (k << 5) + lane;
             bool hit = g < G;
             if (can_cull && hit) hit = !gt_culled(s_gt[g], s_area[g], wy1, wx1, wy2, wx2);
-            uint32_t m = __ballot_sync(0xffffffffu, hit);
-            hitmask[k] = m;
+            hitmask[k] = __ballot_sync(0xffffffffu, hit);
+            any |= hitmask[k];
+        }
+        // The tile's outputs are ONE contiguous run of total = rows*G floats.  e = element index,
+        // i = e + mis its position relative to the preceding 16-byte boundary of global memory.
+        float* dst = o + (size_t)n0 * G;
+        const int total = min(32, N - n0) * G;
+        const int mis = (int)(((uintptr_t)dst >> 2) & 3);
+        const int head = min(total, (4 - mis) & 3);          // scalar elements before the first full group
+        const int nvec = (total - head) >> 2;
+        const int tail0 = head + (nvec << 2);
+        float4* vdst = reinterpret_cast<float4*>(dst + head);
+        if (any == 0) {                                      // nothing can overlap: stream +0
+            if (lane < head) __stcs(dst + lane, 0.0f);
+            for (int v = lane; v < nvec; v += 32) __stcs(vdst + v, zero4);
+            if (tail0 + lane < total) __stcs(dst + tail0 + lane, 0.0f);
+            continue;
+        }
+        float4* t4 = reinterpret_cast<float4*>(tile);
+        for (int v = lane; v < (tile_floats >> 2); v += 32) t4[v] = zero4;
+        __syncwarp();
+        const int rowbase = lane * G + mis;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            uint32_t m = hitmask[k];
             while (m) {
-                const int gg = g0 + __ffs(m) - 1;
+                const int gg = (k << 5) + __ffs(m) - 1;
                 m &= m - 1;
-                row[gg] = iou_ref(p, pa, s_gt[gg], s_area[gg]);
+                const float v = iou_ref(p, pa, s_gt[gg], s_area[gg]);
+                if (valid) tile[tile_swz(rowbase + gg)] = v;
             }
         }
         __syncwarp();
-        // The tile's outputs are one contiguous run of rows*G floats: lane f, f+32, ... so every
-        // store instruction writes 128 contiguous bytes; (row, column) advance incrementally and
-        // culled columns are +0 without touching shared memory.
-        const int total = min(32, N - n0) * G;
-        float* dst = o + (size_t)n0 * G;
-        const int dr = 32 / G, dc = 32 - dr * G;
-        int r = lane / G, c = lane - r * G;
-        for (int f = lane; f < total; f += 32) {
-            uint32_t hm = hitmask[0];
-#pragma unroll
-            for (int k = 1; k < NCH; ++k) hm = (c >> 5) == k ? hitmask[k] : hm;
-            __stcs(dst + f, ((hm >> (c & 31)) & 1u) ? tile[r * pitch + c] : 0.0f);
-            r += dr; c += dc;
-            if (c >= G) { c -= G; ++r; }
+        if (lane < head) __stcs(dst + lane, tile[tile_swz(mis + lane)]);
+        {
+            const int g0 = (mis + head) >> 2;                // first full 16-byte group of the tile
+            for (int v = lane; v < nvec; v += 32)
+                __stcs(vdst + v, t4[tile_swz((g0 + v) << 2) >> 2]);
         }
+        if (tail0 + lane < total) __stcs(dst + tail0 + lane, tile[tile_swz(mis + tail0 + lane)]);
         __syncwarp();
     }
 }
@@ -257,11 +281,25 @@ decode_kernel(const float4* __restrict__ priors, const float4* __restrict__ delt
 // ------------------------------------------------------------ match+encode --
 // utils/train_utils.py:123-135 fused with the encode above.  One thread per
 // (image, anchor); the G ground-truth boxes of the image live in shared
-// memory; the IoU row exists only in registers.  The one-hot block of the CTA
-// (ANCHORS_PER_CTA * L consecutive floats) is written cooperatively so the
-// dominant 4*L bytes/anchor stream is fully coalesced.
+// memory; the IoU row exists only in registers.
+//
+// Culling (warp granularity, one ballot per 32 ground-truth boxes):
+//  * a box disjoint from the warp's bounding box has IoU = +0 for all 32 anchors and can
+//    never win the strict ">" of the arg-max;
+//  * NEED_IDX = false (the arg-max index itself is not an output): only anchors whose best
+//    IoU exceeds iou_thr produce anything that depends on the index, so a box that provably
+//    cannot reach iou_thr with ANY anchor of the warp is skipped as well.  IoU > t implies
+//    inter > t*area_gt, inter > t*area_anchor, and inter <= area(gt ^ warp bounding box),
+//    inter <= min(area_gt, area_anchor); the tests below use a 10 % margin, far above the
+//    few-ulp rounding of the float32 expressions, so no box with IoU > t is ever skipped and
+//    the surviving boxes are evaluated with the exact reference arithmetic in index order.
+//
+// The one-hot block of the CTA (kMatchThreads * L consecutive floats) is built in shared
+// memory (zero fill, one store per anchor) and streamed out with 16-byte stores: the
+// dominant 4*L bytes/anchor of this kernel.
 constexpr int kMatchThreads = 256;
 
+template <bool NEED_IDX, bool SMEM_ONEHOT>
 __global__ void __launch_bounds__(kMatchThreads)
 match_encode_kernel(const float4* __restrict__ priors, const float4* __restrict__ gt_boxes,
                     const int32_t* __restrict__ gt_labels, int N, int G, int L, float iou_thr,
@@ -271,25 +309,30 @@ match_encode_kernel(const float4* __restrict__ priors, const float4* __restrict_
     float*   s_area = reinterpret_cast<float*>(s_gt + G);          // [G]
     int32_t* s_glab = reinterpret_cast<int32_t*>(s_area + G);      // [G]
     int32_t* s_lab  = s_glab + G;                                  // [kMatchThreads]
+    // [kMatchThreads*L + 4] one-hot staging, 16-byte aligned (SMEM_ONEHOT only)
+    float*   s_hot  = reinterpret_cast<float*>(s_gt) + ((6 * G + kMatchThreads + 3) & ~3);
     const int b = blockIdx.y;
+    const int n0 = blockIdx.x * kMatchThreads;
+    const int cnt = min(kMatchThreads, N - n0);
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         float4 v = gt_boxes[(size_t)b * G + g];
         s_gt[g] = v;
         s_area[g] = box_area(v);
         s_glab[g] = gt_labels[(size_t)b * G + g];
     }
+    if (SMEM_ONEHOT && out_onehot != nullptr) {
+        float4* h4 = reinterpret_cast<float4*>(s_hot);
+        const int n4 = (cnt * L + 3 + 3) >> 2;
+        for (int v = threadIdx.x; v < n4; v += kMatchThreads) h4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     __syncthreads();
 
-    const int n0 = blockIdx.x * kMatchThreads;
     const int n = n0 + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool valid = n < N;
     const float inf = __int_as_float(0x7f800000);
     int label = 0;
     {
-        // Ground-truth boxes that cannot overlap any anchor of this warp (tested against
-        // the warp's bounding box) have IoU = +0 for all 32 anchors and can never win the
-        // strict ">" of the arg-max, so only the boxes that pass the ballot are evaluated.
         const float4 p = valid ? __ldg(priors + n) : make_float4(inf, inf, -inf, -inf);
         const float pa = box_area(p);
         const float wy1 = warp_min_f(p.x), wx1 = warp_min_f(p.y), wy2 = warp_max_f(p.z), wx2 = warp_max_f(p.w);
@@ -297,11 +340,24 @@ match_encode_kernel(const float4* __restrict__ priors, const float4* __restrict_
         float best;
         int idx = 0;
         if (can_cull) {
-            best = 0.0f;                                           // == IoU of every culled box
+            best = 0.0f;                                           // == IoU of every disjoint box
+            // threshold culling needs 0 < thr (and finite areas); a_lo/a_hi bound the warp's anchor areas
+            const bool thr_cull = !NEED_IDX && iou_thr > 0.0f;
+            const float a_lo = warp_min_f(valid ? pa : inf), a_hi = warp_max_f(valid ? pa : 0.0f);
+            const float t9 = 0.9f * iou_thr;
             for (int g0 = 0; g0 < G; g0 += 32) {
                 const int g = g0 + lane;
                 bool hit = false;
-                if (g < G) hit = !gt_culled(s_gt[g], s_area[g], wy1, wx1, wy2, wx2);
+                if (g < G) {
+                    const float4 q = s_gt[g];
+                    const float qa = s_area[g];
+                    hit = !gt_culled(q, qa, wy1, wx1, wy2, wx2);
+                    if (thr_cull && hit) {
+                        const float cy = fminf(q.z, wy2) - fmaxf(q.x, wy1), cx = fminf(q.w, wx2) - fmaxf(q.y, wx1);
+                        const float cover = cy * cx;               // area(gt ^ warp bounding box) >= any inter
+                        if (cover < t9 * qa || cover < t9 * a_lo || a_hi < t9 * qa || qa < t9 * a_lo) hit = false;
+                    }
+                }
                 unsigned mask = __ballot_sync(0xffffffffu, hit);
                 while (mask) {
                     const int gg = g0 + __ffs(mask) - 1;
@@ -317,27 +373,39 @@ match_encode_kernel(const float4* __restrict__ priors, const float4* __restrict_
                 if (v > best) { best = v; idx = g; }
             }
         }
-        if (valid) {
-            const bool pos = best > iou_thr;                           // strict (:126)
+        const bool pos = valid && best > iou_thr;                  // strict (:126)
+        // encode(p, 0-box) / variances is exactly +0 for positive finite variances: only warps
+        // that hold a positive anchor run the log/divide chain
+        const bool var_ok = variances.x > 0.f && variances.y > 0.f && variances.z > 0.f && variances.w > 0.f;
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (__any_sync(0xffffffffu, pos) || !var_ok) {
             float4 g4 = pos ? s_gt[idx] : make_float4(0.f, 0.f, 0.f, 0.f);   // :129-130
-            float4 d = encode_one(p, g4);
+            d = encode_one(p, g4);
             d.x = fdiv(d.x, variances.x); d.y = fdiv(d.y, variances.y);      // :131
             d.z = fdiv(d.z, variances.z); d.w = fdiv(d.w, variances.w);
+        }
+        if (valid) {
             __stcs(out_deltas + (size_t)b * N + n, d);
             label = pos ? s_glab[idx] : 0;                             // :133-134
             if (out_label) out_label[(size_t)b * N + n] = label;
-            if (out_match) out_match[(size_t)b * N + n] = idx;
+            if (NEED_IDX && out_match) out_match[(size_t)b * N + n] = idx;
         }
     }
     if (out_onehot == nullptr) return;
-    s_lab[threadIdx.x] = label;
-    __syncthreads();
 
     // :135  one_hot: CTA writes floats [first, first + cnt*L) of the output.
-    const int cnt = min(kMatchThreads, N - n0);
     const int64_t first = ((int64_t)b * N + n0) * L;
     const int total = cnt * L;
     float* dst = out_onehot + first;
+    if (SMEM_ONEHOT) {
+        float* hot = stage_rows_ptr(dst, s_hot);                   // same 16-byte phase as global memory
+        if (valid && label >= 0 && label < L) hot[threadIdx.x * L + label] = 1.0f;
+        __syncthreads();
+        stage_rows_out(dst, total, hot);
+        return;
+    }
+    s_lab[threadIdx.x] = label;
+    __syncthreads();
     const int head = (int)((4 - (((uintptr_t)dst >> 2) & 3)) & 3);      // floats until 16B alignment
     const int nvec = (total > head) ? (total - head) >> 2 : 0;
     for (int e = threadIdx.x; e < min(head, total); e += blockDim.x) {
@@ -417,8 +485,9 @@ extern "C" int ssd_iou_map(const float* d_boxes, const float* d_gt, int B, int N
                 "ssd_iou_map: bad shape B=%d N=%d G=%d", B, N, G);
     if (B == 0 || N == 0 || G == 0) return SSD_OK;
     if (G <= kIouTileMaxG) {
-        const int pitch = G | 1;                                   // odd pitch: conflict-free column writes
-        size_t smem_t = (size_t)G * 20 + (size_t)kIouTileWarps * 32 * pitch * sizeof(float);
+        // per-warp tile: 32*G floats + up to 3 of misalignment, rounded to the swizzle period (256 floats)
+        const int tile_floats = (32 * G + 3 + 255) & ~255;
+        size_t smem_t = (size_t)G * 16 + (size_t)((G + 3) & ~3) * 4 + (size_t)kIouTileWarps * tile_floats * sizeof(float);
         const int nch = (G + 31) / 32;
         auto kern = nch == 1 ? iou_map_tile_kernel<1> : nch == 2 ? iou_map_tile_kernel<2>
                   : nch == 3 ? iou_map_tile_kernel<3> : iou_map_tile_kernel<4>;
@@ -429,7 +498,7 @@ extern "C" int ssd_iou_map(const float* d_boxes, const float* d_gt, int B, int N
         const int cap = max(1, (sm_count() * 16 + B - 1) / B);
         dim3 grid(min(per_img, cap), B);
         kern<<<grid, kIouTileWarps * 32, smem_t, as_stream(stream)>>>(
-            reinterpret_cast<const float4*>(d_boxes), reinterpret_cast<const float4*>(d_gt), N, G, pitch,
+            reinterpret_cast<const float4*>(d_boxes), reinterpret_cast<const float4*>(d_gt), N, G, tile_floats,
             boxes_batched, d_out);
         SSD_CHECK_LAUNCH("iou_map_tile_kernel");
         return SSD_OK;
@@ -465,15 +534,21 @@ extern "C" int ssd_match_encode(const float* d_priors, const float* d_gt_boxes, 
     SSD_REQUIRE(B >= 0 && N >= 0 && G >= 1 && L >= 1 && B <= 65535, SSD_ERR_SHAPE,
                 "ssd_match_encode: bad shape B=%d N=%d G=%d L=%d (G must be >= 1)", B, N, G, L);
     if (B == 0 || N == 0) return SSD_OK;
-    size_t smem = (size_t)G * 24 + kMatchThreads * sizeof(int32_t);
-    SSD_REQUIRE(smem <= 160 * 1024, SSD_ERR_UNSUPPORTED, "ssd_match_encode: G=%d exceeds shared-memory staging", G);
-    if (smem > 40 * 1024)
-        cudaFuncSetAttribute(match_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem_base = (size_t)((6 * G + kMatchThreads + 3) & ~3) * 4;      // gt boxes/areas/labels + anchor labels
+    const size_t smem_hot = ((size_t)kMatchThreads * L + 8) * sizeof(float);        // one-hot staging
+    SSD_REQUIRE(smem_base <= 160 * 1024, SSD_ERR_UNSUPPORTED, "ssd_match_encode: G=%d exceeds shared-memory staging", G);
+    const bool smem_onehot = d_onehot != nullptr && smem_base + smem_hot <= 100 * 1024;   // >= 2 CTAs per SM
+    const size_t smem = smem_base + (smem_onehot ? smem_hot : 0);
     dim3 grid(ceil_div(N, kMatchThreads), B);
     float4 var = make_float4(h_variances[0], h_variances[1], h_variances[2], h_variances[3]);
-    match_encode_kernel<<<grid, kMatchThreads, smem, as_stream(stream)>>>(
-        reinterpret_cast<const float4*>(d_priors), reinterpret_cast<const float4*>(d_gt_boxes), d_gt_labels,
-        N, G, L, iou_threshold, var, reinterpret_cast<float4*>(d_deltas), d_onehot, d_label, d_match);
+    auto launch = [&](auto kern) {
+        if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, kMatchThreads, smem, as_stream(stream)>>>(
+            reinterpret_cast<const float4*>(d_priors), reinterpret_cast<const float4*>(d_gt_boxes), d_gt_labels,
+            N, G, L, iou_threshold, var, reinterpret_cast<float4*>(d_deltas), d_onehot, d_label, d_match);
+    };
+    if (d_match != nullptr) { if (smem_onehot) launch(match_encode_kernel<true, true>); else launch(match_encode_kernel<true, false>); }
+    else                    { if (smem_onehot) launch(match_encode_kernel<false, true>); else launch(match_encode_kernel<false, false>); }
     SSD_CHECK_LAUNCH("match_encode_kernel");
     return SSD_OK;
 }

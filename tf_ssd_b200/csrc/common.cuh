@@ -84,23 +84,35 @@ __device__ __forceinline__ int warp_sum_i(int v) {
     return v;
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS, bypasses L1 and the register file): a
+// thread can have many of these in flight, so a whole staging tile is requested before the
+// first byte arrives instead of paying one DRAM round trip per loop iteration.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // Cooperative copy of `total` consecutive floats between global memory and a shared
 // staging region with 16-byte global accesses AND 16-byte shared accesses: the data is
 // placed in shared memory at the same misalignment (mod 4 floats) as in global memory,
 // so both sides of every vector move are aligned.  `region` must be 16-byte aligned and
 // hold total + 3 floats.  Returns the pointer p with p[e] == src[e].
+// The vector part is issued with cp.async: call stage_rows_wait() (then __syncthreads())
+// before reading the rows; several regions may be issued back to back before one wait.
 __device__ __forceinline__ float* stage_rows_in(const float* __restrict__ src, int total, float* __restrict__ region) {
     const int mis = (int)(((uintptr_t)src >> 2) & 3);          // floats past a 16-byte boundary
     float* s = region + mis;
     const int head = min(total, (4 - mis) & 3);
     const int nvec = (total - head) >> 2;
-    for (int e = threadIdx.x; e < head; e += blockDim.x) s[e] = __ldcs(src + e);
     const float4* v = reinterpret_cast<const float4*>(src + head);
     float4* d = reinterpret_cast<float4*>(s + head);
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) d[i] = __ldcs(v + i);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) cp_async16(d + i, v + i);
+    for (int e = threadIdx.x; e < head; e += blockDim.x) s[e] = __ldcs(src + e);
     for (int e = head + (nvec << 2) + threadIdx.x; e < total; e += blockDim.x) s[e] = __ldcs(src + e);
     return s;
 }
+__device__ __forceinline__ void stage_rows_wait() { cp_async_wait_all(); }
 // The reverse: s must have been laid out with the destination's misalignment, i.e.
 // s == region + ((uintptr_t)dst >> 2 & 3).
 __device__ __forceinline__ float* stage_rows_ptr(const float* dst, float* region) {

@@ -57,18 +57,24 @@ loss_anchor_kernel(const float4* __restrict__ act_d, const float4* __restrict__ 
     float* s_y = s_rows;
     float* s_p = s_rows + region;
     const bool do_conf = act_l != nullptr;
+    const bool mine = (int)threadIdx.x < cnt;
+    const size_t i = row0 + threadIdx.x;
+    // every global read of the CTA is requested before anything is consumed
     if (do_conf) {
         s_y = stage_rows_in(act_l + row0 * L, cnt * L, s_rows);
         s_p = stage_rows_in(pred_l + row0 * L, cnt * L, s_rows + region);
+    }
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), p4 = a;
+    if (act_d != nullptr && mine) { a = __ldcs(act_d + i); p4 = __ldcs(pred_d + i); }
+    if (do_conf) {
+        stage_rows_wait();
         __syncthreads();
     }
-    if ((int)threadIdx.x >= cnt) return;
-    const size_t i = row0 + threadIdx.x;
+    if (!mine) return;
     uint8_t flag = 0;
 
     if (act_d != nullptr) {                           // ssd_loss.py:36-50
-        float4 a = __ldcs(act_d + i), p = __ldcs(pred_d + i);
-        float av[4] = {a.x, a.y, a.z, a.w}, pv[4] = {p.x, p.y, p.z, p.w};
+        float av[4] = {a.x, a.y, a.z, a.w}, pv[4] = {p4.x, p4.y, p4.z, p4.w};
         float hsum = 0.0f;
         bool pos = false;
 #pragma unroll
@@ -85,35 +91,50 @@ loss_anchor_kernel(const float4* __restrict__ act_d, const float4* __restrict__ 
     if (do_conf) {                                    // ssd_loss.py:69-78
         const float* y = s_y + (size_t)threadIdx.x * L;
         const float* p = s_p + (size_t)threadIdx.x * L;
+        // label scan: foreground flag (:72), number of non-zero entries and the last one.  Targets
+        // are one-hot in practice, so the sum over classes (:70) has at most one non-zero term.
+        uint32_t fg_bits = 0;
+        int nnz = 0, last = 0;
+        for (int l = 0; l < L; ++l) {
+            const uint32_t bits = __float_as_uint(y[l]) & 0x7fffffffu;     // +-0 -> 0
+            if (l > 0) fg_bits |= bits;
+            if (bits) { ++nnz; last = l; }
+        }
         float ce = 0.0f;
-        bool pos = false;
         if (FROM_LOGITS) {
             float m = p[0];
             for (int l = 1; l < L; ++l) m = fmaxf(m, p[l]);
             float s = 0.0f;
             for (int l = 0; l < L; ++l) s = fadd(s, expf(fsub(p[l], m)));
-            float lse = fadd(logf(s), m);
-            for (int l = 0; l < L; ++l) {
-                float yl = y[l];
-                if (yl != 0.0f) ce = fadd(ce, fmul(yl, fsub(p[l], lse)));
-                if (l > 0) pos |= (yl != 0.0f);
+            const float lse = fadd(logf(s), m);
+            if (nnz == 1) {
+                ce = fadd(0.0f, fmul(y[last], fsub(p[last], lse)));
+            } else if (nnz > 1) {
+                for (int l = 0; l < L; ++l) {
+                    float yl = y[l];
+                    if (yl != 0.0f) ce = fadd(ce, fmul(yl, fsub(p[l], lse)));
+                }
             }
         } else {
             float s = 0.0f;
             for (int l = 0; l < L; ++l) s = fadd(s, p[l]);
-            for (int l = 0; l < L; ++l) {
-                float yl = y[l];
-                if (yl != 0.0f) {
-                    float q = fminf(fmaxf(fdiv(p[l], s), 1e-7f), fsub(1.0f, 1e-7f));
-                    ce = fadd(ce, fmul(yl, logf(q)));
+            if (nnz == 1) {
+                float q = fminf(fmaxf(fdiv(p[last], s), 1e-7f), fsub(1.0f, 1e-7f));
+                ce = fadd(0.0f, fmul(y[last], logf(q)));
+            } else if (nnz > 1) {
+                for (int l = 0; l < L; ++l) {
+                    float yl = y[l];
+                    if (yl != 0.0f) {
+                        float q = fminf(fmaxf(fdiv(p[l], s), 1e-7f), fsub(1.0f, 1e-7f));
+                        ce = fadd(ce, fmul(yl, logf(q)));
+                    }
                 }
-                if (l > 0) pos |= (yl != 0.0f);
             }
         }
         ce = -ce;
         w.ce[i] = ce;
         w.masked[i] = fmul(ce, y[0]);
-        flag |= pos ? 2 : 0;
+        flag |= fg_bits ? 2 : 0;
     }
     w.flags[i] = flag;
 }
@@ -183,7 +204,7 @@ loss_select_kernel(int N, float neg_pos_ratio, float alpha, bool do_loc, bool do
         acc.x += (f & 1) ? 1.0f : 0.0f;
         acc.y += (f & 2) ? 1.0f : 0.0f;
         if (do_loc) acc.z += w.hub[base + i];
-        if (do_conf) s_key[i] = order_key(w.masked[base + i]);
+        if (do_conf) s_key[i] = order_key(fadd(w.masked[base + i], 0.0f));   // -0 ranks like +0 (argsort ties)
     }
     acc = block_sum3(acc, s_red3);
     const float n_pos_loc = acc.x, n_pos_conf = acc.y;
@@ -320,6 +341,7 @@ loss_bwd_kernel(const float4* __restrict__ act_d, const float4* __restrict__ pre
     if (do_conf) {
         s_y = stage_rows_in(act_l + row0 * L, cnt * L, s_rows);
         s_z = stage_rows_in(logits + row0 * L, cnt * L, s_rows + region);   // g_z + row0*L is misaligned like logits
+        stage_rows_wait();
         __syncthreads();
     }
     if ((int)threadIdx.x < cnt) {

@@ -35,6 +35,17 @@ __device__ __forceinline__ float unorder_bits(uint32_t o) {
     return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
 }
 
+__device__ __forceinline__ float exp2f_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float warp_max_f32(float v) {     // redux.sync on f32: sm_100a
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+
 // ---------------------------------------------------------------- softmax --
 __global__ void __launch_bounds__(kRowThreadsNms)
 softmax_kernel(const float* __restrict__ logits, int64_t rows, int L, float* __restrict__ probs) {
@@ -42,6 +53,7 @@ softmax_kernel(const float* __restrict__ logits, int64_t rows, int L, float* __r
     for (int64_t r0 = (int64_t)blockIdx.x * kRowThreadsNms; r0 < rows; r0 += (int64_t)gridDim.x * kRowThreadsNms) {
         const int cnt = (int)min((int64_t)kRowThreadsNms, rows - r0);
         float* rows = stage_rows_in(logits + r0 * L, cnt * L, s_rows);   // probs + r0*L has the same misalignment
+        stage_rows_wait();
         __syncthreads();
         if ((int)threadIdx.x < cnt) {
             float* z = rows + (size_t)threadIdx.x * L;
@@ -65,6 +77,16 @@ softmax_kernel(const float* __restrict__ logits, int64_t rows, int L, float* __r
 // ---------------------------------------------------------- candidate pass --
 // DECODER=true : models/decoder.py:78-83 rule (argmax==0 kills the row).
 // DECODER=false: plain combined NMS, every (anchor, class) above threshold.
+//
+// FROM_LOGITS (models/header.py:88 fused in) runs in two phases so that the full-precision
+// softmax is only evaluated for rows that can produce a candidate:
+//   1. per thread, one row: max, then an approximate sum of exponentials (ex2.approx, relative
+//      error < 1e-5).  The largest probability of the row is 1/sum, so a row with
+//      1/sum < thr * (1 - 1e-4) certainly has no score above thr; with DECODER a row whose
+//      first maximum is class 0 is certainly zeroed by the background rule.
+//   2. per warp, the surviving rows one at a time with the classes spread over the lanes: the
+//      arithmetic of softmax_kernel (expf, sequential float32 sum, IEEE division), so the
+//      fused path emits bit-identical scores to softmax followed by the probability path.
 template <bool DECODER, bool FROM_LOGITS>
 __global__ void __launch_bounds__(kRowThreadsNms)
 nms_candidates_kernel(const float* __restrict__ scores, int N, int L, float score_thr, int cap,
@@ -77,17 +99,53 @@ nms_candidates_kernel(const float* __restrict__ scores, int N, int L, float scor
     const int cnt = min(kRowThreadsNms, N - n0);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float* rows = stage_rows_in(scores + ((size_t)b * N + n0) * L, cnt * L, s_rows);
+    stage_rows_wait();
     __syncthreads();
     float* p = rows + (size_t)threadIdx.x * L;
     int mine = 0;                                        // candidates of this anchor
-    if ((int)threadIdx.x < cnt) {
-        if (FROM_LOGITS) {                               // models/header.py:88 fused in
+    if (FROM_LOGITS) {
+        bool maybe = false;
+        if ((int)threadIdx.x < cnt) {
             float m = p[0];
             for (int l = 1; l < L; ++l) m = fmaxf(m, p[l]);
             float s = 0.0f;
-            for (int l = 0; l < L; ++l) { float e = expf(fsub(p[l], m)); p[l] = e; s = fadd(s, e); }
-            for (int l = 0; l < L; ++l) p[l] = fdiv(p[l], s);
+            for (int l = 0; l < L; ++l) s += exp2f_approx((p[l] - m) * 1.4426950408889634f);
+            const float thr_lo = score_thr - 1e-4f * fabsf(score_thr);
+            maybe = thr_lo * s < 1.0f;
+            if (DECODER && p[0] == m) maybe = false;     // first maximum is the background class
+            if (!(s == s)) maybe = true;                 // NaN/Inf rows: let the exact path decide
         }
+        unsigned todo = __ballot_sync(0xffffffffu, maybe);
+        while (todo) {
+            const int r = __ffs(todo) - 1;
+            todo &= todo - 1;
+            float* q = rows + (size_t)((wid << 5) + r) * L;
+            float m = -__int_as_float(0x7f800000);
+            for (int l = lane; l < L; l += 32) m = fmaxf(m, q[l]);
+            m = warp_max_f32(m);
+            for (int l = lane; l < L; l += 32) q[l] = expf(fsub(q[l], m));
+            __syncwarp();
+            float s = 0.0f;
+            for (int l = 0; l < L; ++l) s = fadd(s, q[l]);           // same order as softmax_kernel
+            __syncwarp();
+            int c = 0, am = 0x7fffffff;
+            float best = -__int_as_float(0x7f800000);
+            for (int l = lane; l < L; l += 32) {
+                const float v = fdiv(q[l], s);
+                q[l] = v;
+                c += (v > score_thr) ? 1 : 0;
+                if (v > best) { best = v; am = l; }
+            }
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (DECODER) {                               // decoder.py:78-83: first maximum == 0 zeroes the row
+                const float gb = warp_max_f32(best);
+                const int first = __reduce_min_sync(0xffffffffu, best == gb ? am : 0x7fffffff);
+                if (first == 0 || first == 0x7fffffff) c = 0;
+            }
+            if (lane == r) mine = c;
+            __syncwarp();
+        }
+    } else if ((int)threadIdx.x < cnt) {
         bool alive = true;
         if (DECODER) {                                   // decoder.py:78-83: argmax == 0 zeroes the row
             int am = 0;
