@@ -278,6 +278,32 @@ int ssd_head_grad_gather(const float* d_g_logits, const float* d_g_deltas, void*
 int ssd_adam_step(float* d_w, float* d_m, float* d_v, const float* d_grad, void* d_w16, int64_t n, float lr_t,
                   float beta1, float beta2, float eps, float inv_scale, float l2, float* d_sumsq, ssd_stream_t stream);
 
+/* ---- MobileNetV2 training (keras_applications MobileNetV2 under models/ssd_mobilenet_v2.py:25) ----
+ * keras.layers.BatchNormalization(epsilon=1e-3, momentum=0.999) in TRAINING mode over the rows of an
+ * [M = B*H*W, C] fp16 NHWC activation (C % 8 == 0, C <= 2048): batch mean / biased variance per channel,
+ * y = act(gamma * (x - mean) * rstd + beta) (+ d_res, the block_i_add shortcut; may be NULL).
+ * d_save [2*C] fp32 receives mean | rstd for the backward pass.  d_moving_mean / d_moving_var (may be
+ * NULL) are updated as m*momentum + batch*(1-momentum), the variance with Bessel's correction like the
+ * fused Keras kernel.  Deterministic (fixed-order partial sums in the workspace). */
+size_t ssd_bn_workspace_bytes(int C);
+int ssd_bn_train_fwd(const void* d_x, const float* d_gamma, const float* d_beta, float* d_moving_mean,
+                     float* d_moving_var, int64_t M, int C, float eps, float momentum, int act,
+                     const void* d_res, void* d_y, float* d_save, void* d_workspace, size_t workspace_bytes,
+                     ssd_stream_t stream);
+/* Backward of the above: d_dy is the gradient w.r.t. y.  d_dx [M,C] fp16 is overwritten; d_dres (may be
+ * NULL) receives (accumulate_res ? += : =) d_dy; d_dgamma / d_dbeta [C] fp32 ACCUMULATE. */
+int ssd_bn_train_bwd(const void* d_x, const void* d_dy, const float* d_gamma, const float* d_beta,
+                     const float* d_save, int64_t M, int C, int act, void* d_dx, void* d_dres,
+                     int accumulate_res, float* d_dgamma, float* d_dbeta, void* d_workspace,
+                     size_t workspace_bytes, ssd_stream_t stream);
+/* Gradients of Keras DepthwiseConv2D 3x3 (same geometry arguments as ssd_depthwise3x3):
+ * data gradient d_dx [B,H,W,C] fp16 (accumulate != 0 adds), filter gradient d_dw [3,3,C] fp32 ACCUMULATES. */
+int ssd_depthwise3x3_dgrad(const void* d_dy, const void* d_weight, void* d_dx, int B, int H, int W, int C,
+                           int Ho, int Wo, int stride, int pad_top, int pad_left, int accumulate,
+                           ssd_stream_t stream);
+int ssd_depthwise3x3_wgrad(const void* d_x, const void* d_dy, float* d_dw, int B, int H, int W, int C, int Ho,
+                           int Wo, int stride, int pad_top, int pad_left, ssd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,5 +1,5 @@
 """torch-CPU autograd restatement of one Keras training step of the reference
-(trainer.py:86-127): forward (models/ssd_vgg16.py), the two CustomLoss terms
+(trainer.py:86-127): forward (models/ssd_vgg16.py, models/ssd_mobilenet_v2.py in training mode), the two CustomLoss terms
 (ssd_loss.py:26-91) reduced like Keras ``compile(loss=[...])`` does (mean over the batch, summed),
 the l2(5e-4) kernel regulariser (ssd_vgg16.py:76) and Adam (trainer.py:92, Keras defaults).
 
@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 
 from oracle import box_oracle as bo
-from oracle.net_oracle import same_pad
+from oracle.net_oracle import BN_EPS, MNV2_BLOCKS, correct_pad, same_pad
 
 L2_REG = 5e-4
 
@@ -72,6 +72,66 @@ def vgg16_forward_torch(w: Dict[str, torch.Tensor], hyper_params, images: torch.
     return torch.cat(boxes, 1), torch.cat(labels, 1)
 
 
+def _bn_train(y, w, name, stats=None):
+    """[TF-recall] keras BatchNormalization(epsilon=1e-3) with training=True: batch mean and BIASED variance
+    over (B, H, W); ``stats`` (optional dict) receives them for the moving-average check."""
+    mean = y.mean(dim=(0, 2, 3), keepdim=True)
+    var = ((y - mean) ** 2).mean(dim=(0, 2, 3), keepdim=True)
+    if stats is not None:
+        stats[name] = (mean.detach().reshape(-1).numpy(), var.detach().reshape(-1).numpy(), y.shape[0] * y.shape[2] * y.shape[3])
+    return (y - mean) * torch.rsqrt(var + BN_EPS) * w[name + "/gamma"].view(1, -1, 1, 1) + w[name + "/beta"].view(1, -1, 1, 1)
+
+
+def _conv_bn(x, w, name, bn, stride=1, pads=None, depthwise=False, relu6=True, stats=None):
+    if depthwise:
+        wt = w[name + "/depthwise_kernel"].permute(2, 3, 0, 1)          # [C,1,3,3]
+        groups = wt.shape[0]
+    else:
+        wt = w[name + "/kernel"].permute(3, 2, 0, 1)
+        groups = 1
+    kh = wt.shape[2]
+    if pads is None:
+        pads = (same_pad(x.shape[2], kh, stride), same_pad(x.shape[3], kh, stride))
+    x = F.pad(x, (pads[1][0], pads[1][1], pads[0][0], pads[0][1]))
+    y = _bn_train(F.conv2d(x, wt, None, stride=stride, groups=groups), w, bn, stats)
+    return torch.clamp(y, 0.0, 6.0) if relu6 else y
+
+
+def mobilenet_v2_forward_torch(w: Dict[str, torch.Tensor], hyper_params, images: torch.Tensor, stats=None):
+    """models/ssd_mobilenet_v2.py:24-46 over [TF-recall] keras_applications MobileNetV2, TRAINING mode
+    (BatchNorm on batch statistics), differentiable; returns (pred_deltas, logits)."""
+    x = images.permute(0, 3, 1, 2)
+    x = _conv_bn(x, w, "Conv1", "bn_Conv1", stride=2, pads=(correct_pad(x.shape[2]), correct_pad(x.shape[3])), stats=stats)
+    taps = []
+    for bid, (t, c, s) in enumerate(MNV2_BLOCKS):
+        prefix = f"block_{bid}_" if bid else "expanded_conv_"
+        inp = x
+        if bid:
+            x = _conv_bn(x, w, prefix + "expand", prefix + "expand_BN", stats=stats)
+            if bid == 13:
+                taps.append(x)
+        pads = (correct_pad(x.shape[2]), correct_pad(x.shape[3])) if s == 2 else None
+        x = _conv_bn(x, w, prefix + "depthwise", prefix + "depthwise_BN", stride=s, pads=pads, depthwise=True, stats=stats)
+        x = _conv_bn(x, w, prefix + "project", prefix + "project_BN", relu6=False, stats=stats)
+        if s == 1 and inp.shape[1] == c:
+            x = x + inp
+    x = _conv_bn(x, w, "Conv_1", "Conv_1_bn", stats=stats)
+    taps.append(x)
+    for i in range(1, 5):
+        x = _conv(x, w, f"extra{i}_1", padding="valid")
+        x = _conv(x, w, f"extra{i}_2", stride=2)
+        taps.append(x)
+    L = hyper_params["total_labels"]
+    labels, boxes = [], []
+    for i, t in enumerate(taps):
+        lab = _conv(t, w, f"{i + 1}_conv_label_output", relu=False)
+        box = _conv(t, w, f"{i + 1}_conv_boxes_output", relu=False)
+        B = t.shape[0]
+        labels.append(lab.permute(0, 2, 3, 1).reshape(B, -1, L))
+        boxes.append(box.permute(0, 2, 3, 1).reshape(B, -1, 4))
+    return torch.cat(boxes, 1), torch.cat(labels, 1)
+
+
 def losses_torch(actual_deltas, actual_labels, pred_deltas, logits, neg_pos_ratio=3.0, alpha=1.0):
     """ssd_loss.py:26-91 on tensors (from logits); per-image ``(loc [B], conf [B])``."""
     ad, al = torch.as_tensor(actual_deltas), torch.as_tensor(actual_labels)
@@ -95,12 +155,18 @@ def losses_torch(actual_deltas, actual_labels, pred_deltas, logits, neg_pos_rati
 
 
 def train_step(weights: Dict[str, np.ndarray], hyper_params, images: np.ndarray, actual_deltas: np.ndarray,
-               actual_labels: np.ndarray, l2_kernels: Sequence[str], neg_pos_ratio=3.0, alpha=1.0):
+               actual_labels: np.ndarray, l2_kernels: Sequence[str], neg_pos_ratio=3.0, alpha=1.0,
+               backbone: str = "vgg16", stats=None):
     """Returns ``(loss dict, grads dict)`` -- gradients of mean_B(loc) + mean_B(conf) + reg w.r.t. every variable."""
-    w = {k: torch.tensor(v, dtype=torch.float32, requires_grad=True) for k, v in weights.items()}
-    pd, z = vgg16_forward_torch(w, hyper_params, torch.from_numpy(np.ascontiguousarray(images, np.float32)))
+    w = {k: torch.tensor(v, dtype=torch.float32, requires_grad=not k.split("/")[-1].startswith("moving_"))
+         for k, v in weights.items()}
+    img = torch.from_numpy(np.ascontiguousarray(images, np.float32))
+    if backbone == "mobilenet_v2":
+        pd, z = mobilenet_v2_forward_torch(w, hyper_params, img, stats)
+    else:
+        pd, z = vgg16_forward_torch(w, hyper_params, img)
     loc, conf = losses_torch(actual_deltas, actual_labels, pd, z, neg_pos_ratio, alpha)
-    reg = sum(L2_REG * (w[k] ** 2).sum() for k in l2_kernels)
+    reg = sum((L2_REG * (w[k] ** 2).sum() for k in l2_kernels), torch.zeros(()))
     total = loc.mean() + conf.mean() + reg
     total.backward()
     grads = {k: (v.grad.numpy() if v.grad is not None else np.zeros_like(weights[k])) for k, v in w.items()}

@@ -262,3 +262,197 @@ def test_vgg16_training_reduces_loss_and_syncs_weights():
     # inference after training uses the updated weights
     d, p = model(img)
     assert bool(torch.isfinite(d).all()) and bool(torch.isfinite(p).all())
+
+
+# ------------------------------------------------------------------ MobileNetV2 (BatchNorm, depthwise) --
+@pytest.mark.parametrize("M,Cc,act,with_res", [(2 * 19 * 19, 96, 2, False), (3 * 10 * 10, 320, 0, True), (4 * 75 * 75, 24, 0, False),
+                                                (2 * 38 * 38, 192, 2, False), (5, 1280, 2, False), (1000, 16, 1, True)])
+def test_bn_train_fwd_bwd_against_autograd(M, Cc, act, with_res):
+    from tf_ssd_b200 import _ffi
+    rng = np.random.default_rng(M + Cc)
+    x = (rng.standard_normal((M, Cc)) * rng.uniform(0.5, 2.0, Cc) + rng.uniform(-1, 1, Cc)).astype(np.float16)
+    gamma = rng.uniform(0.5, 1.5, Cc).astype(np.float32)
+    beta = rng.uniform(-0.5, 2.0, Cc).astype(np.float32)
+    res = rng.standard_normal((M, Cc)).astype(np.float16) if with_res else None
+    dy = rng.standard_normal((M, Cc)).astype(np.float16)
+    xt = torch.tensor(x.astype(np.float32), requires_grad=True)
+    gt_, bt = torch.tensor(gamma, requires_grad=True), torch.tensor(beta, requires_grad=True)
+    mean = xt.mean(0, keepdim=True)
+    var = ((xt - mean) ** 2).mean(0, keepdim=True)
+    y = (xt - mean) * torch.rsqrt(var + 1e-3) * gt_ + bt
+    if act == 2:
+        y = torch.clamp(y, 0.0, 6.0)
+    elif act == 1:
+        y = torch.relu(y)
+    rt = None
+    if with_res:
+        rt = torch.tensor(res.astype(np.float32), requires_grad=True)
+        y = y + rt
+    y.backward(torch.tensor(dy.astype(np.float32)))
+
+    lib = _ffi.lib()
+    ws = _ffi.workspace(lib.ssd_bn_workspace_bytes(Cc))
+    xd, dyd = torch.from_numpy(x).to(DEV), torch.from_numpy(dy).to(DEV)
+    gd, bd = torch.from_numpy(gamma).to(DEV), torch.from_numpy(beta).to(DEV)
+    mm, mv = torch.zeros(Cc, device=DEV), torch.ones(Cc, device=DEV)
+    rd = torch.from_numpy(res).to(DEV) if with_res else None
+    yd = torch.empty_like(xd)
+    save = torch.zeros(2 * Cc, device=DEV)
+    _ffi.check(lib.ssd_bn_train_fwd(_ffi.ptr(xd), _ffi.ptr(gd), _ffi.ptr(bd), _ffi.ptr(mm), _ffi.ptr(mv), M, Cc, 1e-3, 0.999, act,
+                                    _ffi.ptr(rd), _ffi.ptr(yd), _ffi.ptr(save), _ffi.ptr(ws), ws.numel(), _ffi.stream()), "bn_fwd")
+    assert _rel(yd.float().cpu().numpy(), y.detach().numpy()) < 2e-3
+    assert np.allclose(save[:Cc].cpu().numpy(), mean.detach().numpy().ravel(), rtol=1e-4, atol=1e-5)
+    assert np.allclose(save[Cc:].cpu().numpy(), torch.rsqrt(var + 1e-3).detach().numpy().ravel(), rtol=1e-4)
+    # [TF-recall] moving averages: momentum 0.999, unbiased batch variance
+    v_unb = var.detach().numpy().ravel() * (M / max(M - 1, 1))
+    assert np.allclose(mm.cpu().numpy(), 0.001 * mean.detach().numpy().ravel(), rtol=1e-3, atol=1e-7)
+    assert np.allclose(mv.cpu().numpy(), 0.999 + 0.001 * v_unb, rtol=1e-5)
+
+    dx = torch.empty_like(xd)
+    prev = rng.standard_normal((M, Cc)).astype(np.float16)
+    dres = torch.from_numpy(prev.copy()).to(DEV) if with_res else None
+    dg, db = torch.zeros(Cc, device=DEV), torch.zeros(Cc, device=DEV)
+    _ffi.check(lib.ssd_bn_train_bwd(_ffi.ptr(xd), _ffi.ptr(dyd), _ffi.ptr(gd), _ffi.ptr(bd), _ffi.ptr(save), M, Cc, act,
+                                    _ffi.ptr(dx), _ffi.ptr(dres), 1, _ffi.ptr(dg), _ffi.ptr(db), _ffi.ptr(ws), ws.numel(),
+                                    _ffi.stream()), "bn_bwd")
+    assert _rel(dx.float().cpu().numpy(), xt.grad.numpy()) < 4e-3
+    assert _rel(dg.cpu().numpy(), gt_.grad.numpy()) < 2e-3
+    assert _rel(db.cpu().numpy(), bt.grad.numpy()) < 2e-3
+    if with_res:
+        assert _rel(dres.float().cpu().numpy(), prev.astype(np.float32) + rt.grad.numpy()) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,Cc,stride", [(2, 19, 96, 1), (2, 38, 144, 2), (1, 75, 24, 2), (3, 10, 960, 1), (2, 150, 32, 1)])
+def test_depthwise_grads_against_autograd(B, H, Cc, stride):
+    from oracle.net_oracle import correct_pad, same_pad
+    from tf_ssd_b200 import _ffi
+    rng = np.random.default_rng(H + Cc)
+    pads = same_pad(H, 3, 1) if stride == 1 else correct_pad(H)
+    Ho = (H + pads[0] + pads[1] - 3) // stride + 1
+    x = rng.standard_normal((B, H, H, Cc)).astype(np.float16)
+    w = (rng.standard_normal((3, 3, Cc)) / 3).astype(np.float16)
+    dy = rng.standard_normal((B, Ho, Ho, Cc)).astype(np.float16)
+    xt = torch.tensor(x.astype(np.float32)).permute(0, 3, 1, 2).requires_grad_(True)
+    wt = torch.tensor(w.astype(np.float32)).permute(2, 0, 1).unsqueeze(1).requires_grad_(True)       # [C,1,3,3]
+    y = F.conv2d(F.pad(xt, (pads[0], pads[1], pads[0], pads[1])), wt, None, stride=stride, groups=Cc)
+    y.backward(torch.tensor(dy.astype(np.float32)).permute(0, 3, 1, 2))
+    lib = _ffi.lib()
+    xd, wd, dyd = torch.from_numpy(x).to(DEV), torch.from_numpy(w).to(DEV), torch.from_numpy(dy).to(DEV)
+    # forward without bias / activation (what the training plan launches)
+    yd = torch.empty((B, Ho, Ho, Cc), dtype=torch.float16, device=DEV)
+    _ffi.check(lib.ssd_depthwise3x3(_ffi.ptr(xd), _ffi.ptr(wd), None, _ffi.ptr(yd), B, H, H, Cc, Ho, Ho, stride, pads[0], pads[0], 0,
+                                    _ffi.stream()), "dw_fwd")
+    assert _rel(yd.float().cpu().numpy(), y.detach().permute(0, 2, 3, 1).numpy()) < 2e-3
+    dw = torch.zeros((3, 3, Cc), dtype=torch.float32, device=DEV)
+    _ffi.check(lib.ssd_depthwise3x3_wgrad(_ffi.ptr(xd), _ffi.ptr(dyd), _ffi.ptr(dw), B, H, H, Cc, Ho, Ho, stride, pads[0], pads[0],
+                                          _ffi.stream()), "dw_wgrad")
+    assert _rel(dw.cpu().numpy(), wt.grad[:, 0].permute(1, 2, 0).numpy()) < 2e-3
+    ref_dx = xt.grad.permute(0, 2, 3, 1).numpy()
+    for accumulate in (0, 1):
+        prev = rng.standard_normal(x.shape).astype(np.float16)
+        dx = torch.from_numpy(prev.copy()).to(DEV)
+        _ffi.check(lib.ssd_depthwise3x3_dgrad(_ffi.ptr(dyd), _ffi.ptr(wd), _ffi.ptr(dx), B, H, H, Cc, Ho, Ho, stride, pads[0], pads[0],
+                                              accumulate, _ffi.stream()), "dw_dgrad")
+        want = ref_dx + (prev.astype(np.float32) if accumulate else 0.0)
+        assert _rel(dx.float().cpu().numpy(), want) < 3e-3, accumulate
+
+
+def _mnv2_setup(B, seed=2):
+    from tf_ssd_b200 import synth
+    from tf_ssd_b200.models import ssd_mobilenet_v2
+    from tf_ssd_b200.utils import train_utils
+    hp = train_utils.get_hyper_params("mobilenet_v2")
+    hp["total_labels"] = 21
+    model = ssd_mobilenet_v2.get_model(hp, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    w = {}
+    for k, v in model.weights.items():
+        if k.endswith("/bias") or k.endswith("/beta"):
+            w[k] = rng.normal(0, 0.05, v.shape).astype(np.float32)
+        elif k.endswith("/gamma"):
+            w[k] = rng.uniform(0.8, 1.2, v.shape).astype(np.float32)
+    model.set_weights(w)
+    model.set_weights({k: v.astype(np.float16).astype(np.float32) for k, v in model.weights.items() if k.endswith("kernel")})
+    img = synth.make_images(B, 300, seed=seed + 2)
+    priors = bo.prior_boxes(hp["feature_map_shapes"], hp["aspect_ratios"])
+    gt, lab = synth.make_ground_truth(B, padded=6, seed=seed + 3)
+    ad, al = bo.match_encode(priors, gt, lab, 21, 0.5, hp["variances"])
+    return model, hp, img, ad, al
+
+
+def test_mobilenet_v2_backward_against_autograd():
+    """BASELINE config 4's step on one GPU: training-mode forward (batch statistics), loss, full backward."""
+    from tf_ssd_b200.models.train_engine import Trainer
+    model, hp, img, ad, al = _mnv2_setup(4)
+    stats = {}
+    ref_loss, ref_grads = to.train_step(model.weights, hp, img, ad, al, model.l2_kernels, backbone="mobilenet_v2", stats=stats)
+    tr = Trainer(model, loss_scale=256.0)
+    out = tr.forward_backward(img, ad, al)
+    torch.cuda.synchronize()
+    assert np.allclose(out["loc"].cpu().numpy(), ref_loss["loc"], rtol=3e-2, atol=2e-3)
+    assert np.allclose(out["conf"].cpu().numpy(), ref_loss["conf"], rtol=3e-2, atol=2e-3)
+    # batch statistics of the first and of a deep BatchNorm layer (through save = mean | rstd)
+    plan = model.train_plan(4)
+    for s in plan.steps:
+        if s.kind == "bn" and s.name in ("bn_Conv1", "block_13_expand_BN", "Conv_1_bn"):
+            mean, var, _ = stats[s.name]
+            Cc = mean.shape[0]
+            save = s.meta["save"].cpu().numpy()
+            assert _l2(save[:Cc], mean) < 2e-2, s.name
+            assert _l2(save[Cc:], 1.0 / np.sqrt(var + 1e-3)) < 2e-2, s.name
+    worst = {}
+    for name, v in tr.vars.items():
+        g = v["grad"].cpu().numpy() / tr.loss_scale
+        layer, var = name.rsplit("/", 1)
+        if layer.endswith("_conv_head"):
+            idx = layer.split("_")[0]
+            if var == "kernel":
+                ref = np.concatenate([ref_grads[f"{idx}_conv_label_output/kernel"], ref_grads[f"{idx}_conv_boxes_output/kernel"]], -1)
+                ref = ref.transpose(3, 0, 1, 2)
+            else:
+                ref = np.concatenate([ref_grads[f"{idx}_conv_label_output/bias"], ref_grads[f"{idx}_conv_boxes_output/bias"]])
+        elif var == "kernel":
+            ref = ref_grads[name].transpose(3, 0, 1, 2)
+            if ref.shape[3] != g.shape[3]:                         # Conv1: Cin padded 3 -> 8
+                assert np.all(g[..., ref.shape[3]:] == 0)
+                g = g[..., :ref.shape[3]]
+        elif var == "depthwise_kernel":
+            ref = ref_grads[name][..., 0]
+        else:
+            ref = ref_grads[name]
+        worst[name] = _l2(g, ref)
+    top = sorted(worst.items(), key=lambda kv: -kv[1])[:8]
+    print("worst relative L2 gradient errors:", top)
+    bad = {k: v for k, v in worst.items() if v > 8e-2}
+    assert not bad, bad
+
+
+def test_mobilenet_v2_training_reduces_loss_and_updates_batchnorm():
+    from tf_ssd_b200.models.decoder import get_decoder_model
+    from tf_ssd_b200.models.train_engine import Adam, LearningRateScheduler
+    from tf_ssd_b200.ssd_loss import CustomLoss
+    from tf_ssd_b200.utils import train_utils
+    model, hp, img, ad, al = _mnv2_setup(4, seed=5)
+    loss = CustomLoss(hp["neg_pos_ratio"], hp["loc_loss_alpha"])
+    model.compile(optimizer=Adam(learning_rate=1e-3), loss=[loss.loc_loss_fn, loss.conf_loss_fn])
+
+    def gen():
+        while True:
+            yield img, (ad, al)
+    before = {k: v.copy() for k, v in model.weights.items()}
+    hist = model.fit(gen(), steps_per_epoch=6, validation_data=gen(), validation_steps=1, epochs=2,
+                     callbacks=[LearningRateScheduler(train_utils.scheduler)])
+    assert all(np.isfinite(hist["loss"])) and all(np.isfinite(hist["val_loss"]))
+    assert hist["loss"][1] < hist["loss"][0]
+    changed = {k for k in before if not np.array_equal(before[k], model.weights[k])}
+    for k in ("Conv1/kernel", "block_5_depthwise/depthwise_kernel", "block_5_expand_BN/gamma", "block_5_project_BN/beta",
+              "bn_Conv1/moving_mean", "Conv_1_bn/moving_variance", "extra2_2/bias", "1_conv_label_output/kernel"):
+        assert k in changed, k
+    assert model.weights["Conv1/kernel"].shape == (3, 3, 3, 32)
+    assert model.weights["block_5_depthwise/depthwise_kernel"].shape == before["block_5_depthwise/depthwise_kernel"].shape
+    # inference (folded BatchNorm, moving statistics) picks up the trained variables
+    d, p = model(img)
+    assert bool(torch.isfinite(d).all()) and bool(torch.isfinite(p).all())
+    dec = get_decoder_model(model, bo.prior_boxes(hp["feature_map_shapes"], hp["aspect_ratios"]), hp)
+    b, l, s = dec(img)
+    assert b.shape == (4, 200, 4) and bool(torch.isfinite(b).all())

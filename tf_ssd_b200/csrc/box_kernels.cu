@@ -126,7 +126,7 @@ iou_map_kernel(const float4* __restrict__ boxes, const float4* __restrict__ gt, 
 // and is otherwise a pure streaming write.  The [32][G] tile is transposed
 // through shared memory so the global stores are contiguous 16-byte vectors.
 constexpr int kIouTileMaxG = 128;
-constexpr int kIouTileWarps = 8;
+constexpr int kIouTileWarps = 4;
 
 // warp-wide float min/max in ONE instruction: sm_100a has redux.sync on f32 (CREDUX.MIN/MAX.F32);
 // NaN inputs are ignored like fminf/fmaxf.
@@ -217,7 +217,7 @@ iou_map_tile_kernel(const float4* __restrict__ boxes, const float4* __restrict__
                 const int gg = (k << 5) + __ffs(m) - 1;
                 m &= m - 1;
                 const float v = iou_ref(p, pa, s_gt[gg], s_area[gg]);
-                if (valid) tile[tile_swz(rowbase + gg)] = v;
+                tile[tile_swz(rowbase + gg)] = v;            // rows of lanes past N are never written out
             }
         }
         __syncwarp();
@@ -485,8 +485,8 @@ extern "C" int ssd_iou_map(const float* d_boxes, const float* d_gt, int B, int N
                 "ssd_iou_map: bad shape B=%d N=%d G=%d", B, N, G);
     if (B == 0 || N == 0 || G == 0) return SSD_OK;
     if (G <= kIouTileMaxG) {
-        // per-warp tile: 32*G floats + up to 3 of misalignment, rounded to the swizzle period (256 floats)
-        const int tile_floats = (32 * G + 3 + 255) & ~255;
+        // per-warp tile: 32*G floats + up to 3 of misalignment, rounded to the swizzle block (32 floats)
+        const int tile_floats = (32 * G + 3 + 31) & ~31;
         size_t smem_t = (size_t)G * 16 + (size_t)((G + 3) & ~3) * 4 + (size_t)kIouTileWarps * tile_floats * sizeof(float);
         const int nch = (G + 31) / 32;
         auto kern = nch == 1 ? iou_map_tile_kernel<1> : nch == 2 ? iou_map_tile_kernel<2>
@@ -495,7 +495,7 @@ extern "C" int ssd_iou_map(const float* d_boxes, const float* d_gt, int B, int N
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
         const int ntiles = (N + 31) / 32;
         const int per_img = (ntiles + kIouTileWarps - 1) / kIouTileWarps;
-        const int cap = max(1, (sm_count() * 16 + B - 1) / B);
+        const int cap = max(1, (sm_count() * 32 + B - 1) / B);
         dim3 grid(min(per_img, cap), B);
         kern<<<grid, kIouTileWarps * 32, smem_t, as_stream(stream)>>>(
             reinterpret_cast<const float4*>(d_boxes), reinterpret_cast<const float4*>(d_gt), N, G, tile_floats,

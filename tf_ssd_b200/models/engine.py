@@ -381,6 +381,73 @@ class _PlanBuilder:
         return deltas, logits
 
 
+class _TrainPlanBuilder(_PlanBuilder):
+    """Training-mode interpretation of a graph (Keras ``fit``: ``training=True``): BatchNormalization is NOT
+    folded -- a BN'd layer becomes  convolution (raw fp16 kernel, no bias, no activation) -> ``ssd_bn_train_fwd``
+    (batch statistics, affine, activation, shortcut add).  Layers without BN are emitted exactly as in the
+    inference plan.  The first layer always reads the fp16 copy of the image (its filter gradient needs it)."""
+
+    BN_MOMENTUM = 0.999      # keras_applications.mobilenet_v2: BatchNormalization(momentum=0.999)
+
+    def __init__(self, model: "SSDModel", B: int):
+        super().__init__(model, B)
+        self.bn_ws: Optional[torch.Tensor] = None
+
+    def _bn_workspace(self, C: int) -> torch.Tensor:
+        need = int(self.lib.ssd_bn_workspace_bytes(int(C)))
+        if self.bn_ws is None or self.bn_ws.numel() < need:
+            self.bn_ws = _ffi.workspace(need)          # one shared scratch (launches are stream-ordered)
+        return self.bn_ws
+
+    def _emit_bn(self, bn: str, x_pre: Act, act: int, residual: Optional[Act]) -> Act:
+        m = self.m
+        C_ = x_pre.C
+        gamma, beta = m._train_f32(bn + "/gamma"), m._train_f32(bn + "/beta")
+        mm, mv = m._train_f32(bn + "/moving_mean"), m._train_f32(bn + "/moving_variance")
+        save = torch.zeros(2 * C_, dtype=torch.float32, device=self.dev)
+        out = self._buf(x_pre.H, x_pre.W, C_)
+        ws = self._bn_workspace(1280)
+        M = self.B * x_pre.H * x_pre.W
+        args = (_ffi.ptr(x_pre.t), _ffi.ptr(gamma), _ffi.ptr(beta), _ffi.ptr(mm), _ffi.ptr(mv), M, C_, BN_EPS,
+                self.BN_MOMENTUM, act, _ffi.ptr(residual.t) if residual is not None else None, _ffi.ptr(out),
+                _ffi.ptr(save), _ffi.ptr(ws), ws.numel())
+        nbytes = M * C_ * 2 * (3 + (1 if residual is not None else 0))
+        self.plan.steps.append(Step(bn, "bn", self.lib.ssd_bn_train_fwd, args, 0.0, nbytes,
+                                    (gamma, beta, mm, mv, save, out, ws, x_pre.t),
+                                    dict(x=x_pre.t, out=out, gamma=gamma, beta=beta, save=save, act=act, ws=ws,
+                                         res=residual.t if residual is not None else None, M=M, C=C_)))
+        return Act(out, x_pre.H, x_pre.W, C_)
+
+    def conv(self, x, name, cout, k=1, stride=1, pad="same", dilation=1, act=ACT_NONE, bn=None, use_bias=True,
+             residual=None, init=None, l2=False):
+        if x.t is None:
+            x = self._image_as_f16()
+        if bn is None:
+            return super().conv(x, name, cout, k=k, stride=stride, pad=pad, dilation=dilation, act=act, bn=None,
+                                use_bias=use_bias, residual=residual)
+        ph, pw = _resolve_pads(x.H, x.W, k, stride, dilation, pad)
+        w = self.m._train_conv_kernel(name, x.C)
+        Ho, Wo = _out_size(x.H, k, stride, dilation, ph), _out_size(x.W, k, stride, dilation, pw)
+        pre = self._buf(Ho, Wo, cout)
+        real_cin = self.m.weights[name + "/kernel"].shape[2]
+        self._emit_conv(name, x, w, None, cout, k, stride, dilation, ph, pw, ACT_NONE, None, pre, real_cin=real_cin)
+        return self._emit_bn(bn, Act(pre, Ho, Wo, cout), act, residual)
+
+    def dw(self, x, name, stride=1, act=ACT_RELU6, bn=None):
+        ph, pw = _resolve_pads(x.H, x.W, 3, stride, 1, "same" if stride == 1 else "correct")
+        Ho, Wo = _out_size(x.H, 3, stride, 1, ph), _out_size(x.W, 3, stride, 1, pw)
+        w = self.m._train_dw_kernel(name)
+        pre = self._buf(Ho, Wo, x.C)
+        args = (_ffi.ptr(x.t), _ffi.ptr(w), None, _ffi.ptr(pre), self.B, x.H, x.W, x.C, Ho, Wo, stride, ph[0], pw[0],
+                ACT_NONE)
+        nbytes = self.B * (x.H * x.W + Ho * Wo) * x.C * 2 + 9 * x.C * 2
+        self.plan.steps.append(Step(name, "dw", self.lib.ssd_depthwise3x3, args, 2.0 * self.B * Ho * Wo * 9 * x.C,
+                                    nbytes, (w, x.t, pre),
+                                    dict(x=x.t, w=w, bias=None, out=pre, stride=stride, ph=ph, pw=pw, act=ACT_NONE,
+                                         Ho=Ho, Wo=Wo)))
+        return self._emit_bn(bn, Act(pre, Ho, Wo, x.C), act, None)
+
+
 # ----------------------------------------------------------------- the model --
 class SSDModel(object):
     """What ``get_model(hyper_params)`` returns: the object ``trainer.py`` /
@@ -412,6 +479,9 @@ class SSDModel(object):
         self.n_anchors = sum(t.H * t.W * (len(hyper_params["aspect_ratios"][i]) + 1) for i, t in enumerate(taps))
         self._packed: Dict[str, Tuple[torch.Tensor, Optional[torch.Tensor]]] = {}
         self._plans: Dict[Tuple[int, int], Plan] = {}
+        self._train_vars: Dict[str, torch.Tensor] = {}       # un-folded device variables of the training plans
+        self._train_plans: Dict[int, Plan] = {}
+        self.has_batchnorm = any(k.endswith("/gamma") for k in self.weights)
 
     # -- weights ---------------------------------------------------------------
     def set_weights(self, weights: Dict[str, np.ndarray]) -> None:
@@ -438,6 +508,10 @@ class SSDModel(object):
     def _invalidate(self) -> None:
         self._packed.clear()
         self._plans.clear()
+        self._version = getattr(self, "_version", 0) + 1     # DecoderModel drops its captured graphs when this moves
+        if getattr(self, "trainer", None) is None:       # a live trainer owns the training-mode variables
+            self._train_vars.clear()
+            self._train_plans.clear()
 
     def _bn_fold(self, bn: Optional[str], cout: int, bias: Optional[np.ndarray]):
         b = bias if bias is not None else np.zeros(cout, np.float32)
@@ -481,6 +555,42 @@ class SSDModel(object):
         bias = np.concatenate([self.weights[f"{index}_conv_label_output/bias"],
                                self.weights[f"{index}_conv_boxes_output/bias"]])
         return self._upload(key, k.transpose(3, 0, 1, 2), bias)
+
+    # -- training-mode variables (BatchNorm not folded; see _TrainPlanBuilder) ----
+    def _train_f32(self, key: str) -> torch.Tensor:
+        if key not in self._train_vars:
+            self._train_vars[key] = torch.from_numpy(np.ascontiguousarray(self.weights[key], np.float32)).to(_ffi.require_cuda())
+        return self._train_vars[key]
+
+    def _train_conv_kernel(self, name: str, cin_buf: int) -> torch.Tensor:
+        key = name + "/kernel"
+        if key not in self._train_vars:
+            k = self.weights[key]                                     # HWIO
+            if cin_buf != k.shape[2]:
+                k = np.concatenate([k, np.zeros(k.shape[:2] + (cin_buf - k.shape[2], k.shape[3]), np.float32)], axis=2)
+            t = torch.from_numpy(np.ascontiguousarray(k.transpose(3, 0, 1, 2))).to(_ffi.require_cuda())
+            self._train_vars[key] = t.to(torch.float16).contiguous()  # OHWI fp16
+        return self._train_vars[key]
+
+    def _train_dw_kernel(self, name: str) -> torch.Tensor:
+        key = name + "/depthwise_kernel"
+        if key not in self._train_vars:
+            k = self.weights[key][:, :, :, 0]                         # [3,3,C]
+            self._train_vars[key] = torch.from_numpy(np.ascontiguousarray(k)).to(_ffi.require_cuda()).to(torch.float16).contiguous()
+        return self._train_vars[key]
+
+    def train_plan(self, B: int) -> Plan:
+        """Launch plan of the TRAINING-mode forward (``model(x, training=True)`` inside Keras ``fit``).  Graphs
+        without BatchNorm train on their inference plan."""
+        if not self.has_batchnorm:
+            return self.plan(B)
+        if B not in self._train_plans:
+            _ffi.check_device()
+            pb = _TrainPlanBuilder(self, B)
+            taps = GRAPHS[self.backbone](pb, pb.input(), self.hyper_params)
+            pb.head(taps, self.hyper_params)
+            self._train_plans[B] = pb.plan
+        return self._train_plans[B]
 
     def _dev_f32(self, key: str) -> torch.Tensor:
         if key not in self._packed:
@@ -612,6 +722,10 @@ class DecoderModel(object):
         self._copy_stream: Optional[Tuple[torch.cuda.Stream, torch.cuda.Stream]] = None
 
     def _prepare(self, B: int, slot: int = 0) -> Dict[str, Any]:
+        version = getattr(self.base_model, "_version", 0)
+        if version != getattr(self, "_seen_version", version):
+            self._state.clear()                       # weights were re-packed (set_weights / BatchNorm training)
+        self._seen_version = version
         if (B, slot) in self._state:
             return self._state[(B, slot)]
         plan = self.base_model.plan(B, slot)

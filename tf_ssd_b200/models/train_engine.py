@@ -10,9 +10,10 @@ Adam on fp32 master weights that also refreshes the fp16 working copies the plan
 Mixed precision: activations and activation gradients are fp16 (loss-scaled), variable gradients,
 master weights and Adam moments are fp32.
 
-Scope: graphs without BatchNorm / depthwise layers (SSD300-VGG16, BASELINE.json config 3, and the
-``vgg16_512`` extension).  MobileNetV2 training additionally needs BatchNorm in training mode and
-the depthwise backward kernels, which are not built yet: ``Trainer`` raises for that backbone.
+Scope: both graphs.  SSD300-VGG16 (BASELINE.json config 3, and the ``vgg16_512`` extension) trains on its
+inference plan (no BatchNorm).  SSD300-MobileNetV2 (config 4) trains on ``SSDModel.train_plan``: BatchNorm in
+training mode (``ssd_bn_train_fwd/bwd``: batch statistics, moving-average update), depthwise data / filter
+gradients (``ssd_depthwise3x3_dgrad/wgrad``), shortcut adds folded into the BatchNorm kernels.
 """
 
 from __future__ import annotations
@@ -58,12 +59,10 @@ class Trainer(object):
 
     def __init__(self, model: SSDModel, learning_rate: float = 1e-3, neg_pos_ratio: float = 3.0, loc_loss_alpha: float = 1.0,
                  beta_1: float = 0.9, beta_2: float = 0.999, epsilon: float = 1e-7, loss_scale: float = 1024.0):
-        if model.backbone != "vgg16":
-            raise NotImplementedError(
-                "training is implemented for the BatchNorm-free VGG16 graphs only; MobileNetV2 needs BatchNorm in "
-                "training mode and depthwise backward kernels (not built yet)")
         _ffi.check_device()
         self.model = model
+        model.trainer = self                         # the model's training-mode variables now belong to this trainer
+        self._eval_dirty = True
         self.lib = _ffi.lib()
         self.dev = _ffi.require_cuda()
         self.lr, self.b1, self.b2, self.eps = float(learning_rate), float(beta_1), float(beta_2), float(epsilon)
@@ -77,15 +76,25 @@ class Trainer(object):
     # -- variables: fp32 masters in the kernels' layouts, views into flat gradient buckets ---------------------
     def _build_variables(self) -> None:
         m = self.model
-        plan = m.plan(1)                              # forces every packed (fp16, OHWI) tensor into existence
+        plan = m.train_plan(1)                        # forces every packed (fp16, OHWI) tensor into existence
         self.vars: Dict[str, Dict[str, Any]] = {}
         shapes = []
         for s in plan.steps:
             if s.kind == "conv":
                 w16, b32 = s.meta["w"], s.meta["bias"]
                 self.vars[s.name + "/kernel"] = dict(w16=w16, master=w16.float().clone(), l2=0.0)
-                self.vars[s.name + "/bias"] = dict(w16=None, master=b32, l2=0.0)        # bias buffers are fp32 already
-                shapes += [(s.name + "/kernel", tuple(w16.shape)), (s.name + "/bias", tuple(b32.shape))]
+                shapes.append((s.name + "/kernel", tuple(w16.shape)))
+                if b32 is not None:                   # layers followed by BatchNorm have no bias
+                    self.vars[s.name + "/bias"] = dict(w16=None, master=b32, l2=0.0)    # bias buffers are fp32 already
+                    shapes.append((s.name + "/bias", tuple(b32.shape)))
+            elif s.kind == "dw":
+                w16 = s.meta["w"]
+                self.vars[s.name + "/depthwise_kernel"] = dict(w16=w16, master=w16.float().clone(), l2=0.0)
+                shapes.append((s.name + "/depthwise_kernel", tuple(w16.shape)))
+            elif s.kind == "bn":
+                for var in ("gamma", "beta"):
+                    self.vars[f"{s.name}/{var}"] = dict(w16=None, master=s.meta[var], l2=0.0)
+                    shapes.append((f"{s.name}/{var}", tuple(s.meta[var].shape)))
             elif s.kind == "l2norm":
                 sc = s.meta["scale"]
                 self.vars[s.name + "/scale"] = dict(w16=None, master=sc, l2=0.0)
@@ -119,15 +128,25 @@ class Trainer(object):
             elif var == "kernel":
                 cin = m.weights[name].shape[2]
                 m.weights[name] = np.ascontiguousarray(arr.transpose(1, 2, 3, 0)[:, :, :cin, :])
+            elif var == "depthwise_kernel":
+                m.weights[name] = np.ascontiguousarray(arr[..., None])                   # [3,3,C] -> [3,3,C,1]
             else:
                 m.weights[name] = arr.copy()
+        if m.has_batchnorm:
+            for key, t in m._train_vars.items():     # moving statistics are updated by the forward kernels
+                if key.endswith("/moving_mean") or key.endswith("/moving_variance"):
+                    m.weights[key] = t.detach().cpu().numpy().copy()
+            m._packed.clear()                        # inference plans fold BatchNorm: rebuild them from the new values
+            m._plans.clear()
+            m._version = getattr(m, "_version", 0) + 1
+            self._eval_dirty = False
 
     # -- backward launch list ---------------------------------------------------------------------------------
     def _prepare(self, B: int) -> Dict[str, Any]:
         if B in self._state:
             return self._state[B]
         m, lib, dev = self.model, self.lib, self.dev
-        plan = m.plan(B)
+        plan = m.train_plan(B)
         N, L = m.n_anchors, m.total_labels
         st: Dict[str, Any] = dict(plan=plan)
         st["g_deltas"] = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
@@ -183,8 +202,9 @@ class Trainer(object):
                 keep.append(d)
                 add(lib.ssd_conv2d_wgrad, (C.byref(d), _ffi.ptr(dy), ldy, _ffi.ptr(self.vars[s.name + "/kernel"]["grad"])),
                     s.name + ":wgrad")
-                add(lib.ssd_bias_grad, (_ffi.ptr(dy), _ffi.ptr(self.vars[s.name + "/bias"]["grad"]), B * Ho * Wo, ldy, cout),
-                    s.name + ":bgrad")
+                if s.name + "/bias" in self.vars:
+                    add(lib.ssd_bias_grad, (_ffi.ptr(dy), _ffi.ptr(self.vars[s.name + "/bias"]["grad"]), B * Ho * Wo, ldy, cout),
+                        s.name + ":bgrad")
                 # data gradient (not needed for the layer fed by the image)
                 if x.data_ptr() == first_conv_input:
                     continue
@@ -209,6 +229,36 @@ class Trainer(object):
                 g.img_stride0, g.pix_stride0 = H * W * cin, cin
                 keep += [wt, src, g]
                 add(lib.ssd_conv2d, (C.byref(g),), s.name + ":dgrad")
+                written[x.data_ptr()] = True
+            elif s.kind == "bn":
+                # y = act(BN(x)) (+ res):  dX of the normalisation into grad(x); the shortcut receives dY itself
+                x, out, res = mt["x"], mt["out"], mt["res"]
+                dy = grad_of[out.data_ptr()]
+                assert written[out.data_ptr()], s.name
+                dx = grad_buf(x)
+                dres, acc_res = None, 0
+                if res is not None:
+                    dres = grad_buf(res)
+                    acc_res = int(written[res.data_ptr()])
+                    written[res.data_ptr()] = True
+                add(lib.ssd_bn_train_bwd, (_ffi.ptr(x), _ffi.ptr(dy), _ffi.ptr(mt["gamma"]), _ffi.ptr(mt["beta"]),
+                                           _ffi.ptr(mt["save"]), mt["M"], mt["C"], mt["act"], _ffi.ptr(dx), _ffi.ptr(dres),
+                                           acc_res, _ffi.ptr(self.vars[s.name + "/gamma"]["grad"]),
+                                           _ffi.ptr(self.vars[s.name + "/beta"]["grad"]), _ffi.ptr(mt["ws"]),
+                                           mt["ws"].numel()), s.name + ":bn")
+                written[x.data_ptr()] = True
+            elif s.kind == "dw":
+                x, out = mt["x"], mt["out"]
+                dy = grad_of[out.data_ptr()]
+                assert written[out.data_ptr()], s.name
+                geo = (B, x.shape[1], x.shape[2], x.shape[3], mt["Ho"], mt["Wo"], mt["stride"], mt["ph"][0], mt["pw"][0])
+                add(lib.ssd_depthwise3x3_wgrad, (_ffi.ptr(x), _ffi.ptr(dy),
+                                                 _ffi.ptr(self.vars[s.name + "/depthwise_kernel"]["grad"])) + geo,
+                    s.name + ":dw_wgrad")
+                dx = grad_buf(x)
+                acc = written[x.data_ptr()]
+                add(lib.ssd_depthwise3x3_dgrad, (_ffi.ptr(dy), _ffi.ptr(mt["w"]), _ffi.ptr(dx)) + geo + (int(acc),),
+                    s.name + ":dw_dgrad")
                 written[x.data_ptr()] = True
             elif s.kind == "pool":
                 x, out = mt["x"], mt["out"]
@@ -251,6 +301,7 @@ class Trainer(object):
         _ffi.check(lib.ssd_loss_bwd(_ffi.ptr(ad), _ffi.ptr(plan.deltas), _ffi.ptr(al), _ffi.ptr(plan.logits), B, N, L,
                                     self.alpha, self.loss_scale / B, _ffi.ptr(st["g_deltas"]), _ffi.ptr(st["g_logits"]),
                                     _ffi.ptr(st["ws"]), st["ws"].numel(), stream), "ssd_loss_bwd")
+        self._eval_dirty = True
         self.grads.zero_()
         for fn, args, what in st["launches"]:
             rc = fn(*args, stream)
@@ -280,6 +331,10 @@ class Trainer(object):
         B = int(images.shape[0])
         st = self._prepare(B)
         plan = st["plan"]
+        if m.has_batchnorm:                          # Keras validates with training=False: moving statistics, folded BN
+            if self._eval_dirty:
+                self.sync_weights_to_host()
+            plan = m.plan(B)
         ad, al = _ffi.to_dev(targets[0]), _ffi.to_dev(targets[1])
         m._to_image_buffer(plan, images)
         plan.run()
