@@ -72,6 +72,12 @@ def vgg16_forward_torch(w: Dict[str, torch.Tensor], hyper_params, images: torch.
     return torch.cat(boxes, 1), torch.cat(labels, 1)
 
 
+def _q16(x, sim):
+    """``sim``: round to fp16 like the device's activation storage, with a straight-through gradient, so that
+    activation masks (ReLU6 knees) are evaluated on the values the device actually stored."""
+    return x + (x.to(torch.float16).to(torch.float32) - x).detach() if sim else x
+
+
 def _bn_train(y, w, name, stats=None):
     """[TF-recall] keras BatchNormalization(epsilon=1e-3) with training=True: batch mean and BIASED variance
     over (B, H, W); ``stats`` (optional dict) receives them for the moving-average check."""
@@ -82,7 +88,7 @@ def _bn_train(y, w, name, stats=None):
     return (y - mean) * torch.rsqrt(var + BN_EPS) * w[name + "/gamma"].view(1, -1, 1, 1) + w[name + "/beta"].view(1, -1, 1, 1)
 
 
-def _conv_bn(x, w, name, bn, stride=1, pads=None, depthwise=False, relu6=True, stats=None):
+def _conv_bn(x, w, name, bn, stride=1, pads=None, depthwise=False, relu6=True, stats=None, sim=False, res=None):
     if depthwise:
         wt = w[name + "/depthwise_kernel"].permute(2, 3, 0, 1)          # [C,1,3,3]
         groups = wt.shape[0]
@@ -93,33 +99,36 @@ def _conv_bn(x, w, name, bn, stride=1, pads=None, depthwise=False, relu6=True, s
     if pads is None:
         pads = (same_pad(x.shape[2], kh, stride), same_pad(x.shape[3], kh, stride))
     x = F.pad(x, (pads[1][0], pads[1][1], pads[0][0], pads[0][1]))
-    y = _bn_train(F.conv2d(x, wt, None, stride=stride, groups=groups), w, bn, stats)
-    return torch.clamp(y, 0.0, 6.0) if relu6 else y
+    y = _bn_train(_q16(F.conv2d(x, wt, None, stride=stride, groups=groups), sim), w, bn, stats)
+    y = torch.clamp(y, 0.0, 6.0) if relu6 else y
+    if res is not None:
+        y = y + res
+    return _q16(y, sim)
 
 
-def mobilenet_v2_forward_torch(w: Dict[str, torch.Tensor], hyper_params, images: torch.Tensor, stats=None):
+def mobilenet_v2_forward_torch(w: Dict[str, torch.Tensor], hyper_params, images: torch.Tensor, stats=None, sim=False):
     """models/ssd_mobilenet_v2.py:24-46 over [TF-recall] keras_applications MobileNetV2, TRAINING mode
-    (BatchNorm on batch statistics), differentiable; returns (pred_deltas, logits)."""
-    x = images.permute(0, 3, 1, 2)
-    x = _conv_bn(x, w, "Conv1", "bn_Conv1", stride=2, pads=(correct_pad(x.shape[2]), correct_pad(x.shape[3])), stats=stats)
+    (BatchNorm on batch statistics), differentiable; returns (pred_deltas, logits).  ``sim=True`` additionally
+    rounds every stored activation to fp16 (straight-through), mirroring the device's storage format."""
+    x = _q16(images.permute(0, 3, 1, 2), sim)
+    x = _conv_bn(x, w, "Conv1", "bn_Conv1", stride=2, pads=(correct_pad(x.shape[2]), correct_pad(x.shape[3])), stats=stats, sim=sim)
     taps = []
     for bid, (t, c, s) in enumerate(MNV2_BLOCKS):
         prefix = f"block_{bid}_" if bid else "expanded_conv_"
         inp = x
         if bid:
-            x = _conv_bn(x, w, prefix + "expand", prefix + "expand_BN", stats=stats)
+            x = _conv_bn(x, w, prefix + "expand", prefix + "expand_BN", stats=stats, sim=sim)
             if bid == 13:
                 taps.append(x)
         pads = (correct_pad(x.shape[2]), correct_pad(x.shape[3])) if s == 2 else None
-        x = _conv_bn(x, w, prefix + "depthwise", prefix + "depthwise_BN", stride=s, pads=pads, depthwise=True, stats=stats)
-        x = _conv_bn(x, w, prefix + "project", prefix + "project_BN", relu6=False, stats=stats)
-        if s == 1 and inp.shape[1] == c:
-            x = x + inp
-    x = _conv_bn(x, w, "Conv_1", "Conv_1_bn", stats=stats)
+        x = _conv_bn(x, w, prefix + "depthwise", prefix + "depthwise_BN", stride=s, pads=pads, depthwise=True, stats=stats, sim=sim)
+        x = _conv_bn(x, w, prefix + "project", prefix + "project_BN", relu6=False, stats=stats, sim=sim,
+                     res=inp if (s == 1 and inp.shape[1] == c) else None)
+    x = _conv_bn(x, w, "Conv_1", "Conv_1_bn", stats=stats, sim=sim)
     taps.append(x)
     for i in range(1, 5):
-        x = _conv(x, w, f"extra{i}_1", padding="valid")
-        x = _conv(x, w, f"extra{i}_2", stride=2)
+        x = _q16(_conv(x, w, f"extra{i}_1", padding="valid"), sim)
+        x = _q16(_conv(x, w, f"extra{i}_2", stride=2), sim)
         taps.append(x)
     L = hyper_params["total_labels"]
     labels, boxes = [], []
@@ -156,13 +165,13 @@ def losses_torch(actual_deltas, actual_labels, pred_deltas, logits, neg_pos_rati
 
 def train_step(weights: Dict[str, np.ndarray], hyper_params, images: np.ndarray, actual_deltas: np.ndarray,
                actual_labels: np.ndarray, l2_kernels: Sequence[str], neg_pos_ratio=3.0, alpha=1.0,
-               backbone: str = "vgg16", stats=None):
+               backbone: str = "vgg16", stats=None, fp16sim: bool = False):
     """Returns ``(loss dict, grads dict)`` -- gradients of mean_B(loc) + mean_B(conf) + reg w.r.t. every variable."""
     w = {k: torch.tensor(v, dtype=torch.float32, requires_grad=not k.split("/")[-1].startswith("moving_"))
          for k, v in weights.items()}
     img = torch.from_numpy(np.ascontiguousarray(images, np.float32))
     if backbone == "mobilenet_v2":
-        pd, z = mobilenet_v2_forward_torch(w, hyper_params, img, stats)
+        pd, z = mobilenet_v2_forward_torch(w, hyper_params, img, stats, sim=fp16sim)
     else:
         pd, z = vgg16_forward_torch(w, hyper_params, img)
     loc, conf = losses_torch(actual_deltas, actual_labels, pd, z, neg_pos_ratio, alpha)

@@ -380,51 +380,143 @@ def _mnv2_setup(B, seed=2):
     return model, hp, img, ad, al
 
 
-def test_mobilenet_v2_backward_against_autograd():
-    """BASELINE config 4's step on one GPU: training-mode forward (batch statistics), loss, full backward."""
+def _nchw(t):
+    return t.float().cpu().permute(0, 3, 1, 2).contiguous()
+
+
+def test_mobilenet_v2_backward_layerwise_against_autograd():
+    """BASELINE config 4's step on one GPU: training-mode forward (batch statistics), loss, full backward.
+
+    The randomly initialised 52-BatchNorm network amplifies one-ulp fp16 differences by ~1.2x per layer (measured:
+    forward statistics agree to 2e-7 at the stem and 1.6e-3 at Conv_1 against an fp16-storage-simulating oracle), so
+    a whole-network comparison cannot separate kernel errors from that drift.  Every backward launch is therefore
+    checked against torch autograd of ITS OWN layer, fed with the tensors the device actually stored (input,
+    upstream gradient); gradients of tensors with several consumers must equal the sum of the consumers'
+    contributions.  Tolerance 5e-3 of the tensor's max (fp16 operands / fp16 gradient storage)."""
     from tf_ssd_b200.models.train_engine import Trainer
-    model, hp, img, ad, al = _mnv2_setup(4)
-    stats = {}
-    ref_loss, ref_grads = to.train_step(model.weights, hp, img, ad, al, model.l2_kernels, backbone="mobilenet_v2", stats=stats)
+    B = 4
+    model, hp, img, ad, al = _mnv2_setup(B)
     tr = Trainer(model, loss_scale=256.0)
     out = tr.forward_backward(img, ad, al)
     torch.cuda.synchronize()
-    assert np.allclose(out["loc"].cpu().numpy(), ref_loss["loc"], rtol=3e-2, atol=2e-3)
-    assert np.allclose(out["conf"].cpu().numpy(), ref_loss["conf"], rtol=3e-2, atol=2e-3)
-    # batch statistics of the first and of a deep BatchNorm layer (through save = mean | rstd)
+    st = tr._state[B]
+    plan, grad_of = st["plan"], st["grad_of"]
+    N, L = model.n_anchors, 21
+    g_logits, g_deltas = st["g_logits"].cpu(), st["g_deltas"].cpu()
+    contrib = {}                                   # activation data_ptr -> summed torch dX of all consumers (NHWC)
+    checked = dict(conv=0, dw=0, bn=0)
+
+    def add_contrib(t, dx_nchw):
+        v = dx_nchw.permute(0, 2, 3, 1).numpy()
+        contrib[t.data_ptr()] = contrib.get(t.data_ptr(), 0.0) + v
+
+    def var_grad(name):
+        return tr.vars[name]["grad"].cpu().numpy()
+
+    first_input = [s for s in plan.steps if s.kind == "cast"][0].keep[0].data_ptr()
+    for s in plan.steps:
+        mt = s.meta
+        if s.kind == "conv":
+            x, w16 = mt["x"], mt["w"]
+            cout, k, stride, dil = mt["cout"], mt["k"], mt["stride"], mt["dilation"]
+            (pt, pb), (pl, pr) = mt["ph"], mt["pw"]
+            if "head" in mt:
+                off, cnt, A = mt["head"]
+                Ho, Wo = mt["Ho"], mt["Wo"]
+                gl = g_logits[:, off:off + cnt].reshape(B, Ho, Wo, A * L)
+                gd = g_deltas[:, off:off + cnt].reshape(B, Ho, Wo, A * 4)
+                dy = torch.cat([gl, gd], -1).half().float().permute(0, 3, 1, 2)
+            else:
+                dy = _nchw(grad_of[mt["out0"].data_ptr()])          # already ReLU-masked in place where the layer has one
+            xt = _nchw(x).requires_grad_(True)
+            wt = w16.float().cpu().permute(0, 3, 1, 2).contiguous().requires_grad_(True)      # OHWI -> OIHW
+            y = F.conv2d(F.pad(xt, (pl, pr, pt, pb)), wt, None, stride=stride, dilation=dil)
+            y.backward(dy)
+            assert _rel(var_grad(s.name + "/kernel"), wt.grad.permute(0, 2, 3, 1).numpy()) < 5e-3, s.name
+            if s.name + "/bias" in tr.vars:
+                assert _rel(var_grad(s.name + "/bias"), dy.sum((0, 2, 3)).numpy()) < 5e-3, s.name
+            if x.data_ptr() != first_input:
+                add_contrib(x, xt.grad)
+            checked["conv"] += 1
+        elif s.kind == "dw":
+            x, w16 = mt["x"], mt["w"]
+            (pt, pb), (pl, pr) = mt["ph"], mt["pw"]
+            dy = _nchw(grad_of[mt["out"].data_ptr()])
+            xt = _nchw(x).requires_grad_(True)
+            wt = w16.float().cpu().permute(2, 0, 1).unsqueeze(1).contiguous().requires_grad_(True)
+            y = F.conv2d(F.pad(xt, (pl, pr, pt, pb)), wt, None, stride=mt["stride"], groups=x.shape[3])
+            y.backward(dy)
+            assert _rel(var_grad(s.name + "/depthwise_kernel"), wt.grad[:, 0].permute(1, 2, 0).numpy()) < 5e-3, s.name
+            add_contrib(x, xt.grad)
+            checked["dw"] += 1
+        elif s.kind == "bn":
+            x, res = mt["x"], mt["res"]
+            dy = _nchw(grad_of[mt["out"].data_ptr()])
+            xt = _nchw(x).requires_grad_(True)
+            gt_ = mt["gamma"].cpu().clone().requires_grad_(True)
+            bt = mt["beta"].cpu().clone().requires_grad_(True)
+            mean = xt.mean((0, 2, 3), keepdim=True)
+            var = ((xt - mean) ** 2).mean((0, 2, 3), keepdim=True)
+            y = (xt - mean) * torch.rsqrt(var + 1e-3) * gt_.view(1, -1, 1, 1) + bt.view(1, -1, 1, 1)
+            if mt["act"] == 2:
+                y = torch.clamp(y, 0.0, 6.0)
+            y.backward(dy)
+            assert _rel(var_grad(s.name + "/gamma"), gt_.grad.numpy()) < 5e-3, s.name
+            # sum(dY) of a layer followed by another BatchNorm'd convolution is ~0: compare against the scale of dgamma
+            assert np.max(np.abs(var_grad(s.name + "/beta") - bt.grad.numpy())) < 5e-3 * max(
+                np.abs(bt.grad.numpy()).max(), np.abs(gt_.grad.numpy()).max()), s.name
+            add_contrib(x, xt.grad)
+            if res is not None:
+                add_contrib(res, dy)
+            checked["bn"] += 1
+    assert checked["bn"] == 52 and checked["dw"] == 17 and checked["conv"] == 35 + 8 + 6, checked
+    n_multi = 0
+    for ptr_, want in contrib.items():
+        got = grad_of[ptr_].float().cpu().numpy()
+        assert _rel(got, want) < 5e-3, ptr_
+        n_multi += 1
+    assert n_multi > 100
+    assert np.isfinite(out["loc"].cpu().numpy()).all()
+
+
+def test_mobilenet_v2_step_against_fp32_oracle():
+    """Whole-step sanity against the float32 torch oracle: losses and batch statistics agree; gradients agree in
+    direction (the residual is the fp16 drift documented above, dominated by ReLU6 masks flipping)."""
+    from tf_ssd_b200.models.train_engine import Trainer
+    model, hp, img, ad, al = _mnv2_setup(4)
+    stats = {}
+    # neg_pos_ratio large enough to select every negative: the comparison is then independent of the mining order
+    ref_loss, ref_grads = to.train_step(model.weights, hp, img, ad, al, model.l2_kernels, neg_pos_ratio=1e4,
+                                        backbone="mobilenet_v2", stats=stats, fp16sim=True)
+    tr = Trainer(model, loss_scale=256.0, neg_pos_ratio=1e4)
+    out = tr.forward_backward(img, ad, al)
+    torch.cuda.synchronize()
+    assert np.allclose(out["loc"].cpu().numpy(), ref_loss["loc"], rtol=1e-2, atol=1e-3)
+    assert np.allclose(out["conf"].cpu().numpy(), ref_loss["conf"], rtol=1e-2, atol=1e-3)
     plan = model.train_plan(4)
     for s in plan.steps:
-        if s.kind == "bn" and s.name in ("bn_Conv1", "block_13_expand_BN", "Conv_1_bn"):
+        if s.kind == "bn":
             mean, var, _ = stats[s.name]
             Cc = mean.shape[0]
             save = s.meta["save"].cpu().numpy()
-            assert _l2(save[:Cc], mean) < 2e-2, s.name
-            assert _l2(save[Cc:], 1.0 / np.sqrt(var + 1e-3)) < 2e-2, s.name
-    worst = {}
+            tol = 1e-5 if s.name == "bn_Conv1" else 1e-2
+            assert _l2(save[:Cc], mean) < tol and _l2(save[Cc:], 1.0 / np.sqrt(var + 1e-3)) < tol, s.name
+    cos = {}
     for name, v in tr.vars.items():
-        g = v["grad"].cpu().numpy() / tr.loss_scale
         layer, var = name.rsplit("/", 1)
-        if layer.endswith("_conv_head"):
-            idx = layer.split("_")[0]
-            if var == "kernel":
-                ref = np.concatenate([ref_grads[f"{idx}_conv_label_output/kernel"], ref_grads[f"{idx}_conv_boxes_output/kernel"]], -1)
-                ref = ref.transpose(3, 0, 1, 2)
-            else:
-                ref = np.concatenate([ref_grads[f"{idx}_conv_label_output/bias"], ref_grads[f"{idx}_conv_boxes_output/bias"]])
-        elif var == "kernel":
+        if layer.endswith("_conv_head") or (var == "beta" and layer.endswith("project_BN")):
+            continue
+        g = v["grad"].cpu().numpy() / tr.loss_scale
+        if var == "kernel":
             ref = ref_grads[name].transpose(3, 0, 1, 2)
-            if ref.shape[3] != g.shape[3]:                         # Conv1: Cin padded 3 -> 8
-                assert np.all(g[..., ref.shape[3]:] == 0)
-                g = g[..., :ref.shape[3]]
+            g = g[..., :ref.shape[3]]
         elif var == "depthwise_kernel":
             ref = ref_grads[name][..., 0]
         else:
             ref = ref_grads[name]
-        worst[name] = _l2(g, ref)
-    top = sorted(worst.items(), key=lambda kv: -kv[1])[:8]
-    print("worst relative L2 gradient errors:", top)
-    bad = {k: v for k, v in worst.items() if v > 8e-2}
-    assert not bad, bad
+        cos[name] = float((g * ref).sum() / (np.linalg.norm(g) * np.linalg.norm(ref) + 1e-30))
+    assert cos["block_13_expand_BN/gamma"] > 0.999 and cos["extra1_2/kernel"] > 0.99
+    assert min(cos.values()) > 0.85, sorted(cos.items(), key=lambda kv: kv[1])[:5]
 
 
 def test_mobilenet_v2_training_reduces_loss_and_updates_batchnorm():
