@@ -406,9 +406,13 @@ def test_mobilenet_v2_backward_layerwise_against_autograd():
     contrib = {}                                   # activation data_ptr -> summed torch dX of all consumers (NHWC)
     checked = dict(conv=0, dw=0, bn=0)
 
-    def add_contrib(t, dx_nchw):
+    consumers = {}
+    relu_mask = {}                                 # outputs of bias+ReLU convolutions: their gradient buffer is masked in place
+
+    def add_contrib(t, dx_nchw, who="?"):
         v = dx_nchw.permute(0, 2, 3, 1).numpy()
         contrib[t.data_ptr()] = contrib.get(t.data_ptr(), 0.0) + v
+        consumers.setdefault(t.data_ptr(), []).append(who)
 
     def var_grad(name):
         return tr.vars[name]["grad"].cpu().numpy()
@@ -428,6 +432,8 @@ def test_mobilenet_v2_backward_layerwise_against_autograd():
                 dy = torch.cat([gl, gd], -1).half().float().permute(0, 3, 1, 2)
             else:
                 dy = _nchw(grad_of[mt["out0"].data_ptr()])          # already ReLU-masked in place where the layer has one
+                if mt["act"] != 0:
+                    relu_mask[mt["out0"].data_ptr()] = (mt["out0"].float().cpu().numpy() > 0)
             xt = _nchw(x).requires_grad_(True)
             wt = w16.float().cpu().permute(0, 3, 1, 2).contiguous().requires_grad_(True)      # OHWI -> OIHW
             y = F.conv2d(F.pad(xt, (pl, pr, pt, pb)), wt, None, stride=stride, dilation=dil)
@@ -436,7 +442,7 @@ def test_mobilenet_v2_backward_layerwise_against_autograd():
             if s.name + "/bias" in tr.vars:
                 assert _rel(var_grad(s.name + "/bias"), dy.sum((0, 2, 3)).numpy()) < 5e-3, s.name
             if x.data_ptr() != first_input:
-                add_contrib(x, xt.grad)
+                add_contrib(x, xt.grad, s.name)
             checked["conv"] += 1
         elif s.kind == "dw":
             x, w16 = mt["x"], mt["w"]
@@ -447,7 +453,7 @@ def test_mobilenet_v2_backward_layerwise_against_autograd():
             y = F.conv2d(F.pad(xt, (pl, pr, pt, pb)), wt, None, stride=mt["stride"], groups=x.shape[3])
             y.backward(dy)
             assert _rel(var_grad(s.name + "/depthwise_kernel"), wt.grad[:, 0].permute(1, 2, 0).numpy()) < 5e-3, s.name
-            add_contrib(x, xt.grad)
+            add_contrib(x, xt.grad, s.name)
             checked["dw"] += 1
         elif s.kind == "bn":
             x, res = mt["x"], mt["res"]
@@ -465,17 +471,21 @@ def test_mobilenet_v2_backward_layerwise_against_autograd():
             # sum(dY) of a layer followed by another BatchNorm'd convolution is ~0: compare against the scale of dgamma
             assert np.max(np.abs(var_grad(s.name + "/beta") - bt.grad.numpy())) < 5e-3 * max(
                 np.abs(bt.grad.numpy()).max(), np.abs(gt_.grad.numpy()).max()), s.name
-            add_contrib(x, xt.grad)
+            add_contrib(x, xt.grad, s.name)
             if res is not None:
-                add_contrib(res, dy)
+                add_contrib(res, dy, s.name + ":shortcut")
             checked["bn"] += 1
     assert checked["bn"] == 52 and checked["dw"] == 17 and checked["conv"] == 35 + 8 + 6, checked
-    n_multi = 0
+    errs = {}
     for ptr_, want in contrib.items():
         got = grad_of[ptr_].float().cpu().numpy()
-        assert _rel(got, want) < 5e-3, ptr_
-        n_multi += 1
-    assert n_multi > 100
+        if ptr_ in relu_mask:
+            want = want * relu_mask[ptr_]
+        errs["+".join(consumers[ptr_])] = (_rel(got, want), _l2(got, want))
+    # L2 within fp16 storage noise everywhere; the max norm additionally tolerates single elements whose ReLU6 knee
+    # (v == 0 or 6 to within float32 rounding of the normalisation) is resolved differently by torch
+    bad = {k: v for k, v in errs.items() if v[1] > 2e-3 or v[0] > 3e-2}
+    assert len(errs) > 100 and not bad, bad
     assert np.isfinite(out["loc"].cpu().numpy()).all()
 
 
