@@ -95,19 +95,28 @@ bn_stats_partial_kernel(const uint4* __restrict__ x, ChunkGeom g, float* __restr
     cta_combine<2>(acc, g.C8, g.tpr, s_red, partial + (size_t)blockIdx.x * 2 * g.C8 * 8);
 }
 
-// One thread per channel: partial rows added in order; mean / biased variance -> save[0..C) = mean,
-// save[C..2C) = rstd; moving statistics updated like Keras' fused BatchNormalization ([TF-recall]:
-// moving_mean = m*mom + mean*(1-mom); moving_variance uses the unbiased batch variance).
-__global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int chunks, int C, double inv_m, double bessel,
-                                         float eps, float momentum, float* __restrict__ save,
-                                         float* __restrict__ moving_mean, float* __restrict__ moving_var) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// Fixed-order sum of column c of the partial rows by ONE WARP: lane l adds rows l, l+32, ... (double), then a
+// shuffle tree -- the same association every run, and 32 independent load streams instead of one serial chain.
+__device__ __forceinline__ double warp_column_sum(const float* __restrict__ col, int chunks, size_t row_stride, int lane) {
+    double s = 0.0;
+    for (int j = lane; j < chunks; j += 32) s += (double)__ldg(col + (size_t)j * row_stride);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+
+// One warp per channel: mean / biased variance -> save[0..C) = mean, save[C..2C) = rstd; moving statistics
+// updated like Keras' fused BatchNormalization ([TF-recall]: moving_mean = m*mom + mean*(1-mom);
+// moving_variance uses the unbiased batch variance).
+__global__ void __launch_bounds__(256)
+bn_stats_finalize_kernel(const float* __restrict__ partial, int chunks, int C, double inv_m, double bessel,
+                         float eps, float momentum, float* __restrict__ save,
+                         float* __restrict__ moving_mean, float* __restrict__ moving_var) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
-    double s = 0.0, ss = 0.0;
-    for (int j = 0; j < chunks; ++j) {
-        s += (double)partial[(size_t)j * 2 * C + c];
-        ss += (double)partial[(size_t)j * 2 * C + C + c];
-    }
+    const double s = warp_column_sum(partial + c, chunks, (size_t)2 * C, lane);
+    const double ss = warp_column_sum(partial + C + c, chunks, (size_t)2 * C, lane);
+    if (lane) return;
     const double mean = s * inv_m;
     double var = ss * inv_m - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -183,16 +192,15 @@ bn_bwd_partial_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
     cta_combine<2>(acc, g.C8, g.tpr, s_red, partial + (size_t)blockIdx.x * 2 * g.C8 * 8);
 }
 
-// dbeta += sum g, dgamma += sum g*xhat; coef[0..C) = sum g / M, coef[C..2C) = sum g*xhat / M
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int chunks, int C, double inv_m,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// dbeta += sum g, dgamma += sum g*xhat; coef[0..C) = sum g / M, coef[C..2C) = sum g*xhat / M  (one warp per channel)
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int chunks, int C, double inv_m,
+                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
-    double s1 = 0.0, s2 = 0.0;
-    for (int j = 0; j < chunks; ++j) {
-        s1 += (double)partial[(size_t)j * 2 * C + c];
-        s2 += (double)partial[(size_t)j * 2 * C + C + c];
-    }
+    const double s1 = warp_column_sum(partial + c, chunks, (size_t)2 * C, lane);
+    const double s2 = warp_column_sum(partial + C + c, chunks, (size_t)2 * C, lane);
+    if (lane) return;
     if (dbeta) dbeta[c] += (float)s1;
     if (dgamma) dgamma[c] += (float)s2;
     coef[c] = (float)(s1 * inv_m);
@@ -361,7 +369,7 @@ extern "C" int ssd_bn_train_fwd(const void* d_x, const float* d_gamma, const flo
         reinterpret_cast<const uint4*>(d_x), g, partial);
     SSD_CHECK_LAUNCH("bn_stats_partial_kernel");
     const double bessel = M > 1 ? (double)M / (double)(M - 1) : 1.0;
-    bn_stats_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(partial, g.chunks, C, 1.0 / (double)M, bessel, eps, momentum,
+    bn_stats_finalize_kernel<<<ceil_div(C, 8), 256, 0, st>>>(partial, g.chunks, C, 1.0 / (double)M, bessel, eps, momentum,
                                                                d_save, d_moving_mean, d_moving_var);
     SSD_CHECK_LAUNCH("bn_stats_finalize_kernel");
     bn_apply_kernel<<<ew_grid(g.total), 256, 0, st>>>(reinterpret_cast<const uint4*>(d_x), d_gamma, d_beta, d_save,
@@ -389,7 +397,7 @@ extern "C" int ssd_bn_train_bwd(const void* d_x, const void* d_dy, const float* 
         reinterpret_cast<const uint4*>(d_x), reinterpret_cast<const uint4*>(d_dy), d_gamma, d_beta, d_save, C, act, g,
         partial);
     SSD_CHECK_LAUNCH("bn_bwd_partial_kernel");
-    bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(partial, g.chunks, C, 1.0 / (double)M, d_dgamma, d_dbeta, coef);
+    bn_bwd_finalize_kernel<<<ceil_div(C, 8), 256, 0, st>>>(partial, g.chunks, C, 1.0 / (double)M, d_dgamma, d_dbeta, coef);
     SSD_CHECK_LAUNCH("bn_bwd_finalize_kernel");
     bn_bwd_apply_kernel<<<ew_grid(g.total), 256, 0, st>>>(
         reinterpret_cast<const uint4*>(d_x), reinterpret_cast<const uint4*>(d_dy), d_gamma, d_beta, d_save, coef, g.C8, C,

@@ -58,10 +58,12 @@ class Trainer(object):
     """Owns the master weights, Adam state, gradient buffers and the backward launch list."""
 
     def __init__(self, model: SSDModel, learning_rate: float = 1e-3, neg_pos_ratio: float = 3.0, loc_loss_alpha: float = 1.0,
-                 beta_1: float = 0.9, beta_2: float = 0.999, epsilon: float = 1e-7, loss_scale: float = 1024.0):
+                 beta_1: float = 0.9, beta_2: float = 0.999, epsilon: float = 1e-7, loss_scale: float = 1024.0,
+                 use_cuda_graph: bool = True):
         _ffi.check_device()
         self.model = model
         model.trainer = self                         # the model's training-mode variables now belong to this trainer
+        self.use_cuda_graph = bool(use_cuda_graph)
         self._eval_dirty = True
         self.lib = _ffi.lib()
         self.dev = _ffi.require_cuda()
@@ -154,6 +156,9 @@ class Trainer(object):
         st["loc"] = torch.empty((B,), dtype=torch.float32, device=dev)
         st["conf"] = torch.empty((B,), dtype=torch.float32, device=dev)
         st["ws"] = _ffi.workspace(lib.ssd_loss_workspace_bytes(B, N, L))
+        st["ad"] = torch.zeros((B, N, 4), dtype=torch.float32, device=dev)      # static target buffers (graph inputs)
+        st["al"] = torch.zeros((B, N, L), dtype=torch.float32, device=dev)
+        st["graph"] = None
         keep: List[Any] = []
         launches: List[Tuple[Any, tuple, str]] = []
         grad_of: Dict[int, torch.Tensor] = {}       # activation data_ptr -> fp16 gradient buffer
@@ -283,15 +288,14 @@ class Trainer(object):
         return st
 
     # -- one step ---------------------------------------------------------------------------------------------
-    def forward_backward(self, images: Any, actual_deltas: Any, actual_labels: Any) -> Dict[str, torch.Tensor]:
-        """Forward, loss, backward: fills the gradient buckets (loss-scaled) and returns the per-image losses."""
+    def _enqueue_step(self, st: Dict[str, Any], B: int) -> None:
+        """Forward plan, fused loss forward/backward and the backward launch list on the current stream.  Nothing
+        here allocates or synchronises, so the whole sequence is captured once per batch size into a CUDA graph
+        (several hundred small launches per MobileNetV2 step would otherwise be bound by the host's launch rate)."""
         m, lib = self.model, self.lib
-        B = int(images.shape[0])
-        st = self._prepare(B)
         plan = st["plan"]
         N, L = m.n_anchors, m.total_labels
-        ad, al = _ffi.to_dev(actual_deltas), _ffi.to_dev(actual_labels)
-        m._to_image_buffer(plan, images)
+        ad, al = st["ad"], st["al"]
         plan.run()
         stream = _ffi.stream()
         _ffi.check(lib.ssd_loss_fwd(_ffi.ptr(ad), _ffi.ptr(plan.deltas), _ffi.ptr(al), _ffi.ptr(plan.logits), B, N, L,
@@ -301,12 +305,32 @@ class Trainer(object):
         _ffi.check(lib.ssd_loss_bwd(_ffi.ptr(ad), _ffi.ptr(plan.deltas), _ffi.ptr(al), _ffi.ptr(plan.logits), B, N, L,
                                     self.alpha, self.loss_scale / B, _ffi.ptr(st["g_deltas"]), _ffi.ptr(st["g_logits"]),
                                     _ffi.ptr(st["ws"]), st["ws"].numel(), stream), "ssd_loss_bwd")
-        self._eval_dirty = True
         self.grads.zero_()
         for fn, args, what in st["launches"]:
             rc = fn(*args, stream)
             if rc != 0:
                 _ffi.check(rc, what)
+
+    def forward_backward(self, images: Any, actual_deltas: Any, actual_labels: Any) -> Dict[str, torch.Tensor]:
+        """Forward, loss, backward: fills the gradient buckets (loss-scaled) and returns the per-image losses."""
+        m = self.model
+        B = int(images.shape[0])
+        st = self._prepare(B)
+        st["ad"].copy_(_ffi.to_dev(actual_deltas), non_blocking=True)
+        st["al"].copy_(_ffi.to_dev(actual_labels), non_blocking=True)
+        m._to_image_buffer(st["plan"], images)
+        self._eval_dirty = True
+        if not self.use_cuda_graph:
+            self._enqueue_step(st, B)
+        elif st["graph"] is None:
+            self._enqueue_step(st, B)                # the first step runs eagerly (workspaces, function attributes) ...
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):                # ... and is then recorded, without executing, for every later step
+                self._enqueue_step(st, B)
+            st["graph"] = g
+        else:
+            st["graph"].replay()
         return dict(loc=st["loc"], conf=st["conf"])
 
     def apply_gradients(self, learning_rate: Optional[float] = None) -> None:

@@ -1,8 +1,9 @@
-"""Config-3 measurement helper (BASELINE.json configs[2]): SSD300-VGG16, batch 32 per GPU, one full
-training step = IoU match + target encode -> forward -> hard-negative-mining loss -> backward ->
-(all-reduce) -> Adam.  Used by bench.py (``training`` key) and runnable on its own / under torchrun.
+"""Training-step measurement helper: BASELINE.json configs[2] (SSD300-VGG16, batch 32 per GPU) and configs[3]
+(SSD300-MobileNetV2, batch 32 per GPU, 256 over 8 GPUs).  One full training step = IoU match + target encode ->
+forward (BatchNorm on batch statistics for MobileNetV2) -> hard-negative-mining loss -> backward -> (gradient
+all-reduce) -> Adam.  Used by bench.py (``training`` key) and runnable on its own / under torchrun.
 
-    python tools/train_bench.py [--steps K] [--warmup W] [--batch B] [--check-dp]
+    python tools/train_bench.py [--backbone vgg16|mobilenet_v2] [--steps K] [--warmup W] [--batch B] [--check-dp]
 """
 import argparse
 import json
@@ -14,15 +15,18 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+BACKBONE = "vgg16"
+
+
 def build(batch, seed=1234):
     import torch
     from tf_ssd_b200 import synth
-    from tf_ssd_b200.models import ssd_vgg16
+    from tf_ssd_b200.models import ssd_mobilenet_v2, ssd_vgg16
     from tf_ssd_b200.models.train_engine import Trainer
     from tf_ssd_b200.utils import bbox_utils, train_utils
-    hp = train_utils.get_hyper_params("vgg16")
+    hp = train_utils.get_hyper_params(BACKBONE)
     hp["total_labels"] = 21
-    model = ssd_vgg16.get_model(hp, seed=seed)
+    model = (ssd_mobilenet_v2 if BACKBONE == "mobilenet_v2" else ssd_vgg16).get_model(hp, seed=seed)
     trainer = Trainer(model)
     priors = bbox_utils.generate_prior_boxes(hp["feature_map_shapes"], hp["aspect_ratios"])
     return hp, model, trainer, priors
@@ -65,7 +69,8 @@ def measure(steps=10, warmup=3, batch=32):
     torch.cuda.synchronize()
     ms = dist_utils.max_over_ranks(float(e0.elapsed_time(e1)), torch.device("cuda", local_rank))
     flops = 3 * 2.0 * model.macs_per_image * batch                        # fwd + dgrad + wgrad
-    return {"workload": "SSD300-VGG16 batch=32/GPU training step (IoU match + encode, forward, hard-negative loss, backward, "
+    name = "SSD300-MobileNetV2" if BACKBONE == "mobilenet_v2" else "SSD300-VGG16"
+    return {"workload": f"{name} batch={batch}/GPU training step (IoU match + encode, forward, hard-negative loss, backward, "
                         "grad all-reduce, Adam), fp16 activations / fp32 master weights",
             "value": world * batch * steps / (ms / 1e3), "unit": "images/s", "ms_per_step": ms / steps, "n_gpus": world,
             "steps": steps, "conv_tflops": world * flops * steps / (ms / 1e3) / 1e12,
@@ -109,7 +114,7 @@ def breakdown(batch=32):
     trainer.grads.zero_(); mark("zero_grads")
     per_layer = []
     for fn, args, what in st["launches"]:
-        _ffi.check(fn(*args, stream), what); mark("bwd:" + what.split(":")[1])
+        _ffi.check(fn(*args, stream), what); mark("bwd:" + what.split(":")[-1])
         per_layer.append(what)
     trainer.apply_gradients(); mark("adam")
     torch.cuda.synchronize()
@@ -142,7 +147,23 @@ def check_dp():
     trainer.grads.allreduce_mean_()
     torch.cuda.synchronize()
     mine = torch.cat([bk.flatten() for bk in trainer.grads.buckets])
-    if rank == 0:
+    if rank == 0 and BACKBONE == "mobilenet_v2":
+        # BatchNorm statistics stay per replica (Keras default): the reference is the mean of the
+        # per-shard gradients computed one after the other in this process
+        hp1, model1, trainer1, _ = build(2)
+        ref = None
+        for r in range(world):
+            b1, e1 = dist_utils.shard_range(2 * world, r, world)
+            d1, oh1 = train_utils.calculate_actual_outputs(priors, gt[b1:e1], lab[b1:e1], hp1)
+            trainer1.forward_backward(img[b1:e1], d1, oh1)
+            torch.cuda.synchronize()
+            g1 = torch.cat([bk.flatten() for bk in trainer1.grads.buckets])
+            ref = g1 if ref is None else ref + g1
+        ref = ref / world
+        rel = float((mine - ref).norm() / ref.norm())
+        print(json.dumps({"dp_equivalence_rel_l2": rel, "world": world, "ok": rel < 2e-3, "backbone": BACKBONE}))
+        assert rel < 2e-3, rel
+    elif rank == 0:
         hp1, model1, trainer1, _ = build(2 * world)
         d1, oh1 = train_utils.calculate_actual_outputs(priors, gt, lab, hp1)
         trainer1.forward_backward(img, d1, oh1)
@@ -159,9 +180,11 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--backbone", default="vgg16", choices=["vgg16", "mobilenet_v2"])
     ap.add_argument("--check-dp", action="store_true")
     ap.add_argument("--breakdown", action="store_true")
     a = ap.parse_args()
+    BACKBONE = a.backbone
     if a.breakdown:
         breakdown(a.batch)
     elif a.check_dp:
