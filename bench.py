@@ -50,6 +50,21 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def _ncu_traffic(kind):
+    """Per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel group, taken from the
+    committed ``ncu --set full`` capture of this same step (profiles/r1_traffic.json; written by tools/ncu_traffic.py).
+    None when no capture is committed for that group."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f)
+    e = t.get(kind)
+    return None if e is None else {"dram_bytes_per_launch": e["dram_bytes_per_launch"], "launches": e["launches"],
+                                   "algorithmic_bytes_per_launch": e.get("algorithmic_bytes_per_launch"),
+                                   "source": e.get("source", "profiles/r1_traffic.json")}
+
+
 def _hyper_params():
     from tf_ssd_b200.utils import train_utils
     hp = train_utils.get_hyper_params(BACKBONE)
@@ -356,6 +371,12 @@ def run_b200(args):
     for _ in range(W):
         dm.run_resident(B, 0)
     barrier()
+    if args.profile_one_step:               # ncu --profile-from-start off: exactly one step's launches, eagerly
+        torch.cuda.profiler.start()
+        st["enqueue"]()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(_physical_gpu_index(local_rank))
     sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -388,6 +409,19 @@ def run_b200(args):
     dev_ms = dist_utils.max_over_ranks(dev_ms, plan.device)        # slowest rank
     e2e_ms = dist_utils.max_over_ranks(e2e_ms, plan.device)
 
+    # ---- training steps of BASELINE configs[2] / configs[3] (every rank takes part: gradient all-reduce) -----
+    training = None
+    if not args.skip_train:
+        del flush
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import train_bench
+        training = {}
+        for bb, key in (("mobilenet_v2", "ssd300_mobilenet_v2_b32_per_gpu"), ("vgg16", "ssd300_vgg16_b32_per_gpu")):
+            train_bench.BACKBONE = bb
+            training[key] = train_bench.measure(steps=args.train_steps, warmup=3, batch=32)
+            torch.cuda.empty_cache()
+
     if rank == 0:
         total_images = world * B * K
         value = total_images / (dev_ms / 1e3)
@@ -406,6 +440,8 @@ def run_b200(args):
                     "api": "get_decoder_model(...).predict(host batches): pinned H2D + graph replay + D2H, 2 slots in flight"},
             "gpu_launches": K * dm.launches_per_batch(B),
         }
+        if training is not None:
+            line["training"] = training
         if world == 1:
             per = _profile_steps(dm, B)
             steps = plan.steps
@@ -427,7 +463,7 @@ def run_b200(args):
             else:
                 ach = g["bytes"] / (g["ms"] * 1e-3) / 1e9
                 roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]}
-            roof.update({"traffic": None, "kernel": {"conv": "ssd_conv2d launches: conv_tcgen05_kernel (stride 1) + conv_igemm_kernel (stride 2)",
+            roof.update({"traffic": _ncu_traffic(top), "kernel": {"conv": "ssd_conv2d launches: conv_tcgen05_kernel (stride 1) + conv_igemm_kernel (stride 2)",
                                                      "dw": "depthwise3x3_kernel", "decode_nms": "nms_candidates+nms_image"}.get(top, top),
                          "launches_per_step": g["launches"], "ms_per_step": g["ms"], "share_of_step": g["ms"] / total,
                          "algorithmic_bytes_per_step": g["bytes"], "flops_per_step": g["flops"], "peak_source": peaks["source"],
@@ -465,6 +501,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     ap.add_argument("--skip-box", action="store_true", help="omit the box-kernel stress rooflines")
+    ap.add_argument("--profile-one-step", action="store_true",
+                    help="warm up, run ONE eager step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
+    ap.add_argument("--skip-train", action="store_true", help="omit the training-step measurements (configs[2], configs[3])")
+    ap.add_argument("--train-steps", type=int, default=10)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -24,9 +24,11 @@ for what in "$@"; do
           python bench.py --steps 2 --warmup 3 --skip-cpu --skip-box > $OUT/launches_$tag.log 2>&1
       ;;
     conv)
-      ncu --set full --clock-control none --import-source on -k regex:"conv_|gemm_|depthwise" -s 138 -c 69 \
-          -o $OUT/conv_$tag python bench.py --steps 1 --warmup 3 --skip-cpu --skip-box > $OUT/conv_$tag.log 2>&1
+      ncu --set full --clock-control none --import-source on --profile-from-start off \
+          -o $OUT/conv_$tag python bench.py --profile-one-step > $OUT/conv_$tag.log 2>&1
       ncu -i $OUT/conv_$tag.ncu-rep --page raw --csv > $OUT/conv_${tag}_raw.csv 2>/dev/null
+      python tools/ncu_summary.py $OUT/conv_${tag}_raw.csv > $OUT/conv_${tag}_summary.csv 2>&1
+      python tools/ncu_traffic.py $OUT/conv_${tag}_raw.csv $OUT/traffic_$tag.json > /dev/null 2>&1
       rm -f $OUT/conv_$tag.ncu-rep
       ;;
   esac
