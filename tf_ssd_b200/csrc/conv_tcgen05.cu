@@ -42,9 +42,9 @@ constexpr int TC_BK = 64;            // 64 fp16 = 128 B = one swizzle row
 constexpr int TC_STAGES = 4;
 constexpr int TC_EPI_WARPS = 8;      // two warps per TMEM lane quarter (they split the column chunks)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..9: epilogue
-constexpr int TC_CHUNK = 32;         // epilogue column chunk (fp16: 64 B per row)
-constexpr int TC_STAGE_PITCH = TC_CHUNK * 2 + 16;    // bytes per staged row: conflict-free 16-byte accesses
-constexpr int TC_STAGE_WARP = 32 * TC_STAGE_PITCH + TC_CHUNK * 4;   // per-warp staging: 32 rows + the chunk's bias
+constexpr int TC_CHUNK = 32;         // epilogue column chunk per warp (fp16: 64 B per row)
+constexpr int TC_OUT_TILE = TC_BM * 128;             // one output staging tile: 128 rows x 64 fp16 channels, 128B-swizzled
+constexpr int TC_OUT_BYTES = 2 * TC_OUT_TILE + TC_EPI_WARPS * TC_CHUNK * 4;   // two tiles (double buffer) + per-warp bias rows
 
 struct TcParams {
     int mode4d;                      // 0: A is a 2-D [M, K] matrix (1x1 conv); 1: 4-D im2col boxes
@@ -68,6 +68,7 @@ struct TcParams {
     long long img0, pix0, img1, pix1;
     float* partial;                  // split-K workspace [splits][tiles_m*128][ldp] or nullptr
     int splits, ldp;
+    int tma_store;                   // fp16 single-segment output written with TMA stores (map_o is valid)
 };
 
 // ------------------------------------------------------------------ PTX glue --
@@ -125,6 +126,32 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// TMA stores (shared -> global, bulk async-group completion); out-of-bounds parts of the box are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory"); }
+
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == SSD_ACT_RELU) return fmaxf(v, 0.0f);
     if (act == SSD_ACT_RELU6) return fminf(fmaxf(v, 0.0f), 6.0f);
@@ -172,7 +199,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const TcParams p) {
+                    const __grid_constant__ CUtensorMap map_o, const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 1024-byte alignment for the 128-byte swizzle atoms
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -180,8 +207,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const uint32_t b_stage = (uint32_t)p.BN * TC_BK * 2;
     unsigned char* sA = smem;
     unsigned char* sB = smem + TC_STAGES * a_stage;
-    unsigned char* sStage = sB + TC_STAGES * b_stage;            // [TC_EPI_WARPS][32][TC_STAGE_PITCH]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + TC_EPI_WARPS * TC_STAGE_WARP);
+    unsigned char* sOut = sB + TC_STAGES * b_stage;              // [2][128 rows][128 B] swizzled output tiles (1024-aligned)
+    float* sBias = reinterpret_cast<float*>(sOut + 2 * TC_OUT_TILE);     // [TC_EPI_WARPS][TC_CHUNK]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + TC_OUT_BYTES);
     // bars: full[S] | empty[S] | tmem_full[2] | tmem_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
 
@@ -193,6 +221,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
+        if (p.tma_store) tma_prefetch_desc(&map_o);
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);                      // one arrive.expect_tx (+ TMA bytes)
             mbar_init(bar_empty + 8 * s, 1);                     // one tcgen05.commit
@@ -275,15 +304,14 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // ===================== epilogue: 8 warps, two per TMEM lane quarter =====================
         const int ew = warp - 2;
         const int q = warp & 3;                                  // tcgen05.ld: warp w may touch lanes 32*(w%4)..+31
-        const int half = ew >> 2;                                // which half of the column chunks this warp takes
+        const int half = ew >> 2;                                // which 32-column half of a 64-column group this warp takes
         const int r = q * 32 + lane;
-        unsigned char* stage = sStage + (size_t)ew * TC_STAGE_WARP;
-        const bool fast16 = !p.partial && !p.out_f32 && p.split >= p.Cout && (p.Cout & 7) == 0 && (p.pix0 & 7) == 0 &&
-                            (p.img0 & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.out0) & 15) == 0) &&
-                            (p.res == nullptr || (reinterpret_cast<uintptr_t>(p.res) & 15) == 0);
+        const bool elected = ew == 0 && lane == 0;               // issues / retires the TMA stores of this CTA
+        float* sbias = sBias + ew * TC_CHUNK;
         const float act_lo = p.act == SSD_ACT_NONE ? -__int_as_float(0x7f800000) : 0.0f;
         const float act_hi = p.act == SSD_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
         int j = 0;
+        uint32_t n_groups = 0;                                   // output groups staged so far (selects the buffer)
         for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++j) {
             const int z = t / tiles_mn, tm_ = (t - z * tiles_mn) / p.tiles_n, tn = t - z * tiles_mn - tm_ * p.tiles_n;
             const int n0 = tn * p.BN;
@@ -292,78 +320,92 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             int b = 0, pix = 0;
             const bool row_ok = tc_row_to_pixel(p, tm_, r, b, pix);
-            const unsigned ok_mask = __ballot_sync(0xffffffffu, row_ok);
             const long long row_off = (long long)b * p.img0 + (long long)pix * p.pix0;     // element offset of the row (segment 0)
             const uint32_t trow = tmem_base + (uint32_t)a * p.acc_cols + ((uint32_t)(q * 32) << 16);
-            for (int c0 = half * TC_CHUNK; c0 < p.BN; c0 += 2 * TC_CHUNK) {
-                if (n0 + c0 >= p.Cout) break;                    // warp-uniform
-                uint32_t acc[TC_CHUNK];
-                tmem_ld16(trow + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));      // all lanes (sync.aligned)
-                if (c0 + 16 < p.BN) tmem_ld16(trow + (uint32_t)c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
-                const int ncols = min(min(TC_CHUNK, p.BN - c0), p.Cout - (n0 + c0));    // valid columns of this chunk
-                if (p.partial) {
-                    if (row_ok) {
-                        float* dst = p.partial + ((size_t)z * p.tiles_m * TC_BM + (size_t)tm_ * TC_BM + r) * p.ldp + n0 + c0;
+            if (p.tma_store) {
+                // ---- fp16 output through shared memory + TMA: 64-channel groups, double-buffered staging tile.
+                // Thread r owns tile row r; its 32 channels (64 B) go to 16-byte chunks (half*4 + h) ^ (r & 7) of
+                // the row's 128 bytes -- the SWIZZLE_128B layout of map_o, conflict-free for the warp.
+                int ox0 = 0, oy0 = 0, b0 = 0;
+                if (p.mode4d) {
+                    const int per_img = p.tiles_w * p.tiles_h;
+                    const int tb = tm_ / per_img, tr = tm_ - tb * per_img;
+                    const int th = tr / p.tiles_w, tw = tr - th * p.tiles_w;
+                    b0 = tb * p.bb; oy0 = th * p.bh; ox0 = tw * p.bw;
+                }
+                for (int g0 = 0; g0 < p.BN && n0 + g0 < p.Cout; g0 += 64, ++n_groups) {
+                    unsigned char* buf = sOut + (n_groups & 1u) * TC_OUT_TILE;
+                    if (elected) bulk_wait_read<1>();            // the store that last read this buffer has drained it
+                    epi_barrier();
+                    const int c0 = g0 + half * TC_CHUNK;
+                    if (c0 < p.BN && n0 + c0 < p.Cout) {         // warp-uniform
+                        const int n = n0 + c0;
+                        const int ncols = min(TC_CHUNK, p.Cout - n);
+                        uint32_t acc[TC_CHUNK];
+                        tmem_ld32(trow + (uint32_t)c0, acc);
+                        sbias[lane] = (p.bias && lane < ncols) ? __ldg(p.bias + n + lane) : 0.0f;
+                        __syncwarp();
 #pragma unroll
-                        for (int jj = 0; jj < TC_CHUNK; jj += 4)
-                            if (jj < p.BN - c0)
-                                *reinterpret_cast<float4*>(dst + jj) = make_float4(__uint_as_float(acc[jj]), __uint_as_float(acc[jj + 1]),
-                                                                                   __uint_as_float(acc[jj + 2]), __uint_as_float(acc[jj + 3]));
-                    }
-                } else if (fast16) {
-                    const int n = n0 + c0;
-                    // 0. this chunk's 32 bias values -> the warp's private smem row (one coalesced load)
-                    float* sbias = reinterpret_cast<float*>(stage + 32 * TC_STAGE_PITCH);
-                    sbias[lane] = (p.bias && lane < ncols) ? __ldg(p.bias + n + lane) : 0.0f;
-                    __syncwarp();
-                    // 1. per-row math in registers (this thread owns tile row r, 32 channels); the
-                    //    activation is a branch-free clamp to [act_lo, act_hi]
+                        for (int h = 0; h < TC_CHUNK / 8; ++h) {
+                            const float4 b0v = *reinterpret_cast<const float4*>(sbias + h * 8);
+                            const float4 b1v = *reinterpret_cast<const float4*>(sbias + h * 8 + 4);
+                            const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
+                            float v[8];
 #pragma unroll
-                    for (int h = 0; h < TC_CHUNK / 8; ++h) {
-                        const float4 b0 = *reinterpret_cast<const float4*>(sbias + h * 8);
-                        const float4 b1 = *reinterpret_cast<const float4*>(sbias + h * 8 + 4);
-                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                        float v[8];
+                            for (int e = 0; e < 8; ++e)
+                                v[e] = fminf(fmaxf(__uint_as_float(acc[h * 8 + e]) + bb[e], act_lo), act_hi);
+                            if (p.res && row_ok && h * 8 < ncols) {
+                                const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + row_off + n + h * 8));
+                                const __half2* rh = reinterpret_cast<const __half2*>(&rr);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            v[e] = fminf(fmaxf(__uint_as_float(acc[h * 8 + e]) + bb[e], act_lo), act_hi);
-                        if (p.res && row_ok && h * 8 < ncols) {
-                            const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + row_off + n + h * 8));
-                            const __half2* rh = reinterpret_cast<const __half2*>(&rr);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 f = __half22float2(rh[e]);
-                                v[2 * e] += f.x; v[2 * e + 1] += f.y;
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 f = __half22float2(rh[e]);
+                                    v[2 * e] += f.x; v[2 * e + 1] += f.y;
+                                }
                             }
+                            uint4 o;
+                            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                            *reinterpret_cast<uint4*>(buf + r * 128 + (((half * 4 + h) ^ (r & 7)) << 4)) = o;
                         }
-                        uint4 o;
-                        __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-                        *reinterpret_cast<uint4*>(stage + lane * TC_STAGE_PITCH + h * 16) = o;
+                        __syncwarp();                            // sbias is rewritten by the next group
                     }
-                    __syncwarp();
-                    // 2. coalesced write-out: 32 rows x 4 pieces of 16 B; 4 consecutive lanes cover one row's 64 B
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    epi_barrier();
+                    if (elected) {
+                        if (p.mode4d) tma_store_4d(&map_o, smem_addr(buf), n0 + g0, ox0, oy0, b0);
+                        else          tma_store_2d(&map_o, smem_addr(buf), n0 + g0, tm_ * TC_BM);
+                        bulk_commit();
+                    }
+                }
+            } else {
+                for (int c0 = half * TC_CHUNK; c0 < p.BN; c0 += 2 * TC_CHUNK) {
+                    if (n0 + c0 >= p.Cout) break;                // warp-uniform
+                    uint32_t acc[TC_CHUNK];
+                    tmem_ld32(trow + (uint32_t)c0, acc);
+                    const int ncols = min(min(TC_CHUNK, p.BN - c0), p.Cout - (n0 + c0));    // valid columns of this chunk
+                    if (p.partial) {
+                        if (row_ok) {
+                            float* dst = p.partial + ((size_t)z * p.tiles_m * TC_BM + (size_t)tm_ * TC_BM + r) * p.ldp + n0 + c0;
 #pragma unroll
-                    for (int itw = 0; itw < (32 * (TC_CHUNK / 8)) / 32; ++itw) {
-                        const int idx = itw * 32 + lane, rr_ = idx >> 2, piece = idx & 3;
-                        const long long off = __shfl_sync(0xffffffffu, row_off, rr_);
-                        if (((ok_mask >> rr_) & 1u) && piece * 8 < ncols) {
-                            const uint4 o = *reinterpret_cast<const uint4*>(stage + rr_ * TC_STAGE_PITCH + piece * 16);
-                            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out0) + off + n + piece * 8) = o;
+                            for (int jj = 0; jj < TC_CHUNK; jj += 4)
+                                if (jj < p.BN - c0)
+                                    *reinterpret_cast<float4*>(dst + jj) = make_float4(__uint_as_float(acc[jj]), __uint_as_float(acc[jj + 1]),
+                                                                                       __uint_as_float(acc[jj + 2]), __uint_as_float(acc[jj + 3]));
                         }
-                    }
-                    __syncwarp();
-                } else if (row_ok) {
+                    } else if (row_ok) {
 #pragma unroll
-                    for (int jj = 0; jj < TC_CHUNK; ++jj)
-                        if (jj < ncols) tc_store_one(p, b, pix, n0 + c0 + jj, __uint_as_float(acc[jj]));
+                        for (int jj = 0; jj < TC_CHUNK; ++jj)
+                            if (jj < ncols) tc_store_one(p, b, pix, n0 + c0 + jj, __uint_as_float(acc[jj]));
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * a);      // this warp is done reading accumulator a
         }
+        if (elected) bulk_wait_all();                            // staged tiles must outlive their stores
     }
     __syncthreads();
     if (warp == 1) {
@@ -563,8 +605,31 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
     }
 
     p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.n_tiles = tiles_m * tiles_n * splits;
+
+    // fp16 single-segment outputs leave through TMA stores (64-channel boxes of the NHWC output)
+    CUtensorMap map_o;
+    memset(&map_o, 0, sizeof(map_o));
+    p.tma_store = 0;
+    if (splits == 1 && !d->out_f32 && d->split >= d->Cout && (d->Cout & 7) == 0 && (p.pix0 & 7) == 0 && (p.img0 & 7) == 0 &&
+        (reinterpret_cast<uintptr_t>(d->out0) & 15) == 0 && (d->residual == nullptr || (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0) &&
+        (p.mode4d || p.img0 == (long long)p.HoWo * p.pix0)) {
+        int rc;
+        if (p.mode4d) {
+            uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->B};
+            uint64_t str[3] = {(uint64_t)p.pix0 * 2, (uint64_t)d->Wo * p.pix0 * 2, (uint64_t)p.img0 * 2};
+            uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bb};
+            rc = cached_map(&map_o, d->out0, 4, dims, str, box);
+        } else {
+            uint64_t dims[2] = {(uint64_t)d->Cout, (uint64_t)p.M};
+            uint64_t str[1] = {(uint64_t)p.pix0 * 2};
+            uint32_t box[2] = {64, TC_BM};
+            rc = cached_map(&map_o, d->out0, 2, dims, str, box);
+        }
+        if (rc) return rc;
+        p.tma_store = 1;
+    }
     const size_t smem = (size_t)TC_STAGES * (TC_BM * TC_BK * 2 + (size_t)p.BN * TC_BK * 2) +
-                        (size_t)TC_EPI_WARPS * TC_STAGE_WARP + (2 * TC_STAGES + 4) * 8 + 16 + 1024;
+                        (size_t)TC_OUT_BYTES + (2 * TC_STAGES + 4) * 8 + 16 + 1024;
     static thread_local int attr_dev = -1;                       // opt-in once per (thread, device): maximum footprint
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
@@ -576,7 +641,7 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
     // persistent: one CTA per SM (512 TMEM columns and ~100-215 KB of shared memory per CTA)
     dim3 grid(min(p.n_tiles, sms), 1, 1);
     {
-        cudaError_t le = launch_pdl(conv_tcgen05_kernel, grid, dim3(TC_THREADS), smem, st, map_a, map_b, p);
+        cudaError_t le = launch_pdl(conv_tcgen05_kernel, grid, dim3(TC_THREADS), smem, st, map_a, map_b, map_o, p);
         if (le != cudaSuccess) return cuda_fail(le, "conv_tcgen05_kernel");
     }
     if (splits > 1) {

@@ -6,6 +6,7 @@ export SSD_B200_PDL=0
 tag=$1; shift
 OUT=gpurun_out
 mkdir -p $OUT
+trap 'rm -f $OUT/*.ncu-rep' EXIT          # reports are far beyond what gpurun copies back: only the CSV summaries travel
 METRICS='gpu__time_duration.sum|dram__bytes_read.sum |dram__bytes_write.sum |dram__throughput.avg.pct_of_peak_sustained_elapsed|sm__throughput.avg.pct_of_peak_sustained_elapsed|sm__warps_active.avg.pct_of_peak_sustained_active|launch__registers_per_thread|launch__grid_size|launch__block_size|sm__pipe_tensor_cycles_active|sm__inst_executed_pipe_tensor|smsp__cycles_active.avg|l1tex__t_bytes|lts__t_bytes.sum |launch__occupancy_limit|smsp__average_warp.*_per_issue_active|sm__pipe_tensor_op_hmma_cycles_active'
 for what in "$@"; do
   case $what in
@@ -24,7 +25,7 @@ for what in "$@"; do
           python bench.py --steps 2 --warmup 3 --skip-cpu --skip-box > $OUT/launches_$tag.log 2>&1
       ;;
     conv)
-      ncu --set full --clock-control none --import-source on --profile-from-start off \
+      ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"conv_tcgen05_kernel|conv_igemm|splitk" \
           -o $OUT/conv_$tag python bench.py --profile-one-step > $OUT/conv_$tag.log 2>&1
       ncu -i $OUT/conv_$tag.ncu-rep --page raw --csv > $OUT/conv_${tag}_raw.csv 2>/dev/null
       python tools/ncu_summary.py $OUT/conv_${tag}_raw.csv > $OUT/conv_${tag}_summary.csv 2>&1
