@@ -536,9 +536,11 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
 
     // N tile: the largest multiple of 16 (<= 256) that tiles Cout evenly; whole Cout when it fits one UMMA
     const int cout16 = (d->Cout + 15) / 16 * 16;
+    // (with several N tiles the tile width is a multiple of 64: the TMA-store boxes are 64 channels wide and must
+    // not reach into the neighbouring N tile; a ragged last tile is clipped by the tensor bounds)
     p.BN = 128;
     if (cout16 <= 256) p.BN = cout16;
-    else for (int bn = 256; bn >= 96; bn -= 16) if (cout16 % bn == 0) { p.BN = bn; break; }
+    else for (int bn = 256; bn >= 128; bn -= 64) if (cout16 % bn == 0) { p.BN = bn; break; }
     const int tiles_n = (d->Cout + p.BN - 1) / p.BN;
     p.acc_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
     p.tmem_cols = 2 * p.acc_cols;                                  // double-buffered accumulator (<= 512 columns)
