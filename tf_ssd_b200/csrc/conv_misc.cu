@@ -38,14 +38,17 @@ depthwise3x3_kernel(const uint4* __restrict__ in, const uint4* __restrict__ w, c
     constexpr int COLS = (PX - 1) * STRIDE + 3;
     pdl_trigger();
     pdl_wait();
+    // grid = (chunks of one output row's (pixel group, channel group) items, Ho, B): one 32-bit division per
+    // thread instead of the 64-bit div/mod chain of a flat index (that chain cost more issue slots than the
+    // convolution itself)
     const int wgroups = (Wo + PX - 1) / PX;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-         t += (int64_t)gridDim.x * blockDim.x) {
-        int c8 = (int)(t % C8);
-        int64_t r = t / C8;
-        int xg = (int)(r % wgroups); r /= wgroups;
-        int oy = (int)(r % Ho);
-        int b = (int)(r / Ho);
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    (void)total;
+    if (item < wgroups * C8) {
+        const int xg = item / C8;
+        const int c8 = item - xg * C8;
+        const int oy = blockIdx.y;
+        const int b = blockIdx.z;
         const int ox0 = xg * PX;
 
         float acc[PX][8];
@@ -64,21 +67,35 @@ depthwise3x3_kernel(const uint4* __restrict__ in, const uint4* __restrict__ w, c
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc[p][k] = bv[k];
 
+        // All input vectors of the 3 x COLS window are requested before the first one is consumed (predicated
+        // loads, zero for padding): 12 (stride 1) / 15 (stride 2) independent 16-byte loads in flight per thread --
+        // this kernel is bound by memory latency x bytes in flight, not by arithmetic.
         const uint4* img = in + (size_t)b * H * W * C8;
+        uint4 xin[3][COLS];
+        uint4 wv[3][3];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int iy = oy * STRIDE - pad_t + ky;
-            if ((unsigned)iy >= (unsigned)H) continue;
-            float wk[3][8];
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) h8_to_f(__ldg(w + (size_t)(ky * 3 + kx) * C8 + c8), wk[kx]);
-            const uint4* row = img + (size_t)iy * W * C8 + c8;
+            const bool vy = (unsigned)iy < (unsigned)H;
+            const uint4* row = img + (size_t)(vy ? iy : 0) * W * C8 + c8;
 #pragma unroll
             for (int cx = 0; cx < COLS; ++cx) {
                 const int ix = ox0 * STRIDE - pad_l + cx;
-                if ((unsigned)ix >= (unsigned)W) continue;
+                const bool v = vy && (unsigned)ix < (unsigned)W;
+                xin[ky][cx] = v ? __ldg(row + (size_t)ix * C8) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) wv[ky][kx] = __ldg(w + (size_t)(ky * 3 + kx) * C8 + c8);
+        }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            float wk[3][8];
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) h8_to_f(wv[ky][kx], wk[kx]);
+#pragma unroll
+            for (int cx = 0; cx < COLS; ++cx) {
                 float x[8];
-                h8_to_f(__ldg(row + (size_t)ix * C8), x);
+                h8_to_f(xin[ky][cx], x);
 #pragma unroll
                 for (int p = 0; p < PX; ++p) {
                     const int kx = cx - p * STRIDE;
@@ -264,8 +281,10 @@ extern "C" int ssd_depthwise3x3(const void* d_in, const void* d_weight, const fl
     const int C8 = C / 8;
     constexpr int PX = 2;
     const int64_t total = (int64_t)B * Ho * ((Wo + PX - 1) / PX) * C8;
+    SSD_REQUIRE(Ho <= 65535 && B <= 65535, SSD_ERR_SHAPE, "ssd_depthwise3x3: Ho=%d / B=%d exceed the grid limits", Ho, B);
+    const int row_items = ((Wo + PX - 1) / PX) * C8;
     auto args = [&](auto kern) {
-        return launch_pdl(kern, dim3(grid_for(total, 16)), dim3(256), 0, as_stream(stream),
+        return launch_pdl(kern, dim3((row_items + 255) / 256, Ho, B), dim3(256), 0, as_stream(stream),
                           reinterpret_cast<const uint4*>(d_in), reinterpret_cast<const uint4*>(d_weight), d_bias,
                           reinterpret_cast<uint4*>(d_out), H, W, C8, Ho, Wo, pad_top, pad_left, act, total);
     };

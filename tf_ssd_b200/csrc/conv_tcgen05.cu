@@ -44,7 +44,7 @@ constexpr int TC_EPI_WARPS = 8;      // two warps per TMEM lane quarter (they sp
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..9: epilogue
 constexpr int TC_CHUNK = 32;         // epilogue column chunk per warp (fp16: 64 B per row)
 constexpr int TC_OUT_TILE = TC_BM * 128;             // one output staging tile: 128 rows x 64 fp16 channels, 128B-swizzled
-constexpr int TC_OUT_BYTES = 2 * TC_OUT_TILE + TC_EPI_WARPS * TC_CHUNK * 4;   // two tiles (double buffer) + per-warp bias rows
+constexpr int TC_OUT_BYTES = 2 * TC_OUT_TILE + 256 * 4;   // two tiles (double buffer) + the N tile's bias values
 
 struct TcParams {
     int mode4d;                      // 0: A is a 2-D [M, K] matrix (1x1 conv); 1: 4-D im2col boxes
@@ -69,6 +69,7 @@ struct TcParams {
     float* partial;                  // split-K workspace [splits][tiles_m*128][ldp] or nullptr
     int splits, ldp;
     int tma_store;                   // fp16 single-segment output written with TMA stores (map_o is valid)
+    int stages;                      // operand ring depth (2..TC_STAGES): shallow-K layers trade depth for 2 CTAs per SM
 };
 
 // ------------------------------------------------------------------ PTX glue --
@@ -135,7 +136,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
                    "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// The loaded registers are operands of the wait so that no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
 }
 // TMA stores (shared -> global, bulk async-group completion); out-of-bounds parts of the box are clipped
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
@@ -197,7 +206,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)     // <= 102 registers: two CTAs may share an SM (shallow-K layers)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_o, const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -206,9 +215,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const uint32_t a_stage = TC_BM * TC_BK * 2;                 // 16 KB
     const uint32_t b_stage = (uint32_t)p.BN * TC_BK * 2;
     unsigned char* sA = smem;
-    unsigned char* sB = smem + TC_STAGES * a_stage;
-    unsigned char* sOut = sB + TC_STAGES * b_stage;              // [2][128 rows][128 B] swizzled output tiles (1024-aligned)
-    float* sBias = reinterpret_cast<float*>(sOut + 2 * TC_OUT_TILE);     // [TC_EPI_WARPS][TC_CHUNK]
+    unsigned char* sB = smem + p.stages * a_stage;
+    unsigned char* sOut = sB + p.stages * b_stage;               // [2][128 rows][128 B] swizzled output tiles (1024-aligned)
+    float* sBias = reinterpret_cast<float*>(sOut + 2 * TC_OUT_TILE);     // [256]: bias of the current N tile
     uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + TC_OUT_BYTES);
     // bars: full[S] | empty[S] | tmem_full[2] | tmem_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
@@ -247,7 +256,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 0) {
         // ===================== TMA producer (one elected lane) =====================
         if (lane == 0) {
-            int it = 0;                                          // k-block counter across all tiles of this CTA
+            int it = 0, s = 0;                                   // k-block counter across all tiles of this CTA, ring slot
+            uint32_t ph = 0;                                     // parity of the ring's wrap count
             for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
                 const int z = t / tiles_mn, tm_ = (t - z * tiles_mn) / p.tiles_n, tn = t - z * tiles_mn - tm_ * p.tiles_n;
                 const int kb0 = z * p.kb_per_split, kb1 = min(p.n_kblocks, kb0 + p.kb_per_split);
@@ -259,8 +269,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     b0 = tb * p.bb; oy0 = th * p.bh; ox0 = tw * p.bw;
                 }
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % TC_STAGES;
-                    if (it >= TC_STAGES) mbar_wait(bar_empty + 8 * s, ((it / TC_STAGES) - 1) & 1);
+                    if (it >= p.stages) mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                     const int tap = kb / p.kb_per_tap, c0 = (kb - tap * p.kb_per_tap) * TC_BK;
                     mbar_expect_tx(bar_full + 8 * s, p.a_bytes + p.b_bytes);
                     const uint32_t dst_a = smem_addr(sA + (size_t)s * a_stage), dst_b = smem_addr(sB + (size_t)s * b_stage);
@@ -272,13 +281,15 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         tma_load_2d(dst_a, &map_a, bar_full + 8 * s, c0, tm_ * TC_BM);
                     }
                     tma_load_2d(dst_b, &map_b, bar_full + 8 * s, tap * p.Cin + c0, tn * p.BN);
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one elected lane) =====================
         if (lane == 0) {
-            int it = 0, j = 0;
+            int j = 0, s = 0;
+            uint32_t ph = 0;
             for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++j) {
                 const int z = t / tiles_mn;
                 const int kb0 = z * p.kb_per_split, kb1 = min(p.n_kblocks, kb0 + p.kb_per_split);
@@ -286,9 +297,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 if (j >= 2) mbar_wait(bar_tempty + 8 * a, ((j >> 1) - 1) & 1);      // epilogue drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tacc = tmem_base + (uint32_t)a * p.acc_cols;
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % TC_STAGES;
-                    mbar_wait(bar_full + 8 * s, (it / TC_STAGES) & 1);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(bar_full + 8 * s, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint64_t da = umma_desc_sw128(smem_addr(sA + (size_t)s * a_stage));
                     const uint64_t db = umma_desc_sw128(smem_addr(sB + (size_t)s * b_stage));
@@ -296,6 +306,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     for (int k = 0; k < TC_BK / 16; ++k)         // UMMA_K = 16: +32 bytes along K inside the swizzle row
                         umma_f16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (kb > kb0) || k > 0);
                     umma_commit(bar_empty + 8 * s);              // frees the stage when these MMAs retire
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
                 umma_commit(bar_tfull + 8 * a);                  // accumulator complete
             }
@@ -307,7 +318,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int half = ew >> 2;                                // which 32-column half of a 64-column group this warp takes
         const int r = q * 32 + lane;
         const bool elected = ew == 0 && lane == 0;               // issues / retires the TMA stores of this CTA
-        float* sbias = sBias + ew * TC_CHUNK;
+        int bias_tn = -1;                                        // N tile whose bias sits in sBias
         const float act_lo = p.act == SSD_ACT_NONE ? -__int_as_float(0x7f800000) : 0.0f;
         const float act_hi = p.act == SSD_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
         int j = 0;
@@ -333,18 +344,24 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const int th = tr / p.tiles_w, tw = tr - th * p.tiles_w;
                     b0 = tb * p.bb; oy0 = th * p.bh; ox0 = tw * p.bw;
                 }
+                if (bias_tn != tn) {                             // (re)load this N tile's bias: visible after the next barrier;
+                    const int i = ew * 32 + lane;                // the previous tile's readers are all past their last barrier
+                    sBias[i] = (p.bias && i < p.BN && n0 + i < p.Cout) ? __ldg(p.bias + n0 + i) : 0.0f;
+                    bias_tn = tn;
+                }
                 for (int g0 = 0; g0 < p.BN && n0 + g0 < p.Cout; g0 += 64, ++n_groups) {
                     unsigned char* buf = sOut + (n_groups & 1u) * TC_OUT_TILE;
+                    const int c0 = g0 + half * TC_CHUNK;
+                    const bool mine = c0 < p.BN && n0 + c0 < p.Cout;   // warp-uniform
+                    uint32_t acc[TC_CHUNK];
+                    if (mine) tmem_ld32(trow + (uint32_t)c0, acc);     // in flight across the buffer hand-over below
                     if (elected) bulk_wait_read<1>();            // the store that last read this buffer has drained it
                     epi_barrier();
-                    const int c0 = g0 + half * TC_CHUNK;
-                    if (c0 < p.BN && n0 + c0 < p.Cout) {         // warp-uniform
+                    if (mine) {
                         const int n = n0 + c0;
                         const int ncols = min(TC_CHUNK, p.Cout - n);
-                        uint32_t acc[TC_CHUNK];
-                        tmem_ld32(trow + (uint32_t)c0, acc);
-                        sbias[lane] = (p.bias && lane < ncols) ? __ldg(p.bias + n + lane) : 0.0f;
-                        __syncwarp();
+                        const float* sbias = sBias + c0;
+                        tmem_ld_wait(acc);
 #pragma unroll
                         for (int h = 0; h < TC_CHUNK / 8; ++h) {
                             const float4 b0v = *reinterpret_cast<const float4*>(sbias + h * 8);
@@ -369,7 +386,6 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                             for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
                             *reinterpret_cast<uint4*>(buf + r * 128 + (((half * 4 + h) ^ (r & 7)) << 4)) = o;
                         }
-                        __syncwarp();                            // sbias is rewritten by the next group
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     epi_barrier();
@@ -384,6 +400,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     if (n0 + c0 >= p.Cout) break;                // warp-uniform
                     uint32_t acc[TC_CHUNK];
                     tmem_ld32(trow + (uint32_t)c0, acc);
+                    tmem_ld_wait(acc);
                     const int ncols = min(min(TC_CHUNK, p.BN - c0), p.Cout - (n0 + c0));    // valid columns of this chunk
                     if (p.partial) {
                         if (row_ok) {
@@ -630,8 +647,22 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
         if (rc) return rc;
         p.tma_store = 1;
     }
-    const size_t smem = (size_t)TC_STAGES * (TC_BM * TC_BK * 2 + (size_t)p.BN * TC_BK * 2) +
-                        (size_t)TC_OUT_BYTES + (2 * TC_STAGES + 4) * 8 + 16 + 1024;
+    // Operand ring depth and CTAs per SM.  A tile with few k-blocks (1x1 convolutions with Cin <= 128: every MobileNetV2
+    // expand layer up to block 13) cannot use a deep ring; its persistent loop is bound by the latency of the epilogue's
+    // dependent instruction chain, so a shallower ring that lets TWO CTAs share an SM (shared memory <= 113 KB and
+    // TMEM <= 256 columns each) doubles the warps that hide that latency.
+    auto smem_for = [&](int stages) {
+        return (size_t)stages * (TC_BM * TC_BK * 2 + (size_t)p.BN * TC_BK * 2) + (size_t)TC_OUT_BYTES +
+               (2 * TC_STAGES + 4) * 8 + 16 + 1024;
+    };
+    p.stages = min(TC_STAGES, max(2, p.kb_per_split));
+    int ctas_per_sm = 1;
+    if (p.n_tiles > sms && 2 * p.tmem_cols <= 512) {
+        const int floor_stages = p.kb_per_split <= 2 ? 2 : 3;
+        for (int st_ = p.stages; st_ >= floor_stages; --st_)
+            if (2 * (smem_for(st_) + 1024) <= (size_t)227 * 1024) { p.stages = st_; ctas_per_sm = 2; break; }
+    }
+    const size_t smem = smem_for(p.stages);
     static thread_local int attr_dev = -1;                       // opt-in once per (thread, device): maximum footprint
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
@@ -641,7 +672,7 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
         attr_dev = cur_dev;
     }
     // persistent: one CTA per SM (512 TMEM columns and ~100-215 KB of shared memory per CTA)
-    dim3 grid(min(p.n_tiles, sms), 1, 1);
+    dim3 grid(min(p.n_tiles, sms * ctas_per_sm), 1, 1);
     {
         cudaError_t le = launch_pdl(conv_tcgen05_kernel, grid, dim3(TC_THREADS), smem, st, map_a, map_b, map_o, p);
         if (le != cudaSuccess) return cuda_fail(le, "conv_tcgen05_kernel");
