@@ -1,0 +1,130 @@
+"""dataset / io helpers (CPU), GPU evaluation (mAP) and the trainer.py / predictor.py flows."""
+
+import os
+
+import numpy as np
+import pytest
+
+from oracle import box_oracle as bo
+
+
+def test_data_utils_contract():
+    from tf_ssd_b200.utils import data_utils
+    ds, info = data_utils.get_dataset("voc/2007", "test", total_items=10)
+    assert data_utils.get_total_item_size(info, "test") == 10 and len(data_utils.get_labels(info)) == 20
+    batches = list(ds.padded_batch(4, padded_shapes=data_utils.get_data_shapes(), padding_values=data_utils.get_padding_values()))
+    assert [b[0].shape[0] for b in batches] == [4, 4, 2]
+    img, gb, gl = batches[0]
+    assert img.dtype == np.float32 and img.shape[1:] == (300, 300, 3) and 0.0 <= img.min() and img.max() <= 1.0
+    assert gb.shape[:2] == gl.shape and gb.shape[2] == 4 and gl.dtype == np.int32
+    pad = gl == -1
+    assert pad.any() and not gb[pad].any()                               # padded boxes are zero, labels -1
+    assert ((gl[~pad] >= 1) & (gl[~pad] <= 20)).all()                    # labels shifted by one: 0 is background
+    assert (gb[~pad][:, 2] > gb[~pad][:, 0]).all() and (gb[~pad][:, 3] > gb[~pad][:, 1]).all()
+    again = list(data_utils.get_dataset("voc/2007", "test", total_items=10)[0].padded_batch(4))
+    assert np.array_equal(again[0][1], gb)                               # seeded: the same stream every time
+    both = ds.concatenate(data_utils.get_dataset("voc/2012", "train+validation", total_items=3)[0])
+    assert sum(b[0].shape[0] for b in both.padded_batch(5)) == 13
+    assert len(list(ds.padded_batch(4, drop_remainder=True))) == 2
+    # the default split sizes are the TFDS ones the reference trains on (trainer.py:47-58)
+    assert data_utils.get_total_item_size(data_utils.get_dataset("voc/2007", "train+validation")[1], "train+validation") == 5011
+
+
+def test_io_utils_and_checkpoint(tmp_path):
+    from tf_ssd_b200.models.train_engine import ModelCheckpoint
+    from tf_ssd_b200.utils import io_utils
+    a = io_utils.handle_args(["--backbone", "vgg16", "-handle-gpu"])
+    assert a.backbone == "vgg16" and a.handle_gpu
+    assert io_utils.handle_args([]).backbone == "mobilenet_v2"
+    io_utils.is_valid_backbone("mobilenet_v2")
+    with pytest.raises(AssertionError):
+        io_utils.is_valid_backbone("resnet")
+    p = io_utils.get_model_path("vgg16", str(tmp_path / "trained"))
+    assert p.endswith("ssd_vgg16_model_weights.npz") and os.path.isdir(os.path.dirname(p))
+    assert io_utils.get_log_path("vgg16").startswith("logs/vgg16/")
+
+    class FakeModel(object):
+        saved = 0
+
+        def save_weights(self, path):
+            self.saved += 1
+    cb = ModelCheckpoint(p, monitor="val_loss", save_best_only=True)
+    m = FakeModel()
+    cb.set_model(m)
+    for epoch, v in enumerate([3.0, 2.0, 2.5, 1.0]):
+        cb.on_epoch_end(epoch, {"val_loss": v})
+    assert m.saved == 3 and cb.saved_epochs == [0, 1, 3] and cb.best == 1.0
+
+
+def test_average_precision_arithmetic():
+    from tf_ssd_b200.utils import eval_utils
+    stats = eval_utils.init_stats(["bg", "a", "b"])
+    assert sorted(stats) == [1, 2]
+    stats[1].update(total=2, tp=[1, 0, 1], fp=[0, 1, 0], scores=[0.9, 0.8, 0.7])
+    stats[2].update(total=1, tp=[0], fp=[1], scores=[0.6])
+    stats, m_ap = eval_utils.calculate_mAP(stats)
+    # class 1: precision [1, .5, 2/3], recall [.5, .5, 1] -> 11-point AP = (6*1 + 5*(2/3))/11
+    assert stats[1]["AP"] == pytest.approx((6 + 5 * 2 / 3) / 11)
+    assert stats[2]["AP"] == 0.0 and m_ap == pytest.approx(stats[1]["AP"] / 2)
+
+
+def _update_stats_reference(pb, pl, ps, gb, gl, stats):
+    """utils/eval_utils.py:36-91 restated with the oracle's IoU map."""
+    iou = bo.iou_map(pb, gb)
+    merged, gt_of = iou.max(-1), iou.argmax(-1)
+    order = np.argsort(-merged, axis=-1, kind="stable")
+    for lab in gl.reshape(-1):
+        if lab != -1:
+            stats[int(lab)]["total"] += 1
+    for b in range(pb.shape[0]):
+        taken = []
+        for m in order[b]:
+            if pl[b, m] == 0:
+                continue
+            lab, g = int(pl[b, m]), int(gt_of[b, m])
+            stats[lab]["scores"].append(float(ps[b, m]))
+            ok = merged[b, m] >= 0.5 and lab == int(gl[b, g]) and g not in taken
+            stats[lab]["tp"].append(int(ok)); stats[lab]["fp"].append(int(not ok))
+            if ok:
+                taken.append(g)
+    return stats
+
+
+@pytest.mark.gpu
+def test_update_stats_matches_reference_loops():
+    from tf_ssd_b200 import synth
+    from tf_ssd_b200.utils import eval_utils
+    rng = np.random.default_rng(3)
+    B, M = 3, 40
+    gb, gl = synth.make_ground_truth(B, padded=6, max_boxes=5, seed=9)
+    pb = np.zeros((B, M, 4), np.float32); pl = np.zeros((B, M), np.float32); ps = np.zeros((B, M), np.float32)
+    for b in range(B):
+        n = int((gl[b] > 0).sum())
+        for m in range(30):                                               # jittered copies of the ground truth + noise
+            g = m % n
+            pb[b, m] = np.clip(gb[b, g] + rng.normal(0, 0.04, 4), 0, 1)
+            pl[b, m] = gl[b, g] if m % 3 else (gl[b, g] % 20) + 1
+            ps[b, m] = rng.random()
+    labels = ["bg"] + [str(i) for i in range(1, 21)]
+    got = eval_utils.update_stats(pb, pl, ps, gb, gl, eval_utils.init_stats(labels))
+    ref = _update_stats_reference(pb, pl, ps, gb, gl, eval_utils.init_stats(labels))
+    for k in ref:
+        assert got[k]["total"] == ref[k]["total"] and got[k]["tp"] == ref[k]["tp"] and got[k]["fp"] == ref[k]["fp"], k
+        assert np.allclose(got[k]["scores"], ref[k]["scores"])
+    assert sum(sum(v["tp"]) for v in ref.values()) > 0
+
+
+@pytest.mark.gpu
+def test_trainer_and_predictor_flows(tmp_path):
+    import predictor
+    import trainer
+    argv = ["--backbone", "mobilenet_v2", "--epochs", "2", "--batch-size", "8", "--train-items", "32", "--val-items", "16",
+            "--model-dir", str(tmp_path)]
+    hist = trainer.main(argv)
+    assert len(hist["loss"]) == 2 and np.isfinite(hist["loss"]).all() and np.isfinite(hist["val_loss"]).all()
+    path = os.path.join(str(tmp_path), "ssd_mobilenet_v2_model_weights.npz")
+    assert os.path.exists(path)
+    with np.load(path) as z:
+        assert "block_13_expand/kernel" in z.files and "bn_Conv1/moving_mean" in z.files and z["Conv1/kernel"].shape == (3, 3, 3, 32)
+    stats = predictor.main(argv)
+    assert sorted(stats) == list(range(1, 21)) and all("AP" in v for v in stats.values())

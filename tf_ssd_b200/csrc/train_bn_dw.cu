@@ -47,7 +47,7 @@ static ChunkGeom chunk_geom(int64_t M, int C) {
     g.C8 = C / 8;
     g.tpr = (kRedThreads / g.C8) * g.C8;
     g.total = M * g.C8;
-    int64_t want = (g.total + (int64_t)g.tpr * 8 - 1) / ((int64_t)g.tpr * 8);      // >= 8 elements per thread
+    int64_t want = (g.total + (int64_t)g.tpr * 16 - 1) / ((int64_t)g.tpr * 16);    // >= 16 elements per thread
     g.chunks = (int)(want < 1 ? 1 : want > kMaxChunks ? kMaxChunks : want);
     int64_t per = (g.total + g.chunks - 1) / g.chunks;
     g.per_chunk = (per + g.tpr - 1) / g.tpr * g.tpr;
@@ -110,7 +110,8 @@ __device__ __forceinline__ double warp_column_sum(const float* __restrict__ col,
 // moving_variance uses the unbiased batch variance).
 __global__ void __launch_bounds__(256)
 bn_stats_finalize_kernel(const float* __restrict__ partial, int chunks, int C, double inv_m, double bessel,
-                         float eps, float momentum, float* __restrict__ save,
+                         float eps, float momentum, const float* __restrict__ gamma, const float* __restrict__ beta,
+                         float* __restrict__ save, float* __restrict__ coef,
                          float* __restrict__ moving_mean, float* __restrict__ moving_var) {
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
@@ -120,54 +121,50 @@ bn_stats_finalize_kernel(const float* __restrict__ partial, int chunks, int C, d
     const double mean = s * inv_m;
     double var = ss * inv_m - mean * mean;
     if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
     save[c] = (float)mean;
-    save[C + c] = (float)(1.0 / sqrt(var + (double)eps));
+    save[C + c] = rstd;
+    const float a = gamma[c] * rstd;                  // y = a * x + b
+    coef[c] = a;
+    coef[C + c] = fmaf(-(float)mean, a, beta[c]);
     if (moving_mean) moving_mean[c] = moving_mean[c] * momentum + (float)mean * (1.0f - momentum);
     if (moving_var) moving_var[c] = moving_var[c] * momentum + (float)(var * bessel) * (1.0f - momentum);
 }
 
-// y = act(gamma * (x - mean) * rstd + beta) (+ res)
+// y = act(a * x + b) (+ res) with the per-channel affine of the finalize kernel.  The thread stride is a
+// multiple of C8, so a thread's channel group -- and its 16 coefficients -- never change.
 __global__ void __launch_bounds__(256)
-bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                const float* __restrict__ save, const uint4* __restrict__ res, uint4* __restrict__ y, int C8, int C,
-                int act, int64_t total) {
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int cg = (int)(e % C8);
-        float f[8], r[8];
-        h8_unpack(__ldg(x + e), f);
-        if (res) h8_unpack(__ldg(res + e), r);
+bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ coef, const uint4* __restrict__ res,
+                uint4* __restrict__ y, int C8, int C, int act, int64_t total, int64_t stride) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= stride) return;
+    const int cg = (int)(t % C8);
+    float a[8], b[8];
+    {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(coef) + cg * 2), a1 = __ldg(reinterpret_cast<const float4*>(coef) + cg * 2 + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(coef + C) + cg * 2), b1 = __ldg(reinterpret_cast<const float4*>(coef + C) + cg * 2 + 1);
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+    }
+    const float lo = act == SSD_ACT_NONE ? -__int_as_float(0x7f800000) : 0.0f;
+    const float hi = act == SSD_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
+    for (int64_t e = t; e < total; e += stride) {
+        float f[8];
+        h8_unpack(__ldcs(x + e), f);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int c = cg * 8 + k;
-            const float a = __ldg(gamma + c) * __ldg(save + C + c);
-            float v = fmaf(f[k] - __ldg(save + c), a, __ldg(beta + c));
-            if (act == SSD_ACT_RELU) v = fmaxf(v, 0.0f);
-            else if (act == SSD_ACT_RELU6) v = fminf(fmaxf(v, 0.0f), 6.0f);
-            if (res) v += r[k];
-            f[k] = v;
+        for (int k = 0; k < 8; ++k) f[k] = fminf(fmaxf(fmaf(f[k], a[k], b[k]), lo), hi);
+        if (res) {
+            float r[8];
+            h8_unpack(__ldg(res + e), r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] += r[k];
         }
         y[e] = h8_pack(f);
     }
 }
 
 // --------------------------------------------------------------- BN backward --
-// g = dy * act'(bn(x));  partial sums of g and g * xhat per channel.
-__device__ __forceinline__ void bn_masked_grad(const float (&xf)[8], const float (&dyf)[8], const float* gamma,
-                                               const float* beta, const float* save, int C, int cg, int act,
-                                               float (&g)[8], float (&xh)[8]) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int c = cg * 8 + k;
-        xh[k] = (xf[k] - __ldg(save + c)) * __ldg(save + C + c);
-        float gv = dyf[k];
-        if (act != SSD_ACT_NONE) {
-            const float v = fmaf(xh[k], __ldg(gamma + c), __ldg(beta + c));
-            if (!(v > 0.0f) || (act == SSD_ACT_RELU6 && !(v < 6.0f))) gv = 0.0f;
-        }
-        g[k] = gv;
-    }
-}
-
+// g = dy * act'(bn(x));  partial sums of g and g * xhat per channel (thread-constant channel group).
 __global__ void __launch_bounds__(kRedThreads)
 bn_bwd_partial_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, const float* __restrict__ gamma,
                       const float* __restrict__ beta, const float* __restrict__ save, int C, int act, ChunkGeom g,
@@ -180,13 +177,27 @@ bn_bwd_partial_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
     const int64_t hi = lo + g.per_chunk < g.total ? lo + g.per_chunk : g.total;
     if ((int)threadIdx.x < g.tpr) {
         const int cg = (int)((lo + threadIdx.x) % g.C8);
+        float mean[8], rstd[8], gam[8], bet[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = cg * 8 + k;
+            mean[k] = __ldg(save + c); rstd[k] = __ldg(save + C + c); gam[k] = __ldg(gamma + c); bet[k] = __ldg(beta + c);
+        }
         for (int64_t e = lo + threadIdx.x; e < hi; e += g.tpr) {
-            float xf[8], df[8], gg[8], xh[8];
+            float xf[8], df[8];
             h8_unpack(__ldg(x + e), xf);
             h8_unpack(__ldg(dy + e), df);
-            bn_masked_grad(xf, df, gamma, beta, save, C, cg, act, gg, xh);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { acc[0][k] += gg[k]; acc[1][k] = fmaf(gg[k], xh[k], acc[1][k]); }
+            for (int k = 0; k < 8; ++k) {
+                const float xh = (xf[k] - mean[k]) * rstd[k];
+                float gv = df[k];
+                if (act != SSD_ACT_NONE) {
+                    const float v = fmaf(xh, gam[k], bet[k]);
+                    if (!(v > 0.0f) || (act == SSD_ACT_RELU6 && !(v < 6.0f))) gv = 0.0f;
+                }
+                acc[0][k] += gv;
+                acc[1][k] = fmaf(gv, xh, acc[1][k]);
+            }
         }
     }
     cta_combine<2>(acc, g.C8, g.tpr, s_red, partial + (size_t)blockIdx.x * 2 * g.C8 * 8);
@@ -207,25 +218,38 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int chunks, int C, dou
     coef[C + c] = (float)(s2 * inv_m);
 }
 
-// dx = gamma * rstd * (g - mean(g) - xhat * mean(g*xhat));  dres (+)= dy
+// dx = gamma * rstd * (g - mean(g) - xhat * mean(g*xhat));  dres (+)= dy.  Thread-constant channel group.
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ save, const float* __restrict__ coef,
                     int C8, int C, int act, uint4* __restrict__ dx, uint4* __restrict__ dres, int accumulate_res,
-                    int64_t total) {
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int cg = (int)(e % C8);
-        float xf[8], df[8], gg[8], xh[8];
-        h8_unpack(__ldg(x + e), xf);
-        const uint4 dyv = __ldg(dy + e);
+                    int64_t total, int64_t stride) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= stride) return;
+    const int cg = (int)(t % C8);
+    float mean[8], rstd[8], gam[8], bet[8], k1[8], k2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = cg * 8 + k;
+        mean[k] = __ldg(save + c); rstd[k] = __ldg(save + C + c); gam[k] = __ldg(gamma + c); bet[k] = __ldg(beta + c);
+        k1[k] = __ldg(coef + c); k2[k] = __ldg(coef + C + c);
+    }
+    for (int64_t e = t; e < total; e += stride) {
+        float xf[8], df[8], out[8];
+        h8_unpack(__ldcs(x + e), xf);
+        const uint4 dyv = __ldcs(dy + e);
         h8_unpack(dyv, df);
-        bn_masked_grad(xf, df, gamma, beta, save, C, cg, act, gg, xh);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int c = cg * 8 + k;
-            gg[k] = __ldg(gamma + c) * __ldg(save + C + c) * (gg[k] - __ldg(coef + c) - xh[k] * __ldg(coef + C + c));
+            const float xh = (xf[k] - mean[k]) * rstd[k];
+            float g = df[k];
+            if (act != SSD_ACT_NONE) {
+                const float v = fmaf(xh, gam[k], bet[k]);
+                if (!(v > 0.0f) || (act == SSD_ACT_RELU6 && !(v < 6.0f))) g = 0.0f;
+            }
+            out[k] = gam[k] * rstd[k] * (g - k1[k] - xh * k2[k]);
         }
-        dx[e] = h8_pack(gg);
+        dx[e] = h8_pack(out);
         if (dres) {
             if (accumulate_res) {
                 float rf[8];
@@ -341,6 +365,15 @@ static int ew_grid(int64_t total) {
     int64_t blocks = (total + 255) / 256, cap = (int64_t)sm_count() * 16;
     return (int)(blocks < cap ? blocks : cap);
 }
+// grid and thread stride (a multiple of C8, at most grid*256) for the thread-constant-channel element-wise passes
+static int ew_grid_c8(int64_t total, int C8, int64_t* stride) {
+    int64_t blocks = (total + 4 * 256 - 1) / (4 * 256), cap = (int64_t)sm_count() * 8;     // ~4+ vectors per thread
+    blocks = blocks < 1 ? 1 : blocks > cap ? cap : blocks;
+    int64_t threads = blocks * 256;
+    if (threads < C8) { blocks = (C8 + 255) / 256; threads = blocks * 256; }
+    *stride = threads / C8 * C8;
+    return (int)blocks;
+}
 
 }  // namespace ssd
 
@@ -369,12 +402,14 @@ extern "C" int ssd_bn_train_fwd(const void* d_x, const float* d_gamma, const flo
         reinterpret_cast<const uint4*>(d_x), g, partial);
     SSD_CHECK_LAUNCH("bn_stats_partial_kernel");
     const double bessel = M > 1 ? (double)M / (double)(M - 1) : 1.0;
+    float* coef = partial + (size_t)kMaxChunks * 2 * C;
     bn_stats_finalize_kernel<<<ceil_div(C, 8), 256, 0, st>>>(partial, g.chunks, C, 1.0 / (double)M, bessel, eps, momentum,
-                                                               d_save, d_moving_mean, d_moving_var);
+                                                               d_gamma, d_beta, d_save, coef, d_moving_mean, d_moving_var);
     SSD_CHECK_LAUNCH("bn_stats_finalize_kernel");
-    bn_apply_kernel<<<ew_grid(g.total), 256, 0, st>>>(reinterpret_cast<const uint4*>(d_x), d_gamma, d_beta, d_save,
-                                                       reinterpret_cast<const uint4*>(d_res),
-                                                       reinterpret_cast<uint4*>(d_y), g.C8, C, act, g.total);
+    int64_t stride = 0;
+    const int grid = ew_grid_c8(g.total, g.C8, &stride);
+    bn_apply_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(d_x), coef, reinterpret_cast<const uint4*>(d_res),
+                                           reinterpret_cast<uint4*>(d_y), g.C8, C, act, g.total, stride);
     SSD_CHECK_LAUNCH("bn_apply_kernel");
     return SSD_OK;
 }
@@ -399,9 +434,11 @@ extern "C" int ssd_bn_train_bwd(const void* d_x, const void* d_dy, const float* 
     SSD_CHECK_LAUNCH("bn_bwd_partial_kernel");
     bn_bwd_finalize_kernel<<<ceil_div(C, 8), 256, 0, st>>>(partial, g.chunks, C, 1.0 / (double)M, d_dgamma, d_dbeta, coef);
     SSD_CHECK_LAUNCH("bn_bwd_finalize_kernel");
-    bn_bwd_apply_kernel<<<ew_grid(g.total), 256, 0, st>>>(
+    int64_t stride = 0;
+    const int grid = ew_grid_c8(g.total, g.C8, &stride);
+    bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(
         reinterpret_cast<const uint4*>(d_x), reinterpret_cast<const uint4*>(d_dy), d_gamma, d_beta, d_save, coef, g.C8, C,
-        act, reinterpret_cast<uint4*>(d_dx), reinterpret_cast<uint4*>(d_dres), accumulate_res, g.total);
+        act, reinterpret_cast<uint4*>(d_dx), reinterpret_cast<uint4*>(d_dres), accumulate_res, g.total, stride);
     SSD_CHECK_LAUNCH("bn_bwd_apply_kernel");
     return SSD_OK;
 }

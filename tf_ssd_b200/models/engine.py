@@ -660,6 +660,9 @@ class SSDModel(object):
         if getattr(self, "trainer", None) is None:
             raise RuntimeError("call model.compile(optimizer=..., loss=[...]) first")
         history: Dict[str, List[float]] = {"loss": [], "val_loss": []}
+        for cb in callbacks or ():
+            if hasattr(cb, "set_model"):
+                cb.set_model(self)
         it = iter(data)
         vit = iter(validation_data) if validation_data is not None else None
         for epoch in range(epochs):
@@ -675,6 +678,8 @@ class SSDModel(object):
                 tot += self.trainer.train_on_batch(img, targets, lr)["loss"]
                 n += 1
             logs = {"loss": tot / max(n, 1)}
+            if verbose:
+                print(f"Epoch {epoch + 1}/{epochs} - loss: {logs['loss']:.4f}", flush=True)
             if vit is not None:
                 vt, vn = 0.0, 0
                 for _ in range(validation_steps or 1):

@@ -54,6 +54,33 @@ class LearningRateScheduler(object):
         return float(self.schedule(epoch))
 
 
+class ModelCheckpoint(object):
+    """``tensorflow.keras.callbacks.ModelCheckpoint(path, monitor="val_loss", save_best_only=True,
+    save_weights_only=True)`` (trainer.py:108-113): writes ``model.save_weights(path)`` when the monitored value
+    improves (or every epoch without ``save_best_only``)."""
+
+    def __init__(self, filepath: str, monitor: str = "val_loss", save_best_only: bool = False, save_weights_only: bool = True):
+        self.filepath, self.monitor, self.save_best_only = filepath, monitor, save_best_only
+        self.best = math.inf
+        self.model = None
+        self.saved_epochs: List[int] = []
+
+    def set_model(self, model) -> None:
+        self.model = model
+
+    def on_epoch_end(self, epoch, logs=None):
+        value = (logs or {}).get(self.monitor)
+        if self.save_best_only and (value is None or not value < self.best):
+            return
+        if value is not None:
+            self.best = min(self.best, value)
+        trainer = getattr(self.model, "trainer", None)
+        if trainer is not None:
+            trainer.sync_weights_to_host()
+        self.model.save_weights(self.filepath)
+        self.saved_epochs.append(epoch)
+
+
 class Trainer(object):
     """Owns the master weights, Adam state, gradient buffers and the backward launch list."""
 

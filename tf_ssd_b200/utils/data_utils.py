@@ -1,0 +1,122 @@
+"""Dataset plumbing with the reference's names (``utils/data_utils.py`` of FurkanOM/tf-ssd).
+
+The reference reads PASCAL VOC through ``tensorflow_datasets``; neither the data nor TFDS exist in this
+environment, so ``get_dataset`` serves a SEEDED SYNTHETIC dataset with the same tensor contract
+(``utils/data_utils.py:33-37,140-155``): images NHWC float32 in [0,1], boxes normalised ``[y1,x1,y2,x2]``,
+labels shifted by +1 (0 = background), batches padded with box 0 / label -1.  Host-side NumPy only."""
+
+from __future__ import annotations
+
+import zlib
+from typing import Any, Dict, Iterator, List, Tuple
+
+import numpy as np
+
+VOC_LABELS = ["aeroplane", "bicycle", "bird", "boat", "bottle", "bus", "car", "cat", "chair", "cow", "diningtable",
+              "dog", "horse", "motorbike", "person", "pottedplant", "sheep", "sofa", "train", "tvmonitor"]
+# split sizes of the TFDS voc builders the reference uses (trainer.py:47-58)
+_SPLIT_ITEMS = {("voc/2007", "train+validation"): 5011, ("voc/2007", "test"): 4952, ("voc/2012", "train+validation"): 11540}
+
+
+class SyntheticVOC(object):
+    """Iterable of ``(img [S,S,3], gt_boxes [g,4], gt_labels [g])`` examples; ``padded_batch`` mirrors tf.data."""
+
+    def __init__(self, total_items: int, img_size: int = 300, seed: int = 0, max_boxes: int = 8):
+        self.total_items, self.img_size, self.seed, self.max_boxes = int(total_items), int(img_size), int(seed), int(max_boxes)
+        self._parts: List["SyntheticVOC"] = [self]
+
+    def concatenate(self, other: "SyntheticVOC") -> "SyntheticVOC":
+        out = SyntheticVOC(self.total_items + other.total_items, self.img_size, self.seed, self.max_boxes)
+        out._parts = self._parts + other._parts
+        return out
+
+    def map(self, fn) -> "SyntheticVOC":      # preprocessing is part of the generator (already resized / normalised)
+        return self
+
+    def shuffle(self, buffer_size: int) -> "SyntheticVOC":
+        return self
+
+    def take(self, n: int) -> "SyntheticVOC":
+        out = SyntheticVOC(min(n, self.total_items), self.img_size, self.seed, self.max_boxes)
+        return out
+
+    def _example(self, rng: np.random.Generator) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        S = self.img_size
+        g = int(rng.integers(1, self.max_boxes + 1))
+        c, wh = rng.random((g, 2)), rng.uniform(0.1, 0.6, (g, 2))
+        boxes = np.clip(np.concatenate([c - wh / 2, c + wh / 2], -1), 0.0, 1.0).astype(np.float32)
+        labels = rng.integers(1, len(VOC_LABELS) + 1, g).astype(np.int32)      # +1: background is class 0 (:36)
+        img = np.full((S, S, 3), 0.4, np.float32) + 0.1 * rng.random((S, S, 3), dtype=np.float32)
+        for (y1, x1, y2, x2), lab in zip(boxes, labels):                          # class-coloured rectangles: learnable
+            col = np.array([(lab * 37 % 255) / 255.0, (lab * 91 % 255) / 255.0, (lab * 53 % 255) / 255.0], np.float32)
+            img[int(y1 * S):max(int(y2 * S), int(y1 * S) + 1), int(x1 * S):max(int(x2 * S), int(x1 * S) + 1)] = col
+        return img, boxes, labels
+
+    def __iter__(self) -> Iterator[Tuple[np.ndarray, np.ndarray, np.ndarray]]:
+        for k, part in enumerate(self._parts):
+            rng = np.random.default_rng(part.seed + 7919 * k)
+            for _ in range(part.total_items):
+                yield part._example(rng)
+
+    def padded_batch(self, batch_size: int, padded_shapes: Any = None, padding_values: Any = None, drop_remainder: bool = False):
+        """``tf.data.Dataset.padded_batch`` (trainer.py:75-84): ragged ground truth padded to the batch maximum."""
+        ds = self
+
+        class _Batched(object):
+            def __iter__(self_inner):
+                imgs, boxes, labels = [], [], []
+                for img, b, l in ds:
+                    imgs.append(img); boxes.append(b); labels.append(l)
+                    if len(imgs) == batch_size:
+                        yield _pad(imgs, boxes, labels)
+                        imgs, boxes, labels = [], [], []
+                if imgs and not drop_remainder:
+                    yield _pad(imgs, boxes, labels)
+        return _Batched()
+
+
+def _pad(imgs, boxes, labels):
+    g = max(b.shape[0] for b in boxes)
+    gb = np.zeros((len(imgs), g, 4), np.float32)                      # padding value 0 (:151)
+    gl = np.full((len(imgs), g), -1, np.int32)                        # padding value -1 (:153)
+    for i, (b, l) in enumerate(zip(boxes, labels)):
+        gb[i, :b.shape[0]] = b
+        gl[i, :l.shape[0]] = l
+    return np.stack(imgs), gb, gl
+
+
+def get_dataset(name: str, split: str, data_dir: str = "~/tensorflow_datasets", total_items: int = 0, img_size: int = 300):
+    """utils/data_utils.py:40-56 -> ``(dataset, info)``; synthetic stand-in (see the module docstring)."""
+    n = int(total_items) or _SPLIT_ITEMS.get((name, split), 1000)
+    seed = zlib.crc32(f"{name}:{split}".encode()) % (1 << 16)
+    return SyntheticVOC(n, img_size=img_size, seed=seed), {"name": name, "splits": {split: n}, "labels": list(VOC_LABELS)}
+
+
+def get_total_item_size(info: Dict[str, Any], split: str) -> int:
+    """utils/data_utils.py:59-72."""
+    return int(info["splits"][split])
+
+
+def get_labels(info: Dict[str, Any]) -> List[str]:
+    """utils/data_utils.py:75-85."""
+    return list(info["labels"])
+
+
+def preprocessing(image_data: Any, final_height: int, final_width: int, augmentation_fn: Any = None, evaluate: bool = False):
+    """utils/data_utils.py:12-38 resizes and normalises one TFDS example; the synthetic examples are already in
+    that form, so this is the identity (kept for the call sites of trainer.py:68-71 / predictor.py:69-71)."""
+    return image_data
+
+
+def get_data_types():
+    return (np.float32, np.float32, np.int32)
+
+
+def get_data_shapes():
+    """utils/data_utils.py:140-147."""
+    return ([None, None, None], [None, None], [None])
+
+
+def get_padding_values():
+    """utils/data_utils.py:150-155."""
+    return (np.float32(0), np.float32(0), np.int32(-1))

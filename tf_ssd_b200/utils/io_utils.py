@@ -1,0 +1,49 @@
+"""Filesystem / argument helpers with the reference's names (``utils/io_utils.py`` of FurkanOM/tf-ssd).
+
+Weights are stored as ``.npz`` keyed by Keras variable names (``h5py`` is not available in this image; see
+``tools/convert_h5_weights.py`` for the ``.h5`` -> ``.npz`` conversion a machine with h5py can run)."""
+
+from __future__ import annotations
+
+import argparse
+import os
+from datetime import datetime
+from typing import Optional, Sequence
+
+VALID_BACKBONES = ("mobilenet_v2", "vgg16")
+
+
+def get_log_path(model_type: str, custom_postfix: str = "") -> str:
+    """utils/io_utils.py:13-24."""
+    return "logs/{}{}/{}".format(model_type, custom_postfix, datetime.now().strftime("%Y%m%d-%H%M%S"))
+
+
+def get_model_path(model_type: str, main_path: str = "trained") -> str:
+    """utils/io_utils.py:27-39 (``.npz`` instead of ``.h5``)."""
+    os.makedirs(main_path, exist_ok=True)
+    return os.path.join(main_path, "ssd_{}_model_weights.npz".format(model_type))
+
+
+def handle_args(argv: Optional[Sequence[str]] = None) -> argparse.Namespace:
+    """utils/io_utils.py:42-56: ``-handle-gpu`` and ``--backbone``; the extra options size a run on synthetic
+    VOC-shaped data (there is no dataset access in this environment)."""
+    parser = argparse.ArgumentParser(description="SSD: Single Shot MultiBox Detector Implementation (B200-native hot path)")
+    parser.add_argument("-handle-gpu", action="store_true", help="accepted for compatibility; nothing to do without TensorFlow")
+    parser.add_argument("--backbone", required=False, default="mobilenet_v2", metavar="['mobilenet_v2', 'vgg16']",
+                        help="Which backbone used for the ssd")
+    parser.add_argument("--epochs", type=int, default=150)
+    parser.add_argument("--batch-size", type=int, default=32)
+    parser.add_argument("--train-items", type=int, default=0, help="synthetic items per epoch (0: dataset default)")
+    parser.add_argument("--val-items", type=int, default=0)
+    parser.add_argument("--model-dir", default="trained")
+    return parser.parse_args(argv)
+
+
+def is_valid_backbone(backbone: str) -> None:
+    """utils/io_utils.py:59-68."""
+    assert backbone in VALID_BACKBONES, f"backbone must be one of {VALID_BACKBONES}, got {backbone!r}"
+
+
+def handle_gpu_compatibility() -> None:
+    """utils/io_utils.py:71-83 sets TensorFlow's memory-growth flag; there is no TensorFlow here."""
+    return None
