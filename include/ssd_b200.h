@@ -278,6 +278,17 @@ int ssd_head_grad_gather(const float* d_g_logits, const float* d_g_deltas, void*
 int ssd_adam_step(float* d_w, float* d_m, float* d_v, const float* d_grad, void* d_w16, int64_t n, float lr_t,
                   float beta1, float beta2, float eps, float inv_scale, float l2, float* d_sumsq, ssd_stream_t stream);
 
+/* Multi-tensor form of ssd_adam_step: ONE launch for all variables.  d_vars is a DEVICE array of n_vars
+ * descriptors; sum(w^2) is accumulated only for descriptors with l2 != 0; max_n = the largest n. */
+typedef struct ssd_adam_var {
+    float* w; float* m; float* v; const float* grad; void* w16;   /* w16 may be NULL */
+    int64_t n;
+    float l2;
+    float reserved;
+} ssd_adam_var;
+int ssd_adam_step_multi(const ssd_adam_var* d_vars, int n_vars, int64_t max_n, float lr_t, float beta1, float beta2,
+                        float eps, float inv_scale, float* d_sumsq, ssd_stream_t stream);
+
 /* ---- MobileNetV2 training (keras_applications MobileNetV2 under models/ssd_mobilenet_v2.py:25) ----
  * keras.layers.BatchNormalization(epsilon=1e-3, momentum=0.999) in TRAINING mode over the rows of an
  * [M = B*H*W, C] fp16 NHWC activation (C % 8 == 0, C <= 2048): batch mean / biased variance per channel,

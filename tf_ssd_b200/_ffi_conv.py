@@ -23,6 +23,11 @@ class ConvDesc(C.Structure):
     ]
 
 
+class AdamVar(C.Structure):
+    """``struct ssd_adam_var`` (include/ssd_b200.h)."""
+    _fields_ = [("w", vp), ("m", vp), ("v", vp), ("grad", vp), ("w16", vp), ("n", i64), ("l2", f), ("reserved", f)]
+
+
 SIGNATURES = {
     "ssd_conv2d": (i, [C.POINTER(ConvDesc), vp]),
     "ssd_depthwise3x3": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),
@@ -40,6 +45,7 @@ SIGNATURES = {
     "ssd_l2norm_bwd": (i, [vp, vp, vp, vp, vp, i64, i, i, vp]),
     "ssd_head_grad_gather": (i, [vp, vp, vp, i, i, i, i, i, i, i, vp]),
     "ssd_adam_step": (i, [vp, vp, vp, vp, vp, i64, f, f, f, f, f, f, vp, vp]),
+    "ssd_adam_step_multi": (i, [vp, i, i64, f, f, f, f, f, vp, vp]),
     "ssd_bn_workspace_bytes": (C.c_size_t, [i]),
     "ssd_bn_train_fwd": (i, [vp, vp, vp, vp, vp, i64, i, f, f, i, vp, vp, vp, vp, C.c_size_t, vp]),
     "ssd_bn_train_bwd": (i, [vp, vp, vp, vp, vp, i64, i, i, vp, vp, i, vp, vp, vp, C.c_size_t, vp]),

@@ -42,12 +42,12 @@ struct ChunkGeom {
     int chunks;
 };
 
-static ChunkGeom chunk_geom(int64_t M, int C) {
+static ChunkGeom chunk_geom(int64_t M, int C, int per_thread = 16) {
     ChunkGeom g;
     g.C8 = C / 8;
     g.tpr = (kRedThreads / g.C8) * g.C8;
     g.total = M * g.C8;
-    int64_t want = (g.total + (int64_t)g.tpr * 16 - 1) / ((int64_t)g.tpr * 16);    // >= 16 elements per thread
+    int64_t want = (g.total + (int64_t)g.tpr * per_thread - 1) / ((int64_t)g.tpr * per_thread);   // >= per_thread elements each
     g.chunks = (int)(want < 1 ? 1 : want > kMaxChunks ? kMaxChunks : want);
     int64_t per = (g.total + g.chunks - 1) / g.chunks;
     g.per_chunk = (per + g.tpr - 1) / g.tpr * g.tpr;
@@ -464,7 +464,7 @@ extern "C" int ssd_depthwise3x3_wgrad(const void* d_x, const void* d_dy, float* 
     SSD_REQUIRE(B >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0 && C <= 8 * kRedThreads && Ho >= 1 && Wo >= 1 &&
                 (stride == 1 || stride == 2), SSD_ERR_SHAPE,
                 "ssd_depthwise3x3_wgrad: bad shape B=%d H=%d W=%d C=%d Ho=%d Wo=%d stride=%d", B, H, W, C, Ho, Wo, stride);
-    const ChunkGeom g = chunk_geom((int64_t)B * Ho * Wo, C);
+    const ChunkGeom g = chunk_geom((int64_t)B * Ho * Wo, C, 4);
     dw_wgrad_kernel<<<g.chunks, kRedThreads, kRedThreads * 24 * sizeof(float), as_stream(stream)>>>(
         reinterpret_cast<const uint4*>(d_x), reinterpret_cast<const uint4*>(d_dy), H, W, Ho, Wo, stride, pad_top, pad_left,
         g, d_dw);

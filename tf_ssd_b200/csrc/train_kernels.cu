@@ -397,6 +397,32 @@ adam_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
     }
 }
 
+// Multi-tensor variant: one launch updates every variable of the model.  blockIdx.y selects the descriptor,
+// blockIdx.x strides over its elements (descriptors shorter than the grid simply finish early).
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(const ssd_adam_var* __restrict__ vars, float lr_t, float b1, float b2, float eps, float inv_scale,
+                  float* __restrict__ sumsq) {
+    const ssd_adam_var d = vars[blockIdx.y];
+    float* __restrict__ w = d.w; float* __restrict__ m = d.m; float* __restrict__ v = d.v;
+    const float* __restrict__ g = d.grad;
+    __half* __restrict__ w16 = reinterpret_cast<__half*>(d.w16);
+    float local = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float wv = w[i];
+        const float gv = g[i] * inv_scale + d.l2 * wv;
+        const float mv = b1 * m[i] + (1.0f - b1) * gv;
+        const float vv = b2 * v[i] + (1.0f - b2) * gv * gv;
+        const float nw = wv - lr_t * mv / (sqrtf(vv) + eps);
+        m[i] = mv; v[i] = vv; w[i] = nw;
+        if (w16) w16[i] = __float2half_rn(nw);
+        local += wv * wv;
+    }
+    if (sumsq && d.l2 != 0.0f) {
+        local = warp_sum(local);
+        if ((threadIdx.x & 31) == 0 && local != 0.0f) atomicAdd(sumsq, local);
+    }
+}
+
 // conv_tcgen05.cu
 bool conv_wgrad_tcgen05_supported(const ssd_conv_desc* d, int ldy);
 int  conv_wgrad_tcgen05_launch(const ssd_conv_desc* d, const void* d_dy, int ldy, float* d_dw, cudaStream_t st);
@@ -549,5 +575,22 @@ extern "C" int ssd_adam_step(float* d_w, float* d_m, float* d_v, const float* d_
     adam_kernel<<<grid1d(n, 8), 256, 0, as_stream(stream)>>>(d_w, d_m, d_v, d_grad, (__half*)d_w16, n, lr_t, beta1, beta2, eps,
                                                             inv_scale, l2, d_sumsq);
     SSD_CHECK_LAUNCH("adam_kernel");
+    return SSD_OK;
+}
+
+extern "C" int ssd_adam_step_multi(const ssd_adam_var* d_vars, int n_vars, int64_t max_n, float lr_t, float beta1, float beta2,
+                                   float eps, float inv_scale, float* d_sumsq, ssd_stream_t stream) {
+    SSD_REQUIRE_PTR(d_vars);
+    SSD_REQUIRE(n_vars >= 0 && n_vars <= 65535 && max_n >= 0, SSD_ERR_SHAPE, "ssd_adam_step_multi: n_vars=%d max_n=%lld", n_vars,
+                (long long)max_n);
+    if (n_vars == 0 || max_n == 0) return SSD_OK;
+    // enough CTAs per variable that the largest one (a few million elements) still spreads over the device
+    int64_t bx = (max_n + 256 * 8 - 1) / (256 * 8);
+    const int64_t cap = max((int64_t)1, (int64_t)sm_count() * 16 / n_vars + 1);
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    adam_multi_kernel<<<dim3((unsigned)bx, (unsigned)n_vars), 256, 0, as_stream(stream)>>>(d_vars, lr_t, beta1, beta2, eps,
+                                                                                          inv_scale, d_sumsq);
+    SSD_CHECK_LAUNCH("adam_multi_kernel");
     return SSD_OK;
 }

@@ -137,6 +137,17 @@ class Trainer(object):
             v["m"] = torch.zeros_like(v["master"])
             v["v"] = torch.zeros_like(v["master"])
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        # descriptor table of the multi-tensor Adam launch (device array of struct ssd_adam_var)
+        from tf_ssd_b200._ffi_conv import AdamVar
+        table = (AdamVar * len(self.vars))()
+        for i, v in enumerate(self.vars.values()):
+            table[i].w, table[i].m, table[i].v = v["master"].data_ptr(), v["m"].data_ptr(), v["v"].data_ptr()
+            table[i].grad = v["grad"].data_ptr()
+            table[i].w16 = v["w16"].data_ptr() if v["w16"] is not None else None
+            table[i].n, table[i].l2 = v["master"].numel(), v["l2"]
+        raw = np.frombuffer(bytes(table), dtype=np.uint8).copy()
+        self._adam_table = torch.from_numpy(raw).to(self.dev)
+        self._adam_max_n = max(v["master"].numel() for v in self.vars.values())
 
     def sync_weights_to_host(self) -> None:
         """Write the trained variables back into ``model.weights`` (Keras names / layouts)."""
@@ -367,13 +378,9 @@ class Trainer(object):
         lr = self.lr if learning_rate is None else float(learning_rate)
         lr_t = lr * math.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
         self.sumsq.zero_()
-        stream = _ffi.stream()
-        for name, v in self.vars.items():
-            w16 = v["w16"]
-            _ffi.check(self.lib.ssd_adam_step(_ffi.ptr(v["master"]), _ffi.ptr(v["m"]), _ffi.ptr(v["v"]), _ffi.ptr(v["grad"]),
-                                              _ffi.ptr(w16), v["master"].numel(), lr_t, self.b1, self.b2, self.eps,
-                                              1.0 / self.loss_scale, v["l2"], _ffi.ptr(self.sumsq) if v["l2"] else None,
-                                              stream), "ssd_adam_step")
+        _ffi.check(self.lib.ssd_adam_step_multi(_ffi.ptr(self._adam_table), len(self.vars), self._adam_max_n, lr_t, self.b1,
+                                                self.b2, self.eps, 1.0 / self.loss_scale, _ffi.ptr(self.sumsq), _ffi.stream()),
+                   "ssd_adam_step_multi")
 
     def evaluate_batch(self, images: Any, targets: Tuple[Any, Any]) -> Dict[str, float]:
         """Validation loss of one batch (no gradient, no update): mean loc + mean conf (+ the regulariser of the
