@@ -87,10 +87,11 @@ softmax_kernel(const float* __restrict__ logits, int64_t rows, int L, float* __r
 //   2. per warp, the surviving rows one at a time with the classes spread over the lanes: the
 //      arithmetic of softmax_kernel (expf, sequential float32 sum, IEEE division), so the
 //      fused path emits bit-identical scores to softmax followed by the probability path.
-template <bool DECODER, bool FROM_LOGITS>
+template <bool DECODER, bool FROM_LOGITS, int LT>          // LT: compile-time label count (0 = use the runtime L)
 __global__ void __launch_bounds__(kRowThreadsNms)
-nms_candidates_kernel(const float* __restrict__ scores, int N, int L, float score_thr, int cap,
+nms_candidates_kernel(const float* __restrict__ scores, int N, int L_rt, float score_thr, int cap,
                       uint64_t* __restrict__ keys, int key_stride, int* __restrict__ counts) {
+    const int L = LT ? LT : L_rt;                        // phase 1 unrolls completely for the VOC label count
     extern __shared__ __align__(16) float s_rows[];
     __shared__ int s_warp_tot[kRowThreadsNms / 32];
     __shared__ int s_base;
@@ -103,12 +104,15 @@ nms_candidates_kernel(const float* __restrict__ scores, int N, int L, float scor
     __syncthreads();
     float* p = rows + (size_t)threadIdx.x * L;
     int mine = 0;                                        // candidates of this anchor
+    int first_cls = -1;                                  // its lowest candidate class when known (fused-softmax path)
     if (FROM_LOGITS) {
         bool maybe = false;
         if ((int)threadIdx.x < cnt) {
             float m = p[0];
+#pragma unroll
             for (int l = 1; l < L; ++l) m = fmaxf(m, p[l]);
             float s = 0.0f;
+#pragma unroll
             for (int l = 0; l < L; ++l) s += exp2f_approx((p[l] - m) * 1.4426950408889634f);
             const float thr_lo = score_thr - 1e-4f * fabsf(score_thr);
             maybe = thr_lo * s < 1.0f;
@@ -128,21 +132,22 @@ nms_candidates_kernel(const float* __restrict__ scores, int N, int L, float scor
             float s = 0.0f;
             for (int l = 0; l < L; ++l) s = fadd(s, q[l]);           // same order as softmax_kernel
             __syncwarp();
-            int c = 0, am = 0x7fffffff;
+            int c = 0, am = 0x7fffffff, lowest = 0x7fffffff;
             float best = -__int_as_float(0x7f800000);
             for (int l = lane; l < L; l += 32) {
                 const float v = fdiv(q[l], s);
                 q[l] = v;
-                c += (v > score_thr) ? 1 : 0;
+                if (v > score_thr) { ++c; lowest = min(lowest, l); }
                 if (v > best) { best = v; am = l; }
             }
             c = __reduce_add_sync(0xffffffffu, c);
+            lowest = __reduce_min_sync(0xffffffffu, lowest);
             if (DECODER) {                               // decoder.py:78-83: first maximum == 0 zeroes the row
                 const float gb = warp_max_f32(best);
                 const int first = __reduce_min_sync(0xffffffffu, best == gb ? am : 0x7fffffff);
                 if (first == 0 || first == 0x7fffffff) c = 0;
             }
-            if (lane == r) mine = c;
+            if (lane == r) { mine = c; first_cls = lowest; }
             __syncwarp();
         }
     } else if ((int)threadIdx.x < cnt) {
@@ -179,6 +184,10 @@ nms_candidates_kernel(const float* __restrict__ scores, int N, int L, float scor
     int slot = s_base + s_warp_tot[wid] + incl - mine;
     const uint32_t anchor = (uint32_t)(n0 + threadIdx.x);
     uint64_t* dst = keys + (size_t)b * key_stride;
+    if (mine == 1 && first_cls >= 0) {                   // the usual case above a 0.5 threshold: exactly one class
+        if (slot < cap) dst[slot] = ((uint64_t)first_cls << 56) | ((uint64_t)(~order_bits(p[first_cls])) << 24) | anchor;
+        return;
+    }
     for (int l = 0; l < L; ++l) {
         float sc = p[l];
         if (sc > score_thr) {
@@ -243,6 +252,23 @@ __device__ void bitonic_sort(uint64_t* a, int P) {
         }
     }
 }
+// Ascending sort of n UNIQUE keys by rank counting: every key counts the smaller keys (broadcast shared-memory
+// reads, no barrier per stage) and is written to its rank.  O(n^2) compares but only two barriers: cheaper than
+// the 36-55 barrier stages of the bitonic network for the few hundred keys an image produces.
+__device__ void rank_sort(uint64_t* a, uint64_t* tmp, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t key = a[i];
+        int rank = 0;
+#pragma unroll 8
+        for (int j = 0; j < n; ++j) rank += (a[j] < key) ? 1 : 0;
+        tmp[rank] = key;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = tmp[i];
+    __syncthreads();
+}
+constexpr int kRankSortMax = 768;          // beyond this the bitonic network wins
+
 __device__ __forceinline__ int pow2_ceil(int v) {
     int p = 32;
     while (p < v) p <<= 1;
@@ -276,6 +302,7 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
     float4*   s_box  = reinterpret_cast<float4*>(s_raw + (size_t)P.smem_sort_slots * 8);
     uint16_t* s_kidx = reinterpret_cast<uint16_t*>(s_raw + (size_t)P.smem_sort_slots * 8 + (size_t)P.fast_slots * 16);
     __shared__ int s_seg_start[257];
+    __shared__ int s_cnt[256], s_cur[256];
     __shared__ int s_mcount;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nwarps = kNmsThreads / 32;
@@ -297,22 +324,71 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
     uint64_t* gk = keys + (size_t)b * P.key_stride;
     uint64_t* cand = (P1 <= P.smem_sort_slots) ? s_sort : gk;
     const bool fast = P1 <= P.fast_slots;
-    if (cand == s_sort) {
-        for (int i = tid; i < P1; i += kNmsThreads) s_sort[i] = (i < M) ? gk[i] : kPadKey;
-    } else {
-        for (int i = M + tid; i < P1; i += kNmsThreads) gk[i] = kPadKey;
-    }
+    const bool grouped = cand == s_sort && 2 * M <= P.smem_sort_slots;      // class-grouped counting sort (common case)
     for (int i = tid; i < 257; i += kNmsThreads) s_seg_start[i] = -1;
+    for (int i = tid; i < 256; i += kNmsThreads) { s_cnt[i] = 0; }
     if (tid == 0) s_mcount = 0;
     __syncthreads();
-    if (M > 1) bitonic_sort(cand, P1);
+    if (grouped) {
+        // a. class histogram -> segment starts; b. scatter into class segments (arbitrary order inside);
+        // c. rank inside the own segment only (a class holds a few dozen candidates): sum n_c^2 compares instead
+        //    of a CTA-wide sorting network
+        uint64_t* tmp = s_sort + (P.smem_sort_slots >> 1);
+        for (int i = tid; i < M; i += kNmsThreads) atomicAdd(&s_cnt[(int)(gk[i] >> 56)], 1);
+        __syncthreads();
+        if (wid == 0) {                                // exclusive scan of the 256 class counts (8 per lane)
+            int c8[8], t = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { c8[q] = s_cnt[lane * 8 + q]; t += c8[q]; }
+            int incl = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            int start = incl - t;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                s_cur[lane * 8 + q] = start;
+                if (c8[q] > 0) s_seg_start[lane * 8 + q] = start;
+                start += c8[q];
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < M; i += kNmsThreads) {
+            const uint64_t key = gk[i];
+            tmp[atomicAdd(&s_cur[(int)(key >> 56)], 1)] = key;
+        }
+        __syncthreads();
+        for (int i = tid; i < M; i += kNmsThreads) {
+            const uint64_t key = tmp[i];
+            const int c = (int)(key >> 56), start = s_seg_start[c], end = start + s_cnt[c];
+            int rank = 0;
+            for (int j = start; j < end; ++j) rank += (tmp[j] < key) ? 1 : 0;
+            s_sort[start + rank] = key;
+        }
+        __syncthreads();
+        if (fast)
+            for (int i = tid; i < M; i += kNmsThreads) {
+                const uint64_t key = cand[i];
+                s_box[i] = fetch(b, (int)(key & 0xFFFFFFu), (int)(key >> 56));
+            }
+    } else {
+        if (cand == s_sort) {
+            for (int i = tid; i < P1; i += kNmsThreads) s_sort[i] = (i < M) ? gk[i] : kPadKey;
+        } else {
+            for (int i = M + tid; i < P1; i += kNmsThreads) gk[i] = kPadKey;
+        }
+        __syncthreads();
+        if (M > 1) bitonic_sort(cand, P1);
 
-    // ---- 2. class segments; decode every candidate box once (fast path) ------
-    for (int i = tid; i < M; i += kNmsThreads) {
-        const uint64_t key = cand[i];
-        const int c = (int)(key >> 56);
-        if (i == 0 || (int)(cand[i - 1] >> 56) != c) s_seg_start[c] = i;
-        if (fast) s_box[i] = fetch(b, (int)(key & 0xFFFFFFu), c);
+        // ---- 2. class segments; decode every candidate box once (fast path) ------
+        for (int i = tid; i < M; i += kNmsThreads) {
+            const uint64_t key = cand[i];
+            const int c = (int)(key >> 56);
+            if (i == 0 || (int)(cand[i - 1] >> 56) != c) s_seg_start[c] = i;
+            if (fast) s_box[i] = fetch(b, (int)(key & 0xFFFFFFu), c);
+        }
     }
     __syncthreads();
 
@@ -322,7 +398,41 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
         const int start = s_seg_start[c];
         if (start < 0) continue;
         int nk = 0;
-        if (fast) {
+        const int seg = grouped ? s_cnt[c] : 0;          // segment length (known up front on the grouped path)
+        if (fast && seg > 0 && seg <= 64 && seg <= P.per_class) {
+            // Bit-mask greedy NMS for a class with <= 64 candidates: lane r owns rows r and r + 32 of the strictly
+            // upper-triangular "i suppresses j" matrix (all IoUs of the class computed in parallel), then the
+            // sequential part is a scan over 64-bit masks.  Same result as the candidate-by-candidate loop below:
+            // a candidate is dropped iff an EARLIER KEPT candidate overlaps it by more than the threshold.
+            const float4 box0 = lane < seg ? s_box[start + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 box1 = lane + 32 < seg ? s_box[start + lane + 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+            uint64_t row0 = 0, row1 = 0;
+            for (int j = 1; j < seg; ++j) {
+                const float4 bj = s_box[start + j];
+                if (lane < j && nms_iou(box0, bj) > P.iou_thr) row0 |= 1ull << j;
+                if (lane + 32 < j && nms_iou(box1, bj) > P.iou_thr) row1 |= 1ull << j;
+            }
+            uint64_t removed = 0;
+            for (int i = 0; i < seg; ++i) {
+                const uint64_t row = __shfl_sync(0xffffffffu, i < 32 ? row0 : row1, i & 31);
+                if (!((removed >> i) & 1ull)) removed |= row;
+            }
+            const uint64_t valid = seg == 64 ? ~0ull : ((1ull << seg) - 1ull);
+            const uint64_t kept = ~removed & valid;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_mcount, __popcll(kept));
+            base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = lane + 32 * h;
+                if (i < seg && ((kept >> i) & 1ull)) {
+                    const uint64_t key = cand[start + i];
+                    const int slot = base + __popcll(kept & ((1ull << i) - 1ull));
+                    const uint32_t inv_score = (uint32_t)((key >> 24) & 0xFFFFFFFFu);
+                    mk[slot] = ((uint64_t)inv_score << 32) | ((uint64_t)c << 24) | (uint32_t)(key & 0xFFFFFFu);
+                }
+            }
+        } else if (fast) {
             uint16_t* kidx = s_kidx + (size_t)wid * P.per_class;
             for (int i = start; i < M && nk < P.per_class; ++i) {
                 const uint64_t key = cand[i];
@@ -376,7 +486,10 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
         for (int i = K + tid; i < P2; i += kNmsThreads) mk[i] = kPadKey;
     }
     __syncthreads();
-    if (K > 1) bitonic_sort(ms, P2);
+    if (K > 1) {
+        if (ms == s_sort && K <= kRankSortMax && 2 * P2 <= P.smem_sort_slots) rank_sort(ms, s_sort + (P.smem_sort_slots >> 1), K);
+        else bitonic_sort(ms, P2);
+    }
     const int V = min(K, T);
     for (int r = tid; r < T; r += kNmsThreads) {
         if (r < V) {
@@ -512,7 +625,8 @@ extern "C" int ssd_decode_nms(const float* d_priors, const float* d_pred_deltas,
         kern<<<grid, kRowThreadsNms, smem, st>>>(d_pred_labels, N, L, score_threshold, plan.p.cap, w.keys,
                                                  plan.p.key_stride, w.counts);
     };
-    if (from_logits) launch(nms_candidates_kernel<true, true>); else launch(nms_candidates_kernel<true, false>);
+    if (from_logits) { if (L == 21) launch(nms_candidates_kernel<true, true, 21>); else launch(nms_candidates_kernel<true, true, 0>); }
+    else launch(nms_candidates_kernel<true, false, 0>);
     SSD_CHECK_LAUNCH("nms_candidates_kernel");
 
     DecodeFetch fetch{reinterpret_cast<const float4*>(d_priors), reinterpret_cast<const float4*>(d_pred_deltas),
@@ -555,7 +669,7 @@ extern "C" int ssd_combined_nms(const float* d_boxes, const float* d_scores, int
     size_t smem = ((size_t)kRowThreadsNms * L + 4) * sizeof(float);
     SSD_REQUIRE(smem <= 200 * 1024, SSD_ERR_UNSUPPORTED, "ssd_combined_nms: L=%d too large", L);
     dim3 grid(ceil_div(N, kRowThreadsNms), B);
-    auto kern = nms_candidates_kernel<false, false>;
+    auto kern = nms_candidates_kernel<false, false, 0>;
     if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<grid, kRowThreadsNms, smem, st>>>(d_scores, N, L, score_threshold, plan.p.cap, w.keys,
                                              plan.p.key_stride, w.counts);
