@@ -43,11 +43,12 @@ static size_t loss_ws_layout(int B, int N, LossWs* w, void* base) {
 }
 
 // ------------------------------------------------------------------ pass 1 --
-template <bool FROM_LOGITS>
+template <bool FROM_LOGITS, int LT>                    // LT: compile-time label count (0 = runtime L)
 __global__ void __launch_bounds__(kRowThreads)
 loss_anchor_kernel(const float4* __restrict__ act_d, const float4* __restrict__ pred_d,
                    const float* __restrict__ act_l, const float* __restrict__ pred_l,
-                   int N, int L, LossWs w) {
+                   int N, int L_rt, LossWs w) {
+    const int L = LT ? LT : L_rt;                         // the per-row loops unroll completely for the VOC label count
     extern __shared__ __align__(16) float s_rows[];   // [cnt*L + 4] labels, [cnt*L + 4] predictions
     const int b = blockIdx.y;
     const int n0 = blockIdx.x * kRowThreads;
@@ -95,6 +96,7 @@ loss_anchor_kernel(const float4* __restrict__ act_d, const float4* __restrict__ 
         // are one-hot in practice, so the sum over classes (:70) has at most one non-zero term.
         uint32_t fg_bits = 0;
         int nnz = 0, last = 0;
+#pragma unroll
         for (int l = 0; l < L; ++l) {
             const uint32_t bits = __float_as_uint(y[l]) & 0x7fffffffu;     // +-0 -> 0
             if (l > 0) fg_bits |= bits;
@@ -103,8 +105,10 @@ loss_anchor_kernel(const float4* __restrict__ act_d, const float4* __restrict__ 
         float ce = 0.0f;
         if (FROM_LOGITS) {
             float m = p[0];
+#pragma unroll
             for (int l = 1; l < L; ++l) m = fmaxf(m, p[l]);
             float s = 0.0f;
+#pragma unroll
             for (int l = 0; l < L; ++l) s = fadd(s, expf(fsub(p[l], m)));
             const float lse = fadd(logf(s), m);
             if (nnz == 1) {
@@ -117,6 +121,7 @@ loss_anchor_kernel(const float4* __restrict__ act_d, const float4* __restrict__ 
             }
         } else {
             float s = 0.0f;
+#pragma unroll
             for (int l = 0; l < L; ++l) s = fadd(s, p[l]);
             if (nnz == 1) {
                 float q = fminf(fmaxf(fdiv(p[last], s), 1e-7f), fsub(1.0f, 1e-7f));
@@ -182,8 +187,8 @@ __device__ float3 block_sum3(float3 v, float3* s_red3) {
 __global__ void __launch_bounds__(kSelThreads)
 loss_select_kernel(int N, float neg_pos_ratio, float alpha, bool do_loc, bool do_conf, LossWs w,
                    float* __restrict__ out_loc, float* __restrict__ out_conf) {
-    extern __shared__ uint32_t s_key[];               // [N] keys, then [N] flag bytes
-    uint8_t* s_flag = reinterpret_cast<uint8_t*>(s_key + N);
+    extern __shared__ uint32_t s_key[];               // [N] keys (the flag bytes are re-read from L2 in the last pass:
+                                                      //  4 B/anchor of shared memory lets two CTAs share an SM up to N = 28 000)
     __shared__ float s_red[32];
     __shared__ float3 s_red3[32];
     __shared__ int s_hist[256];
@@ -199,8 +204,7 @@ loss_select_kernel(int N, float neg_pos_ratio, float alpha, bool do_loc, bool do
     // counts (exact in float while N < 2^24, like the reference's float sums)
     float3 acc = make_float3(0.f, 0.f, 0.f);          // n_pos_loc, n_pos_conf, huber sum
     for (int i = tid; i < N; i += kSelThreads) {
-        uint8_t f = w.flags[base + i];
-        s_flag[i] = f;
+        const uint8_t f = w.flags[base + i];
         acc.x += (f & 1) ? 1.0f : 0.0f;
         acc.y += (f & 2) ? 1.0f : 0.0f;
         if (do_loc) acc.z += w.hub[base + i];
@@ -311,7 +315,7 @@ loss_select_kernel(int N, float neg_pos_ratio, float alpha, bool do_loc, bool do
             uint32_t key = s_key[i];
             neg = key > T ? 1 : (key == T ? (eq_rank++ < need_eq ? 1 : 0) : 0);
         }
-        int fm = neg + ((s_flag[i] & 2) ? 1 : 0);                  // :84
+        int fm = neg + ((w.flags[base + i] & 2) ? 1 : 0);          // :84
         w.fmask[base + i] = (uint8_t)fm;
         if (fm) total = fadd(total, fmul((float)fm, w.ce[base + i]));    // :85
     }
@@ -420,12 +424,13 @@ extern "C" int ssd_loss_fwd(const float* d_actual_deltas, const float* d_pred_de
             reinterpret_cast<const float4*>(d_pred_deltas),
             do_conf ? d_actual_labels : nullptr, d_pred_labels, N, L, w);
     };
-    if (from_logits) launch1(loss_anchor_kernel<true>); else launch1(loss_anchor_kernel<false>);
+    if (L == 21) { if (from_logits) launch1(loss_anchor_kernel<true, 21>); else launch1(loss_anchor_kernel<false, 21>); }
+    else         { if (from_logits) launch1(loss_anchor_kernel<true, 0>); else launch1(loss_anchor_kernel<false, 0>); }
     SSD_CHECK_LAUNCH("loss_anchor_kernel");
 
-    size_t smem2 = (size_t)N * (sizeof(uint32_t) + 1) + 16;
+    size_t smem2 = (size_t)N * sizeof(uint32_t) + 16;
     SSD_REQUIRE(smem2 <= 200 * 1024, SSD_ERR_UNSUPPORTED,
-                "ssd_loss_fwd: N=%d anchors exceed the per-image shared-memory select (max 40000)", N);
+                "ssd_loss_fwd: N=%d anchors exceed the per-image shared-memory select (max 51000)", N);
     if (smem2 > 40 * 1024)
         cudaFuncSetAttribute(loss_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     loss_select_kernel<<<B, kSelThreads, smem2, st>>>(N, neg_pos_ratio, loc_loss_alpha, do_loc, do_conf, w,

@@ -15,10 +15,7 @@ for what in "$@"; do
           -o $OUT/box_$tag python tools/prof_box.py > $OUT/prof_box_$tag.log 2>&1
       ncu -i $OUT/box_$tag.ncu-rep --page raw --csv > $OUT/box_${tag}_raw.csv 2>/dev/null
       ncu -i $OUT/box_$tag.ncu-rep --page details --csv > $OUT/box_${tag}_details.csv 2>/dev/null
-      ncu -i $OUT/box_$tag.ncu-rep --page source --print-source cuda --csv > $OUT/box_${tag}_source.csv 2>/dev/null
-      python tools/ncu_source_top.py $OUT/box_${tag}_source.csv 22 > $OUT/box_${tag}_source_top.txt 2>&1
-      head -c 3000 $OUT/box_${tag}_source.csv > $OUT/box_${tag}_source_head.txt
-      rm -f $OUT/box_${tag}_source.csv
+      python tools/ncu_summary.py $OUT/box_${tag}_raw.csv > $OUT/box_${tag}_summary.csv 2>&1
       ;;
     launches)
       ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$tag.csv \
