@@ -18,8 +18,8 @@ for what in "$@"; do
       python tools/ncu_summary.py $OUT/box_${tag}_raw.csv > $OUT/box_${tag}_summary.csv 2>&1
       ;;
     launches)
-      ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$tag.csv \
-          python bench.py --steps 2 --warmup 3 --skip-cpu --skip-box > $OUT/launches_$tag.log 2>&1
+      ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $OUT/launches_$tag.csv \
+          python bench.py --profile-one-step > $OUT/launches_$tag.log 2>&1
       ;;
     conv)
       ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"conv_tcgen05_kernel|conv_igemm|splitk" \
