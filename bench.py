@@ -50,19 +50,17 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def _ncu_traffic(kind):
-    """Per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel group, taken from the
-    committed ``ncu --set full`` capture of this same step (profiles/r1_traffic.json; written by tools/ncu_traffic.py).
+def _ncu_traffic(kind, launches_per_step):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the dominant kernel group, from the
+    committed ``ncu --set full`` capture of one step of this same workload (profiles/r1_traffic.json, written by
+    tools/ncu_traffic.py): the group's DRAM bytes per step / its launches per step, i.e. per launch like ``achieved``.
     None when no capture is committed for that group."""
     path = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as f:
-        t = json.load(f)
-    e = t.get(kind)
-    return None if e is None else {"dram_bytes_per_launch": e["dram_bytes_per_launch"], "launches": e["launches"],
-                                   "algorithmic_bytes_per_launch": e.get("algorithmic_bytes_per_launch"),
-                                   "source": e.get("source", "profiles/r1_traffic.json")}
+        e = json.load(f).get(kind)
+    return None if e is None else float(e["dram_bytes"]) / max(int(launches_per_step), 1)
 
 
 def _hyper_params():
@@ -463,7 +461,7 @@ def run_b200(args):
             else:
                 ach = g["bytes"] / (g["ms"] * 1e-3) / 1e9
                 roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]}
-            roof.update({"traffic": _ncu_traffic(top), "kernel": {"conv": "ssd_conv2d launches: conv_tcgen05_kernel (stride 1) + conv_igemm_kernel (stride 2)",
+            roof.update({"traffic": _ncu_traffic(top, g["launches"]), "algorithmic_bytes_per_launch": g["bytes"] / max(g["launches"], 1), "kernel": {"conv": "ssd_conv2d launches: conv_tcgen05_kernel (stride 1) + conv_igemm_kernel (stride 2)",
                                                      "dw": "depthwise3x3_kernel", "decode_nms": "nms_candidates+nms_image"}.get(top, top),
                          "launches_per_step": g["launches"], "ms_per_step": g["ms"], "share_of_step": g["ms"] / total,
                          "algorithmic_bytes_per_step": g["bytes"], "flops_per_step": g["flops"], "peak_source": peaks["source"],

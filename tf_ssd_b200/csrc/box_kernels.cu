@@ -290,7 +290,7 @@ decode_kernel(const float4* __restrict__ priors, const float4* __restrict__ delt
 //    IoU exceeds iou_thr produce anything that depends on the index, so a box that provably
 //    cannot reach iou_thr with ANY anchor of the warp is skipped as well.  IoU > t implies
 //    inter > t*area_gt, inter > t*area_anchor, and inter <= area(gt ^ warp bounding box),
-//    inter <= min(area_gt, area_anchor), inter <= min(heights)*min(widths); the tests below use a 10 % margin, far above the
+//    inter <= min(area_gt, area_anchor); the tests below use a 10 % margin, far above the
 //    few-ulp rounding of the float32 expressions, so no box with IoU > t is ever skipped and
 //    the surviving boxes are evaluated with the exact reference arithmetic in index order.
 //
@@ -344,7 +344,6 @@ match_encode_kernel(const float4* __restrict__ priors, const float4* __restrict_
             // threshold culling needs 0 < thr (and finite areas); a_lo/a_hi bound the warp's anchor areas
             const bool thr_cull = !NEED_IDX && iou_thr > 0.0f;
             const float a_lo = warp_min_f(valid ? pa : inf), a_hi = warp_max_f(valid ? pa : 0.0f);
-            const float h_hi = warp_max_f(valid ? p.z - p.x : 0.0f), w_hi = warp_max_f(valid ? p.w - p.y : 0.0f);
             const float t9 = 0.9f * iou_thr;
             for (int g0 = 0; g0 < G; g0 += 32) {
                 const int g = g0 + lane;
@@ -357,9 +356,6 @@ match_encode_kernel(const float4* __restrict__ priors, const float4* __restrict_
                         const float cy = fminf(q.z, wy2) - fmaxf(q.x, wy1), cx = fminf(q.w, wx2) - fmaxf(q.y, wx1);
                         const float cover = cy * cx;               // area(gt ^ warp bounding box) >= any inter
                         if (cover < t9 * qa || cover < t9 * a_lo || a_hi < t9 * qa || qa < t9 * a_lo) hit = false;
-                        // shape bound: inter <= min(h)*min(w) and union >= max(areas), maximised over the warp's anchors
-                        const float ib = fminf(h_hi, q.z - q.x) * fminf(w_hi, q.w - q.y);
-                        if (ib < t9 * fmaxf(a_lo, qa)) hit = false;
                     }
                 }
                 unsigned mask = __ballot_sync(0xffffffffu, hit);
