@@ -22,8 +22,9 @@
 //     11 520): fp32 partials in a workspace + a deterministic fixed-order
 //     reduction kernel that applies the epilogue.
 //
-// Handles every stride-1 Conv2D of the two graphs (1x1, 3x3, dilation 6, SAME /
-// VALID).  Stride-2 convolutions stay on the mma.sync kernel (conv_igemm.cu).
+// Handles every Conv2D of the two graphs (1x1, 3x3, dilation 6, SAME / VALID, stride 1 and 2 -- a strided
+// convolution uses a tensor map whose W/H element strides equal the convolution stride, so the im2col box still
+// arrives as bw x bh output pixels).  conv_igemm.cu (mma.sync) remains as the fallback for unsupported shapes.
 
 #include "common.cuh"
 
@@ -52,7 +53,7 @@ struct TcParams {
     int B, Ho, Wo, HoWo;
     int bw, bh, bb;                  // output-pixel box of one M tile (4-D mode), bw*bh*bb <= 128
     int tiles_w, tiles_h;            // tiles per image row / column
-    int Cin, KW, dil, pad_t, pad_l;
+    int Cin, KW, dil, pad_t, pad_l, stride;
     int kb_per_tap;                  // ceil(Cin / 64)
     int n_kblocks;                   // taps * kb_per_tap
     int kb_per_split;                // k-blocks handled by one blockIdx.z
@@ -275,8 +276,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const uint32_t dst_a = smem_addr(sA + (size_t)s * a_stage), dst_b = smem_addr(sB + (size_t)s * b_stage);
                     if (p.mode4d) {
                         const int ky = tap / p.KW, kx = tap - ky * p.KW;
-                        tma_load_4d(dst_a, &map_a, bar_full + 8 * s, c0, ox0 + kx * p.dil - p.pad_l,
-                                    oy0 + ky * p.dil - p.pad_t, b0);
+                        // strided convolutions: the tensor map traverses W and H with element stride = conv stride,
+                        // so the box still lands as bw x bh output pixels
+                        tma_load_4d(dst_a, &map_a, bar_full + 8 * s, c0, ox0 * p.stride + kx * p.dil - p.pad_l,
+                                    oy0 * p.stride + ky * p.dil - p.pad_t, b0);
                     } else {
                         tma_load_2d(dst_a, &map_a, bar_full + 8 * s, c0, tm_ * TC_BM);
                     }
@@ -461,12 +464,12 @@ static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
 }
 
 static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box) {
+                    const uint32_t* box, const uint32_t* elem_strides = nullptr) {
     auto enc = tensor_map_encoder();
     if (!enc) return fail(SSD_ERR_UNSUPPORTED, "conv_tcgen05: cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t gdim[4], gstr[3];
     cuuint32_t bx[4], es[4];
-    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -478,7 +481,7 @@ static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t
 // Encoded tensor maps are cached per (pointer, geometry): cuTensorMapEncodeTiled costs a few
 // microseconds of host time, which would otherwise dominate eager launches of small layers.
 struct MapKey {
-    const void* base; uint64_t dims[4]; uint64_t strides[3]; uint32_t box[4]; int rank;
+    const void* base; uint64_t dims[4]; uint64_t strides[3]; uint32_t box[4]; uint32_t es[4]; int rank;
     bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
 };
 struct MapKeyHash {
@@ -493,16 +496,16 @@ static std::mutex g_map_mutex;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
 
 static int cached_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box) {
+                      const uint32_t* box, const uint32_t* elem_strides = nullptr) {
     MapKey k;
     memset(&k, 0, sizeof(k));
     k.base = base; k.rank = rank;
-    for (int i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; }
+    for (int i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; k.es[i] = elem_strides ? elem_strides[i] : 1; }
     for (int i = 0; i + 1 < rank; ++i) k.strides[i] = strides_bytes[i];
     std::lock_guard<std::mutex> lock(g_map_mutex);
     auto it = g_map_cache.find(k);
     if (it != g_map_cache.end()) { *map = it->second; return SSD_OK; }
-    int rc = make_map(map, base, rank, dims, strides_bytes, box);
+    int rc = make_map(map, base, rank, dims, strides_bytes, box, elem_strides);
     if (rc == SSD_OK) {
         if (g_map_cache.size() > 4096) g_map_cache.clear();
         g_map_cache.emplace(k, *map);
@@ -533,7 +536,7 @@ static int partial_workspace(size_t bytes, float** out) {
 }
 
 bool conv_tcgen05_supported(const ssd_conv_desc* d) {
-    return d->stride == 1 && d->Cin % 8 == 0 && d->KH == d->KW && d->KH * d->KW <= 49 &&
+    return (d->stride == 1 || d->stride == 2) && d->Cin % 8 == 0 && d->KH == d->KW && d->KH * d->KW <= 49 &&
            (reinterpret_cast<uintptr_t>(d->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0;
 }
 
@@ -541,7 +544,8 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
     TcParams p;
     memset(&p, 0, sizeof(p));
     const int taps = d->KH * d->KW;
-    p.mode4d = !(taps == 1 && d->pad_top == 0 && d->pad_left == 0 && d->Ho == d->H && d->Wo == d->W);
+    p.mode4d = !(taps == 1 && d->stride == 1 && d->pad_top == 0 && d->pad_left == 0 && d->Ho == d->H && d->Wo == d->W);
+    p.stride = d->stride;
     p.B = d->B; p.Ho = d->Ho; p.Wo = d->Wo; p.HoWo = d->Ho * d->Wo; p.M = d->B * p.HoWo;
     p.Cin = d->Cin; p.KW = d->KW; p.dil = d->dilation; p.pad_t = d->pad_top; p.pad_l = d->pad_left;
     p.kb_per_tap = (d->Cin + TC_BK - 1) / TC_BK;
@@ -576,9 +580,10 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
     } else {
         // choose the output-pixel box (bw x bh x bb <= 128) that wastes the fewest MMA rows
         double best = -1.0;
-        for (int bw = 1; bw <= min(d->Wo, TC_BM); ++bw) {
+        const int max_bw = d->stride == 1 ? TC_BM : 256 / d->stride;          // TMA box dimensions are limited to 256 elements
+        for (int bw = 1; bw <= min(d->Wo, min(TC_BM, max_bw)); ++bw) {
             const int tw = (d->Wo + bw - 1) / bw;
-            for (int bh = 1; bh <= min(d->Ho, TC_BM / bw); ++bh) {
+            for (int bh = 1; bh <= min(d->Ho, min(TC_BM / bw, max_bw)); ++bh) {
                 const int th = (d->Ho + bh - 1) / bh;
                 int bb = 1;
                 if (bw == d->Wo && bh == d->Ho) bb = max(1, min(d->B, TC_BM / (bw * bh)));
@@ -590,8 +595,10 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
         tiles_m = p.tiles_w * p.tiles_h * ((d->B + p.bb - 1) / p.bb);
         uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
         uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
-        uint32_t box[4] = {TC_BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bb};
-        int rc = cached_map(&map_a, d->in, 4, dims, str, box);
+        const uint32_t sst = (uint32_t)d->stride;
+        uint32_t box[4] = {TC_BK, (uint32_t)p.bw * sst, (uint32_t)p.bh * sst, (uint32_t)p.bb};
+        uint32_t est[4] = {1, sst, sst, 1};
+        int rc = cached_map(&map_a, d->in, 4, dims, str, box, est);
         if (rc) return rc;
         p.a_bytes = (uint32_t)(p.bw * p.bh * p.bb) * TC_BK * 2;
     }
