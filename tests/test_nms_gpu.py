@@ -62,7 +62,8 @@ def test_decoder_fused_softmax_and_softmax_kernel():
     _check_decode(priors, deltas, _np(probs))
 
 
-def test_decoder_integer_ties():
+@pytest.mark.parametrize("n_cls", [4, 12])       # ~100 candidates per class (candidate-by-candidate loop) / ~33 (bit-mask path)
+def test_decoder_integer_ties(n_cls):
     """Equal scores and IoU exactly at 0.5: order must follow the documented
     oracle rule (score desc, class asc, anchor asc); suppression is strict >."""
     rng = np.random.default_rng(12)
@@ -73,11 +74,11 @@ def test_decoder_integer_ties():
     priors = (np.stack([y1, x1, y1 + h, x1 + w], -1) / k).astype(np.float32)
     deltas = np.zeros((3, N, 4), np.float32)                       # exp(0) exact -> boxes exact
     levels = np.array([0.55, 0.6, 0.75, 0.9], np.float32)
-    cls = rng.integers(0, 4, (3, N))
+    cls = rng.integers(0, n_cls, (3, N))
     sc = levels[rng.integers(0, 4, (3, N))]
-    probs = np.zeros((3, N, 4), np.float32)
+    probs = np.zeros((3, N, n_cls), np.float32)
     np.put_along_axis(probs, cls[..., None], sc[..., None], axis=2)
-    rest = (1 - sc) / 3
+    rest = (1 - sc) / (n_cls - 1)
     probs = np.where(probs == 0, rest[..., None], probs).astype(np.float32)
     from tf_ssd_b200.models.decoder import SSDDecoder
     dec = SSDDecoder(priors, [1., 1., 1., 1.], max_total_size=50)
