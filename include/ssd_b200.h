@@ -213,6 +213,21 @@ int ssd_depthwise3x3(const void* d_in, const void* d_weight, const float* d_bias
                      int B, int H, int W, int C, int Ho, int Wo, int stride, int pad_top, int pad_left,
                      int act, ssd_stream_t stream);
 
+/* The tail of a MobileNetV2 inverted-residual block (keras_applications mobilenet_v2._inverted_res_block under
+ * models/ssd_mobilenet_v2.py:25) as ONE launch: DepthwiseConv2D 3x3 (+ folded BN + dw_act) -> 1x1 Conv2D (+ folded
+ * BN + act, + residual).  The depthwise output is produced in shared memory as the tensor-core operand and never
+ * written to global memory.  in [B,H,W,C] fp16, dw_weight [3,3,C] fp16, dw_bias [C] fp32 (may be NULL),
+ * proj_weight [Cout,C] fp16, proj_bias [Cout] fp32 (may be NULL), residual / out [B,Ho,Wo,Cout] fp16.
+ * C % 8 == 0, Cout % 8 == 0, Cout <= 256, stride 1 or 2; returns SSD_ERR_UNSUPPORTED otherwise. */
+typedef struct ssd_dwproj_desc {
+    const void* in; const void* dw_weight; const float* dw_bias;
+    const void* proj_weight; const float* proj_bias; const void* residual; void* out;
+    int32_t B, H, W, C, Ho, Wo, Cout;
+    int32_t stride, pad_top, pad_left, dw_act, act;
+    int32_t reserved;
+} ssd_dwproj_desc;
+int ssd_dwproj(const ssd_dwproj_desc* h_desc, ssd_stream_t stream);
+
 /* MobileNetV2 stem: keras_applications Conv1_pad + Conv1 (3x3, stride 2, Cin = 3) + bn_Conv1 +
  * Conv1_relu (models/ssd_mobilenet_v2.py:25), computed straight from the fp32 NHWC image
  * [B,H,W,3] (the fp32->fp16 input rounding of the pipeline is fused in).

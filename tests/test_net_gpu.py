@@ -228,6 +228,21 @@ def test_every_layer_in_situ(backbone, B):
             y = F.conv2d(F.pad(x, (pl, pr, pt, pb)), w, f32(mt["bias"]), stride=mt["stride"], groups=w.shape[0])
             y = torch.clamp(y, 0, 6).permute(0, 2, 3, 1).numpy()
             assert _rel(f32(mt["out"]).numpy(), y) < 2e-3, s.name
+        elif s.kind == "dwproj":
+            # fused depthwise 3x3 (+ bias + ReLU6, rounded to fp16 like the operand tile) -> 1x1 conv (+ bias, residual)
+            x = f32(mt["x"]).permute(0, 3, 1, 2)
+            wd = f32(mt["dw_w"]).permute(2, 0, 1).unsqueeze(1)
+            (pt, pb), (pl, pr) = mt["dw_ph"], mt["dw_pw"]
+            h = F.conv2d(F.pad(x, (pl, pr, pt, pb)), wd, f32(mt["dw_bias"]), stride=mt["dw_stride"], groups=wd.shape[0])
+            h = torch.clamp(h, 0, 6).half().float()
+            w = f32(mt["w"]).permute(0, 3, 1, 2)
+            y = F.conv2d(h, w, f32(mt["bias"]))
+            y = torch.relu(y) if mt["act"] == 1 else torch.clamp(y, 0, 6) if mt["act"] == 2 else y
+            y = y.permute(0, 2, 3, 1)
+            if mt["res"] is not None:
+                y = y + f32(mt["res"])
+            assert y.shape[1:3] == (mt["Ho"], mt["Wo"])
+            assert _rel(f32(mt["out0"]).numpy(), y.numpy()) < 2e-3, f"{s.name}: {_rel(f32(mt['out0']).numpy(), y.numpy())}"
         elif s.kind == "pool":
             x = f32(mt["x"]).permute(0, 3, 1, 2)
             (pt, pb), (pl, pr) = mt["ph"], mt["pw"]

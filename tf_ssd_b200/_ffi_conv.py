@@ -23,6 +23,16 @@ class ConvDesc(C.Structure):
     ]
 
 
+class DwProjDesc(C.Structure):
+    """``struct ssd_dwproj_desc`` (include/ssd_b200.h)."""
+    _fields_ = [
+        ("inp", vp), ("dw_weight", vp), ("dw_bias", vp), ("proj_weight", vp), ("proj_bias", vp), ("residual", vp), ("out", vp),
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("Ho", C.c_int32), ("Wo", C.c_int32),
+        ("Cout", C.c_int32), ("stride", C.c_int32), ("pad_top", C.c_int32), ("pad_left", C.c_int32),
+        ("dw_act", C.c_int32), ("act", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
 class AdamVar(C.Structure):
     """``struct ssd_adam_var`` (include/ssd_b200.h)."""
     _fields_ = [("w", vp), ("m", vp), ("v", vp), ("grad", vp), ("w16", vp), ("n", i64), ("l2", f), ("reserved", f)]
@@ -31,6 +41,7 @@ class AdamVar(C.Structure):
 SIGNATURES = {
     "ssd_conv2d": (i, [C.POINTER(ConvDesc), vp]),
     "ssd_depthwise3x3": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),
+    "ssd_dwproj": (i, [C.POINTER(DwProjDesc), vp]),
     "ssd_stem_conv3x3s2": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
     "ssd_image_to_f16c8": (i, [vp, vp, i64, vp]),
     "ssd_maxpool": (i, [vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),

@@ -258,6 +258,8 @@ static int launch_conv(const ConvK& k, cudaStream_t st) {
 
 // conv_tcgen05.cu
 bool conv_tcgen05_supported(const ssd_conv_desc* d);
+bool conv_dwproj_supported(const ssd_dwproj_desc* d);
+int  conv_dwproj_launch(const ssd_dwproj_desc* d, cudaStream_t st);
 int  conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st);
 
 // SSD_B200_CONV=legacy forces the mma.sync kernel for every convolution (A/B measurements, cross-checks).
@@ -315,4 +317,16 @@ extern "C" int ssd_conv2d(const ssd_conv_desc* d, ssd_stream_t stream) {
         if (tiles64 >= sms) return launch_conv<128, 64, 4, 2>(k, st);
         return launch_conv<64, 64, 2, 4>(k, st);
     }
+}
+
+extern "C" int ssd_dwproj(const ssd_dwproj_desc* d, ssd_stream_t stream) {
+    SSD_REQUIRE_PTR(d);
+    SSD_REQUIRE_PTR(d->in); SSD_REQUIRE_PTR(d->dw_weight); SSD_REQUIRE_PTR(d->proj_weight); SSD_REQUIRE_PTR(d->out);
+    SSD_REQUIRE(d->B >= 1 && d->H >= 1 && d->W >= 1 && d->C >= 8 && d->Ho >= 1 && d->Wo >= 1 && d->Cout >= 8 &&
+                d->dw_act >= SSD_ACT_NONE && d->dw_act <= SSD_ACT_RELU6 && d->act >= SSD_ACT_NONE && d->act <= SSD_ACT_RELU6,
+                SSD_ERR_SHAPE, "ssd_dwproj: bad shape B=%d H=%d W=%d C=%d Ho=%d Wo=%d Cout=%d", d->B, d->H, d->W, d->C, d->Ho,
+                d->Wo, d->Cout);
+    SSD_REQUIRE(ssd::conv_dwproj_supported(d), SSD_ERR_UNSUPPORTED,
+                "ssd_dwproj: unsupported configuration (C %% 8, Cout %% 8, Cout <= 256, stride 1|2, 16-byte aligned pointers)");
+    return ssd::conv_dwproj_launch(d, as_stream(stream));
 }

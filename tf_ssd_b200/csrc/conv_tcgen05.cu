@@ -43,6 +43,8 @@ constexpr int TC_BK = 64;            // 64 fp16 = 128 B = one swizzle row
 constexpr int TC_STAGES = 4;
 constexpr int TC_EPI_WARPS = 8;      // two warps per TMEM lane quarter (they split the column chunks)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..9: epilogue
+constexpr int TC_DW_WARPS = 8;       // fused depthwise -> 1x1: warps 10..17 compute the A operand (depthwise output)
+constexpr int TC_THREADS_DW = TC_THREADS + 32 * TC_DW_WARPS;
 constexpr int TC_CHUNK = 32;         // epilogue column chunk per warp (fp16: 64 B per row)
 constexpr int TC_OUT_TILE = TC_BM * 128;             // one output staging tile: 128 rows x 64 fp16 channels, 128B-swizzled
 constexpr int TC_OUT_BYTES = 2 * TC_OUT_TILE + 256 * 4;   // two tiles (double buffer) + the N tile's bias values
@@ -71,6 +73,9 @@ struct TcParams {
     int splits, ldp;
     int tma_store;                   // fp16 single-segment output written with TMA stores (map_o is valid)
     int stages;                      // operand ring depth (2..TC_STAGES): shallow-K layers trade depth for 2 CTAs per SM
+    // fused depthwise 3x3 (+ bias + activation) producing the A operand of a 1x1 convolution (DW kernel variant)
+    const uint4* dw_x; const uint4* dw_w; const float* dw_bias;
+    int dw_H, dw_W, dw_C8, dw_stride, dw_pad_t, dw_pad_l, dw_act;
 };
 
 // ------------------------------------------------------------------ PTX glue --
@@ -207,9 +212,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2)     // <= 102 registers: two CTAs may share an SM (shallow-K layers)
-conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const __grid_constant__ CUtensorMap map_o, const TcParams p) {
+template <bool DW>                                   // DW: the A operand is computed in-kernel (depthwise 3x3), not loaded
+__device__ __forceinline__ void conv_tcgen05_body(const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap& map_o,
+                                                  const TcParams& p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 1024-byte alignment for the 128-byte swizzle atoms
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -233,7 +238,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         tma_prefetch_desc(&map_b);
         if (p.tma_store) tma_prefetch_desc(&map_o);
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, 1);                      // one arrive.expect_tx (+ TMA bytes)
+            mbar_init(bar_full + 8 * s, DW ? 1 + TC_DW_WARPS : 1);   // one arrive.expect_tx (+ TMA bytes) [+ the depthwise warps]
             mbar_init(bar_empty + 8 * s, 1);                     // one tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
@@ -272,9 +277,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     if (it >= p.stages) mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                     const int tap = kb / p.kb_per_tap, c0 = (kb - tap * p.kb_per_tap) * TC_BK;
-                    mbar_expect_tx(bar_full + 8 * s, p.a_bytes + p.b_bytes);
+                    mbar_expect_tx(bar_full + 8 * s, DW ? p.b_bytes : p.a_bytes + p.b_bytes);
                     const uint32_t dst_a = smem_addr(sA + (size_t)s * a_stage), dst_b = smem_addr(sB + (size_t)s * b_stage);
-                    if (p.mode4d) {
+                    if (DW) {
+                        // the depthwise warps write this stage's A tile
+                    } else if (p.mode4d) {
                         const int ky = tap / p.KW, kx = tap - ky * p.KW;
                         // strided convolutions: the tensor map traverses W and H with element stride = conv stride,
                         // so the box still lands as bw x bh output pixels
@@ -312,6 +319,94 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
                 umma_commit(bar_tfull + 8 * a);                  // accumulator complete
+            }
+        }
+    } else if (DW && warp >= 2 + TC_EPI_WARPS) {
+        // ===================== depthwise 3x3 producers (8 warps): A tile = act(dw(x) + bias) =====================
+        // Thread -> (16-byte channel chunk j of the 64-channel k-block, tile rows r0 + 32 i): 8 consecutive threads
+        // read 128 contiguous bytes of one input pixel.  The result goes straight into the 128-byte-swizzled K-major
+        // layout the UMMA descriptor expects (what TMA would have written), so the expanded activation is read once
+        // and the depthwise output never exists in global memory.
+        const int pt = (int)threadIdx.x - 32 * (2 + TC_EPI_WARPS);
+        const int j = pt & 7, r0 = pt >> 3;
+        const int C8 = p.dw_C8, Hi = p.dw_H, Wi = p.dw_W, st = p.dw_stride;
+        const float lo = p.dw_act == SSD_ACT_NONE ? -__int_as_float(0x7f800000) : 0.0f;
+        const float hi = p.dw_act == SSD_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
+        int it = 0, s = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+            const int tm_ = t / p.tiles_n;
+            int pb[4], py[4], px[4];
+            bool ok[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int m = tm_ * TC_BM + r0 + 32 * i;
+                ok[i] = m < p.M;
+                const int mm = ok[i] ? m : 0;
+                pb[i] = mm / p.HoWo;
+                const int pix = mm - pb[i] * p.HoWo;
+                py[i] = (pix / p.Wo) * st - p.dw_pad_t;
+                px[i] = (pix - (pix / p.Wo) * p.Wo) * st - p.dw_pad_l;
+            }
+            for (int kb = 0; kb < p.n_kblocks; ++kb, ++it) {
+                const int c8 = kb * 8 + j;
+                const bool cok = c8 < C8;
+                float bias8[8];
+                {
+                    const float4 b0 = (cok && p.dw_bias) ? __ldg(reinterpret_cast<const float4*>(p.dw_bias) + c8 * 2) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 b1 = (cok && p.dw_bias) ? __ldg(reinterpret_cast<const float4*>(p.dw_bias) + c8 * 2 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
+                    bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
+                }
+                if (it >= p.stages) mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                unsigned char* a_tile = sA + (size_t)s * a_stage;
+                const uint4* wk = p.dw_w + (cok ? c8 : 0);
+#pragma unroll
+                for (int hp = 0; hp < 2; ++hp) {                 // two passes of two tile rows: bounded register footprint
+                    float acc[2][8];
+#pragma unroll
+                    for (int q2 = 0; q2 < 2; ++q2)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[q2][e] = bias8[e];
+                    const uint4* img0 = p.dw_x + (size_t)pb[2 * hp] * Hi * Wi * C8 + (cok ? c8 : 0);
+                    const uint4* img1 = p.dw_x + (size_t)pb[2 * hp + 1] * Hi * Wi * C8 + (cok ? c8 : 0);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        const uint4 wv = __ldg(wk + (size_t)tap * C8);
+                        const int iy0 = py[2 * hp] + ky, ix0 = px[2 * hp] + kx;
+                        const int iy1 = py[2 * hp + 1] + ky, ix1 = px[2 * hp + 1] + kx;
+                        const bool v0 = cok && ok[2 * hp] && (unsigned)iy0 < (unsigned)Hi && (unsigned)ix0 < (unsigned)Wi;
+                        const bool v1 = cok && ok[2 * hp + 1] && (unsigned)iy1 < (unsigned)Hi && (unsigned)ix1 < (unsigned)Wi;
+                        const uint4 x0 = v0 ? __ldg(img0 + ((size_t)iy0 * Wi + ix0) * C8) : make_uint4(0u, 0u, 0u, 0u);
+                        const uint4 x1 = v1 ? __ldg(img1 + ((size_t)iy1 * Wi + ix1) * C8) : make_uint4(0u, 0u, 0u, 0u);
+                        const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+                        const __half2* xh0 = reinterpret_cast<const __half2*>(&x0);
+                        const __half2* xh1 = reinterpret_cast<const __half2*>(&x1);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 wf = __half22float2(wh[e]), f0 = __half22float2(xh0[e]), f1 = __half22float2(xh1[e]);
+                            acc[0][2 * e] = fmaf(f0.x, wf.x, acc[0][2 * e]); acc[0][2 * e + 1] = fmaf(f0.y, wf.y, acc[0][2 * e + 1]);
+                            acc[1][2 * e] = fmaf(f1.x, wf.x, acc[1][2 * e]); acc[1][2 * e + 1] = fmaf(f1.y, wf.y, acc[1][2 * e + 1]);
+                        }
+                    }
+#pragma unroll
+                    for (int q2 = 0; q2 < 2; ++q2) {
+                        const int i = 2 * hp + q2, r = r0 + 32 * i;
+                        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                        if (cok && ok[i]) {
+                            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                oh[e] = __floats2half2_rn(fminf(fmaxf(acc[q2][2 * e], lo), hi), fminf(fmaxf(acc[q2][2 * e + 1], lo), hi));
+                        }
+                        *reinterpret_cast<uint4*>(a_tile + r * 128 + ((j ^ (r & 7)) << 4)) = o;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full + 8 * s);
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else {
@@ -432,6 +527,17 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2)     // <= 102 registers: two CTAs may share an SM (shallow-K layers)
+conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_o, const __grid_constant__ TcParams p) {
+    conv_tcgen05_body<false>(map_a, map_b, map_o, p);
+}
+__global__ void __maxnreg__(112)                                      // one CTA per SM: 18 warps x 112 registers
+conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_o,
+                           const __grid_constant__ TcParams p) {
+    conv_tcgen05_body<true>(map_b, map_b, map_o, p);
 }
 
 // Deterministic split-K reduction + epilogue: partial[z][row][n] summed for z = 0..splits-1 in order.
@@ -691,6 +797,75 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
         cudaError_t le = launch_pdl(conv_splitk_reduce_kernel, dim3(blocks), dim3(256), 0, st, p, rows_total);
         if (le != cudaSuccess) return cuda_fail(le, "conv_splitk_reduce_kernel");
     }
+    return SSD_OK;
+}
+
+// Fused DepthwiseConv2D 3x3 (+ folded BN + activation) -> 1x1 Conv2D (+ folded BN, residual): the "depthwise ->
+// project" tail of a MobileNetV2 inverted-residual block as ONE launch.  GEMM view: M = B*Ho*Wo pixels,
+// K = C (expanded channels, computed on the fly by the depthwise warps), N = Cout <= 256.
+bool conv_dwproj_supported(const ssd_dwproj_desc* d) {
+    return d->C % 8 == 0 && d->Cout % 8 == 0 && d->Cout <= 256 && (d->stride == 1 || d->stride == 2) &&
+           (reinterpret_cast<uintptr_t>(d->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->dw_weight) & 15) == 0 &&
+           (reinterpret_cast<uintptr_t>(d->proj_weight) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 &&
+           (d->residual == nullptr || (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0) &&
+           (d->dw_bias == nullptr || (reinterpret_cast<uintptr_t>(d->dw_bias) & 15) == 0);
+}
+
+int conv_dwproj_launch(const ssd_dwproj_desc* d, cudaStream_t st) {
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.mode4d = 0;
+    p.B = d->B; p.Ho = d->Ho; p.Wo = d->Wo; p.HoWo = d->Ho * d->Wo; p.M = d->B * p.HoWo;
+    p.Cin = d->C; p.KW = 1; p.dil = 1; p.stride = 1;
+    p.kb_per_tap = (d->C + TC_BK - 1) / TC_BK;
+    p.n_kblocks = p.kb_per_tap;
+    p.kb_per_split = p.n_kblocks;
+    p.Cout = d->Cout;
+    p.bias = d->proj_bias; p.res = (const __half*)d->residual; p.out0 = d->out; p.out1 = nullptr;
+    p.act = d->act; p.out_f32 = 0; p.split = d->Cout;
+    p.pix0 = d->Cout; p.img0 = (long long)p.HoWo * d->Cout;
+    p.BN = (d->Cout + 15) / 16 * 16;
+    p.acc_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+    p.tmem_cols = 2 * p.acc_cols;
+    p.idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    p.dw_x = reinterpret_cast<const uint4*>(d->in); p.dw_w = reinterpret_cast<const uint4*>(d->dw_weight); p.dw_bias = d->dw_bias;
+    p.dw_H = d->H; p.dw_W = d->W; p.dw_C8 = d->C / 8; p.dw_stride = d->stride; p.dw_pad_t = d->pad_top; p.dw_pad_l = d->pad_left;
+    p.dw_act = d->dw_act;
+
+    CUtensorMap map_b, map_o;
+    {
+        uint64_t dims[2] = {(uint64_t)d->C, (uint64_t)d->Cout};
+        uint64_t str[1] = {(uint64_t)d->C * 2};
+        uint32_t box[2] = {TC_BK, (uint32_t)p.BN};
+        int rc = cached_map(&map_b, d->proj_weight, 2, dims, str, box);
+        if (rc) return rc;
+        p.b_bytes = (uint32_t)p.BN * TC_BK * 2;
+        p.a_bytes = 0;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)d->Cout, (uint64_t)p.M};
+        uint64_t str[1] = {(uint64_t)d->Cout * 2};
+        uint32_t box[2] = {64, TC_BM};
+        int rc = cached_map(&map_o, d->out, 2, dims, str, box);
+        if (rc) return rc;
+        p.tma_store = 1;
+    }
+    p.splits = 1;
+    p.tiles_m = (p.M + TC_BM - 1) / TC_BM; p.tiles_n = 1; p.n_tiles = p.tiles_m;
+    p.stages = min(TC_STAGES, max(2, p.n_kblocks));
+    const size_t smem = (size_t)p.stages * (TC_BM * TC_BK * 2 + (size_t)p.BN * TC_BK * 2) + (size_t)TC_OUT_BYTES +
+                        (2 * TC_STAGES + 4) * 8 + 16 + 1024;
+    static thread_local int attr_dev = -1;
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (attr_dev != cur_dev) {
+        cudaError_t e = cudaFuncSetAttribute(conv_dwproj_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "conv_dwproj: cudaFuncSetAttribute");
+        attr_dev = cur_dev;
+    }
+    dim3 grid(min(p.n_tiles, sm_count()), 1, 1);
+    cudaError_t le = launch_pdl(conv_dwproj_tcgen05_kernel, grid, dim3(TC_THREADS_DW), smem, st, map_b, map_o, p);
+    if (le != cudaSuccess) return cuda_fail(le, "conv_tcgen05_kernel<dw>");
     return SSD_OK;
 }
 

@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -27,7 +28,7 @@ import numpy as np
 import torch
 
 from tf_ssd_b200 import _ffi
-from tf_ssd_b200._ffi_conv import ACT_NONE, ACT_RELU, ACT_RELU6, ConvDesc
+from tf_ssd_b200._ffi_conv import ACT_NONE, ACT_RELU, ACT_RELU6, ConvDesc, DwProjDesc
 
 BN_EPS = 1e-3        # keras_applications.mobilenet_v2: BatchNormalization(epsilon=1e-3, momentum=0.999)
 
@@ -248,6 +249,8 @@ class Plan:
 
 
 class _PlanBuilder:
+    FUSE_DW = os.environ.get("SSD_B200_FUSE_DW", "1") != "0"      # depthwise + 1x1 projection as one launch (ssd_dwproj)
+
     def __init__(self, model: "SSDModel", B: int):
         self.m = model
         self.B = B
@@ -322,6 +325,29 @@ class _PlanBuilder:
         Ho, Wo = _out_size(x.H, k, stride, dilation, ph), _out_size(x.W, k, stride, dilation, pw)
         out = self._buf(Ho, Wo, cout)
         real_cin = self.m.weights[name + "/kernel"].shape[2]
+        last = self.plan.steps[-1] if self.plan.steps else None
+        if (self.FUSE_DW and last is not None and last.kind == "dw" and last.meta["out"] is x.t and k == 1 and stride == 1
+                and dilation == 1 and cout <= 256 and cout % 8 == 0 and type(self) is _PlanBuilder):
+            # depthwise 3x3 -> 1x1 projection as ONE launch (ssd_dwproj): the depthwise output stays on chip
+            self.plan.steps.pop()
+            dm = last.meta
+            d = DwProjDesc()
+            d.inp, d.dw_weight, d.dw_bias = dm["x"].data_ptr(), dm["w"].data_ptr(), dm["bias"].data_ptr()
+            d.proj_weight, d.proj_bias = w.data_ptr(), b.data_ptr()
+            d.residual = residual.t.data_ptr() if residual is not None else None
+            d.out = out.data_ptr()
+            d.B, d.H, d.W, d.C = self.B, dm["x"].shape[1], dm["x"].shape[2], x.C
+            d.Ho, d.Wo, d.Cout = Ho, Wo, cout
+            d.stride, d.pad_top, d.pad_left, d.dw_act, d.act = dm["stride"], dm["ph"][0], dm["pw"][0], dm["act"], act
+            nbytes = self.B * dm["x"].shape[1] * dm["x"].shape[2] * x.C * 2 + 9 * x.C * 2 + x.C * cout * 2 + \
+                self.B * Ho * Wo * cout * 2 * (2 if residual is not None else 1)
+            flops = 2.0 * self.B * Ho * Wo * x.C * (9 + cout)
+            meta = dict(x=dm["x"], dw_w=dm["w"], dw_bias=dm["bias"], dw_stride=dm["stride"], dw_ph=dm["ph"], dw_pw=dm["pw"],
+                        dw_act=dm["act"], w=w, bias=b, res=residual.t if residual is not None else None, out0=out, act=act,
+                        Ho=Ho, Wo=Wo, cout=cout, dw_name=last.name)
+            self.plan.steps.append(Step(name, "dwproj", self.lib.ssd_dwproj, (C.byref(d),), flops, nbytes,
+                                        (d, w, b, dm["x"], dm["w"], dm["bias"], out), meta))
+            return Act(out, Ho, Wo, cout)
         self._emit_conv(name, x, w, b, cout, k, stride, dilation, ph, pw, act, residual, out, real_cin=real_cin)
         return Act(out, Ho, Wo, cout)
 
