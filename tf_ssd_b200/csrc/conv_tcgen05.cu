@@ -43,7 +43,9 @@ constexpr int TC_BK = 64;            // 64 fp16 = 128 B = one swizzle row
 constexpr int TC_STAGES = 4;
 constexpr int TC_EPI_WARPS = 8;      // two warps per TMEM lane quarter (they split the column chunks)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..9: epilogue
-constexpr int TC_DW_WARPS = 8;       // fused depthwise -> 1x1: warps 10..17 compute the A operand (depthwise output)
+constexpr int TC_DW_WARPS = 6;       // fused depthwise -> 1x1: warps 10..15 compute the A operand (16 warps: the register
+                                     // file is allocated in groups of 4 warps, so 18 warps would cap at 96 registers)
+constexpr int TC_DW_ROWS = (TC_BM + 4 * TC_DW_WARPS - 1) / (4 * TC_DW_WARPS);   // tile rows per producer thread (6)
 constexpr int TC_THREADS_DW = TC_THREADS + 32 * TC_DW_WARPS;
 constexpr int TC_CHUNK = 32;         // epilogue column chunk per warp (fp16: 64 B per row)
 constexpr int TC_OUT_TILE = TC_BM * 128;             // one output staging tile: 128 rows x 64 fp16 channels, 128B-swizzled
@@ -336,12 +338,13 @@ __device__ __forceinline__ void conv_tcgen05_body(const CUtensorMap& map_a, cons
         uint32_t ph = 0;
         for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
             const int tm_ = t / p.tiles_n;
-            int pb[4], py[4], px[4];
-            bool ok[4];
+            int pb[TC_DW_ROWS], py[TC_DW_ROWS], px[TC_DW_ROWS];
+            bool ok[TC_DW_ROWS];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int m = tm_ * TC_BM + r0 + 32 * i;
-                ok[i] = m < p.M;
+            for (int i = 0; i < TC_DW_ROWS; ++i) {
+                const int r = r0 + 4 * TC_DW_WARPS * i;
+                const int m = tm_ * TC_BM + r;
+                ok[i] = r < TC_BM && m < p.M;
                 const int mm = ok[i] ? m : 0;
                 pb[i] = mm / p.HoWo;
                 const int pix = mm - pb[i] * p.HoWo;
@@ -362,7 +365,7 @@ __device__ __forceinline__ void conv_tcgen05_body(const CUtensorMap& map_a, cons
                 unsigned char* a_tile = sA + (size_t)s * a_stage;
                 const uint4* wk = p.dw_w + (cok ? c8 : 0);
 #pragma unroll
-                for (int hp = 0; hp < 2; ++hp) {                 // two passes of two tile rows: bounded register footprint
+                for (int hp = 0; hp < TC_DW_ROWS / 2; ++hp) {    // passes of two tile rows: bounded register footprint
                     float acc[2][8];
 #pragma unroll
                     for (int q2 = 0; q2 < 2; ++q2)
@@ -392,7 +395,8 @@ __device__ __forceinline__ void conv_tcgen05_body(const CUtensorMap& map_a, cons
                     }
 #pragma unroll
                     for (int q2 = 0; q2 < 2; ++q2) {
-                        const int i = 2 * hp + q2, r = r0 + 32 * i;
+                        const int i = 2 * hp + q2, r = r0 + 4 * TC_DW_WARPS * i;
+                        if (r >= TC_BM) continue;
                         uint4 o = make_uint4(0u, 0u, 0u, 0u);
                         if (cok && ok[i]) {
                             __half2* oh = reinterpret_cast<__half2*>(&o);
@@ -534,7 +538,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const __grid_constant__ CUtensorMap map_o, const __grid_constant__ TcParams p) {
     conv_tcgen05_body<false>(map_a, map_b, map_o, p);
 }
-__global__ void __maxnreg__(112)                                      // one CTA per SM: 18 warps x 112 registers
+__global__ void __launch_bounds__(TC_THREADS_DW, 1)                   // one CTA per SM: 16 warps x <= 128 registers
 conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_o,
                            const __grid_constant__ TcParams p) {
     conv_tcgen05_body<true>(map_b, map_b, map_o, p);

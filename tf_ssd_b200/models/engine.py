@@ -249,7 +249,8 @@ class Plan:
 
 
 class _PlanBuilder:
-    FUSE_DW = os.environ.get("SSD_B200_FUSE_DW", "1") != "0"      # depthwise + 1x1 projection as one launch (ssd_dwproj)
+    # depthwise + 1x1 projection as one launch (ssd_dwproj); opt-in until the fused kernel beats the two launches
+    FUSE_DW = os.environ.get("SSD_B200_FUSE_DW", "0") == "1"
 
     def __init__(self, model: "SSDModel", B: int):
         self.m = model
