@@ -227,6 +227,8 @@ typedef struct ssd_dwproj_desc {
     int32_t reserved;
 } ssd_dwproj_desc;
 int ssd_dwproj(const ssd_dwproj_desc* h_desc, ssd_stream_t stream);
+/* 1 when ssd_dwproj can run this configuration (shape limits, alignment, a tile geometry that fits shared memory). */
+int ssd_dwproj_supported(const ssd_dwproj_desc* h_desc);
 
 /* MobileNetV2 stem: keras_applications Conv1_pad + Conv1 (3x3, stride 2, Cin = 3) + bn_Conv1 +
  * Conv1_relu (models/ssd_mobilenet_v2.py:25), computed straight from the fp32 NHWC image

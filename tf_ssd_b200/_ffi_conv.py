@@ -42,6 +42,7 @@ SIGNATURES = {
     "ssd_conv2d": (i, [C.POINTER(ConvDesc), vp]),
     "ssd_depthwise3x3": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),
     "ssd_dwproj": (i, [C.POINTER(DwProjDesc), vp]),
+    "ssd_dwproj_supported": (i, [C.POINTER(DwProjDesc)]),
     "ssd_stem_conv3x3s2": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
     "ssd_image_to_f16c8": (i, [vp, vp, i64, vp]),
     "ssd_maxpool": (i, [vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),

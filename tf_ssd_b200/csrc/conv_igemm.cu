@@ -330,3 +330,8 @@ extern "C" int ssd_dwproj(const ssd_dwproj_desc* d, ssd_stream_t stream) {
                 "ssd_dwproj: unsupported configuration (C %% 8, Cout %% 8, Cout <= 256, stride 1|2, 16-byte aligned pointers)");
     return ssd::conv_dwproj_launch(d, as_stream(stream));
 }
+
+extern "C" int ssd_dwproj_supported(const ssd_dwproj_desc* d) {
+    if (d == nullptr || d->in == nullptr || d->dw_weight == nullptr || d->proj_weight == nullptr || d->out == nullptr) return 0;
+    return ssd::conv_dwproj_supported(d) ? 1 : 0;
+}

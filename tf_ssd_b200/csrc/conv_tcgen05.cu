@@ -43,10 +43,10 @@ constexpr int TC_BK = 64;            // 64 fp16 = 128 B = one swizzle row
 constexpr int TC_STAGES = 4;
 constexpr int TC_EPI_WARPS = 8;      // two warps per TMEM lane quarter (they split the column chunks)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..9: epilogue
-constexpr int TC_DW_WARPS = 6;       // fused depthwise -> 1x1: warps 10..15 compute the A operand (16 warps: the register
-                                     // file is allocated in groups of 4 warps, so 18 warps would cap at 96 registers)
-constexpr int TC_DW_ROWS = (TC_BM + 4 * TC_DW_WARPS - 1) / (4 * TC_DW_WARPS);   // tile rows per producer thread (6)
+constexpr int TC_DW_WARPS = 10;      // fused depthwise -> 1x1: warps 10..19 compute the A operand (20 warps, <= 96 registers)
+constexpr int TC_DW_ROWS = (TC_BM + 4 * TC_DW_WARPS - 1) / (4 * TC_DW_WARPS);   // tile rows per depthwise thread (4)
 constexpr int TC_THREADS_DW = TC_THREADS + 32 * TC_DW_WARPS;
+constexpr int TC_DW_ASTAGES = 2;     // (A, B) operand ring of the fused kernel
 constexpr int TC_CHUNK = 32;         // epilogue column chunk per warp (fp16: 64 B per row)
 constexpr int TC_OUT_TILE = TC_BM * 128;             // one output staging tile: 128 rows x 64 fp16 channels, 128B-swizzled
 constexpr int TC_OUT_BYTES = 2 * TC_OUT_TILE + 256 * 4;   // two tiles (double buffer) + the N tile's bias values
@@ -78,6 +78,10 @@ struct TcParams {
     // fused depthwise 3x3 (+ bias + activation) producing the A operand of a 1x1 convolution (DW kernel variant)
     const uint4* dw_x; const uint4* dw_w; const float* dw_bias;
     int dw_H, dw_W, dw_C8, dw_stride, dw_pad_t, dw_pad_l, dw_act;
+    int dw_pw, dw_ph;                // input patch of one tile: pw x ph x bb positions of 64 channels
+    uint32_t dw_patch_bytes;         // TMA transaction bytes of one patch
+    uint32_t dw_patch_stage;         // patch stage size in shared memory (1024-byte multiple)
+    int dw_pstages;                  // patch ring depth
 };
 
 // ------------------------------------------------------------------ PTX glue --
@@ -214,7 +218,6 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <bool DW>                                   // DW: the A operand is computed in-kernel (depthwise 3x3), not loaded
 __device__ __forceinline__ void conv_tcgen05_body(const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap& map_o,
                                                   const TcParams& p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -240,7 +243,7 @@ __device__ __forceinline__ void conv_tcgen05_body(const CUtensorMap& map_a, cons
         tma_prefetch_desc(&map_b);
         if (p.tma_store) tma_prefetch_desc(&map_o);
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, DW ? 1 + TC_DW_WARPS : 1);   // one arrive.expect_tx (+ TMA bytes) [+ the depthwise warps]
+            mbar_init(bar_full + 8 * s, 1);                      // one arrive.expect_tx (+ TMA bytes)
             mbar_init(bar_empty + 8 * s, 1);                     // one tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
@@ -279,11 +282,9 @@ __device__ __forceinline__ void conv_tcgen05_body(const CUtensorMap& map_a, cons
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     if (it >= p.stages) mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                     const int tap = kb / p.kb_per_tap, c0 = (kb - tap * p.kb_per_tap) * TC_BK;
-                    mbar_expect_tx(bar_full + 8 * s, DW ? p.b_bytes : p.a_bytes + p.b_bytes);
+                    mbar_expect_tx(bar_full + 8 * s, p.a_bytes + p.b_bytes);
                     const uint32_t dst_a = smem_addr(sA + (size_t)s * a_stage), dst_b = smem_addr(sB + (size_t)s * b_stage);
-                    if (DW) {
-                        // the depthwise warps write this stage's A tile
-                    } else if (p.mode4d) {
+                    if (p.mode4d) {
                         const int ky = tap / p.KW, kx = tap - ky * p.KW;
                         // strided convolutions: the tensor map traverses W and H with element stride = conv stride,
                         // so the box still lands as bw x bh output pixels
@@ -321,96 +322,6 @@ __device__ __forceinline__ void conv_tcgen05_body(const CUtensorMap& map_a, cons
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
                 umma_commit(bar_tfull + 8 * a);                  // accumulator complete
-            }
-        }
-    } else if (DW && warp >= 2 + TC_EPI_WARPS) {
-        // ===================== depthwise 3x3 producers (8 warps): A tile = act(dw(x) + bias) =====================
-        // Thread -> (16-byte channel chunk j of the 64-channel k-block, tile rows r0 + 32 i): 8 consecutive threads
-        // read 128 contiguous bytes of one input pixel.  The result goes straight into the 128-byte-swizzled K-major
-        // layout the UMMA descriptor expects (what TMA would have written), so the expanded activation is read once
-        // and the depthwise output never exists in global memory.
-        const int pt = (int)threadIdx.x - 32 * (2 + TC_EPI_WARPS);
-        const int j = pt & 7, r0 = pt >> 3;
-        const int C8 = p.dw_C8, Hi = p.dw_H, Wi = p.dw_W, st = p.dw_stride;
-        const float lo = p.dw_act == SSD_ACT_NONE ? -__int_as_float(0x7f800000) : 0.0f;
-        const float hi = p.dw_act == SSD_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
-        int it = 0, s = 0;
-        uint32_t ph = 0;
-        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-            const int tm_ = t / p.tiles_n;
-            int pb[TC_DW_ROWS], py[TC_DW_ROWS], px[TC_DW_ROWS];
-            bool ok[TC_DW_ROWS];
-#pragma unroll
-            for (int i = 0; i < TC_DW_ROWS; ++i) {
-                const int r = r0 + 4 * TC_DW_WARPS * i;
-                const int m = tm_ * TC_BM + r;
-                ok[i] = r < TC_BM && m < p.M;
-                const int mm = ok[i] ? m : 0;
-                pb[i] = mm / p.HoWo;
-                const int pix = mm - pb[i] * p.HoWo;
-                py[i] = (pix / p.Wo) * st - p.dw_pad_t;
-                px[i] = (pix - (pix / p.Wo) * p.Wo) * st - p.dw_pad_l;
-            }
-            for (int kb = 0; kb < p.n_kblocks; ++kb, ++it) {
-                const int c8 = kb * 8 + j;
-                const bool cok = c8 < C8;
-                float bias8[8];
-                {
-                    const float4 b0 = (cok && p.dw_bias) ? __ldg(reinterpret_cast<const float4*>(p.dw_bias) + c8 * 2) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4 b1 = (cok && p.dw_bias) ? __ldg(reinterpret_cast<const float4*>(p.dw_bias) + c8 * 2 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
-                    bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
-                }
-                if (it >= p.stages) mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                unsigned char* a_tile = sA + (size_t)s * a_stage;
-                const uint4* wk = p.dw_w + (cok ? c8 : 0);
-#pragma unroll
-                for (int hp = 0; hp < TC_DW_ROWS / 2; ++hp) {    // passes of two tile rows: bounded register footprint
-                    float acc[2][8];
-#pragma unroll
-                    for (int q2 = 0; q2 < 2; ++q2)
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) acc[q2][e] = bias8[e];
-                    const uint4* img0 = p.dw_x + (size_t)pb[2 * hp] * Hi * Wi * C8 + (cok ? c8 : 0);
-                    const uint4* img1 = p.dw_x + (size_t)pb[2 * hp + 1] * Hi * Wi * C8 + (cok ? c8 : 0);
-#pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int ky = tap / 3, kx = tap - ky * 3;
-                        const uint4 wv = __ldg(wk + (size_t)tap * C8);
-                        const int iy0 = py[2 * hp] + ky, ix0 = px[2 * hp] + kx;
-                        const int iy1 = py[2 * hp + 1] + ky, ix1 = px[2 * hp + 1] + kx;
-                        const bool v0 = cok && ok[2 * hp] && (unsigned)iy0 < (unsigned)Hi && (unsigned)ix0 < (unsigned)Wi;
-                        const bool v1 = cok && ok[2 * hp + 1] && (unsigned)iy1 < (unsigned)Hi && (unsigned)ix1 < (unsigned)Wi;
-                        const uint4 x0 = v0 ? __ldg(img0 + ((size_t)iy0 * Wi + ix0) * C8) : make_uint4(0u, 0u, 0u, 0u);
-                        const uint4 x1 = v1 ? __ldg(img1 + ((size_t)iy1 * Wi + ix1) * C8) : make_uint4(0u, 0u, 0u, 0u);
-                        const __half2* wh = reinterpret_cast<const __half2*>(&wv);
-                        const __half2* xh0 = reinterpret_cast<const __half2*>(&x0);
-                        const __half2* xh1 = reinterpret_cast<const __half2*>(&x1);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 wf = __half22float2(wh[e]), f0 = __half22float2(xh0[e]), f1 = __half22float2(xh1[e]);
-                            acc[0][2 * e] = fmaf(f0.x, wf.x, acc[0][2 * e]); acc[0][2 * e + 1] = fmaf(f0.y, wf.y, acc[0][2 * e + 1]);
-                            acc[1][2 * e] = fmaf(f1.x, wf.x, acc[1][2 * e]); acc[1][2 * e + 1] = fmaf(f1.y, wf.y, acc[1][2 * e + 1]);
-                        }
-                    }
-#pragma unroll
-                    for (int q2 = 0; q2 < 2; ++q2) {
-                        const int i = 2 * hp + q2, r = r0 + 4 * TC_DW_WARPS * i;
-                        if (r >= TC_BM) continue;
-                        uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                        if (cok && ok[i]) {
-                            __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                oh[e] = __floats2half2_rn(fminf(fmaxf(acc[q2][2 * e], lo), hi), fminf(fmaxf(acc[q2][2 * e + 1], lo), hi));
-                        }
-                        *reinterpret_cast<uint4*>(a_tile + r * 128 + ((j ^ (r & 7)) << 4)) = o;
-                    }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_full + 8 * s);
-                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else {
@@ -536,12 +447,276 @@ __device__ __forceinline__ void conv_tcgen05_body(const CUtensorMap& map_a, cons
 __global__ void __launch_bounds__(TC_THREADS, 2)     // <= 102 registers: two CTAs may share an SM (shallow-K layers)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_o, const __grid_constant__ TcParams p) {
-    conv_tcgen05_body<false>(map_a, map_b, map_o, p);
+    conv_tcgen05_body(map_a, map_b, map_o, p);
 }
-__global__ void __launch_bounds__(TC_THREADS_DW, 1)                   // one CTA per SM: 16 warps x <= 128 registers
-conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_o,
-                           const __grid_constant__ TcParams p) {
-    conv_tcgen05_body<true>(map_b, map_b, map_o, p);
+// ======================================================================================
+// Fused DepthwiseConv2D 3x3 -> 1x1 Conv2D (the tail of a MobileNetV2 inverted-residual block).
+//
+//   warp 0      TMA: per k-block (64 expanded channels) the INPUT PATCH of the tile -- (bw-1)s+3 x (bh-1)s+3 x bb
+//               positions x 64 channels, one 4-D box, zero-filled outside the image (= the convolution padding) --
+//               and the 1x1 weight tile B;
+//   warps 10-19 depthwise: 3x3 taps from the swizzled patch in shared memory, + bias, activation, fp16, written
+//               straight into the 128-byte-swizzled K-major A tile the UMMA descriptor expects;
+//   warp 1      tcgen05.mma into double-buffered TMEM accumulators;
+//   warps 2-9   epilogue: bias / activation / residual -> swizzled staging tile -> TMA store (as conv_tcgen05_kernel).
+//
+// The expanded activation is read from L2/HBM exactly once (by TMA, fully asynchronous, prefetched dw_pstages deep)
+// and the depthwise output never exists in global memory.
+__global__ void __launch_bounds__(TC_THREADS_DW, 1)
+conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b,
+                           const __grid_constant__ CUtensorMap map_o, const __grid_constant__ TcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_stage = TC_BM * TC_BK * 2;                 // 16 KB
+    const uint32_t b_stage = (uint32_t)p.BN * TC_BK * 2;
+    unsigned char* sA = smem;
+    unsigned char* sB = sA + TC_DW_ASTAGES * a_stage;
+    unsigned char* sP = sB + TC_DW_ASTAGES * ((b_stage + 1023u) & ~1023u);
+    unsigned char* sOut = sP + (size_t)p.dw_pstages * p.dw_patch_stage;
+    float* sBias = reinterpret_cast<float*>(sOut + 2 * TC_OUT_TILE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + TC_OUT_BYTES);
+    // bars: full[2] | empty[2] | pfull[4] | pempty[4] | tmem_full[2] | tmem_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    const uint32_t b_pitch = (b_stage + 1023u) & ~1023u;
+
+    pdl_trigger();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = smem_addr(bars), bar_empty = smem_addr(bars + 2);
+    const uint32_t bar_pfull = smem_addr(bars + 4), bar_pempty = smem_addr(bars + 8);
+    const uint32_t bar_tfull = smem_addr(bars + 12), bar_tempty = smem_addr(bars + 14);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_b); tma_prefetch_desc(&map_o);
+        for (int s = 0; s < TC_DW_ASTAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1 + TC_DW_WARPS);        // B bytes (expect_tx) + one arrive per depthwise warp
+            mbar_init(bar_empty + 8 * s, 1);                     // tcgen05.commit
+        }
+        for (int s = 0; s < 4; ++s) {
+            mbar_init(bar_pfull + 8 * s, 1);                     // patch bytes (expect_tx)
+            mbar_init(bar_pempty + 8 * s, TC_DW_WARPS);          // every depthwise warp is done with the patch
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, TC_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_addr(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+    const int per_img = p.tiles_w * p.tiles_h;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int it = 0, s = 0, ps = 0;
+            uint32_t ph = 0, pph = 0;
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+                const int tb = t / per_img, tr = t - tb * per_img;
+                const int th = tr / p.tiles_w, tw = tr - th * p.tiles_w;
+                const int b0 = tb * p.bb, oy0 = th * p.bh, ox0 = tw * p.bw;
+                for (int kb = 0; kb < p.n_kblocks; ++kb, ++it) {
+                    if (it >= p.dw_pstages) mbar_wait(bar_pempty + 8 * ps, pph ^ 1u);
+                    mbar_expect_tx(bar_pfull + 8 * ps, p.dw_patch_bytes);
+                    tma_load_4d(smem_addr(sP + (size_t)ps * p.dw_patch_stage), &map_x, bar_pfull + 8 * ps, kb * TC_BK,
+                                ox0 * p.dw_stride - p.dw_pad_l, oy0 * p.dw_stride - p.dw_pad_t, b0);
+                    if (++ps == p.dw_pstages) { ps = 0; pph ^= 1u; }
+                    if (it >= TC_DW_ASTAGES) mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                    mbar_expect_tx(bar_full + 8 * s, p.b_bytes);
+                    tma_load_2d(smem_addr(sB + (size_t)s * b_pitch), &map_b, bar_full + 8 * s, kb * TC_BK, 0);
+                    if (++s == TC_DW_ASTAGES) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int j = 0, s = 0;
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++j) {
+                const int a = j & 1;
+                if (j >= 2) mbar_wait(bar_tempty + 8 * a, ((j >> 1) - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tacc = tmem_base + (uint32_t)a * p.acc_cols;
+                for (int kb = 0; kb < p.n_kblocks; ++kb) {
+                    mbar_wait(bar_full + 8 * s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t da = umma_desc_sw128(smem_addr(sA + (size_t)s * a_stage));
+                    const uint64_t db = umma_desc_sw128(smem_addr(sB + (size_t)s * b_pitch));
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k)
+                        umma_f16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (kb > 0) || k > 0);
+                    umma_commit(bar_empty + 8 * s);
+                    if (++s == TC_DW_ASTAGES) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(bar_tfull + 8 * a);
+            }
+        }
+    } else if (warp >= 2 + TC_EPI_WARPS) {
+        // ===================== depthwise 3x3 from the shared-memory patch =====================
+        const int pt = (int)threadIdx.x - 32 * (2 + TC_EPI_WARPS);
+        const int j = pt & 7, rg = pt >> 3;                      // 16-byte channel chunk, row group (0..39)
+        const int C8 = p.dw_C8, st = p.dw_stride, pw = p.dw_pw, php = p.dw_ph;
+        const float lo = p.dw_act == SSD_ACT_NONE ? -__int_as_float(0x7f800000) : 0.0f;
+        const float hi = p.dw_act == SSD_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
+        const int box_rows = p.bw * p.bh * p.bb;
+        int q0[TC_DW_ROWS];                                      // patch position of tap (0,0) per owned row; -1: padding row
+#pragma unroll
+        for (int i = 0; i < TC_DW_ROWS; ++i) {
+            const int r = rg + 4 * TC_DW_WARPS * i;
+            if (r < box_rows) {
+                const int dx = r % p.bw, qq = r / p.bw, dy = qq % p.bh, db = qq / p.bh;
+                q0[i] = dx * st + pw * (dy * st + php * db);
+            } else {
+                q0[i] = -1;
+            }
+        }
+        int s = 0, ps = 0, it = 0;
+        uint32_t ph = 0, pph = 0;
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+            for (int kb = 0; kb < p.n_kblocks; ++kb, ++it) {
+                const int c8 = kb * 8 + j;
+                const bool cok = c8 < C8;
+                uint4 wv[9];
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) wv[tap] = cok ? __ldg(p.dw_w + (size_t)tap * C8 + c8) : make_uint4(0u, 0u, 0u, 0u);
+                float bias8[8];
+                {
+                    const float4 b0 = (cok && p.dw_bias) ? __ldg(reinterpret_cast<const float4*>(p.dw_bias) + c8 * 2) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 b1 = (cok && p.dw_bias) ? __ldg(reinterpret_cast<const float4*>(p.dw_bias) + c8 * 2 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
+                    bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
+                }
+                mbar_wait(bar_pfull + 8 * ps, pph);                                   // patch landed
+                if (it >= TC_DW_ASTAGES) mbar_wait(bar_empty + 8 * s, ph ^ 1u);         // A slot drained by the MMA
+                const unsigned char* patch = sP + (size_t)ps * p.dw_patch_stage;
+                unsigned char* a_tile = sA + (size_t)s * a_stage;
+#pragma unroll
+                for (int i = 0; i < TC_DW_ROWS; ++i) {
+                    const int r = rg + 4 * TC_DW_WARPS * i;
+                    if (r >= TC_BM) continue;
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                    if (q0[i] >= 0 && cok) {
+                        float acc[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[e] = bias8[e];
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const int q = q0[i] + kx + pw * ky;
+                                const uint4 xv = *reinterpret_cast<const uint4*>(patch + (size_t)q * 128 + ((j ^ (q & 7)) << 4));
+                                const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+                                const __half2* wh = reinterpret_cast<const __half2*>(&wv[ky * 3 + kx]);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 xf = __half22float2(xh[e]), wf = __half22float2(wh[e]);
+                                    acc[2 * e] = fmaf(xf.x, wf.x, acc[2 * e]);
+                                    acc[2 * e + 1] = fmaf(xf.y, wf.y, acc[2 * e + 1]);
+                                }
+                            }
+                        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            oh[e] = __floats2half2_rn(fminf(fmaxf(acc[2 * e], lo), hi), fminf(fmaxf(acc[2 * e + 1], lo), hi));
+                    }
+                    *reinterpret_cast<uint4*>(a_tile + r * 128 + ((j ^ (r & 7)) << 4)) = o;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic-proxy writes -> visible to the MMA
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(bar_full + 8 * s); mbar_arrive(bar_pempty + 8 * ps); }
+                if (++s == TC_DW_ASTAGES) { s = 0; ph ^= 1u; }
+                if (++ps == p.dw_pstages) { ps = 0; pph ^= 1u; }
+            }
+        }
+    } else {
+        // ===================== epilogue (8 warps): TMEM -> bias/act/residual -> swizzled tile -> TMA store =====================
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        const int r = q * 32 + lane;
+        const bool elected = ew == 0 && lane == 0;
+        const float act_lo = p.act == SSD_ACT_NONE ? -__int_as_float(0x7f800000) : 0.0f;
+        const float act_hi = p.act == SSD_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
+        {
+            const int i = ew * 32 + lane;                        // bias of the (single) N tile, once
+            sBias[i] = (p.bias && i < p.Cout) ? __ldg(p.bias + i) : 0.0f;
+        }
+        int j = 0;
+        uint32_t n_groups = 0;
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++j) {
+            const int a = j & 1;
+            mbar_wait(bar_tfull + 8 * a, (j >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            int b = 0, pix = 0;
+            const bool row_ok = tc_row_to_pixel(p, t, r, b, pix);
+            const long long row_off = (long long)b * p.img0 + (long long)pix * p.pix0;
+            const uint32_t trow = tmem_base + (uint32_t)a * p.acc_cols + ((uint32_t)(q * 32) << 16);
+            const int tb = t / per_img, tr = t - tb * per_img;
+            const int th = tr / p.tiles_w, tw = tr - th * p.tiles_w;
+            const int b0 = tb * p.bb, oy0 = th * p.bh, ox0 = tw * p.bw;
+            for (int g0 = 0; g0 < p.BN && g0 < p.Cout; g0 += 64, ++n_groups) {
+                unsigned char* buf = sOut + (n_groups & 1u) * TC_OUT_TILE;
+                const int c0 = g0 + half * TC_CHUNK;
+                const bool mine = c0 < p.BN && c0 < p.Cout;
+                uint32_t acc[TC_CHUNK];
+                if (mine) tmem_ld32(trow + (uint32_t)c0, acc);
+                if (elected) bulk_wait_read<1>();
+                epi_barrier();
+                if (mine) {
+                    const int ncols = min(TC_CHUNK, p.Cout - c0);
+                    const float* sbias = sBias + c0;
+                    tmem_ld_wait(acc);
+#pragma unroll
+                    for (int h = 0; h < TC_CHUNK / 8; ++h) {
+                        const float4 b0v = *reinterpret_cast<const float4*>(sbias + h * 8);
+                        const float4 b1v = *reinterpret_cast<const float4*>(sbias + h * 8 + 4);
+                        const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
+                        float v[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            v[e] = fminf(fmaxf(__uint_as_float(acc[h * 8 + e]) + bb[e], act_lo), act_hi);
+                        if (p.res && row_ok && h * 8 < ncols) {
+                            const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + row_off + c0 + h * 8));
+                            const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __half22float2(rh[e]);
+                                v[2 * e] += f.x; v[2 * e + 1] += f.y;
+                            }
+                        }
+                        uint4 o;
+                        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                        *reinterpret_cast<uint4*>(buf + r * 128 + (((half * 4 + h) ^ (r & 7)) << 4)) = o;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                epi_barrier();
+                if (elected) {
+                    tma_store_4d(&map_o, smem_addr(buf), g0, ox0, oy0, b0);
+                    bulk_commit();
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * a);
+        }
+        if (elected) bulk_wait_all();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
 }
 
 // Deterministic split-K reduction + epilogue: partial[z][row][n] summed for z = 0..splits-1 in order.
@@ -807,18 +982,61 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
 // Fused DepthwiseConv2D 3x3 (+ folded BN + activation) -> 1x1 Conv2D (+ folded BN, residual): the "depthwise ->
 // project" tail of a MobileNetV2 inverted-residual block as ONE launch.  GEMM view: M = B*Ho*Wo pixels,
 // K = C (expanded channels, computed on the fly by the depthwise warps), N = Cout <= 256.
+// Tile / ring geometry of the fused kernel; returns false when no output box fits the shared-memory budget.
+static bool dwproj_plan(const ssd_dwproj_desc* d, TcParams* pp, size_t* smem_out) {
+    TcParams& p = *pp;
+    p.BN = (d->Cout + 15) / 16 * 16;
+    const size_t b_pitch = ((size_t)p.BN * TC_BK * 2 + 1023) & ~(size_t)1023;
+    const size_t fixed = (size_t)TC_DW_ASTAGES * (TC_BM * TC_BK * 2 + b_pitch) + (size_t)TC_OUT_BYTES + 17 * 8 + 16 + 1024;
+    const size_t budget = (size_t)227 * 1024;
+    const int M = d->B * d->Ho * d->Wo, s = d->stride;
+    double best = -1.0;
+    for (int bw = 1; bw <= min(d->Wo, TC_BM); ++bw) {
+        const int tw = (d->Wo + bw - 1) / bw;
+        for (int bh = 1; bh <= min(d->Ho, TC_BM / bw); ++bh) {
+            const int th = (d->Ho + bh - 1) / bh;
+            int bb = 1;
+            if (bw == d->Wo && bh == d->Ho) bb = max(1, min(d->B, TC_BM / (bw * bh)));
+            const int tb = (d->B + bb - 1) / bb;
+            const int pw = (bw - 1) * s + 3, ph = (bh - 1) * s + 3;
+            if (pw > 256 || ph > 256) continue;
+            const size_t patch = ((size_t)pw * ph * bb * 128 + 1023) & ~(size_t)1023;
+            int pst = 0;
+            for (int c = 3; c >= 2; --c) if (fixed + c * patch <= budget) { pst = c; break; }
+            if (!pst) continue;
+            // MMA-row efficiency, discounted by the halo the patch re-reads
+            const double eff = (double)M / ((double)tw * th * tb * TC_BM) * ((double)bw * bh * s * s / ((double)pw * ph)) + 1e-6 * bw;
+            if (eff > best) {
+                best = eff; p.bw = bw; p.bh = bh; p.bb = bb; p.tiles_w = tw; p.tiles_h = th;
+                p.dw_pw = pw; p.dw_ph = ph; p.dw_patch_bytes = (uint32_t)(pw * ph * bb * 128); p.dw_patch_stage = (uint32_t)patch;
+                p.dw_pstages = pst;
+                p.n_tiles = tw * th * tb;
+                *smem_out = fixed + pst * patch;
+            }
+        }
+    }
+    return best > 0.0;
+}
+
 bool conv_dwproj_supported(const ssd_dwproj_desc* d) {
-    return d->C % 8 == 0 && d->Cout % 8 == 0 && d->Cout <= 256 && (d->stride == 1 || d->stride == 2) &&
-           (reinterpret_cast<uintptr_t>(d->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->dw_weight) & 15) == 0 &&
-           (reinterpret_cast<uintptr_t>(d->proj_weight) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 &&
-           (d->residual == nullptr || (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0) &&
-           (d->dw_bias == nullptr || (reinterpret_cast<uintptr_t>(d->dw_bias) & 15) == 0);
+    if (!(d->C % 8 == 0 && d->Cout % 8 == 0 && d->Cout <= 256 && (d->stride == 1 || d->stride == 2) &&
+          (reinterpret_cast<uintptr_t>(d->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->dw_weight) & 15) == 0 &&
+          (reinterpret_cast<uintptr_t>(d->proj_weight) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 &&
+          (d->residual == nullptr || (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0) &&
+          (d->dw_bias == nullptr || (reinterpret_cast<uintptr_t>(d->dw_bias) & 15) == 0)))
+        return false;
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    size_t smem = 0;
+    return dwproj_plan(d, &p, &smem);
 }
 
 int conv_dwproj_launch(const ssd_dwproj_desc* d, cudaStream_t st) {
     TcParams p;
     memset(&p, 0, sizeof(p));
-    p.mode4d = 0;
+    size_t smem = 0;
+    if (!dwproj_plan(d, &p, &smem)) return fail(SSD_ERR_UNSUPPORTED, "ssd_dwproj: no tile geometry fits shared memory");
+    p.mode4d = 1;
     p.B = d->B; p.Ho = d->Ho; p.Wo = d->Wo; p.HoWo = d->Ho * d->Wo; p.M = d->B * p.HoWo;
     p.Cin = d->C; p.KW = 1; p.dil = 1; p.stride = 1;
     p.kb_per_tap = (d->C + TC_BK - 1) / TC_BK;
@@ -828,15 +1046,22 @@ int conv_dwproj_launch(const ssd_dwproj_desc* d, cudaStream_t st) {
     p.bias = d->proj_bias; p.res = (const __half*)d->residual; p.out0 = d->out; p.out1 = nullptr;
     p.act = d->act; p.out_f32 = 0; p.split = d->Cout;
     p.pix0 = d->Cout; p.img0 = (long long)p.HoWo * d->Cout;
-    p.BN = (d->Cout + 15) / 16 * 16;
     p.acc_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
     p.tmem_cols = 2 * p.acc_cols;
     p.idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     p.dw_x = reinterpret_cast<const uint4*>(d->in); p.dw_w = reinterpret_cast<const uint4*>(d->dw_weight); p.dw_bias = d->dw_bias;
     p.dw_H = d->H; p.dw_W = d->W; p.dw_C8 = d->C / 8; p.dw_stride = d->stride; p.dw_pad_t = d->pad_top; p.dw_pad_l = d->pad_left;
     p.dw_act = d->dw_act;
+    p.splits = 1; p.tiles_m = p.n_tiles; p.tiles_n = 1; p.tma_store = 1; p.stages = TC_DW_ASTAGES;
 
-    CUtensorMap map_b, map_o;
+    CUtensorMap map_x, map_b, map_o;
+    {
+        uint64_t dims[4] = {(uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+        uint64_t str[3] = {(uint64_t)d->C * 2, (uint64_t)d->W * d->C * 2, (uint64_t)d->H * d->W * d->C * 2};
+        uint32_t box[4] = {TC_BK, (uint32_t)p.dw_pw, (uint32_t)p.dw_ph, (uint32_t)p.bb};
+        int rc = cached_map(&map_x, d->in, 4, dims, str, box);
+        if (rc) return rc;
+    }
     {
         uint64_t dims[2] = {(uint64_t)d->C, (uint64_t)d->Cout};
         uint64_t str[1] = {(uint64_t)d->C * 2};
@@ -844,21 +1069,14 @@ int conv_dwproj_launch(const ssd_dwproj_desc* d, cudaStream_t st) {
         int rc = cached_map(&map_b, d->proj_weight, 2, dims, str, box);
         if (rc) return rc;
         p.b_bytes = (uint32_t)p.BN * TC_BK * 2;
-        p.a_bytes = 0;
     }
     {
-        uint64_t dims[2] = {(uint64_t)d->Cout, (uint64_t)p.M};
-        uint64_t str[1] = {(uint64_t)d->Cout * 2};
-        uint32_t box[2] = {64, TC_BM};
-        int rc = cached_map(&map_o, d->out, 2, dims, str, box);
+        uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->B};
+        uint64_t str[3] = {(uint64_t)d->Cout * 2, (uint64_t)d->Wo * d->Cout * 2, (uint64_t)p.HoWo * d->Cout * 2};
+        uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bb};
+        int rc = cached_map(&map_o, d->out, 4, dims, str, box);
         if (rc) return rc;
-        p.tma_store = 1;
     }
-    p.splits = 1;
-    p.tiles_m = (p.M + TC_BM - 1) / TC_BM; p.tiles_n = 1; p.n_tiles = p.tiles_m;
-    p.stages = min(TC_STAGES, max(2, p.n_kblocks));
-    const size_t smem = (size_t)p.stages * (TC_BM * TC_BK * 2 + (size_t)p.BN * TC_BK * 2) + (size_t)TC_OUT_BYTES +
-                        (2 * TC_STAGES + 4) * 8 + 16 + 1024;
     static thread_local int attr_dev = -1;
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
@@ -868,8 +1086,8 @@ int conv_dwproj_launch(const ssd_dwproj_desc* d, cudaStream_t st) {
         attr_dev = cur_dev;
     }
     dim3 grid(min(p.n_tiles, sm_count()), 1, 1);
-    cudaError_t le = launch_pdl(conv_dwproj_tcgen05_kernel, grid, dim3(TC_THREADS_DW), smem, st, map_b, map_o, p);
-    if (le != cudaSuccess) return cuda_fail(le, "conv_tcgen05_kernel<dw>");
+    cudaError_t le = launch_pdl(conv_dwproj_tcgen05_kernel, grid, dim3(TC_THREADS_DW), smem, st, map_x, map_b, map_o, p);
+    if (le != cudaSuccess) return cuda_fail(le, "conv_dwproj_tcgen05_kernel");
     return SSD_OK;
 }
 

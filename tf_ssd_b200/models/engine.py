@@ -330,7 +330,6 @@ class _PlanBuilder:
         if (self.FUSE_DW and last is not None and last.kind == "dw" and last.meta["out"] is x.t and k == 1 and stride == 1
                 and dilation == 1 and cout <= 256 and cout % 8 == 0 and type(self) is _PlanBuilder):
             # depthwise 3x3 -> 1x1 projection as ONE launch (ssd_dwproj): the depthwise output stays on chip
-            self.plan.steps.pop()
             dm = last.meta
             d = DwProjDesc()
             d.inp, d.dw_weight, d.dw_bias = dm["x"].data_ptr(), dm["w"].data_ptr(), dm["bias"].data_ptr()
@@ -340,6 +339,10 @@ class _PlanBuilder:
             d.B, d.H, d.W, d.C = self.B, dm["x"].shape[1], dm["x"].shape[2], x.C
             d.Ho, d.Wo, d.Cout = Ho, Wo, cout
             d.stride, d.pad_top, d.pad_left, d.dw_act, d.act = dm["stride"], dm["ph"][0], dm["pw"][0], dm["act"], act
+            if not self.lib.ssd_dwproj_supported(C.byref(d)):
+                self._emit_conv(name, x, w, b, cout, k, stride, dilation, ph, pw, act, residual, out, real_cin=real_cin)
+                return Act(out, Ho, Wo, cout)
+            self.plan.steps.pop()
             nbytes = self.B * dm["x"].shape[1] * dm["x"].shape[2] * x.C * 2 + 9 * x.C * 2 + x.C * cout * 2 + \
                 self.B * Ho * Wo * cout * 2 * (2 if residual is not None else 1)
             flops = 2.0 * self.B * Ho * Wo * x.C * (9 + cout)
