@@ -463,8 +463,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // The expanded activation is read from L2/HBM exactly once (by TMA, fully asynchronous, prefetched dw_pstages deep)
 // and the depthwise output never exists in global memory.
 __global__ void __launch_bounds__(TC_THREADS_DW, 1)
-conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b,
-                           const __grid_constant__ CUtensorMap map_o, const __grid_constant__ TcParams p) {
+conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                           const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_o,
+                           const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t a_stage = TC_BM * TC_BK * 2;                 // 16 KB
@@ -486,7 +487,7 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
     const uint32_t bar_tfull = smem_addr(bars + 12), bar_tempty = smem_addr(bars + 14);
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_b); tma_prefetch_desc(&map_o);
+        tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_b); tma_prefetch_desc(&map_o);
         for (int s = 0; s < TC_DW_ASTAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1 + TC_DW_WARPS);        // B bytes (expect_tx) + one arrive per depthwise warp
             mbar_init(bar_empty + 8 * s, 1);                     // tcgen05.commit
@@ -524,9 +525,12 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
                 const int b0 = tb * p.bb, oy0 = th * p.bh, ox0 = tw * p.bw;
                 for (int kb = 0; kb < p.n_kblocks; ++kb, ++it) {
                     if (it >= p.dw_pstages) mbar_wait(bar_pempty + 8 * ps, pph ^ 1u);
-                    mbar_expect_tx(bar_pfull + 8 * ps, p.dw_patch_bytes);
+                    mbar_expect_tx(bar_pfull + 8 * ps, p.dw_patch_bytes + 9 * 128);
                     tma_load_4d(smem_addr(sP + (size_t)ps * p.dw_patch_stage), &map_x, bar_pfull + 8 * ps, kb * TC_BK,
                                 ox0 * p.dw_stride - p.dw_pad_l, oy0 * p.dw_stride - p.dw_pad_t, b0);
+                    // the k-block's depthwise filter: 9 taps x 64 channels behind the patch (own 1024-byte aligned atom)
+                    tma_load_2d(smem_addr(sP + (size_t)ps * p.dw_patch_stage + p.dw_patch_stage - 2048), &map_w, bar_pfull + 8 * ps,
+                                kb * TC_BK, 0);
                     if (++ps == p.dw_pstages) { ps = 0; pph ^= 1u; }
                     if (it >= TC_DW_ASTAGES) mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                     mbar_expect_tx(bar_full + 8 * s, p.b_bytes);
@@ -578,25 +582,55 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
                 q0[i] = -1;
             }
         }
+        // Arithmetic: packed half2 FMAs (4 per tap and row instead of 16 conversions + 8 FMAs).  The nine products of
+        // an output are summed in fp16 -- the same storage format the result is rounded to for the tensor-core
+        // operand -- starting from the fp16-rounded bias; the 1x1 projection accumulates in fp32 as everywhere else.
         int s = 0, ps = 0, it = 0;
         uint32_t ph = 0, pph = 0;
+        const bool has_bias = p.dw_bias != nullptr;
+        auto load_bias = [&](int kb, __half2 (&b4)[4]) {
+            const int c8 = kb * 8 + j;
+            const bool okb = has_bias && c8 < C8;
+            const float4 b0 = okb ? __ldg(reinterpret_cast<const float4*>(p.dw_bias) + c8 * 2) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 b1 = okb ? __ldg(reinterpret_cast<const float4*>(p.dw_bias) + c8 * 2 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            b4[0] = __floats2half2_rn(b0.x, b0.y); b4[1] = __floats2half2_rn(b0.z, b0.w);
+            b4[2] = __floats2half2_rn(b1.x, b1.y); b4[3] = __floats2half2_rn(b1.z, b1.w);
+        };
+        const __half2 lo2 = __float2half2_rn(p.dw_act == SSD_ACT_NONE ? -65504.0f : 0.0f);
+        const __half2 hi2 = __float2half2_rn(p.dw_act == SSD_ACT_RELU6 ? 6.0f : 65504.0f);
+        __half2 bias_next[4];
+        load_bias(0, bias_next);
         for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
             for (int kb = 0; kb < p.n_kblocks; ++kb, ++it) {
                 const int c8 = kb * 8 + j;
                 const bool cok = c8 < C8;
-                uint4 wv[9];
+                __half2 acc[TC_DW_ROWS][4];
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) wv[tap] = cok ? __ldg(p.dw_w + (size_t)tap * C8 + c8) : make_uint4(0u, 0u, 0u, 0u);
-                float bias8[8];
-                {
-                    const float4 b0 = (cok && p.dw_bias) ? __ldg(reinterpret_cast<const float4*>(p.dw_bias) + c8 * 2) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4 b1 = (cok && p.dw_bias) ? __ldg(reinterpret_cast<const float4*>(p.dw_bias) + c8 * 2 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
-                    bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
-                }
-                mbar_wait(bar_pfull + 8 * ps, pph);                                   // patch landed
-                if (it >= TC_DW_ASTAGES) mbar_wait(bar_empty + 8 * s, ph ^ 1u);         // A slot drained by the MMA
+                for (int i = 0; i < TC_DW_ROWS; ++i)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[i][e] = bias_next[e];
+                load_bias(kb + 1 < p.n_kblocks ? kb + 1 : 0, bias_next);              // in flight during this k-block
+                mbar_wait(bar_pfull + 8 * ps, pph);                                   // patch + filter landed
                 const unsigned char* patch = sP + (size_t)ps * p.dw_patch_stage;
+                const unsigned char* wsm = patch + p.dw_patch_stage - 2048;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int tap = ky * 3 + kx;
+                        const uint4 wvv = *reinterpret_cast<const uint4*>(wsm + tap * 128 + ((j ^ (tap & 7)) << 4));
+                        const __half2* wh = reinterpret_cast<const __half2*>(&wvv);
+#pragma unroll
+                        for (int i = 0; i < TC_DW_ROWS; ++i) {
+                            if (q0[i] < 0) continue;
+                            const int q = q0[i] + kx + pw * ky;
+                            const uint4 xv = *reinterpret_cast<const uint4*>(patch + (size_t)q * 128 + ((j ^ (q & 7)) << 4));
+                            const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) acc[i][e] = __hfma2(xh[e], wh[e], acc[i][e]);
+                        }
+                    }
+                if (it >= TC_DW_ASTAGES) mbar_wait(bar_empty + 8 * s, ph ^ 1u);         // A slot drained by the MMA
                 unsigned char* a_tile = sA + (size_t)s * a_stage;
 #pragma unroll
                 for (int i = 0; i < TC_DW_ROWS; ++i) {
@@ -604,28 +638,9 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
                     if (r >= TC_BM) continue;
                     uint4 o = make_uint4(0u, 0u, 0u, 0u);
                     if (q0[i] >= 0 && cok) {
-                        float acc[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) acc[e] = bias8[e];
-#pragma unroll
-                        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                            for (int kx = 0; kx < 3; ++kx) {
-                                const int q = q0[i] + kx + pw * ky;
-                                const uint4 xv = *reinterpret_cast<const uint4*>(patch + (size_t)q * 128 + ((j ^ (q & 7)) << 4));
-                                const __half2* xh = reinterpret_cast<const __half2*>(&xv);
-                                const __half2* wh = reinterpret_cast<const __half2*>(&wv[ky * 3 + kx]);
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float2 xf = __half22float2(xh[e]), wf = __half22float2(wh[e]);
-                                    acc[2 * e] = fmaf(xf.x, wf.x, acc[2 * e]);
-                                    acc[2 * e + 1] = fmaf(xf.y, wf.y, acc[2 * e + 1]);
-                                }
-                            }
                         __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            oh[e] = __floats2half2_rn(fminf(fmaxf(acc[2 * e], lo), hi), fminf(fmaxf(acc[2 * e + 1], lo), hi));
+                        for (int e = 0; e < 4; ++e) oh[e] = __hmin2(__hmax2(acc[i][e], lo2), hi2);
                     }
                     *reinterpret_cast<uint4*>(a_tile + r * 128 + ((j ^ (r & 7)) << 4)) = o;
                 }
@@ -1000,7 +1015,7 @@ static bool dwproj_plan(const ssd_dwproj_desc* d, TcParams* pp, size_t* smem_out
             const int tb = (d->B + bb - 1) / bb;
             const int pw = (bw - 1) * s + 3, ph = (bh - 1) * s + 3;
             if (pw > 256 || ph > 256) continue;
-            const size_t patch = ((size_t)pw * ph * bb * 128 + 1023) & ~(size_t)1023;
+            const size_t patch = (((size_t)pw * ph * bb * 128 + 1023) & ~(size_t)1023) + 2048;   // + the k-block's filter
             int pst = 0;
             for (int c = 3; c >= 2; --c) if (fixed + c * patch <= budget) { pst = c; break; }
             if (!pst) continue;
@@ -1054,7 +1069,14 @@ int conv_dwproj_launch(const ssd_dwproj_desc* d, cudaStream_t st) {
     p.dw_act = d->dw_act;
     p.splits = 1; p.tiles_m = p.n_tiles; p.tiles_n = 1; p.tma_store = 1; p.stages = TC_DW_ASTAGES;
 
-    CUtensorMap map_x, map_b, map_o;
+    CUtensorMap map_x, map_w, map_b, map_o;
+    {
+        uint64_t dims[2] = {(uint64_t)d->C, 9};
+        uint64_t str[1] = {(uint64_t)d->C * 2};
+        uint32_t box[2] = {TC_BK, 9};
+        int rc = cached_map(&map_w, d->dw_weight, 2, dims, str, box);
+        if (rc) return rc;
+    }
     {
         uint64_t dims[4] = {(uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
         uint64_t str[3] = {(uint64_t)d->C * 2, (uint64_t)d->W * d->C * 2, (uint64_t)d->H * d->W * d->C * 2};
@@ -1086,7 +1108,7 @@ int conv_dwproj_launch(const ssd_dwproj_desc* d, cudaStream_t st) {
         attr_dev = cur_dev;
     }
     dim3 grid(min(p.n_tiles, sm_count()), 1, 1);
-    cudaError_t le = launch_pdl(conv_dwproj_tcgen05_kernel, grid, dim3(TC_THREADS_DW), smem, st, map_x, map_b, map_o, p);
+    cudaError_t le = launch_pdl(conv_dwproj_tcgen05_kernel, grid, dim3(TC_THREADS_DW), smem, st, map_x, map_w, map_b, map_o, p);
     if (le != cudaSuccess) return cuda_fail(le, "conv_dwproj_tcgen05_kernel");
     return SSD_OK;
 }

@@ -249,8 +249,9 @@ class Plan:
 
 
 class _PlanBuilder:
-    # depthwise + 1x1 projection as one launch (ssd_dwproj); opt-in until the fused kernel beats the two launches
-    FUSE_DW = os.environ.get("SSD_B200_FUSE_DW", "0") == "1"
+    # depthwise + 1x1 projection as one launch (ssd_dwproj): "all", "s2" (stride-2 depthwise layers only: where the
+    # fused kernel beats the two launches today) or "0"
+    FUSE_DW = os.environ.get("SSD_B200_FUSE_DW", "s2")
 
     def __init__(self, model: "SSDModel", B: int):
         self.m = model
@@ -327,7 +328,8 @@ class _PlanBuilder:
         out = self._buf(Ho, Wo, cout)
         real_cin = self.m.weights[name + "/kernel"].shape[2]
         last = self.plan.steps[-1] if self.plan.steps else None
-        if (self.FUSE_DW and last is not None and last.kind == "dw" and last.meta["out"] is x.t and k == 1 and stride == 1
+        if (self.FUSE_DW not in ("0", "") and last is not None and last.kind == "dw" and last.meta["out"] is x.t
+                and (self.FUSE_DW in ("1", "all") or last.meta["stride"] == 2) and k == 1 and stride == 1
                 and dilation == 1 and cout <= 256 and cout % 8 == 0 and type(self) is _PlanBuilder):
             # depthwise 3x3 -> 1x1 projection as ONE launch (ssd_dwproj): the depthwise output stays on chip
             dm = last.meta
