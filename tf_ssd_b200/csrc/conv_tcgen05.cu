@@ -82,6 +82,7 @@ struct TcParams {
     uint32_t dw_patch_bytes;         // TMA transaction bytes of one patch
     uint32_t dw_patch_stage;         // patch stage size in shared memory (1024-byte multiple)
     int dw_pstages;                  // patch ring depth
+    int dw_quad;                     // stride 1 and bw % 4 == 0: a thread owns 4 horizontally adjacent pixels (sliding window)
 };
 
 // ------------------------------------------------------------------ PTX glue --
@@ -571,11 +572,13 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
         const float lo = p.dw_act == SSD_ACT_NONE ? -__int_as_float(0x7f800000) : 0.0f;
         const float hi = p.dw_act == SSD_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
         const int box_rows = p.bw * p.bh * p.bb;
+        // rows owned by this thread: strided (rg + 40 i) or, in quad mode, 4 horizontally adjacent pixels (4 rg + i)
+        const int quad = p.dw_quad;
         int q0[TC_DW_ROWS];                                      // patch position of tap (0,0) per owned row; -1: padding row
 #pragma unroll
         for (int i = 0; i < TC_DW_ROWS; ++i) {
-            const int r = rg + 4 * TC_DW_WARPS * i;
-            if (r < box_rows) {
+            const int r = quad ? 4 * rg + i : rg + 4 * TC_DW_WARPS * i;
+            if (r < box_rows && r < TC_BM) {
                 const int dx = r % p.bw, qq = r / p.bw, dy = qq % p.bh, db = qq / p.bh;
                 q0[i] = dx * st + pw * (dy * st + php * db);
             } else {
@@ -613,6 +616,35 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
                 mbar_wait(bar_pfull + 8 * ps, pph);                                   // patch + filter landed
                 const unsigned char* patch = sP + (size_t)ps * p.dw_patch_stage;
                 const unsigned char* wsm = patch + p.dw_patch_stage - 2048;
+                if (quad) {
+                    // sliding window: the 4 outputs of a thread share 6 input columns per filter row (18 loads, not 36)
+                    if (q0[0] >= 0) {
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            uint4 w3[3];
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const int tap = ky * 3 + kx;
+                                w3[kx] = *reinterpret_cast<const uint4*>(wsm + tap * 128 + ((j ^ (tap & 7)) << 4));
+                            }
+#pragma unroll
+                            for (int c = 0; c < 6; ++c) {
+                                const int q = q0[0] + c + pw * ky;
+                                const uint4 xv = *reinterpret_cast<const uint4*>(patch + (size_t)q * 128 + ((j ^ (q & 7)) << 4));
+                                const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const int kx = c - i;
+                                    if (kx >= 0 && kx < 3) {
+                                        const __half2* wh = reinterpret_cast<const __half2*>(&w3[kx]);
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) acc[i][e] = __hfma2(xh[e], wh[e], acc[i][e]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                } else {
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -630,11 +662,12 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
                             for (int e = 0; e < 4; ++e) acc[i][e] = __hfma2(xh[e], wh[e], acc[i][e]);
                         }
                     }
+                }
                 if (it >= TC_DW_ASTAGES) mbar_wait(bar_empty + 8 * s, ph ^ 1u);         // A slot drained by the MMA
                 unsigned char* a_tile = sA + (size_t)s * a_stage;
 #pragma unroll
                 for (int i = 0; i < TC_DW_ROWS; ++i) {
-                    const int r = rg + 4 * TC_DW_WARPS * i;
+                    const int r = quad ? 4 * rg + i : rg + 4 * TC_DW_WARPS * i;
                     if (r >= TC_BM) continue;
                     uint4 o = make_uint4(0u, 0u, 0u, 0u);
                     if (q0[i] >= 0 && cok) {
@@ -1019,8 +1052,10 @@ static bool dwproj_plan(const ssd_dwproj_desc* d, TcParams* pp, size_t* smem_out
             int pst = 0;
             for (int c = 3; c >= 2; --c) if (fixed + c * patch <= budget) { pst = c; break; }
             if (!pst) continue;
-            // MMA-row efficiency, discounted by the halo the patch re-reads
-            const double eff = (double)M / ((double)tw * th * tb * TC_BM) * ((double)bw * bh * s * s / ((double)pw * ph)) + 1e-6 * bw;
+            // MMA-row efficiency, discounted by the halo the patch re-reads; stride-1 boxes whose width is a multiple of 4
+            // run the sliding-window depthwise (half the shared-memory loads)
+            const double eff = (double)M / ((double)tw * th * tb * TC_BM) * ((double)bw * bh * s * s / ((double)pw * ph)) *
+                               ((s == 1 && bw % 4 == 0) ? 1.25 : 1.0) + 1e-6 * bw;
             if (eff > best) {
                 best = eff; p.bw = bw; p.bh = bh; p.bb = bb; p.tiles_w = tw; p.tiles_h = th;
                 p.dw_pw = pw; p.dw_ph = ph; p.dw_patch_bytes = (uint32_t)(pw * ph * bb * 128); p.dw_patch_stage = (uint32_t)patch;
@@ -1068,6 +1103,7 @@ int conv_dwproj_launch(const ssd_dwproj_desc* d, cudaStream_t st) {
     p.dw_H = d->H; p.dw_W = d->W; p.dw_C8 = d->C / 8; p.dw_stride = d->stride; p.dw_pad_t = d->pad_top; p.dw_pad_l = d->pad_left;
     p.dw_act = d->dw_act;
     p.splits = 1; p.tiles_m = p.n_tiles; p.tiles_n = 1; p.tma_store = 1; p.stages = TC_DW_ASTAGES;
+    p.dw_quad = (d->stride == 1 && p.bw % 4 == 0) ? 1 : 0;
 
     CUtensorMap map_x, map_w, map_b, map_o;
     {

@@ -251,7 +251,8 @@ class Plan:
 class _PlanBuilder:
     # depthwise + 1x1 projection as one launch (ssd_dwproj): "all", "s2" (stride-2 depthwise layers only: where the
     # fused kernel beats the two launches today) or "0"
-    FUSE_DW = os.environ.get("SSD_B200_FUSE_DW", "s2")
+    FUSE_DW = os.environ.get("SSD_B200_FUSE_DW", "all")
+    FUSE_MIN_TILES = int(os.environ.get("SSD_B200_FUSE_MIN_TILES", "0"))     # fuse only layers with at least this many 128-pixel tiles
 
     def __init__(self, model: "SSDModel", B: int):
         self.m = model
@@ -341,7 +342,7 @@ class _PlanBuilder:
             d.B, d.H, d.W, d.C = self.B, dm["x"].shape[1], dm["x"].shape[2], x.C
             d.Ho, d.Wo, d.Cout = Ho, Wo, cout
             d.stride, d.pad_top, d.pad_left, d.dw_act, d.act = dm["stride"], dm["ph"][0], dm["pw"][0], dm["act"], act
-            if not self.lib.ssd_dwproj_supported(C.byref(d)):
+            if self.B * Ho * Wo < 128 * self.FUSE_MIN_TILES or not self.lib.ssd_dwproj_supported(C.byref(d)):
                 self._emit_conv(name, x, w, b, cout, k, stride, dilation, ph, pw, act, residual, out, real_cin=real_cin)
                 return Act(out, Ho, Wo, cout)
             self.plan.steps.pop()
