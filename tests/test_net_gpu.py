@@ -171,6 +171,56 @@ def test_maxpool_and_l2norm(k, s, H):
     assert _rel(out2.float().cpu().numpy(), ref) < 2e-3
 
 
+@pytest.mark.parametrize("case", [
+    # B, H, C, Cout, stride, residual
+    (2, 19, 96, 24, 1, False), (2, 19, 144, 24, 1, True), (1, 20, 144, 32, 2, False), (3, 7, 32, 16, 1, False),
+    (2, 10, 960, 160, 1, True), (1, 33, 8, 8, 2, False), (2, 5, 64, 256, 1, False), (1, 75, 24, 16, 1, True),
+    (2, 38, 192, 64, 2, False),
+])
+def test_dwproj_fused_against_torch(case):
+    """ssd_dwproj (depthwise 3x3 + bias + ReLU6 -> 1x1 + bias (+ residual)) on shapes beyond the MobileNetV2 ones:
+    channel counts that are not multiples of 64, box widths that are / are not multiples of 4 (sliding-window and
+    per-pixel depthwise paths), partial tiles, both strides."""
+    import ctypes as C
+    from tf_ssd_b200 import _ffi
+    from tf_ssd_b200._ffi_conv import DwProjDesc
+    B, H, Cc, Cout, stride, with_res = case
+    rng = np.random.default_rng(sum(case[:5]))
+    pads = no.same_pad(H, 3, 1) if stride == 1 else no.correct_pad(H)
+    Ho = (H + pads[0] + pads[1] - 3) // stride + 1
+    x = rng.standard_normal((B, H, H, Cc)).astype(np.float16)
+    wd = (rng.standard_normal((3, 3, Cc)) / 3).astype(np.float16)
+    bd = rng.uniform(-0.2, 0.5, Cc).astype(np.float32)
+    wp = (rng.standard_normal((Cout, Cc)) / np.sqrt(Cc)).astype(np.float16)
+    bp = rng.uniform(-0.2, 0.2, Cout).astype(np.float32)
+    res = rng.standard_normal((B, Ho, Ho, Cout)).astype(np.float16) if with_res else None
+    xt = torch.from_numpy(x.astype(np.float32)).permute(0, 3, 1, 2)
+    h = F.conv2d(F.pad(xt, (pads[0], pads[1], pads[0], pads[1])), torch.from_numpy(wd.astype(np.float32)).permute(2, 0, 1).unsqueeze(1),
+                 torch.from_numpy(bd), stride=stride, groups=Cc)
+    h = torch.clamp(h, 0, 6).half().float()
+    y = F.conv2d(h, torch.from_numpy(wp.astype(np.float32)).view(Cout, Cc, 1, 1), torch.from_numpy(bp)).permute(0, 2, 3, 1)
+    if with_res:
+        y = y + torch.from_numpy(res.astype(np.float32))
+    dev = torch.device("cuda")
+    t = lambda a: torch.from_numpy(a).to(dev)
+    xd, wdd, bdd, wpd, bpd = t(x), t(wd), t(bd), t(wp), t(bp)
+    rd = t(res) if with_res else None
+    out = torch.full((B, Ho, Ho, Cout), 7.0, dtype=torch.float16, device=dev)
+    d = DwProjDesc()
+    d.inp, d.dw_weight, d.dw_bias, d.proj_weight, d.proj_bias = xd.data_ptr(), wdd.data_ptr(), bdd.data_ptr(), wpd.data_ptr(), bpd.data_ptr()
+    d.residual = rd.data_ptr() if with_res else None
+    d.out = out.data_ptr()
+    d.B, d.H, d.W, d.C, d.Ho, d.Wo, d.Cout = B, H, H, Cc, Ho, Ho, Cout
+    d.stride, d.pad_top, d.pad_left, d.dw_act, d.act = stride, pads[0], pads[0], 2, 0
+    lib = _ffi.lib()
+    assert lib.ssd_dwproj_supported(C.byref(d)) == 1
+    _ffi.check(lib.ssd_dwproj(C.byref(d), _ffi.stream()), "ssd_dwproj")
+    torch.cuda.synchronize()
+    assert _rel(out.float().cpu().numpy(), y.numpy()) < 3e-3, _rel(out.float().cpu().numpy(), y.numpy())
+    d.Cout = 320                                                    # more than one N tile: must be refused, not mis-computed
+    assert lib.ssd_dwproj_supported(C.byref(d)) == 0 and lib.ssd_dwproj(C.byref(d), _ffi.stream()) < 0
+
+
 def _model(backbone, seed=3):
     from tf_ssd_b200.models import ssd_mobilenet_v2, ssd_vgg16
     from tf_ssd_b200.utils import train_utils
