@@ -461,7 +461,7 @@ def run_b200(args):
             else:
                 ach = g["bytes"] / (g["ms"] * 1e-3) / 1e9
                 roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]}
-            roof.update({"traffic": _ncu_traffic(top, g["launches"]), "algorithmic_bytes_per_launch": g["bytes"] / max(g["launches"], 1), "kernel": {"conv": "ssd_conv2d launches: conv_tcgen05_kernel (stride 1) + conv_igemm_kernel (stride 2)",
+            roof.update({"traffic": _ncu_traffic(top, g["launches"]), "algorithmic_bytes_per_launch": g["bytes"] / max(g["launches"], 1), "kernel": {"conv": "ssd_conv2d launches: conv_tcgen05_kernel (+ conv_splitk_reduce_kernel for the multibox heads)",
                                                      "dw": "depthwise3x3_kernel", "dwproj": "conv_dwproj_tcgen05_kernel (fused depthwise 3x3 -> 1x1 projection)", "decode_nms": "nms_candidates+nms_image"}.get(top, top),
                          "launches_per_step": g["launches"], "ms_per_step": g["ms"], "share_of_step": g["ms"] / total,
                          "algorithmic_bytes_per_step": g["bytes"], "flops_per_step": g["flops"], "peak_source": peaks["source"],
