@@ -895,8 +895,9 @@ class DecoderModel(object):
         return np.concatenate(ob, 0), np.concatenate(ol, 0), np.concatenate(os_, 0)
 
 
-def smoke_forward() -> None:
-    """Tiny forward of both graphs (used by ``__graft_entry__.smoke``)."""
+def smoke_forward(check: Optional[Callable[..., None]] = None) -> None:
+    """Tiny forward of the MobileNetV2 graph (used by ``__graft_entry__.smoke``); ``check(model, hyper_params, images,
+    deltas, logits)`` lets the caller compare against its oracle (the product never imports ``oracle/``)."""
     from tf_ssd_b200.utils import train_utils
     for backbone in ("mobilenet_v2",):
         hp = train_utils.get_hyper_params(backbone)
@@ -907,3 +908,7 @@ def smoke_forward() -> None:
         torch.cuda.synchronize()
         assert d.shape == (1, model.n_anchors, 4) and p.shape == (1, model.n_anchors, 21)
         assert bool(torch.isfinite(d).all()) and bool(torch.isfinite(p).all())
+        if check is not None:
+            dd, zz = model.forward_logits(x)
+            torch.cuda.synchronize()
+            check(model, hp, x, dd.cpu().numpy(), zz.cpu().numpy())
