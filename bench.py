@@ -306,6 +306,17 @@ def _box_kernel_rooflines(peaks, hp, iters=10, warmup=3):
             lambda: _ffi.check(lib.ssd_match_encode(_ffi.ptr(priors), _ffi.ptr(gt_d), _ffi.ptr(lab_d), B, N, g_pad, L, 0.5, var,
                                                     _ffi.ptr(deltas), _ffi.ptr(onehot), None, None, _ffi.stream())),
             16 * N + 20 * B * g_pad + B * N * (16 + 4 * L))
+    # batch sweep of the anchor-IoU kernel: where the launch stops being latency-bound
+    sweep = {}
+    for b_ in (8, 32, 64, 128, 256):
+        gt, _ = synth.make_ground_truth(b_, padded=16, max_boxes=8, seed=5)
+        gt_d = _ffi.to_dev(gt)
+        iou = torch.empty((b_, N, 16), dtype=torch.float32, device=dev)
+        r = timeit(lambda: _ffi.check(lib.ssd_iou_map(_ffi.ptr(priors), _ffi.ptr(gt_d), b_, N, 16, 0, _ffi.ptr(iou), _ffi.stream())),
+                   4 * b_ * N * 16 + 16 * N + 16 * b_ * 16)
+        sweep[str(b_)] = {"ms": round(r["ms"], 5), "frac": round(r["frac"], 4)}
+        del iou
+    out["generate_iou_map_G16_batch_sweep"] = sweep
     pd, logits = synth.make_head_outputs(B, N, L, seed=6, background_bias=10.0)   # ~2.5 % of the anchors reach NMS
     pd_d, z_d = _ffi.to_dev(pd), _ffi.to_dev(logits)
     ws = _ffi.workspace(lib.ssd_loss_workspace_bytes(B, N, L))

@@ -300,7 +300,7 @@ decode_kernel(const float4* __restrict__ priors, const float4* __restrict__ delt
 constexpr int kMatchThreads = 256;
 
 template <bool NEED_IDX, bool SMEM_ONEHOT>
-__global__ void __launch_bounds__(kMatchThreads)
+__global__ void __launch_bounds__(kMatchThreads)         // (forcing 32 registers for full occupancy measured 3-12 % slower)
 match_encode_kernel(const float4* __restrict__ priors, const float4* __restrict__ gt_boxes,
                     const int32_t* __restrict__ gt_labels, int N, int G, int L, float iou_thr,
                     float4 variances, float4* __restrict__ out_deltas, float* __restrict__ out_onehot,
