@@ -846,22 +846,24 @@ static int cached_map(CUtensorMap* map, const void* base, int rank, const uint64
     return rc;
 }
 
-// split-K workspace: grown on demand, owned by the library, per device (the only allocation the
-// library makes; it happens outside stream capture because plans are warmed up before capture)
+// split-K workspace: grown on demand, owned by the library, per device (the only allocation the library makes; it
+// happens outside stream capture because plans are warmed up before capture).  A superseded buffer is NOT freed:
+// CUDA graphs captured earlier still carry its address.
 static float* g_partial[16] = {nullptr};
 static size_t g_partial_bytes[16] = {0};
+static std::mutex g_partial_mutex;
 
 static int partial_workspace(size_t bytes, float** out) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 16) return fail(SSD_ERR_UNSUPPORTED, "conv_tcgen05: device index %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_partial_mutex);
     if (g_partial_bytes[dev] < bytes) {
-        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-        (void)st;
-        if (g_partial[dev]) cudaFree(g_partial[dev]);
         size_t want = bytes < ((size_t)64 << 20) ? ((size_t)64 << 20) : bytes;
-        cudaError_t e = cudaMalloc(&g_partial[dev], want);
-        if (e != cudaSuccess) { g_partial[dev] = nullptr; g_partial_bytes[dev] = 0; return cuda_fail(e, "conv_tcgen05: split-K workspace"); }
+        float* fresh = nullptr;
+        cudaError_t e = cudaMalloc(&fresh, want);
+        if (e != cudaSuccess) return cuda_fail(e, "conv_tcgen05: split-K workspace");
+        g_partial[dev] = fresh;                                   // the previous buffer stays alive for captured graphs
         g_partial_bytes[dev] = want;
     }
     *out = g_partial[dev];
