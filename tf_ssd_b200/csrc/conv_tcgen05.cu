@@ -772,14 +772,23 @@ __global__ void __launch_bounds__(256)
 conv_splitk_reduce_kernel(const TcParams p, int rows_total) {
     pdl_trigger();
     pdl_wait();
-    const int64_t total = (int64_t)rows_total * p.Cout;
+    // one thread per (row, 4 consecutive channels): 16-byte loads of the partial planes, one row -> pixel
+    // decomposition per 4 outputs
+    const int n4 = (p.Cout + 3) >> 2;
+    const int64_t total = (int64_t)rows_total * n4;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int row = (int)(e / p.Cout), n = (int)(e - (int64_t)row * p.Cout);
+        const int row = (int)(e / n4), n = (int)(e - (int64_t)row * n4) << 2;
         int b, pix;
         if (!tc_row_to_pixel(p, row / TC_BM, row % TC_BM, b, pix)) continue;
-        float v = 0.0f;
-        for (int z = 0; z < p.splits; ++z) v += p.partial[((size_t)z * rows_total + row) * p.ldp + n];
-        tc_store_one(p, b, pix, n, v);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z = 0; z < p.splits; ++z) {
+            const float4 t = __ldcs(reinterpret_cast<const float4*>(p.partial + ((size_t)z * rows_total + row) * p.ldp + n));
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (n + k < p.Cout) tc_store_one(p, b, pix, n + k, vv[k]);
     }
 }
 
@@ -1020,7 +1029,7 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
         if (le != cudaSuccess) return cuda_fail(le, "conv_tcgen05_kernel");
     }
     if (splits > 1) {
-        const int64_t total = (int64_t)rows_total * p.Cout;
+        const int64_t total = (int64_t)rows_total * ((p.Cout + 3) / 4);
         const int64_t want = (total + 255) / 256, cap = (int64_t)sms * 8;
         int blocks = (int)(want < cap ? want : cap);
         cudaError_t le = launch_pdl(conv_splitk_reduce_kernel, dim3(blocks), dim3(256), 0, st, p, rows_total);
