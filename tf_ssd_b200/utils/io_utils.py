@@ -14,28 +14,32 @@ VALID_BACKBONES = ("mobilenet_v2", "vgg16")
 
 
 def get_log_path(model_type: str, custom_postfix: str = "") -> str:
-    """utils/io_utils.py:13-24."""
-    return "logs/{}{}/{}".format(model_type, custom_postfix, datetime.now().strftime("%Y%m%d-%H%M%S"))
+    """utils/io_utils.py:13-24: ``logs/<model><postfix>/<YYYYmmdd-HHMMSS>``."""
+    stamp = datetime.now().strftime("%Y%m%d-%H%M%S")
+    return os.path.join("logs", f"{model_type}{custom_postfix}", stamp)
 
 
 def get_model_path(model_type: str, main_path: str = "trained") -> str:
-    """utils/io_utils.py:27-39 (``.npz`` instead of ``.h5``)."""
+    """utils/io_utils.py:27-39 (``.npz`` instead of ``.h5``); creates the directory."""
     os.makedirs(main_path, exist_ok=True)
-    return os.path.join(main_path, "ssd_{}_model_weights.npz".format(model_type))
+    return os.path.join(main_path, f"ssd_{model_type}_model_weights.npz")
 
 
 def handle_args(argv: Optional[Sequence[str]] = None) -> argparse.Namespace:
     """utils/io_utils.py:42-56: ``-handle-gpu`` and ``--backbone``; the extra options size a run on synthetic
     VOC-shaped data (there is no dataset access in this environment)."""
     parser = argparse.ArgumentParser(description="SSD: Single Shot MultiBox Detector Implementation (B200-native hot path)")
-    parser.add_argument("-handle-gpu", action="store_true", help="accepted for compatibility; nothing to do without TensorFlow")
-    parser.add_argument("--backbone", required=False, default="mobilenet_v2", metavar="['mobilenet_v2', 'vgg16']",
-                        help="Which backbone used for the ssd")
-    parser.add_argument("--epochs", type=int, default=150)
-    parser.add_argument("--batch-size", type=int, default=32)
-    parser.add_argument("--train-items", type=int, default=0, help="synthetic items per epoch (0: dataset default)")
-    parser.add_argument("--val-items", type=int, default=0)
-    parser.add_argument("--model-dir", default="trained")
+    options = [
+        (("-handle-gpu",), dict(action="store_true", help="accepted for compatibility; nothing to do without TensorFlow")),
+        (("--backbone",), dict(default=VALID_BACKBONES[0], metavar=str(list(VALID_BACKBONES)), help="Which backbone used for the ssd")),
+        (("--epochs",), dict(type=int, default=150)),
+        (("--batch-size",), dict(type=int, default=32)),
+        (("--train-items",), dict(type=int, default=0, help="synthetic items per epoch (0: dataset default)")),
+        (("--val-items",), dict(type=int, default=0)),
+        (("--model-dir",), dict(default="trained")),
+    ]
+    for flags, kw in options:
+        parser.add_argument(*flags, **kw)
     return parser.parse_args(argv)
 
 
