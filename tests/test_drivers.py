@@ -68,6 +68,57 @@ def test_average_precision_arithmetic():
     assert stats[2]["AP"] == 0.0 and m_ap == pytest.approx(stats[1]["AP"] / 2)
 
 
+def test_reference_kats_of_the_driver_modules(tmp_path, monkeypatch):
+    """The known-answer tests the reference keeps for these modules (tests/test_eval_utils.py:110-147,
+    tests/test_io_utils.py:17-57, tests/test_data_utils.py:31-71 of FurkanOM/tf-ssd), restated on this package."""
+    import types
+    from datetime import datetime
+    from tf_ssd_b200.utils import data_utils, eval_utils, io_utils
+    # eval_utils
+    stats = eval_utils.init_stats(["bg", "person", "car"])
+    assert sorted(stats.keys()) == [1, 2] and stats[1]["label"] == "person" and stats[2]["total"] == 0
+    ap = eval_utils.calculate_ap(np.array([0.25, 0.5, 0.75, 1.0]), np.array([1.0, 0.75, 0.5, 0.25]))
+    assert ap == pytest.approx(0.6363636364)
+    st = {1: {"label": "person", "total": 1, "tp": [1, 0], "fp": [0, 1], "scores": [0.9, 0.2]},
+          2: {"label": "car", "total": 1, "tp": [0, 1], "fp": [1, 0], "scores": [0.1, 0.8]}}
+    out, m_ap = eval_utils.calculate_mAP(st)
+    assert out[1]["AP"] == pytest.approx(1.0) and out[2]["AP"] == pytest.approx(1.0) and m_ap == pytest.approx(1.0)
+    assert list(out[2]["recall"]) == [1.0, 1.0]
+    # io_utils
+
+    class FixedDateTime:
+        @staticmethod
+        def now():
+            return datetime(2020, 1, 2, 3, 4, 5)
+    monkeypatch.setattr(io_utils, "datetime", FixedDateTime)
+    assert io_utils.get_log_path("mobilenet_v2", custom_postfix="_debug") == "logs/mobilenet_v2_debug/20200102-030405"
+    monkeypatch.chdir(tmp_path)
+    path = io_utils.get_model_path("vgg16")
+    assert os.path.isdir(os.path.join(str(tmp_path), "trained"))
+    assert path == "trained/ssd_vgg16_model_weights.npz"             # the reference writes .h5 (no h5py here)
+    monkeypatch.setattr("sys.argv", ["prog", "-handle-gpu", "--backbone", "vgg16"])
+    args = io_utils.handle_args()
+    assert args.handle_gpu and args.backbone == "vgg16"
+    io_utils.is_valid_backbone("mobilenet_v2")
+    with pytest.raises(AssertionError):
+        io_utils.is_valid_backbone("resnet50")
+    # data_utils
+    info = types.SimpleNamespace(splits={"train": types.SimpleNamespace(num_examples=8),
+                                         "validation": types.SimpleNamespace(num_examples=3),
+                                         "test": types.SimpleNamespace(num_examples=5)},
+                                 features={"labels": types.SimpleNamespace(names=["person", "car", "dog"])})
+    assert data_utils.get_total_item_size(info, "train+validation") == 11 and data_utils.get_total_item_size(info, "test") == 5
+    assert data_utils.get_labels(info) == ["person", "car", "dog"]
+    top = [str(tmp_path / "first.jpg"), str(tmp_path / "second.png")]
+    os.makedirs(str(tmp_path / "nested"))
+    for f in top + [str(tmp_path / "nested" / "ignored.jpg")]:
+        open(f, "w").write("placeholder")
+    assert sorted(p for p in data_utils.get_custom_imgs(str(tmp_path)) if not p.endswith("trained")) == sorted(top)
+    assert data_utils.get_data_types() == ("float32", "float32", "int32")
+    assert data_utils.get_data_shapes() == ([None, None, None], [None, None], [None])
+    assert data_utils.get_padding_values() == (0, 0, -1)
+
+
 def _update_stats_reference(pb, pl, ps, gb, gl, stats):
     """utils/eval_utils.py:36-91 restated with the oracle's IoU map."""
     iou = bo.iou_map(pb, gb)

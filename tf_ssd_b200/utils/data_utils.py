@@ -92,14 +92,32 @@ def get_dataset(name: str, split: str, data_dir: str = "~/tensorflow_datasets", 
     return SyntheticVOC(n, img_size=img_size, seed=seed), {"name": name, "splits": {split: n}, "labels": list(VOC_LABELS)}
 
 
-def get_total_item_size(info: Dict[str, Any], split: str) -> int:
-    """utils/data_utils.py:59-72."""
-    return int(info["splits"][split])
+def get_total_item_size(info: Any, split: str) -> int:
+    """utils/data_utils.py:59-72: ``"train+validation"`` sums the named splits.  Accepts the synthetic ``info`` dict of
+    ``get_dataset`` as well as a TFDS ``DatasetInfo`` (``info.splits[name].num_examples``)."""
+    splits = info["splits"] if isinstance(info, dict) else info.splits
+    if split in splits and not hasattr(splits[split], "num_examples"):
+        return int(splits[split])
+    total = 0
+    for name in split.split("+"):
+        item = splits[name]
+        total += int(getattr(item, "num_examples", item))
+    return total
 
 
-def get_labels(info: Dict[str, Any]) -> List[str]:
-    """utils/data_utils.py:75-85."""
-    return list(info["labels"])
+def get_labels(info: Any) -> List[str]:
+    """utils/data_utils.py:75-85 (TFDS: ``info.features["labels"].names``)."""
+    if isinstance(info, dict):
+        return list(info["labels"])
+    return list(info.features["labels"].names)
+
+
+def get_custom_imgs(custom_image_path: str) -> List[str]:
+    """utils/data_utils.py:88-101: the files directly inside ``custom_image_path`` (sub-directories are ignored)."""
+    import os
+    for path, _, files in os.walk(custom_image_path):
+        return [os.path.join(path, name) for name in files]
+    return []
 
 
 def preprocessing(image_data: Any, final_height: int, final_width: int, augmentation_fn: Any = None, evaluate: bool = False):
@@ -109,7 +127,8 @@ def preprocessing(image_data: Any, final_height: int, final_width: int, augmenta
 
 
 def get_data_types():
-    return (np.float32, np.float32, np.int32)
+    """utils/data_utils.py:127-137 (NumPy dtypes instead of TensorFlow's)."""
+    return (np.dtype("float32"), np.dtype("float32"), np.dtype("int32"))
 
 
 def get_data_shapes():
