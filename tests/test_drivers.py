@@ -179,3 +179,20 @@ def test_trainer_and_predictor_flows(tmp_path):
         assert "block_13_expand/kernel" in z.files and "bn_Conv1/moving_mean" in z.files and z["Conv1/kernel"].shape == (3, 3, 3, 32)
     stats = predictor.main(argv)
     assert sorted(stats) == list(range(1, 21)) and all("AP" in v for v in stats.values())
+
+
+def test_reference_kats_of_train_utils():
+    """tests/test_train_utils.py:27-60 of the reference, restated on the package's host-side mirror."""
+    from tf_ssd_b200.utils import train_utils
+    params = train_utils.get_hyper_params("vgg16")
+    assert params["img_size"] == 300 and params["iou_threshold"] == 0.5 and params["neg_pos_ratio"] == 3
+    assert params["loc_loss_alpha"] == 1 and params["variances"] == [0.1, 0.1, 0.2, 0.2]
+    over = train_utils.get_hyper_params("mobilenet_v2", img_size=320, iou_threshold=0.6)
+    assert over["img_size"] == 320 and over["iou_threshold"] == 0.6
+    assert train_utils.get_hyper_params("vgg16", img_size=0)["img_size"] == 300          # falsy overrides are ignored
+    params["img_size"] = 320
+    assert train_utils.SSD["vgg16"]["img_size"] == 300                                  # a copy, not the table itself
+    assert train_utils.scheduler(0) == 1e-3 and train_utils.scheduler(110) == 1e-4 and train_utils.scheduler(130) == 1e-5
+    assert train_utils.get_step_size(10, 4) == 3 and train_utils.get_step_size(8, 4) == 2
+    assert train_utils.SSD["mobilenet_v2"]["feature_map_shapes"] == [19, 10, 5, 3, 2, 1]
+    assert train_utils.SSD["vgg16"]["feature_map_shapes"] == [38, 19, 10, 5, 3, 1]
