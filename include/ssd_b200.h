@@ -238,6 +238,14 @@ int ssd_stem_conv3x3s2(const float* d_img, const void* d_weight, const float* d_
                        int B, int H, int W, int Cout, int Ho, int Wo, int pad_top, int pad_left, int act,
                        ssd_stream_t stream);
 
+/* Device-side input pipeline.  utils/data_utils.py:33-37: tf.image.convert_image_dtype(uint8 ->
+ * float32) + tf.image.resize(img, (out_h, out_w)) (bilinear, half-pixel centres), optionally followed by
+ * augmentation.py:119-139 flip_left_right, in one pass: d_img_u8 [H,W,3] uint8 -> d_out [out_h,out_w,3] float32
+ * (one slot of the NHWC batch).  ssd_flip_boxes mirrors n boxes [y1,x1,y2,x2] in place (all-zero padding stays). */
+int ssd_preprocess_image(const void* d_img_u8, int H, int W, float* d_out, int out_h, int out_w, int flip,
+                         ssd_stream_t stream);
+int ssd_flip_boxes(float* d_boxes, int n, ssd_stream_t stream);
+
 /* fp32 NHWC image [B,H,W,3] (utils/data_utils.py:36 convert_image_dtype output)
  * -> fp16 NHWC with the channel dimension zero-padded to 8. */
 int ssd_image_to_f16c8(const float* d_img, void* d_out, int64_t n_pixels, ssd_stream_t stream);

@@ -378,3 +378,41 @@ def ssd_decode(priors, variances, pred_deltas, pred_label_probs, max_total_size:
     if return_aux:
         return fb, fc, fs, valid, fi
     return fb, fc, fs
+
+
+# --------------------------------------------------------------------------
+# input pipeline  (utils/data_utils.py:33-37, augmentation.py:119-139)
+# --------------------------------------------------------------------------
+def preprocess_image(img_u8: np.ndarray, out_h: int, out_w: int, flip: bool = False) -> np.ndarray:
+    """``tf.image.convert_image_dtype(img, tf.float32)`` then ``tf.image.resize(img, (out_h, out_w))``
+    (utils/data_utils.py:36-37), optionally ``tf.image.flip_left_right`` (augmentation.py:127).  [TF-recall]
+    convert = cast * float32(1/255); resize = bilinear with half-pixel centres
+    (``in = (out + 0.5) * scale - 0.5``, lower = max(floor, 0), upper = min(ceil, size-1), lerp = in - floor),
+    one float32 rounding per operation like the TensorFlow kernel."""
+    img = np.asarray(img_u8, dtype=np.uint8)
+    H, W = img.shape[:2]
+    x = img.astype(F32) * F32(1.0 / 255.0)
+    sy, sx = F32(F32(H) / F32(out_h)), F32(F32(W) / F32(out_w))
+    in_y = ((np.arange(out_h, dtype=F32) + F32(0.5)) * sy - F32(0.5)).astype(F32)
+    in_x = ((np.arange(out_w, dtype=F32) + F32(0.5)) * sx - F32(0.5)).astype(F32)
+    fy, fx = np.floor(in_y), np.floor(in_x)
+    y0 = np.maximum(fy.astype(np.int64), 0); y1 = np.minimum(np.ceil(in_y).astype(np.int64), H - 1)
+    x0 = np.maximum(fx.astype(np.int64), 0); x1 = np.minimum(np.ceil(in_x).astype(np.int64), W - 1)
+    ly = (in_y - fy).astype(F32)[:, None, None]
+    lx = (in_x - fx).astype(F32)[None, :, None]
+    tl, tr = x[y0][:, x0], x[y0][:, x1]
+    bl, br = x[y1][:, x0], x[y1][:, x1]
+    top = (tl + ((tr - tl).astype(F32) * lx).astype(F32)).astype(F32)
+    bot = (bl + ((br - bl).astype(F32) * lx).astype(F32)).astype(F32)
+    out = (top + ((bot - top).astype(F32) * ly).astype(F32)).astype(F32)
+    return out[:, ::-1].copy() if flip else out
+
+
+def flip_boxes(gt_boxes: np.ndarray) -> np.ndarray:
+    """augmentation.py:128-137: ``[y1, 1 - x2, y2, 1 - x1]`` (all-zero padding rows are left untouched)."""
+    b = np.asarray(gt_boxes, dtype=F32)
+    out = np.stack([b[..., 0], F32(1.0) - b[..., 3], b[..., 2], F32(1.0) - b[..., 1]], axis=-1).astype(F32)
+    pad = ~b.any(axis=-1)
+    out[pad] = 0
+    return out
+

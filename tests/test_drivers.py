@@ -196,3 +196,39 @@ def test_reference_kats_of_train_utils():
     assert train_utils.get_step_size(10, 4) == 3 and train_utils.get_step_size(8, 4) == 2
     assert train_utils.SSD["mobilenet_v2"]["feature_map_shapes"] == [19, 10, 5, 3, 2, 1]
     assert train_utils.SSD["vgg16"]["feature_map_shapes"] == [38, 19, 10, 5, 3, 1]
+
+
+def test_preprocess_oracle_against_torch_interpolate():
+    """The oracle's resize (TF half-pixel bilinear) agrees with torch's align_corners=False bilinear (same sampling rule)."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(4)
+    for (H, W, S) in [(375, 500, 300), (120, 90, 300), (512, 512, 512), (333, 77, 64)]:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        got = bo.preprocess_image(img, S, S)
+        ref = F.interpolate(torch.from_numpy(img.astype(np.float32) / 255).permute(2, 0, 1)[None], size=(S, S), mode="bilinear",
+                            align_corners=False, antialias=False)[0].permute(1, 2, 0).numpy()
+        assert got.shape == (S, S, 3) and np.abs(got - ref).max() < 1e-5      # interpolation weights are rounded differently
+        assert np.array_equal(bo.preprocess_image(img, S, S, flip=True), got[:, ::-1])
+    b = np.array([[0.1, 0.2, 0.5, 0.6], [0, 0, 0, 0]], np.float32)
+    assert np.allclose(bo.flip_boxes(b), [[0.1, 0.4, 0.5, 0.8], [0, 0, 0, 0]])
+
+
+@pytest.mark.gpu
+def test_device_preprocess_bit_exact():
+    import torch
+    from tf_ssd_b200.utils import data_utils
+    rng = np.random.default_rng(8)
+    batch = torch.zeros((3, 300, 300, 3), dtype=torch.float32, device="cuda")
+    for i, (H, W, flip) in enumerate([(375, 500, False), (120, 90, True), (300, 300, False)]):
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        data_utils.device_preprocess(img, out=batch[i], flip=flip)
+        ref = bo.preprocess_image(img, 300, 300, flip=flip)
+        got = batch[i].cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (H, W, flip, np.abs(got - ref).max())
+    out = data_utils.device_preprocess(rng.integers(0, 256, (64, 48, 3), dtype=np.uint8), final_height=512, final_width=512)
+    assert out.shape == (512, 512, 3) and float(out.min()) >= 0 and float(out.max()) <= 1
+    boxes = np.array([[[0.1, 0.2, 0.5, 0.6], [0.3, 0.0, 0.9, 1.0], [0, 0, 0, 0]]], np.float32)
+    got = data_utils.device_flip_boxes(boxes.copy()).cpu().numpy()
+    assert np.array_equal(got, bo.flip_boxes(boxes))
+

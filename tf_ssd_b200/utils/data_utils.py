@@ -139,3 +139,31 @@ def get_data_shapes():
 def get_padding_values():
     """utils/data_utils.py:150-155."""
     return (np.float32(0), np.float32(0), np.int32(-1))
+
+
+def device_preprocess(img_u8: Any, out: Any = None, final_height: int = 300, final_width: int = 300, flip: bool = False):
+    """The per-example work of ``preprocessing`` (utils/data_utils.py:33-37) on the DEVICE: uint8 ``[H,W,3]`` ->
+    float32 ``[final_height, final_width, 3]`` in [0,1] (convert_image_dtype + bilinear resize, half-pixel centres),
+    optionally mirrored (augmentation.py:flip_horizontally), written into ``out`` -- typically one slot
+    ``batch[i]`` of the NHWC batch buffer the network reads, so no host-side resize / float image ever exists."""
+    import torch
+    from tf_ssd_b200 import _ffi
+    src = _ffi.to_dev(img_u8, dtype=torch.uint8)
+    if src.dim() != 3 or src.shape[2] != 3:
+        raise ValueError("expected a uint8 image [H, W, 3]")
+    if out is None:
+        out = torch.empty((final_height, final_width, 3), dtype=torch.float32, device=src.device)
+    if tuple(out.shape) != (final_height, final_width, 3) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float32 [final_height, final_width, 3] CUDA tensor")
+    _ffi.check(_ffi.lib().ssd_preprocess_image(_ffi.ptr(src), int(src.shape[0]), int(src.shape[1]), _ffi.ptr(out), final_height,
+                                               final_width, int(bool(flip)), _ffi.stream()), "ssd_preprocess_image")
+    return out
+
+
+def device_flip_boxes(gt_boxes: Any):
+    """augmentation.py:128-137 on the device, in place on a float32 ``[..., 4]`` CUDA tensor (padding rows stay zero)."""
+    from tf_ssd_b200 import _ffi
+    b = _ffi.to_dev(gt_boxes)
+    _ffi.check(_ffi.lib().ssd_flip_boxes(_ffi.ptr(b), int(b.numel() // 4), _ffi.stream()), "ssd_flip_boxes")
+    return b
+
