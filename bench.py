@@ -428,7 +428,13 @@ def run_b200(args):
         training = {}
         for bb, key in (("mobilenet_v2", "ssd300_mobilenet_v2_b32_per_gpu"), ("vgg16", "ssd300_vgg16_b32_per_gpu")):
             train_bench.BACKBONE = bb
-            training[key] = train_bench.measure(steps=args.train_steps, warmup=3, batch=32)
+            if world == 1:
+                try:                    # a side measurement must never cost the headline line (single process: no peer can hang)
+                    training[key] = train_bench.measure(steps=args.train_steps, warmup=3, batch=32)
+                except Exception as exc:  # noqa: BLE001
+                    training[key] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            else:
+                training[key] = train_bench.measure(steps=args.train_steps, warmup=3, batch=32)
             torch.cuda.empty_cache()
 
     if rank == 0:
@@ -483,7 +489,10 @@ def run_b200(args):
                                      "tflops": round(s.flops / (ms * 1e-3) / 1e12, 2), "gbs": round(s.bytes / (ms * 1e-3) / 1e9, 1)}
                                     for ms, s in worst]
             if not args.skip_box:
-                line["box_kernels"] = _box_kernel_rooflines(peaks, hp)
+                try:
+                    line["box_kernels"] = _box_kernel_rooflines(peaks, hp)
+                except Exception as exc:  # noqa: BLE001
+                    line["box_kernels"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
             if not args.skip_cpu:
                 from oracle import box_oracle as bo
                 line["cpu_baseline"] = cpu_baseline(model.weights, hp, bo.prior_boxes(hp["feature_map_shapes"], hp["aspect_ratios"]))
