@@ -558,3 +558,25 @@ def test_mobilenet_v2_training_reduces_loss_and_updates_batchnorm():
     dec = get_decoder_model(model, bo.prior_boxes(hp["feature_map_shapes"], hp["aspect_ratios"]), hp)
     b, l, s = dec(img)
     assert b.shape == (4, 200, 4) and bool(torch.isfinite(b).all())
+
+
+@pytest.mark.parametrize("setup", ["mobilenet_v2", "vgg16"])
+def test_load_weights_after_compile_reaches_the_trainer(setup):
+    """trainer.py:91-99 compiles first and loads weights afterwards: the trainer's device variables must follow."""
+    from tf_ssd_b200.models.train_engine import Adam
+    from tf_ssd_b200.ssd_loss import CustomLoss
+    model, hp, img, ad, al = (_mnv2_setup if setup == "mobilenet_v2" else _vgg_setup)(2, seed=7)
+    loss = CustomLoss(hp["neg_pos_ratio"], hp["loc_loss_alpha"])
+    model.compile(optimizer=Adam(learning_rate=1e-3), loss=[loss.loc_loss_fn, loss.conf_loss_fn])
+    model.train_on_batch(img, (ad, al))
+    saved = {k: v.copy() for k, v in model.weights.items()}
+    key = "1_conv_label_output/kernel"
+    new = {k: (v * 0.5).astype(np.float32) if k == key else v for k, v in saved.items()}
+    model.set_weights(new)
+    got = model.trainer.vars["1_conv_head/kernel"]["master"].cpu().numpy()
+    want = new[key].transpose(3, 0, 1, 2)
+    assert np.allclose(got[:want.shape[0], :, :, :want.shape[3]], want, atol=1e-3)
+    assert np.isfinite(model.train_on_batch(img, (ad, al))["loss"])
+    model.trainer.sync_weights_to_host()
+    assert not np.array_equal(model.weights[key], saved[key])
+

@@ -524,7 +524,14 @@ class SSDModel(object):
             if tuple(v.shape) != tuple(self.weights[k].shape):
                 raise ValueError(f"{k}: shape {v.shape} != {self.weights[k].shape}")
             self.weights[k] = np.ascontiguousarray(v, dtype=np.float32)
+        # ``load_weights`` after ``compile`` (trainer.py:91-99 loads AFTER compiling): the trainer's device-side
+        # variables are rebuilt from the new host values (optimizer moments restart at zero)
+        trainer = getattr(self, "trainer", None)
+        self.trainer = None
         self._invalidate()
+        if trainer is not None:
+            from tf_ssd_b200.models.train_engine import Trainer
+            self.trainer = Trainer(self, **trainer.init_kwargs)
 
     def get_weights(self) -> Dict[str, np.ndarray]:
         return dict(self.weights)

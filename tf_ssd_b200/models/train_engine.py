@@ -88,6 +88,9 @@ class Trainer(object):
                  beta_1: float = 0.9, beta_2: float = 0.999, epsilon: float = 1e-7, loss_scale: float = 1024.0,
                  use_cuda_graph: bool = True):
         _ffi.check_device()
+        self.init_kwargs = dict(learning_rate=learning_rate, neg_pos_ratio=neg_pos_ratio, loc_loss_alpha=loc_loss_alpha,
+                                beta_1=beta_1, beta_2=beta_2, epsilon=epsilon, loss_scale=loss_scale,
+                                use_cuda_graph=use_cuda_graph)
         self.model = model
         model.trainer = self                         # the model's training-mode variables now belong to this trainer
         self.use_cuda_graph = bool(use_cuda_graph)
