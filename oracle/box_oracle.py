@@ -1,8 +1,10 @@
 """NumPy restatement of the reference's box math, targets, loss and decode+NMS.
 
-TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  PARITY UNPINNED
-against TensorFlow: every rule that comes from TensorFlow itself rather than
-from ``/root/reference`` is tagged ``[TF-recall]``.
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Pinned by fixtures that
+the reference's own source produced on the NumPy ``tensorflow`` stand-in
+(``tests/golden/ref_*.npz``, ``tests/test_ref_golden.py``: bit-exact for priors,
+IoU, targets and NMS selection); rules that come from TensorFlow itself and that
+its documentation does not pin are tagged ``[TF-recall]``.
 
 All arithmetic is float32 with one rounding per elementary operation, exactly
 as a chain of separate TensorFlow eager ops would produce it (TensorFlow never

@@ -1,9 +1,12 @@
 """torch-CPU restatement of the reference's two SSD graphs (forward only).
 
-TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  PARITY UNPINNED
-against Keras: TensorFlow/Keras are not installable here, so the MobileNetV2
-topology (keras-applications 1.0.8, ``environment.yml:32``) and the Keras layer
-semantics (SAME padding, BatchNormalization, ReLU6) are ``[TF-recall]``.
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  The float32 forward is
+pinned (1e-4 of the output range, variable names and shapes exact) by fixtures
+that the reference's own ``models/ssd_vgg16.py``, ``models/ssd_mobilenet_v2.py``
+and ``models/header.py`` produced on the Keras stand-in of ``tests/tf_shim``
+(``tests/golden/ref_net.npz``).  Still ``[TF-recall]``: the MobileNetV2 backbone
+constructor (keras-applications 1.0.8, ``environment.yml:32`` -- third-party, not
+under /root/reference) and BatchNormalization's epsilon.
 
 Weights are a flat dict keyed ``"<keras layer name>/<variable>"`` holding
 float32 NumPy arrays in Keras layouts: ``kernel`` HWIO, ``depthwise_kernel``

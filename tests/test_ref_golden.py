@@ -1,0 +1,228 @@
+"""Parity against fixtures produced by the reference's OWN source.
+
+``tests/golden/ref_*.npz`` were written by ``tests/golden/make_ref_golden.py``: the unmodified modules under
+``/root/reference`` (utils/bbox_utils.py, utils/train_utils.py, ssd_loss.py, models/decoder.py, models/header.py,
+models/ssd_vgg16.py, models/ssd_mobilenet_v2.py) executed on the NumPy-backed ``tensorflow`` stand-in in
+``tests/tf_shim``.  Three kinds of test:
+
+* CPU: the committed fixtures are reproducible from the reference (only where /root/reference exists);
+* CPU: the oracle (``oracle/``) reproduces them -- bit-exact for priors, IoU, indices, one-hot targets, NMS selection;
+* GPU: the CUDA path, through the C ABI, reproduces them -- bit-exact for integer/index results, 1e-4 relative for
+  float32 box / loss tensors (north_star), fp16-storage yardstick for the networks.
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+from oracle import box_oracle as bo
+from oracle import net_oracle as no
+from tests.golden import ref_inputs as ri
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = {k: np.load(os.path.join(HERE, "golden", f"ref_{k}.npz")) for k in ("priors", "box", "loss", "decode", "net")}
+VAR = ri.VARIANCES
+RTOL = 1e-4                  # north_star: box / loss tensors within 1e-4 relative float32
+HAVE_REFERENCE = os.path.isdir(os.environ.get("SSD_REFERENCE_DIR", "/root/reference"))
+
+
+def _targets():
+    pri = REF["priors"]["priors_mobilenet_v2"]
+    gt, lab = ri.ground_truth(3, 8, seed=11)
+    assert np.array_equal(gt, REF["box"]["gt_rand"]) and np.array_equal(lab, REF["box"]["lab_rand"])
+    return pri, gt, lab
+
+
+# ------------------------------------------------------------ reproducibility --
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="/root/reference is not present on this machine")
+@pytest.mark.parametrize("which", ["priors", "box", "loss", "decode"])
+def test_fixtures_regenerate_from_the_reference_source(which):
+    """Running the reference's modules under the shim again yields the committed bytes."""
+    from tests.golden import make_ref_golden as gen
+    fresh = gen.generate([which])[which]
+    assert sorted(fresh) == sorted(REF[which].files)
+    for k, v in fresh.items():
+        assert v.dtype == REF[which][k].dtype and np.array_equal(v, REF[which][k], equal_nan=v.dtype.kind == "f"), k
+
+
+def test_shim_is_independent_of_the_oracle_and_the_product():
+    for dirpath, _, files in os.walk(os.path.join(HERE, "tf_shim")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "tf_ssd_b200" not in src.replace(
+                    "``tf_ssd_b200``", ""), f
+    src = open(os.path.join(HERE, "golden", "make_ref_golden.py")).read()
+    assert "from oracle" not in src and "import oracle" not in src and "import tf_ssd_b200" not in src
+
+
+# ------------------------------------------------------------- oracle (CPU) --
+def test_oracle_priors_bit_exact():
+    assert REF["priors"]["scale_k3"][0] == pytest.approx(0.48)          # the reference's own KAT (tests/test_bbox_utils.py:19-22)
+    for name, (fm, ars) in ri.PRIOR_CONFIGS.items():
+        assert np.array_equal(bo.prior_boxes(fm, ars), REF["priors"][f"priors_{name}"]), name
+        for i in (0, len(fm) - 1):
+            assert np.array_equal(bo.base_prior_boxes(ars[i], i + 1, len(fm)), REF["priors"][f"base_{name}_{i + 1}"])
+    assert REF["priors"]["priors_vgg16"].shape == (8732, 4) and REF["priors"]["priors_vgg16_512"].shape == (24564, 4)
+
+
+def test_oracle_iou_match_encode_bit_exact():
+    X = REF["box"]
+    pri = REF["priors"]["priors_mobilenet_v2"]
+    for tag in ("rand", "snap"):
+        gt, lab = X[f"gt_{tag}"], X[f"lab_{tag}"]
+        assert np.array_equal(bo.iou_map(pri, gt), X[f"iou_{tag}"])
+        d, oh = bo.match_encode(pri, gt, lab, 21, 0.5, VAR)
+        assert np.array_equal(oh, X[f"onehot_{tag}"].astype(np.float32))
+        assert np.array_equal(d, X[f"deltas_{tag}"])
+    lat, gtt, labt = ri.tie_case()
+    iou = bo.iou_map(lat, gtt)
+    assert np.array_equal(iou, X["iou_tie"]) and (iou == 0.5).any()
+    d, oh = bo.match_encode(lat, gtt, labt, 21, 0.5, VAR)
+    assert np.array_equal(oh, X["onehot_tie"].astype(np.float32)) and np.array_equal(d, X["deltas_tie"])
+    assert not (X["onehot_tie"][0].argmax(-1) == 9).any()          # the duplicated box never wins: first maximum
+    assert np.array_equal(bo.iou_map(X["eval_boxes"], X["gt_rand"]), X["iou_eval"])
+    assert np.array_equal(bo.iou_map(pri[:500], X["gt_rand"][0], transpose_perm=[1, 0]), X["iou_rank2"])
+    assert np.array_equal(bo.iou_map(X["deg_a"], X["deg_g"]), X["iou_deg"], equal_nan=True)
+    assert np.isnan(X["iou_deg"][0, 0, 0])                            # 0/0 (bbox_utils.py:55)
+    assert np.array_equal(bo.deltas_from_boxes(X["enc_priors"], X["enc_gt"]), X["enc_deltas"])
+    got = bo.boxes_from_deltas(pri, X["dec_in_deltas"] * np.array(VAR, np.float32))
+    np.testing.assert_allclose(got, X["dec_boxes"], rtol=1e-6, atol=1e-7)
+
+
+def test_oracle_losses():
+    Ls = REF["loss"]
+    pri, gt, lab = _targets()
+    ad, al = bo.match_encode(pri, gt, lab, 21, 0.5, VAR)
+    pd, probs = Ls["pred_deltas"], Ls["pred_probs"]
+    y, p, ead, epd = ri.loss_edge_inputs()
+    for ratio, alpha, tag in ((3.0, 1.0, "r3a1"), (2.0, 0.5, "r2a05")):
+        for sfx in ("", "_tf20"):                                    # Huber mean*4 (TF >= 2.2) and element-wise (2.0/2.1)
+            np.testing.assert_allclose(bo.loc_loss(ad, pd, alpha), Ls[f"loc_{tag}{sfx}"], rtol=1e-6)
+            np.testing.assert_allclose(bo.loc_loss(ead, epd, alpha), Ls[f"edge_loc_{tag}{sfx}"], rtol=1e-6)
+        np.testing.assert_allclose(bo.conf_loss(al, probs, ratio), Ls[f"conf_{tag}"], rtol=1e-6)
+        np.testing.assert_allclose(bo.conf_loss(y, p, ratio), Ls[f"edge_conf_{tag}"], rtol=1e-6)
+    assert Ls["rank_example"].tolist() == [[4, 1, 2, 5, 0, 3]]
+    assert bo.hard_negative_rank(np.array([[0, .5, .5, 0, 2, .1]], np.float32)).tolist() == [[4, 1, 2, 5, 0, 3]]
+
+
+def test_oracle_decoder_selection_exact():
+    D = REF["decode"]
+    for tag, cfg, B, seed, bg in ri.DECODE_CASES:
+        pri = REF["priors"][f"priors_{cfg}"]
+        pd, probs, _ = ri.head_outputs(B, pri.shape[0], seed=seed, background_bias=bg)
+        b, l, s = bo.ssd_decode(pri, VAR, pd, probs)
+        assert np.array_equal(l, D[f"{tag}_labels"]) and np.array_equal(s, D[f"{tag}_scores"]), tag
+        np.testing.assert_allclose(b, D[f"{tag}_boxes"], rtol=1e-6, atol=1e-7)
+    assert (D["mnv2_sparse_count"] < 200).all() and (D["mnv2_dense_count"] == 200).all()
+    boxes, scores = ri.nms_tie_inputs()
+    r = bo.combined_nms(boxes, scores, 10, 40, score_threshold=0.5)
+    for got, k in zip(r, ("nms_boxes", "nms_scores", "nms_classes", "nms_valid")):
+        assert np.array_equal(got, D[k]), k
+
+
+@pytest.mark.parametrize("name", ["vgg16", "mobilenet_v2"])
+def test_oracle_networks_match_the_reference_graphs(name):
+    """Keras variable names / shapes and the float32 forward of the reference's model files."""
+    from tf_ssd_b200.models.engine import SSDModel
+    from tf_ssd_b200.utils import train_utils
+    Nn = REF["net"]
+    hp = train_utils.get_hyper_params(name)
+    hp["total_labels"] = 21
+    m = SSDModel(name, hp, seed=0)
+    mine = sorted(f"{k}:{','.join(map(str, v.shape))}" for k, v in m.weights.items())
+    assert mine == list(Nn[f"{name}_variables"])                      # same variables under the same Keras names
+    w = ri.weights_for({k: v.shape for k, v in m.weights.items()})
+    d, p = no.forward(name, w, hp, ri.image(1, 300), mode="fp32")
+    rd, rp = Nn[f"{name}_deltas"], Nn[f"{name}_probs"]
+    assert np.abs(d - rd).max() < 1e-4 * np.abs(rd).max() and np.abs(p - rp).max() < 1e-4
+
+
+# ------------------------------------------------------------------ CUDA (GPU) --
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.gpu
+def test_cuda_priors_iou_match_encode():
+    from tf_ssd_b200.utils import bbox_utils, train_utils
+    X = REF["box"]
+    for name, (fm, ars) in ri.PRIOR_CONFIGS.items():
+        assert np.array_equal(_np(bbox_utils.generate_prior_boxes(fm, ars)), REF["priors"][f"priors_{name}"]), name
+    pri = REF["priors"]["priors_mobilenet_v2"]
+    hp = {"total_labels": 21, "iou_threshold": 0.5, "variances": VAR}
+    cases = [("rand", pri, X["gt_rand"], X["lab_rand"]), ("snap", pri, X["gt_snap"], X["lab_snap"]),
+             ("tie",) + ri.tie_case()]
+    for tag, p, gt, lab in cases:
+        assert np.array_equal(_np(bbox_utils.generate_iou_map(p, gt)), X[f"iou_{tag}"]), tag          # bit-exact
+        d, oh = train_utils.calculate_actual_outputs(p, gt, lab, hp)
+        assert np.array_equal(_np(oh), X[f"onehot_{tag}"].astype(np.float32)), tag                     # exact indices
+        np.testing.assert_allclose(_np(d), X[f"deltas_{tag}"], rtol=RTOL, atol=1e-6)
+    assert np.array_equal(_np(bbox_utils.generate_iou_map(X["eval_boxes"], X["gt_rand"])), X["iou_eval"])
+    assert np.array_equal(_np(bbox_utils.generate_iou_map(pri[:500], X["gt_rand"][0], transpose_perm=[1, 0])), X["iou_rank2"])
+    assert np.array_equal(_np(bbox_utils.generate_iou_map(X["deg_a"], X["deg_g"])), X["iou_deg"], equal_nan=True)
+    np.testing.assert_allclose(_np(bbox_utils.get_deltas_from_bboxes(X["enc_priors"], X["enc_gt"])), X["enc_deltas"],
+                               rtol=RTOL, atol=1e-6)
+    import torch
+    dd = torch.from_numpy(X["dec_in_deltas"] * np.array(VAR, np.float32))
+    np.testing.assert_allclose(_np(bbox_utils.get_bboxes_from_deltas(pri, dd)), X["dec_boxes"], rtol=RTOL, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_cuda_losses():
+    from tf_ssd_b200.ssd_loss import CustomLoss
+    from tf_ssd_b200.utils import train_utils
+    Ls = REF["loss"]
+    pri, gt, lab = _targets()
+    ad, al = train_utils.calculate_actual_outputs(pri, gt, lab, {"total_labels": 21, "iou_threshold": 0.5, "variances": VAR})
+    pd, probs = Ls["pred_deltas"], Ls["pred_probs"]
+    y, p, ead, epd = ri.loss_edge_inputs()
+    for ratio, alpha, tag in ((3, 1, "r3a1"), (2, 0.5, "r2a05")):
+        fn = CustomLoss(ratio, alpha)
+        np.testing.assert_allclose(_np(fn.loc_loss_fn(ad, pd)), Ls[f"loc_{tag}"], rtol=RTOL)
+        np.testing.assert_allclose(_np(fn.loc_loss_fn(ead, epd)), Ls[f"edge_loc_{tag}"], rtol=RTOL)
+        np.testing.assert_allclose(_np(fn.conf_loss_fn(al, probs)), Ls[f"conf_{tag}"], rtol=RTOL)
+        np.testing.assert_allclose(_np(fn.conf_loss_fn(y, p)), Ls[f"edge_conf_{tag}"], rtol=RTOL)
+
+
+@pytest.mark.gpu
+def test_cuda_decoder_selection_exact():
+    from tf_ssd_b200.models.decoder import SSDDecoder
+    from tf_ssd_b200.utils import bbox_utils
+    D = REF["decode"]
+    for tag, cfg, B, seed, bg in ri.DECODE_CASES:
+        pri = REF["priors"][f"priors_{cfg}"]
+        pd, probs, _ = ri.head_outputs(B, pri.shape[0], seed=seed, background_bias=bg)
+        b, l, s = SSDDecoder(pri, VAR)([pd, probs])
+        assert np.array_equal(_np(l), D[f"{tag}_labels"]) and np.array_equal(_np(s), D[f"{tag}_scores"]), tag   # order exact
+        np.testing.assert_allclose(_np(b), D[f"{tag}_boxes"], rtol=1e-5, atol=1e-6)
+    boxes, scores = ri.nms_tie_inputs()
+    r = bbox_utils.non_max_suppression(boxes, scores, max_output_size_per_class=10, max_total_size=40, score_threshold=0.5)
+    for got, k in zip(r, ("nms_boxes", "nms_scores", "nms_classes", "nms_valid")):
+        assert np.array_equal(_np(got), D[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["vgg16", "mobilenet_v2"])
+def test_cuda_networks_match_the_reference_graphs(name):
+    """fp16-storage forward against the reference graph's float32 result: the distance must stay within 1.5x the
+    distance of the oracle's fp16-storage simulation (the yardstick of what fp16 storage costs on this net)."""
+    from tf_ssd_b200.models.engine import SSDModel
+    from tf_ssd_b200.utils import train_utils
+    import torch
+    Nn = REF["net"]
+    hp = train_utils.get_hyper_params(name)
+    hp["total_labels"] = 21
+    m = SSDModel(name, hp, seed=0)
+    w = ri.weights_for({k: v.shape for k, v in m.weights.items()})
+    m.set_weights(w)
+    x = ri.image(1, 300)
+    d, p = m(x)
+    torch.cuda.synchronize()
+    sd, sp = no.forward(name, w, hp, x, mode="fp16sim")
+    rd, rp = Nn[f"{name}_deltas"], Nn[f"{name}_probs"]
+    rms = lambda a, b: float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-12))
+    assert rms(_np(d), rd) < 1.5 * rms(sd, rd) + 1e-3, (rms(_np(d), rd), rms(sd, rd))
+    assert rms(_np(p), rp) < 1.5 * rms(sp, rp) + 1e-3, (rms(_np(p), rp), rms(sp, rp))
+    assert (_np(p).argmax(-1) == rp.argmax(-1)).mean() > 0.97
