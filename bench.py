@@ -13,9 +13,16 @@ batch: SSD300-MobileNetV2, batch 32 per GPU, forward + softmax + decode + NMS
          H2D of every step's images and D2H of its detections inside the timing
   roofline / cpu_baseline / box_kernels: see DESIGN.md
 
+Input batches are uint8 NHWC (the image the reference's pipeline holds before
+``tf.image.convert_image_dtype``, utils/data_utils.py:33-37); the conversion to
+[0,1] float is part of the step in BOTH arms (fused into the first layer on the
+GPU, ``u8 * float32(1/255)`` in the CPU restatement).
+
 ``--impl reference`` times the CPU restatement of the reference (oracle/, torch
-CPU + NumPy, all host threads) on the same workload: the reference itself is
-TensorFlow 2.0 and cannot be installed in this image (no wheel, no network).
+CPU + NumPy, all host threads) on the SAME workload -- same weights recipe (seeded
+random init, background bias calibrated to 200 NMS candidates per image), same
+synthetic batches, same ``config``: the reference itself is TensorFlow 2.0 and
+cannot be installed in this image (no wheel, no network).
 """
 
 from __future__ import annotations
@@ -70,16 +77,35 @@ def _hyper_params():
     return hp
 
 
-def _calibrated_weights(model, hp, seed=1234):
+CAND_TARGET = 200.0
+
+
+def _config(world):
+    """The workload description: identical in both arms (the reference arm runs a bounded sample of it)."""
+    return {"workload": WORKLOAD, "global_batch": world * BATCH, "parallelism": f"independent inference shards x{world}",
+            "input": "uint8 NHWC 300x300x3 host batches (pre-convert_image_dtype), conversion inside the step",
+            "weights": f"random-init (seed 1234), BN folded, background bias calibrated to {CAND_TARGET:.0f} NMS candidates/image",
+            "l2": "256 MiB memset between timed steps (outside the event pairs)", "cuda_graph": True}
+
+
+def _make_images_u8(batch, size, seed):
+    return np.random.default_rng(seed).integers(0, 256, (batch, size, size, 3), dtype=np.uint8)
+
+
+def _calibrated_weights(model, hp, seed=1234, forward=None):
     """Random-init weights of the architecture (no checkpoints offline), with the
     background logit bias shifted so that a detector-like number of anchors
-    (about 200 per image) passes the 0.5 score threshold and reaches NMS."""
-    from tf_ssd_b200 import synth
-    import torch
-    img = synth.make_images(4, hp["img_size"], seed=seed)
-    _, z = model.forward_logits(img)
-    torch.cuda.synchronize()
-    z = z.cpu().numpy().astype(np.float64)
+    (about 200 per image) passes the 0.5 score threshold and reaches NMS.
+    ``forward(images_f32) -> logits`` replaces the GPU forward (the reference arm calibrates with the CPU oracle)."""
+    img = _make_images_u8(4, hp["img_size"], seed).astype(np.float32) * np.float32(1.0 / 255.0)
+    if forward is None:
+        import torch
+        _, z = model.forward_logits(img)
+        torch.cuda.synchronize()
+        z = z.cpu().numpy()
+    else:
+        z = forward(img)
+    z = z.astype(np.float64)
 
     def candidates(shift):
         zz = z.copy()
@@ -92,7 +118,7 @@ def _calibrated_weights(model, hp, seed=1234):
     lo, hi = -50.0, 50.0
     for _ in range(40):
         mid = 0.5 * (lo + hi)
-        if candidates(mid) > 200.0:
+        if candidates(mid) > CAND_TARGET:
             lo = mid
         else:
             hi = mid
@@ -102,7 +128,10 @@ def _calibrated_weights(model, hp, seed=1234):
         b = model.weights[f"{i}_conv_label_output/bias"].copy().reshape(-1, 21)
         b[:, 0] += np.float32(shift)
         w[f"{i}_conv_label_output/bias"] = b.reshape(-1)
-    model.set_weights(w)
+    if forward is None:
+        model.set_weights(w)
+    else:
+        model.weights.update(w)            # host-side only: the reference arm never touches the GPU
     return candidates(shift)
 
 
@@ -166,11 +195,12 @@ def _physical_gpu_index(local_rank: int) -> int:
 
 
 # ------------------------------------------------------------------ CPU arms --
-def _cpu_reference_step(weights, hp, priors, images):
-    """The reference's inference path restated on the CPU (oracle/): forward in
+def _cpu_reference_step(weights, hp, priors, images_u8):
+    """The reference's inference path restated on the CPU (oracle/): convert_image_dtype, forward in
     fp32 (torch CPU conv2d), softmax, SSDDecoder (NumPy)."""
     from oracle import box_oracle as bo
     from oracle import net_oracle as no
+    images = images_u8.astype(np.float32) * np.float32(1.0 / 255.0)         # utils/data_utils.py:36
     d, p = no.forward(BACKBONE, weights, hp, images, mode="fp32")
     return bo.ssd_decode(priors, hp["variances"], d, p)
 
@@ -179,7 +209,7 @@ def cpu_baseline(weights, hp, priors, budget_s=12.0):
     import torch
     from tf_ssd_b200 import synth
     cores = torch.get_num_threads()
-    img = synth.make_images(BATCH, hp["img_size"], seed=77)
+    img = _make_images_u8(BATCH, hp["img_size"], seed=1000)     # rank 0's first batch of the GPU arm
     _cpu_reference_step(weights, hp, priors, img[:4])           # warm-up (thread pools, allocator)
     n, t0 = 0, time.perf_counter()
     while True:
@@ -194,21 +224,23 @@ def cpu_baseline(weights, hp, priors, budget_s=12.0):
 
 
 def run_reference(args):
-    """--impl reference: the CPU restatement timed with all host threads (rank 0 only)."""
+    """--impl reference: the CPU restatement timed with all host threads (rank 0 only), same workload as the GPU arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     from oracle import box_oracle as bo
-    from tf_ssd_b200 import synth
+    from oracle import net_oracle as no
     from tf_ssd_b200.models.engine import SSDModel
     torch.set_num_threads(os.cpu_count() or 1)         # torchrun exports OMP_NUM_THREADS=1: use every host core
     hp = _hyper_params()
     model = SSDModel(BACKBONE, hp, seed=1234)          # host-side variable initialisation only (no GPU use)
+    cand = _calibrated_weights(model, hp, forward=lambda x: no.forward(BACKBONE, model.weights, hp, x, mode="fp32",
+                                                                       return_logits=True)[1])
     weights = model.weights
     priors = bo.prior_boxes(hp["feature_map_shapes"], hp["aspect_ratios"])
     # bounded sample per step so that steps+warmup stay within minutes
-    img = synth.make_images(BATCH, hp["img_size"], seed=77)
+    img = _make_images_u8(BATCH, hp["img_size"], seed=1000)         # rank 0's first batch of the GPU arm
     t0 = time.perf_counter()
     _cpu_reference_step(weights, hp, priors, img[:4])
     per_img = (time.perf_counter() - t0) / 4
@@ -218,7 +250,7 @@ def run_reference(args):
         _cpu_reference_step(weights, hp, priors, img[:sample])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _cpu_reference_step(weights, hp, priors, img[:sample])
+        out = _cpu_reference_step(weights, hp, priors, img[:sample])
     el = time.perf_counter() - t0
     value = args.steps * sample / el
     cores = torch.get_num_threads()
@@ -226,8 +258,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "images_per_step": sample,
-                   "note": "CPU restatement of the reference (oracle/); TensorFlow 2.0 is not installable in this image"},
+        "config": _config(args.gpus),
+        "workload_check": {"nms_candidates_per_image": round(cand, 1),
+                           "valid_detections_mean": float((out[2] > 0).sum(-1).mean()), "images_per_step": sample},
+        "note": "CPU restatement of the reference (oracle/: torch-CPU fp32 forward + NumPy SSDDecoder) on rank 0's host "
+                "cores; TensorFlow 2.0 is not installable in this image",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} images per step x {args.steps} steps, {os.cpu_count()} logical CPUs"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -255,7 +290,7 @@ def _profile_steps(dm, B, iters=5):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 2)]
         evs[0].record()
         for i in range(n):
-            plan.run(i, i + 1)
+            plan.run(i, i + 1, u8=True)
             evs[i + 1].record()
         st["enqueue_decode"]()
         evs[n + 1].record()
@@ -365,11 +400,11 @@ def run_b200(args):
     S = hp["img_size"]
 
     # distinct synthetic batches per rank (inference shards are independent: no data-path collective)
-    host_batches = [torch.from_numpy(synth.make_images(B, S, seed=1000 + 17 * rank + i)).pin_memory() for i in range(4)]
+    host_batches = [torch.from_numpy(_make_images_u8(B, S, seed=1000 + 17 * rank + i)).pin_memory() for i in range(4)]
     st = dm._prepare(B, 0)
     plan = st["plan"]
     st["enqueue_decode"] = lambda: _decode_only(dm, st, B)
-    plan.image.copy_(host_batches[0], non_blocking=False)
+    plan.image_u8.copy_(host_batches[0], non_blocking=False)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=plan.device)      # > 126 MB L2
 
     def barrier():
@@ -378,11 +413,11 @@ def run_b200(args):
 
     # ---- device-resident throughput ("value") -------------------------------
     for _ in range(W):
-        dm.run_resident(B, 0)
+        dm.run_resident(B, 0, u8=True)
     barrier()
     if args.profile_one_step:               # ncu --profile-from-start off: exactly one step's launches, eagerly
         torch.cuda.profiler.start()
-        st["enqueue"]()
+        st["enqueue"](True)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
@@ -392,7 +427,7 @@ def run_b200(args):
     for a, b in evs:
         flush.zero_()                       # L2 flush between timed steps, outside the event pair
         a.record()
-        dm.run_resident(B, 0)
+        dm.run_resident(B, 0, u8=True)
         b.record()
     barrier()
     clocks = sampler.finish()
@@ -444,15 +479,13 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"independent inference shards x{world}",
-                       "weights": "random-init, BN folded, background bias calibrated",
-                       "nms_candidates_per_image": round(cand, 1), "valid_detections_mean": float(valid.mean()),
-                       "l2": "256 MiB memset between timed steps (outside the event pairs)",
-                       "cuda_graph": True, "peaks": peaks["source"]},
+            "config": _config(world),
+            "workload_check": {"nms_candidates_per_image": round(cand, 1), "valid_detections_mean": float(valid.mean()),
+                               "images_per_step": B, "peaks": peaks["source"]},
             "clocks": clocks,
             "e2e": {"value": total_images / (e2e_ms / 1e3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(B * S * S * 3 * 4), "d2h_bytes_per_step": int(B * 200 * 6 * 4),
-                    "api": "get_decoder_model(...).predict(host batches): pinned H2D + graph replay + D2H, 2 slots in flight"},
+                    "h2d_bytes_per_step": int(B * S * S * 3), "d2h_bytes_per_step": int(B * 200 * 6 * 4),
+                    "api": "get_decoder_model(...).predict(uint8 host batches): pinned H2D + graph replay + D2H, 2 slots in flight"},
             "gpu_launches": K * dm.launches_per_batch(B),
         }
         if training is not None:

@@ -237,6 +237,12 @@ int ssd_dwproj_supported(const ssd_dwproj_desc* h_desc);
 int ssd_stem_conv3x3s2(const float* d_img, const void* d_weight, const float* d_bias, void* d_out,
                        int B, int H, int W, int Cout, int Ho, int Wo, int pad_top, int pad_left, int act,
                        ssd_stream_t stream);
+/* The same layer fed with the uint8 NHWC batch [B,H,W,3] the reference's input pipeline holds BEFORE
+ * tf.image.convert_image_dtype (utils/data_utils.py:33-37): float32(u8) * float32(1/255) is fused into the load, so
+ * the result is bit-identical to ssd_stem_conv3x3s2 on the converted float32 image, at a quarter of the bytes. */
+int ssd_stem_conv3x3s2_u8(const void* d_img_u8, const void* d_weight, const float* d_bias, void* d_out,
+                          int B, int H, int W, int Cout, int Ho, int Wo, int pad_top, int pad_left, int act,
+                          ssd_stream_t stream);
 
 /* Device-side input pipeline.  utils/data_utils.py:33-37: tf.image.convert_image_dtype(uint8 ->
  * float32) + tf.image.resize(img, (out_h, out_w)) (bilinear, half-pixel centres), optionally followed by
@@ -249,6 +255,8 @@ int ssd_flip_boxes(float* d_boxes, int n, ssd_stream_t stream);
 /* fp32 NHWC image [B,H,W,3] (utils/data_utils.py:36 convert_image_dtype output)
  * -> fp16 NHWC with the channel dimension zero-padded to 8. */
 int ssd_image_to_f16c8(const float* d_img, void* d_out, int64_t n_pixels, ssd_stream_t stream);
+/* uint8 NHWC image -> the same fp16 c8 layout, convert_image_dtype (utils/data_utils.py:36) fused in. */
+int ssd_image_u8_to_f16c8(const void* d_img_u8, void* d_out, int64_t n_pixels, ssd_stream_t stream);
 
 /* Keras MaxPool2D(padding="same") (models/ssd_vgg16.py:82-101): window k,
  * stride s, TensorFlow SAME padding (odd pixel after, -inf padded). fp16 NHWC. */

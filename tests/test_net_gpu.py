@@ -388,3 +388,84 @@ def test_decoder_model_end_to_end():
         assert np.array_equal(labels[sl], rl) and np.allclose(scores[sl], rs, rtol=1e-6, atol=0)
         close = np.isclose(boxes[sl], rb, rtol=1e-5, atol=2e-5).all(-1)
         assert close.mean() > 0.98, close.mean()
+
+
+@pytest.mark.parametrize("backbone", ["mobilenet_v2", "vgg16"])
+def test_uint8_input_is_bit_identical_to_converted_float32(backbone):
+    """A uint8 NHWC batch (the image before ``tf.image.convert_image_dtype``, utils/data_utils.py:33-37) must give
+    bit-identical head outputs to the float32 batch ``float32(u8) * float32(1/255)`` the reference model receives."""
+    m, hp = _model(backbone)
+    B, S = 2, hp["img_size"]
+    u8 = np.random.default_rng(5).integers(0, 256, (B, S, S, 3), dtype=np.uint8)
+    f32 = u8.astype(np.float32) * np.float32(1.0 / 255.0)
+    d0, z0 = [t.clone() for t in m.forward_logits(f32)]
+    d1, z1 = [t.clone() for t in m.forward_logits(u8)]
+    torch.cuda.synchronize()
+    assert torch.equal(d0, d1) and torch.equal(z0, z1)
+    d2, _ = m.forward_logits(torch.from_numpy(u8).cuda())            # device-resident uint8 tensor
+    assert torch.equal(d0, d2)
+
+
+def test_decoder_model_uint8_batches_and_parallel_heads():
+    """predict() on uint8 host batches == predict() on the converted float32 batches (bit for bit), and the captured
+    graph with the heads as parallel branches == the same launches in plain stream order."""
+    from tf_ssd_b200.models import engine
+    from tf_ssd_b200.models.decoder import get_decoder_model
+    from tf_ssd_b200.utils import bbox_utils
+    m, hp = _model("mobilenet_v2", seed=11)
+    priors = bbox_utils.generate_prior_boxes(hp["feature_map_shapes"], hp["aspect_ratios"])
+    dm = get_decoder_model(m, priors, hp)
+    B = 3
+    rng = np.random.default_rng(6)
+    u8 = [rng.integers(0, 256, (B, 300, 300, 3), dtype=np.uint8) for _ in range(3)]
+    f32 = [x.astype(np.float32) * np.float32(1.0 / 255.0) for x in u8]
+    r8 = dm.predict(u8, steps=3)
+    rf = dm.predict(f32, steps=3)
+    for a, b in zip(r8, rf):
+        assert np.array_equal(a, b)
+    plan = m.plan(B)
+    assert sum(1 for s in plan.steps if s.branch) == 6 and plan.steps[-1].branch          # heads are side branches
+    first_head = next(i for i, s in enumerate(plan.steps) if s.branch)
+    assert first_head < len(plan.steps) - 12                                             # hoisted behind their taps
+    m._to_image_buffer(plan, u8[0])
+    plan.run(u8=True, parallel=True)
+    torch.cuda.synchronize()
+    d_par, z_par = plan.deltas.clone(), plan.logits.clone()
+    plan.deltas.zero_(); plan.logits.zero_()
+    plan.run(u8=True, parallel=False)
+    torch.cuda.synchronize()
+    assert torch.equal(d_par, plan.deltas) and torch.equal(z_par, plan.logits)
+    # eager (no CUDA graph) decoder model agrees with the captured one
+    dm2 = engine.DecoderModel(m, dm.decoder, use_cuda_graph=False)
+    for a, b in zip(dm2.predict(u8[:1], steps=1), [r[:B] for r in r8]):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("H,W,pad", [(300, 300, (0, 0)), (31, 45, (1, 1)), (64, 322, (0, 1)), (9, 7, (1, 0))])
+def test_stem_kernel_shapes(H, W, pad):
+    """ssd_stem_conv3x3s2 / _u8 on odd sizes, both paddings, rows longer than one CTA chunk (Wo > 160)."""
+    from tf_ssd_b200 import _ffi
+    lib = _ffi.lib()
+    rng = np.random.default_rng(H * W)
+    B = 2
+    pt, pl = pad
+    Ho, Wo = (H + pt - 2) // 2 + 1, (W + pl - 2) // 2 + 1          # at most one padded row / column after
+    u8 = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    x32 = u8.astype(np.float32) * np.float32(1.0 / 255.0)
+    w = (rng.standard_normal((32, 3, 3, 3)) * 0.3).astype(np.float16)
+    bias = rng.standard_normal(32).astype(np.float32)
+    xt, ut = torch.from_numpy(x32).cuda(), torch.from_numpy(u8).cuda()
+    wt, bt = torch.from_numpy(w).cuda(), torch.from_numpy(bias).cuda()
+    outs = []
+    for fn, src in ((lib.ssd_stem_conv3x3s2, xt), (lib.ssd_stem_conv3x3s2_u8, ut)):
+        out = torch.full((B, Ho, Wo, 32), float("nan"), dtype=torch.float16, device="cuda")
+        _ffi.check(fn(_ffi.ptr(src), _ffi.ptr(wt), _ffi.ptr(bt), _ffi.ptr(out), B, H, W, 32, Ho, Wo, pt, pl, 2, _ffi.stream()))
+        outs.append(out)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    xr = torch.from_numpy(x32).half().float().permute(0, 3, 1, 2)
+    pb, pr = max(0, (Ho - 1) * 2 + 3 - H - pt), max(0, (Wo - 1) * 2 + 3 - W - pl)
+    y = F.conv2d(F.pad(xr, (pl, pr, pt, pb)), torch.from_numpy(w).float().permute(0, 3, 1, 2), torch.from_numpy(bias), stride=2)
+    y = torch.clamp(y, 0, 6).permute(0, 2, 3, 1).numpy()
+    assert y.shape == (B, Ho, Wo, 32)
+    assert _rel(outs[0].float().cpu().numpy(), y) < 2e-3

@@ -44,7 +44,9 @@ SIGNATURES = {
     "ssd_dwproj": (i, [C.POINTER(DwProjDesc), vp]),
     "ssd_dwproj_supported": (i, [C.POINTER(DwProjDesc)]),
     "ssd_stem_conv3x3s2": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
+    "ssd_stem_conv3x3s2_u8": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
     "ssd_image_to_f16c8": (i, [vp, vp, i64, vp]),
+    "ssd_image_u8_to_f16c8": (i, [vp, vp, i64, vp]),
     "ssd_preprocess_image": (i, [vp, i, i, vp, i, i, i, vp]),
     "ssd_flip_boxes": (i, [vp, i, vp]),
     "ssd_maxpool": (i, [vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),

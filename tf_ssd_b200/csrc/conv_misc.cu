@@ -132,70 +132,6 @@ image_to_f16c8_kernel(const float* __restrict__ img, uint4* __restrict__ out, in
     }
 }
 
-// ------------------------------------------------------------------- stem --
-// 3x3 stride-2 convolution with Cin = 3 straight from the fp32 image: K = 27 is far too
-// small for the tensor cores, so this is a direct CUDA-core convolution, one output pixel
-// (all COUT channels) per thread, weights broadcast from shared memory.  The fp32 -> fp16
-// rounding of the input that the rest of the pipeline applies is fused in.
-template <int COUT>
-__global__ void __launch_bounds__(128)
-stem_conv3x3s2_kernel(const float* __restrict__ img, const __half* __restrict__ w, const float* __restrict__ bias,
-                      __half* __restrict__ out, int H, int W, int Ho, int Wo, int pad_t, int pad_l, int act,
-                      int64_t total) {
-    __shared__ __align__(16) float sw[27][COUT];
-    __shared__ float sb[COUT];
-    pdl_trigger();
-    pdl_wait();
-    for (int e = threadIdx.x; e < 27 * COUT; e += blockDim.x) {
-        const int c = e / 27, k = e - c * 27;
-        sw[k][c] = __half2float(w[e]);
-    }
-    for (int c = threadIdx.x; c < COUT; c += blockDim.x) sb[c] = bias ? bias[c] : 0.0f;
-    __syncthreads();
-    const float lo = act == SSD_ACT_NONE ? -INFINITY : 0.0f, hi = act == SSD_ACT_RELU6 ? 6.0f : INFINITY;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int ox = (int)(t % Wo);
-        const int64_t r = t / Wo;
-        const int oy = (int)(r % Ho), b = (int)(r / Ho);
-        float acc[COUT];
-#pragma unroll
-        for (int c = 0; c < COUT; ++c) acc[c] = sb[c];
-        const float* base = img + (size_t)b * H * W * 3;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int iy = oy * 2 - pad_t + ky;
-            if ((unsigned)iy >= (unsigned)H) continue;
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int ix = ox * 2 - pad_l + kx;
-                if ((unsigned)ix >= (unsigned)W) continue;
-                const float* px = base + ((size_t)iy * W + ix) * 3;
-#pragma unroll
-                for (int ci = 0; ci < 3; ++ci) {
-                    const float x = __half2float(__float2half_rn(__ldg(px + ci)));
-                    const float4* wr = reinterpret_cast<const float4*>(&sw[(ky * 3 + kx) * 3 + ci][0]);
-#pragma unroll
-                    for (int c4 = 0; c4 < COUT / 4; ++c4) {
-                        const float4 wv = wr[c4];
-                        acc[c4 * 4 + 0] = fmaf(x, wv.x, acc[c4 * 4 + 0]);
-                        acc[c4 * 4 + 1] = fmaf(x, wv.y, acc[c4 * 4 + 1]);
-                        acc[c4 * 4 + 2] = fmaf(x, wv.z, acc[c4 * 4 + 2]);
-                        acc[c4 * 4 + 3] = fmaf(x, wv.w, acc[c4 * 4 + 3]);
-                    }
-                }
-            }
-        }
-        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)t * COUT);
-#pragma unroll
-        for (int g = 0; g < COUT / 8; ++g) {
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = fminf(fmaxf(acc[g * 8 + k], lo), hi);
-            dst[g] = f_to_h8(v);
-        }
-    }
-}
-
 // ---------------------------------------------------------------- maxpool --
 __global__ void __launch_bounds__(256)
 maxpool_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int H, int W, int C8, int Ho, int Wo,
@@ -290,22 +226,6 @@ extern "C" int ssd_depthwise3x3(const void* d_in, const void* d_weight, const fl
     };
     cudaError_t le = (stride == 1) ? args(depthwise3x3_kernel<1, PX>) : args(depthwise3x3_kernel<2, PX>);
     if (le != cudaSuccess) return cuda_fail(le, "depthwise3x3_kernel");
-    return SSD_OK;
-}
-
-extern "C" int ssd_stem_conv3x3s2(const float* d_img, const void* d_weight, const float* d_bias, void* d_out,
-                                  int B, int H, int W, int Cout, int Ho, int Wo, int pad_top, int pad_left, int act,
-                                  ssd_stream_t stream) {
-    SSD_REQUIRE_PTR(d_img); SSD_REQUIRE_PTR(d_weight); SSD_REQUIRE_PTR(d_out);
-    SSD_REQUIRE(B >= 1 && H >= 1 && W >= 1 && Ho >= 1 && Wo >= 1 && act >= SSD_ACT_NONE && act <= SSD_ACT_RELU6,
-                SSD_ERR_SHAPE, "ssd_stem_conv3x3s2: bad shape B=%d H=%d W=%d Ho=%d Wo=%d act=%d", B, H, W, Ho, Wo, act);
-    SSD_REQUIRE(Cout == 32, SSD_ERR_UNSUPPORTED, "ssd_stem_conv3x3s2: Cout=%d (this build instantiates Cout == 32)", Cout);
-    const int64_t total = (int64_t)B * Ho * Wo;
-    const int64_t blocks = (total + 127) / 128, cap = (int64_t)sm_count() * 16;
-    cudaError_t le = launch_pdl(stem_conv3x3s2_kernel<32>, dim3((int)(blocks < cap ? blocks : cap)), dim3(128), 0,
-                                as_stream(stream), d_img, reinterpret_cast<const __half*>(d_weight), d_bias,
-                                reinterpret_cast<__half*>(d_out), H, W, Ho, Wo, pad_top, pad_left, act, total);
-    if (le != cudaSuccess) return cuda_fail(le, "stem_conv3x3s2_kernel");
     return SSD_OK;
 }
 

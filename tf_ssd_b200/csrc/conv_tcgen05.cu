@@ -855,27 +855,46 @@ static int cached_map(CUtensorMap* map, const void* base, int rank, const uint64
     return rc;
 }
 
-// split-K workspace: grown on demand, owned by the library, per device (the only allocation the library makes; it
-// happens outside stream capture because plans are warmed up before capture).  A superseded buffer is NOT freed:
-// CUDA graphs captured earlier still carry its address.
-static float* g_partial[16] = {nullptr};
-static size_t g_partial_bytes[16] = {0};
+// split-K workspaces: owned by the library (the only allocations it makes; they happen outside stream capture because
+// plans are warmed up before capture).  Each split-K convolution gets its OWN region, keyed by (device, output pointer),
+// carved from 64 MB arenas: launches of different layers may run concurrently on different streams (the multibox heads
+// are parallel branches of the captured graph), and a region's address never changes once handed out, so CUDA graphs
+// captured earlier stay valid.  Arenas are never freed.
+struct PartialRegion { float* ptr; size_t bytes; };
+struct PartialKey {
+    int dev; const void* out;
+    bool operator==(const PartialKey& o) const { return dev == o.dev && out == o.out; }
+};
+struct PartialKeyHash {
+    size_t operator()(const PartialKey& k) const { return std::hash<const void*>()(k.out) ^ ((size_t)k.dev * 0x9E3779B97F4A7C15ull); }
+};
+static std::unordered_map<PartialKey, PartialRegion, PartialKeyHash> g_partial_regions;
+static unsigned char* g_arena[16] = {nullptr};
+static size_t g_arena_bytes[16] = {0}, g_arena_used[16] = {0};
 static std::mutex g_partial_mutex;
 
-static int partial_workspace(size_t bytes, float** out) {
+static int partial_workspace(const void* out_key, size_t bytes, float** out) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 16) return fail(SSD_ERR_UNSUPPORTED, "conv_tcgen05: device index %d out of range", dev);
     std::lock_guard<std::mutex> lock(g_partial_mutex);
-    if (g_partial_bytes[dev] < bytes) {
-        size_t want = bytes < ((size_t)64 << 20) ? ((size_t)64 << 20) : bytes;
-        float* fresh = nullptr;
+    const PartialKey key{dev, out_key};
+    auto it = g_partial_regions.find(key);
+    if (it != g_partial_regions.end() && it->second.bytes >= bytes) { *out = it->second.ptr; return SSD_OK; }
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (g_arena_bytes[dev] - g_arena_used[dev] < bytes) {
+        const size_t want = bytes < ((size_t)64 << 20) ? ((size_t)64 << 20) : bytes;
+        void* fresh = nullptr;
         cudaError_t e = cudaMalloc(&fresh, want);
         if (e != cudaSuccess) return cuda_fail(e, "conv_tcgen05: split-K workspace");
-        g_partial[dev] = fresh;                                   // the previous buffer stays alive for captured graphs
-        g_partial_bytes[dev] = want;
+        g_arena[dev] = static_cast<unsigned char*>(fresh);        // the previous arena stays alive for captured graphs
+        g_arena_bytes[dev] = want;
+        g_arena_used[dev] = 0;
     }
-    *out = g_partial[dev];
+    float* ptr = reinterpret_cast<float*>(g_arena[dev] + g_arena_used[dev]);
+    g_arena_used[dev] += bytes;
+    g_partial_regions[key] = PartialRegion{ptr, bytes};
+    *out = ptr;
     return SSD_OK;
 }
 
@@ -970,7 +989,7 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
     const int rows_total = tiles_m * TC_BM;
     if (splits > 1) {
         p.ldp = tiles_n * p.BN;
-        int rc = partial_workspace((size_t)splits * rows_total * p.ldp * sizeof(float), &p.partial);
+        int rc = partial_workspace(d->out0, (size_t)splits * rows_total * p.ldp * sizeof(float), &p.partial);
         if (rc) return rc;
     }
 

@@ -223,6 +223,7 @@ class Step:
     bytes: float            # algorithmic bytes: inputs + weights + outputs, once each
     keep: tuple = ()        # objects that must outlive the plan (descs, tensors)
     meta: Optional[Dict[str, Any]] = None   # tensors + geometry of the launch (tests check every layer in situ)
+    branch: int = 0         # 0: the main chain; k > 0: side branch k (a multibox head: consumes its tap only)
 
 
 class Plan:
@@ -232,16 +233,75 @@ class Plan:
         self.B, self.img_size, self.device = B, img_size, device
         self.steps: List[Step] = []
         self.image = torch.zeros((B, img_size, img_size, 3), dtype=torch.float32, device=device)
+        # uint8 NHWC input (what the reference's pipeline holds before convert_image_dtype, utils/data_utils.py:33-37):
+        # ``first_u8`` replaces ``steps[0]`` (the only step that reads the image) when a uint8 batch is fed
+        self.image_u8 = torch.zeros((B, img_size, img_size, 3), dtype=torch.uint8, device=device)
+        self.first_u8: Optional[Step] = None
         self.logits: Optional[torch.Tensor] = None
         self.deltas: Optional[torch.Tensor] = None
         self.taps: List[Act] = []
 
-    def run(self, first: int = 0, last: Optional[int] = None) -> None:
-        st = _ffi.stream()
-        for s in self.steps[first:last]:
+    # Multibox heads consume their tap only (models/header.py:68-85), so each head is a side branch of the launch
+    # graph: it is forked (event wait on a side stream) right after the step that produces its tap and joined at the
+    # end.  Inside a CUDA-graph capture this yields parallel graph branches; eagerly it is plain multi-stream overlap.
+    PARALLEL_HEADS = os.environ.get("SSD_B200_PARALLEL_HEADS", "1") not in ("0", "")
+
+    def run(self, first: int = 0, last: Optional[int] = None, u8: bool = False, parallel: Optional[bool] = None) -> None:
+        parallel = self.PARALLEL_HEADS if parallel is None else parallel
+        main = torch.cuda.current_stream()
+        st = vp_main = _ffi.stream()
+        used: Dict[int, torch.cuda.Stream] = {}
+        for i, s in enumerate(self.steps[first:last], start=first):
+            if u8 and i == 0:
+                s = self.first_u8
+            if parallel and s.branch:
+                side = used.get(s.branch)
+                if side is None:
+                    side = self._side_stream(s.branch)
+                    side.wait_stream(main)                      # fork: everything enqueued on main so far
+                    used[s.branch] = side
+                st = C.c_void_p(side.cuda_stream)
+            else:
+                st = vp_main
             rc = s.fn(*s.args, st)
             if rc != 0:
                 _ffi.check(rc, f"{s.fn.__name__} [{s.name}]")
+        for side in used.values():
+            main.wait_stream(side)                              # join
+
+    def _side_stream(self, k: int) -> torch.cuda.Stream:
+        pool = getattr(self, "_sides", None)
+        if pool is None:
+            pool = self._sides = {}
+        if k not in pool:
+            pool[k] = torch.cuda.Stream(device=self.device)
+        return pool[k]
+
+    def hoist_heads(self) -> None:
+        """Moves every head step directly behind the step that produces its tap (and marks it as a side branch) so that
+        the fork happens as early as the data dependency allows.  A tap-only pre-processing step (VGG16's
+        L2Normalization of conv4_3) travels with its head."""
+        heads = [s for s in self.steps if s.meta and "head" in s.meta]
+        rest = [s for s in self.steps if not (s.meta and "head" in s.meta)]
+
+        def produces(step, t):
+            m = step.meta or {}
+            return any(m.get(k) is t for k in ("out", "out0"))
+
+        def producer(t):
+            return max((i for i, s in enumerate(rest) if produces(s, t)), default=len(rest) - 1)
+
+        for bi, h in enumerate(heads, start=1):
+            h.branch = bi
+            idx = producer(h.meta["x"])
+            prod = rest[idx]
+            if prod.kind == "l2norm":                           # consumed by this head only: runs on the head's branch,
+                prod.branch = bi                                # right behind the producer of ITS input
+                rest.pop(idx)
+                idx = producer(prod.meta["x"]) + 1
+                rest.insert(idx, prod)
+            rest.insert(idx + 1, h)
+        self.steps = rest
 
     @property
     def n_launches(self) -> int:
@@ -276,6 +336,8 @@ class _PlanBuilder:
         npx = self.B * S * S
         self.plan.steps.append(Step("input_cast", "cast", self.lib.ssd_image_to_f16c8,
                                     (_ffi.ptr(self.plan.image), _ffi.ptr(x), npx), 0.0, npx * (12 + 16), (x,)))
+        self.plan.first_u8 = Step("input_cast_u8", "cast", self.lib.ssd_image_u8_to_f16c8,
+                                  (_ffi.ptr(self.plan.image_u8), _ffi.ptr(x), npx), 0.0, npx * (3 + 16), (x,))
         return Act(x, S, S, 8)
 
     def _stem(self, x, name, cout, ph, pw, act, bn):
@@ -288,6 +350,10 @@ class _PlanBuilder:
         self.plan.steps.append(Step(name, "stem", self.lib.ssd_stem_conv3x3s2, args, 2.0 * self.B * Ho * Wo * 27 * cout,
                                     nbytes, (w, b, out),
                                     dict(x=self.plan.image, w=w, bias=b, out=out, ph=ph, pw=pw, act=act)))
+        self.plan.first_u8 = Step(name + "_u8", "stem", self.lib.ssd_stem_conv3x3s2_u8,
+                                  (_ffi.ptr(self.plan.image_u8),) + args[1:], 2.0 * self.B * Ho * Wo * 27 * cout,
+                                  nbytes - self.B * x.H * x.W * 9, (w, b, out),
+                                  dict(x=self.plan.image_u8, w=w, bias=b, out=out, ph=ph, pw=pw, act=act))
         return Act(out, Ho, Wo, cout)
 
     def _emit_conv(self, name, x: Act, w: torch.Tensor, bias, cout, k, stride, dilation, ph, pw, act,
@@ -646,22 +712,36 @@ class SSDModel(object):
             pb = _PlanBuilder(self, B)
             taps = GRAPHS[self.backbone](pb, pb.input(), self.hyper_params)
             pb.head(taps, self.hyper_params)
+            pb.plan.hoist_heads()
             self._plans[(B, slot)] = pb.plan
         return self._plans[(B, slot)]
 
-    def _to_image_buffer(self, plan: Plan, images: Any) -> None:
-        x = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images, np.float32))
+    @staticmethod
+    def _is_u8(images: Any) -> bool:
+        return (images.dtype == torch.uint8) if isinstance(images, torch.Tensor) else (np.asarray(images).dtype == np.uint8)
+
+    def _to_image_buffer(self, plan: Plan, images: Any) -> bool:
+        """Copies a batch into the plan's input buffer; returns True when it was a uint8 batch (NHWC uint8 = the image
+        before ``convert_image_dtype``, utils/data_utils.py:33-37: the first layer then converts on the fly)."""
+        u8 = self._is_u8(images)
+        if isinstance(images, torch.Tensor):
+            x = images
+        else:
+            x = torch.from_numpy(np.ascontiguousarray(images, np.uint8 if u8 else np.float32))
         if tuple(x.shape) != tuple(plan.image.shape):
-            raise ValueError(f"expected images {tuple(plan.image.shape)} (NHWC float32), got {tuple(x.shape)}")
-        plan.image.copy_(x.to(torch.float32), non_blocking=True)
+            raise ValueError(f"expected images {tuple(plan.image.shape)} (NHWC float32 or uint8), got {tuple(x.shape)}")
+        if u8:
+            plan.image_u8.copy_(x, non_blocking=True)
+        else:
+            plan.image.copy_(x.to(torch.float32), non_blocking=True)
+        return u8
 
     def forward_logits(self, images: Any) -> Tuple[torch.Tensor, torch.Tensor]:
         """``(pred_deltas, logits)`` -- the pre-softmax head outputs (what Keras feeds
         the cross-entropy inside ``fit`` and what the fused decoder consumes)."""
         B = int(images.shape[0])
         plan = self.plan(B)
-        self._to_image_buffer(plan, images)
-        plan.run()
+        plan.run(u8=self._to_image_buffer(plan, images))
         return plan.deltas, plan.logits
 
     def __call__(self, images: Any, training: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -753,7 +833,11 @@ class DecoderModel(object):
     ``(boxes [B,200,4], labels [B,200], scores [B,200])``.
 
     The forward plan and the fused softmax+decode+NMS are captured into one
-    CUDA graph per (batch size, slot).  ``predict`` keeps two slots in flight:
+    CUDA graph per (batch size, slot, input dtype); the multibox heads are parallel
+    branches of that graph.  Batches may be float32 in [0,1] (what the reference model
+    receives, utils/data_utils.py:36) or uint8 (the image before
+    ``convert_image_dtype``: a quarter of the host->device bytes; the conversion is
+    fused into the first layer and the results are bit-identical).  ``predict`` keeps two slots in flight:
     the host->device image copy of batch i+1 and the device->host copy of
     batch i-1's detections overlap batch i's graph replay."""
 
@@ -783,7 +867,7 @@ class DecoderModel(object):
             "labels": torch.empty((B, T), dtype=torch.float32, device=dev),
             "scores": torch.empty((B, T), dtype=torch.float32, device=dev),
             "valid": torch.empty((B,), dtype=torch.int32, device=dev),
-            "graph": None,
+            "graph": {},                      # input dtype (False: float32, True: uint8) -> captured CUDA graph
             "ws": _ffi.workspace(_ffi.lib().ssd_decode_nms_workspace_bytes(B, self.base_model.n_anchors,
                                                                             self.base_model.total_labels, T, 0)),
         }
@@ -792,47 +876,52 @@ class DecoderModel(object):
         priors = dec._priors()
         N, L = self.base_model.n_anchors, self.base_model.total_labels
 
-        def enqueue():
-            plan.run()
+        def enqueue(u8: bool = False):
+            plan.run(u8=u8)
             _ffi.check(lib.ssd_decode_nms(_ffi.ptr(priors), _ffi.ptr(plan.deltas), _ffi.ptr(plan.logits), B, N, L, var, 1,
                                           dec.score_threshold, dec.iou_threshold, T, 0, _ffi.ptr(st["boxes"]),
                                           _ffi.ptr(st["labels"]), _ffi.ptr(st["scores"]), _ffi.ptr(st["valid"]),
                                           _ffi.ptr(st["ws"]), st["ws"].numel(), _ffi.stream()), "ssd_decode_nms")
 
         st["enqueue"] = enqueue
-        if self.use_cuda_graph:
+        self._state[(B, slot)] = st
+        return st
+
+    def _graph(self, st: Dict[str, Any], u8: bool):
+        """The captured forward + decode + NMS graph of one slot for one input dtype (captured on first use)."""
+        g = st["graph"].get(u8)
+        if g is None:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                for _ in range(2):                      # warm-up: function attributes, lazy module load
-                    enqueue()
+                for _ in range(2):                      # warm-up: function attributes, lazy module load, workspaces
+                    st["enqueue"](u8)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                enqueue()
-            st["graph"] = g
-        self._state[(B, slot)] = st
-        return st
+                st["enqueue"](u8)
+            st["graph"][u8] = g
+        return g
 
     def launches_per_batch(self, B: int) -> int:
         """libssd_b200 kernels per forward+decode: plan steps + candidate pass + per-image NMS."""
         return self.base_model.plan(B).n_launches + 2
 
-    def run_resident(self, B: int, slot: int = 0) -> Dict[str, Any]:
-        """Replay on whatever already sits in the slot's image buffer (device-resident timing)."""
+    def run_resident(self, B: int, slot: int = 0, u8: bool = False) -> Dict[str, Any]:
+        """Replay on whatever already sits in the slot's (float32 or uint8) image buffer (device-resident timing)."""
         st = self._prepare(B, slot)
-        if st["graph"] is not None:
-            st["graph"].replay()
+        if self.use_cuda_graph:
+            self._graph(st, u8).replay()
         else:
-            st["enqueue"]()
+            st["enqueue"](u8)
         return st
 
     def __call__(self, images: Any):
         B = int(images.shape[0])
         st = self._prepare(B)
-        self.base_model._to_image_buffer(st["plan"], images)
-        self.run_resident(B)
+        u8 = self.base_model._to_image_buffer(st["plan"], images)
+        self.run_resident(B, 0, u8)
         self.decoder.last_valid_detections = st["valid"]
         return st["boxes"].clone(), st["labels"].clone(), st["scores"].clone()
 
@@ -864,28 +953,33 @@ class DecoderModel(object):
             st = self._prepare(B, slot)
             if len(pending) >= self.N_SLOTS:           # the slot's previous user must be fully drained
                 drain(pending.pop(0))
-            hb = host.get((B, slot))
+            u8 = SSDModel._is_u8(img)
+            dst_img = st["plan"].image_u8 if u8 else st["plan"].image
+            hb = host.get((B, slot, u8))
             if hb is None:
-                hb = {"img": torch.empty(tuple(st["plan"].image.shape), dtype=torch.float32, pin_memory=True),
+                hb = {"img": torch.empty(tuple(dst_img.shape), dtype=dst_img.dtype, pin_memory=True),
                       "boxes": torch.empty((B, T, 4), dtype=torch.float32, pin_memory=True),
                       "labels": torch.empty((B, T), dtype=torch.float32, pin_memory=True),
                       "scores": torch.empty((B, T), dtype=torch.float32, pin_memory=True)}
-                host[(B, slot)] = hb
+                host[(B, slot, u8)] = hb
             if isinstance(img, torch.Tensor) and img.is_cuda:
                 with torch.cuda.stream(cs):
                     cs.wait_stream(ms)
-                    st["plan"].image.copy_(img.to(torch.float32), non_blocking=True)
+                    dst_img.copy_(img if u8 else img.to(torch.float32), non_blocking=True)
             else:
-                src = img if isinstance(img, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(img, np.float32))
+                src = img if isinstance(img, torch.Tensor) else torch.from_numpy(
+                    np.ascontiguousarray(img, np.uint8 if u8 else np.float32))
                 if tuple(src.shape) != tuple(hb["img"].shape):
-                    raise ValueError(f"expected images {tuple(hb['img'].shape)} (NHWC float32), got {tuple(src.shape)}")
+                    raise ValueError(f"expected images {tuple(hb['img'].shape)} (NHWC float32 or uint8), got {tuple(src.shape)}")
+                if src.dtype != dst_img.dtype:
+                    src = src.to(dst_img.dtype)
                 if not src.is_pinned():
                     hb["img"].copy_(src)
                     src = hb["img"]
                 with torch.cuda.stream(cs):
-                    st["plan"].image.copy_(src, non_blocking=True)
+                    dst_img.copy_(src, non_blocking=True)
             ms.wait_stream(cs)
-            self.run_resident(B, slot)
+            self.run_resident(B, slot, u8)
             ds.wait_stream(ms)
             with torch.cuda.stream(ds):
                 hb["boxes"].copy_(st["boxes"], non_blocking=True)

@@ -337,7 +337,7 @@ class Trainer(object):
         plan = st["plan"]
         N, L = m.n_anchors, m.total_labels
         ad, al = st["ad"], st["al"]
-        plan.run()
+        plan.run(parallel=False)
         stream = _ffi.stream()
         _ffi.check(lib.ssd_loss_fwd(_ffi.ptr(ad), _ffi.ptr(plan.deltas), _ffi.ptr(al), _ffi.ptr(plan.logits), B, N, L,
                                     self.neg_pos_ratio, self.alpha, 1, _ffi.ptr(st["loc"]), _ffi.ptr(st["conf"]),
