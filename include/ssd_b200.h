@@ -230,6 +230,26 @@ int ssd_dwproj(const ssd_dwproj_desc* h_desc, ssd_stream_t stream);
 /* 1 when ssd_dwproj can run this configuration (shape limits, alignment, a tile geometry that fits shared memory). */
 int ssd_dwproj_supported(const ssd_dwproj_desc* h_desc);
 
+/* A WHOLE MobileNetV2 inverted-residual block (keras_applications mobilenet_v2._inverted_res_block under
+ * models/ssd_mobilenet_v2.py:25) as ONE launch: 1x1 expand Conv2D (+ folded BN + exp_act) -> DepthwiseConv2D 3x3
+ * (+ folded BN + dw_act) -> 1x1 project Conv2D (+ folded BN + act, + residual).  Neither the expanded activation nor
+ * the depthwise output is written to global memory: per output tile the input patch (tile + halo) is loaded once, the
+ * expansion is computed on the tensor cores into TMEM 64 channels at a time, converted to a shared-memory patch, the
+ * depthwise taps build the projection's operand tile in shared memory.
+ * in [B,H,W,Cin] fp16, exp_weight [Cexp,Cin] fp16, dw_weight [3,3,Cexp] fp16, proj_weight [Cout,Cexp] fp16, biases
+ * fp32 (may be NULL), residual / out [B,Ho,Wo,Cout] fp16.  Channels % 8 == 0, Cin <= 256, Cexp <= 1024, Cout <= 256,
+ * stride 1 or 2; returns SSD_ERR_UNSUPPORTED otherwise (ssd_irblock_supported tells beforehand). */
+typedef struct ssd_irblock_desc {
+    const void* in; const void* exp_weight; const float* exp_bias;
+    const void* dw_weight; const float* dw_bias;
+    const void* proj_weight; const float* proj_bias; const void* residual; void* out;
+    int32_t B, H, W, Cin, Cexp, Ho, Wo, Cout;
+    int32_t stride, pad_top, pad_left, exp_act, dw_act, act;
+    int32_t reserved0, reserved1;
+} ssd_irblock_desc;
+int ssd_irblock(const ssd_irblock_desc* h_desc, ssd_stream_t stream);
+int ssd_irblock_supported(const ssd_irblock_desc* h_desc);
+
 /* MobileNetV2 stem: keras_applications Conv1_pad + Conv1 (3x3, stride 2, Cin = 3) + bn_Conv1 +
  * Conv1_relu (models/ssd_mobilenet_v2.py:25), computed straight from the fp32 NHWC image
  * [B,H,W,3] (the fp32->fp16 input rounding of the pipeline is fused in).

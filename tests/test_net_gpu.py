@@ -236,6 +236,80 @@ def _rms(a, b):
     return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-12))
 
 
+def _act(y, act):
+    return torch.relu(y) if act == 1 else torch.clamp(y, 0, 6) if act == 2 else y
+
+
+def _irblock_reference(x, we, be, exp_act, wd, bd, stride, ph, pw, dw_act, wp, bp, act, res):
+    """expand 1x1 -> depthwise 3x3 -> project 1x1 on NHWC float tensors, with the fp16 roundings of the fused kernel:
+    the expanded activation and the depthwise output are rounded to fp16 (they are tensor-core operands)."""
+    xn = x.permute(0, 3, 1, 2)
+    h = _act(F.conv2d(xn, we.permute(0, 3, 1, 2), be), exp_act).half().float()
+    (pt, pb), (pl, pr) = ph, pw
+    h = F.conv2d(F.pad(h, (pl, pr, pt, pb)), wd.permute(2, 0, 1).unsqueeze(1), bd, stride=stride, groups=wd.shape[2])
+    h = _act(h, dw_act).half().float()
+    y = _act(F.conv2d(h, wp.permute(0, 3, 1, 2), bp), act).permute(0, 2, 3, 1)
+    return y + res if res is not None else y
+
+
+IRBLOCK_CASES = [
+    # B, H, W, Cin, Cexp, Cout, stride, residual
+    (2, 150, 150, 16, 96, 24, 2, False),      # block 1
+    (2, 75, 75, 24, 144, 24, 1, True),        # block 2
+    (2, 75, 75, 24, 144, 32, 2, False),       # block 3
+    (2, 38, 38, 32, 192, 32, 1, True),        # blocks 4, 5
+    (3, 38, 38, 32, 192, 64, 2, False),       # block 6
+    (2, 19, 19, 64, 384, 64, 1, True),        # blocks 7-9
+    (2, 19, 19, 96, 576, 96, 1, True),        # blocks 11, 12  (two input chunks)
+    (3, 10, 10, 160, 960, 160, 1, True),      # blocks 14, 15  (three input chunks)
+    (1, 7, 9, 8, 40, 16, 1, False),           # odd sizes, one slice, channels below one MMA K step
+    (5, 5, 5, 72, 200, 48, 2, False),         # several images per tile
+]
+
+
+@pytest.mark.parametrize("case", IRBLOCK_CASES)
+def test_irblock_fused_against_torch(case):
+    """ssd_irblock (whole inverted-residual block in one launch) against torch-CPU with the same fp16 roundings."""
+    from tf_ssd_b200 import _ffi
+    from tf_ssd_b200._ffi_conv import IrBlockDesc
+    import ctypes as C
+    B, H, W, Cin, Cexp, Cout, stride, residual = case
+    rng = np.random.default_rng(sum(case))
+    if stride == 1:
+        ph = pw = (1, 1)
+    else:
+        ph, pw = (1 - H % 2, 1), (1 - W % 2, 1)                          # keras_applications correct_pad
+    Ho, Wo = (H + ph[0] + ph[1] - 3) // stride + 1, (W + pw[0] + pw[1] - 3) // stride + 1
+    x = rng.standard_normal((B, H, W, Cin)).astype(np.float16)
+    we = (rng.standard_normal((Cexp, 1, 1, Cin)) * np.sqrt(2.0 / Cin)).astype(np.float16)
+    be = (0.3 * rng.standard_normal(Cexp)).astype(np.float32)
+    wd = (rng.standard_normal((3, 3, Cexp)) * 0.4).astype(np.float16)
+    bd = (0.3 * rng.standard_normal(Cexp)).astype(np.float32)
+    wp = (rng.standard_normal((Cout, 1, 1, Cexp)) * np.sqrt(1.0 / Cexp)).astype(np.float16)
+    bp = (0.3 * rng.standard_normal(Cout)).astype(np.float32)
+    res = rng.standard_normal((B, Ho, Wo, Cout)).astype(np.float16) if residual else None
+    t = lambda a: torch.from_numpy(a).cuda() if a is not None else None
+    xt, wet, bet, wdt, bdt, wpt, bpt, rt = map(t, (x, we, be, wd, bd, wp, bp, res))
+    out = torch.full((B, Ho, Wo, Cout), float("nan"), dtype=torch.float16, device="cuda")
+    d = IrBlockDesc()
+    d.inp, d.exp_weight, d.exp_bias = xt.data_ptr(), wet.data_ptr(), bet.data_ptr()
+    d.dw_weight, d.dw_bias, d.proj_weight, d.proj_bias = wdt.data_ptr(), bdt.data_ptr(), wpt.data_ptr(), bpt.data_ptr()
+    d.residual = rt.data_ptr() if rt is not None else None
+    d.out = out.data_ptr()
+    d.B, d.H, d.W, d.Cin, d.Cexp, d.Ho, d.Wo, d.Cout = B, H, W, Cin, Cexp, Ho, Wo, Cout
+    d.stride, d.pad_top, d.pad_left, d.exp_act, d.dw_act, d.act = stride, ph[0], pw[0], 2, 2, 0
+    lib = _ffi.lib()
+    assert lib.ssd_irblock_supported(C.byref(d)) == 1
+    for _ in range(2):                                                    # twice: barrier phases / buffers start clean
+        _ffi.check(lib.ssd_irblock(C.byref(d), _ffi.stream()), "ssd_irblock")
+    torch.cuda.synchronize()
+    f = lambda a: torch.from_numpy(a).float() if a is not None else None
+    y = _irblock_reference(f(x), f(we), f(be), 2, f(wd), f(bd), stride, ph, pw, 2, f(wp), f(bp), 0, f(res))
+    got = out.float().cpu().numpy()
+    assert np.isfinite(got).all()
+    assert _rel(got, y.numpy()) < 3e-3, _rel(got, y.numpy())
+
+
 @pytest.mark.parametrize("backbone,B", [("mobilenet_v2", 2), ("vgg16", 1), ("vgg16_512", 1)])
 def test_every_layer_in_situ(backbone, B):
     """Each launch of the plan is checked against torch-CPU on the launch's ACTUAL device
@@ -293,6 +367,12 @@ def test_every_layer_in_situ(backbone, B):
                 y = y + f32(mt["res"])
             assert y.shape[1:3] == (mt["Ho"], mt["Wo"])
             assert _rel(f32(mt["out0"]).numpy(), y.numpy()) < 2e-3, f"{s.name}: {_rel(f32(mt['out0']).numpy(), y.numpy())}"
+        elif s.kind == "irblock":
+            y = _irblock_reference(f32(mt["x"]), f32(mt["exp_w"]), f32(mt["exp_bias"]), mt["exp_act"], f32(mt["dw_w"]),
+                                   f32(mt["dw_bias"]), mt["dw_stride"], mt["dw_ph"], mt["dw_pw"], mt["dw_act"], f32(mt["w"]),
+                                   f32(mt["bias"]), mt["act"], f32(mt["res"]) if mt["res"] is not None else None)
+            assert y.shape[1:3] == (mt["Ho"], mt["Wo"])
+            assert _rel(f32(mt["out0"]).numpy(), y.numpy()) < 3e-3, f"{s.name}: {_rel(f32(mt['out0']).numpy(), y.numpy())}"
         elif s.kind == "pool":
             x = f32(mt["x"]).permute(0, 3, 1, 2)
             (pt, pb), (pl, pr) = mt["ph"], mt["pw"]

@@ -33,6 +33,17 @@ class DwProjDesc(C.Structure):
     ]
 
 
+class IrBlockDesc(C.Structure):
+    """``struct ssd_irblock_desc`` (include/ssd_b200.h)."""
+    _fields_ = [
+        ("inp", vp), ("exp_weight", vp), ("exp_bias", vp), ("dw_weight", vp), ("dw_bias", vp), ("proj_weight", vp),
+        ("proj_bias", vp), ("residual", vp), ("out", vp),
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cexp", C.c_int32), ("Ho", C.c_int32),
+        ("Wo", C.c_int32), ("Cout", C.c_int32), ("stride", C.c_int32), ("pad_top", C.c_int32), ("pad_left", C.c_int32),
+        ("exp_act", C.c_int32), ("dw_act", C.c_int32), ("act", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+    ]
+
+
 class AdamVar(C.Structure):
     """``struct ssd_adam_var`` (include/ssd_b200.h)."""
     _fields_ = [("w", vp), ("m", vp), ("v", vp), ("grad", vp), ("w16", vp), ("n", i64), ("l2", f), ("reserved", f)]
@@ -43,6 +54,8 @@ SIGNATURES = {
     "ssd_depthwise3x3": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),
     "ssd_dwproj": (i, [C.POINTER(DwProjDesc), vp]),
     "ssd_dwproj_supported": (i, [C.POINTER(DwProjDesc)]),
+    "ssd_irblock": (i, [C.POINTER(IrBlockDesc), vp]),
+    "ssd_irblock_supported": (i, [C.POINTER(IrBlockDesc)]),
     "ssd_stem_conv3x3s2": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
     "ssd_stem_conv3x3s2_u8": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
     "ssd_image_to_f16c8": (i, [vp, vp, i64, vp]),

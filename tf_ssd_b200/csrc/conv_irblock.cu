@@ -1,0 +1,612 @@
+// A whole MobileNetV2 inverted-residual block as ONE launch on sm_100a:
+//
+//     1x1 expand (+ folded BN + ReLU6)  ->  depthwise 3x3 (+ folded BN + ReLU6)  ->  1x1 project (+ folded BN, + shortcut)
+//
+// (keras_applications.mobilenet_v2._inverted_res_block under models/ssd_mobilenet_v2.py:25 of the reference).  The 6x
+// expanded activation -- the largest tensor of the network -- never leaves the SM: per output tile the INPUT patch
+// (tile + halo) is loaded once by TMA, and for every 64-channel slice of the expanded tensor
+//
+//   warp 1      tcgen05.mma   D1[patch positions x 64] = patch[positions x Cin] * Wexp[64 x Cin]^T       (TMEM)
+//   warps 2-9   "mid":        D1 -> + bias, ReLU6, zero outside the image (the depthwise padding) -> fp16 -> the
+//                             128-byte-swizzled expanded patch in shared memory
+//   warps 10-19 depthwise:    3x3 taps from that patch (packed half2 FMAs, sliding window), + bias, ReLU6 -> the K-major
+//                             A operand tile of the projection
+//   warp 1      tcgen05.mma   D2[128 pixels x Cout] += A2[128 x 64] * Wproj[Cout x 64]^T                  (TMEM)
+//
+// run as a software pipeline (double-buffered D1, expanded patch, A2 and weight slices; mbarrier hand-offs), so the
+// expand MMA and mid stage of slice e+1 overlap the depthwise stage of slice e.  Warp 0 is the TMA producer; warps 2-9
+// also run the final epilogue (D2 -> bias / residual -> fp16 -> swizzled staging tile -> TMA store).
+//
+// HBM traffic per block: input once (+ halo), weights (L2-resident), output once -- against input + 2 x expanded + output
+// for the layer-by-layer path.  The halo's expand work is recomputed per tile; the tensor pipe is otherwise idle here.
+
+#include "tc_common.cuh"
+
+#include <string.h>
+
+namespace ssd {
+
+constexpr int IR_MID_WARPS = 8;                     // warps 2..9
+constexpr int IR_DW_WARPS = 10;                     // warps 10..19
+constexpr int IR_THREADS = 64 + 32 * (IR_MID_WARPS + IR_DW_WARPS);      // 640
+constexpr int IR_DW_ROWS = (TC_BM + 4 * IR_DW_WARPS - 1) / (4 * IR_DW_WARPS);   // tile rows per depthwise thread (4)
+constexpr uint32_t IR_D2_COL = 256;                 // TMEM: D1[buf][half] at buf*128 + half*64, D2 at 256
+constexpr uint32_t IR_TMEM_COLS = 512;
+
+struct IrParams {
+    int B, H, W, Cin, Cexp, Cout, Ho, Wo, stride, pad_t, pad_l;
+    int bw, bh, bb, tiles_w, tiles_h, n_tiles;
+    int pw, ph, P;                   // patch width / height, patch positions = pw * ph * bb (<= 256)
+    int halves;                      // expand MMAs per slice: 1 (P <= 128) or 2
+    int kc_in;                       // 64-channel chunks of the input
+    int k16_last;                    // UMMA_K = 16 steps that carry data in the last input chunk
+    int n_e;                         // 64-channel slices of the expanded tensor
+    int BN;                          // projection N (Cout rounded up to 16)
+    int exp_act, dw_act, act, quad;
+    uint32_t idesc_exp, idesc_proj;
+    // shared-memory layout (byte offsets from the 1024-aligned base)
+    uint32_t off_patch, patch_chunk;             // input patch: kc_in chunks of [P rows][128 B]
+    uint32_t off_wexp, wexp_stage; int wexp_stages;   // [stages][kc_in][64 rows][128 B]
+    uint32_t off_ep, ep_stage, ep_filter;        // expanded patch [2][P rows x 128 B | 9 x 128 B depthwise filter]
+    uint32_t off_a2;                             // [2][128 rows][128 B]
+    uint32_t off_wproj, wproj_stage;             // [2][BN rows][128 B]
+    uint32_t off_out; int out_bufs;              // [out_bufs][128 rows][128 B]
+    uint32_t off_bias;                           // floats: expand bias [n_e * 64] | depthwise bias [n_e * 64] | project bias [256]
+    uint32_t off_bars;
+    uint32_t patch_bytes, wproj_bytes;
+    const float* exp_bias; const float* dw_bias; const float* proj_bias; const __half* res;
+};
+
+__device__ __forceinline__ void ir_tile_origin(const IrParams& p, int t, int& b0, int& oy0, int& ox0) {
+    const int per_img = p.tiles_w * p.tiles_h;
+    const int tb = t / per_img, tr = t - tb * per_img;
+    const int th = tr / p.tiles_w, tw = tr - th * p.tiles_w;
+    b0 = tb * p.bb; oy0 = th * p.bh; ox0 = tw * p.bw;
+}
+
+__global__ void __launch_bounds__(IR_THREADS, 1)
+conv_irblock_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_we,
+                            const __grid_constant__ CUtensorMap map_dw, const __grid_constant__ CUtensorMap map_wp,
+                            const __grid_constant__ CUtensorMap map_o, const __grid_constant__ IrParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* sPatch = smem + p.off_patch;
+    unsigned char* sWexp = smem + p.off_wexp;
+    unsigned char* sEp = smem + p.off_ep;
+    unsigned char* sA2 = smem + p.off_a2;
+    unsigned char* sWproj = smem + p.off_wproj;
+    unsigned char* sOut = smem + p.off_out;
+    float* sBiasE = reinterpret_cast<float*>(smem + p.off_bias);
+    float* sBiasD = sBiasE + p.n_e * 64;
+    float* sBiasP = sBiasD + p.n_e * 64;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+    pdl_trigger();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = smem_addr(bars);
+    const uint32_t bar_patch_full = bar0, bar_patch_empty = bar0 + 8;
+    const uint32_t bar_wexp_full = bar0 + 16, bar_wexp_empty = bar0 + 32;       // [2] each
+    const uint32_t bar_d1_full = bar0 + 48, bar_d1_empty = bar0 + 64;
+    const uint32_t bar_ep_full = bar0 + 80, bar_ep_empty = bar0 + 96;
+    const uint32_t bar_a2_full = bar0 + 112, bar_a2_empty = bar0 + 128;
+    const uint32_t bar_d2_full = bar0 + 144, bar_d2_empty = bar0 + 152;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_we); tma_prefetch_desc(&map_dw);
+        tma_prefetch_desc(&map_wp); tma_prefetch_desc(&map_o);
+        mbar_init(bar_patch_full, 1);                             // expect_tx arrive (+ TMA bytes)
+        mbar_init(bar_patch_empty, 1);                            // tcgen05.commit after the tile's last expand MMA
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_wexp_full + 8 * s, 1);
+            mbar_init(bar_wexp_empty + 8 * s, 1);                 // tcgen05.commit
+            mbar_init(bar_d1_full + 8 * s, 1);                    // tcgen05.commit
+            mbar_init(bar_d1_empty + 8 * s, IR_MID_WARPS);        // D1 drained into registers
+            mbar_init(bar_ep_full + 8 * s, IR_MID_WARPS + 1);     // expanded patch written + depthwise filter bytes
+            mbar_init(bar_ep_empty + 8 * s, IR_DW_WARPS);
+            mbar_init(bar_a2_full + 8 * s, IR_DW_WARPS + 1);      // A2 written + projection weight bytes
+            mbar_init(bar_a2_empty + 8 * s, 1);                   // tcgen05.commit
+        }
+        mbar_init(bar_d2_full, 1);                                // tcgen05.commit
+        mbar_init(bar_d2_empty, IR_MID_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_addr(tmem_slot)), "r"(IR_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // biases (weights: never written by a predecessor kernel of the plan, safe before the PDL wait)
+    for (int i = threadIdx.x; i < p.n_e * 64; i += IR_THREADS) {
+        sBiasE[i] = (p.exp_bias && i < p.Cexp) ? __ldg(p.exp_bias + i) : 0.0f;
+        sBiasD[i] = (p.dw_bias && i < p.Cexp) ? __ldg(p.dw_bias + i) : 0.0f;
+    }
+    for (int i = threadIdx.x; i < 256; i += IR_THREADS) sBiasP[i] = (p.proj_bias && i < p.Cout) ? __ldg(p.proj_bias + i) : 0.0f;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int it = 0, ti = 0;
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++ti) {
+                int b0, oy0, ox0;
+                ir_tile_origin(p, t, b0, oy0, ox0);
+                if (ti >= 1) mbar_wait(bar_patch_empty, (uint32_t)(ti - 1) & 1u);
+                mbar_expect_tx(bar_patch_full, (uint32_t)p.kc_in * p.patch_bytes);
+                for (int kc = 0; kc < p.kc_in; ++kc)
+                    tma_load_4d(smem_addr(sPatch + (size_t)kc * p.patch_chunk), &map_x, bar_patch_full, kc * 64,
+                                ox0 * p.stride - p.pad_l, oy0 * p.stride - p.pad_t, b0);
+                for (int e = 0; e < p.n_e; ++e, ++it) {
+                    const int ws = it % p.wexp_stages, wq = it / p.wexp_stages;
+                    if (wq >= 1) mbar_wait(bar_wexp_empty + 8 * ws, (uint32_t)(wq - 1) & 1u);
+                    mbar_expect_tx(bar_wexp_full + 8 * ws, (uint32_t)p.kc_in * 8192u);
+                    for (int kc = 0; kc < p.kc_in; ++kc)
+                        tma_load_2d(smem_addr(sWexp + (size_t)ws * p.wexp_stage + (size_t)kc * 8192), &map_we,
+                                    bar_wexp_full + 8 * ws, kc * 64, e * 64);
+                    const int b = it & 1;
+                    const uint32_t par = (uint32_t)((it >> 1) - 1) & 1u;
+                    if (it >= 2) mbar_wait(bar_ep_empty + 8 * b, par);
+                    mbar_expect_tx(bar_ep_full + 8 * b, 9 * 128);
+                    tma_load_2d(smem_addr(sEp + (size_t)b * p.ep_stage + p.ep_filter), &map_dw, bar_ep_full + 8 * b, e * 64, 0);
+                    if (it >= 2) mbar_wait(bar_a2_empty + 8 * b, par);
+                    mbar_expect_tx(bar_a2_full + 8 * b, p.wproj_bytes);
+                    tma_load_2d(smem_addr(sWproj + (size_t)b * p.wproj_stage), &map_wp, bar_a2_full + 8 * b, e * 64, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer: expand of slice e, then projection of slice e - 1 =====================
+        if (lane == 0) {
+            int it = 0, ti = 0;
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++ti, it += p.n_e) {
+                mbar_wait(bar_patch_full, (uint32_t)ti & 1u);
+                for (int step = 0; step <= p.n_e; ++step) {
+                    if (step < p.n_e) {
+                        const int i = it + step, ws = i % p.wexp_stages, wq = i / p.wexp_stages, db = i & 1;
+                        mbar_wait(bar_wexp_full + 8 * ws, (uint32_t)wq & 1u);
+                        if (i >= 2) mbar_wait(bar_d1_empty + 8 * db, (uint32_t)((i >> 1) - 1) & 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        for (int h = 0; h < p.halves; ++h) {
+                            const uint32_t tacc = tmem_base + (uint32_t)db * 128u + (uint32_t)h * 64u;
+                            for (int kc = 0; kc < p.kc_in; ++kc) {
+                                const uint64_t da = umma_desc_sw128(smem_addr(sPatch + (size_t)kc * p.patch_chunk + (size_t)h * 16384));
+                                const uint64_t dbd = umma_desc_sw128(smem_addr(sWexp + (size_t)ws * p.wexp_stage + (size_t)kc * 8192));
+                                const int nk = kc == p.kc_in - 1 ? p.k16_last : 4;
+                                for (int k = 0; k < nk; ++k)
+                                    umma_f16(tacc, da + (uint64_t)(k * 2), dbd + (uint64_t)(k * 2), p.idesc_exp, (kc > 0) || (k > 0));
+                            }
+                        }
+                        umma_commit(bar_wexp_empty + 8 * ws);
+                        umma_commit(bar_d1_full + 8 * db);
+                        if (step == p.n_e - 1) umma_commit(bar_patch_empty);     // the input patch may be overwritten
+                    }
+                    if (step >= 1) {
+                        const int i = it + step - 1, s2 = i & 1;
+                        mbar_wait(bar_a2_full + 8 * s2, (uint32_t)(i >> 1) & 1u);
+                        if (step == 1 && ti >= 1) mbar_wait(bar_d2_empty, (uint32_t)(ti - 1) & 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint64_t da = umma_desc_sw128(smem_addr(sA2 + (size_t)s2 * 16384));
+                        const uint64_t dbd = umma_desc_sw128(smem_addr(sWproj + (size_t)s2 * p.wproj_stage));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16(tmem_base + IR_D2_COL, da + (uint64_t)(k * 2), dbd + (uint64_t)(k * 2), p.idesc_proj,
+                                     (step > 1) || (k > 0));
+                        umma_commit(bar_a2_empty + 8 * s2);
+                        if (step == p.n_e) umma_commit(bar_d2_full);
+                    }
+                }
+            }
+        }
+    } else if (warp >= 2 + IR_MID_WARPS) {
+        // ===================== depthwise 3x3 from the expanded patch =====================
+        const int pt = (int)threadIdx.x - 32 * (2 + IR_MID_WARPS);
+        const int j = pt & 7, rg = pt >> 3;                      // 16-byte channel chunk, row group (0..39)
+        const int st = p.stride, pw = p.pw, php = p.ph;
+        const int box_rows = p.bw * p.bh * p.bb;
+        const int quad = p.quad;
+        int q0[IR_DW_ROWS];                                      // patch position of tap (0,0) per owned row; -1: padding row
+#pragma unroll
+        for (int i = 0; i < IR_DW_ROWS; ++i) {
+            const int r = quad ? 4 * rg + i : rg + 4 * IR_DW_WARPS * i;
+            if (r < box_rows && r < TC_BM) {
+                const int dx = r % p.bw, qq = r / p.bw, dy = qq % p.bh, db = qq / p.bh;
+                q0[i] = dx * st + pw * (dy * st + php * db);
+            } else {
+                q0[i] = -1;
+            }
+        }
+        const __half2 lo2 = __float2half2_rn(p.dw_act == SSD_ACT_NONE ? -65504.0f : 0.0f);
+        const __half2 hi2 = __float2half2_rn(p.dw_act == SSD_ACT_RELU6 ? 6.0f : 65504.0f);
+        int it = 0;
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+            for (int e = 0; e < p.n_e; ++e, ++it) {
+                const int b = it & 1;
+                const uint32_t par = (uint32_t)(it >> 1) & 1u;
+                const bool cok = e * 64 + j * 8 < p.Cexp;
+                __half2 acc[IR_DW_ROWS][4];
+                {
+                    const float4 b0 = *reinterpret_cast<const float4*>(sBiasD + e * 64 + j * 8);
+                    const float4 b1 = *reinterpret_cast<const float4*>(sBiasD + e * 64 + j * 8 + 4);
+                    const __half2 b4[4] = {__floats2half2_rn(b0.x, b0.y), __floats2half2_rn(b0.z, b0.w),
+                                           __floats2half2_rn(b1.x, b1.y), __floats2half2_rn(b1.z, b1.w)};
+#pragma unroll
+                    for (int i = 0; i < IR_DW_ROWS; ++i)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[i][c] = b4[c];
+                }
+                mbar_wait(bar_ep_full + 8 * b, par);                                  // expanded patch + filter are there
+                const unsigned char* patch = sEp + (size_t)b * p.ep_stage;
+                const unsigned char* wsm = patch + p.ep_filter;
+                if (quad) {
+                    // sliding window: the 4 outputs of a thread share 6 input columns per filter row (18 loads, not 36)
+                    if (q0[0] >= 0) {
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            uint4 w3[3];
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const int tap = ky * 3 + kx;
+                                w3[kx] = *reinterpret_cast<const uint4*>(wsm + tap * 128 + ((j ^ (tap & 7)) << 4));
+                            }
+#pragma unroll
+                            for (int c = 0; c < 6; ++c) {
+                                const int q = q0[0] + c + pw * ky;
+                                const uint4 xv = *reinterpret_cast<const uint4*>(patch + (size_t)q * 128 + ((j ^ (q & 7)) << 4));
+                                const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const int kx = c - i;
+                                    if (kx >= 0 && kx < 3) {
+                                        const __half2* wh = reinterpret_cast<const __half2*>(&w3[kx]);
+#pragma unroll
+                                        for (int c2 = 0; c2 < 4; ++c2) acc[i][c2] = __hfma2(xh[c2], wh[c2], acc[i][c2]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const int tap = ky * 3 + kx;
+                            const uint4 wvv = *reinterpret_cast<const uint4*>(wsm + tap * 128 + ((j ^ (tap & 7)) << 4));
+                            const __half2* wh = reinterpret_cast<const __half2*>(&wvv);
+#pragma unroll
+                            for (int i = 0; i < IR_DW_ROWS; ++i) {
+                                if (q0[i] < 0) continue;
+                                const int q = q0[i] + kx + pw * ky;
+                                const uint4 xv = *reinterpret_cast<const uint4*>(patch + (size_t)q * 128 + ((j ^ (q & 7)) << 4));
+                                const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+                                for (int c2 = 0; c2 < 4; ++c2) acc[i][c2] = __hfma2(xh[c2], wh[c2], acc[i][c2]);
+                            }
+                        }
+                }
+                if (it >= 2) mbar_wait(bar_a2_empty + 8 * b, par ^ 1u);                 // A2 slot drained by the projection MMA
+                unsigned char* a_tile = sA2 + (size_t)b * 16384;
+#pragma unroll
+                for (int i = 0; i < IR_DW_ROWS; ++i) {
+                    const int r = quad ? 4 * rg + i : rg + 4 * IR_DW_WARPS * i;
+                    if (r >= TC_BM) continue;
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                    if (q0[i] >= 0 && cok) {
+                        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int c2 = 0; c2 < 4; ++c2) oh[c2] = __hmin2(__hmax2(acc[i][c2], lo2), hi2);
+                    }
+                    *reinterpret_cast<uint4*>(a_tile + r * 128 + ((j ^ (r & 7)) << 4)) = o;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic writes -> visible to the MMA / TMA
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(bar_a2_full + 8 * b); mbar_arrive(bar_ep_empty + 8 * b); }
+            }
+        }
+    } else {
+        // ===================== mid (D1 -> expanded patch) and final epilogue: warps 2..9 =====================
+        const int mw = warp - 2;
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may read
+        const int half = mw >> 2;                                // mid: which 128-row half; epilogue: which 32-column half
+        const int r = q * 32 + lane;                             // row inside a 128-row accumulator
+        const int pos = half * 128 + r;                          // patch position handled in the mid stage
+        const bool pos_live = half < p.halves && pos < p.P;
+        const int px = pos % p.pw, prr = pos / p.pw, py = prr % p.ph, pdb = prr / p.ph;
+        const bool elected = mw == 0 && lane == 0;
+        const float e_lo = p.exp_act == SSD_ACT_NONE ? -__int_as_float(0x7f800000) : 0.0f;
+        const float e_hi = p.exp_act == SSD_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
+        const float act_lo = p.act == SSD_ACT_NONE ? -__int_as_float(0x7f800000) : 0.0f;
+        const float act_hi = p.act == SSD_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
+        const long long pix0 = p.Cout, img0 = (long long)p.Ho * p.Wo * p.Cout;
+        int it = 0, ti = 0;
+        uint32_t n_groups = 0;
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++ti) {
+            int b0, oy0, ox0;
+            ir_tile_origin(p, t, b0, oy0, ox0);
+            // inside the image?  positions outside are the depthwise convolution's zero padding
+            const int iy = oy0 * p.stride - p.pad_t + py, ix = ox0 * p.stride - p.pad_l + px;
+            const bool inside = pos_live && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W && b0 + pdb < p.B;
+            for (int e = 0; e < p.n_e; ++e, ++it) {
+                const int db = it & 1;
+                const uint32_t par = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(bar_d1_full + 8 * db, par);
+                if (it >= 2) mbar_wait(bar_ep_empty + 8 * db, par ^ 1u);              // depthwise warps left this buffer
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                unsigned char* row = sEp + (size_t)db * p.ep_stage + (size_t)pos * 128;
+                const float* be = sBiasE + e * 64;
+                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)db * 128u + (uint32_t)half * 64u;
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {           // 32 columns at a time (register budget: 640 threads)
+                    uint32_t acc[32];
+                    if (half < p.halves) {                       // warp-uniform
+                        tmem_ld32(trow + (uint32_t)part * 32u, acc);
+                        tmem_ld_wait(acc);
+                    }
+                    if (pos_live) {
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                            if (inside) {
+                                const float4 b0v = *reinterpret_cast<const float4*>(be + part * 32 + h * 8);
+                                const float4 b1v = *reinterpret_cast<const float4*>(be + part * 32 + h * 8 + 4);
+                                const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
+                                float v[8];
+#pragma unroll
+                                for (int c = 0; c < 8; ++c)
+                                    v[c] = fminf(fmaxf(__uint_as_float(acc[h * 8 + c]) + bb[c], e_lo), e_hi);
+                                __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) oh[c] = __floats2half2_rn(v[2 * c], v[2 * c + 1]);
+                            }
+                            *reinterpret_cast<uint4*>(row + (((part * 4 + h) ^ (pos & 7)) << 4)) = o;
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(bar_d1_empty + 8 * db); mbar_arrive(bar_ep_full + 8 * db); }
+            }
+            // ---- final epilogue of this tile: D2 -> bias / residual -> fp16 -> swizzled staging tile -> TMA store ----
+            mbar_wait(bar_d2_full, (uint32_t)ti & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            bool row_ok = false;
+            long long row_off = 0;
+            {
+                const int dx = r % p.bw, qq = r / p.bw, dy = qq % p.bh, dbb = qq / p.bh;
+                const int b = b0 + dbb, oy = oy0 + dy, ox = ox0 + dx;
+                row_ok = dbb < p.bb && b < p.B && oy < p.Ho && ox < p.Wo;
+                row_off = (long long)b * img0 + (long long)(oy * p.Wo + ox) * pix0;
+            }
+            const uint32_t trow2 = tmem_base + ((uint32_t)(q * 32) << 16) + IR_D2_COL;
+            for (int g0 = 0; g0 < p.BN && g0 < p.Cout; g0 += 64, ++n_groups) {
+                unsigned char* buf = sOut + (size_t)(p.out_bufs == 2 ? (n_groups & 1u) : 0u) * TC_OUT_TILE;
+                const int c0 = g0 + half * TC_CHUNK;
+                const bool mine = c0 < p.BN && c0 < p.Cout;
+                uint32_t acc[TC_CHUNK];
+                if (mine) tmem_ld32(trow2 + (uint32_t)c0, acc);
+                if (elected) { if (p.out_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+                epi_barrier();
+                if (mine) {
+                    const int ncols = min(TC_CHUNK, p.Cout - c0);
+                    const float* sbias = sBiasP + c0;
+                    tmem_ld_wait(acc);
+#pragma unroll
+                    for (int h = 0; h < TC_CHUNK / 8; ++h) {
+                        const float4 b0v = *reinterpret_cast<const float4*>(sbias + h * 8);
+                        const float4 b1v = *reinterpret_cast<const float4*>(sbias + h * 8 + 4);
+                        const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
+                        float v[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            v[c] = fminf(fmaxf(__uint_as_float(acc[h * 8 + c]) + bb[c], act_lo), act_hi);
+                        if (p.res && row_ok && h * 8 < ncols) {
+                            const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + row_off + c0 + h * 8));
+                            const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const float2 f = __half22float2(rh[c]);
+                                v[2 * c] += f.x; v[2 * c + 1] += f.y;
+                            }
+                        }
+                        uint4 o;
+                        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) oh[c] = __floats2half2_rn(v[2 * c], v[2 * c + 1]);
+                        *reinterpret_cast<uint4*>(buf + r * 128 + (((half * 4 + h) ^ (r & 7)) << 4)) = o;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                epi_barrier();
+                if (elected) {
+                    tma_store_4d(&map_o, smem_addr(buf), g0, ox0, oy0, b0);
+                    bulk_commit();
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_d2_empty);
+        }
+        if (elected) bulk_wait_all();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(IR_TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side --
+static inline uint32_t up1k(size_t v) { return (uint32_t)((v + 1023) & ~(size_t)1023); }
+
+// Tile geometry + shared-memory layout; false when nothing fits.
+static bool irblock_plan(const ssd_irblock_desc* d, IrParams* pp, size_t* smem_out) {
+    IrParams& p = *pp;
+    const int s = d->stride;
+    p.kc_in = (d->Cin + 63) / 64;
+    p.k16_last = (d->Cin - 64 * (p.kc_in - 1) + 15) / 16;
+    p.n_e = (d->Cexp + 63) / 64;
+    p.BN = (d->Cout + 15) / 16 * 16;
+    p.wproj_stage = up1k((size_t)p.BN * 128);
+    p.wproj_bytes = (uint32_t)p.BN * 128u;
+    const size_t budget = (size_t)227 * 1024 - 1024;               // minus the alignment slack
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const long long M = (long long)d->B * d->Ho * d->Wo;
+    double best = 1e30;
+    bool found = false;
+    for (int bw = 1; bw <= min(d->Wo, TC_BM); ++bw) {
+        const int tw = (d->Wo + bw - 1) / bw;
+        for (int bh = 1; bh <= min(d->Ho, TC_BM / bw); ++bh) {
+            const int th = (d->Ho + bh - 1) / bh;
+            int bb = 1;
+            if (bw == d->Wo && bh == d->Ho) {
+                const int pw1 = (bw - 1) * s + 3, ph1 = (bh - 1) * s + 3;
+                bb = max(1, min(d->B, min(TC_BM / (bw * bh), 256 / (pw1 * ph1))));
+            }
+            const int tb = (d->B + bb - 1) / bb;
+            const int pw = (bw - 1) * s + 3, ph = (bh - 1) * s + 3;
+            const int P = pw * ph * bb;
+            if (P > 256 || pw > 256 || ph > 256) continue;
+            // layout
+            const uint32_t patch_chunk = up1k((size_t)P * 128);
+            const uint32_t ep_rows = up1k((size_t)P * 128);
+            size_t fixed = (size_t)p.kc_in * patch_chunk + 2 * (size_t)(ep_rows + 2048) + 2 * 16384 + 2 * (size_t)p.wproj_stage +
+                           (size_t)(2 * p.n_e * 64 + 256) * 4 + 21 * 8 + 16;
+            int wst = 0, obufs = 0;
+            for (int ws_try = 2; ws_try >= 1 && !wst; --ws_try)
+                for (int ob = 2; ob >= 1; --ob)
+                    if (fixed + (size_t)ws_try * p.kc_in * 8192 + (size_t)ob * TC_OUT_TILE <= budget) { wst = ws_try; obufs = ob; break; }
+            if (!wst) continue;
+            // cost model: waves of tiles x (depthwise rounds of the tile + fixed per-slice hand-off cost)
+            const long long tiles = (long long)tw * th * tb;
+            const double waves = (double)((tiles + sms - 1) / sms);
+            const int rows = bw * bh * bb;
+            const bool quad = s == 1 && bw % 4 == 0;
+            const double dw_rounds = quad ? (double)((rows / 4 * 8 + 32 * IR_DW_WARPS - 1) / (32 * IR_DW_WARPS)) * 4 * 0.6
+                                          : (double)((rows * 8 + 32 * IR_DW_WARPS - 1) / (32 * IR_DW_WARPS));
+            const double mid = P > 128 ? 1.0 : 0.6;
+            const double cost = waves * (fmax(dw_rounds, mid) + 1.2) * (1.0 + 0.02 * (double)((long long)tiles * TC_BM - M) / (double)M);
+            if (cost < best - 1e-9) {
+                best = cost; found = true;
+                p.bw = bw; p.bh = bh; p.bb = bb; p.tiles_w = tw; p.tiles_h = th; p.n_tiles = (int)tiles;
+                p.pw = pw; p.ph = ph; p.P = P; p.halves = P > 128 ? 2 : 1;
+                p.quad = quad ? 1 : 0;
+                p.patch_chunk = patch_chunk; p.patch_bytes = (uint32_t)P * 128u;
+                p.wexp_stages = wst; p.wexp_stage = (uint32_t)p.kc_in * 8192u;
+                p.ep_filter = ep_rows; p.ep_stage = ep_rows + 2048;
+                p.out_bufs = obufs;
+                uint32_t off = 0;
+                p.off_patch = off; off += (uint32_t)p.kc_in * patch_chunk;
+                p.off_wexp = off;  off += (uint32_t)wst * p.wexp_stage;
+                p.off_ep = off;    off += 2 * p.ep_stage;
+                p.off_a2 = off;    off += 2 * 16384;
+                p.off_wproj = off; off += 2 * p.wproj_stage;
+                p.off_out = off;   off += (uint32_t)obufs * TC_OUT_TILE;
+                p.off_bias = off;  off += (uint32_t)(2 * p.n_e * 64 + 256) * 4;
+                off = (off + 7u) & ~7u;
+                p.off_bars = off;  off += 21 * 8 + 16;
+                *smem_out = (size_t)off + 1024;
+            }
+        }
+    }
+    return found;
+}
+
+bool conv_irblock_supported(const ssd_irblock_desc* d) {
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (!(d->Cin % 8 == 0 && d->Cexp % 8 == 0 && d->Cout % 8 == 0 && d->Cout <= 256 && d->Cin <= 256 && d->Cexp <= 1024 &&
+          (d->stride == 1 || d->stride == 2) && al16(d->in) && al16(d->exp_weight) && al16(d->dw_weight) &&
+          al16(d->proj_weight) && al16(d->out) && (d->residual == nullptr || al16(d->residual))))
+        return false;
+    IrParams p;
+    memset(&p, 0, sizeof(p));
+    size_t smem = 0;
+    return irblock_plan(d, &p, &smem);
+}
+
+int conv_irblock_launch(const ssd_irblock_desc* d, cudaStream_t st) {
+    IrParams p;
+    memset(&p, 0, sizeof(p));
+    size_t smem = 0;
+    if (!irblock_plan(d, &p, &smem)) return fail(SSD_ERR_UNSUPPORTED, "ssd_irblock: no tile geometry fits shared memory");
+    p.B = d->B; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cexp = d->Cexp; p.Cout = d->Cout; p.Ho = d->Ho; p.Wo = d->Wo;
+    p.stride = d->stride; p.pad_t = d->pad_top; p.pad_l = d->pad_left;
+    p.exp_act = d->exp_act; p.dw_act = d->dw_act; p.act = d->act;
+    p.exp_bias = d->exp_bias; p.dw_bias = d->dw_bias; p.proj_bias = d->proj_bias; p.res = (const __half*)d->residual;
+    p.idesc_exp = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    p.idesc_proj = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+    CUtensorMap map_x, map_we, map_dw, map_wp, map_o;
+    {
+        uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+        uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
+        uint32_t box[4] = {64, (uint32_t)p.pw, (uint32_t)p.ph, (uint32_t)p.bb};
+        int rc = cached_map(&map_x, d->in, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)d->Cin, (uint64_t)d->Cexp};
+        uint64_t str[1] = {(uint64_t)d->Cin * 2};
+        uint32_t box[2] = {64, 64};
+        int rc = cached_map(&map_we, d->exp_weight, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)d->Cexp, 9};
+        uint64_t str[1] = {(uint64_t)d->Cexp * 2};
+        uint32_t box[2] = {64, 9};
+        int rc = cached_map(&map_dw, d->dw_weight, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)d->Cexp, (uint64_t)d->Cout};
+        uint64_t str[1] = {(uint64_t)d->Cexp * 2};
+        uint32_t box[2] = {64, (uint32_t)p.BN};
+        int rc = cached_map(&map_wp, d->proj_weight, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->B};
+        uint64_t str[3] = {(uint64_t)d->Cout * 2, (uint64_t)d->Wo * d->Cout * 2, (uint64_t)d->Ho * d->Wo * d->Cout * 2};
+        uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bb};
+        int rc = cached_map(&map_o, d->out, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    static thread_local int attr_dev = -1;
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (attr_dev != cur_dev) {
+        cudaError_t e = cudaFuncSetAttribute(conv_irblock_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "ssd_irblock: cudaFuncSetAttribute");
+        attr_dev = cur_dev;
+    }
+    dim3 grid(min(p.n_tiles, sm_count()), 1, 1);
+    cudaError_t le = launch_pdl(conv_irblock_tcgen05_kernel, grid, dim3(IR_THREADS), smem, st, map_x, map_we, map_dw, map_wp, map_o, p);
+    if (le != cudaSuccess) return cuda_fail(le, "conv_irblock_tcgen05_kernel");
+    return SSD_OK;
+}
+
+}  // namespace ssd
+
+extern "C" int ssd_irblock(const ssd_irblock_desc* d, ssd_stream_t stream) {
+    SSD_REQUIRE_PTR(d);
+    SSD_REQUIRE_PTR(d->in); SSD_REQUIRE_PTR(d->exp_weight); SSD_REQUIRE_PTR(d->dw_weight); SSD_REQUIRE_PTR(d->proj_weight);
+    SSD_REQUIRE_PTR(d->out);
+    SSD_REQUIRE(d->B >= 1 && d->H >= 1 && d->W >= 1 && d->Cin >= 8 && d->Cexp >= 8 && d->Cout >= 8 && d->Ho >= 1 && d->Wo >= 1 &&
+                d->exp_act >= SSD_ACT_NONE && d->exp_act <= SSD_ACT_RELU6 && d->dw_act >= SSD_ACT_NONE && d->dw_act <= SSD_ACT_RELU6 &&
+                d->act >= SSD_ACT_NONE && d->act <= SSD_ACT_RELU6, SSD_ERR_SHAPE,
+                "ssd_irblock: bad shape B=%d H=%d W=%d Cin=%d Cexp=%d Ho=%d Wo=%d Cout=%d", d->B, d->H, d->W, d->Cin, d->Cexp,
+                d->Ho, d->Wo, d->Cout);
+    SSD_REQUIRE(ssd::conv_irblock_supported(d), SSD_ERR_UNSUPPORTED,
+                "ssd_irblock: unsupported configuration (channels %% 8, Cin <= 256, Cexp <= 1024, Cout <= 256, stride 1|2, "
+                "16-byte aligned pointers)");
+    return ssd::conv_irblock_launch(d, ssd::as_stream(stream));
+}
+
+extern "C" int ssd_irblock_supported(const ssd_irblock_desc* d) {
+    if (!d || !d->in || !d->exp_weight || !d->dw_weight || !d->proj_weight || !d->out) return 0;
+    return ssd::conv_irblock_supported(d) ? 1 : 0;
+}

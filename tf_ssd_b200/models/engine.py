@@ -28,7 +28,7 @@ import numpy as np
 import torch
 
 from tf_ssd_b200 import _ffi
-from tf_ssd_b200._ffi_conv import ACT_NONE, ACT_RELU, ACT_RELU6, ConvDesc, DwProjDesc
+from tf_ssd_b200._ffi_conv import ACT_NONE, ACT_RELU, ACT_RELU6, ConvDesc, DwProjDesc, IrBlockDesc
 
 BN_EPS = 1e-3        # keras_applications.mobilenet_v2: BatchNormalization(epsilon=1e-3, momentum=0.999)
 
@@ -90,9 +90,11 @@ def mobilenet_v2_graph(n: Any, x: Act, hp: Dict[str, Any]) -> List[Act]:
         prefix = f"block_{bid}_" if bid else "expanded_conv_"
         inp = x
         if bid:
-            x = n.conv(x, prefix + "expand", t * inp.C, act=ACT_RELU6, bn=prefix + "expand_BN", use_bias=False)
+            # block_13_expand_relu is a head tap (:27): it must exist in memory, so that block is not fused whole
+            x = n.conv(x, prefix + "expand", t * inp.C, act=ACT_RELU6, bn=prefix + "expand_BN", use_bias=False,
+                       tap=(bid == 13))
             if bid == 13:
-                taps.append(x)                                  # block_13_expand_relu   :27
+                taps.append(x)
         x = n.dw(x, prefix + "depthwise", stride=s, act=ACT_RELU6, bn=prefix + "depthwise_BN")
         res = inp if (s == 1 and inp.C == c) else None          # block_i_add
         x = n.conv(x, prefix + "project", c, act=ACT_NONE, bn=prefix + "project_BN", use_bias=False, residual=res)
@@ -172,7 +174,7 @@ class _ParamTracer:
         self.weights[name + "/moving_variance"] = np.ones(c, np.float32)
 
     def conv(self, x, name, cout, k=1, stride=1, pad="same", dilation=1, act=ACT_NONE, bn=None, use_bias=True,
-             residual=None, init="he_normal", l2=False):
+             residual=None, init="he_normal", l2=False, tap=False):
         ph, pw = _resolve_pads(x.H, x.W, k, stride, dilation, pad)
         Ho, Wo = _out_size(x.H, k, stride, dilation, ph), _out_size(x.W, k, stride, dilation, pw)
         self.weights[name + "/kernel"] = self._kernel((k, k, x.C, cout), k * k * x.C, k * k * cout, init)
@@ -384,7 +386,7 @@ class _PlanBuilder:
         return Ho, Wo
 
     def conv(self, x, name, cout, k=1, stride=1, pad="same", dilation=1, act=ACT_NONE, bn=None, use_bias=True,
-             residual=None, init=None, l2=False):
+             residual=None, init=None, l2=False, tap=False):
         ph, pw = _resolve_pads(x.H, x.W, k, stride, dilation, pad)
         if x.t is None:                                  # first layer, fed by the fp32 image
             if k == 3 and stride == 2 and dilation == 1 and cout == 32 and residual is None:
@@ -400,6 +402,8 @@ class _PlanBuilder:
                 and dilation == 1 and cout <= 256 and cout % 8 == 0 and type(self) is _PlanBuilder):
             # depthwise 3x3 -> 1x1 projection as ONE launch (ssd_dwproj): the depthwise output stays on chip
             dm = last.meta
+            if self._try_irblock(name, x, w, b, cout, act, residual, out, Ho, Wo):
+                return Act(out, Ho, Wo, cout)
             d = DwProjDesc()
             d.inp, d.dw_weight, d.dw_bias = dm["x"].data_ptr(), dm["w"].data_ptr(), dm["bias"].data_ptr()
             d.proj_weight, d.proj_bias = w.data_ptr(), b.data_ptr()
@@ -422,7 +426,49 @@ class _PlanBuilder:
                                         (d, w, b, dm["x"], dm["w"], dm["bias"], out), meta))
             return Act(out, Ho, Wo, cout)
         self._emit_conv(name, x, w, b, cout, k, stride, dilation, ph, pw, act, residual, out, real_cin=real_cin)
+        if tap:
+            self.plan.steps[-1].meta["tap"] = True
         return Act(out, Ho, Wo, cout)
+
+    # expand 1x1 -> depthwise 3x3 -> project 1x1 as ONE launch (ssd_irblock): "1" / "0"
+    FUSE_IR = os.environ.get("SSD_B200_FUSE_IR", "1")
+
+    def _try_irblock(self, name, x, w, b, cout, act, residual, out, Ho, Wo) -> bool:
+        """Called while emitting a block's 1x1 projection with a depthwise step last in the plan: when the step
+        before that is the block's 1x1 expansion (consumed by the depthwise layer only), the three become one launch."""
+        steps = self.plan.steps
+        if self.FUSE_IR in ("0", "") or len(steps) < 2 or type(self) is not _PlanBuilder:
+            return False
+        dws, exp = steps[-1], steps[-2]
+        dm, em = dws.meta, exp.meta
+        if not (exp.kind == "conv" and em["k"] == 1 and em["stride"] == 1 and em["res"] is None and not em.get("tap")
+                and not em["out_f32"] and em["out0"] is dm["x"] and "head" not in em):
+            return False
+        xin = em["x"]
+        d = IrBlockDesc()
+        d.inp, d.exp_weight, d.exp_bias = xin.data_ptr(), em["w"].data_ptr(), em["bias"].data_ptr()
+        d.dw_weight, d.dw_bias = dm["w"].data_ptr(), dm["bias"].data_ptr()
+        d.proj_weight, d.proj_bias = w.data_ptr(), b.data_ptr()
+        d.residual = residual.t.data_ptr() if residual is not None else None
+        d.out = out.data_ptr()
+        d.B, d.H, d.W, d.Cin, d.Cexp = self.B, xin.shape[1], xin.shape[2], xin.shape[3], x.C
+        d.Ho, d.Wo, d.Cout = Ho, Wo, cout
+        d.stride, d.pad_top, d.pad_left = dm["stride"], dm["ph"][0], dm["pw"][0]
+        d.exp_act, d.dw_act, d.act = em["act"], dm["act"], act
+        if not self.lib.ssd_irblock_supported(C.byref(d)):
+            return False
+        steps.pop(); steps.pop()
+        B, H, W, cin, cexp = self.B, d.H, d.W, d.Cin, d.Cexp
+        nbytes = B * H * W * cin * 2 + (cin * cexp + 9 * cexp + cexp * cout) * 2 + \
+            B * Ho * Wo * cout * 2 * (2 if residual is not None else 1)
+        flops = 2.0 * B * (H * W * cin * cexp + Ho * Wo * cexp * (9 + cout))
+        meta = dict(x=xin, exp_w=em["w"], exp_bias=em["bias"], exp_act=em["act"], dw_w=dm["w"], dw_bias=dm["bias"],
+                    dw_stride=dm["stride"], dw_ph=dm["ph"], dw_pw=dm["pw"], dw_act=dm["act"], w=w, bias=b,
+                    res=residual.t if residual is not None else None, out0=out, act=act, Ho=Ho, Wo=Wo, cout=cout,
+                    exp_name=exp.name, dw_name=dws.name)
+        steps.append(Step(name, "irblock", self.lib.ssd_irblock, (C.byref(d),), flops, nbytes,
+                          (d, w, b, xin, em["w"], em["bias"], dm["w"], dm["bias"], out), meta))
+        return True
 
     def dw(self, x, name, stride=1, act=ACT_RELU6, bn=None):
         ph, pw = _resolve_pads(x.H, x.W, 3, stride, 1, "same" if stride == 1 else "correct")
@@ -518,7 +564,7 @@ class _TrainPlanBuilder(_PlanBuilder):
         return Act(out, x_pre.H, x_pre.W, C_)
 
     def conv(self, x, name, cout, k=1, stride=1, pad="same", dilation=1, act=ACT_NONE, bn=None, use_bias=True,
-             residual=None, init=None, l2=False):
+             residual=None, init=None, l2=False, tap=False):
         if x.t is None:
             x = self._image_as_f16()
         if bn is None:
