@@ -249,6 +249,9 @@ typedef struct ssd_irblock_desc {
 } ssd_irblock_desc;
 int ssd_irblock(const ssd_irblock_desc* h_desc, ssd_stream_t stream);
 int ssd_irblock_supported(const ssd_irblock_desc* h_desc);
+/* Debug aid, not a reference interface: d_buf = device buffer of 5 x 512 uint64 that CTA 0 of later ssd_irblock
+ * launches fills with per-role (globaltimer << 8 | tag) stamps (tools/trace_irblock.py); NULL switches it off. */
+int ssd_irblock_trace(void* d_buf);
 
 /* MobileNetV2 stem: keras_applications Conv1_pad + Conv1 (3x3, stride 2, Cin = 3) + bn_Conv1 +
  * Conv1_relu (models/ssd_mobilenet_v2.py:25), computed straight from the fp32 NHWC image

@@ -28,8 +28,9 @@ namespace ssd {
 
 constexpr int IR_MID_WARPS = 8;                     // warps 2..9
 constexpr int IR_DW_WARPS = 10;                     // warps 10..19
-constexpr int IR_THREADS = 64 + 32 * (IR_MID_WARPS + IR_DW_WARPS);      // 640
-constexpr int IR_DW_ROWS = (TC_BM + 4 * IR_DW_WARPS - 1) / (4 * IR_DW_WARPS);   // tile rows per depthwise thread (4)
+constexpr int IR_EPI_WARPS = 4;                     // warps 20..23: final epilogue (one per TMEM lane quarter)
+constexpr int IR_THREADS = 64 + 32 * (IR_MID_WARPS + IR_DW_WARPS + IR_EPI_WARPS);      // 768
+
 constexpr uint32_t IR_D2_COL = 256;                 // TMEM: D1[buf][half] at buf*128 + half*64, D2 at 256
 constexpr uint32_t IR_TMEM_COLS = 512;
 
@@ -43,9 +44,11 @@ struct IrParams {
     int n_e;                         // 64-channel slices of the expanded tensor
     int BN;                          // projection N (Cout rounded up to 16)
     int exp_act, dw_act, act, quad;
+    int dw_R;                        // tile rows per depthwise thread (1..4; quad mode: one group of 4)
     uint32_t idesc_exp, idesc_proj;
     // shared-memory layout (byte offsets from the 1024-aligned base)
-    uint32_t off_patch, patch_chunk;             // input patch: kc_in chunks of [P rows][128 B]
+    uint32_t off_patch, patch_chunk;             // input patch: [n_patch][kc_in chunks of [P rows][128 B]]
+    int n_patch;                                 // 1 or 2 patch buffers (2: the next tile's patch is prefetched a tile ahead)
     uint32_t off_wexp, wexp_stage; int wexp_stages;   // [stages][kc_in][64 rows][128 B]
     uint32_t off_ep, ep_stage, ep_filter;        // expanded patch [2][P rows x 128 B | 9 x 128 B depthwise filter]
     uint32_t off_a2;                             // [2][128 rows][128 B]
@@ -55,7 +58,97 @@ struct IrParams {
     uint32_t off_bars;
     uint32_t patch_bytes, wproj_bytes;
     const float* exp_bias; const float* dw_bias; const float* proj_bias; const __half* res;
+    unsigned long long* trace;       // debug: per-role event timestamps of CTA 0 (ssd_irblock_trace), else nullptr
 };
+
+// Debug tracing (tools/trace_irblock.py): CTA 0 records globaltimer stamps, 5 roles x 512 slots.
+__device__ __forceinline__ void ir_stamp(const IrParams& p, int role, int& slot, int tag) {
+    if (p.trace && blockIdx.x == 0 && slot < 512) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        p.trace[role * 512 + slot] = (t << 8) | (unsigned long long)(tag & 0xff);
+        ++slot;
+    }
+}
+
+// Explicit shared-memory accesses with 32-bit addresses (LDS / STS instead of generic LD / ST and 64-bit address math).
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+// Non-blocking probe of an mbarrier phase (acquire): lets the MMA thread serve whichever of its two streams is ready.
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void ir_epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * IR_EPI_WARPS) : "memory"); }
+// byte offset of 16-byte chunk j of row q in a 128-byte-swizzled [rows][128 B] tile
+__device__ __forceinline__ uint32_t sw_off(int q, int j) { return (uint32_t)(q * 128 + ((j ^ (q & 7)) << 4)); }
+
+// Depthwise 3x3 of R tile rows x 8 channels for one thread, BRANCH-FREE: every load is unconditional (rows that do not
+// exist read position 0 and their result is discarded), so the compiler issues the shared-memory loads back to back
+// instead of one dependent load per basic block.  QUAD: the R (= 4) rows are horizontally adjacent outputs of a stride-1
+// tile and share 6 input columns per filter row (18 loads instead of 36).
+template <int R, bool QUAD>
+__device__ __forceinline__ void ir_depthwise(uint32_t patch, uint32_t wsm, int j, int pw, const int (&q0)[4],
+                                             const __half2 (&bias)[4], __half2 (&acc)[4][4]) {
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[i][c] = bias[c];
+    if (QUAD) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            uint4 w3[3];
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) w3[kx] = lds128(wsm + sw_off(ky * 3 + kx, j));
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const uint4 xv = lds128(patch + sw_off(q0[0] + c + pw * ky, j));
+                const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int kx = c - i;
+                    if (kx >= 0 && kx < 3) {
+                        const __half2* wh = reinterpret_cast<const __half2*>(&w3[kx]);
+#pragma unroll
+                        for (int c2 = 0; c2 < 4; ++c2) acc[i][c2] = __hfma2(xh[c2], wh[c2], acc[i][c2]);
+                    }
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const uint4 wv = lds128(wsm + sw_off(ky * 3 + kx, j));
+                const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    const uint4 xv = lds128(patch + sw_off(q0[i] + kx + pw * ky, j));
+                    const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+                    for (int c2 = 0; c2 < 4; ++c2) acc[i][c2] = __hfma2(xh[c2], wh[c2], acc[i][c2]);
+                }
+            }
+    }
+}
 
 __device__ __forceinline__ void ir_tile_origin(const IrParams& p, int t, int& b0, int& oy0, int& ox0) {
     const int per_img = p.tiles_w * p.tiles_h;
@@ -80,24 +173,27 @@ conv_irblock_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
     float* sBiasD = sBiasE + p.n_e * 64;
     float* sBiasP = sBiasD + p.n_e * 64;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
     pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_addr(bars);
-    const uint32_t bar_patch_full = bar0, bar_patch_empty = bar0 + 8;
-    const uint32_t bar_wexp_full = bar0 + 16, bar_wexp_empty = bar0 + 32;       // [2] each
-    const uint32_t bar_d1_full = bar0 + 48, bar_d1_empty = bar0 + 64;
-    const uint32_t bar_ep_full = bar0 + 80, bar_ep_empty = bar0 + 96;
-    const uint32_t bar_a2_full = bar0 + 112, bar_a2_empty = bar0 + 128;
-    const uint32_t bar_d2_full = bar0 + 144, bar_d2_empty = bar0 + 152;
+    const uint32_t bar_patch_full = bar0, bar_patch_empty = bar0 + 16;          // [2] each
+    const uint32_t bar_wexp_full = bar0 + 32, bar_wexp_empty = bar0 + 48;
+    const uint32_t bar_d1_full = bar0 + 64, bar_d1_empty = bar0 + 80;
+    const uint32_t bar_ep_full = bar0 + 96, bar_ep_empty = bar0 + 112;
+    const uint32_t bar_a2_full = bar0 + 128, bar_a2_empty = bar0 + 144;
+    const uint32_t bar_d2_full = bar0 + 160, bar_d2_empty = bar0 + 168;
+    const uint32_t patch_buf = (uint32_t)p.kc_in * p.patch_chunk;               // bytes of one patch buffer
+    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const int my_tiles = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_we); tma_prefetch_desc(&map_dw);
         tma_prefetch_desc(&map_wp); tma_prefetch_desc(&map_o);
-        mbar_init(bar_patch_full, 1);                             // expect_tx arrive (+ TMA bytes)
-        mbar_init(bar_patch_empty, 1);                            // tcgen05.commit after the tile's last expand MMA
         for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_patch_full + 8 * s, 1);                 // expect_tx arrive (+ TMA bytes)
+            mbar_init(bar_patch_empty + 8 * s, 1);                // tcgen05.commit after the tile's last expand MMA
             mbar_init(bar_wexp_full + 8 * s, 1);
             mbar_init(bar_wexp_empty + 8 * s, 1);                 // tcgen05.commit
             mbar_init(bar_d1_full + 8 * s, 1);                    // tcgen05.commit
@@ -108,7 +204,7 @@ conv_irblock_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
             mbar_init(bar_a2_empty + 8 * s, 1);                   // tcgen05.commit
         }
         mbar_init(bar_d2_full, 1);                                // tcgen05.commit
-        mbar_init(bar_d2_empty, IR_MID_WARPS);
+        mbar_init(bar_d2_empty, IR_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -130,50 +226,80 @@ conv_irblock_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
 
     if (warp == 0) {
         // ===================== TMA producer =====================
+        // Four independent streams -- input patches, expansion weight slices, depthwise filter slices, projection weight
+        // slices -- each gated only by ITS consumer's "empty" barrier.  The thread polls the barriers without blocking
+        // and issues whatever is ready, so e.g. the next expansion weights never wait behind a depthwise stage.
         if (lane == 0) {
-            int it = 0, ti = 0;
-            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++ti) {
-                int b0, oy0, ox0;
-                ir_tile_origin(p, t, b0, oy0, ox0);
-                if (ti >= 1) mbar_wait(bar_patch_empty, (uint32_t)(ti - 1) & 1u);
-                mbar_expect_tx(bar_patch_full, (uint32_t)p.kc_in * p.patch_bytes);
-                for (int kc = 0; kc < p.kc_in; ++kc)
-                    tma_load_4d(smem_addr(sPatch + (size_t)kc * p.patch_chunk), &map_x, bar_patch_full, kc * 64,
-                                ox0 * p.stride - p.pad_l, oy0 * p.stride - p.pad_t, b0);
-                for (int e = 0; e < p.n_e; ++e, ++it) {
-                    const int ws = it % p.wexp_stages, wq = it / p.wexp_stages;
-                    if (wq >= 1) mbar_wait(bar_wexp_empty + 8 * ws, (uint32_t)(wq - 1) & 1u);
-                    mbar_expect_tx(bar_wexp_full + 8 * ws, (uint32_t)p.kc_in * 8192u);
-                    for (int kc = 0; kc < p.kc_in; ++kc)
-                        tma_load_2d(smem_addr(sWexp + (size_t)ws * p.wexp_stage + (size_t)kc * 8192), &map_we,
-                                    bar_wexp_full + 8 * ws, kc * 64, e * 64);
-                    const int b = it & 1;
-                    const uint32_t par = (uint32_t)((it >> 1) - 1) & 1u;
-                    if (it >= 2) mbar_wait(bar_ep_empty + 8 * b, par);
-                    mbar_expect_tx(bar_ep_full + 8 * b, 9 * 128);
-                    tma_load_2d(smem_addr(sEp + (size_t)b * p.ep_stage + p.ep_filter), &map_dw, bar_ep_full + 8 * b, e * 64, 0);
-                    if (it >= 2) mbar_wait(bar_a2_empty + 8 * b, par);
-                    mbar_expect_tx(bar_a2_full + 8 * b, p.wproj_bytes);
-                    tma_load_2d(smem_addr(sWproj + (size_t)b * p.wproj_stage), &map_wp, bar_a2_full + 8 * b, e * 64, 0);
+            const int G = my_tiles * p.n_e;
+            int tp = 0, gw = 0, gf = 0, gq = 0, tslot = 0;
+            while (tp < my_tiles || gw < G || gf < G || gq < G) {
+                if (tp < my_tiles && tp * p.n_e <= gw + p.n_e) {          // at most one tile ahead of the weight stream
+                    const int pb = tp % p.n_patch, pq = tp / p.n_patch;
+                    if (pq == 0 || mbar_test(bar_patch_empty + 8 * pb, (uint32_t)(pq - 1) & 1u)) {
+                        int b0, oy0, ox0;
+                        ir_tile_origin(p, (int)blockIdx.x + tp * (int)gridDim.x, b0, oy0, ox0);
+                        mbar_expect_tx(bar_patch_full + 8 * pb, (uint32_t)p.kc_in * p.patch_bytes);
+                        for (int kc = 0; kc < p.kc_in; ++kc)
+                            tma_load_4d(smem_addr(sPatch + (size_t)pb * patch_buf + (size_t)kc * p.patch_chunk), &map_x,
+                                        bar_patch_full + 8 * pb, kc * 64, ox0 * p.stride - p.pad_l, oy0 * p.stride - p.pad_t, b0);
+                        ++tp;
+                        ir_stamp(p, 0, tslot, 1);
+                    }
+                }
+                if (gw < G) {
+                    const int ws = gw % p.wexp_stages, wq = gw / p.wexp_stages, e = gw % p.n_e;
+                    if (wq == 0 || mbar_test(bar_wexp_empty + 8 * ws, (uint32_t)(wq - 1) & 1u)) {
+                        mbar_expect_tx(bar_wexp_full + 8 * ws, (uint32_t)p.kc_in * 8192u);
+                        for (int kc = 0; kc < p.kc_in; ++kc)
+                            tma_load_2d(smem_addr(sWexp + (size_t)ws * p.wexp_stage + (size_t)kc * 8192), &map_we,
+                                        bar_wexp_full + 8 * ws, kc * 64, e * 64);
+                        ++gw;
+                        ir_stamp(p, 0, tslot, 2);
+                    }
+                }
+                if (gf < G) {
+                    const int b = gf & 1, e = gf % p.n_e;
+                    if (gf < 2 || mbar_test(bar_ep_empty + 8 * b, (uint32_t)((gf >> 1) - 1) & 1u)) {
+                        mbar_expect_tx(bar_ep_full + 8 * b, 9 * 128);
+                        tma_load_2d(smem_addr(sEp + (size_t)b * p.ep_stage + p.ep_filter), &map_dw, bar_ep_full + 8 * b, e * 64, 0);
+                        ++gf;
+                    }
+                }
+                if (gq < G) {
+                    const int b = gq & 1, e = gq % p.n_e;
+                    if (gq < 2 || mbar_test(bar_a2_empty + 8 * b, (uint32_t)((gq >> 1) - 1) & 1u)) {
+                        mbar_expect_tx(bar_a2_full + 8 * b, p.wproj_bytes);
+                        tma_load_2d(smem_addr(sWproj + (size_t)b * p.wproj_stage), &map_wp, bar_a2_full + 8 * b, e * 64, 0);
+                        ++gq;
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer: expand of slice e, then projection of slice e - 1 =====================
+        // ===================== MMA issuer =====================
+        // Two independent streams over all slices of this CTA (tile boundaries included): the EXPANSION of slice ge (gated
+        // by the weight slice, the patch and a free D1 buffer) and the PROJECTION of slice gp (gated by the depthwise
+        // warps).  The thread polls both with non-blocking mbarrier probes and issues whichever is ready, so the expansion
+        // and the mid stage run up to two slices ahead of the depthwise stage instead of in lock step with it.
         if (lane == 0) {
-            int it = 0, ti = 0;
-            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++ti, it += p.n_e) {
-                mbar_wait(bar_patch_full, (uint32_t)ti & 1u);
-                for (int step = 0; step <= p.n_e; ++step) {
-                    if (step < p.n_e) {
-                        const int i = it + step, ws = i % p.wexp_stages, wq = i / p.wexp_stages, db = i & 1;
-                        mbar_wait(bar_wexp_full + 8 * ws, (uint32_t)wq & 1u);
-                        if (i >= 2) mbar_wait(bar_d1_empty + 8 * db, (uint32_t)((i >> 1) - 1) & 1u);
+            const int G = my_tiles * p.n_e;
+            int tslot = 0;
+            int ge = 0, gp = 0;
+            while (gp < G) {
+                if (ge < G) {
+                    const int ti = ge / p.n_e, e = ge - ti * p.n_e;
+                    const int pb = ti % p.n_patch, pq = ti / p.n_patch;
+                    const int ws = ge % p.wexp_stages, wq = ge / p.wexp_stages, db = ge & 1;
+                    if ((e != 0 || mbar_test(bar_patch_full + 8 * pb, (uint32_t)pq & 1u)) &&
+                        mbar_test(bar_wexp_full + 8 * ws, (uint32_t)wq & 1u) &&
+                        (ge < 2 || mbar_test(bar_d1_empty + 8 * db, (uint32_t)((ge >> 1) - 1) & 1u))) {
+                        ir_stamp(p, 1, tslot, 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         for (int h = 0; h < p.halves; ++h) {
                             const uint32_t tacc = tmem_base + (uint32_t)db * 128u + (uint32_t)h * 64u;
                             for (int kc = 0; kc < p.kc_in; ++kc) {
-                                const uint64_t da = umma_desc_sw128(smem_addr(sPatch + (size_t)kc * p.patch_chunk + (size_t)h * 16384));
+                                const uint64_t da = umma_desc_sw128(smem_addr(sPatch + (size_t)pb * patch_buf +
+                                                                              (size_t)kc * p.patch_chunk + (size_t)h * 16384));
                                 const uint64_t dbd = umma_desc_sw128(smem_addr(sWexp + (size_t)ws * p.wexp_stage + (size_t)kc * 8192));
                                 const int nk = kc == p.kc_in - 1 ? p.k16_last : 4;
                                 for (int k = 0; k < nk; ++k)
@@ -182,197 +308,117 @@ conv_irblock_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
                         }
                         umma_commit(bar_wexp_empty + 8 * ws);
                         umma_commit(bar_d1_full + 8 * db);
-                        if (step == p.n_e - 1) umma_commit(bar_patch_empty);     // the input patch may be overwritten
+                        if (e == p.n_e - 1) umma_commit(bar_patch_empty + 8 * pb);   // this patch buffer may be overwritten
+                        ++ge;
                     }
-                    if (step >= 1) {
-                        const int i = it + step - 1, s2 = i & 1;
-                        mbar_wait(bar_a2_full + 8 * s2, (uint32_t)(i >> 1) & 1u);
-                        if (step == 1 && ti >= 1) mbar_wait(bar_d2_empty, (uint32_t)(ti - 1) & 1u);
+                }
+                if (gp < ge) {
+                    const int tc = gp / p.n_e, ec = gp - tc * p.n_e, s2 = gp & 1;
+                    if (mbar_test(bar_a2_full + 8 * s2, (uint32_t)(gp >> 1) & 1u) &&
+                        (ec != 0 || tc == 0 || mbar_test(bar_d2_empty, (uint32_t)(tc - 1) & 1u))) {   // previous tile's D2 was read
+                        ir_stamp(p, 1, tslot, 2);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint64_t da = umma_desc_sw128(smem_addr(sA2 + (size_t)s2 * 16384));
                         const uint64_t dbd = umma_desc_sw128(smem_addr(sWproj + (size_t)s2 * p.wproj_stage));
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             umma_f16(tmem_base + IR_D2_COL, da + (uint64_t)(k * 2), dbd + (uint64_t)(k * 2), p.idesc_proj,
-                                     (step > 1) || (k > 0));
+                                     (ec > 0) || (k > 0));
                         umma_commit(bar_a2_empty + 8 * s2);
-                        if (step == p.n_e) umma_commit(bar_d2_full);
+                        if (ec == p.n_e - 1) umma_commit(bar_d2_full);
+                        ++gp;
                     }
                 }
             }
         }
-    } else if (warp >= 2 + IR_MID_WARPS) {
+    } else if (warp >= 2 + IR_MID_WARPS && warp < 2 + IR_MID_WARPS + IR_DW_WARPS) {
         // ===================== depthwise 3x3 from the expanded patch =====================
         const int pt = (int)threadIdx.x - 32 * (2 + IR_MID_WARPS);
         const int j = pt & 7, rg = pt >> 3;                      // 16-byte channel chunk, row group (0..39)
         const int st = p.stride, pw = p.pw, php = p.ph;
-        const int box_rows = p.bw * p.bh * p.bb;
+        const int box_rows = min(p.bw * p.bh * p.bb, TC_BM);
         const int quad = p.quad;
-        int q0[IR_DW_ROWS];                                      // patch position of tap (0,0) per owned row; -1: padding row
+        // rows owned by this thread: rg + 40 i, or in quad mode the 4 horizontally adjacent pixels 4 rg + i
+        int q0[4];                                               // patch position of tap (0,0); 0 for rows that do not exist
+        int rrow[4];                                             // tile row, -1: does not exist
 #pragma unroll
-        for (int i = 0; i < IR_DW_ROWS; ++i) {
+        for (int i = 0; i < 4; ++i) {
             const int r = quad ? 4 * rg + i : rg + 4 * IR_DW_WARPS * i;
-            if (r < box_rows && r < TC_BM) {
+            if (r < box_rows) {
                 const int dx = r % p.bw, qq = r / p.bw, dy = qq % p.bh, db = qq / p.bh;
                 q0[i] = dx * st + pw * (dy * st + php * db);
+                rrow[i] = r;
             } else {
-                q0[i] = -1;
+                q0[i] = 0;
+                rrow[i] = -1;
             }
         }
         const __half2 lo2 = __float2half2_rn(p.dw_act == SSD_ACT_NONE ? -65504.0f : 0.0f);
         const __half2 hi2 = __float2half2_rn(p.dw_act == SSD_ACT_RELU6 ? 6.0f : 65504.0f);
-        int it = 0;
-        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const uint32_t sEp32 = smem_addr(sEp), sA232 = smem_addr(sA2), sBiasD32 = smem_addr(sBiasD);
+        const int R = p.dw_R;
+        int it = 0, tslot = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
             for (int e = 0; e < p.n_e; ++e, ++it) {
                 const int b = it & 1;
                 const uint32_t par = (uint32_t)(it >> 1) & 1u;
                 const bool cok = e * 64 + j * 8 < p.Cexp;
-                __half2 acc[IR_DW_ROWS][4];
+                __half2 bias4[4];
                 {
-                    const float4 b0 = *reinterpret_cast<const float4*>(sBiasD + e * 64 + j * 8);
-                    const float4 b1 = *reinterpret_cast<const float4*>(sBiasD + e * 64 + j * 8 + 4);
-                    const __half2 b4[4] = {__floats2half2_rn(b0.x, b0.y), __floats2half2_rn(b0.z, b0.w),
-                                           __floats2half2_rn(b1.x, b1.y), __floats2half2_rn(b1.z, b1.w)};
-#pragma unroll
-                    for (int i = 0; i < IR_DW_ROWS; ++i)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) acc[i][c] = b4[c];
+                    const float4 b0 = lds_f4(sBiasD32 + (uint32_t)(e * 64 + j * 8) * 4u);
+                    const float4 b1 = lds_f4(sBiasD32 + (uint32_t)(e * 64 + j * 8 + 4) * 4u);
+                    bias4[0] = __floats2half2_rn(b0.x, b0.y); bias4[1] = __floats2half2_rn(b0.z, b0.w);
+                    bias4[2] = __floats2half2_rn(b1.x, b1.y); bias4[3] = __floats2half2_rn(b1.z, b1.w);
                 }
                 mbar_wait(bar_ep_full + 8 * b, par);                                  // expanded patch + filter are there
-                const unsigned char* patch = sEp + (size_t)b * p.ep_stage;
-                const unsigned char* wsm = patch + p.ep_filter;
-                if (quad) {
-                    // sliding window: the 4 outputs of a thread share 6 input columns per filter row (18 loads, not 36)
-                    if (q0[0] >= 0) {
-#pragma unroll
-                        for (int ky = 0; ky < 3; ++ky) {
-                            uint4 w3[3];
-#pragma unroll
-                            for (int kx = 0; kx < 3; ++kx) {
-                                const int tap = ky * 3 + kx;
-                                w3[kx] = *reinterpret_cast<const uint4*>(wsm + tap * 128 + ((j ^ (tap & 7)) << 4));
-                            }
-#pragma unroll
-                            for (int c = 0; c < 6; ++c) {
-                                const int q = q0[0] + c + pw * ky;
-                                const uint4 xv = *reinterpret_cast<const uint4*>(patch + (size_t)q * 128 + ((j ^ (q & 7)) << 4));
-                                const __half2* xh = reinterpret_cast<const __half2*>(&xv);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const int kx = c - i;
-                                    if (kx >= 0 && kx < 3) {
-                                        const __half2* wh = reinterpret_cast<const __half2*>(&w3[kx]);
-#pragma unroll
-                                        for (int c2 = 0; c2 < 4; ++c2) acc[i][c2] = __hfma2(xh[c2], wh[c2], acc[i][c2]);
-                                    }
-                                }
-                            }
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const int tap = ky * 3 + kx;
-                            const uint4 wvv = *reinterpret_cast<const uint4*>(wsm + tap * 128 + ((j ^ (tap & 7)) << 4));
-                            const __half2* wh = reinterpret_cast<const __half2*>(&wvv);
-#pragma unroll
-                            for (int i = 0; i < IR_DW_ROWS; ++i) {
-                                if (q0[i] < 0) continue;
-                                const int q = q0[i] + kx + pw * ky;
-                                const uint4 xv = *reinterpret_cast<const uint4*>(patch + (size_t)q * 128 + ((j ^ (q & 7)) << 4));
-                                const __half2* xh = reinterpret_cast<const __half2*>(&xv);
-#pragma unroll
-                                for (int c2 = 0; c2 < 4; ++c2) acc[i][c2] = __hfma2(xh[c2], wh[c2], acc[i][c2]);
-                            }
-                        }
-                }
+                if (pt == 0) ir_stamp(p, 2, tslot, 1);
+                const uint32_t patch = sEp32 + (uint32_t)b * p.ep_stage;
+                const uint32_t wsm = patch + p.ep_filter;
+                // Arithmetic: packed half2 FMAs; the nine products of an output are summed in fp16 -- the storage format
+                // the result is rounded to for the tensor-core operand -- starting from the fp16-rounded bias.
+                __half2 acc[4][4];
+                if (quad)        ir_depthwise<4, true>(patch, wsm, j, pw, q0, bias4, acc);
+                else if (R == 1) ir_depthwise<1, false>(patch, wsm, j, pw, q0, bias4, acc);
+                else if (R == 2) ir_depthwise<2, false>(patch, wsm, j, pw, q0, bias4, acc);
+                else if (R == 3) ir_depthwise<3, false>(patch, wsm, j, pw, q0, bias4, acc);
+                else             ir_depthwise<4, false>(patch, wsm, j, pw, q0, bias4, acc);
+                if (pt == 0) ir_stamp(p, 2, tslot, 2);
                 if (it >= 2) mbar_wait(bar_a2_empty + 8 * b, par ^ 1u);                 // A2 slot drained by the projection MMA
-                unsigned char* a_tile = sA2 + (size_t)b * 16384;
+                const uint32_t a_tile = sA232 + (uint32_t)b * 16384u;
 #pragma unroll
-                for (int i = 0; i < IR_DW_ROWS; ++i) {
-                    const int r = quad ? 4 * rg + i : rg + 4 * IR_DW_WARPS * i;
-                    if (r >= TC_BM) continue;
-                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                    if (q0[i] >= 0 && cok) {
-                        __half2* oh = reinterpret_cast<__half2*>(&o);
+                for (int i = 0; i < 4; ++i) {
+                    if (i < (quad ? 4 : R) && rrow[i] >= 0) {
+                        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                        if (cok) {
+                            __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-                        for (int c2 = 0; c2 < 4; ++c2) oh[c2] = __hmin2(__hmax2(acc[i][c2], lo2), hi2);
+                            for (int c2 = 0; c2 < 4; ++c2) oh[c2] = __hmin2(__hmax2(acc[i][c2], lo2), hi2);
+                        }
+                        sts128(a_tile + sw_off(rrow[i], j), o);
                     }
-                    *reinterpret_cast<uint4*>(a_tile + r * 128 + ((j ^ (r & 7)) << 4)) = o;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic writes -> visible to the MMA / TMA
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(bar_a2_full + 8 * b); mbar_arrive(bar_ep_empty + 8 * b); }
+                if (pt == 0) ir_stamp(p, 2, tslot, 3);
             }
         }
-    } else {
-        // ===================== mid (D1 -> expanded patch) and final epilogue: warps 2..9 =====================
-        const int mw = warp - 2;
-        const int q = warp & 3;                                  // TMEM lane quarter this warp may read
-        const int half = mw >> 2;                                // mid: which 128-row half; epilogue: which 32-column half
-        const int r = q * 32 + lane;                             // row inside a 128-row accumulator
-        const int pos = half * 128 + r;                          // patch position handled in the mid stage
-        const bool pos_live = half < p.halves && pos < p.P;
-        const int px = pos % p.pw, prr = pos / p.pw, py = prr % p.ph, pdb = prr / p.ph;
-        const bool elected = mw == 0 && lane == 0;
-        const float e_lo = p.exp_act == SSD_ACT_NONE ? -__int_as_float(0x7f800000) : 0.0f;
-        const float e_hi = p.exp_act == SSD_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
+    } else if (warp >= 2 + IR_MID_WARPS + IR_DW_WARPS) {
+        // ===================== final epilogue: warps 20..23, one per TMEM lane quarter =====================
+        // D2 -> bias / residual -> fp16 -> swizzled staging tile -> TMA store; both 32-column halves of a 64-channel group
+        // are handled by the same thread.  Off the critical path: it only has to keep up with one tile per n_e slices.
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const bool elected = warp == 2 + IR_MID_WARPS + IR_DW_WARPS && lane == 0;
         const float act_lo = p.act == SSD_ACT_NONE ? -__int_as_float(0x7f800000) : 0.0f;
         const float act_hi = p.act == SSD_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
         const long long pix0 = p.Cout, img0 = (long long)p.Ho * p.Wo * p.Cout;
-        int it = 0, ti = 0;
+        const uint32_t sOut32 = smem_addr(sOut), sBiasP32 = smem_addr(sBiasP);
         uint32_t n_groups = 0;
-        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++ti) {
+        int tslot = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
             int b0, oy0, ox0;
-            ir_tile_origin(p, t, b0, oy0, ox0);
-            // inside the image?  positions outside are the depthwise convolution's zero padding
-            const int iy = oy0 * p.stride - p.pad_t + py, ix = ox0 * p.stride - p.pad_l + px;
-            const bool inside = pos_live && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W && b0 + pdb < p.B;
-            for (int e = 0; e < p.n_e; ++e, ++it) {
-                const int db = it & 1;
-                const uint32_t par = (uint32_t)(it >> 1) & 1u;
-                mbar_wait(bar_d1_full + 8 * db, par);
-                if (it >= 2) mbar_wait(bar_ep_empty + 8 * db, par ^ 1u);              // depthwise warps left this buffer
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                unsigned char* row = sEp + (size_t)db * p.ep_stage + (size_t)pos * 128;
-                const float* be = sBiasE + e * 64;
-                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)db * 128u + (uint32_t)half * 64u;
-#pragma unroll
-                for (int part = 0; part < 2; ++part) {           // 32 columns at a time (register budget: 640 threads)
-                    uint32_t acc[32];
-                    if (half < p.halves) {                       // warp-uniform
-                        tmem_ld32(trow + (uint32_t)part * 32u, acc);
-                        tmem_ld_wait(acc);
-                    }
-                    if (pos_live) {
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                            if (inside) {
-                                const float4 b0v = *reinterpret_cast<const float4*>(be + part * 32 + h * 8);
-                                const float4 b1v = *reinterpret_cast<const float4*>(be + part * 32 + h * 8 + 4);
-                                const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
-                                float v[8];
-#pragma unroll
-                                for (int c = 0; c < 8; ++c)
-                                    v[c] = fminf(fmaxf(__uint_as_float(acc[h * 8 + c]) + bb[c], e_lo), e_hi);
-                                __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                                for (int c = 0; c < 4; ++c) oh[c] = __floats2half2_rn(v[2 * c], v[2 * c + 1]);
-                            }
-                            *reinterpret_cast<uint4*>(row + (((part * 4 + h) ^ (pos & 7)) << 4)) = o;
-                        }
-                    }
-                }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) { mbar_arrive(bar_d1_empty + 8 * db); mbar_arrive(bar_ep_full + 8 * db); }
-            }
-            // ---- final epilogue of this tile: D2 -> bias / residual -> fp16 -> swizzled staging tile -> TMA store ----
-            mbar_wait(bar_d2_full, (uint32_t)ti & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            ir_tile_origin(p, (int)blockIdx.x + ti * (int)gridDim.x, b0, oy0, ox0);
             bool row_ok = false;
             long long row_off = 0;
             {
@@ -381,56 +427,123 @@ conv_irblock_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
                 row_ok = dbb < p.bb && b < p.B && oy < p.Ho && ox < p.Wo;
                 row_off = (long long)b * img0 + (long long)(oy * p.Wo + ox) * pix0;
             }
+            if (elected) ir_stamp(p, 4, tslot, 4);
+            mbar_wait(bar_d2_full, (uint32_t)ti & 1u);
+            if (elected) ir_stamp(p, 4, tslot, 5);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t trow2 = tmem_base + ((uint32_t)(q * 32) << 16) + IR_D2_COL;
             for (int g0 = 0; g0 < p.BN && g0 < p.Cout; g0 += 64, ++n_groups) {
-                unsigned char* buf = sOut + (size_t)(p.out_bufs == 2 ? (n_groups & 1u) : 0u) * TC_OUT_TILE;
-                const int c0 = g0 + half * TC_CHUNK;
-                const bool mine = c0 < p.BN && c0 < p.Cout;
-                uint32_t acc[TC_CHUNK];
-                if (mine) tmem_ld32(trow2 + (uint32_t)c0, acc);
+                const uint32_t buf = sOut32 + (p.out_bufs == 2 ? (n_groups & 1u) : 0u) * TC_OUT_TILE;
                 if (elected) { if (p.out_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
-                epi_barrier();
-                if (mine) {
-                    const int ncols = min(TC_CHUNK, p.Cout - c0);
-                    const float* sbias = sBiasP + c0;
-                    tmem_ld_wait(acc);
+                ir_epi_barrier();
 #pragma unroll
-                    for (int h = 0; h < TC_CHUNK / 8; ++h) {
-                        const float4 b0v = *reinterpret_cast<const float4*>(sbias + h * 8);
-                        const float4 b1v = *reinterpret_cast<const float4*>(sbias + h * 8 + 4);
-                        const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
-                        float v[8];
+                for (int half = 0; half < 2; ++half) {
+                    const int c0 = g0 + half * TC_CHUNK;
+                    if (c0 < p.BN && c0 < p.Cout) {               // warp-uniform
+                        uint32_t acc[TC_CHUNK];
+                        tmem_ld32(trow2 + (uint32_t)c0, acc);
+                        tmem_ld_wait(acc);
+                        const int ncols = min(TC_CHUNK, p.Cout - c0);
 #pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            v[c] = fminf(fmaxf(__uint_as_float(acc[h * 8 + c]) + bb[c], act_lo), act_hi);
-                        if (p.res && row_ok && h * 8 < ncols) {
-                            const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + row_off + c0 + h * 8));
-                            const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+                        for (int h = 0; h < TC_CHUNK / 8; ++h) {
+                            const float4 b0v = lds_f4(sBiasP32 + (uint32_t)(c0 + h * 8) * 4u);
+                            const float4 b1v = lds_f4(sBiasP32 + (uint32_t)(c0 + h * 8 + 4) * 4u);
+                            const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
+                            float v[8];
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                const float2 f = __half22float2(rh[c]);
-                                v[2 * c] += f.x; v[2 * c + 1] += f.y;
+                            for (int c = 0; c < 8; ++c)
+                                v[c] = fminf(fmaxf(__uint_as_float(acc[h * 8 + c]) + bb[c], act_lo), act_hi);
+                            if (p.res && row_ok && h * 8 < ncols) {
+                                const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + row_off + c0 + h * 8));
+                                const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) {
+                                    const float2 f = __half22float2(rh[c]);
+                                    v[2 * c] += f.x; v[2 * c + 1] += f.y;
+                                }
                             }
-                        }
-                        uint4 o;
-                        __half2* oh = reinterpret_cast<__half2*>(&o);
+                            uint4 o;
+                            __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) oh[c] = __floats2half2_rn(v[2 * c], v[2 * c + 1]);
-                        *reinterpret_cast<uint4*>(buf + r * 128 + (((half * 4 + h) ^ (r & 7)) << 4)) = o;
+                            for (int c = 0; c < 4; ++c) oh[c] = __floats2half2_rn(v[2 * c], v[2 * c + 1]);
+                            sts128(buf + sw_off(r, half * 4 + h), o);
+                        }
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                epi_barrier();
+                ir_epi_barrier();
                 if (elected) {
-                    tma_store_4d(&map_o, smem_addr(buf), g0, ox0, oy0, b0);
+                    tma_store_4d(&map_o, buf, g0, ox0, oy0, b0);
                     bulk_commit();
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_d2_empty);
+            if (elected) ir_stamp(p, 4, tslot, 6);
         }
         if (elected) bulk_wait_all();
+    } else {
+        // ===================== mid (D1 -> expanded patch): warps 2..9 =====================
+        const int mw = warp - 2;
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may read
+        const int half = mw >> 2;                                // which 128-row half of the patch
+        const int r = q * 32 + lane;                             // row inside a 128-row accumulator
+        const int pos = half * 128 + r;                          // patch position handled by this thread
+        const bool pos_live = half < p.halves && pos < p.P;
+        const int px = pos % p.pw, prr = pos / p.pw, py = prr % p.ph, pdb = prr / p.ph;
+        const float e_lo = p.exp_act == SSD_ACT_NONE ? -__int_as_float(0x7f800000) : 0.0f;
+        const float e_hi = p.exp_act == SSD_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
+        const uint32_t sEp32 = smem_addr(sEp), sBiasE32 = smem_addr(sBiasE);
+        int it = 0, tslot = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            int b0, oy0, ox0;
+            ir_tile_origin(p, (int)blockIdx.x + ti * (int)gridDim.x, b0, oy0, ox0);
+            // inside the image?  positions outside are the depthwise convolution's zero padding
+            const int iy = oy0 * p.stride - p.pad_t + py, ix = ox0 * p.stride - p.pad_l + px;
+            const bool inside = pos_live && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W && b0 + pdb < p.B;
+            for (int e = 0; e < p.n_e; ++e, ++it) {
+                const int db = it & 1;
+                const uint32_t par = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(bar_d1_full + 8 * db, par);
+                if (mw == 0 && lane == 0) ir_stamp(p, 3, tslot, 1);
+                if (it >= 2) mbar_wait(bar_ep_empty + 8 * db, par ^ 1u);              // depthwise warps left this buffer
+                if (mw == 0 && lane == 0) ir_stamp(p, 3, tslot, 2);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t row = sEp32 + (uint32_t)db * p.ep_stage;
+                const uint32_t be = sBiasE32 + (uint32_t)(e * 64) * 4u;
+                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)db * 128u + (uint32_t)half * 64u;
+                const uint32_t keep = inside ? 0xffffffffu : 0u;  // positions outside the image: zeros (depthwise padding)
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {           // 32 columns at a time (register budget: 640 threads)
+                    uint32_t acc[32];
+                    if (half < p.halves) {                       // warp-uniform
+                        tmem_ld32(trow + (uint32_t)part * 32u, acc);
+                        tmem_ld_wait(acc);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const float4 b0v = lds_f4(be + (uint32_t)(part * 32 + h * 8) * 4u);
+                        const float4 b1v = lds_f4(be + (uint32_t)(part * 32 + h * 8 + 4) * 4u);
+                        const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
+                        float v[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            v[c] = fminf(fmaxf(__uint_as_float(acc[h * 8 + c]) + bb[c], e_lo), e_hi);
+                        uint4 o;
+                        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) oh[c] = __floats2half2_rn(v[2 * c], v[2 * c + 1]);
+                        o.x &= keep; o.y &= keep; o.z &= keep; o.w &= keep;
+                        if (pos_live) sts128(row + sw_off(pos, part * 4 + h), o);
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(bar_d1_empty + 8 * db); mbar_arrive(bar_ep_full + 8 * db); }
+                if (mw == 0 && lane == 0) ir_stamp(p, 3, tslot, 3);
+            }
+        }
     }
     __syncthreads();
     if (warp == 1) {
@@ -473,12 +586,18 @@ static bool irblock_plan(const ssd_irblock_desc* d, IrParams* pp, size_t* smem_o
             // layout
             const uint32_t patch_chunk = up1k((size_t)P * 128);
             const uint32_t ep_rows = up1k((size_t)P * 128);
-            size_t fixed = (size_t)p.kc_in * patch_chunk + 2 * (size_t)(ep_rows + 2048) + 2 * 16384 + 2 * (size_t)p.wproj_stage +
-                           (size_t)(2 * p.n_e * 64 + 256) * 4 + 21 * 8 + 16;
-            int wst = 0, obufs = 0;
-            for (int ws_try = 2; ws_try >= 1 && !wst; --ws_try)
-                for (int ob = 2; ob >= 1; --ob)
-                    if (fixed + (size_t)ws_try * p.kc_in * 8192 + (size_t)ob * TC_OUT_TILE <= budget) { wst = ws_try; obufs = ob; break; }
+            size_t fixed = 2 * (size_t)(ep_rows + 2048) + 2 * 16384 + 2 * (size_t)p.wproj_stage +
+                           (size_t)(2 * p.n_e * 64 + 256) * 4 + 23 * 8 + 16;
+            // optional buffers, most valuable first: second weight-slice stage, second patch buffer, second staging tile
+            int wst = 0, obufs = 0, npatch = 0;
+            const int options[5][3] = {{2, 2, 2}, {2, 2, 1}, {2, 1, 1}, {1, 1, 1}, {0, 0, 0}};
+            for (int o = 0; options[o][0]; ++o) {
+                if (fixed + (size_t)options[o][1] * p.kc_in * patch_chunk + (size_t)options[o][0] * p.kc_in * 8192 +
+                        (size_t)options[o][2] * TC_OUT_TILE <= budget) {
+                    wst = options[o][0]; npatch = options[o][1]; obufs = options[o][2];
+                    break;
+                }
+            }
             if (!wst) continue;
             // cost model: waves of tiles x (depthwise rounds of the tile + fixed per-slice hand-off cost)
             const long long tiles = (long long)tw * th * tb;
@@ -494,12 +613,14 @@ static bool irblock_plan(const ssd_irblock_desc* d, IrParams* pp, size_t* smem_o
                 p.bw = bw; p.bh = bh; p.bb = bb; p.tiles_w = tw; p.tiles_h = th; p.n_tiles = (int)tiles;
                 p.pw = pw; p.ph = ph; p.P = P; p.halves = P > 128 ? 2 : 1;
                 p.quad = quad ? 1 : 0;
+                p.dw_R = quad ? 4 : max(1, (min(rows, TC_BM) + 4 * IR_DW_WARPS - 1) / (4 * IR_DW_WARPS));
                 p.patch_chunk = patch_chunk; p.patch_bytes = (uint32_t)P * 128u;
                 p.wexp_stages = wst; p.wexp_stage = (uint32_t)p.kc_in * 8192u;
                 p.ep_filter = ep_rows; p.ep_stage = ep_rows + 2048;
                 p.out_bufs = obufs;
+                p.n_patch = npatch;
                 uint32_t off = 0;
-                p.off_patch = off; off += (uint32_t)p.kc_in * patch_chunk;
+                p.off_patch = off; off += (uint32_t)npatch * (uint32_t)p.kc_in * patch_chunk;
                 p.off_wexp = off;  off += (uint32_t)wst * p.wexp_stage;
                 p.off_ep = off;    off += 2 * p.ep_stage;
                 p.off_a2 = off;    off += 2 * 16384;
@@ -507,7 +628,7 @@ static bool irblock_plan(const ssd_irblock_desc* d, IrParams* pp, size_t* smem_o
                 p.off_out = off;   off += (uint32_t)obufs * TC_OUT_TILE;
                 p.off_bias = off;  off += (uint32_t)(2 * p.n_e * 64 + 256) * 4;
                 off = (off + 7u) & ~7u;
-                p.off_bars = off;  off += 21 * 8 + 16;
+                p.off_bars = off;  off += 23 * 8 + 16;
                 *smem_out = (size_t)off + 1024;
             }
         }
@@ -527,9 +648,12 @@ bool conv_irblock_supported(const ssd_irblock_desc* d) {
     return irblock_plan(d, &p, &smem);
 }
 
+static unsigned long long* g_ir_trace = nullptr;
+
 int conv_irblock_launch(const ssd_irblock_desc* d, cudaStream_t st) {
     IrParams p;
     memset(&p, 0, sizeof(p));
+    p.trace = g_ir_trace;
     size_t smem = 0;
     if (!irblock_plan(d, &p, &smem)) return fail(SSD_ERR_UNSUPPORTED, "ssd_irblock: no tile geometry fits shared memory");
     p.B = d->B; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cexp = d->Cexp; p.Cout = d->Cout; p.Ho = d->Ho; p.Wo = d->Wo;
@@ -583,6 +707,10 @@ int conv_irblock_launch(const ssd_irblock_desc* d, cudaStream_t st) {
         if (e != cudaSuccess) return cuda_fail(e, "ssd_irblock: cudaFuncSetAttribute");
         attr_dev = cur_dev;
     }
+    if (p.trace)
+        fprintf(stderr, "ssd_irblock: box %dx%dx%d patch %dx%d P=%d halves=%d tiles=%d n_e=%d kc_in=%d wexp_stages=%d n_patch=%d "
+                "out_bufs=%d quad=%d smem=%zu\n", p.bw, p.bh, p.bb, p.pw, p.ph, p.P, p.halves, p.n_tiles, p.n_e, p.kc_in,
+                p.wexp_stages, p.n_patch, p.out_bufs, p.quad, smem);
     dim3 grid(min(p.n_tiles, sm_count()), 1, 1);
     cudaError_t le = launch_pdl(conv_irblock_tcgen05_kernel, grid, dim3(IR_THREADS), smem, st, map_x, map_we, map_dw, map_wp, map_o, p);
     if (le != cudaSuccess) return cuda_fail(le, "conv_irblock_tcgen05_kernel");
@@ -604,6 +732,14 @@ extern "C" int ssd_irblock(const ssd_irblock_desc* d, ssd_stream_t stream) {
                 "ssd_irblock: unsupported configuration (channels %% 8, Cin <= 256, Cexp <= 1024, Cout <= 256, stride 1|2, "
                 "16-byte aligned pointers)");
     return ssd::conv_irblock_launch(d, ssd::as_stream(stream));
+}
+
+// Debug only (not part of the reference-facing ABI): a device buffer of 5 x 512 uint64 that CTA 0 of every later
+// ssd_irblock launch fills with (globaltimer << 8 | tag) stamps per role; NULL switches tracing off.  With a non-NULL
+// buffer the call also prints the tile geometry the planner chose.
+extern "C" int ssd_irblock_trace(void* d_buf) {
+    ssd::g_ir_trace = static_cast<unsigned long long*>(d_buf);
+    return SSD_OK;
 }
 
 extern "C" int ssd_irblock_supported(const ssd_irblock_desc* d) {
