@@ -375,6 +375,49 @@ def _box_kernel_rooflines(peaks, hp, iters=10, warmup=3):
     return {"shape": {"B": B, "N": N, "G": G, "L": L}, "peak_gbs": peaks["hbm_gbs"], "kernels": out}
 
 
+def _other_inference_configs(steps=10, warmup=3):
+    """Device-resident inference (forward + softmax + decode + NMS, one CUDA graph, uint8 input) of the other BASELINE
+    configurations: configs[2]'s network in inference (SSD300-VGG16, 32 images per GPU) and configs[4] (SSD512-VGG16,
+    128 images over 8 GPUs = 16 per GPU, 24 564 anchors; the SSD512 graph is an extension).  Every
+    rank runs its own shard (no collective); times are the slowest rank's."""
+    import torch
+    from tf_ssd_b200 import dist_utils
+    from tf_ssd_b200.models import ssd_vgg16
+    from tf_ssd_b200.models.decoder import get_decoder_model
+    from tf_ssd_b200.utils import bbox_utils, train_utils
+    rank, local_rank, world = dist_utils.env_rank()
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for backbone, batch, key in (("vgg16", 32, "ssd300_vgg16_b32_per_gpu_inference"),
+                                 ("vgg16_512", 16, "ssd512_vgg16_b16_per_gpu_inference")):
+        hp = train_utils.get_hyper_params(backbone)
+        hp["total_labels"] = 21
+        model = ssd_vgg16.get_model(hp, seed=1234)
+        priors = bbox_utils.generate_prior_boxes(hp["feature_map_shapes"], hp["aspect_ratios"])
+        dm = get_decoder_model(model, priors, hp)
+        st = dm._prepare(batch, 0)
+        st["plan"].image_u8.copy_(torch.from_numpy(_make_images_u8(batch, hp["img_size"], seed=300 + rank)))
+        for _ in range(warmup):
+            dm.run_resident(batch, 0, u8=True)
+        dist_utils.barrier()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in evs:
+            flush.zero_()
+            a.record(); dm.run_resident(batch, 0, u8=True); b.record()
+        dist_utils.barrier()
+        torch.cuda.synchronize()
+        ms = dist_utils.max_over_ranks(float(sum(a.elapsed_time(b) for a, b in evs)), st["plan"].device) / steps
+        flops = 2.0 * model.macs_per_image * batch
+        out[key] = {"workload": f"{backbone} batch={batch}/GPU inference fwd+softmax+decode+NMS, {model.n_anchors} anchors, "
+                                "uint8 input resident, random-init weights (uncalibrated: every anchor scores ~1/21)",
+                    "value": world * batch / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "steps": steps,
+                    "conv_tflops_per_gpu": flops / (ms * 1e-3) / 1e12, "launches": dm.launches_per_batch(batch)}
+        del dm, model, st
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -383,6 +426,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU restatement)")
     torch.cuda.set_device(local_rank)
+    numa_bound = dist_utils.bind_to_gpu_numa(local_rank)      # pinned staging buffers on the GPU's NUMA node
     dist_utils.init_from_env("nccl")
 
     from tf_ssd_b200 import _ffi, synth
@@ -472,6 +516,15 @@ def run_b200(args):
                 training[key] = train_bench.measure(steps=args.train_steps, warmup=3, batch=32)
             torch.cuda.empty_cache()
 
+    other = None
+    if not args.skip_other:
+        try:
+            other = _other_inference_configs()
+        except Exception as exc:  # noqa: BLE001
+            if world > 1:
+                raise
+            other = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     if rank == 0:
         total_images = world * B * K
         value = total_images / (dev_ms / 1e3)
@@ -481,7 +534,7 @@ def run_b200(args):
             "dtype": "f16", "data": "synthetic",
             "config": _config(world),
             "workload_check": {"nms_candidates_per_image": round(cand, 1), "valid_detections_mean": float(valid.mean()),
-                               "images_per_step": B, "peaks": peaks["source"]},
+                               "images_per_step": B, "peaks": peaks["source"], "numa_bound": numa_bound},
             "clocks": clocks,
             "e2e": {"value": total_images / (e2e_ms / 1e3), "unit": UNIT,
                     "h2d_bytes_per_step": int(B * S * S * 3), "d2h_bytes_per_step": int(B * 200 * 6 * 4),
@@ -490,6 +543,8 @@ def run_b200(args):
         }
         if training is not None:
             line["training"] = training
+        if other is not None:
+            line["other_configs"] = other
         if world == 1:
             per = _profile_steps(dm, B)
             steps = plan.steps
@@ -512,7 +567,8 @@ def run_b200(args):
                 ach = g["bytes"] / (g["ms"] * 1e-3) / 1e9
                 roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]}
             roof.update({"traffic": _ncu_traffic(top, g["launches"]), "algorithmic_bytes_per_launch": g["bytes"] / max(g["launches"], 1), "kernel": {"conv": "ssd_conv2d launches: conv_tcgen05_kernel (+ conv_splitk_reduce_kernel for the multibox heads)",
-                                                     "dw": "depthwise3x3_kernel", "dwproj": "conv_dwproj_tcgen05_kernel (fused depthwise 3x3 -> 1x1 projection)", "decode_nms": "nms_candidates+nms_image"}.get(top, top),
+                                                     "irblock": "conv_irblock_tcgen05_kernel (whole inverted-residual block: 1x1 expand -> depthwise 3x3 -> 1x1 project)",
+                         "dw": "depthwise3x3_kernel", "dwproj": "conv_dwproj_tcgen05_kernel (fused depthwise 3x3 -> 1x1 projection)", "decode_nms": "nms_candidates+nms_image"}.get(top, top),
                          "launches_per_step": g["launches"], "ms_per_step": g["ms"], "share_of_step": g["ms"] / total,
                          "algorithmic_bytes_per_step": g["bytes"], "flops_per_step": g["flops"], "peak_source": peaks["source"],
                          "by_kind_ms": {k: round(v["ms"], 4) for k, v in groups.items()}})
@@ -556,6 +612,7 @@ def main():
                     help="warm up, run ONE eager step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     ap.add_argument("--skip-train", action="store_true", help="omit the training-step measurements (configs[2], configs[3])")
     ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--skip-other", action="store_true", help="omit the VGG16 / SSD512 inference side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

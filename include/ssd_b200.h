@@ -344,6 +344,13 @@ typedef struct ssd_adam_var {
 } ssd_adam_var;
 int ssd_adam_step_multi(const ssd_adam_var* d_vars, int n_vars, int64_t max_n, float lr_t, float beta1, float beta2,
                         float eps, float inv_scale, float* d_sumsq, ssd_stream_t stream);
+/* Mixed-precision guard (no counterpart in the reference, which trains in fp32 -- trainer.py:91-94): activation gradients
+ * are fp16 and loss-scaled, so one overflow would feed Inf / NaN into every variable.  ssd_grad_nonfinite_multi sets
+ * d_flag[0] = 1 when any gradient of the table is non-finite (0 otherwise); the guarded Adam skips the whole update when
+ * d_guard[0] != 0 and counts the skipped step in d_guard[1] (d_guard = int[2]; NULL = plain ssd_adam_step_multi). */
+int ssd_grad_nonfinite_multi(const ssd_adam_var* d_vars, int n_vars, int64_t max_n, int* d_flag, ssd_stream_t stream);
+int ssd_adam_step_multi_guarded(const ssd_adam_var* d_vars, int n_vars, int64_t max_n, float lr_t, float beta1, float beta2,
+                                float eps, float inv_scale, float* d_sumsq, int* d_guard, ssd_stream_t stream);
 
 /* ---- MobileNetV2 training (keras_applications MobileNetV2 under models/ssd_mobilenet_v2.py:25) ----
  * keras.layers.BatchNormalization(epsilon=1e-3, momentum=0.999) in TRAINING mode over the rows of an

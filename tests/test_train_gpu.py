@@ -580,3 +580,79 @@ def test_load_weights_after_compile_reaches_the_trainer(setup):
     model.trainer.sync_weights_to_host()
     assert not np.array_equal(model.weights[key], saved[key])
 
+
+
+def test_guarded_adam_skips_nonfinite_steps_and_loss_scale_controller():
+    """One Inf in any gradient: the device-side guard leaves every variable, moment and fp16 copy untouched and counts
+    the skipped step; the host controller then halves the loss scale (and doubles it after enough clean steps)."""
+    from tf_ssd_b200.models.train_engine import Trainer
+    model, hp, img, ad, al = _vgg_setup(1)
+    tr = Trainer(model, loss_scale=512.0, scale_check_every=10 ** 9, scale_growth_interval=2)
+    tr.forward_backward(img, ad, al)
+    name = "conv4_3/kernel"
+    before = {k: (v["master"].clone(), v["m"].clone(), None if v["w16"] is None else v["w16"].clone()) for k, v in tr.vars.items()}
+    tr.vars[name]["grad"].view(-1)[123] = float("inf")
+    tr.apply_gradients()
+    torch.cuda.synchronize()
+    assert tr._guard.tolist() == [1, 1]
+    for k, v in tr.vars.items():
+        assert torch.equal(v["master"], before[k][0]) and torch.equal(v["m"], before[k][1]), k
+        if v["w16"] is not None:
+            assert torch.equal(v["w16"], before[k][2]), k
+    assert tr.update_loss_scale() == 256.0 and tr.skipped_steps == 1 and tr.t == 0
+    assert all(st["graphs"] is None for st in tr._state.values())          # captured graphs carry the old scale
+    # clean steps: weights move, no skip; after scale_growth_interval clean steps the scale doubles
+    for _ in range(2):
+        tr.forward_backward(img, ad, al)
+        tr.apply_gradients()
+    torch.cuda.synchronize()
+    assert tr._guard.tolist() == [0, 0]
+    assert not torch.equal(tr.vars[name]["master"], before[name][0])
+    assert all(bool(torch.isfinite(v["master"]).all()) for v in tr.vars.values())
+    assert tr.update_loss_scale() == 512.0
+    # NaN is caught as well; a tail element (n % 4 != 0 case is covered by the bias vectors of 21 * A channels)
+    tr.forward_backward(img, ad, al)
+    tr.vars["1_conv_head/bias"]["grad"].view(-1)[-1] = float("nan")
+    tr.apply_gradients()
+    torch.cuda.synchronize()
+    assert tr._guard.tolist()[0] == 1
+
+
+def test_trainer_owned_weights_survive_a_host_sync_for_new_batch_sizes():
+    """MobileNetV2: layers without BatchNorm (extras, heads) keep their weights in the model's packed cache.  After a
+    validation / checkpoint sync (which clears that cache to re-fold BatchNorm) a training plan built for ANOTHER batch
+    size must still point at the tensors Adam updates -- not at fresh uploads of stale host copies."""
+    from tf_ssd_b200.models.train_engine import Trainer
+    model, hp, img, ad, al = _mnv2_setup(3)
+    tr = Trainer(model)
+    tr.forward_backward(img[:2], ad[:2], al[:2])
+    tr.apply_gradients()
+    tr.sync_weights_to_host()                               # what ModelCheckpoint / validation do
+    st = tr._prepare(3)                                     # a plan for a batch size that did not exist before the sync
+    for s in st["plan"].steps:
+        if s.kind == "conv" and s.name + "/kernel" in tr.vars:
+            assert s.meta["w"] is tr.vars[s.name + "/kernel"]["w16"], s.name
+            if s.meta["bias"] is not None:
+                assert s.meta["bias"] is tr.vars[s.name + "/bias"]["master"], s.name
+    w_before = tr.vars["extra2_2/kernel"]["w16"].clone()
+    tr.forward_backward(img, ad, al)
+    tr.apply_gradients()
+    torch.cuda.synchronize()
+    plan_w = next(s.meta["w"] for s in st["plan"].steps if s.name == "extra2_2")
+    assert not torch.equal(plan_w, w_before)                # the weights the B=3 plan computes with DID move
+
+
+def test_fit_runs_without_per_step_host_sync_and_accepts_uint8_images():
+    from tf_ssd_b200.models.train_engine import Adam
+    from tf_ssd_b200.ssd_loss import CustomLoss
+    model, hp, img, ad, al = _vgg_setup(2)
+    loss = CustomLoss(3, 1)
+    model.compile(optimizer=Adam(learning_rate=1e-4), loss=[loss.loc_loss_fn, loss.conf_loss_fn], loss_scale=256.0)
+    assert model.trainer.loss_scale == 256.0
+    u8 = (img * 255).astype(np.uint8)
+
+    def gen():
+        while True:
+            yield u8, (ad, al)
+    hist = model.fit(gen(), steps_per_epoch=3, epochs=2)
+    assert len(hist["loss"]) == 2 and np.isfinite(hist["loss"]).all() and hist["loss"][1] < hist["loss"][0]

@@ -76,6 +76,8 @@ SIGNATURES = {
     "ssd_head_grad_gather": (i, [vp, vp, vp, i, i, i, i, i, i, i, vp]),
     "ssd_adam_step": (i, [vp, vp, vp, vp, vp, i64, f, f, f, f, f, f, vp, vp]),
     "ssd_adam_step_multi": (i, [vp, i, i64, f, f, f, f, f, vp, vp]),
+    "ssd_grad_nonfinite_multi": (i, [vp, i, i64, vp, vp]),
+    "ssd_adam_step_multi_guarded": (i, [vp, i, i64, f, f, f, f, f, vp, vp, vp]),
     "ssd_bn_workspace_bytes": (C.c_size_t, [i]),
     "ssd_bn_train_fwd": (i, [vp, vp, vp, vp, vp, i64, i, f, f, i, vp, vp, vp, vp, C.c_size_t, vp]),
     "ssd_bn_train_bwd": (i, [vp, vp, vp, vp, vp, i64, i, i, vp, vp, i, vp, vp, vp, C.c_size_t, vp]),

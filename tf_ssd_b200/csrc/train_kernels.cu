@@ -399,9 +399,16 @@ adam_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
 
 // Multi-tensor variant: one launch updates every variable of the model.  blockIdx.y selects the descriptor,
 // blockIdx.x strides over its elements (descriptors shorter than the grid simply finish early).
+// ``guard`` (may be NULL): guard[0] != 0 means this step's gradients hold a non-finite value (fp16 overflow of a
+// loss-scaled activation gradient): the whole update is skipped -- weights, moments and the fp16 copies stay as they
+// are -- and guard[1] counts the skipped steps for the host's loss-scale controller.
 __global__ void __launch_bounds__(256)
 adam_multi_kernel(const ssd_adam_var* __restrict__ vars, float lr_t, float b1, float b2, float eps, float inv_scale,
-                  float* __restrict__ sumsq) {
+                  float* __restrict__ sumsq, int* __restrict__ guard) {
+    if (guard && guard[0] != 0) {
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(guard + 1, 1);
+        return;
+    }
     const ssd_adam_var d = vars[blockIdx.y];
     float* __restrict__ w = d.w; float* __restrict__ m = d.m; float* __restrict__ v = d.v;
     const float* __restrict__ g = d.grad;
@@ -421,6 +428,27 @@ adam_multi_kernel(const ssd_adam_var* __restrict__ vars, float lr_t, float b1, f
         local = warp_sum(local);
         if ((threadIdx.x & 31) == 0 && local != 0.0f) atomicAdd(sumsq, local);
     }
+}
+
+// Any non-finite gradient among all variables -> flag[0] = 1 (the caller zeroes it first).
+__global__ void __launch_bounds__(256)
+grad_nonfinite_kernel(const ssd_adam_var* __restrict__ vars, int* __restrict__ flag) {
+    const ssd_adam_var d = vars[blockIdx.y];
+    const float* __restrict__ g = d.grad;
+    bool bad = false;
+    const int64_t n4 = d.n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);          // gradient views start on 16-byte boundaries
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = g4[i];
+        // x - x is 0 for finite x and NaN for +-inf / NaN
+        const float t = (v.x - v.x) + (v.y - v.y) + (v.z - v.z) + (v.w - v.w);
+        bad |= !(t == 0.0f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(d.n & 3)) {
+        const float x = g[(n4 << 2) + threadIdx.x];
+        bad |= !((x - x) == 0.0f);
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
 // conv_tcgen05.cu
@@ -578,6 +606,39 @@ extern "C" int ssd_adam_step(float* d_w, float* d_m, float* d_v, const float* d_
     return SSD_OK;
 }
 
+static int adam_multi_grid(int n_vars, int64_t max_n) {
+    // enough CTAs per variable that the largest one (a few million elements) still spreads over the device
+    int64_t bx = (max_n + 256 * 8 - 1) / (256 * 8);
+    const int64_t cap = max((int64_t)1, (int64_t)sm_count() * 16 / n_vars + 1);
+    if (bx > cap) bx = cap;
+    return (int)(bx < 1 ? 1 : bx);
+}
+
+extern "C" int ssd_grad_nonfinite_multi(const ssd_adam_var* d_vars, int n_vars, int64_t max_n, int* d_flag, ssd_stream_t stream) {
+    SSD_REQUIRE_PTR(d_vars); SSD_REQUIRE_PTR(d_flag);
+    SSD_REQUIRE(n_vars >= 0 && n_vars <= 65535 && max_n >= 0, SSD_ERR_SHAPE, "ssd_grad_nonfinite_multi: n_vars=%d max_n=%lld",
+                n_vars, (long long)max_n);
+    cudaError_t e = cudaMemsetAsync(d_flag, 0, sizeof(int), as_stream(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "ssd_grad_nonfinite_multi: memset");
+    if (n_vars == 0 || max_n == 0) return SSD_OK;
+    grad_nonfinite_kernel<<<dim3((unsigned)adam_multi_grid(n_vars, max_n), (unsigned)n_vars), 256, 0, as_stream(stream)>>>(d_vars, d_flag);
+    SSD_CHECK_LAUNCH("grad_nonfinite_kernel");
+    return SSD_OK;
+}
+
+extern "C" int ssd_adam_step_multi_guarded(const ssd_adam_var* d_vars, int n_vars, int64_t max_n, float lr_t, float beta1,
+                                           float beta2, float eps, float inv_scale, float* d_sumsq, int* d_guard,
+                                           ssd_stream_t stream) {
+    SSD_REQUIRE_PTR(d_vars);
+    SSD_REQUIRE(n_vars >= 0 && n_vars <= 65535 && max_n >= 0, SSD_ERR_SHAPE, "ssd_adam_step_multi_guarded: n_vars=%d max_n=%lld",
+                n_vars, (long long)max_n);
+    if (n_vars == 0 || max_n == 0) return SSD_OK;
+    adam_multi_kernel<<<dim3((unsigned)adam_multi_grid(n_vars, max_n), (unsigned)n_vars), 256, 0, as_stream(stream)>>>(
+        d_vars, lr_t, beta1, beta2, eps, inv_scale, d_sumsq, d_guard);
+    SSD_CHECK_LAUNCH("adam_multi_kernel");
+    return SSD_OK;
+}
+
 extern "C" int ssd_adam_step_multi(const ssd_adam_var* d_vars, int n_vars, int64_t max_n, float lr_t, float beta1, float beta2,
                                    float eps, float inv_scale, float* d_sumsq, ssd_stream_t stream) {
     SSD_REQUIRE_PTR(d_vars);
@@ -590,7 +651,7 @@ extern "C" int ssd_adam_step_multi(const ssd_adam_var* d_vars, int n_vars, int64
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     adam_multi_kernel<<<dim3((unsigned)bx, (unsigned)n_vars), 256, 0, as_stream(stream)>>>(d_vars, lr_t, beta1, beta2, eps,
-                                                                                          inv_scale, d_sumsq);
+                                                                                          inv_scale, d_sumsq, nullptr);
     SSD_CHECK_LAUNCH("adam_multi_kernel");
     return SSD_OK;
 }

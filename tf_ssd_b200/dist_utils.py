@@ -49,6 +49,36 @@ def max_over_ranks(value: float, device: torch.device) -> float:
     return float(t.item())
 
 
+def world_size() -> int:
+    return dist.get_world_size() if dist.is_initialized() else 1
+
+
+class _Done(object):
+    def wait(self) -> None:
+        return None
+
+
+def bind_to_gpu_numa(local_rank: int) -> bool:
+    """Pin the calling process to the CPUs NVML reports as closest to GPU ``local_rank`` so that pinned staging
+    buffers are first-touched on that GPU's NUMA node (8 ranks streaming images from one node's memory are
+    host-bandwidth bound).  Best effort: returns False when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(vis.split(",")[local_rank]) if vis else local_rank
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = [64 * i + b for i, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:  # noqa: BLE001
+        return False
+
+
 def barrier() -> None:
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
@@ -63,6 +93,7 @@ class GradBuckets(object):
 
     def __init__(self, shapes: Sequence[Tuple[str, Sequence[int]]], device: torch.device, bucket_bytes: int = 16 << 20):
         self.views = {}
+        self.bucket_of = {}                               # variable name -> index of its bucket
         self.buckets: List[torch.Tensor] = []
         cur: List[Tuple[str, Sequence[int], int]] = []
         cur_elems = 0
@@ -76,6 +107,7 @@ class GradBuckets(object):
             off = 0
             for name, shape, n in cur:
                 self.views[name] = buf[off:off + n].view(*shape)
+                self.bucket_of[name] = len(self.buckets)
                 off += (n + 3) // 4 * 4                    # every view starts on a 16-byte boundary
             self.buckets.append(buf)
             cur, cur_elems = [], 0
@@ -94,6 +126,14 @@ class GradBuckets(object):
     def zero_(self) -> None:
         for b in self.buckets:
             b.zero_()
+
+    def allreduce_sum_async(self, k: int):
+        """Starts the SUM all-reduce of bucket ``k`` (NCCL runs it on its own stream behind everything enqueued on the
+        current stream so far) and returns a handle whose ``wait()`` makes the current stream wait for it.  The 1 / world
+        of the mean is the consumer's business (the fused optimizer folds it into its gradient scale)."""
+        if not (dist.is_initialized() and dist.get_world_size() > 1):
+            return _Done()
+        return dist.all_reduce(self.buckets[k], op=dist.ReduceOp.SUM, async_op=True)
 
     def allreduce_mean_(self) -> None:
         """Sum over ranks then divide by the world size (Keras' batch mean over the global batch when

@@ -630,11 +630,12 @@ class SSDModel(object):
 
     # -- weights ---------------------------------------------------------------
     def set_weights(self, weights: Dict[str, np.ndarray]) -> None:
-        for k, v in weights.items():
+        for k, v in weights.items():                     # validate everything before touching any state
             if k not in self.weights:
                 raise KeyError(f"unknown variable {k!r}")
             if tuple(v.shape) != tuple(self.weights[k].shape):
                 raise ValueError(f"{k}: shape {v.shape} != {self.weights[k].shape}")
+        for k, v in weights.items():
             self.weights[k] = np.ascontiguousarray(v, dtype=np.float32)
         # ``load_weights`` after ``compile`` (trainer.py:91-99 loads AFTER compiling): the trainer's device-side
         # variables are rebuilt from the new host values (optimizer moments restart at zero)
@@ -807,9 +808,11 @@ class SSDModel(object):
         owner = getattr(loss[0], "__self__", None) if loss else None
         ratio = float(getattr(owner, "neg_pos_ratio", 3.0))
         alpha = float(getattr(owner, "loc_loss_alpha", 1.0))
+        extra = {k: kwargs[k] for k in ("loss_scale", "dynamic_loss_scale", "scale_check_every", "scale_growth_interval",
+                                        "use_cuda_graph") if k in kwargs}      # mixed-precision knobs (no Keras counterpart)
         self.trainer = Trainer(self, learning_rate=lr, neg_pos_ratio=ratio, loc_loss_alpha=alpha,
                                beta_1=float(getattr(optimizer, "beta_1", 0.9)), beta_2=float(getattr(optimizer, "beta_2", 0.999)),
-                               epsilon=float(getattr(optimizer, "epsilon", 1e-7)))
+                               epsilon=float(getattr(optimizer, "epsilon", 1e-7)), **extra)
 
     def train_on_batch(self, x: Any, y: Tuple[Any, Any], learning_rate: Optional[float] = None) -> Dict[str, float]:
         if getattr(self, "trainer", None) is None:
@@ -838,12 +841,15 @@ class SSDModel(object):
                 r = hook(epoch, {}) if hook else None
                 if isinstance(r, float):
                     lr = r
-            tot, n = 0.0, 0
+            tot, n = None, 0                             # the running loss stays on the device: one read per epoch
             for _ in range(steps_per_epoch or 1):
                 img, targets = next(it)
-                tot += self.trainer.train_on_batch(img, targets, lr)["loss"]
+                step_loss = self.trainer.train_step(img, targets, lr)
+                tot = step_loss if tot is None else tot + step_loss
                 n += 1
-            logs = {"loss": tot / max(n, 1)}
+            logs = {"loss": float(tot) / max(n, 1) if tot is not None else 0.0}
+            if self.trainer.dynamic_loss_scale:
+                self.trainer.update_loss_scale()
             if verbose:
                 print(f"Epoch {epoch + 1}/{epochs} - loss: {logs['loss']:.4f}", flush=True)
             if vit is not None:

@@ -86,11 +86,21 @@ class Trainer(object):
 
     def __init__(self, model: SSDModel, learning_rate: float = 1e-3, neg_pos_ratio: float = 3.0, loc_loss_alpha: float = 1.0,
                  beta_1: float = 0.9, beta_2: float = 0.999, epsilon: float = 1e-7, loss_scale: float = 1024.0,
-                 use_cuda_graph: bool = True):
+                 use_cuda_graph: bool = True, dynamic_loss_scale: bool = True, scale_check_every: int = 100,
+                 scale_growth_interval: int = 2000):
         _ffi.check_device()
         self.init_kwargs = dict(learning_rate=learning_rate, neg_pos_ratio=neg_pos_ratio, loc_loss_alpha=loc_loss_alpha,
                                 beta_1=beta_1, beta_2=beta_2, epsilon=epsilon, loss_scale=loss_scale,
-                                use_cuda_graph=use_cuda_graph)
+                                use_cuda_graph=use_cuda_graph, dynamic_loss_scale=dynamic_loss_scale,
+                                scale_check_every=scale_check_every, scale_growth_interval=scale_growth_interval)
+        # Mixed-precision guard: a step whose gradients hold a non-finite value is SKIPPED on the device (guarded Adam);
+        # the host looks at the skip counter every ``scale_check_every`` steps (one synchronisation) and halves the loss
+        # scale after an overflow / doubles it after ``scale_growth_interval`` clean steps (re-capturing the step graph).
+        self.dynamic_loss_scale = bool(dynamic_loss_scale)
+        self.scale_check_every, self.scale_growth_interval = int(scale_check_every), int(scale_growth_interval)
+        self._since_check = self._clean_steps = 0
+        self.skipped_steps = 0
+        self._pending: List[Any] = []                # in-flight gradient all-reduces of the current step
         self.model = model
         model.trainer = self                         # the model's training-mode variables now belong to this trainer
         self.use_cuda_graph = bool(use_cuda_graph)
@@ -140,6 +150,12 @@ class Trainer(object):
             v["m"] = torch.zeros_like(v["master"])
             v["v"] = torch.zeros_like(v["master"])
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self._guard = torch.zeros(2, dtype=torch.int32, device=self.dev)     # [overflow of this step, skipped steps]
+        # weights of layers WITHOUT BatchNorm live in the model's packed cache and are updated in place by Adam: they
+        # must survive the cache being cleared (sync_weights_to_host), or a plan built later for another batch size would
+        # re-upload stale host copies that Adam never touches
+        self._owned_packed = {k: v for k, v in m._packed.items()
+                              if any(v[0] is s.meta.get("w") or v[0] is s.meta.get("scale") for s in plan.steps if s.meta)}
         # descriptor table of the multi-tensor Adam launch (device array of struct ssd_adam_var)
         from tf_ssd_b200._ffi_conv import AdamVar
         table = (AdamVar * len(self.vars))()
@@ -180,6 +196,7 @@ class Trainer(object):
                 if key.endswith("/moving_mean") or key.endswith("/moving_variance"):
                     m.weights[key] = t.detach().cpu().numpy().copy()
             m._packed.clear()                        # inference plans fold BatchNorm: rebuild them from the new values
+            m._packed.update(self._owned_packed)     # ... except the trainer-owned (BatchNorm-free) layers: same tensors
             m._plans.clear()
             m._version = getattr(m, "_version", 0) + 1
             self._eval_dirty = False
@@ -199,7 +216,6 @@ class Trainer(object):
         st["ws"] = _ffi.workspace(lib.ssd_loss_workspace_bytes(B, N, L))
         st["ad"] = torch.zeros((B, N, 4), dtype=torch.float32, device=dev)      # static target buffers (graph inputs)
         st["al"] = torch.zeros((B, N, L), dtype=torch.float32, device=dev)
-        st["graph"] = None
         keep: List[Any] = []
         launches: List[Tuple[Any, tuple, str]] = []
         grad_of: Dict[int, torch.Tensor] = {}       # activation data_ptr -> fp16 gradient buffer
@@ -211,8 +227,12 @@ class Trainer(object):
                 written[t.data_ptr()] = False
             return grad_of[t.data_ptr()]
 
-        def add(fn, args, what):
+        def add(fn, args, what, writes=()):
             launches.append((fn, args, what))
+            for name in writes:                          # last launch that writes each variable's gradient
+                last_writer[name] = len(launches) - 1
+
+        last_writer: Dict[str, int] = {}
 
         first_conv_input = None
         for s in plan.steps:
@@ -247,10 +267,10 @@ class Trainer(object):
                 d.stride, d.dilation, d.pad_top, d.pad_left = stride, dil, mt["ph"][0], mt["pw"][0]
                 keep.append(d)
                 add(lib.ssd_conv2d_wgrad, (C.byref(d), _ffi.ptr(dy), ldy, _ffi.ptr(self.vars[s.name + "/kernel"]["grad"])),
-                    s.name + ":wgrad")
+                    s.name + ":wgrad", writes=(s.name + "/kernel",))
                 if s.name + "/bias" in self.vars:
                     add(lib.ssd_bias_grad, (_ffi.ptr(dy), _ffi.ptr(self.vars[s.name + "/bias"]["grad"]), B * Ho * Wo, ldy, cout),
-                        s.name + ":bgrad")
+                        s.name + ":bgrad", writes=(s.name + "/bias",))
                 # data gradient (not needed for the layer fed by the image)
                 if x.data_ptr() == first_conv_input:
                     continue
@@ -291,7 +311,7 @@ class Trainer(object):
                                            _ffi.ptr(mt["save"]), mt["M"], mt["C"], mt["act"], _ffi.ptr(dx), _ffi.ptr(dres),
                                            acc_res, _ffi.ptr(self.vars[s.name + "/gamma"]["grad"]),
                                            _ffi.ptr(self.vars[s.name + "/beta"]["grad"]), _ffi.ptr(mt["ws"]),
-                                           mt["ws"].numel()), s.name + ":bn")
+                                           mt["ws"].numel()), s.name + ":bn", writes=(s.name + "/gamma", s.name + "/beta"))
                 written[x.data_ptr()] = True
             elif s.kind == "dw":
                 x, out = mt["x"], mt["out"]
@@ -300,7 +320,7 @@ class Trainer(object):
                 geo = (B, x.shape[1], x.shape[2], x.shape[3], mt["Ho"], mt["Wo"], mt["stride"], mt["ph"][0], mt["pw"][0])
                 add(lib.ssd_depthwise3x3_wgrad, (_ffi.ptr(x), _ffi.ptr(dy),
                                                  _ffi.ptr(self.vars[s.name + "/depthwise_kernel"]["grad"])) + geo,
-                    s.name + ":dw_wgrad")
+                    s.name + ":dw_wgrad", writes=(s.name + "/depthwise_kernel",))
                 dx = grad_buf(x)
                 acc = written[x.data_ptr()]
                 add(lib.ssd_depthwise3x3_dgrad, (_ffi.ptr(dy), _ffi.ptr(mt["w"]), _ffi.ptr(dx)) + geo + (int(acc),),
@@ -322,14 +342,30 @@ class Trainer(object):
                 acc = written[x.data_ptr()]
                 add(lib.ssd_l2norm_bwd, (_ffi.ptr(x), _ffi.ptr(mt["scale"]), _ffi.ptr(dy), _ffi.ptr(dx),
                                          _ffi.ptr(self.vars[s.name + "/scale"]["grad"]), B * x.shape[1] * x.shape[2],
-                                         x.shape[3], int(acc)), s.name + ":l2norm")
+                                         x.shape[3], int(acc)), s.name + ":l2norm", writes=(s.name + "/scale",))
                 written[x.data_ptr()] = True
         st["launches"], st["keep"], st["grad_of"] = launches, keep, grad_of
+        # Segments for the overlapped all-reduce: bucket k is complete after the last launch that writes one of its
+        # variables.  The backward pass runs in reverse layer order, so the LAST bucket completes first.
+        ready_at: Dict[int, int] = {}
+        for name, idx in last_writer.items():
+            k = self.grads.bucket_of[name]
+            ready_at[k] = max(ready_at.get(k, -1), idx)
+        assert len(ready_at) == len(self.grads.buckets), "every bucket must be written by the backward pass"
+        cuts = sorted(set(ready_at.values()))
+        segments, begin = [], 0
+        for c in cuts:
+            segments.append((begin, c + 1, sorted(k for k, v in ready_at.items() if v == c)))
+            begin = c + 1
+        if begin < len(launches):
+            segments.append((begin, len(launches), []))
+        st["segments"] = segments                       # [(first launch, end launch, buckets complete afterwards)]
+        st["graphs"] = None
         self._state[B] = st
         return st
 
     # -- one step ---------------------------------------------------------------------------------------------
-    def _enqueue_step(self, st: Dict[str, Any], B: int) -> None:
+    def _enqueue_step(self, st: Dict[str, Any], B: int, upto: Optional[int] = None) -> None:
         """Forward plan, fused loss forward/backward and the backward launch list on the current stream.  Nothing
         here allocates or synchronises, so the whole sequence is captured once per batch size into a CUDA graph
         (several hundred small launches per MobileNetV2 step would otherwise be bound by the host's launch rate)."""
@@ -347,43 +383,119 @@ class Trainer(object):
                                     self.alpha, self.loss_scale / B, _ffi.ptr(st["g_deltas"]), _ffi.ptr(st["g_logits"]),
                                     _ffi.ptr(st["ws"]), st["ws"].numel(), stream), "ssd_loss_bwd")
         self.grads.zero_()
-        for fn, args, what in st["launches"]:
+        self._enqueue_launches(st, 0, len(st["launches"]) if upto is None else upto)
+
+    def _enqueue_launches(self, st: Dict[str, Any], first: int, last: int) -> None:
+        stream = _ffi.stream()
+        for fn, args, what in st["launches"][first:last]:
             rc = fn(*args, stream)
             if rc != 0:
                 _ffi.check(rc, what)
 
-    def forward_backward(self, images: Any, actual_deltas: Any, actual_labels: Any) -> Dict[str, torch.Tensor]:
-        """Forward, loss, backward: fills the gradient buckets (loss-scaled) and returns the per-image losses."""
+    def _feed(self, plan, images: Any) -> None:
+        """Training plans read the float32 image buffer: a uint8 batch is converted first (convert_image_dtype,
+        utils/data_utils.py:36)."""
+        if SSDModel._is_u8(images):
+            images = _ffi.to_dev(images, dtype=torch.uint8).to(torch.float32) * (1.0 / 255.0)
+        self.model._to_image_buffer(plan, images)
+
+    def forward_backward(self, images: Any, actual_deltas: Any, actual_labels: Any, reduce: bool = True) -> Dict[str, torch.Tensor]:
+        """Forward, loss, backward: fills the gradient buckets (loss-scaled) and returns the per-image losses.
+
+        With several ranks (``reduce=True``) the step is replayed as one CUDA graph PER SEGMENT of the backward pass; after
+        each segment the gradient buckets it completed are all-reduced asynchronously (NCCL's stream picks up behind the
+        segment), so the exchange of the late layers' gradients overlaps the backward pass of the early layers.
+        ``apply_gradients`` waits for the exchanges.  Single process: one graph, no exchange."""
         m = self.model
         B = int(images.shape[0])
         st = self._prepare(B)
         st["ad"].copy_(_ffi.to_dev(actual_deltas), non_blocking=True)
         st["al"].copy_(_ffi.to_dev(actual_labels), non_blocking=True)
-        m._to_image_buffer(st["plan"], images)
+        self._feed(st["plan"], images)
         self._eval_dirty = True
-        if not self.use_cuda_graph:
-            self._enqueue_step(st, B)
-        elif st["graph"] is None:
-            self._enqueue_step(st, B)                # the first step runs eagerly (workspaces, function attributes) ...
+        distributed = reduce and dist_utils.world_size() > 1
+        segments = st["segments"] if distributed else [(0, len(st["launches"]), [])]
+        self._pending = []
+
+        def run_segment(i):
+            first, last, _ = segments[i]
+            if i == 0:
+                self._enqueue_step(st, B, upto=last)
+            else:
+                self._enqueue_launches(st, first, last)
+
+        key = "graphs_dist" if distributed else "graphs"
+        if self.use_cuda_graph and st.get(key) is None:
+            # the first step runs eagerly (workspaces, function attributes, split-K regions) ...
+            for i in range(len(segments)):
+                run_segment(i)
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):                # ... and is then recorded, without executing, for every later step
-                self._enqueue_step(st, B)
-            st["graph"] = g
-        else:
-            st["graph"].replay()
+            graphs = []
+            for i in range(len(segments)):           # ... and is then recorded, without executing, for every later step
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    run_segment(i)
+                graphs.append(g)
+            st[key] = graphs
+        for i, (_, _, done) in enumerate(segments):
+            if self.use_cuda_graph:
+                st[key][i].replay()
+            else:
+                run_segment(i)
+            if distributed:
+                for k in done:
+                    self._pending.append(self.grads.allreduce_sum_async(k))
         return dict(loc=st["loc"], conf=st["conf"])
 
-    def apply_gradients(self, learning_rate: Optional[float] = None) -> None:
-        """Mean over ranks (one all-reduce per bucket), then fused Adam on every variable."""
-        self.grads.allreduce_mean_()
+    def apply_gradients(self, learning_rate: Optional[float] = None, reduced: Optional[bool] = None) -> None:
+        """Waits for the gradient exchange (sum over ranks; the 1 / world of the mean is folded into the optimizer's
+        gradient scale), then ONE fused Adam launch over every variable, skipped on the device when a gradient is
+        non-finite."""
+        world = dist_utils.world_size()
+        if self._pending:
+            for w in self._pending:
+                w.wait()
+            self._pending = []
+        elif world > 1 and reduced is not True:
+            for w in [self.grads.allreduce_sum_async(k) for k in range(len(self.grads.buckets))]:
+                w.wait()
         self.t += 1
         lr = self.lr if learning_rate is None else float(learning_rate)
         lr_t = lr * math.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
         self.sumsq.zero_()
-        _ffi.check(self.lib.ssd_adam_step_multi(_ffi.ptr(self._adam_table), len(self.vars), self._adam_max_n, lr_t, self.b1,
-                                                self.b2, self.eps, 1.0 / self.loss_scale, _ffi.ptr(self.sumsq), _ffi.stream()),
-                   "ssd_adam_step_multi")
+        st = _ffi.stream()
+        _ffi.check(self.lib.ssd_grad_nonfinite_multi(_ffi.ptr(self._adam_table), len(self.vars), self._adam_max_n,
+                                                     _ffi.ptr(self._guard), st), "ssd_grad_nonfinite_multi")
+        _ffi.check(self.lib.ssd_adam_step_multi_guarded(_ffi.ptr(self._adam_table), len(self.vars), self._adam_max_n, lr_t,
+                                                        self.b1, self.b2, self.eps, 1.0 / (self.loss_scale * world),
+                                                        _ffi.ptr(self.sumsq), _ffi.ptr(self._guard), st),
+                   "ssd_adam_step_multi_guarded")
+        self._since_check += 1
+        if self.dynamic_loss_scale and self._since_check >= self.scale_check_every:
+            self.update_loss_scale()
+
+    def update_loss_scale(self) -> float:
+        """Host side of the loss-scale controller (one device synchronisation): halve after a skipped step, double after
+        ``scale_growth_interval`` clean ones.  The scale is an argument of captured kernels, so a change drops the
+        captured step graphs (they are re-captured on the next step)."""
+        skipped = int(self._guard[1].item())
+        self._guard[1].zero_()
+        new = self.loss_scale
+        if skipped > 0:
+            self.skipped_steps += skipped
+            self.t -= skipped                          # skipped steps did not advance Adam's bias correction
+            self._clean_steps = 0
+            new = max(self.loss_scale / 2.0, 1.0)
+        else:
+            self._clean_steps += self._since_check
+            if self._clean_steps >= self.scale_growth_interval:
+                new, self._clean_steps = min(self.loss_scale * 2.0, 65536.0), 0
+        self._since_check = 0
+        if new != self.loss_scale:
+            self.loss_scale = new
+            for st in self._state.values():
+                st["graphs"] = st["graphs_dist"] = None
+        return self.loss_scale
 
     def evaluate_batch(self, images: Any, targets: Tuple[Any, Any]) -> Dict[str, float]:
         """Validation loss of one batch (no gradient, no update): mean loc + mean conf (+ the regulariser of the
@@ -397,7 +509,7 @@ class Trainer(object):
                 self.sync_weights_to_host()
             plan = m.plan(B)
         ad, al = _ffi.to_dev(targets[0]), _ffi.to_dev(targets[1])
-        m._to_image_buffer(plan, images)
+        self._feed(plan, images)
         plan.run()
         _ffi.check(lib.ssd_loss_fwd(_ffi.ptr(ad), _ffi.ptr(plan.deltas), _ffi.ptr(al), _ffi.ptr(plan.logits), B, m.n_anchors,
                                     m.total_labels, self.neg_pos_ratio, self.alpha, 1, _ffi.ptr(st["loc"]), _ffi.ptr(st["conf"]),
@@ -406,8 +518,17 @@ class Trainer(object):
         reg = L2_REG * float(self.sumsq)
         return dict(loss=loc + conf + reg, loc_loss=loc, conf_loss=conf, reg_loss=reg)
 
+    def train_step(self, images: Any, targets: Tuple[Any, Any], learning_rate: Optional[float] = None) -> torch.Tensor:
+        """One optimisation step WITHOUT a host synchronisation: returns the step's total loss (mean loc + mean conf +
+        regulariser, like Keras' ``loss``) as a device scalar.  ``fit`` accumulates these on the device and reads the
+        epoch mean once."""
+        out = self.forward_backward(images, targets[0], targets[1])
+        self.apply_gradients(learning_rate)
+        return out["loc"].mean() + out["conf"].mean() + L2_REG * self.sumsq[0]
+
     def train_on_batch(self, images: Any, targets: Tuple[Any, Any], learning_rate: Optional[float] = None) -> Dict[str, float]:
-        """One optimisation step; ``targets = (actual_deltas, actual_labels)`` as ``train_utils.generator`` yields."""
+        """One optimisation step; ``targets = (actual_deltas, actual_labels)`` as ``train_utils.generator`` yields.
+        Returns host floats (one synchronisation) like Keras' ``train_on_batch``."""
         out = self.forward_backward(images, targets[0], targets[1])
         self.apply_gradients(learning_rate)
         loc, conf = float(out["loc"].mean()), float(out["conf"].mean())

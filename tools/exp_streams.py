@@ -28,7 +28,7 @@ for S in (1, 2, 4, 8):
         for st, s in zip(sts, streams):
             s.wait_event(ev)
             with torch.cuda.stream(s):
-                st["graph"].replay()
+                dm._graph(st, False).replay()
             main.wait_stream(s)
     for _ in range(5):
         step()

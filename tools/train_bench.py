@@ -143,10 +143,12 @@ def check_dp():
     img, gt, lab = make_batch(2 * world, hp, 7)
     b, e = dist_utils.shard_range(2 * world, rank, world)
     d, oh = train_utils.calculate_actual_outputs(priors, gt[b:e], lab[b:e], hp)
-    trainer.forward_backward(img[b:e], d, oh)
-    trainer.grads.allreduce_mean_()
+    trainer.forward_backward(img[b:e], d, oh)            # segments + overlapped SUM all-reduce per bucket
+    for w in trainer._pending:
+        w.wait()
+    trainer._pending = []
     torch.cuda.synchronize()
-    mine = torch.cat([bk.flatten() for bk in trainer.grads.buckets])
+    mine = torch.cat([bk.flatten() for bk in trainer.grads.buckets]) / world
     if rank == 0 and BACKBONE == "mobilenet_v2":
         # BatchNorm statistics stay per replica (Keras default): the reference is the mean of the
         # per-shard gradients computed one after the other in this process
@@ -155,7 +157,7 @@ def check_dp():
         for r in range(world):
             b1, e1 = dist_utils.shard_range(2 * world, r, world)
             d1, oh1 = train_utils.calculate_actual_outputs(priors, gt[b1:e1], lab[b1:e1], hp1)
-            trainer1.forward_backward(img[b1:e1], d1, oh1)
+            trainer1.forward_backward(img[b1:e1], d1, oh1, reduce=False)
             torch.cuda.synchronize()
             g1 = torch.cat([bk.flatten() for bk in trainer1.grads.buckets])
             ref = g1 if ref is None else ref + g1
@@ -166,7 +168,7 @@ def check_dp():
     elif rank == 0:
         hp1, model1, trainer1, _ = build(2 * world)
         d1, oh1 = train_utils.calculate_actual_outputs(priors, gt, lab, hp1)
-        trainer1.forward_backward(img, d1, oh1)
+        trainer1.forward_backward(img, d1, oh1, reduce=False)
         torch.cuda.synchronize()
         ref = torch.cat([bk.flatten() for bk in trainer1.grads.buckets])
         rel = float((mine - ref).norm() / ref.norm())
