@@ -426,7 +426,9 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU restatement)")
     torch.cuda.set_device(local_rank)
-    numa_bound = dist_utils.bind_to_gpu_numa(local_rank)      # pinned staging buffers on the GPU's NUMA node
+    # pinned staging buffers on the GPU's NUMA node (multi-GPU runs only: at N = 1 this process also runs the CPU baseline
+    # on all host cores)
+    numa_bound = dist_utils.bind_to_gpu_numa(local_rank) if world > 1 else False
     dist_utils.init_from_env("nccl")
 
     from tf_ssd_b200 import _ffi, synth

@@ -7,6 +7,8 @@ import pytest
 
 from oracle import box_oracle as bo
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 def test_data_utils_contract():
     from tf_ssd_b200.utils import data_utils
@@ -232,3 +234,40 @@ def test_device_preprocess_bit_exact():
     got = data_utils.device_flip_boxes(boxes.copy()).cpu().numpy()
     assert np.array_equal(got, bo.flip_boxes(boxes))
 
+
+
+@pytest.mark.parametrize("backbone", ["vgg16", "mobilenet_v2"])
+def test_h5_weight_converter_on_a_keras_shaped_tree(backbone, tmp_path):
+    """tools/convert_h5_weights.py on a hand-built tree with Keras' on-disk shape (``model_weights/<layer>/<layer>/
+    <variable>:0``; the reference's L2Normalization saves its unnamed variable as ``Variable:0``): every variable comes
+    out under the name and shape ``SSDModel`` expects, and ``load_weights`` accepts the result (h5py itself is not
+    available in this image: the file layer of the converter is the only part not exercised)."""
+    import importlib.util
+    from tf_ssd_b200.models.engine import SSDModel
+    from tf_ssd_b200.utils import train_utils
+    spec = importlib.util.spec_from_file_location("convert_h5_weights", os.path.join(ROOT, "tools", "convert_h5_weights.py"))
+    conv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(conv)
+    hp = train_utils.get_hyper_params(backbone)
+    hp["total_labels"] = 21
+    model = SSDModel(backbone, hp, seed=0)
+    rng = np.random.default_rng(1)
+    want = {k: rng.standard_normal(v.shape).astype(np.float32) for k, v in model.weights.items()}
+    tree = {}
+    for name, arr in want.items():
+        layer, var = name.rsplit("/", 1)
+        if layer == "l2_normalization":
+            var = "Variable"                              # unnamed tf.Variable (models/ssd_vgg16.py:52)
+        tree.setdefault(layer, {}).setdefault(layer, {})[var + ":0"] = arr.astype(np.float64)
+    got = conv.convert_tree({"model_weights": tree, "optimizer_weights": {}} if backbone == "vgg16" else tree)
+    assert sorted(got) == sorted(want)
+    for k in want:
+        assert got[k].dtype == np.float32 and np.array_equal(got[k], want[k]), k
+    path = str(tmp_path / "w.npz")
+    np.savez(path, **got)
+    model.load_weights(path)
+    assert all(np.array_equal(model.weights[k], want[k]) for k in want)
+    with pytest.raises(ValueError):
+        conv.convert_tree({"layer": {"layer": {"kernel:0": np.zeros(1), "mystery:0": np.zeros(1)}}})
+    with pytest.raises(KeyError):
+        model.set_weights({"no_such_layer/kernel": np.zeros(1, np.float32)})

@@ -172,3 +172,24 @@ def test_decoder_full_size_properties():
         assert (s[i, :v] > 0.5).all() and (l[i, :v] >= 1).all()
         assert not s[i, v:].any() and not b[i, v:].any()
         assert b[i].min() >= 0 and b[i].max() <= 1
+
+
+@pytest.mark.parametrize("thr,scale", [(0.5, 3.0), (0.3, 1.0), (0.05, 1.0)])
+def test_decoder_candidate_capacity(thr, scale):
+    """More than one class per anchor may pass the threshold when the scores are not normalised (scale > 1) or the
+    threshold is below 0.5: the candidate list must grow instead of reporting an overflow (TensorFlow has no limit)."""
+    from tf_ssd_b200 import synth
+    from tf_ssd_b200.models.decoder import SSDDecoder
+    priors = bo.prior_boxes(*CONFIGS["mobilenet_v2"][:2])[:600]
+    deltas, z = synth.make_head_outputs(2, priors.shape[0], 21, seed=5, hot_fraction=0.3, hot_boost=2.0)
+    probs = (bo.softmax(z) * np.float32(scale)).astype(np.float32)
+    dec = SSDDecoder(priors, VARIANCES, max_total_size=300, score_threshold=thr)
+    b, l, s = dec([deltas, probs])
+    rb, rl, rs, rvalid, _ = bo.ssd_decode(priors, VARIANCES, deltas, probs, 300, thr, return_aux=True)
+    n_cand = ((probs > thr) & (probs.argmax(-1, keepdims=True) != 0)).sum((1, 2))
+    if scale > 1.0 or thr < 0.1:
+        assert (n_cand > priors.shape[0]).any()                 # really exceeds the N-candidate assumption
+    np.testing.assert_array_equal(_np(dec.last_valid_detections), rvalid)
+    np.testing.assert_array_equal(_np(l), rl)
+    np.testing.assert_array_equal(_np(s), rs)
+    np.testing.assert_allclose(_np(b), rb, rtol=1e-5, atol=1e-6)

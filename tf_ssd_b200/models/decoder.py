@@ -51,20 +51,31 @@ class SSDDecoder(object):
             self._priors_dev = _ffi.to_dev(self.prior_boxes)
         return self._priors_dev
 
+    def candidate_capacity(self, N: int, L: int, from_logits: bool) -> int:
+        """Per-image capacity of the candidate list handed to ``ssd_decode_nms`` (0 = N).  Softmax rows sum to 1, so with
+        a threshold >= 0.5 at most one class per anchor can pass (models/decoder.py:78-92) and N is exact.  Below 0.5 a
+        normalised row can hold floor(1 / threshold) passing classes; inputs that are not normalised at all may overflow
+        any bound short of N * L -- the kernel then reports valid = -1 and ``call`` retries with the full N * L."""
+        thr = self.score_threshold
+        if from_logits or thr >= 0.5:
+            return 0
+        return N * L if thr <= 0.0 else min(N * L, N * max(1, int(1.0 / thr)))
+
     def decode_into(self, pred_deltas: torch.Tensor, pred_labels: torch.Tensor, from_logits: bool,
                     out_boxes: torch.Tensor, out_labels: torch.Tensor, out_scores: torch.Tensor,
-                    out_valid: torch.Tensor) -> None:
+                    out_valid: torch.Tensor, max_candidates: Optional[int] = None) -> None:
         """Enqueue the fused decode+NMS on the current stream into caller
         buffers (allocation-free once the workspace exists: graph-capturable)."""
         B, N, L = pred_labels.shape
         lib = _ffi.lib()
-        key = (B, N, L, self.max_total_size, pred_labels.device)
+        cap = self.candidate_capacity(N, L, from_logits) if max_candidates is None else int(max_candidates)
+        key = (B, N, L, self.max_total_size, cap, pred_labels.device)
         if self._ws is None or self._ws_key != key:
-            self._ws = _ffi.workspace(lib.ssd_decode_nms_workspace_bytes(B, N, L, self.max_total_size, 0))
+            self._ws = _ffi.workspace(lib.ssd_decode_nms_workspace_bytes(B, N, L, self.max_total_size, cap))
             self._ws_key = key
         _ffi.check(lib.ssd_decode_nms(_ffi.ptr(self._priors()), _ffi.ptr(pred_deltas), _ffi.ptr(pred_labels),
                                       B, N, L, _ffi.f32_array(self.variances), int(from_logits),
-                                      self.score_threshold, self.iou_threshold, self.max_total_size, 0,
+                                      self.score_threshold, self.iou_threshold, self.max_total_size, cap,
                                       _ffi.ptr(out_boxes), _ffi.ptr(out_labels), _ffi.ptr(out_scores),
                                       _ffi.ptr(out_valid), _ffi.ptr(self._ws), self._ws.numel(), _ffi.stream()),
                    "ssd_decode_nms")
@@ -81,6 +92,13 @@ class SSDDecoder(object):
         scores = torch.empty((B, T), dtype=torch.float32, device=dev)
         valid = torch.empty((B,), dtype=torch.int32, device=dev)
         self.decode_into(pred_deltas, pred_labels, from_logits, boxes, labels, scores, valid)
+        N, L = pred_labels.shape[1], pred_labels.shape[2]
+        if not from_logits and bool((valid < 0).any()):
+            # more candidates than the capacity assumed for normalised probabilities (un-normalised scores): TensorFlow's
+            # combined NMS has no such limit, so run again with room for every (anchor, class) pair
+            self.decode_into(pred_deltas, pred_labels, from_logits, boxes, labels, scores, valid, max_candidates=N * L)
+        if bool((valid < 0).any()):
+            raise _ffi.SsdB200Error("ssd_decode_nms: candidate list overflow")
         self.last_valid_detections = valid
         return boxes, labels, scores
 

@@ -993,6 +993,8 @@ class DecoderModel(object):
         def drain(entry):
             st, hb, done = entry
             done.synchronize()
+            if int(hb["valid"].min()) < 0:               # cannot happen for softmax outputs (at most one class per anchor > 0.5)
+                raise _ffi.SsdB200Error("ssd_decode_nms reported a candidate overflow (valid = -1)")
             ob.append(hb["boxes"].numpy().copy()); ol.append(hb["labels"].numpy().copy())
             os_.append(hb["scores"].numpy().copy())
 
@@ -1012,7 +1014,8 @@ class DecoderModel(object):
                 hb = {"img": torch.empty(tuple(dst_img.shape), dtype=dst_img.dtype, pin_memory=True),
                       "boxes": torch.empty((B, T, 4), dtype=torch.float32, pin_memory=True),
                       "labels": torch.empty((B, T), dtype=torch.float32, pin_memory=True),
-                      "scores": torch.empty((B, T), dtype=torch.float32, pin_memory=True)}
+                      "scores": torch.empty((B, T), dtype=torch.float32, pin_memory=True),
+                      "valid": torch.empty((B,), dtype=torch.int32, pin_memory=True)}
                 host[(B, slot, u8)] = hb
             if isinstance(img, torch.Tensor) and img.is_cuda:
                 with torch.cuda.stream(cs):
@@ -1037,6 +1040,7 @@ class DecoderModel(object):
                 hb["boxes"].copy_(st["boxes"], non_blocking=True)
                 hb["labels"].copy_(st["labels"], non_blocking=True)
                 hb["scores"].copy_(st["scores"], non_blocking=True)
+                hb["valid"].copy_(st["valid"], non_blocking=True)
                 done = torch.cuda.Event()
                 done.record(ds)
             pending.append((st, hb, done))

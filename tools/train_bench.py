@@ -194,4 +194,8 @@ if __name__ == "__main__":
     else:
         out = measure(a.steps, a.warmup, a.batch)
         if int(os.environ.get("RANK", "0")) == 0:
-            print(json.dumps(out))
+            print(json.dumps(out), flush=True)
+    import torch.distributed as _dist
+    if _dist.is_initialized():
+        _dist.barrier()
+        _dist.destroy_process_group()
