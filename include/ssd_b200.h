@@ -275,6 +275,25 @@ int ssd_preprocess_image(const void* d_img_u8, int H, int W, float* d_out, int o
                          ssd_stream_t stream);
 int ssd_flip_boxes(float* d_boxes, int n, ssd_stream_t stream);
 
+/* Training-time augmentation of a whole batch.  Replaces augmentation.py:16-33 `apply` and the
+ * operations it chains per example -- patch (:205-234: optional expand_image :164-202 on a canvas filled with the
+ * image's per-channel mean, crop window, tf.image.resize back to H x W), flip_horizontally (:119-139),
+ * random_brightness / _contrast / _hue / _saturation (:67-116), tf.clip_by_value(img, 0, 1) -- and the box updates
+ * (utils/bbox_utils.py:217-233 renormalize_bboxes_with_min_max, the flip).  Every random decision is an input:
+ * d_plans holds B plans of 16 32-bit words
+ *   [0] flags: bit0 patch, bit1 expand, bit2 flip, bit3 brightness, bit4 contrast, bit5 hue, bit6 saturation,
+ *       bit7 skip the final clip (the reference's single operations do not clip, only `apply` does, :32)
+ *   [1..4] pad_top, pad_left, canvas_h, canvas_w (int32; H, W and zero pads without expand)
+ *   [5..8] crop y0, x0, height, width on the canvas (int32; tf.image.sample_distorted_bounding_box's window)
+ *   [9..12] brightness delta, contrast factor, hue delta, saturation factor (float32)   [13..15] reserved
+ * d_images [B,H,W,3] float32 (already resized, utils/data_utils.py:36-37) -> d_out [B,out_h,out_w,3] (must not
+ * alias).  `patch` resizes the window to out_h x out_w = H x W (:231); out = canvas size with the window = whole
+ * canvas gives expand_image's own output; images without a patch need out_h x out_w == H x W.
+ * d_boxes [B,G,4] is updated in place (all-zero padding rows stay zero; may be NULL when G == 0). */
+size_t ssd_augment_workspace_bytes(int B, int H, int W, int out_h, int out_w);
+int ssd_augment_batch(const float* d_images, float* d_out, float* d_boxes, int B, int H, int W, int out_h, int out_w, int G,
+                      const void* d_plans, void* d_workspace, size_t workspace_bytes, ssd_stream_t stream);
+
 /* fp32 NHWC image [B,H,W,3] (utils/data_utils.py:36 convert_image_dtype output)
  * -> fp16 NHWC with the channel dimension zero-padded to 8. */
 int ssd_image_to_f16c8(const float* d_img, void* d_out, int64_t n_pixels, ssd_stream_t stream);

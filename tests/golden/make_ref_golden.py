@@ -55,6 +55,8 @@ class Reference(object):
             self.ssd_vgg16 = importlib.import_module("models.ssd_vgg16")
             self.ssd_mobilenet_v2 = importlib.import_module("models.ssd_mobilenet_v2")
             self.keras_layers = importlib.import_module("tensorflow.keras.layers")
+            self.augmentation = importlib.import_module("augmentation")
+            self.tf_image = importlib.import_module("tensorflow.image")
             for m in (self.bbox_utils, self.train_utils, self.ssd_loss, self.decoder, self.header, self.ssd_vgg16):
                 assert os.path.abspath(m.__file__).startswith(os.path.abspath(REFERENCE)), m.__file__
         finally:
@@ -212,7 +214,41 @@ def net_fixture(ref: Reference) -> Dict[str, np.ndarray]:
     return out
 
 
-FIXTURES = {"priors": priors_fixture, "box": box_fixture, "loss": loss_fixture, "decode": decode_fixture,
+def augment_fixture(ref: Reference) -> Dict[str, np.ndarray]:
+    """augmentation.py:16-234 (``apply`` and each operation on its own) with the random stream and the crop window of
+    ``sample_distorted_bounding_box`` fed in; utils/bbox_utils.py:217-233 through ``patch`` / ``expand_image``."""
+    aug, tf, tfi = ref.augmentation, ref.tf, ref.tf_image
+    img, boxes = ri.augment_inputs()
+    out: Dict[str, np.ndarray] = {"img": img, "boxes": boxes}
+    for i, case in enumerate(ri.AUGMENT_CASES):
+        tf.random.queue[:] = ri.augment_queue(case)
+        tf.random.log.clear()
+        tfi.crop_queue[:] = [case["patch"]["crop"]] if case["patch"] is not None else []
+        tfi.crop_log.clear()
+        o_img, o_boxes = aug.apply(tf.constant(img), tf.constant(boxes))
+        assert not tf.random.queue and not tfi.crop_queue, "the reference drew a different number of samples"
+        out[f"case{i}_img"], out[f"case{i}_boxes"] = _n(o_img), _n(o_boxes)
+        out[f"case{i}_window"] = np.array(tfi.crop_log[0] if tfi.crop_log else (0, 0, 0, 0, 0, 0), np.int32)
+        out[f"case{i}_draws"] = np.array([float(np.asarray(v)) for v in tf.random.log], np.float64)
+    # single operations (augmentation.py:67-139, 164-202) with their draw
+    for name, fn, u in (("brightness", aug.random_brightness, 0.9), ("contrast", aug.random_contrast, 0.2),
+                        ("hue", aug.random_hue, 0.35), ("saturation", aug.random_saturation, 0.77)):
+        tf.random.queue[:] = [u]
+        o_img, _ = fn(tf.constant(img), tf.constant(boxes))
+        out[f"op_{name}"] = _n(o_img)
+        out[f"op_{name}_u"] = np.array([u], np.float64)
+    o_img, o_boxes = aug.flip_horizontally(tf.constant(img), tf.constant(boxes))
+    out["op_flip_img"], out["op_flip_boxes"] = _n(o_img), _n(o_boxes)
+    tf.random.queue[:] = [0.5, 0.25, 0.75]
+    H, W = img.shape[:2]
+    o_img, o_boxes = aug.expand_image(tf.constant(img), tf.constant(boxes), tf.constant(np.float32(H)), tf.constant(np.float32(W)))
+    out["op_expand_img"], out["op_expand_boxes"] = _n(o_img), _n(o_boxes)
+    out["op_expand_u"] = np.array([0.5, 0.25, 0.75], np.float64)
+    out["op_renorm"] = _n(ref.bbox_utils.renormalize_bboxes_with_min_max(tf.constant(boxes), tf.constant(np.array([0.2, 0.1, 0.9, 0.6], np.float32))))
+    return out
+
+
+FIXTURES = {"augment": augment_fixture, "priors": priors_fixture, "box": box_fixture, "loss": loss_fixture, "decode": decode_fixture,
             "net": net_fixture}
 
 

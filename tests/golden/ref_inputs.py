@@ -140,3 +140,53 @@ def nms_tie_inputs(n_cls: int = 6):
     scores = np.zeros((B, N, n_cls), np.float32)
     np.put_along_axis(scores, cls[..., None], sc[..., None], axis=2)
     return np.broadcast_to(boxes[None, :, None, :], (B, N, 1, 4)).copy(), scores
+
+
+# ---- augmentation.py fixtures: every random decision of ``augmentation.apply`` spelled out -------------------------
+# patch: None (skipped) or {"expand": None | (u_ratio, u_left, u_top), "overlap": index into [.1,.3,.5,.7,.9],
+# "crop": window as fractions (y0, x0, h, w) of the current canvas}; flip: bool; brightness / contrast / hue /
+# saturation: None (skipped) or the [0,1) sample behind the op's tf.random.uniform call.
+AUGMENT_SIZE = (40, 56)                 # H, W of the fixture image (already "resized": utils/data_utils.py:37)
+AUGMENT_CASES = (
+    {"patch": {"expand": (0.37, 0.61, 0.22), "overlap": 2, "crop": (0.13, 0.21, 0.55, 0.62)}, "flip": True,
+     "brightness": 0.83, "contrast": 0.12, "hue": 0.71, "saturation": 0.90},
+    {"patch": {"expand": None, "overlap": 0, "crop": (0.05, 0.30, 0.80, 0.45)}, "flip": False,
+     "brightness": None, "contrast": 0.95, "hue": None, "saturation": None},
+    {"patch": None, "flip": True, "brightness": None, "contrast": None, "hue": 0.08, "saturation": None},
+    {"patch": None, "flip": False, "brightness": 0.02, "contrast": None, "hue": None, "saturation": 0.31},
+    {"patch": None, "flip": False, "brightness": None, "contrast": None, "hue": None, "saturation": None},
+    {"patch": {"expand": (0.999, 0.0, 0.999), "overlap": 4, "crop": (0.0, 0.0, 1.0, 1.0)}, "flip": False,
+     "brightness": 0.5, "contrast": 0.5, "hue": 0.5, "saturation": 0.5},
+)
+
+
+def augment_inputs(seed: int = 77):
+    """One float image in [0,1] (exact u8/255 values, some saturated pixels) and its boxes."""
+    rng = np.random.default_rng(seed)
+    H, W = AUGMENT_SIZE
+    img = rng.integers(0, 256, (H, W, 3)).astype(np.float32) * np.float32(1.0 / 255.0)
+    img[:4, :6] = 0.0                    # grey / black / white patches: zero saturation, zero value
+    img[4:8, :6] = 1.0
+    img[8:12, :6] = np.float32(0.5)
+    boxes = np.array([[0.10, 0.20, 0.55, 0.70], [0.40, 0.05, 0.95, 0.45], [0.0, 0.0, 1.0, 1.0], [0.62, 0.58, 0.70, 0.66]],
+                     np.float32)
+    return img, boxes
+
+
+def augment_queue(case) -> list:
+    """The uniform samples ``augmentation.apply`` consumes for ``case``, in the order it draws them
+    (augmentation.py:26-31, 205-222, 177-181): a gate sample per operation (> 0.5 applies it), then the operation's own."""
+    gate = lambda on: 0.75 if on else 0.25
+    q = [gate(case["patch"] is not None)]
+    if case["patch"] is not None:
+        ex = case["patch"]["expand"]
+        q.append(gate(ex is not None))
+        if ex is not None:
+            q.extend(ex)
+        q.append(int(case["patch"]["overlap"]))                  # get_random_min_overlap: an int32 draw
+    q.append(gate(case["flip"]))
+    for k in ("brightness", "contrast", "hue", "saturation"):
+        q.append(gate(case[k] is not None))
+        if case[k] is not None:
+            q.append(case[k])
+    return q

@@ -271,3 +271,61 @@ def test_h5_weight_converter_on_a_keras_shaped_tree(backbone, tmp_path):
         conv.convert_tree({"layer": {"layer": {"kernel:0": np.zeros(1), "mystery:0": np.zeros(1)}}})
     with pytest.raises(KeyError):
         model.set_weights({"no_such_layer/kernel": np.zeros(1, np.float32)})
+
+
+def test_dataset_map_and_take():
+    """``map`` must apply its function, ``take`` must keep concatenated parts."""
+    from tf_ssd_b200.utils import data_utils
+    ds, _ = data_utils.get_dataset("voc/2007", "test", total_items=6, img_size=64)
+    other, _ = data_utils.get_dataset("voc/2012", "train+validation", total_items=5, img_size=64)
+    seen = []
+    mapped = ds.concatenate(other).map(lambda ex: (seen.append(1), data_utils.preprocessing(ex, 64, 64))[1])
+    assert sum(1 for _ in mapped.take(9)) == 9 and len(seen) == 9                 # 6 of the first part + 3 of the second
+    flipped = ds.map(lambda ex: (ex[0][:, ::-1], ex[1], ex[2]))
+    a, b = next(iter(ds)), next(iter(flipped))
+    assert np.array_equal(a[0][:, ::-1], b[0])
+    with pytest.raises(ValueError):
+        data_utils.preprocessing(a, 32, 32)
+
+
+@pytest.mark.gpu
+def test_preprocessing_of_a_tfds_style_example_and_batched_augmentation():
+    """utils/data_utils.py:12-38 on a TFDS-shaped example (labels + 1, device resize, is_difficult filter, per-example
+    augmentation_fn) and the batched form: ``train_utils.generator(..., augmentation_fn=augmentation.apply)``."""
+    import torch
+    from oracle import augment_oracle as ao
+    from tf_ssd_b200 import augmentation
+    from tf_ssd_b200.utils import bbox_utils, data_utils, train_utils
+    rng = np.random.default_rng(0)
+    example = {"image": rng.integers(0, 256, (90, 120, 3), dtype=np.uint8),
+               "objects": {"bbox": np.array([[0.1, 0.2, 0.6, 0.7], [0.3, 0.3, 0.9, 0.8]], np.float32),
+                           "label": np.array([4, 11], np.int64), "is_difficult": np.array([False, True])}}
+    img, gb, gl = data_utils.preprocessing(example, 300, 300)
+    assert np.array_equal(img.cpu().numpy(), bo.preprocess_image(example["image"], 300, 300))
+    assert gl.tolist() == [5, 12] and gl.dtype == np.int32 and gb.shape == (2, 4)
+    _, gb_e, gl_e = data_utils.preprocessing(example, 300, 300, evaluate=True)
+    assert gl_e.tolist() == [5] and np.array_equal(gb_e, example["objects"]["bbox"][:1])
+    draws = augmentation.ReplayDraws([0.25, 0.75, 0.25, 0.25, 0.25, 0.25])          # only the flip is taken
+    a_img, a_gb, _ = data_utils.preprocessing(example, 300, 300, augmentation_fn=lambda i, b: augmentation.apply(i, b, draws=draws))
+    assert np.array_equal(a_img.cpu().numpy(), bo.preprocess_image(example["image"], 300, 300, flip=True))
+    assert np.array_equal(a_gb.cpu().numpy(), ao.flip_boxes(example["objects"]["bbox"]))
+    # box helpers of utils/bbox_utils.py:217-269
+    mm = [0.2, 0.1, 0.9, 0.6]
+    assert np.allclose(bbox_utils.renormalize_bboxes_with_min_max(gb, mm).cpu().numpy(), ao.renormalize_boxes(gb, mm), atol=1e-7)
+    px = bbox_utils.denormalize_bboxes(gb, 300, 500).cpu().numpy()
+    assert np.array_equal(px, np.round(gb * np.array([300, 500, 300, 500], np.float32)))
+    assert np.allclose(bbox_utils.normalize_bboxes(px, 300, 500).cpu().numpy(), gb, atol=2e-3)
+    # batched: every batch of the feed is augmented on the device, targets are matched on the augmented boxes
+    hp = train_utils.get_hyper_params("mobilenet_v2")
+    hp["total_labels"] = 21
+    priors = bbox_utils.generate_prior_boxes(hp["feature_map_shapes"], hp["aspect_ratios"])
+    ds, _ = data_utils.get_dataset("voc/2007", "test", total_items=8)
+    batches = ds.padded_batch(4, drop_remainder=True)
+    seed_draws = augmentation.RandomDraws(7)
+    feed = train_utils.generator(batches, priors, hp, augmentation_fn=lambda i, b: augmentation.apply(i, b, draws=seed_draws))
+    img_b, (deltas, onehot) = next(feed)
+    plain = next(train_utils.generator(batches, priors, hp))
+    assert tuple(img_b.shape) == (4, 300, 300, 3) and tuple(deltas.shape) == (4, 2268, 4) and tuple(onehot.shape) == (4, 2268, 21)
+    assert float(img_b.min()) >= 0.0 and float(img_b.max()) <= 1.0
+    assert not torch.equal(img_b, torch.as_tensor(plain[0]).to(img_b.device))
+    assert torch.isfinite(deltas).all() and float(onehot.sum(-1).min()) == 1.0

@@ -17,11 +17,12 @@ import numpy as np
 import pytest
 
 from oracle import box_oracle as bo
+from oracle import augment_oracle as ao
 from oracle import net_oracle as no
 from tests.golden import ref_inputs as ri
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-REF = {k: np.load(os.path.join(HERE, "golden", f"ref_{k}.npz")) for k in ("priors", "box", "loss", "decode", "net")}
+REF = {k: np.load(os.path.join(HERE, "golden", f"ref_{k}.npz")) for k in ("priors", "box", "loss", "decode", "net", "augment")}
 VAR = ri.VARIANCES
 RTOL = 1e-4                  # north_star: box / loss tensors within 1e-4 relative float32
 HAVE_REFERENCE = os.path.isdir(os.environ.get("SSD_REFERENCE_DIR", "/root/reference"))
@@ -36,7 +37,7 @@ def _targets():
 
 # ------------------------------------------------------------ reproducibility --
 @pytest.mark.skipif(not HAVE_REFERENCE, reason="/root/reference is not present on this machine")
-@pytest.mark.parametrize("which", ["priors", "box", "loss", "decode"])
+@pytest.mark.parametrize("which", ["priors", "box", "loss", "decode", "augment"])
 def test_fixtures_regenerate_from_the_reference_source(which):
     """Running the reference's modules under the shim again yields the committed bytes."""
     from tests.golden import make_ref_golden as gen
@@ -140,6 +141,117 @@ def test_oracle_networks_match_the_reference_graphs(name):
 
 
 # ------------------------------------------------------------------ CUDA (GPU) --
+# ------------------------------------------------------ augmentation.py (f3) --
+AUG_TOL = 2e-6            # float32 images in [0,1]: device vs oracle, and operations without a mean vs the reference
+# Operations that use a per-channel MEAN (expand's fill, contrast): the reference's float32 reduction order is
+# TensorFlow's (NumPy's stand-in sums row by row and is itself ~1e-6 off the exact mean; the oracle and the device round
+# the exact mean once); hue / saturation amplify that on near-grey pixels.  Measured: 7.9e-6 on case 0.
+AUG_MEAN_TOL = 2e-5
+
+
+def _aug_tol(i):
+    case = ri.AUGMENT_CASES[i]
+    uses_mean = case["contrast"] is not None or (case["patch"] is not None and case["patch"]["expand"] is not None)
+    return AUG_MEAN_TOL if uses_mean else AUG_TOL
+
+
+def _augment_plan(i):
+    """The product's host planner fed with the samples the reference consumed for case ``i`` (and its crop window)."""
+    from tf_ssd_b200 import augmentation as aug
+    A, case = REF["augment"], ri.AUGMENT_CASES[i]
+    H, W = A["img"].shape[:2]
+    window = tuple(int(v) for v in A[f"case{i}_window"][:4])
+    draws = aug.ReplayDraws(ri.augment_queue(case), [window] if case["patch"] is not None else [])
+    plan = aug.make_plan(H, W, A["boxes"], draws)
+    assert not draws.samples and not draws.crops, "the planner drew a different number of samples than the reference"
+    if case["patch"] is not None and case["patch"]["expand"] is not None:
+        g = plan["patch"]["expand"]
+        assert (g["canvas_h"], g["canvas_w"]) == tuple(A[f"case{i}_window"][4:]), "canvas size differs from the reference's"
+    return plan
+
+
+def test_oracle_augmentation_matches_the_reference_source():
+    """oracle/augment_oracle.py against augmentation.py:16-234 run unmodified on the shim (same draws, same window)."""
+    A = REF["augment"]
+    img, boxes = A["img"], A["boxes"]
+    for i in range(len(ri.AUGMENT_CASES)):
+        o_img, o_boxes = ao.apply(img, boxes, _augment_plan(i))
+        assert o_img.shape == A[f"case{i}_img"].shape
+        np.testing.assert_allclose(o_img, A[f"case{i}_img"], rtol=0, atol=_aug_tol(i), err_msg=f"case {i}")
+        np.testing.assert_allclose(o_boxes, A[f"case{i}_boxes"], rtol=0, atol=1e-6, err_msg=f"case {i}")
+    assert np.array_equal(ao.adjust_brightness(img, ao.uniform(A["op_brightness_u"][0], -0.12, 0.12)), A["op_brightness"])
+    np.testing.assert_allclose(ao.adjust_contrast(img, ao.uniform(A["op_contrast_u"][0], 0.5, 1.5)), A["op_contrast"], rtol=0, atol=AUG_TOL)
+    np.testing.assert_allclose(ao.adjust_hue(img, ao.uniform(A["op_hue_u"][0], -0.08, 0.08)), A["op_hue"], rtol=0, atol=AUG_TOL)
+    np.testing.assert_allclose(ao.adjust_saturation(img, ao.uniform(A["op_saturation_u"][0], 0.5, 1.5)), A["op_saturation"], rtol=0, atol=AUG_TOL)
+    assert np.array_equal(img[:, ::-1], A["op_flip_img"]) and np.array_equal(ao.flip_boxes(boxes), A["op_flip_boxes"])
+    geom = ao.resolve_expand(img.shape[0], img.shape[1], *A["op_expand_u"])
+    e_img, e_boxes = ao.expand_image(img, boxes, geom)
+    assert e_img.shape == A["op_expand_img"].shape
+    np.testing.assert_allclose(e_img, A["op_expand_img"], rtol=0, atol=AUG_TOL)
+    assert np.array_equal(e_boxes, A["op_expand_boxes"])
+    assert np.array_equal(ao.renormalize_boxes(boxes, [0.2, 0.1, 0.9, 0.6]), A["op_renorm"])
+
+
+@pytest.mark.gpu
+def test_cuda_augmentation_matches_the_reference_source():
+    """ssd_augment_batch (all six cases as ONE batch, plus padded box rows) against the reference's outputs."""
+    import torch
+    from tf_ssd_b200 import augmentation as aug
+    A = REF["augment"]
+    n = len(ri.AUGMENT_CASES)
+    img = np.repeat(A["img"][None], n, 0)
+    boxes = np.zeros((n, 6, 4), np.float32)
+    boxes[:, :4] = A["boxes"]
+    plans = [_augment_plan(i) for i in range(n)]
+    o_img, o_boxes = aug.apply_plans(img, boxes, plans)
+    o_img, o_boxes = o_img.cpu().numpy(), o_boxes.cpu().numpy()
+    for i in range(n):
+        np.testing.assert_allclose(o_img[i], A[f"case{i}_img"], rtol=0, atol=_aug_tol(i), err_msg=f"case {i}")
+        np.testing.assert_allclose(o_img[i], ao.apply(A["img"], A["boxes"], plans[i])[0], rtol=0, atol=AUG_TOL, err_msg=f"case {i}")
+        np.testing.assert_allclose(o_boxes[i, :4], A[f"case{i}_boxes"], rtol=0, atol=1e-6, err_msg=f"case {i}")
+        assert not o_boxes[i, 4:].any(), "padding rows must stay zero"
+    # the reference's single operations (no clip), replaying the one sample each of them draws
+    for name, fn in (("brightness", aug.random_brightness), ("contrast", aug.random_contrast), ("hue", aug.random_hue),
+                     ("saturation", aug.random_saturation)):
+        got, same_boxes = fn(A["img"], A["boxes"], draws=aug.ReplayDraws([A[f"op_{name}_u"][0]]))
+        np.testing.assert_allclose(got.cpu().numpy(), A[f"op_{name}"], rtol=0, atol=AUG_TOL, err_msg=name)
+        assert np.array_equal(same_boxes.cpu().numpy(), A["boxes"])
+    f_img, f_boxes = aug.flip_horizontally(A["img"], A["boxes"])
+    assert np.array_equal(f_img.cpu().numpy(), A["op_flip_img"]) and np.array_equal(f_boxes.cpu().numpy(), A["op_flip_boxes"])
+    e_img, e_boxes = aug.expand_image(A["img"], A["boxes"], draws=aug.ReplayDraws(list(A["op_expand_u"])))
+    assert tuple(e_img.shape) == A["op_expand_img"].shape
+    np.testing.assert_allclose(e_img.cpu().numpy(), A["op_expand_img"], rtol=0, atol=AUG_TOL)
+    assert np.array_equal(e_boxes.cpu().numpy(), A["op_expand_boxes"])
+
+
+@pytest.mark.gpu
+def test_cuda_augmentation_batch_against_the_oracle():
+    """A 300x300 batch with random plans from the product's own sampler: device == oracle; deterministic."""
+    import torch
+    from tf_ssd_b200 import augmentation as aug
+    rng = np.random.default_rng(3)
+    B, S, G = 8, 300, 5
+    img = (rng.integers(0, 256, (B, S, S, 3)).astype(np.float32) * np.float32(1 / 255.0))
+    boxes, _ = ri.ground_truth(B, G, seed=21)
+    draws = aug.RandomDraws(1234)
+    plans = [aug.make_plan(S, S, boxes[i], draws) for i in range(B)]
+    assert any(p["patch"] and p["patch"]["expand"] for p in plans) and any(p["patch"] is None for p in plans)
+    o_img, o_boxes = aug.apply_plans(img, boxes, plans)
+    again, _ = aug.apply_plans(img, boxes, plans)
+    assert torch.equal(o_img, again), "augmentation must be deterministic"
+    o_img, o_boxes = o_img.cpu().numpy(), o_boxes.cpu().numpy()
+    for i in range(B):
+        g = int((boxes[i] != 0).any(-1).sum())
+        r_img, r_boxes = ao.apply(img[i], boxes[i, :g], plans[i])
+        np.testing.assert_allclose(o_img[i], r_img, rtol=0, atol=AUG_TOL, err_msg=f"image {i}: {plans[i]}")
+        np.testing.assert_allclose(o_boxes[i, :g], r_boxes, rtol=0, atol=1e-6)
+        assert not o_boxes[i, g:].any()
+    # the public call: reference signature, one example
+    one_img, one_boxes = aug.apply(img[0], boxes[0, :2], draws=aug.RandomDraws(5))
+    assert tuple(one_img.shape) == (S, S, 3) and tuple(one_boxes.shape) == (2, 4)
+    assert float(one_img.min()) >= 0.0 and float(one_img.max()) <= 1.0
+
+
 def _np(t):
     return t.detach().cpu().numpy()
 

@@ -554,12 +554,25 @@ def cond(pred, true_fn=None, false_fn=None, name=None):
 
 
 def pad(tensor, paddings, mode="CONSTANT", constant_values=0, name=None) -> Tensor:
+    """tf.pad, CONSTANT mode.  The reference's ``augmentation.expand_image`` (augmentation.py:191-195) passes a nested
+    tuple that mixes float32 scalar tensors (already rounded to whole numbers) with Python ints; the values are used as
+    whole pixel counts here.  [TF-recall] whether TensorFlow itself accepts float paddings is version dependent."""
     a = convert_to_tensor(tensor)._v
-    p = convert_to_tensor(paddings)._v.astype(np.int64)
     if mode.upper() != "CONSTANT":
         raise NotImplementedError(mode)
+
+    def whole(v):
+        f = _pyfloat(v._v) if isinstance(v, Tensor) else _pyfloat(v)
+        if f != int(f):
+            raise ValueError(f"padding {f} is not a whole number")
+        return int(f)
+
+    if isinstance(paddings, Tensor):
+        pads = [tuple(int(v) for v in r) for r in paddings._v.tolist()]
+    else:
+        pads = [(whole(lo), whole(hi)) for lo, hi in paddings]
     cv = convert_to_tensor(constant_values, dtype_hint=a.dtype)._v
-    return Tensor(np.pad(a, [tuple(r) for r in p.tolist()], mode="constant", constant_values=cv))
+    return Tensor(np.pad(a, pads, mode="constant", constant_values=cv))
 
 
 def slice(input_, begin, size, name=None) -> Tensor:       # noqa: A001

@@ -63,6 +63,8 @@ SIGNATURES = {
     "ssd_image_u8_to_f16c8": (i, [vp, vp, i64, vp]),
     "ssd_preprocess_image": (i, [vp, i, i, vp, i, i, i, vp]),
     "ssd_flip_boxes": (i, [vp, i, vp]),
+    "ssd_augment_workspace_bytes": (C.c_size_t, [i, i, i, i, i]),
+    "ssd_augment_batch": (i, [vp, vp, vp, i, i, i, i, i, i, vp, vp, C.c_size_t, vp]),
     "ssd_maxpool": (i, [vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),
     "ssd_l2norm": (i, [vp, vp, vp, i64, i, vp]),
     # training

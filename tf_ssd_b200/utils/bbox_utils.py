@@ -171,3 +171,28 @@ def generate_prior_boxes(feature_map_shapes: Sequence[int], aspect_ratios: Seque
 
 # north_star alias: the name does not exist in the reference snapshot.
 init_prior_boxes = generate_prior_boxes
+
+
+def renormalize_bboxes_with_min_max(bboxes: Any, min_max: Any):
+    """utils/bbox_utils.py:217-233: boxes re-expressed inside the window ``[y_min, x_min, y_max, x_max]`` and clipped to
+    [0, 1].  (``ssd_augment_batch`` applies the same arithmetic inside the fused augmentation kernels; this stand-alone
+    form serves the other call sites with a handful of boxes.)"""
+    b = _ffi.to_dev(bboxes)
+    mm = _ffi.to_dev(min_max).reshape(4)
+    lo = torch.stack([mm[0], mm[1], mm[0], mm[1]])
+    span = torch.stack([mm[2] - mm[0], mm[3] - mm[1], mm[2] - mm[0], mm[3] - mm[1]])
+    return torch.clamp((b - lo) / span, 0.0, 1.0)
+
+
+def normalize_bboxes(bboxes: Any, height: Any, width: Any):
+    """utils/bbox_utils.py:236-251: pixel corners -> normalised ``[y1, x1, y2, x2]``."""
+    b = _ffi.to_dev(bboxes)
+    scale = torch.tensor([float(height), float(width), float(height), float(width)], dtype=torch.float32, device=b.device)
+    return b / scale
+
+
+def denormalize_bboxes(bboxes: Any, height: Any, width: Any):
+    """utils/bbox_utils.py:254-269: normalised corners -> rounded pixel corners (``tf.round``: half to even)."""
+    b = _ffi.to_dev(bboxes)
+    scale = torch.tensor([float(height), float(width), float(height), float(width)], dtype=torch.float32, device=b.device)
+    return torch.round(b * scale)

@@ -24,20 +24,33 @@ class SyntheticVOC(object):
     def __init__(self, total_items: int, img_size: int = 300, seed: int = 0, max_boxes: int = 8):
         self.total_items, self.img_size, self.seed, self.max_boxes = int(total_items), int(img_size), int(seed), int(max_boxes)
         self._parts: List["SyntheticVOC"] = [self]
+        self._fns: List[Any] = []
+        self._limit = -1
+
+    def _view(self, total_items: int) -> "SyntheticVOC":
+        out = SyntheticVOC(total_items, self.img_size, self.seed, self.max_boxes)
+        out._parts, out._fns, out._limit = list(self._parts), list(self._fns), self._limit
+        return out
 
     def concatenate(self, other: "SyntheticVOC") -> "SyntheticVOC":
         out = SyntheticVOC(self.total_items + other.total_items, self.img_size, self.seed, self.max_boxes)
         out._parts = self._parts + other._parts
         return out
 
-    def map(self, fn) -> "SyntheticVOC":      # preprocessing is part of the generator (already resized / normalised)
-        return self
+    def map(self, fn) -> "SyntheticVOC":
+        """``tf.data.Dataset.map``: ``fn`` is applied to every example when the dataset is iterated."""
+        out = self._view(self.total_items)
+        out._fns.append(fn)
+        return out
 
     def shuffle(self, buffer_size: int) -> "SyntheticVOC":
+        """The synthetic stream is i.i.d. already: shuffling it changes nothing a training run can observe."""
         return self
 
     def take(self, n: int) -> "SyntheticVOC":
-        out = SyntheticVOC(min(n, self.total_items), self.img_size, self.seed, self.max_boxes)
+        """``tf.data.Dataset.take``: the first ``n`` examples (across concatenated parts)."""
+        out = self._view(min(int(n), self.total_items))
+        out._limit = out.total_items
         return out
 
     def _example(self, rng: np.random.Generator) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
@@ -53,10 +66,17 @@ class SyntheticVOC(object):
         return img, boxes, labels
 
     def __iter__(self) -> Iterator[Tuple[np.ndarray, np.ndarray, np.ndarray]]:
+        seen = 0
         for k, part in enumerate(self._parts):
             rng = np.random.default_rng(part.seed + 7919 * k)
             for _ in range(part.total_items):
-                yield part._example(rng)
+                if 0 <= self._limit <= seen:
+                    return
+                example = part._example(rng)
+                for fn in self._fns:
+                    example = fn(example)
+                seen += 1
+                yield example
 
     def padded_batch(self, batch_size: int, padded_shapes: Any = None, padding_values: Any = None, drop_remainder: bool = False):
         """``tf.data.Dataset.padded_batch`` (trainer.py:75-84): ragged ground truth padded to the batch maximum."""
@@ -66,13 +86,17 @@ class SyntheticVOC(object):
             def __iter__(self_inner):
                 imgs, boxes, labels = [], [], []
                 for img, b, l in ds:
-                    imgs.append(img); boxes.append(b); labels.append(l)
+                    imgs.append(_host(img)); boxes.append(_host(b)); labels.append(_host(l))
                     if len(imgs) == batch_size:
                         yield _pad(imgs, boxes, labels)
                         imgs, boxes, labels = [], [], []
                 if imgs and not drop_remainder:
                     yield _pad(imgs, boxes, labels)
         return _Batched()
+
+
+def _host(x: Any) -> np.ndarray:
+    return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
 
 
 def _pad(imgs, boxes, labels):
@@ -121,9 +145,29 @@ def get_custom_imgs(custom_image_path: str) -> List[str]:
 
 
 def preprocessing(image_data: Any, final_height: int, final_width: int, augmentation_fn: Any = None, evaluate: bool = False):
-    """utils/data_utils.py:12-38 resizes and normalises one TFDS example; the synthetic examples are already in
-    that form, so this is the identity (kept for the call sites of trainer.py:68-71 / predictor.py:69-71)."""
-    return image_data
+    """utils/data_utils.py:12-38 for one example -> ``(img, gt_boxes, gt_labels)``.
+
+    A TFDS-style example (``{"image": uint8 [H,W,3], "objects": {"bbox", "label", "is_difficult"}}``) goes through the
+    reference's steps: labels + 1 (:35), ``convert_image_dtype`` + ``resize`` on the device (:36-37,
+    ``ssd_preprocess_image``), the ``is_difficult`` filter when ``evaluate`` (:38-41), then ``augmentation_fn`` (:42-43).
+    The synthetic examples of ``get_dataset`` are ``(img, gt_boxes, gt_labels)`` tuples that are already resized and
+    normalised: only ``augmentation_fn`` applies to them.  (The fast path for training augments whole batches on the
+    device instead: ``train_utils.generator(..., augmentation_fn=augmentation.apply)``.)"""
+    if isinstance(image_data, dict):
+        objects = image_data["objects"]
+        gt_boxes = np.asarray(_host(objects["bbox"]), np.float32).reshape(-1, 4)
+        gt_labels = (np.asarray(_host(objects["label"])).astype(np.int64) + 1).astype(np.int32)
+        img = device_preprocess(image_data["image"], final_height=final_height, final_width=final_width)
+        if evaluate:
+            not_diff = np.logical_not(np.asarray(_host(objects["is_difficult"]), bool))
+            gt_boxes, gt_labels = gt_boxes[not_diff], gt_labels[not_diff]
+    else:
+        img, gt_boxes, gt_labels = image_data
+        if tuple(np.shape(img)[:2]) != (final_height, final_width):
+            raise ValueError(f"synthetic example is {np.shape(img)[:2]}, expected {(final_height, final_width)}")
+    if augmentation_fn is not None:
+        img, gt_boxes = augmentation_fn(img, gt_boxes)
+    return img, gt_boxes, gt_labels
 
 
 def get_data_types():

@@ -37,6 +37,7 @@ def handle_args(argv: Optional[Sequence[str]] = None) -> argparse.Namespace:
         (("--train-items",), dict(type=int, default=0, help="synthetic items per epoch (0: dataset default)")),
         (("--val-items",), dict(type=int, default=0)),
         (("--model-dir",), dict(default="trained")),
+        (("--no-augmentation",), dict(action="store_true", help="skip augmentation.apply on the training batches")),
     ]
     for flags, kw in options:
         parser.add_argument(*flags, **kw)

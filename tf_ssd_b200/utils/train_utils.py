@@ -63,10 +63,15 @@ def get_step_size(total_items: int, batch_size: int) -> int:
     return math.ceil(total_items / batch_size)
 
 
-def generator(dataset: Any, prior_boxes: Any, hyper_params: Dict[str, Any]) -> Iterator[Tuple[Any, Tuple[Any, Any]]]:
-    """utils/train_utils.py:84-100 -- infinite ``(img, (deltas, labels))`` feed."""
+def generator(dataset: Any, prior_boxes: Any, hyper_params: Dict[str, Any],
+              augmentation_fn: Any = None) -> Iterator[Tuple[Any, Tuple[Any, Any]]]:
+    """utils/train_utils.py:84-100 -- infinite ``(img, (deltas, labels))`` feed.  ``augmentation_fn`` (e.g.
+    ``tf_ssd_b200.augmentation.apply``) transforms each padded BATCH on the device before the targets are matched: the
+    batched form of the per-example ``augmentation_fn`` the reference maps over its ``tf.data`` pipeline (trainer.py:68)."""
     while True:
         for img, gt_boxes, gt_labels in dataset:
+            if augmentation_fn is not None:
+                img, gt_boxes = augmentation_fn(img, gt_boxes)
             actual_deltas, actual_labels = calculate_actual_outputs(prior_boxes, gt_boxes, gt_labels, hyper_params)
             yield img, (actual_deltas, actual_labels)
 

@@ -29,6 +29,19 @@ for what in "$@"; do
       python tools/ncu_traffic.py $OUT/conv_${tag}_raw.csv $OUT/traffic_$tag.json > /dev/null 2>&1
       rm -f $OUT/conv_$tag.ncu-rep
       ;;
+    train)
+      # the training kernels of one MobileNetV2 step (BatchNorm fwd/bwd, depthwise gradients, tcgen05 wgrad, loss bwd, Adam);
+      # one pass per kernel family so that each gets a sample from the middle of the network
+      : > $OUT/train_${tag}_summary.csv
+      for fam in "bn_:24:40" "dw_dgrad|dw_wgrad:16:8" "conv_wgrad:16:10" "adam_multi|loss_bwd|loss_anchor|loss_select:6:0"; do
+        re=${fam%%:*}; rest=${fam#*:}; cnt=${rest%%:*}; skip=${rest#*:}
+        ncu --set full --clock-control none --import-source on -k regex:"$re" -c $cnt --launch-skip $skip \
+            -o $OUT/train_$tag python tools/train_bench.py --backbone mobilenet_v2 --breakdown > $OUT/train_$tag.log 2>&1
+        ncu -i $OUT/train_$tag.ncu-rep --page raw --csv > $OUT/train_${tag}_raw.csv 2>/dev/null
+        python tools/ncu_summary.py $OUT/train_${tag}_raw.csv >> $OUT/train_${tag}_summary.csv 2>&1
+        rm -f $OUT/train_$tag.ncu-rep $OUT/train_${tag}_raw.csv
+      done
+      ;;
   esac
 done
 ls -la $OUT; du -sh $OUT

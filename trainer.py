@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from tf_ssd_b200 import dist_utils                                                    # noqa: E402
+from tf_ssd_b200 import augmentation, dist_utils                                                    # noqa: E402
 from tf_ssd_b200.models.train_engine import Adam, LearningRateScheduler, ModelCheckpoint   # noqa: E402
 from tf_ssd_b200.ssd_loss import CustomLoss                                            # noqa: E402
 from tf_ssd_b200.utils import bbox_utils, data_utils, io_utils, train_utils            # noqa: E402
@@ -77,7 +77,9 @@ def main(argv=None):
     if load_weights:
         ssd_model.load_weights(ssd_model_path)
     prior_boxes = bbox_utils.generate_prior_boxes(hyper_params["feature_map_shapes"], hyper_params["aspect_ratios"])
-    ssd_train_feed = train_utils.generator(train_data, prior_boxes, hyper_params)
+    # trainer.py:68 maps augmentation.apply over the examples; here every padded batch is augmented on the device
+    augmentation_fn = None if args.no_augmentation else augmentation.apply
+    ssd_train_feed = train_utils.generator(train_data, prior_boxes, hyper_params, augmentation_fn=augmentation_fn)
     ssd_val_feed = train_utils.generator(val_data, prior_boxes, hyper_params)
 
     callbacks = [LearningRateScheduler(train_utils.scheduler)]
