@@ -252,6 +252,13 @@ int ssd_irblock_supported(const ssd_irblock_desc* h_desc);
 /* Debug aid, not a reference interface: d_buf = device buffer of 5 x 512 uint64 that CTA 0 of later ssd_irblock
  * launches fills with per-role (globaltimer << 8 | tag) stamps (tools/trace_irblock.py); NULL switches it off. */
 int ssd_irblock_trace(void* d_buf);
+/* Debug aid: the tile geometry the planner picks for a block, without launching (h_out16 = bw, bh, bb, pw, ph, P, halves,
+ * n_tiles, n_e, kc_in, wexp_stages, n_patch, out_bufs, quad, dw_R, smem_bytes). */
+int ssd_irblock_plan(const ssd_irblock_desc* h_desc, int32_t* h_out16);
+/* The same aid for ssd_dwproj (roles: 0 TMA, 1 MMA, 2 depthwise, 3 epilogue) and the per-image pass of ssd_decode_nms /
+ * ssd_combined_nms (role 0: phase boundaries of image 0): d_buf = device buffer of 8 x 512 uint64
+ * (tools/trace_kernel.py); NULL switches it off. */
+int ssd_debug_trace(void* d_buf);
 
 /* MobileNetV2 stem: keras_applications Conv1_pad + Conv1 (3x3, stride 2, Cin = 3) + bn_Conv1 +
  * Conv1_relu (models/ssd_mobilenet_v2.py:25), computed straight from the fp32 NHWC image

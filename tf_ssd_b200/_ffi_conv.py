@@ -57,6 +57,8 @@ SIGNATURES = {
     "ssd_irblock": (i, [C.POINTER(IrBlockDesc), vp]),
     "ssd_irblock_supported": (i, [C.POINTER(IrBlockDesc)]),
     "ssd_irblock_trace": (i, [vp]),
+    "ssd_irblock_plan": (i, [C.POINTER(IrBlockDesc), C.POINTER(C.c_int32)]),
+    "ssd_debug_trace": (i, [vp]),
     "ssd_stem_conv3x3s2": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
     "ssd_stem_conv3x3s2_u8": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
     "ssd_image_to_f16c8": (i, [vp, vp, i64, vp]),

@@ -362,8 +362,20 @@ match_encode_kernel(const float4* __restrict__ priors, const float4* __restrict_
                 while (mask) {
                     const int gg = g0 + __ffs(mask) - 1;
                     mask &= mask - 1;
-                    float v = iou_ref(p, pa, s_gt[gg], s_area[gg]);
-                    if (v > best) { best = v; idx = gg; }          // ascending g: first maximum wins (:124)
+                    // iou_ref's intersection / union, with the division only when the quotient can exceed `best`:
+                    // inter / uni > best needs inter > best * uni; the test keeps a 2^-17 relative margin (far above
+                    // the one-ulp roundings of the product), so every candidate that could win the strict ">" is
+                    // still divided exactly like the reference does and the arg-max is unchanged.  (uni <= 0 or NaN
+                    // -- inverted ground-truth boxes -- fail or pass the test consistently with v > best: 0 > 0 is
+                    // false either way, a negative bound sends the pair to the exact path.)
+                    const float4 q = s_gt[gg];
+                    const float inter = fmul(fmaxf(fsub(fminf(p.w, q.w), fmaxf(p.y, q.y)), 0.0f),
+                                             fmaxf(fsub(fminf(p.z, q.z), fmaxf(p.x, q.x)), 0.0f));
+                    const float uni = fsub(fadd(pa, s_area[gg]), inter);
+                    if (inter > fmul(fmul(best, uni), 0.99999f)) {
+                        const float v = fdiv(inter, uni);
+                        if (v > best) { best = v; idx = gg; }      // ascending g: first maximum wins (:124)
+                    }
                 }
             }
         } else {                                                   // degenerate anchors: plain scan (0/0 = NaN semantics)

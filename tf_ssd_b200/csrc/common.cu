@@ -32,6 +32,10 @@ bool pdl_enabled() {
     return v == 1;
 }
 
+static unsigned long long* g_debug_trace = nullptr;
+unsigned long long* debug_trace_buffer() { return g_debug_trace; }
+void set_debug_trace_buffer(unsigned long long* p) { g_debug_trace = p; }
+
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 0;
     int dev = 0;
@@ -46,6 +50,12 @@ int sm_count() {
 }
 
 }  // namespace ssd
+
+namespace ssd { void set_debug_trace_buffer(unsigned long long* p); }
+extern "C" int ssd_debug_trace(void* d_buf) {
+    ssd::set_debug_trace_buffer(static_cast<unsigned long long*>(d_buf));
+    return SSD_OK;
+}
 
 extern "C" int ssd_abi_version(void) { return SSD_B200_ABI_VERSION; }
 

@@ -33,6 +33,19 @@ static inline cudaStream_t as_stream(ssd_stream_t s) { return reinterpret_cast<c
 
 int sm_count();      // cached multiProcessorCount of the current device
 
+// Debug tracing (ssd_debug_trace, tools/trace_kernel.py): when a device buffer is registered, CTA 0 of the instrumented
+// kernels records (globaltimer << 8 | tag) stamps, 8 roles x 512 slots; nullptr (the default) compiles to one
+// predictable branch per stamp.
+unsigned long long* debug_trace_buffer();
+__device__ __forceinline__ void trace_stamp(unsigned long long* trace, int role, int& slot, int tag) {
+    if (trace && blockIdx.x == 0 && blockIdx.y == 0 && slot < 512) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        trace[role * 512 + slot] = (t << 8) | (unsigned long long)(tag & 0xff);
+        ++slot;
+    }
+}
+
 // ---- programmatic dependent launch (PDL) -------------------------------------
 // Consecutive kernels of a plan are launched with programmatic stream serialisation:
 // kernel N+1 may start its prologue (barrier init, TMEM allocation, descriptor

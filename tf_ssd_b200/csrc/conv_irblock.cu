@@ -7,15 +7,18 @@
 // (tile + halo) is loaded once by TMA, and for every 64-channel slice of the expanded tensor
 //
 //   warp 1      tcgen05.mma   D1[patch positions x 64] = patch[positions x Cin] * Wexp[64 x Cin]^T       (TMEM)
-//   warps 2-9   "mid":        D1 -> + bias, ReLU6, zero outside the image (the depthwise padding) -> fp16 -> the
+//   warps 4-11  "mid":        D1 -> + bias, ReLU6, zero outside the image (the depthwise padding) -> fp16 -> the
 //                             128-byte-swizzled expanded patch in shared memory
-//   warps 10-19 depthwise:    3x3 taps from that patch (packed half2 FMAs, sliding window), + bias, ReLU6 -> the K-major
+//   warps 12-19 depthwise:    3x3 taps from that patch (packed half2 FMAs, sliding window), + bias, ReLU6 -> the K-major
 //                             A operand tile of the projection
 //   warp 1      tcgen05.mma   D2[128 pixels x Cout] += A2[128 x 64] * Wproj[Cout x 64]^T                  (TMEM)
+//   warps 20-23 epilogue:     D2 -> bias / residual -> fp16 -> swizzled staging tile -> TMA store
 //
 // run as a software pipeline (double-buffered D1, expanded patch, A2 and weight slices; mbarrier hand-offs), so the
-// expand MMA and mid stage of slice e+1 overlap the depthwise stage of slice e.  Warp 0 is the TMA producer; warps 2-9
-// also run the final epilogue (D2 -> bias / residual -> fp16 -> swizzled staging tile -> TMA store).
+// expand MMA and mid stage of slice e+1 overlap the depthwise stage of slice e.  Warp 0 is the TMA producer; warps 2-3
+// only pad the first warpgroup.  Roles sit on warpgroup boundaries so that setmaxnreg can move registers from the
+// scheduler / epilogue warpgroups to the depthwise warpgroups (the stage that bounds the kernel): 56 / 80 / 104 / 56
+// registers per thread instead of a uniform 80 with spills inside the depthwise loop.
 //
 // HBM traffic per block: input once (+ halo), weights (L2-resident), output once -- against input + 2 x expanded + output
 // for the layer-by-layer path.  The halo's expand work is recomputed per tile; the tensor pipe is otherwise idle here.
@@ -26,10 +29,19 @@
 
 namespace ssd {
 
-constexpr int IR_MID_WARPS = 8;                     // warps 2..9
-constexpr int IR_DW_WARPS = 10;                     // warps 10..19
-constexpr int IR_EPI_WARPS = 4;                     // warps 20..23: final epilogue (one per TMEM lane quarter)
-constexpr int IR_THREADS = 64 + 32 * (IR_MID_WARPS + IR_DW_WARPS + IR_EPI_WARPS);      // 768
+constexpr int IR_MID_WARP0 = 4;                     // warpgroup 0: warp 0 TMA, warp 1 MMA, warps 2-3 idle
+constexpr int IR_MID_WARPS = 8;                     // warps 4..11   (warpgroups 1-2)
+constexpr int IR_DW_WARP0 = IR_MID_WARP0 + IR_MID_WARPS;
+constexpr int IR_DW_WARPS = 8;                      // warps 12..19  (warpgroups 3-4)
+constexpr int IR_EPI_WARP0 = IR_DW_WARP0 + IR_DW_WARPS;
+constexpr int IR_EPI_WARPS = 4;                     // warps 20..23: final epilogue (one per TMEM lane quarter; warpgroup 5)
+constexpr int IR_THREADS = 32 * (IR_EPI_WARP0 + IR_EPI_WARPS);                         // 768
+// setmaxnreg moves registers inside the CTA's OWN pool (threads x launch registers = 768 x 80), not the whole register
+// file: the per-warpgroup budgets must sum to at most 6 x 80 or the increase never completes.
+constexpr int IR_REGS_LAUNCH = 80, IR_REGS_SCHED = 56, IR_REGS_DW = 104, IR_REGS_EPI = 56;   // mid keeps the launch value
+static_assert(IR_MID_WARP0 % 4 == 0 && IR_DW_WARP0 % 4 == 0 && IR_EPI_WARP0 % 4 == 0, "roles must start on warpgroup boundaries");
+static_assert(IR_REGS_SCHED + 2 * IR_REGS_LAUNCH + 2 * IR_REGS_DW + IR_REGS_EPI <= 6 * IR_REGS_LAUNCH, "CTA register pool");
+static_assert(IR_THREADS * IR_REGS_LAUNCH <= 65536 && IR_THREADS * (IR_REGS_LAUNCH + 8) > 65536, "launch registers = 80");
 
 constexpr uint32_t IR_D2_COL = 256;                 // TMEM: D1[buf][half] at buf*128 + half*64, D2 at 256
 constexpr uint32_t IR_TMEM_COLS = 512;
@@ -224,6 +236,10 @@ conv_irblock_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();
 
+    // Register re-allocation per warpgroup (setmaxnreg at the top of each role's branch, so that ptxas allocates every
+    // role against its own budget): warpgroups 0 and 5 release, the depthwise warpgroups wait for the freed registers.
+    if (warp < IR_MID_WARP0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(IR_REGS_SCHED));
     if (warp == 0) {
         // ===================== TMA producer =====================
         // Four independent streams -- input patches, expansion weight slices, depthwise filter slices, projection weight
@@ -331,42 +347,63 @@ conv_irblock_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
                 }
             }
         }
-    } else if (warp >= 2 + IR_MID_WARPS && warp < 2 + IR_MID_WARPS + IR_DW_WARPS) {
+    }
+    } else if (warp >= IR_DW_WARP0 && warp < IR_EPI_WARP0) {
         // ===================== depthwise 3x3 from the expanded patch =====================
-        const int pt = (int)threadIdx.x - 32 * (2 + IR_MID_WARPS);
-        const int j = pt & 7, rg = pt >> 3;                      // 16-byte channel chunk, row group (0..39)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(IR_REGS_DW));
+        const int pt = (int)threadIdx.x - 32 * IR_DW_WARP0;
+        const int j = pt & 7, rg = pt >> 3;                      // 16-byte channel chunk, row group (0..31)
         const int st = p.stride, pw = p.pw, php = p.ph;
         const int box_rows = min(p.bw * p.bh * p.bb, TC_BM);
         const int quad = p.quad;
-        // rows owned by this thread: rg + 40 i, or in quad mode the 4 horizontally adjacent pixels 4 rg + i
+        // rows owned by this thread: rg + 32 i, or in quad mode the 4 horizontally adjacent pixels 4 rg + i
         int q0[4];                                               // patch position of tap (0,0); 0 for rows that do not exist
-        int rrow[4];                                             // tile row, -1: does not exist
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int r = quad ? 4 * rg + i : rg + 4 * IR_DW_WARPS * i;
             if (r < box_rows) {
                 const int dx = r % p.bw, qq = r / p.bw, dy = qq % p.bh, db = qq / p.bh;
                 q0[i] = dx * st + pw * (dy * st + php * db);
-                rrow[i] = r;
             } else {
                 q0[i] = 0;
-                rrow[i] = -1;
+            }
+        }
+        // A last slice with <= 32 live channels (Cexp = 96, 144, ...) gets its own mapping: only the live 16-byte
+        // chunks are spread over the threads (2^sh of them), so every thread owns fewer tile rows; no sliding window.
+        const int last_live = (p.Cexp - (p.n_e - 1) * 64 + 7) >> 3;                      // live chunks of the last slice
+        const int sh = last_live > 4 ? 3 : last_live > 2 ? 2 : last_live > 1 ? 1 : 0;
+        const bool remap = sh < 3;
+        const int jB = pt & ((1 << sh) - 1), rgB = pt >> sh, nrgB = (32 * IR_DW_WARPS) >> sh;
+        const int RB = (box_rows + nrgB - 1) / nrgB;                                     // 1..4
+        int q0B[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = rgB + nrgB * i;
+            if (remap && r < box_rows) {
+                const int dx = r % p.bw, qq = r / p.bw, dy = qq % p.bh, db = qq / p.bh;
+                q0B[i] = dx * st + pw * (dy * st + php * db);
+            } else {
+                q0B[i] = 0;
             }
         }
         const __half2 lo2 = __float2half2_rn(p.dw_act == SSD_ACT_NONE ? -65504.0f : 0.0f);
         const __half2 hi2 = __float2half2_rn(p.dw_act == SSD_ACT_RELU6 ? 6.0f : 65504.0f);
         const uint32_t sEp32 = smem_addr(sEp), sA232 = smem_addr(sA2), sBiasD32 = smem_addr(sBiasD);
         const int R = p.dw_R;
+        // the chunks of A2 no thread of the second mapping writes must still hold finite values (they meet zero weights)
+        for (int i = pt; i < 2 * 16384 / 16; i += 32 * IR_DW_WARPS) sts128(sA232 + (uint32_t)i * 16u, make_uint4(0u, 0u, 0u, 0u));
         int it = 0, tslot = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
             for (int e = 0; e < p.n_e; ++e, ++it) {
                 const int b = it & 1;
                 const uint32_t par = (uint32_t)(it >> 1) & 1u;
-                const bool cok = e * 64 + j * 8 < p.Cexp;
+                const bool alt = remap && e == p.n_e - 1;                 // warp-uniform: second mapping
+                const int jj = alt ? jB : j;
+                const bool cok = e * 64 + jj * 8 < p.Cexp;
                 __half2 bias4[4];
                 {
-                    const float4 b0 = lds_f4(sBiasD32 + (uint32_t)(e * 64 + j * 8) * 4u);
-                    const float4 b1 = lds_f4(sBiasD32 + (uint32_t)(e * 64 + j * 8 + 4) * 4u);
+                    const float4 b0 = lds_f4(sBiasD32 + (uint32_t)(e * 64 + jj * 8) * 4u);
+                    const float4 b1 = lds_f4(sBiasD32 + (uint32_t)(e * 64 + jj * 8 + 4) * 4u);
                     bias4[0] = __floats2half2_rn(b0.x, b0.y); bias4[1] = __floats2half2_rn(b0.z, b0.w);
                     bias4[2] = __floats2half2_rn(b1.x, b1.y); bias4[3] = __floats2half2_rn(b1.z, b1.w);
                 }
@@ -377,7 +414,13 @@ conv_irblock_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
                 // Arithmetic: packed half2 FMAs; the nine products of an output are summed in fp16 -- the storage format
                 // the result is rounded to for the tensor-core operand -- starting from the fp16-rounded bias.
                 __half2 acc[4][4];
-                if (quad)        ir_depthwise<4, true>(patch, wsm, j, pw, q0, bias4, acc);
+                if (alt) {
+                    if (RB == 1)      ir_depthwise<1, false>(patch, wsm, jB, pw, q0B, bias4, acc);
+                    else if (RB == 2) ir_depthwise<2, false>(patch, wsm, jB, pw, q0B, bias4, acc);
+                    else if (RB == 3) ir_depthwise<3, false>(patch, wsm, jB, pw, q0B, bias4, acc);
+                    else              ir_depthwise<4, false>(patch, wsm, jB, pw, q0B, bias4, acc);
+                }
+                else if (quad)   ir_depthwise<4, true>(patch, wsm, j, pw, q0, bias4, acc);
                 else if (R == 1) ir_depthwise<1, false>(patch, wsm, j, pw, q0, bias4, acc);
                 else if (R == 2) ir_depthwise<2, false>(patch, wsm, j, pw, q0, bias4, acc);
                 else if (R == 3) ir_depthwise<3, false>(patch, wsm, j, pw, q0, bias4, acc);
@@ -387,14 +430,15 @@ conv_irblock_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
                 const uint32_t a_tile = sA232 + (uint32_t)b * 16384u;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    if (i < (quad ? 4 : R) && rrow[i] >= 0) {
+                    const int row = alt ? rgB + nrgB * i : quad ? 4 * rg + i : rg + 4 * IR_DW_WARPS * i;
+                    if (i < (alt ? RB : quad ? 4 : R) && row < box_rows) {
                         uint4 o = make_uint4(0u, 0u, 0u, 0u);
                         if (cok) {
                             __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
                             for (int c2 = 0; c2 < 4; ++c2) oh[c2] = __hmin2(__hmax2(acc[i][c2], lo2), hi2);
                         }
-                        sts128(a_tile + sw_off(rrow[i], j), o);
+                        sts128(a_tile + sw_off(row, jj), o);
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic writes -> visible to the MMA / TMA
@@ -403,13 +447,14 @@ conv_irblock_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
                 if (pt == 0) ir_stamp(p, 2, tslot, 3);
             }
         }
-    } else if (warp >= 2 + IR_MID_WARPS + IR_DW_WARPS) {
+    } else if (warp >= IR_EPI_WARP0) {
         // ===================== final epilogue: warps 20..23, one per TMEM lane quarter =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(IR_REGS_EPI));
         // D2 -> bias / residual -> fp16 -> swizzled staging tile -> TMA store; both 32-column halves of a 64-channel group
         // are handled by the same thread.  Off the critical path: it only has to keep up with one tile per n_e slices.
         const int q = warp & 3;
         const int r = q * 32 + lane;
-        const bool elected = warp == 2 + IR_MID_WARPS + IR_DW_WARPS && lane == 0;
+        const bool elected = warp == IR_EPI_WARP0 && lane == 0;
         const float act_lo = p.act == SSD_ACT_NONE ? -__int_as_float(0x7f800000) : 0.0f;
         const float act_hi = p.act == SSD_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
         const long long pix0 = p.Cout, img0 = (long long)p.Ho * p.Wo * p.Cout;
@@ -484,16 +529,18 @@ conv_irblock_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
         }
         if (elected) bulk_wait_all();
     } else {
-        // ===================== mid (D1 -> expanded patch): warps 2..9 =====================
-        const int mw = warp - 2;
+        // ===================== mid (D1 -> expanded patch): warps 4..11 =====================
+        const int mw = warp - IR_MID_WARP0;
         const int q = warp & 3;                                  // TMEM lane quarter this warp may read
         const int half = mw >> 2;                                // which 128-row half of the patch
         const int r = q * 32 + lane;                             // row inside a 128-row accumulator
         const int pos = half * 128 + r;                          // patch position handled by this thread
         const bool pos_live = half < p.halves && pos < p.P;
         const int px = pos % p.pw, prr = pos / p.pw, py = prr % p.ph, pdb = prr / p.ph;
-        const float e_lo = p.exp_act == SSD_ACT_NONE ? -__int_as_float(0x7f800000) : 0.0f;
-        const float e_hi = p.exp_act == SSD_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
+        // the activation clamps AFTER the conversion to fp16 (0 and 6 are exact in fp16 and rounding is monotone, so
+        // clamp(round(v)) == round(clamp(v))): two packed HMNMX2 per two values instead of four FMNMX
+        const __half2 e_lo2 = __float2half2_rn(p.exp_act == SSD_ACT_NONE ? -65504.0f : 0.0f);
+        const __half2 e_hi2 = __float2half2_rn(p.exp_act == SSD_ACT_RELU6 ? 6.0f : 65504.0f);
         const uint32_t sEp32 = smem_addr(sEp), sBiasE32 = smem_addr(sBiasE);
         int it = 0, tslot = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
@@ -515,7 +562,8 @@ conv_irblock_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
                 const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)db * 128u + (uint32_t)half * 64u;
                 const uint32_t keep = inside ? 0xffffffffu : 0u;  // positions outside the image: zeros (depthwise padding)
 #pragma unroll
-                for (int part = 0; part < 2; ++part) {           // 32 columns at a time (register budget: 640 threads)
+                for (int part = 0; part < 2; ++part) {           // 32 columns at a time (register budget: 80 per thread)
+                    if (part == 1 && e * 64 + 32 >= p.Cexp) continue;      // dead half of a partial last slice: never read
                     uint32_t acc[32];
                     if (half < p.halves) {                       // warp-uniform
                         tmem_ld32(trow + (uint32_t)part * 32u, acc);
@@ -526,14 +574,13 @@ conv_irblock_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __g
                         const float4 b0v = lds_f4(be + (uint32_t)(part * 32 + h * 8) * 4u);
                         const float4 b1v = lds_f4(be + (uint32_t)(part * 32 + h * 8 + 4) * 4u);
                         const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
-                        float v[8];
-#pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            v[c] = fminf(fmaxf(__uint_as_float(acc[h * 8 + c]) + bb[c], e_lo), e_hi);
                         uint4 o;
                         __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) oh[c] = __floats2half2_rn(v[2 * c], v[2 * c + 1]);
+                        for (int c = 0; c < 4; ++c)
+                            oh[c] = __hmin2(__hmax2(__floats2half2_rn(__uint_as_float(acc[h * 8 + 2 * c]) + bb[2 * c],
+                                                                      __uint_as_float(acc[h * 8 + 2 * c + 1]) + bb[2 * c + 1]),
+                                                    e_lo2), e_hi2);
                         o.x &= keep; o.y &= keep; o.z &= keep; o.w &= keep;
                         if (pos_live) sts128(row + sw_off(pos, part * 4 + h), o);
                     }
@@ -739,6 +786,20 @@ extern "C" int ssd_irblock(const ssd_irblock_desc* d, ssd_stream_t stream) {
 // buffer the call also prints the tile geometry the planner chose.
 extern "C" int ssd_irblock_trace(void* d_buf) {
     ssd::g_ir_trace = static_cast<unsigned long long*>(d_buf);
+    return SSD_OK;
+}
+
+// Debug only: the tile geometry the planner picks for a block (no launch, no device needed).
+// out = {bw, bh, bb, pw, ph, P, halves, n_tiles, n_e, kc_in, wexp_stages, n_patch, out_bufs, quad, dw_R, smem_bytes}
+extern "C" int ssd_irblock_plan(const ssd_irblock_desc* d, int32_t* h_out16) {
+    SSD_REQUIRE_PTR(d); SSD_REQUIRE_PTR(h_out16);
+    ssd::IrParams p;
+    memset(&p, 0, sizeof(p));
+    size_t smem = 0;
+    if (!ssd::irblock_plan(d, &p, &smem)) return SSD_ERR_UNSUPPORTED;
+    const int v[16] = {p.bw, p.bh, p.bb, p.pw, p.ph, p.P, p.halves, p.n_tiles, p.n_e, p.kc_in, p.wexp_stages, p.n_patch,
+                       p.out_bufs, p.quad, p.dw_R, (int)smem};
+    for (int i = 0; i < 16; ++i) h_out16[i] = v[i];
     return SSD_OK;
 }
 

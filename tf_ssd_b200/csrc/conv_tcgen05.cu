@@ -274,10 +274,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 //   warp 0      TMA: per k-block (64 expanded channels) the INPUT PATCH of the tile -- (bw-1)s+3 x (bh-1)s+3 x bb
 //               positions x 64 channels, one 4-D box, zero-filled outside the image (= the convolution padding) --
 //               and the 1x1 weight tile B;
-//   warps 10-19 depthwise: 3x3 taps from the swizzled patch in shared memory, + bias, activation, fp16, written
+//   warps 12-19 depthwise: 3x3 taps from the swizzled patch in shared memory, + bias, activation, fp16, written
 //               straight into the 128-byte-swizzled K-major A tile the UMMA descriptor expects;
 //   warp 1      tcgen05.mma into double-buffered TMEM accumulators;
-//   warps 2-9   epilogue: bias / activation / residual -> swizzled staging tile -> TMA store (as conv_tcgen05_kernel).
+//   warps 4-11  epilogue: bias / activation / residual -> swizzled staging tile -> TMA store (as conv_tcgen05_kernel).
 //
 // The expanded activation is read from L2/HBM exactly once (by TMA, fully asynchronous, prefetched dw_pstages deep)
 // and the depthwise output never exists in global memory.
@@ -333,10 +333,14 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
     pdl_wait();
     const int per_img = p.tiles_w * p.tiles_h;
 
+    // setmaxnreg at the top of each role's branch: the scheduler and epilogue warpgroups release registers, the depthwise
+    // warpgroups (the stage that bounds the kernel) take them -- no spills inside the depthwise loop
+    if (warp < TC_DW_EPI_WARP0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_DW_REGS_SCHED));
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            int it = 0, s = 0, ps = 0;
+            int it = 0, s = 0, ps = 0, tslot = 0;
             uint32_t ph = 0, pph = 0;
             for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
                 const int tb = t / per_img, tr = t - tb * per_img;
@@ -344,6 +348,7 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
                 const int b0 = tb * p.bb, oy0 = th * p.bh, ox0 = tw * p.bw;
                 for (int kb = 0; kb < p.n_kblocks; ++kb, ++it) {
                     if (it >= p.dw_pstages) mbar_wait(bar_pempty + 8 * ps, pph ^ 1u);
+                    trace_stamp(p.trace, 0, tslot, 1);
                     mbar_expect_tx(bar_pfull + 8 * ps, p.dw_patch_bytes + 9 * 128);
                     tma_load_4d(smem_addr(sP + (size_t)ps * p.dw_patch_stage), &map_x, bar_pfull + 8 * ps, kb * TC_BK,
                                 ox0 * p.dw_stride - p.dw_pad_l, oy0 * p.dw_stride - p.dw_pad_t, b0);
@@ -361,15 +366,17 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            int j = 0, s = 0;
+            int j = 0, s = 0, tslot = 0;
             uint32_t ph = 0;
             for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++j) {
                 const int a = j & 1;
                 if (j >= 2) mbar_wait(bar_tempty + 8 * a, ((j >> 1) - 1) & 1);
+                trace_stamp(p.trace, 1, tslot, 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tacc = tmem_base + (uint32_t)a * p.acc_cols;
                 for (int kb = 0; kb < p.n_kblocks; ++kb) {
                     mbar_wait(bar_full + 8 * s, ph);
+                    trace_stamp(p.trace, 1, tslot, 2);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint64_t da = umma_desc_sw128(smem_addr(sA + (size_t)s * a_stage));
                     const uint64_t db = umma_desc_sw128(smem_addr(sB + (size_t)s * b_pitch));
@@ -382,15 +389,17 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
                 umma_commit(bar_tfull + 8 * a);
             }
         }
-    } else if (warp >= 2 + TC_EPI_WARPS) {
+    }
+    } else if (warp >= TC_DW_WARP0) {
         // ===================== depthwise 3x3 from the shared-memory patch =====================
-        const int pt = (int)threadIdx.x - 32 * (2 + TC_EPI_WARPS);
-        const int j = pt & 7, rg = pt >> 3;                      // 16-byte channel chunk, row group (0..39)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_DW_REGS_DW));
+        const int pt = (int)threadIdx.x - 32 * TC_DW_WARP0;
+        const int j = pt & 7, rg = pt >> 3;                      // 16-byte channel chunk, row group (0..31)
         const int C8 = p.dw_C8, st = p.dw_stride, pw = p.dw_pw, php = p.dw_ph;
         const float lo = p.dw_act == SSD_ACT_NONE ? -__int_as_float(0x7f800000) : 0.0f;
         const float hi = p.dw_act == SSD_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
         const int box_rows = p.bw * p.bh * p.bb;
-        // rows owned by this thread: strided (rg + 40 i) or, in quad mode, 4 horizontally adjacent pixels (4 rg + i)
+        // rows owned by this thread: strided (rg + 32 i) or, in quad mode, 4 horizontally adjacent pixels (4 rg + i)
         const int quad = p.dw_quad;
         int q0[TC_DW_ROWS];                                      // patch position of tap (0,0) per owned row; -1: padding row
 #pragma unroll
@@ -406,7 +415,7 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
         // Arithmetic: packed half2 FMAs (4 per tap and row instead of 16 conversions + 8 FMAs).  The nine products of
         // an output are summed in fp16 -- the same storage format the result is rounded to for the tensor-core
         // operand -- starting from the fp16-rounded bias; the 1x1 projection accumulates in fp32 as everywhere else.
-        int s = 0, ps = 0, it = 0;
+        int s = 0, ps = 0, it = 0, tslot = 0;
         uint32_t ph = 0, pph = 0;
         const bool has_bias = p.dw_bias != nullptr;
         auto load_bias = [&](int kb, __half2 (&b4)[4]) {
@@ -432,6 +441,7 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
                     for (int e = 0; e < 4; ++e) acc[i][e] = bias_next[e];
                 load_bias(kb + 1 < p.n_kblocks ? kb + 1 : 0, bias_next);              // in flight during this k-block
                 mbar_wait(bar_pfull + 8 * ps, pph);                                   // patch + filter landed
+                if (pt == 0) trace_stamp(p.trace, 2, tslot, 1);
                 const unsigned char* patch = sP + (size_t)ps * p.dw_patch_stage;
                 const unsigned char* wsm = patch + p.dw_patch_stage - 2048;
                 if (quad) {
@@ -481,7 +491,9 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
                         }
                     }
                 }
+                if (pt == 0) trace_stamp(p.trace, 2, tslot, 2);
                 if (it >= TC_DW_ASTAGES) mbar_wait(bar_empty + 8 * s, ph ^ 1u);         // A slot drained by the MMA
+                if (pt == 0) trace_stamp(p.trace, 2, tslot, 3);
                 unsigned char* a_tile = sA + (size_t)s * a_stage;
 #pragma unroll
                 for (int i = 0; i < TC_DW_ROWS; ++i) {
@@ -495,16 +507,20 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
                     }
                     *reinterpret_cast<uint4*>(a_tile + r * 128 + ((j ^ (r & 7)) << 4)) = o;
                 }
+                if (pt == 0) trace_stamp(p.trace, 2, tslot, 5);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic-proxy writes -> visible to the MMA
+                if (pt == 0) trace_stamp(p.trace, 2, tslot, 6);
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(bar_full + 8 * s); mbar_arrive(bar_pempty + 8 * ps); }
+                if (pt == 0) trace_stamp(p.trace, 2, tslot, 4);
                 if (++s == TC_DW_ASTAGES) { s = 0; ph ^= 1u; }
                 if (++ps == p.dw_pstages) { ps = 0; pph ^= 1u; }
             }
         }
     } else {
         // ===================== epilogue (8 warps): TMEM -> bias/act/residual -> swizzled tile -> TMA store =====================
-        const int ew = warp - 2;
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_DW_REGS_EPI));
+        const int ew = warp - TC_DW_EPI_WARP0;
         const int q = warp & 3;
         const int half = ew >> 2;
         const int r = q * 32 + lane;
@@ -515,11 +531,13 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
             const int i = ew * 32 + lane;                        // bias of the (single) N tile, once
             sBias[i] = (p.bias && i < p.Cout) ? __ldg(p.bias + i) : 0.0f;
         }
-        int j = 0;
+        int j = 0, tslot = 0;
         uint32_t n_groups = 0;
         for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++j) {
             const int a = j & 1;
+            if (elected) trace_stamp(p.trace, 3, tslot, 1);
             mbar_wait(bar_tfull + 8 * a, (j >> 1) & 1);
+            if (elected) trace_stamp(p.trace, 3, tslot, 2);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             int b = 0, pix = 0;
             const bool row_ok = tc_row_to_pixel(p, t, r, b, pix);
@@ -575,6 +593,7 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * a);
+            if (elected) trace_stamp(p.trace, 3, tslot, 3);
         }
         if (elected) bulk_wait_all();
     }
@@ -934,6 +953,10 @@ int conv_dwproj_launch(const ssd_dwproj_desc* d, cudaStream_t st) {
     memset(&p, 0, sizeof(p));
     size_t smem = 0;
     if (!dwproj_plan(d, &p, &smem)) return fail(SSD_ERR_UNSUPPORTED, "ssd_dwproj: no tile geometry fits shared memory");
+    p.trace = debug_trace_buffer();
+    if (p.trace)
+        fprintf(stderr, "ssd_dwproj: box %dx%dx%d patch %dx%d tiles=%d kblocks=%d pstages=%d quad=%d BN=%d smem=%zu\n", p.bw, p.bh,
+                p.bb, p.dw_pw, p.dw_ph, p.n_tiles, p.n_kblocks, p.dw_pstages, p.dw_quad, p.BN, smem);
     p.mode4d = 1;
     p.B = d->B; p.Ho = d->Ho; p.Wo = d->Wo; p.HoWo = d->Ho * d->Wo; p.M = d->B * p.HoWo;
     p.Cin = d->C; p.KW = 1; p.dil = 1; p.stride = 1;

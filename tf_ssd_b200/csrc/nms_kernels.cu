@@ -268,6 +268,7 @@ __device__ void rank_sort(uint64_t* a, uint64_t* tmp, int n) {
     __syncthreads();
 }
 constexpr int kRankSortMax = 768;          // beyond this the bitonic network wins
+constexpr int kMatrixMaxSeg = 256;         // largest class (candidates) handled by the suppression bit matrix
 
 __device__ __forceinline__ int pow2_ceil(int v) {
     int p = 32;
@@ -284,6 +285,7 @@ struct NmsParams {
     float iou_thr;
     int clip;
     int labels_first;          // output order: decoder (boxes, labels, scores) vs TF (boxes, scores, classes)
+    unsigned long long* trace; // debug (ssd_debug_trace): phase boundaries of image 0, else nullptr
 };
 
 // One CTA per image.  Fast path (candidate count <= fast_slots): keys, the decoded
@@ -304,6 +306,7 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
     __shared__ int s_seg_start[257];
     __shared__ int s_cnt[256], s_cur[256];
     __shared__ int s_mcount;
+    __shared__ int s_all_matrix;       // every non-empty class takes the bit-matrix path (kept lists unused)
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nwarps = kNmsThreads / 32;
     const int T = P.max_total;
@@ -311,6 +314,9 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
     float* oa = out_a + (size_t)b * T;
     float* oc = out_b + (size_t)b * T;
 
+    int tslot = 0;
+#define NMS_STAMP(tag) do { if (tid == 0) trace_stamp(P.trace, 0, tslot, tag); } while (0)
+    NMS_STAMP(1);
     const int raw_count = counts[b];
     if (raw_count > P.cap) {                       // candidate list overflowed: report, emit zeros
         for (int r = tid; r < T; r += kNmsThreads) { ob[r] = make_float4(0, 0, 0, 0); oa[r] = 0.f; oc[r] = 0.f; }
@@ -327,7 +333,7 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
     const bool grouped = cand == s_sort && 2 * M <= P.smem_sort_slots;      // class-grouped counting sort (common case)
     for (int i = tid; i < 257; i += kNmsThreads) s_seg_start[i] = -1;
     for (int i = tid; i < 256; i += kNmsThreads) { s_cnt[i] = 0; }
-    if (tid == 0) s_mcount = 0;
+    if (tid == 0) { s_mcount = 0; s_all_matrix = 0; }
     __syncthreads();
     if (grouped) {
         // a. class histogram -> segment starts; b. scatter into class segments (arbitrary order inside);
@@ -336,6 +342,7 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
         uint64_t* tmp = s_sort + (P.smem_sort_slots >> 1);
         for (int i = tid; i < M; i += kNmsThreads) atomicAdd(&s_cnt[(int)(gk[i] >> 56)], 1);
         __syncthreads();
+        NMS_STAMP(2);
         if (wid == 0) {                                // exclusive scan of the 256 class counts (8 per lane)
             int c8[8], t = 0;
 #pragma unroll
@@ -360,6 +367,7 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
             tmp[atomicAdd(&s_cur[(int)(key >> 56)], 1)] = key;
         }
         __syncthreads();
+        NMS_STAMP(3);
         for (int i = tid; i < M; i += kNmsThreads) {
             const uint64_t key = tmp[i];
             const int c = (int)(key >> 56), start = s_seg_start[c], end = start + s_cnt[c];
@@ -368,11 +376,62 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
             s_sort[start + rank] = key;
         }
         __syncthreads();
-        if (fast)
+        NMS_STAMP(4);
+        if (fast) {
             for (int i = tid; i < M; i += kNmsThreads) {
                 const uint64_t key = cand[i];
                 s_box[i] = fetch(b, (int)(key & 0xFFFFFFu), (int)(key >> 56));
             }
+            // Suppression bit matrix, built by the WHOLE CTA (a warp per class leaves most of the CTA idle and runs
+            // one dependent IoU chain per candidate): row li of class c holds, as 2*W 32-bit words (W = ceil(n_c/64)),
+            // bit lj set iff lj > li and IoU(li, lj) > threshold.  Rows live in the half of the sort buffer the
+            // counting sort no longer needs; s_cur[c] = first word of the class (-1: class keeps the serial path).
+            if (wid == 0) {
+                int w8[8], t = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int n = s_cnt[lane * 8 + q];
+                    w8[q] = (n > 0 && n <= kMatrixMaxSeg) ? n * 2 * ((n + 63) >> 6) : 0;
+                    t += w8[q];
+                }
+                int incl = t;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int u = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += u;
+                }
+                int base = incl - t;
+                bool all = true;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int n = s_cnt[lane * 8 + q];
+                    const bool ok = w8[q] > 0 && base + w8[q] <= P.smem_sort_slots;     // u32 words in half the buffer
+                    s_cur[lane * 8 + q] = ok ? base : -1;
+                    all = all && (ok || n == 0);
+                    base += w8[q];
+                }
+                all = __all_sync(0xffffffffu, all) && M <= 8 * P.per_class;      // staging area: the u16 kept lists' bytes
+                if (lane == 0) s_all_matrix = all ? 1 : 0;
+            }
+            __syncthreads();
+            uint32_t* mask32 = reinterpret_cast<uint32_t*>(tmp);
+            for (int t = tid; t < M * 8; t += kNmsThreads) {
+                const int i = t >> 3, h = t & 7;
+                const int c = (int)(cand[i] >> 56);
+                const int n = s_cnt[c], base = s_cur[c];
+                const int w2 = 2 * ((n + 63) >> 6);
+                if (base < 0 || h >= w2) continue;
+                const int start = s_seg_start[c], li = i - start, j0 = h << 5;
+                uint32_t bits = 0;
+                if (j0 + 31 > li) {
+                    const float4 bi = s_box[i];
+                    const int jend = min(32, n - j0);
+                    for (int jj = max(0, li + 1 - j0); jj < jend; ++jj)
+                        if (nms_iou(bi, s_box[start + j0 + jj]) > P.iou_thr) bits |= 1u << jj;
+                }
+                mask32[base + li * w2 + h] = bits;
+            }
+        }
     } else {
         if (cand == s_sort) {
             for (int i = tid; i < P1; i += kNmsThreads) s_sort[i] = (i < M) ? gk[i] : kPadKey;
@@ -391,6 +450,7 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
         }
     }
     __syncthreads();
+    NMS_STAMP(5);
 
     // ---- 3. greedy suppression, one warp per class ---------------------------
     uint64_t* mk = merge + (size_t)b * P.merge_stride;
@@ -399,37 +459,54 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
         if (start < 0) continue;
         int nk = 0;
         const int seg = grouped ? s_cnt[c] : 0;          // segment length (known up front on the grouped path)
-        if (fast && seg > 0 && seg <= 64 && seg <= P.per_class) {
-            // Bit-mask greedy NMS for a class with <= 64 candidates: lane r owns rows r and r + 32 of the strictly
-            // upper-triangular "i suppresses j" matrix (all IoUs of the class computed in parallel), then the
-            // sequential part is a scan over 64-bit masks.  Same result as the candidate-by-candidate loop below:
-            // a candidate is dropped iff an EARLIER KEPT candidate overlaps it by more than the threshold.
-            const float4 box0 = lane < seg ? s_box[start + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 box1 = lane + 32 < seg ? s_box[start + lane + 32] : make_float4(0.f, 0.f, 0.f, 0.f);
-            uint64_t row0 = 0, row1 = 0;
-            for (int j = 1; j < seg; ++j) {
-                const float4 bj = s_box[start + j];
-                if (lane < j && nms_iou(box0, bj) > P.iou_thr) row0 |= 1ull << j;
-                if (lane + 32 < j && nms_iou(box1, bj) > P.iou_thr) row1 |= 1ull << j;
-            }
-            uint64_t removed = 0;
-            for (int i = 0; i < seg; ++i) {
-                const uint64_t row = __shfl_sync(0xffffffffu, i < 32 ? row0 : row1, i & 31);
-                if (!((removed >> i) & 1ull)) removed |= row;
-            }
-            const uint64_t valid = seg == 64 ? ~0ull : ((1ull << seg) - 1ull);
-            const uint64_t kept = ~removed & valid;
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_mcount, __popcll(kept));
-            base = __shfl_sync(0xffffffffu, base, 0);
+        if (fast && seg > 0 && s_cur[c] >= 0) {
+            // Greedy scan over the class's rows of the bit matrix (built above by the whole CTA): candidate li survives
+            // iff no EARLIER KEPT candidate has its bit set -- the same result as the candidate-by-candidate loop
+            // below.  `removed` is replicated in every lane (warp-uniform control flow, broadcast row loads).
+            const int W = (seg + 63) >> 6;                       // 1..4
+            const uint64_t* rows = reinterpret_cast<const uint64_t*>(s_sort + (P.smem_sort_slots >> 1)) + (s_cur[c] >> 1);
+            uint64_t removed[4] = {0ull, 0ull, 0ull, 0ull};
+            int kept_n = 0;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = lane + 32 * h;
-                if (i < seg && ((kept >> i) & 1ull)) {
-                    const uint64_t key = cand[start + i];
-                    const int slot = base + __popcll(kept & ((1ull << i) - 1ull));
-                    const uint32_t inv_score = (uint32_t)((key >> 24) & 0xFFFFFFFFu);
-                    mk[slot] = ((uint64_t)inv_score << 32) | ((uint64_t)c << 24) | (uint32_t)(key & 0xFFFFFFu);
+            for (int w = 0; w < 4; ++w) {
+                if (w < W) {
+                    const int nb = min(64, seg - (w << 6));
+                    for (int bit = 0; bit < nb; ++bit) {
+                        const int li = (w << 6) + bit;
+                        const bool alive = !((removed[w] >> bit) & 1ull) && kept_n < P.per_class;
+                        if (alive) {
+                            ++kept_n;
+#pragma unroll
+                            for (int w2 = 0; w2 < 4; ++w2)
+                                if (w2 >= w && w2 < W) removed[w2] |= rows[li * W + w2];
+                        } else {
+                            removed[w] |= 1ull << bit;           // suppressed, or beyond the per-class cap
+                        }
+                    }
+                }
+            }
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_mcount, kept_n);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            uint64_t* dst = s_all_matrix ? reinterpret_cast<uint64_t*>(s_kidx) : mk;
+            int before = 0;                                      // kept candidates in earlier words
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                if (w < W) {
+                    const int nb = min(64, seg - (w << 6));
+                    const uint64_t valid = nb == 64 ? ~0ull : ((1ull << nb) - 1ull);
+                    const uint64_t kept = ~removed[w] & valid;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int bit = lane + 32 * h;
+                        if ((kept >> bit) & 1ull) {
+                            const uint64_t key = cand[start + (w << 6) + bit];
+                            const int slot = base + before + __popcll(kept & ((1ull << bit) - 1ull));
+                            const uint32_t inv_score = (uint32_t)((key >> 24) & 0xFFFFFFFFu);
+                            dst[slot] = ((uint64_t)inv_score << 32) | ((uint64_t)c << 24) | (uint32_t)(key & 0xFFFFFFu);
+                        }
+                    }
+                    before += __popcll(kept);
                 }
             }
         } else if (fast) {
@@ -475,13 +552,19 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
     }
     __threadfence_block();
     __syncthreads();
+    NMS_STAMP(6);
 
     // ---- 4. merge: score desc, class asc, anchor asc; first max_total --------
     const int K = s_mcount;
     const int P2 = pow2_ceil(K);
     uint64_t* ms = (P2 <= P.smem_sort_slots) ? s_sort : mk;
     if (ms == s_sort) {
-        for (int i = tid; i < P2; i += kNmsThreads) s_sort[i] = (i < K) ? __ldcg(mk + i) : kPadKey;
+        if (grouped && fast && s_all_matrix) {                  // kept keys were staged in shared memory
+            const uint64_t* stage = reinterpret_cast<const uint64_t*>(s_kidx);
+            for (int i = tid; i < P2; i += kNmsThreads) s_sort[i] = (i < K) ? stage[i] : kPadKey;
+        } else {
+            for (int i = tid; i < P2; i += kNmsThreads) s_sort[i] = (i < K) ? __ldcg(mk + i) : kPadKey;
+        }
     } else {
         for (int i = K + tid; i < P2; i += kNmsThreads) mk[i] = kPadKey;
     }
@@ -490,6 +573,7 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
         if (ms == s_sort && K <= kRankSortMax && 2 * P2 <= P.smem_sort_slots) rank_sort(ms, s_sort + (P.smem_sort_slots >> 1), K);
         else bitonic_sort(ms, P2);
     }
+    NMS_STAMP(7);
     const int V = min(K, T);
     for (int r = tid; r < T; r += kNmsThreads) {
         if (r < V) {
@@ -510,6 +594,8 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
         }
     }
     if (tid == 0) out_valid[b] = V;
+    NMS_STAMP(8);
+#undef NMS_STAMP
 }
 
 // ------------------------------------------------------------- host helpers --
@@ -542,6 +628,7 @@ static int make_plan(int B, int N, int L, int per_class, int max_total, int64_t 
     if ((int64_t)L * per_class > (int64_t)1 << 26) return SSD_ERR_SHAPE;
     NmsParams& p = plan->p;
     p.N = N; p.L = L; p.per_class = per_class; p.max_total = max_total; p.cap = (int)cap64;
+    p.trace = debug_trace_buffer();
     p.key_stride = host_pow2_ceil(cap64);
     p.merge_stride = host_pow2_ceil((int64_t)L * per_class);
     p.smem_sort_slots = min(4096, max(p.key_stride, p.merge_stride));

@@ -14,9 +14,17 @@ constexpr int TC_BK = 64;            // 64 fp16 = 128 B = one swizzle row
 constexpr int TC_STAGES = 4;
 constexpr int TC_EPI_WARPS = 8;      // two warps per TMEM lane quarter (they split the column chunks)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..9: epilogue
-constexpr int TC_DW_WARPS = 10;      // fused depthwise -> 1x1: warps 10..19 compute the A operand (20 warps, <= 96 registers)
+// fused depthwise -> 1x1 kernel: roles on warpgroup boundaries (setmaxnreg works per warpgroup) -- warpgroup 0: warp 0 TMA,
+// warp 1 MMA, warps 2-3 idle; warpgroups 1-2 (warps 4..11): epilogue; warpgroups 3-4 (warps 12..19): depthwise
+constexpr int TC_DW_EPI_WARP0 = 4;
+constexpr int TC_DW_WARP0 = TC_DW_EPI_WARP0 + TC_EPI_WARPS;
+constexpr int TC_DW_WARPS = 8;
 constexpr int TC_DW_ROWS = (TC_BM + 4 * TC_DW_WARPS - 1) / (4 * TC_DW_WARPS);   // tile rows per depthwise thread (4)
-constexpr int TC_THREADS_DW = TC_THREADS + 32 * TC_DW_WARPS;
+constexpr int TC_THREADS_DW = 32 * (TC_DW_WARP0 + TC_DW_WARPS);                  // 640
+// setmaxnreg moves registers inside the CTA's own pool (640 threads x 96 launch registers): budgets sum to <= 5 x 96
+constexpr int TC_DW_REGS_LAUNCH = 96, TC_DW_REGS_SCHED = 56, TC_DW_REGS_EPI = 80, TC_DW_REGS_DW = 128;
+static_assert(TC_DW_REGS_SCHED + 2 * TC_DW_REGS_EPI + 2 * TC_DW_REGS_DW <= 5 * TC_DW_REGS_LAUNCH, "CTA register pool");
+static_assert(TC_THREADS_DW * TC_DW_REGS_LAUNCH <= 65536 && TC_THREADS_DW * (TC_DW_REGS_LAUNCH + 8) > 65536, "launch registers = 96");
 constexpr int TC_DW_ASTAGES = 2;     // (A, B) operand ring of the fused kernel
 constexpr int TC_CHUNK = 32;         // epilogue column chunk per warp (fp16: 64 B per row)
 constexpr int TC_OUT_TILE = TC_BM * 128;             // one output staging tile: 128 rows x 64 fp16 channels, 128B-swizzled
@@ -54,6 +62,7 @@ struct TcParams {
     uint32_t dw_patch_stage;         // patch stage size in shared memory (1024-byte multiple)
     int dw_pstages;                  // patch ring depth
     int dw_quad;                     // stride 1 and bw % 4 == 0: a thread owns 4 horizontally adjacent pixels (sliding window)
+    unsigned long long* trace;       // debug (ssd_debug_trace): per-role stamps of CTA 0, else nullptr
 };
 
 // ------------------------------------------------------------------ PTX glue --
