@@ -206,6 +206,18 @@ typedef struct ssd_conv_desc {
 
 int ssd_conv2d(const ssd_conv_desc* h_desc, ssd_stream_t stream);
 
+/* A chain of small convolutions as ONE launch: the tail of the SSD graphs -- models/ssd_mobilenet_v2.py:33-41
+ * (extra2_1 ... extra4_2), models/ssd_vgg16.py:108-113 (conv9_1 ... conv11_2) -- plus the multibox heads
+ * (models/header.py:68-85) of the feature maps that tail produces.  h_descs[i] are ordinary ssd_conv_desc; a layer may
+ * read the out0 of an EARLIER layer of the chain.  h_phase[i] (non-decreasing) groups the layers: all inputs of a
+ * layer must come from outside the chain or from a layer of a lower phase (e.g. phase k: extra layer k and the head of
+ * the map produced in phase k-1).  A cluster of 8 CTAs owns a few images through the whole chain; every CTA computes a
+ * share of each layer's output channels; a cluster barrier separates the phases (csrc/conv_chain.cu).
+ * Constraints: KH == KW in {1,3}, dilation 1, stride 1|2, Cin % 128 == 0, no residual, one batch size, small maps
+ * (ssd_conv_chain_supported tells; SSD_ERR_UNSUPPORTED otherwise). */
+int ssd_conv_chain(const ssd_conv_desc* h_descs, const int32_t* h_phase, int n_layers, ssd_stream_t stream);
+int ssd_conv_chain_supported(const ssd_conv_desc* h_descs, const int32_t* h_phase, int n_layers);
+
 /* Keras DepthwiseConv2D 3x3 (+ folded BN + ReLU6) inside MobileNetV2
  * (ssd_mobilenet_v2.py:25).  in [B,H,W,C] fp16, weight [3,3,C] fp16,
  * bias [C] fp32, out [B,Ho,Wo,C] fp16; C % 8 == 0. */

@@ -328,27 +328,35 @@ def test_every_layer_in_situ(backbone, B):
     plan = m.plan(B)
     f32 = lambda t: t.float().cpu()
     checked = 0
+    def check_conv(name, mt):
+        x = f32(mt["x"]).permute(0, 3, 1, 2)
+        w = f32(mt["w"]).permute(0, 3, 1, 2)
+        (pt, pb), (pl, pr) = mt["ph"], mt["pw"]
+        y = F.conv2d(F.pad(x, (pl, pr, pt, pb)), w, f32(mt["bias"]), stride=mt["stride"], dilation=mt["dilation"])
+        y = torch.relu(y) if mt["act"] == 1 else torch.clamp(y, 0, 6) if mt["act"] == 2 else y
+        y = y.permute(0, 2, 3, 1)
+        if mt["res"] is not None:
+            y = y + f32(mt["res"])
+        y = y.numpy()
+        assert y.shape[1:3] == (mt["Ho"], mt["Wo"])
+        if "head" in mt:
+            off, cnt, A = mt["head"]
+            lab = plan.logits[:, off:off + cnt].cpu().numpy().reshape(B, mt["Ho"], mt["Wo"], A * 21)
+            box = plan.deltas[:, off:off + cnt].cpu().numpy().reshape(B, mt["Ho"], mt["Wo"], A * 4)
+            got, tol = np.concatenate([lab, box], -1), 2e-4
+        else:
+            got, tol = f32(mt["out0"]).numpy(), 2e-3
+        assert _rel(got, y) < tol, f"{name}: {_rel(got, y)}"
+
     for s in plan.steps:
         mt = s.meta
         if s.kind == "conv":
-            x = f32(mt["x"]).permute(0, 3, 1, 2)
-            w = f32(mt["w"]).permute(0, 3, 1, 2)
-            (pt, pb), (pl, pr) = mt["ph"], mt["pw"]
-            y = F.conv2d(F.pad(x, (pl, pr, pt, pb)), w, f32(mt["bias"]), stride=mt["stride"], dilation=mt["dilation"])
-            y = torch.relu(y) if mt["act"] == 1 else torch.clamp(y, 0, 6) if mt["act"] == 2 else y
-            y = y.permute(0, 2, 3, 1)
-            if mt["res"] is not None:
-                y = y + f32(mt["res"])
-            y = y.numpy()
-            assert y.shape[1:3] == (mt["Ho"], mt["Wo"])
-            if "head" in mt:
-                off, cnt, A = mt["head"]
-                lab = plan.logits[:, off:off + cnt].cpu().numpy().reshape(B, mt["Ho"], mt["Wo"], A * 21)
-                box = plan.deltas[:, off:off + cnt].cpu().numpy().reshape(B, mt["Ho"], mt["Wo"], A * 4)
-                got, tol = np.concatenate([lab, box], -1), 2e-4
-            else:
-                got, tol = f32(mt["out0"]).numpy(), 2e-3
-            assert _rel(got, y) < tol, f"{s.name}: {_rel(got, y)}"
+            check_conv(s.name, mt)
+        elif s.kind == "chain":
+            # the small-map tail + its heads as one launch (ssd_conv_chain): every member layer on its actual input
+            assert len(mt["layers"]) >= 5 and sum(1 for _, m_ in mt["layers"] if "head" in m_) >= 3
+            for name, sub in mt["layers"]:
+                check_conv(name, sub)
         elif s.kind == "dw":
             x = f32(mt["x"]).permute(0, 3, 1, 2)
             w = f32(mt["w"]).permute(2, 0, 1).unsqueeze(1)
@@ -399,6 +407,7 @@ def test_every_layer_in_situ(backbone, B):
         checked += 1
     assert checked == plan.n_launches - sum(1 for s in plan.steps if s.kind == "cast")
     assert any(s.kind == "stem" for s in plan.steps) == (backbone == "mobilenet_v2")
+    assert any(s.kind == "chain" for s in plan.steps)
 
 
 @pytest.mark.parametrize("backbone,B", [("mobilenet_v2", 2), ("vgg16", 1)])
@@ -508,9 +517,10 @@ def test_decoder_model_uint8_batches_and_parallel_heads():
     for a, b in zip(r8, rf):
         assert np.array_equal(a, b)
     plan = m.plan(B)
-    assert sum(1 for s in plan.steps if s.branch) == 6 and plan.steps[-1].branch          # heads are side branches
+    # heads 1-3 are side branches hoisted behind their taps; heads 4-6 live inside the fused tail (ssd_conv_chain)
+    assert sum(1 for s in plan.steps if s.branch) == 3 and plan.steps[-1].kind == "chain"
     first_head = next(i for i, s in enumerate(plan.steps) if s.branch)
-    assert first_head < len(plan.steps) - 12                                             # hoisted behind their taps
+    assert first_head < len(plan.steps) - 8
     m._to_image_buffer(plan, u8[0])
     plan.run(u8=True, parallel=True)
     torch.cuda.synchronize()
@@ -553,3 +563,67 @@ def test_stem_kernel_shapes(H, W, pad):
     y = torch.clamp(y, 0, 6).permute(0, 2, 3, 1).numpy()
     assert y.shape == (B, Ho, Wo, 32)
     assert _rel(outs[0].float().cpu().numpy(), y) < 2e-3
+
+
+@pytest.mark.parametrize("B", [1, 3, 5])
+def test_conv_chain_against_torch(B):
+    """ssd_conv_chain on a VGG-like tail with ragged channel counts: 1x1 -> 3x3 stride 2 SAME -> 1x1 -> 3x3 VALID, plus a
+    split fp32 "head" (3x3 SAME, 150 = 6*21 + 6*4 channels) on the first 3x3's map in the same phase as the next 1x1.
+    B = 3 and 5 leave a partially filled cluster (images per cluster does not divide the batch)."""
+    from tf_ssd_b200 import _ffi
+    from tf_ssd_b200._ffi_conv import ConvDesc
+    rng = np.random.default_rng(40 + B)
+    dev = torch.device("cuda")
+    lib = _ffi.lib()
+
+    def layer(x_t, H, W, cin, cout, k, stride, pads, act, head=None):
+        (pt, pb), (pl, pr) = pads
+        Ho, Wo = (H + pt + pb - k) // stride + 1, (W + pl + pr - k) // stride + 1
+        w = (rng.standard_normal((cout, k, k, cin)) * np.sqrt(2.0 / (k * k * cin))).astype(np.float16)
+        b = (0.1 * rng.standard_normal(cout)).astype(np.float32)
+        wd, bd = torch.from_numpy(w).to(dev), torch.from_numpy(b).to(dev)
+        d = ConvDesc()
+        d.inp, d.weight, d.bias, d.residual = x_t.data_ptr(), wd.data_ptr(), bd.data_ptr(), None
+        d.B, d.H, d.W, d.Cin, d.Ho, d.Wo, d.Cout = B, H, W, cin, Ho, Wo, cout
+        d.KH = d.KW = k
+        d.stride, d.dilation, d.pad_top, d.pad_left, d.act = stride, 1, pt, pl, act
+        if head is None:
+            out = torch.zeros((B, Ho, Wo, cout), dtype=torch.float16, device=dev)
+            d.out0, d.out1, d.out_f32, d.split = out.data_ptr(), None, 0, cout
+            d.img_stride0, d.pix_stride0, d.img_stride1, d.pix_stride1 = Ho * Wo * cout, cout, 0, 0
+            outs = (out,)
+        else:
+            sp = head
+            o0 = torch.zeros((B, Ho, Wo, sp), dtype=torch.float32, device=dev)
+            o1 = torch.zeros((B, Ho, Wo, cout - sp), dtype=torch.float32, device=dev)
+            d.out0, d.out1, d.out_f32, d.split = o0.data_ptr(), o1.data_ptr(), 1, sp
+            d.img_stride0, d.pix_stride0, d.img_stride1, d.pix_stride1 = Ho * Wo * sp, sp, Ho * Wo * (cout - sp), cout - sp
+            outs = (o0, o1)
+        return dict(d=d, w=w, b=b, pads=pads, k=k, stride=stride, act=act, x=x_t, outs=outs, keep=(wd, bd), Ho=Ho, Wo=Wo)
+
+    x0 = torch.from_numpy(rng.standard_normal((B, 5, 5, 256)).astype(np.float16)).to(dev)
+    l0 = layer(x0, 5, 5, 256, 128, 1, 1, ((0, 0), (0, 0)), 1)
+    l1 = layer(l0["outs"][0], 5, 5, 128, 256, 3, 2, ((1, 1), (1, 1)), 1)                   # -> 3x3x256
+    l2 = layer(l1["outs"][0], 3, 3, 256, 128, 1, 1, ((0, 0), (0, 0)), 1)
+    lh = layer(l1["outs"][0], 3, 3, 256, 150, 3, 1, ((1, 1), (1, 1)), 0, head=126)          # head on l1's map, phase of l2
+    l3 = layer(l2["outs"][0], 3, 3, 128, 40, 3, 1, ((0, 0), (0, 0)), 2)                    # VALID -> 1x1x40 (ragged tiles)
+    layers, phases = [l0, l1, l2, lh, l3], [0, 1, 2, 2, 3]
+    descs = (ConvDesc * len(layers))(*[l["d"] for l in layers])
+    ph = (C.c_int32 * len(layers))(*phases)
+    assert lib.ssd_conv_chain_supported(descs, ph, len(layers)) == 1
+    _ffi.check(lib.ssd_conv_chain(descs, ph, len(layers), _ffi.stream()), "ssd_conv_chain")
+    torch.cuda.synchronize()
+    for i, l in enumerate(layers):
+        x = l["x"].float().cpu().permute(0, 3, 1, 2)
+        (pt, pb), (pl, pr) = l["pads"]
+        y = F.conv2d(F.pad(x, (pl, pr, pt, pb)), torch.from_numpy(l["w"].astype(np.float32)).permute(0, 3, 1, 2),
+                     torch.from_numpy(l["b"]), stride=l["stride"])
+        y = torch.relu(y) if l["act"] == 1 else torch.clamp(y, 0, 6) if l["act"] == 2 else y
+        y = y.permute(0, 2, 3, 1).numpy()
+        got = np.concatenate([o.float().cpu().numpy() for o in l["outs"]], -1)
+        assert got.shape == y.shape
+        assert _rel(got, y) < (2e-4 if len(l["outs"]) == 2 else 2e-3), (i, _rel(got, y))
+    # unsupported chains are refused, not mis-computed
+    bad = (C.c_int32 * len(layers))(0, 1, 2, 1, 3)
+    assert lib.ssd_conv_chain_supported(descs, bad, len(layers)) == 0
+    assert lib.ssd_conv_chain(descs, bad, len(layers), _ffi.stream()) == -4

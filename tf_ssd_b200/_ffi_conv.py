@@ -51,6 +51,8 @@ class AdamVar(C.Structure):
 
 SIGNATURES = {
     "ssd_conv2d": (i, [C.POINTER(ConvDesc), vp]),
+    "ssd_conv_chain": (i, [C.POINTER(ConvDesc), C.POINTER(C.c_int32), i, vp]),
+    "ssd_conv_chain_supported": (i, [C.POINTER(ConvDesc), C.POINTER(C.c_int32), i]),
     "ssd_depthwise3x3": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),
     "ssd_dwproj": (i, [C.POINTER(DwProjDesc), vp]),
     "ssd_dwproj_supported": (i, [C.POINTER(DwProjDesc)]),

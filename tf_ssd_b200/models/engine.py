@@ -305,6 +305,56 @@ class Plan:
             rest.insert(idx + 1, h)
         self.steps = rest
 
+    # the small-map tail (extras behind the 5x5 / 10x10 map + the heads of the maps it produces) as ONE launch: "1" / "0"
+    FUSE_TAIL = os.environ.get("SSD_B200_FUSE_TAIL", "1")
+
+    def fuse_tail(self, lib) -> None:
+        """Replaces the longest suffix of the main chain that ``ssd_conv_chain`` can run -- plain convolutions on small
+        maps, each fed by its predecessor (models/ssd_mobilenet_v2.py:33-41 extra2_1..extra4_2, models/ssd_vgg16.py:108-113
+        conv9_1..conv11_2) -- and the multibox heads of the feature maps that suffix produces (models/header.py:68-85) by
+        one launch.  Layers are grouped in phases by dependency depth: a head runs in the same phase as the extra layer
+        that reads the same map."""
+        if self.FUSE_TAIL in ("0", ""):
+            return
+        main = [s for s in self.steps if not s.branch]
+
+        def chain_for(start: int):
+            suffix = main[start:]
+            if len(suffix) < 2 or any(s.kind != "conv" for s in suffix):
+                return None
+            produced = {id(s.meta["out0"]): s for s in suffix if isinstance(s.meta.get("out0"), torch.Tensor)}
+            for a, b in zip(suffix[:-1], suffix[1:]):
+                if b.meta["x"] is not a.meta["out0"]:
+                    return None
+            heads = [s for s in self.steps if s.branch and s.kind == "conv" and "head" in (s.meta or {})
+                     and id(s.meta["x"]) in produced]
+            if any(s.branch and s not in heads and id((s.meta or {}).get("x")) in produced for s in self.steps):
+                return None                                         # some other side step consumes a map of the suffix
+            phase = {}
+            for s in suffix + heads:
+                prod = produced.get(id(s.meta["x"]))
+                phase[id(s)] = phase[id(prod)] + 1 if prod is not None else 0
+            layers = sorted(suffix + heads, key=lambda s: phase[id(s)])     # stable: extras before the heads of a phase
+            return layers, [phase[id(s)] for s in layers]
+
+        for start in range(len(main)):
+            got = chain_for(start)
+            if got is None:
+                continue
+            layers, phases = got
+            descs = (ConvDesc * len(layers))(*[s.args[0]._obj for s in layers])
+            ph = (C.c_int32 * len(layers))(*phases)
+            if not lib.ssd_conv_chain_supported(descs, ph, len(layers)):
+                continue
+            members = {id(s) for s in layers}
+            first = min(i for i, s in enumerate(self.steps) if id(s) in members)
+            keep = tuple(k for s in layers for k in s.keep) + (descs, ph)
+            step = Step("tail_chain", "chain", lib.ssd_conv_chain, (descs, ph, len(layers)), sum(s.flops for s in layers),
+                        sum(s.bytes for s in layers), keep, dict(layers=[(s.name, s.meta) for s in layers], phases=phases))
+            self.steps = [s for i, s in enumerate(self.steps[:first]) if id(s) not in members] + [step] + \
+                         [s for s in self.steps[first:] if id(s) not in members]
+            return
+
     @property
     def n_launches(self) -> int:
         return len(self.steps)
@@ -760,6 +810,7 @@ class SSDModel(object):
             taps = GRAPHS[self.backbone](pb, pb.input(), self.hyper_params)
             pb.head(taps, self.hyper_params)
             pb.plan.hoist_heads()
+            pb.plan.fuse_tail(pb.lib)
             self._plans[(B, slot)] = pb.plan
         return self._plans[(B, slot)]
 

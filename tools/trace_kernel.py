@@ -113,8 +113,39 @@ def trace_nms(stress):
     dump(buf, {0: "nms"}, tags)
 
 
+def trace_chain():
+    import bench
+    from tf_ssd_b200.models import ssd_mobilenet_v2
+    lib = _ffi.lib()
+    hp = bench._hyper_params()
+    model = ssd_mobilenet_v2.get_model(hp, seed=1234)
+    plan = model.plan(bench.BATCH)
+    plan.image_u8.copy_(torch.from_numpy(bench._make_images_u8(bench.BATCH, hp["img_size"], seed=1000)))
+    for _ in range(3):
+        plan.run(u8=True)
+    torch.cuda.synchronize()
+    idx = [i for i, s in enumerate(plan.steps) if s.kind == "chain"][0]
+    print([(n, ph) for (n, _), ph in zip(plan.steps[idx].meta["layers"], plan.steps[idx].meta["phases"])])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        plan.run(idx, idx + 1, u8=True, parallel=False)
+    e1.record()
+    torch.cuda.synchronize()
+    print("chain us per call:", e0.elapsed_time(e1) * 100)
+    buf = torch.zeros(ROLES * 512, dtype=torch.int64, device="cuda")
+    lib.ssd_debug_trace(C.c_void_p(buf.data_ptr()))
+    plan.run(idx, idx + 1, u8=True, parallel=False)
+    torch.cuda.synchronize()
+    lib.ssd_debug_trace(None)
+    dump(buf, {0: "chain", 1: "warp0"}, {0: {1: "layer", 2: "synced", 3: "staged", 4: "computed", 5: "end"}, 1: {1: "unit", 2: "tap"}}, limit=80)
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
+    if what == "chain":
+        trace_chain()
+        sys.exit(0)
     if what == "dwproj":
         trace_dwproj(*map(int, sys.argv[2:8]))
     elif what == "nms":
