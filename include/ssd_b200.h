@@ -217,6 +217,8 @@ int ssd_conv2d(const ssd_conv_desc* h_desc, ssd_stream_t stream);
  * (ssd_conv_chain_supported tells; SSD_ERR_UNSUPPORTED otherwise). */
 int ssd_conv_chain(const ssd_conv_desc* h_descs, const int32_t* h_phase, int n_layers, ssd_stream_t stream);
 int ssd_conv_chain_supported(const ssd_conv_desc* h_descs, const int32_t* h_phase, int n_layers);
+/* 0: unsupported; otherwise the number of waves of clusters the launch needs on the current device (1: all resident). */
+int ssd_conv_chain_waves(const ssd_conv_desc* h_descs, const int32_t* h_phase, int n_layers);
 
 /* Keras DepthwiseConv2D 3x3 (+ folded BN + ReLU6) inside MobileNetV2
  * (ssd_mobilenet_v2.py:25).  in [B,H,W,C] fp16, weight [3,3,C] fp16,

@@ -53,6 +53,7 @@ SIGNATURES = {
     "ssd_conv2d": (i, [C.POINTER(ConvDesc), vp]),
     "ssd_conv_chain": (i, [C.POINTER(ConvDesc), C.POINTER(C.c_int32), i, vp]),
     "ssd_conv_chain_supported": (i, [C.POINTER(ConvDesc), C.POINTER(C.c_int32), i]),
+    "ssd_conv_chain_waves": (i, [C.POINTER(ConvDesc), C.POINTER(C.c_int32), i]),
     "ssd_depthwise3x3": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),
     "ssd_dwproj": (i, [C.POINTER(DwProjDesc), vp]),
     "ssd_dwproj_supported": (i, [C.POINTER(DwProjDesc)]),

@@ -366,6 +366,20 @@ extern "C" int ssd_conv_chain_supported(const ssd_conv_desc* h_descs, const int3
     return chain_plan(h_descs, h_phase, n_layers, 0, &p, &smem) ? 1 : 0;
 }
 
+// 0: unsupported; otherwise how many waves of clusters the launch needs on the current device (1 = every cluster is
+// resident at once; the engine fuses a tail only then: a second wave would double the latency the fusion removes)
+extern "C" int ssd_conv_chain_waves(const ssd_conv_desc* h_descs, const int32_t* h_phase, int n_layers) {
+    if (!h_descs || !h_phase) return 0;
+    ChainParams p;
+    memset(&p, 0, sizeof(p));
+    size_t smem = 0;
+    static thread_local int max_clusters = -1;
+    if (max_clusters < 0) max_clusters = chain_max_clusters(225 * 1024);
+    if (!chain_plan(h_descs, h_phase, n_layers, max_clusters, &p, &smem)) return 0;
+    const int clusters = (p.B + p.ipc - 1) / p.ipc;
+    return max_clusters > 0 ? (clusters + max_clusters - 1) / max_clusters : 1;
+}
+
 extern "C" int ssd_conv_chain(const ssd_conv_desc* h_descs, const int32_t* h_phase, int n_layers, ssd_stream_t stream) {
     SSD_REQUIRE_PTR(h_descs); SSD_REQUIRE_PTR(h_phase);
     SSD_REQUIRE(n_layers >= 1 && n_layers <= CH_MAX_LAYERS, SSD_ERR_SHAPE, "ssd_conv_chain: n_layers=%d (1..%d)", n_layers, CH_MAX_LAYERS);

@@ -24,7 +24,7 @@
 namespace ssd {
 
 constexpr int kRowThreadsNms = 128;
-constexpr int kNmsThreads = 1024;
+constexpr int kNmsThreads = 512;          // 64 registers x 512 threads: two images per SM (1024 threads filled the register file)
 constexpr uint64_t kPadKey = ~0ull;
 
 __device__ __forceinline__ uint32_t order_bits(float f) {
@@ -222,18 +222,47 @@ __device__ __forceinline__ float4 DecodeFetch::operator()(int b, int anchor, int
     return make_float4(y1, x1, fadd(h, y1), fadd(w, x1));
 }
 
-// [TF-recall] IoU of TensorFlow's non_max_suppression_op.cc: corners
-// canonicalised, 0 if either area <= 0.
-__device__ __forceinline__ float nms_iou(const float4 a, const float4 b) {
+// [TF-recall] IoU of TensorFlow's non_max_suppression_op.cc: corners canonicalised, 0 if either area <= 0; a candidate
+// is suppressed when  inter / (area_a + area_b - inter) > thr.  The test below decides that comparison
+// without the division in all but borderline cases: for thr > 0 the quotient inter / uni exceeds thr
+// iff inter > thr * uni, and a 1e-5 relative margin (far above the roundings of the product and of the quotient) decides
+// every pair that is not within that margin of the threshold; those few take the exact division.
+__device__ __forceinline__ bool nms_iou_gt(const float4 a, const float4 b, float thr) {
     float aymin = fminf(a.x, a.z), aymax = fmaxf(a.x, a.z), axmin = fminf(a.y, a.w), axmax = fmaxf(a.y, a.w);
     float bymin = fminf(b.x, b.z), bymax = fmaxf(b.x, b.z), bxmin = fminf(b.y, b.w), bxmax = fmaxf(b.y, b.w);
     float area_a = fmul(fsub(aymax, aymin), fsub(axmax, axmin));
     float area_b = fmul(fsub(bymax, bymin), fsub(bxmax, bxmin));
-    if (area_a <= 0.0f || area_b <= 0.0f) return 0.0f;
+    if (area_a <= 0.0f || area_b <= 0.0f) return 0.0f > thr;
     float ih = fmaxf(fsub(fminf(aymax, bymax), fmaxf(aymin, bymin)), 0.0f);
     float iw = fmaxf(fsub(fminf(axmax, bxmax), fmaxf(axmin, bxmin)), 0.0f);
     float inter = fmul(ih, iw);
-    return fdiv(inter, fsub(fadd(area_a, area_b), inter));
+    float uni = fsub(fadd(area_a, area_b), inter);
+    if (thr > 0.0f && uni > 0.0f) {
+        const float tu = fmul(thr, uni);
+        if (inter < fmul(tu, 0.99999f)) return false;
+        if (inter > fmul(tu, 1.00001f)) return true;
+    }
+    return fdiv(inter, uni) > thr;
+}
+
+// The same test on boxes whose corners are already canonical (ymin, xmin, ymax, xmax): the shared box cache stores them
+// that way, so the per-pair work is the intersection, the union and the comparison only.
+__device__ __forceinline__ float4 nms_canonical(const float4 a) {
+    return make_float4(fminf(a.x, a.z), fminf(a.y, a.w), fmaxf(a.x, a.z), fmaxf(a.y, a.w));
+}
+__device__ __forceinline__ bool nms_iou_gt_canonical(const float4 a, const float4 b, float thr) {
+    const float area_a = fmul(fsub(a.z, a.x), fsub(a.w, a.y)), area_b = fmul(fsub(b.z, b.x), fsub(b.w, b.y));
+    if (area_a <= 0.0f || area_b <= 0.0f) return 0.0f > thr;
+    const float ih = fmaxf(fsub(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
+    const float iw = fmaxf(fsub(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
+    const float inter = fmul(ih, iw);
+    const float uni = fsub(fadd(area_a, area_b), inter);
+    if (thr > 0.0f && uni > 0.0f) {
+        const float tu = fmul(thr, uni);
+        if (inter < fmul(tu, 0.99999f)) return false;
+        if (inter > fmul(tu, 1.00001f)) return true;
+    }
+    return fdiv(inter, uni) > thr;
 }
 
 // In-place ascending bitonic sort of a[0..P) (P a power of two) by the CTA.
@@ -307,6 +336,7 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
     __shared__ int s_cnt[256], s_cur[256];
     __shared__ int s_mcount;
     __shared__ int s_all_matrix;       // every non-empty class takes the bit-matrix path (kept lists unused)
+    __shared__ int s_mwords, s_dmax;   // 32-bit words of the bit matrix; largest class that uses it
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nwarps = kNmsThreads / 32;
     const int T = P.max_total;
@@ -380,7 +410,7 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
         if (fast) {
             for (int i = tid; i < M; i += kNmsThreads) {
                 const uint64_t key = cand[i];
-                s_box[i] = fetch(b, (int)(key & 0xFFFFFFu), (int)(key >> 56));
+                s_box[i] = nms_canonical(fetch(b, (int)(key & 0xFFFFFFu), (int)(key >> 56)));
             }
             // Suppression bit matrix, built by the WHOLE CTA (a warp per class leaves most of the CTA idle and runs
             // one dependent IoU chain per candidate): row li of class c holds, as 2*W 32-bit words (W = ceil(n_c/64)),
@@ -402,34 +432,56 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
                 }
                 int base = incl - t;
                 bool all = true;
+                int dmax = 0, used = 0;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const int n = s_cnt[lane * 8 + q];
                     const bool ok = w8[q] > 0 && base + w8[q] <= P.smem_sort_slots;     // u32 words in half the buffer
                     s_cur[lane * 8 + q] = ok ? base : -1;
                     all = all && (ok || n == 0);
+                    if (ok) { dmax = max(dmax, n); used = base + w8[q]; }
                     base += w8[q];
                 }
-                all = __all_sync(0xffffffffu, all) && M <= 8 * P.per_class;      // staging area: the u16 kept lists' bytes
-                if (lane == 0) s_all_matrix = all ? 1 : 0;
+                all = __all_sync(0xffffffffu, all) && M <= (kNmsThreads / 128) * P.per_class;     // staging area: the u16 kept lists' bytes
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+                    used = max(used, __shfl_xor_sync(0xffffffffu, used, o));
+                }
+                if (lane == 0) { s_all_matrix = all ? 1 : 0; s_dmax = dmax; s_mwords = used; }
             }
             __syncthreads();
+            NMS_STAMP(9);
             uint32_t* mask32 = reinterpret_cast<uint32_t*>(tmp);
-            for (int t = tid; t < M * 8; t += kNmsThreads) {
-                const int i = t >> 3, h = t & 7;
-                const int c = (int)(cand[i] >> 56);
-                const int n = s_cnt[c], base = s_cur[c];
-                const int w2 = 2 * ((n + 63) >> 6);
-                if (base < 0 || h >= w2) continue;
-                const int start = s_seg_start[c], li = i - start, j0 = h << 5;
-                uint32_t bits = 0;
-                if (j0 + 31 > li) {
+            for (int t = tid; t < s_mwords; t += kNmsThreads) mask32[t] = 0u;
+            __syncthreads();
+            NMS_STAMP(10);
+            // every (candidate, later candidate of its class) pair is an independent IoU test; the few overlapping pairs
+            // set their bit atomically.  Classes of <= 64 candidates: one thread per candidate walks its later
+            // partners (no index arithmetic); larger classes, or too few candidates to occupy the CTA
+            // that way: the pairs are spread flat over all threads.
+            const int D = s_dmax - 1;
+            if (D < 64 && M * 2 > kNmsThreads) {
+                for (int i = tid; i < M; i += kNmsThreads) {
+                    const int c = (int)(cand[i] >> 56);
+                    const int n = s_cnt[c], base = s_cur[c];
+                    if (base < 0) continue;
+                    const int start = s_seg_start[c], li = i - start;
                     const float4 bi = s_box[i];
-                    const int jend = min(32, n - j0);
-                    for (int jj = max(0, li + 1 - j0); jj < jend; ++jj)
-                        if (nms_iou(bi, s_box[start + j0 + jj]) > P.iou_thr) bits |= 1u << jj;
+                    uint32_t* row = mask32 + base + li * 2 * ((n + 63) >> 6);
+                    for (int lj = li + 1; lj < n; ++lj)
+                        if (nms_iou_gt_canonical(bi, s_box[start + lj], P.iou_thr)) atomicOr(&row[lj >> 5], 1u << (lj & 31));
                 }
-                mask32[base + li * w2 + h] = bits;
+            } else {
+                for (int t = tid; t < M * D; t += kNmsThreads) {
+                    const int i = t / D, d = t - i * D + 1;
+                    const int c = (int)(cand[i] >> 56);
+                    const int n = s_cnt[c], base = s_cur[c];
+                    const int start = s_seg_start[c], li = i - start, lj = li + d;
+                    if (base < 0 || lj >= n) continue;
+                    if (nms_iou_gt_canonical(s_box[i], s_box[start + lj], P.iou_thr))
+                        atomicOr(&mask32[base + li * 2 * ((n + 63) >> 6) + (lj >> 5)], 1u << (lj & 31));
+                }
             }
         }
     } else {
@@ -446,7 +498,7 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
             const uint64_t key = cand[i];
             const int c = (int)(key >> 56);
             if (i == 0 || (int)(cand[i - 1] >> 56) != c) s_seg_start[c] = i;
-            if (fast) s_box[i] = fetch(b, (int)(key & 0xFFFFFFu), c);
+            if (fast) s_box[i] = nms_canonical(fetch(b, (int)(key & 0xFFFFFFu), c));
         }
     }
     __syncthreads();
@@ -467,6 +519,19 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
             const uint64_t* rows = reinterpret_cast<const uint64_t*>(s_sort + (P.smem_sort_slots >> 1)) + (s_cur[c] >> 1);
             uint64_t removed[4] = {0ull, 0ull, 0ull, 0ull};
             int kept_n = 0;
+            if (W == 1) {
+                // <= 64 candidates: lane r holds rows r and r + 32; the scan pulls row i with a shuffle that does not
+                // depend on `removed`, so only a shift / test / or chain is serial
+                const uint64_t row0 = lane < seg ? rows[lane] : 0ull, row1 = lane + 32 < seg ? rows[lane + 32] : 0ull;
+                uint64_t rem = 0ull;
+                for (int i = 0; i < seg; ++i) {
+                    const uint64_t row = __shfl_sync(0xffffffffu, i < 32 ? row0 : row1, i & 31);
+                    const bool alive = !((rem >> i) & 1ull) && kept_n < P.per_class;
+                    kept_n += alive ? 1 : 0;
+                    rem |= alive ? row : (1ull << i);
+                }
+                removed[0] = rem;
+            } else
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
                 if (w < W) {
@@ -516,7 +581,7 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
                 if ((int)(key >> 56) != c) break;
                 const float4 box = s_box[i];
                 bool sup = false;
-                for (int j = lane; j < nk; j += 32) sup |= nms_iou(box, s_box[kidx[j]]) > P.iou_thr;
+                for (int j = lane; j < nk; j += 32) sup |= nms_iou_gt_canonical(box, s_box[kidx[j]], P.iou_thr);
                 if (!__any_sync(0xffffffffu, sup)) {
                     if (lane == 0) {
                         kidx[nk] = (uint16_t)i;
@@ -536,7 +601,7 @@ nms_image_kernel(NmsParams P, Fetch fetch, uint64_t* __restrict__ keys, uint64_t
                 const int anchor = (int)(key & 0xFFFFFFu);
                 const float4 box = fetch(b, anchor, c);
                 bool sup = false;
-                for (int j = lane; j < nk; j += 32) sup |= nms_iou(box, __ldcg(kept + j)) > P.iou_thr;   // bypass L1
+                for (int j = lane; j < nk; j += 32) sup |= nms_iou_gt(box, __ldcg(kept + j), P.iou_thr);   // bypass L1
                 if (!__any_sync(0xffffffffu, sup)) {
                     if (lane == 0) {
                         kept[nk] = box;

@@ -307,6 +307,7 @@ class Plan:
 
     # the small-map tail (extras behind the 5x5 / 10x10 map + the heads of the maps it produces) as ONE launch: "1" / "0"
     FUSE_TAIL = os.environ.get("SSD_B200_FUSE_TAIL", "1")
+    FUSE_TAIL_MAX_GFLOP = float(os.environ.get("SSD_B200_FUSE_TAIL_MAX_GFLOP", "0.8"))
 
     def fuse_tail(self, lib) -> None:
         """Replaces the longest suffix of the main chain that ``ssd_conv_chain`` can run -- plain convolutions on small
@@ -344,8 +345,10 @@ class Plan:
             layers, phases = got
             descs = (ConvDesc * len(layers))(*[s.args[0]._obj for s in layers])
             ph = (C.c_int32 * len(layers))(*phases)
-            if not lib.ssd_conv_chain_supported(descs, ph, len(layers)):
+            if lib.ssd_conv_chain_waves(descs, ph, len(layers)) != 1:      # unsupported, or the clusters need a second wave
                 continue
+            if sum(s.flops for s in layers) > self.FUSE_TAIL_MAX_GFLOP * 1e9:
+                continue        # the cluster kernel is fragment-load bound (~20 TFLOP/s): beyond this, separate tcgen05 launches win
             members = {id(s) for s in layers}
             first = min(i for i, s in enumerate(self.steps) if id(s) in members)
             keep = tuple(k for s in layers for k in s.keep) + (descs, ph)
@@ -783,15 +786,16 @@ class SSDModel(object):
         return self._train_vars[key]
 
     def train_plan(self, B: int) -> Plan:
-        """Launch plan of the TRAINING-mode forward (``model(x, training=True)`` inside Keras ``fit``).  Graphs
-        without BatchNorm train on their inference plan."""
-        if not self.has_batchnorm:
-            return self.plan(B)
+        """Launch plan of the TRAINING-mode forward (``model(x, training=True)`` inside Keras ``fit``)."""
         if B not in self._train_plans:
             _ffi.check_device()
-            pb = _TrainPlanBuilder(self, B)
+            # graphs without BatchNorm train on the inference launch list, but layer by layer: the backward pass needs every
+            # layer as its own step (no fused tail)
+            pb = _TrainPlanBuilder(self, B) if self.has_batchnorm else _PlanBuilder(self, B)
             taps = GRAPHS[self.backbone](pb, pb.input(), self.hyper_params)
             pb.head(taps, self.hyper_params)
+            if not self.has_batchnorm:
+                pb.plan.hoist_heads()
             self._train_plans[B] = pb.plan
         return self._train_plans[B]
 

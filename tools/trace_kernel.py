@@ -73,7 +73,7 @@ def trace_nms(stress):
     import bench
     lib = _ffi.lib()
     buf = torch.zeros(ROLES * 512, dtype=torch.int64, device="cuda")
-    tags = {0: {1: "start", 2: "histogram", 3: "scatter", 4: "ranked", 5: "boxes_fetched", 6: "suppressed", 7: "merged", 8: "written"}}
+    tags = {0: {1: "start", 2: "histogram", 3: "scatter", 4: "ranked", 5: "boxes_fetched", 6: "suppressed", 7: "merged", 8: "written", 9: "fetched+bases", 10: "zeroed"}}
     if stress:
         lib.ssd_debug_trace(C.c_void_p(buf.data_ptr()))
         out = bench._box_kernel_rooflines(bench._peaks(), bench._hyper_params(), iters=1, warmup=1)
