@@ -762,11 +762,6 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
     p.BN = 128;
     if (cout16 <= 256) p.BN = cout16;
     else for (int bn = 256; bn >= 128; bn -= 64) if (cout16 % bn == 0) { p.BN = bn; break; }
-    const int tiles_n = (d->Cout + p.BN - 1) / p.BN;
-    p.acc_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
-    p.tmem_cols = 2 * p.acc_cols;                                  // double-buffered accumulator (<= 512 columns)
-    p.idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // f16 x f16 -> f32, K-major A and B
-
     int tiles_m;
     CUtensorMap map_a, map_b;
     if (!p.mode4d) {
@@ -802,6 +797,18 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
         if (rc) return rc;
         p.a_bytes = (uint32_t)(p.bw * p.bh * p.bb) * TC_BK * 2;
     }
+    // A layer whose tile grid leaves more than half of the SMs idle (M of a few thousand pixels: the 10x10 and 5x5 maps)
+    // gets narrower N tiles instead of split-K: the same number of CTAs without the fp32 partial planes and without the
+    // second launch that reduces them.  The narrowest of 128 / 64 that still fits one wave is taken.
+    const int sms = sm_count();
+    if (tiles_m * ((d->Cout + p.BN - 1) / p.BN) * 2 <= sms && p.BN >= 128 && d->Cout % 64 == 0) {
+        for (int bn = 128; bn >= 64; bn >>= 1)
+            if (bn < p.BN && d->Cout % bn == 0 && tiles_m * (d->Cout / bn) <= sms) p.BN = bn;
+    }
+    const int tiles_n = (d->Cout + p.BN - 1) / p.BN;
+    p.acc_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+    p.tmem_cols = 2 * p.acc_cols;                                  // double-buffered accumulator (<= 512 columns)
+    p.idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // f16 x f16 -> f32, K-major A and B
     {
         const uint64_t ktot = (uint64_t)taps * d->Cin;
         uint64_t dims[2] = {ktot, (uint64_t)d->Cout};
@@ -813,10 +820,10 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
     }
 
     // split-K when the tile grid cannot fill the SMs and K is deep (the multibox head)
-    const int sms = sm_count();
     int splits = 1;
     const int ctas = tiles_m * tiles_n;
-    if (ctas * 2 <= sms && p.n_kblocks >= 8) {
+    if (ctas * 4 <= sms && p.n_kblocks >= 8) {                     // (a grid that fills a quarter of the SMs runs as it is: the
+                                                                   //  reduction launch costs more than the idle SMs)
         splits = min(min((sms + ctas - 1) / ctas, p.n_kblocks / 4), 32);
         if (splits < 1) splits = 1;
     }
