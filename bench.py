@@ -59,10 +59,10 @@ def _peaks():
 
 def _ncu_traffic(kind, launches_per_step):
     """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the dominant kernel group, from the
-    committed ``ncu --set full`` capture of one step of this same workload (profiles/r1_traffic.json, written by
+    committed ``ncu --set full`` capture of one step of this same workload (profiles/r2_traffic.json, written by
     tools/ncu_traffic.py): the group's DRAM bytes per step / its launches per step, i.e. per launch like ``achieved``.
     None when no capture is committed for that group."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as f:

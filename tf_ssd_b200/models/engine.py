@@ -247,6 +247,7 @@ class Plan:
     # graph: it is forked (event wait on a side stream) right after the step that produces its tap and joined at the
     # end.  Inside a CUDA-graph capture this yields parallel graph branches; eagerly it is plain multi-stream overlap.
     PARALLEL_HEADS = os.environ.get("SSD_B200_PARALLEL_HEADS", "1") not in ("0", "")
+    _DEBUG_SKIP = frozenset(filter(None, os.environ.get("SSD_B200_DEBUG_SKIP_STEPS", "").split(",")))   # timing experiments only
 
     def run(self, first: int = 0, last: Optional[int] = None, u8: bool = False, parallel: Optional[bool] = None) -> None:
         parallel = self.PARALLEL_HEADS if parallel is None else parallel
@@ -254,6 +255,8 @@ class Plan:
         st = vp_main = _ffi.stream()
         used: Dict[int, torch.cuda.Stream] = {}
         for i, s in enumerate(self.steps[first:last], start=first):
+            if s.name in self._DEBUG_SKIP:
+                continue
             if u8 and i == 0:
                 s = self.first_u8
             if parallel and s.branch:

@@ -22,7 +22,7 @@ for what in "$@"; do
           python bench.py --profile-one-step > $OUT/launches_$tag.log 2>&1
       ;;
     conv)
-      ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"conv_tcgen05_kernel|conv_dwproj|conv_igemm|splitk" \
+      ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"conv_tcgen05_kernel|conv_dwproj|conv_irblock|conv_chain|stem_conv|conv_igemm|splitk|nms_|depthwise3x3" \
           -o $OUT/conv_$tag python bench.py --profile-one-step > $OUT/conv_$tag.log 2>&1
       ncu -i $OUT/conv_$tag.ncu-rep --page raw --csv > $OUT/conv_${tag}_raw.csv 2>/dev/null
       python tools/ncu_summary.py $OUT/conv_${tag}_raw.csv > $OUT/conv_${tag}_summary.csv 2>&1

@@ -21,7 +21,9 @@ def main(src, dst):
         if len(r) <= ti:
             continue
         nm = r[ki]
-        kind = "dwproj" if "dwproj" in nm else "conv" if ("conv_tcgen05" in nm or "conv_igemm" in nm or "splitk" in nm) else "dw" if "depthwise" in nm else None
+        kind = ("irblock" if "irblock" in nm else "dwproj" if "dwproj" in nm else "chain" if "conv_chain" in nm
+                else "stem" if "stem_conv" in nm else "decode_nms" if "nms_" in nm
+                else "conv" if ("conv_tcgen05" in nm or "conv_igemm" in nm or "splitk" in nm) else "dw" if "depthwise" in nm else None)
         if kind is None:
             continue
         e = out.setdefault(kind, {"launches": 0, "dram_bytes": 0.0, "time_ns": 0.0})
