@@ -273,6 +273,9 @@ int ssd_irblock_plan(const ssd_irblock_desc* h_desc, int32_t* h_out16);
  * ssd_combined_nms (role 0: phase boundaries of image 0): d_buf = device buffer of 8 x 512 uint64
  * (tools/trace_kernel.py); NULL switches it off. */
 int ssd_debug_trace(void* d_buf);
+/* Test hook for ssd_conv2d's CTA-pair (cta_group::2, M = 256) kernel: -1 automatic (layers with at least one tile per
+ * SM, full 128 / 256-wide N tiles, K >= 512), 0 never, 1 whenever the shape allows (small test shapes). */
+int ssd_debug_pair_mode(int mode);
 
 /* MobileNetV2 stem: keras_applications Conv1_pad + Conv1 (3x3, stride 2, Cin = 3) + bn_Conv1 +
  * Conv1_relu (models/ssd_mobilenet_v2.py:25), computed straight from the fp32 NHWC image
@@ -287,6 +290,17 @@ int ssd_stem_conv3x3s2(const float* d_img, const void* d_weight, const float* d_
 int ssd_stem_conv3x3s2_u8(const void* d_img_u8, const void* d_weight, const float* d_bias, void* d_out,
                           int B, int H, int W, int Cout, int Ho, int Wo, int pad_top, int pad_left, int act,
                           ssd_stream_t stream);
+
+/* The same first-layer kernel with the stride as a parameter: stride 2 / Cout 32 (MobileNetV2 Conv1, as above) and
+ * stride 1 / Cout 64 -- VGG16's conv1_1 (models/ssd_vgg16.py:80: Conv2D(64, 3x3, SAME, ReLU) on the image).  K = 27 is
+ * too shallow for the tensor-map path (nine 64-channel k-blocks for 3 real channels); here the layer is bound by
+ * writing its output. */
+int ssd_stem_conv3x3(const float* d_img, const void* d_weight, const float* d_bias, void* d_out,
+                     int B, int H, int W, int Cout, int Ho, int Wo, int stride, int pad_top, int pad_left, int act,
+                     ssd_stream_t stream);
+int ssd_stem_conv3x3_u8(const void* d_img_u8, const void* d_weight, const float* d_bias, void* d_out,
+                        int B, int H, int W, int Cout, int Ho, int Wo, int stride, int pad_top, int pad_left, int act,
+                        ssd_stream_t stream);
 
 /* Device-side input pipeline.  utils/data_utils.py:33-37: tf.image.convert_image_dtype(uint8 ->
  * float32) + tf.image.resize(img, (out_h, out_w)) (bilinear, half-pixel centres), optionally followed by

@@ -108,6 +108,34 @@ def test_conv2d_against_torch(case):
     assert _rel(got, ref) < 2e-3                       # fp16 output rounding only
 
 
+@pytest.mark.parametrize("case", [
+    # B, H, W, Cin, Cout, k, stride, dil, pads, act, residual
+    (2, 38, 38, 128, 256, 3, 1, 1, ((1, 1), (1, 1)), 1, False),     # VGG body: 23 M tiles (odd: phantom tile), one N tile
+    (3, 19, 19, 512, 512, 3, 1, 1, ((1, 1), (1, 1)), 1, False),     # two N tiles of 256
+    (2, 19, 19, 512, 1024, 3, 1, 6, ((6, 6), (6, 6)), 1, False),    # conv6: dilation 6
+    (4, 19, 19, 1024, 128, 1, 1, 1, ((0, 0), (0, 0)), 2, True),     # 1x1 (2-D operand maps), BN = 128, residual
+    (2, 20, 20, 256, 256, 3, 2, 1, ((0, 1), (0, 1)), 0, False),     # stride 2 through element strides
+])
+def test_conv2d_cta_pair_against_torch(case):
+    """The cta_group::2 kernel (two CTAs, one M = 256 tcgen05.mma, half of the weight tile per CTA) on shapes small
+    enough for a CPU check: forced through the test hook, since the automatic choice needs a tile per SM."""
+    from tf_ssd_b200 import _ffi
+    lib = _ffi.lib()
+    B, H, W, Cin, Cout, k, stride, dil, pads, act, use_res = case
+    _ffi.check(lib.ssd_debug_pair_mode(1))
+    try:
+        got, ref = _conv_case(B, H, W, Cin, Cout, k, stride, dil, pads, act, use_res, seed=3)
+    finally:
+        _ffi.check(lib.ssd_debug_pair_mode(-1))
+    assert _rel(got, ref) < 3e-3, _rel(got, ref)
+    _ffi.check(lib.ssd_debug_pair_mode(0))
+    try:
+        single, _ = _conv_case(B, H, W, Cin, Cout, k, stride, dil, pads, act, use_res, seed=3)
+    finally:
+        _ffi.check(lib.ssd_debug_pair_mode(-1))
+    assert np.array_equal(got, single), "the pair kernel must reproduce the single-CTA kernel bit for bit (same K order)"
+
+
 def test_conv2d_head_split_fp32():
     # head-style: two fp32 segments (A*L = 84 label channels, A*4 = 16 box channels)
     got, ref = _conv_case(2, 10, 10, 64, 100, 3, 1, 1, ((1, 1), (1, 1)), 0, False, seed=5, split=84, out_f32=True)
@@ -398,15 +426,15 @@ def test_every_layer_in_situ(backbone, B):
             x = mt["x"].half().float().cpu().permute(0, 3, 1, 2)          # the kernel rounds the image to fp16 first
             w = f32(mt["w"]).permute(0, 3, 1, 2)
             (pt, pb), (pl, pr) = mt["ph"], mt["pw"]
-            y = F.conv2d(F.pad(x, (pl, pr, pt, pb)), w, f32(mt["bias"]), stride=2)
-            y = torch.clamp(y, 0, 6).permute(0, 2, 3, 1).numpy()
+            y = F.conv2d(F.pad(x, (pl, pr, pt, pb)), w, f32(mt["bias"]), stride=mt["stride"])
+            y = (torch.clamp(y, 0, 6) if mt["act"] == 2 else torch.relu(y) if mt["act"] == 1 else y).permute(0, 2, 3, 1).numpy()
             assert _rel(f32(mt["out"]).numpy(), y) < 2e-3, s.name
         else:
             assert s.kind == "cast"
             continue
         checked += 1
     assert checked == plan.n_launches - sum(1 for s in plan.steps if s.kind == "cast")
-    assert any(s.kind == "stem" for s in plan.steps) == (backbone == "mobilenet_v2")
+    assert any(s.kind == "stem" for s in plan.steps)          # Conv1 (MobileNetV2) / conv1_1 (VGG16) read the image directly
     assert any(s.kind == "chain" for s in plan.steps)
 
 
@@ -563,6 +591,34 @@ def test_stem_kernel_shapes(H, W, pad):
     y = torch.clamp(y, 0, 6).permute(0, 2, 3, 1).numpy()
     assert y.shape == (B, Ho, Wo, 32)
     assert _rel(outs[0].float().cpu().numpy(), y) < 2e-3
+
+
+@pytest.mark.parametrize("H,W", [(300, 300), (33, 47), (5, 200), (1, 1)])
+def test_stem_kernel_stride1_vgg_first_layer(H, W):
+    """ssd_stem_conv3x3 / _u8 with stride 1, Cout 64, SAME padding (VGG16 conv1_1, models/ssd_vgg16.py:80)."""
+    from tf_ssd_b200 import _ffi
+    lib = _ffi.lib()
+    rng = np.random.default_rng(H * 1000 + W)
+    B = 2
+    u8 = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    x32 = u8.astype(np.float32) * np.float32(1.0 / 255.0)
+    w = (rng.standard_normal((64, 3, 3, 3)) * 0.3).astype(np.float16)
+    bias = rng.standard_normal(64).astype(np.float32)
+    xt, ut = torch.from_numpy(x32).cuda(), torch.from_numpy(u8).cuda()
+    wt, bt = torch.from_numpy(w).cuda(), torch.from_numpy(bias).cuda()
+    outs = []
+    for fn, src in ((lib.ssd_stem_conv3x3, xt), (lib.ssd_stem_conv3x3_u8, ut)):
+        out = torch.full((B, H, W, 64), float("nan"), dtype=torch.float16, device="cuda")
+        _ffi.check(fn(_ffi.ptr(src), _ffi.ptr(wt), _ffi.ptr(bt), _ffi.ptr(out), B, H, W, 64, H, W, 1, 1, 1, 1, _ffi.stream()))
+        outs.append(out)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    xr = torch.from_numpy(x32).half().float().permute(0, 3, 1, 2)
+    y = F.conv2d(xr, torch.from_numpy(w).float().permute(0, 3, 1, 2), torch.from_numpy(bias), padding=1)
+    y = torch.relu(y).permute(0, 2, 3, 1).numpy()
+    assert _rel(outs[0].float().cpu().numpy(), y) < 2e-3
+    # unsupported combinations are refused
+    assert lib.ssd_stem_conv3x3(_ffi.ptr(xt), _ffi.ptr(wt), _ffi.ptr(bt), _ffi.ptr(outs[0]), B, H, W, 48, H, W, 1, 1, 1, 1, _ffi.stream()) == -4
 
 
 @pytest.mark.parametrize("B", [1, 3, 5])

@@ -62,8 +62,11 @@ SIGNATURES = {
     "ssd_irblock_trace": (i, [vp]),
     "ssd_irblock_plan": (i, [C.POINTER(IrBlockDesc), C.POINTER(C.c_int32)]),
     "ssd_debug_trace": (i, [vp]),
+    "ssd_debug_pair_mode": (i, [i]),
     "ssd_stem_conv3x3s2": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
     "ssd_stem_conv3x3s2_u8": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
+    "ssd_stem_conv3x3": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),
+    "ssd_stem_conv3x3_u8": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),
     "ssd_image_to_f16c8": (i, [vp, vp, i64, vp]),
     "ssd_image_u8_to_f16c8": (i, [vp, vp, i64, vp]),
     "ssd_preprocess_image": (i, [vp, i, i, vp, i, i, i, vp]),

@@ -20,8 +20,8 @@ namespace ssd {
 
 constexpr int STEM_THREADS = 160;                  // 5 warps x 32 output pixels = one chunk of 160 pixels of a row
 constexpr int STEM_PIX = STEM_THREADS;
-constexpr int STEM_ROWLEN = STEM_PIX * 6 + 16;     // halves per staged row (pixel p's window starts at 6 p)
-constexpr int STEM_OSTRIDE = 40;                   // halves per pixel in the output tile (80 B: conflict-free, 16-B aligned)
+constexpr int STEM_ROWLEN = STEM_PIX * 6 + 16;     // halves per staged row (pixel p's window starts at 3 * stride * p)
+// halves per pixel in the output tile: Cout + 8 (80 B / 144 B: conflict-free, 16-byte aligned)
 
 __device__ __forceinline__ float stem_to_float(float v) { return v; }
 __device__ __forceinline__ float stem_to_float(uint8_t v) { return __fmul_rn((float)v, 1.0f / 255.0f); }
@@ -32,10 +32,15 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <typename TIn>
+// STRIDE 2, NT = 4: MobileNetV2's Conv1 (3 -> 32).  STRIDE 1, NT = 8: VGG16's conv1_1 (3 -> 64, models/ssd_vgg16.py:80) --
+// as a tensor-core layer its K = 27 would be padded to 9 k-blocks of 64 channels (1.1 ms per batch of 32, a third of the
+// whole VGG16 forward); here it is bound by writing its 369 MB output.
+template <typename TIn, int STRIDE, int NT>
 __global__ void __launch_bounds__(STEM_THREADS)
 stem_conv3x3s2_mma_kernel(const TIn* __restrict__ img, const __half* __restrict__ w, const float* __restrict__ bias,
                           __half* __restrict__ out, int H, int W, int Ho, int Wo, int pad_t, int pad_l, int act, int chunks) {
+    constexpr int STEP = 3 * STRIDE;                          // staged halves between neighbouring output pixels
+    constexpr int COUT = 8 * NT, STEM_OSTRIDE = COUT + 8;
     __shared__ __align__(16) __half srow[3][STEM_ROWLEN];
     __shared__ __align__(16) __half sout[STEM_PIX * STEM_OSTRIDE];
     pdl_trigger();
@@ -43,14 +48,14 @@ stem_conv3x3s2_mma_kernel(const TIn* __restrict__ img, const __half* __restrict_
     const int g = lane >> 2, t = lane & 3;
     const int oy = blockIdx.x / chunks, chunk = blockIdx.x - oy * chunks, b = blockIdx.y;
     const int ox0 = chunk * STEM_PIX;                       // first output pixel of this CTA
-    const int ix_first = ox0 * 2 - pad_l;                   // input column of staged element 0
+    const int ix_first = ox0 * STRIDE - pad_l;              // input column of staged element 0
 
-    // B fragments (weights OHWI [32][27] fp16, k = (ky*3+kx)*3+ci, zero for k >= 27): n = 8 j + g
-    uint32_t bf[2][4][2];
+    // B fragments (weights OHWI [Cout][27] fp16, k = (ky*3+kx)*3+ci, zero for k >= 27): n = 8 j + g
+    uint32_t bf[2][NT][2];
 #pragma unroll
     for (int s = 0; s < 2; ++s)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < NT; ++j)
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const int k = 16 * s + 8 * r + 2 * t;
@@ -62,10 +67,10 @@ stem_conv3x3s2_mma_kernel(const TIn* __restrict__ img, const __half* __restrict_
     pdl_wait();
 
     // ---- stage the three input rows as fp16 (zero outside the image) -------------------------------------
-    const int need = min(STEM_PIX, Wo - ox0) * 6 + 3;        // staged halves actually read by valid pixels
+    const int need = min(STEM_PIX, Wo - ox0) * STEP + (9 - STEP);     // staged halves actually read by valid pixels
     const TIn* base = img + (size_t)b * H * W * 3;
     for (int ky = 0; ky < 3; ++ky) {
-        const int iy = oy * 2 - pad_t + ky;
+        const int iy = oy * STRIDE - pad_t + ky;
         __half* dst = srow[ky];
         if ((unsigned)iy >= (unsigned)H) {
             for (int e = tid; e < STEM_ROWLEN; e += STEM_THREADS) dst[e] = __float2half(0.f);
@@ -103,7 +108,7 @@ stem_conv3x3s2_mma_kernel(const TIn* __restrict__ img, const __half* __restrict_
     __syncthreads();
 
     // ---- 32 pixels x 32 channels per warp --------------------------------------------------------------------
-    // A fragment element (row = pixel, k): k -> (ky = k / 9, j = k % 9) lives at srow[ky][6 * pixel + j]
+    // A fragment element (row = pixel, k): k -> (ky = k / 9, j = k % 9) lives at srow[ky][STEP * pixel + j]
     int koff[8];                                              // staged offset of this thread's 8 k values (-1: zero)
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -111,16 +116,16 @@ stem_conv3x3s2_mma_kernel(const TIn* __restrict__ img, const __half* __restrict_
         koff[q] = k < 27 ? (k / 9) * STEM_ROWLEN + (k % 9) : -1;
     }
     const __half* sflat = &srow[0][0];
-    float acc[2][4][4];
+    float acc[2][NT][4];
 #pragma unroll
     for (int m = 0; m < 2; ++m)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < NT; ++j)
 #pragma unroll
             for (int r = 0; r < 4; ++r) acc[m][j][r] = 0.f;
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
-        const int p0 = (warp * 32 + m * 16 + g) * 6, p1 = p0 + 8 * 6;
+        const int p0 = (warp * 32 + m * 16 + g) * STEP, p1 = p0 + 8 * STEP;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             uint32_t a[4];
@@ -135,14 +140,14 @@ stem_conv3x3s2_mma_kernel(const TIn* __restrict__ img, const __half* __restrict_
                 a[r * 2 + 1] = (uint32_t)x10 | ((uint32_t)x11 << 16);      // (row g + 8, k pair)
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) mma16816(acc[m][j], a, bf[s][j][0], bf[s][j][1]);
+            for (int j = 0; j < NT; ++j) mma16816(acc[m][j], a, bf[s][j][0], bf[s][j][1]);
         }
     }
 
     // ---- bias + activation -> fp16 tile -> coalesced 16-byte stores ------------------------------------------
     const float lo = act == SSD_ACT_NONE ? -INFINITY : 0.0f, hi = act == SSD_ACT_RELU6 ? 6.0f : INFINITY;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NT; ++j) {
         const int c = 8 * j + 2 * t;
         const float b0 = bias ? __ldg(bias + c) : 0.f, b1 = bias ? __ldg(bias + c + 1) : 0.f;
 #pragma unroll
@@ -156,23 +161,25 @@ stem_conv3x3s2_mma_kernel(const TIn* __restrict__ img, const __half* __restrict_
     }
     __syncthreads();
     const int npix = min(STEM_PIX, Wo - ox0);
-    uint4* orow = reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox0) * 32);
-    for (int i = tid; i < npix * 4; i += STEM_THREADS)
-        orow[i] = *reinterpret_cast<const uint4*>(&sout[(i >> 2) * STEM_OSTRIDE + (i & 3) * 8]);
+    uint4* orow = reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox0) * COUT);
+    for (int i = tid; i < npix * NT; i += STEM_THREADS)
+        orow[i] = *reinterpret_cast<const uint4*>(&sout[(i / NT) * STEM_OSTRIDE + (i % NT) * 8]);
 }
 
 template <typename TIn>
 static int stem_launch(const TIn* d_img, const void* d_weight, const float* d_bias, void* d_out, int B, int H, int W,
-                       int Cout, int Ho, int Wo, int pad_top, int pad_left, int act, ssd_stream_t stream, const char* who) {
+                       int Cout, int Ho, int Wo, int stride, int pad_top, int pad_left, int act, ssd_stream_t stream, const char* who) {
     SSD_REQUIRE_PTR(d_img); SSD_REQUIRE_PTR(d_weight); SSD_REQUIRE_PTR(d_out);
     SSD_REQUIRE(B >= 1 && H >= 1 && W >= 1 && Ho >= 1 && Wo >= 1 && act >= SSD_ACT_NONE && act <= SSD_ACT_RELU6 &&
                 pad_top >= 0 && pad_left >= 0 && pad_top <= 1 && pad_left <= 1 && B <= 65535,
                 SSD_ERR_SHAPE, "%s: bad shape B=%d H=%d W=%d Ho=%d Wo=%d act=%d pad=%d,%d", who, B, H, W, Ho, Wo, act, pad_top, pad_left);
-    SSD_REQUIRE(Cout == 32, SSD_ERR_UNSUPPORTED, "%s: Cout=%d (this build instantiates Cout == 32)", who, Cout);
-    SSD_REQUIRE((Ho - 1) * 2 - pad_top + 2 <= H && (Wo - 1) * 2 - pad_left + 2 <= W,     // at most one padded row / column after
-                SSD_ERR_SHAPE, "%s: output %dx%d does not fit input %dx%d with stride 2", who, Ho, Wo, H, W);
+    SSD_REQUIRE((stride == 2 && Cout == 32) || (stride == 1 && Cout == 64), SSD_ERR_UNSUPPORTED,
+                "%s: stride=%d Cout=%d (this build instantiates stride 2 / Cout 32 and stride 1 / Cout 64)", who, stride, Cout);
+    SSD_REQUIRE((Ho - 1) * stride - pad_top + 2 <= H && (Wo - 1) * stride - pad_left + 2 <= W,     // at most one padded row / column after
+                SSD_ERR_SHAPE, "%s: output %dx%d does not fit input %dx%d with stride %d", who, Ho, Wo, H, W, stride);
     const int chunks = ceil_div(Wo, STEM_PIX);
-    cudaError_t le = launch_pdl(stem_conv3x3s2_mma_kernel<TIn>, dim3(Ho * chunks, B), dim3(STEM_THREADS), 0, as_stream(stream),
+    auto kern = stride == 2 ? stem_conv3x3s2_mma_kernel<TIn, 2, 4> : stem_conv3x3s2_mma_kernel<TIn, 1, 8>;
+    cudaError_t le = launch_pdl(kern, dim3(Ho * chunks, B), dim3(STEM_THREADS), 0, as_stream(stream),
                                 d_img, reinterpret_cast<const __half*>(d_weight), d_bias, reinterpret_cast<__half*>(d_out),
                                 H, W, Ho, Wo, pad_top, pad_left, act, chunks);
     if (le != cudaSuccess) return cuda_fail(le, "stem_conv3x3s2_mma_kernel");
@@ -199,15 +206,29 @@ using namespace ssd;
 extern "C" int ssd_stem_conv3x3s2(const float* d_img, const void* d_weight, const float* d_bias, void* d_out,
                                   int B, int H, int W, int Cout, int Ho, int Wo, int pad_top, int pad_left, int act,
                                   ssd_stream_t stream) {
-    return stem_launch<float>(d_img, d_weight, d_bias, d_out, B, H, W, Cout, Ho, Wo, pad_top, pad_left, act, stream,
+    return stem_launch<float>(d_img, d_weight, d_bias, d_out, B, H, W, Cout, Ho, Wo, 2, pad_top, pad_left, act, stream,
                               "ssd_stem_conv3x3s2");
+}
+
+extern "C" int ssd_stem_conv3x3(const float* d_img, const void* d_weight, const float* d_bias, void* d_out,
+                                int B, int H, int W, int Cout, int Ho, int Wo, int stride, int pad_top, int pad_left, int act,
+                                ssd_stream_t stream) {
+    return stem_launch<float>(d_img, d_weight, d_bias, d_out, B, H, W, Cout, Ho, Wo, stride, pad_top, pad_left, act, stream,
+                              "ssd_stem_conv3x3");
+}
+
+extern "C" int ssd_stem_conv3x3_u8(const void* d_img_u8, const void* d_weight, const float* d_bias, void* d_out,
+                                   int B, int H, int W, int Cout, int Ho, int Wo, int stride, int pad_top, int pad_left, int act,
+                                   ssd_stream_t stream) {
+    return stem_launch<uint8_t>(static_cast<const uint8_t*>(d_img_u8), d_weight, d_bias, d_out, B, H, W, Cout, Ho, Wo,
+                                stride, pad_top, pad_left, act, stream, "ssd_stem_conv3x3_u8");
 }
 
 extern "C" int ssd_stem_conv3x3s2_u8(const void* d_img_u8, const void* d_weight, const float* d_bias, void* d_out,
                                      int B, int H, int W, int Cout, int Ho, int Wo, int pad_top, int pad_left, int act,
                                      ssd_stream_t stream) {
     return stem_launch<uint8_t>(static_cast<const uint8_t*>(d_img_u8), d_weight, d_bias, d_out, B, H, W, Cout, Ho, Wo,
-                                pad_top, pad_left, act, stream, "ssd_stem_conv3x3s2_u8");
+                                2, pad_top, pad_left, act, stream, "ssd_stem_conv3x3s2_u8");
 }
 
 extern "C" int ssd_image_u8_to_f16c8(const void* d_img_u8, void* d_out, int64_t n_pixels, ssd_stream_t stream) {

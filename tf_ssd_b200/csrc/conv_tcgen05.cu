@@ -269,6 +269,258 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     conv_tcgen05_body(map_a, map_b, map_o, p);
 }
 // ======================================================================================
+// The same implicit GEMM on a CTA PAIR (cta_group::2): the VGG16 body.  Two CTAs of a cluster (the two SMs of a TPC)
+// execute ONE tcgen05.mma of M = 256: each CTA stages its own 128 output pixels of A and only HALF of the weight tile
+// (BN/2 rows), the leader's MMA reads both halves -- per CTA and k-block 16 KB + BN/2 x 128 B instead of 16 KB +
+// BN x 128 B, i.e. two thirds of the operand traffic that bounds the 3x3 layers (im2col re-reads the activation nine
+// times and every M tile re-reads the weights), and a deeper ring in the same shared memory.
+//   * both CTAs issue their TMA loads with .cta_group::2 and signal the LEADER's "full" barrier (expect_tx there counts
+//     the bytes of both); the leader's single thread issues tcgen05.mma.cta_group::2; tcgen05.commit multicasts the
+//     "stage empty" / "accumulator full" arrivals to the barriers of both CTAs;
+//   * every CTA drains its own 128 TMEM lanes; the peer's epilogue warps arrive remotely (mapa) on the leader's
+//     "accumulator empty" barrier;
+//   * cluster barriers after the barrier initialisation and before the TMEM deallocation.
+// fp16 single-segment outputs (TMA-store epilogue) without split-K only; an odd number of M tiles leaves a phantom
+// tile whose loads are zero-filled and whose stores are clipped by the tensor maps.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {          // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+conv_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         const __grid_constant__ CUtensorMap map_o, const __grid_constant__ TcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_stage = TC_BM * TC_BK * 2;                 // 16 KB: this CTA's 128 pixels
+    const uint32_t b_stage = (uint32_t)(p.BN / 2) * TC_BK * 2;  // this CTA's half of the weight tile
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + p.stages * a_stage;
+    unsigned char* sOut = sB + p.stages * b_stage;
+    float* sBias = reinterpret_cast<float*>(sOut + 2 * TC_OUT_TILE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + TC_OUT_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_PAIR_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const uint32_t bar_full = smem_addr(bars), bar_empty = smem_addr(bars + TC_PAIR_STAGES);
+    const uint32_t bar_tfull = smem_addr(bars + 2 * TC_PAIR_STAGES), bar_tempty = smem_addr(bars + 2 * TC_PAIR_STAGES + 2);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_o);
+        for (int s = 0; s < TC_PAIR_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);                      // leader: one arrive.expect_tx (+ the TMA bytes of both CTAs)
+            mbar_init(bar_empty + 8 * s, 1);                     // one multicast tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);                     // one multicast tcgen05.commit
+            mbar_init(bar_tempty + 8 * a, 2 * TC_EPI_WARPS);     // leader: the epilogue warps of both CTAs
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {                                             // one warp of EACH CTA takes part in the pair allocation
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_addr(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_barrier();                                           // barriers of both CTAs are initialised, TMEM is allocated
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int pair_m = (p.tiles_m + 1) >> 1;                     // pairs of M tiles
+    const int n_pair_tiles = pair_m * p.tiles_n;
+    const int n_pairs = (int)gridDim.x >> 1, pair_id = (int)blockIdx.x >> 1;
+    const uint32_t full_leader = mapa_rank(bar_full, 0);         // the leader's "full" barriers in cluster address space
+
+    if (warp == 0) {
+        // ===================== TMA producer (one elected lane of each CTA) =====================
+        if (lane == 0) {
+            int it = 0, s = 0;
+            uint32_t ph = 0;
+            for (int t = pair_id; t < n_pair_tiles; t += n_pairs) {
+                const int pm = t / p.tiles_n, tn = t - pm * p.tiles_n;
+                const int tm_ = 2 * pm + (int)rank;
+                int b0 = 0, oy0 = 0, ox0 = 0;
+                if (p.mode4d) {
+                    const int per_img = p.tiles_w * p.tiles_h;
+                    const int tb = tm_ / per_img, tr = tm_ - tb * per_img;
+                    const int th = tr / p.tiles_w, tw = tr - th * p.tiles_w;
+                    b0 = tb * p.bb; oy0 = th * p.bh; ox0 = tw * p.bw;
+                }
+                for (int kb = 0; kb < p.n_kblocks; ++kb, ++it) {
+                    if (it >= p.stages) mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                    const int tap = kb / p.kb_per_tap, c0 = (kb - tap * p.kb_per_tap) * TC_BK;
+                    if (leader) mbar_expect_tx(bar_full + 8 * s, 2u * (p.a_bytes + p.b_bytes));    // p.b_bytes: one half
+                    const uint32_t dst_a = smem_addr(sA + (size_t)s * a_stage), dst_b = smem_addr(sB + (size_t)s * b_stage);
+                    const uint32_t bar = full_leader + 8 * s;
+                    if (p.mode4d) {
+                        const int ky = tap / p.KW, kx = tap - ky * p.KW;
+                        tma2_load_4d(dst_a, &map_a, bar, c0, ox0 * p.stride + kx * p.dil - p.pad_l,
+                                     oy0 * p.stride + ky * p.dil - p.pad_t, b0);
+                    } else {
+                        tma2_load_2d(dst_a, &map_a, bar, c0, tm_ * TC_BM);
+                    }
+                    tma2_load_2d(dst_b, &map_b, bar, tap * p.Cin + c0, tn * p.BN + (int)rank * (p.BN / 2));
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer: the leader's elected lane, M = 256 over both CTAs =====================
+        if (leader && lane == 0) {
+            int j = 0, s = 0;
+            uint32_t ph = 0;
+            for (int t = pair_id; t < n_pair_tiles; t += n_pairs, ++j) {
+                const int a = j & 1;
+                if (j >= 2) mbar_wait(bar_tempty + 8 * a, ((j >> 1) - 1) & 1);      // both epilogues drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tacc = tmem_base + (uint32_t)a * p.acc_cols;
+                for (int kb = 0; kb < p.n_kblocks; ++kb) {
+                    mbar_wait(bar_full + 8 * s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t da = umma_desc_sw128(smem_addr(sA + (size_t)s * a_stage));
+                    const uint64_t db = umma_desc_sw128(smem_addr(sB + (size_t)s * b_stage));
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k)
+                        umma2_f16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (kb > 0) || k > 0);
+                    umma2_commit(bar_empty + 8 * s);             // frees the stage in both CTAs
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
+                umma2_commit(bar_tfull + 8 * a);                 // accumulator complete, in both CTAs
+            }
+        }
+    } else {
+        // ===================== epilogue: as conv_tcgen05_kernel's TMA-store path, on this CTA's 128 rows =====================
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        const int r = q * 32 + lane;
+        const bool elected = ew == 0 && lane == 0;
+        int bias_tn = -1;
+        const float act_lo = p.act == SSD_ACT_NONE ? -__int_as_float(0x7f800000) : 0.0f;
+        const float act_hi = p.act == SSD_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
+        const uint32_t tempty_leader = mapa_rank(bar_tempty, 0);
+        int j = 0;
+        uint32_t n_groups = 0;
+        for (int t = pair_id; t < n_pair_tiles; t += n_pairs, ++j) {
+            const int pm = t / p.tiles_n, tn = t - pm * p.tiles_n;
+            const int tm_ = 2 * pm + (int)rank;
+            const int n0 = tn * p.BN;
+            const int a = j & 1;
+            mbar_wait(bar_tfull + 8 * a, (j >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            int b = 0, pix = 0;
+            const bool row_ok = tc_row_to_pixel(p, tm_, r, b, pix);
+            const long long row_off = (long long)b * p.img0 + (long long)pix * p.pix0;
+            const uint32_t trow = tmem_base + (uint32_t)a * p.acc_cols + ((uint32_t)(q * 32) << 16);
+            int ox0 = 0, oy0 = 0, b0 = 0;
+            if (p.mode4d) {
+                const int per_img = p.tiles_w * p.tiles_h;
+                const int tb = tm_ / per_img, tr = tm_ - tb * per_img;
+                const int th = tr / p.tiles_w, tw = tr - th * p.tiles_w;
+                b0 = tb * p.bb; oy0 = th * p.bh; ox0 = tw * p.bw;
+            }
+            if (bias_tn != tn) {
+                const int i = ew * 32 + lane;
+                sBias[i] = (p.bias && i < p.BN && n0 + i < p.Cout) ? __ldg(p.bias + n0 + i) : 0.0f;
+                bias_tn = tn;
+            }
+            for (int g0 = 0; g0 < p.BN && n0 + g0 < p.Cout; g0 += 64, ++n_groups) {
+                unsigned char* buf = sOut + (n_groups & 1u) * TC_OUT_TILE;
+                const int c0 = g0 + half * TC_CHUNK;
+                const bool mine = c0 < p.BN && n0 + c0 < p.Cout;
+                uint32_t acc[TC_CHUNK];
+                if (mine) tmem_ld32(trow + (uint32_t)c0, acc);
+                if (elected) bulk_wait_read<1>();
+                epi_barrier();
+                if (mine) {
+                    const int n = n0 + c0;
+                    const int ncols = min(TC_CHUNK, p.Cout - n);
+                    const float* sbias = sBias + c0;
+                    tmem_ld_wait(acc);
+#pragma unroll
+                    for (int h = 0; h < TC_CHUNK / 8; ++h) {
+                        const float4 b0v = *reinterpret_cast<const float4*>(sbias + h * 8);
+                        const float4 b1v = *reinterpret_cast<const float4*>(sbias + h * 8 + 4);
+                        const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
+                        float v[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            v[e] = fminf(fmaxf(__uint_as_float(acc[h * 8 + e]) + bb[e], act_lo), act_hi);
+                        if (p.res && row_ok && h * 8 < ncols) {
+                            const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + row_off + n + h * 8));
+                            const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __half22float2(rh[e]);
+                                v[2 * e] += f.x; v[2 * e + 1] += f.y;
+                            }
+                        }
+                        uint4 o;
+                        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                        *reinterpret_cast<uint4*>(buf + r * 128 + (((half * 4 + h) ^ (r & 7)) << 4)) = o;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                epi_barrier();
+                if (elected) {
+                    if (p.mode4d) tma_store_4d(&map_o, smem_addr(buf), n0 + g0, ox0, oy0, b0);
+                    else          tma_store_2d(&map_o, smem_addr(buf), n0 + g0, tm_ * TC_BM);
+                    bulk_commit();
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * a);     // the leader's MMA thread waits for both CTAs
+        }
+        if (elected) bulk_wait_all();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_barrier();                                           // nobody leaves while the peer may still signal or be read
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// ======================================================================================
 // Fused DepthwiseConv2D 3x3 -> 1x1 Conv2D (the tail of a MobileNetV2 inverted-residual block).
 //
 //   warp 0      TMA: per k-block (64 expanded channels) the INPUT PATCH of the tile -- (bw-1)s+3 x (bh-1)s+3 x bb
@@ -735,6 +987,13 @@ static int partial_workspace(const void* out_key, size_t bytes, float** out) {
     return SSD_OK;
 }
 
+static int pair_mode_from_env() {
+    const char* e = getenv("SSD_B200_PAIR");
+    return e ? atoi(e) : -1;
+}
+static int g_pair_mode = pair_mode_from_env();
+void conv_tcgen05_set_pair_mode(int mode) { g_pair_mode = mode; }
+
 bool conv_tcgen05_supported(const ssd_conv_desc* d) {
     return (d->stride == 1 || d->stride == 2) && d->Cin % 8 == 0 && d->KH == d->KW && d->KH * d->KW <= 49 &&
            (reinterpret_cast<uintptr_t>(d->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0;
@@ -861,6 +1120,44 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
         if (rc) return rc;
         p.tma_store = 1;
     }
+    // ---- CTA pair (cta_group::2, M = 256): deep-K layers with full 128 / 256-wide N tiles and at least one tile per SM
+    //      (the VGG16 body and its gradients).  -1: automatic, 0: never, 1: whenever the shape allows (tests).
+    if (splits == 1 && p.tma_store && (p.BN == 256 || p.BN == 128) && d->Cout % p.BN == 0 && p.n_kblocks >= 8 &&
+        g_pair_mode != 0 && (g_pair_mode == 1 || tiles_m * tiles_n >= sms)) {
+        CUtensorMap map_b2;
+        {
+            const uint64_t ktot = (uint64_t)taps * d->Cin;
+            uint64_t dims[2] = {ktot, (uint64_t)d->Cout};
+            uint64_t str[1] = {ktot * 2};
+            uint32_t box[2] = {TC_BK, (uint32_t)p.BN / 2};
+            int rc = cached_map(&map_b2, d->weight, 2, dims, str, box);
+            if (rc) return rc;
+        }
+        TcParams q = p;
+        q.b_bytes = (uint32_t)(p.BN / 2) * TC_BK * 2;
+        q.idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        auto smem_pair = [&](int stages) {
+            return (size_t)stages * (TC_BM * TC_BK * 2 + (size_t)(p.BN / 2) * TC_BK * 2) + (size_t)TC_OUT_BYTES +
+                   (2 * TC_PAIR_STAGES + 4) * 8 + 16 + 1024;
+        };
+        q.stages = min(TC_PAIR_STAGES, p.n_kblocks);
+        while (q.stages > 2 && smem_pair(q.stages) > (size_t)226 * 1024) --q.stages;
+        static thread_local int pair_attr_dev = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (pair_attr_dev != dev) {
+            cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return cuda_fail(e, "conv_tcgen05 (pair): cudaFuncSetAttribute");
+            pair_attr_dev = dev;
+        }
+        const int n_pair_tiles = ((tiles_m + 1) / 2) * tiles_n;
+        const int pairs = max(1, min(n_pair_tiles, sms / 2));
+        conv_tcgen05_pair_kernel<<<dim3(2 * pairs), dim3(TC_THREADS), smem_pair(q.stages), st>>>(map_a, map_b2, map_o, q);
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) return cuda_fail(le, "conv_tcgen05_pair_kernel");
+        return SSD_OK;
+    }
+
     // Operand ring depth and CTAs per SM.  A tile with few k-blocks (1x1 convolutions with Cin <= 128: every MobileNetV2
     // expand layer up to block 13) cannot use a deep ring; its persistent loop is bound by the latency of the epilogue's
     // dependent instruction chain, so a shallower ring that lets TWO CTAs share an SM (shared memory <= 113 KB and
@@ -900,6 +1197,14 @@ int conv_tcgen05_launch(const ssd_conv_desc* d, cudaStream_t st) {
     }
     return SSD_OK;
 }
+
+}  // namespace ssd
+// Debug / test hook: -1 automatic (CTA pairs for layers with at least one tile per SM), 0 never, 1 whenever the shape allows.
+extern "C" int ssd_debug_pair_mode(int mode) {
+    ssd::conv_tcgen05_set_pair_mode(mode);
+    return SSD_OK;
+}
+namespace ssd {
 
 // Fused DepthwiseConv2D 3x3 (+ folded BN + activation) -> 1x1 Conv2D (+ folded BN, residual): the "depthwise ->
 // project" tail of a MobileNetV2 inverted-residual block as ONE launch.  GEMM view: M = B*Ho*Wo pixels,

@@ -12,6 +12,7 @@ namespace ssd {
 constexpr int TC_BM = 128;           // UMMA M (one CTA, cta_group::1)
 constexpr int TC_BK = 64;            // 64 fp16 = 128 B = one swizzle row
 constexpr int TC_STAGES = 4;
+constexpr int TC_PAIR_STAGES = 6;     // operand ring of the CTA-pair kernel (half the weight bytes per stage)
 constexpr int TC_EPI_WARPS = 8;      // two warps per TMEM lane quarter (they split the column chunks)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..9: epilogue
 // fused depthwise -> 1x1 kernel: roles on warpgroup boundaries (setmaxnreg works per warpgroup) -- warpgroup 0: warp 0 TMA,

@@ -378,6 +378,7 @@ class _PlanBuilder:
         self.dev = _ffi.require_cuda()
         self.lib = _ffi.lib()
         self.plan = Plan(B, model.img_size, self.dev)
+        self.no_stem = False            # training plans keep the first layer on the generic path (its filter gradient reads the fp16 image)
 
     def _buf(self, H, W, C) -> torch.Tensor:
         return torch.empty((self.B, H, W, C), dtype=torch.float16, device=self.dev)
@@ -398,20 +399,21 @@ class _PlanBuilder:
                                   (_ffi.ptr(self.plan.image_u8), _ffi.ptr(x), npx), 0.0, npx * (3 + 16), (x,))
         return Act(x, S, S, 8)
 
-    def _stem(self, x, name, cout, ph, pw, act, bn):
-        Ho, Wo = _out_size(x.H, 3, 2, 1, ph), _out_size(x.W, 3, 2, 1, pw)
+    def _stem(self, x, name, cout, stride, ph, pw, act, bn):
+        """The first layer straight from the image (float32 or uint8): MobileNetV2's Conv1 (3x3 stride 2 -> 32) and
+        VGG16's conv1_1 (3x3 stride 1 -> 64)."""
+        Ho, Wo = _out_size(x.H, 3, stride, 1, ph), _out_size(x.W, 3, stride, 1, pw)
         w, b = self.m._packed_conv(name, bn, 3)
         out = self._buf(Ho, Wo, cout)
         args = (_ffi.ptr(self.plan.image), _ffi.ptr(w), _ffi.ptr(b), _ffi.ptr(out), self.B, x.H, x.W, cout, Ho, Wo,
-                ph[0], pw[0], act)
+                stride, ph[0], pw[0], act)
         nbytes = self.B * (x.H * x.W * 3 * 4 + Ho * Wo * cout * 2) + 27 * cout * 2
-        self.plan.steps.append(Step(name, "stem", self.lib.ssd_stem_conv3x3s2, args, 2.0 * self.B * Ho * Wo * 27 * cout,
-                                    nbytes, (w, b, out),
-                                    dict(x=self.plan.image, w=w, bias=b, out=out, ph=ph, pw=pw, act=act)))
-        self.plan.first_u8 = Step(name + "_u8", "stem", self.lib.ssd_stem_conv3x3s2_u8,
+        meta = dict(w=w, bias=b, out=out, ph=ph, pw=pw, act=act, stride=stride)
+        self.plan.steps.append(Step(name, "stem", self.lib.ssd_stem_conv3x3, args, 2.0 * self.B * Ho * Wo * 27 * cout,
+                                    nbytes, (w, b, out), dict(meta, x=self.plan.image)))
+        self.plan.first_u8 = Step(name + "_u8", "stem", self.lib.ssd_stem_conv3x3_u8,
                                   (_ffi.ptr(self.plan.image_u8),) + args[1:], 2.0 * self.B * Ho * Wo * 27 * cout,
-                                  nbytes - self.B * x.H * x.W * 9, (w, b, out),
-                                  dict(x=self.plan.image_u8, w=w, bias=b, out=out, ph=ph, pw=pw, act=act))
+                                  nbytes - self.B * x.H * x.W * 9, (w, b, out), dict(meta, x=self.plan.image_u8))
         return Act(out, Ho, Wo, cout)
 
     def _emit_conv(self, name, x: Act, w: torch.Tensor, bias, cout, k, stride, dilation, ph, pw, act,
@@ -445,8 +447,9 @@ class _PlanBuilder:
              residual=None, init=None, l2=False, tap=False):
         ph, pw = _resolve_pads(x.H, x.W, k, stride, dilation, pad)
         if x.t is None:                                  # first layer, fed by the fp32 image
-            if k == 3 and stride == 2 and dilation == 1 and cout == 32 and residual is None:
-                return self._stem(x, name, cout, ph, pw, act, bn)
+            if (k == 3 and dilation == 1 and residual is None and (stride, cout) in ((2, 32), (1, 64)) and not self.no_stem
+                    and ph[0] <= 1 and pw[0] <= 1):
+                return self._stem(x, name, cout, stride, ph, pw, act, bn)
             x = self._image_as_f16()
         w, b = self.m._packed_conv(name, bn, x.C)
         Ho, Wo = _out_size(x.H, k, stride, dilation, ph), _out_size(x.W, k, stride, dilation, pw)
@@ -795,6 +798,7 @@ class SSDModel(object):
             # graphs without BatchNorm train on the inference launch list, but layer by layer: the backward pass needs every
             # layer as its own step (no fused tail)
             pb = _TrainPlanBuilder(self, B) if self.has_batchnorm else _PlanBuilder(self, B)
+            pb.no_stem = True
             taps = GRAPHS[self.backbone](pb, pb.input(), self.hyper_params)
             pb.head(taps, self.hyper_params)
             if not self.has_batchnorm:
