@@ -301,6 +301,12 @@ int ssd_stem_conv3x3(const float* d_img, const void* d_weight, const float* d_bi
 int ssd_stem_conv3x3_u8(const void* d_img_u8, const void* d_weight, const float* d_bias, void* d_out,
                         int B, int H, int W, int Cout, int Ho, int Wo, int stride, int pad_top, int pad_left, int act,
                         ssd_stream_t stream);
+/* Training-plan form: the image as fp16 NHWC with 8 channels (ssd_image_to_f16c8's output, which the first layer's
+ * filter gradient reads) and the weights in the zero-padded OHWI [Cout,3,3,8] layout of ssd_conv2d / ssd_conv2d_wgrad,
+ * so the forward of conv1_1 / Conv1 shares its variables with the backward kernels. */
+int ssd_stem_conv3x3_f16c8(const void* d_img_f16c8, const void* d_weight_ohwi8, const float* d_bias, void* d_out,
+                           int B, int H, int W, int Cout, int Ho, int Wo, int stride, int pad_top, int pad_left, int act,
+                           ssd_stream_t stream);
 
 /* Device-side input pipeline.  utils/data_utils.py:33-37: tf.image.convert_image_dtype(uint8 ->
  * float32) + tf.image.resize(img, (out_h, out_w)) (bilinear, half-pixel centres), optionally followed by

@@ -67,6 +67,7 @@ SIGNATURES = {
     "ssd_stem_conv3x3s2_u8": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
     "ssd_stem_conv3x3": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),
     "ssd_stem_conv3x3_u8": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),
+    "ssd_stem_conv3x3_f16c8": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),
     "ssd_image_to_f16c8": (i, [vp, vp, i64, vp]),
     "ssd_image_u8_to_f16c8": (i, [vp, vp, i64, vp]),
     "ssd_preprocess_image": (i, [vp, i, i, vp, i, i, i, vp]),

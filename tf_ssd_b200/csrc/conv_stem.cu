@@ -25,6 +25,9 @@ constexpr int STEM_ROWLEN = STEM_PIX * 6 + 16;     // halves per staged row (pix
 
 __device__ __forceinline__ float stem_to_float(float v) { return v; }
 __device__ __forceinline__ float stem_to_float(uint8_t v) { return __fmul_rn((float)v, 1.0f / 255.0f); }
+// third input form: the fp16 NHWC image with the channel axis padded to 8 (what ssd_image_to_f16c8 writes and what the
+// first layer's filter gradient reads in the training plan)
+struct HalfC8 { __half c[8]; };
 
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -38,7 +41,8 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 template <typename TIn, int STRIDE, int NT>
 __global__ void __launch_bounds__(STEM_THREADS)
 stem_conv3x3s2_mma_kernel(const TIn* __restrict__ img, const __half* __restrict__ w, const float* __restrict__ bias,
-                          __half* __restrict__ out, int H, int W, int Ho, int Wo, int pad_t, int pad_l, int act, int chunks) {
+                          __half* __restrict__ out, int H, int W, int Ho, int Wo, int pad_t, int pad_l, int act, int chunks,
+                          int w_cin) {
     constexpr int STEP = 3 * STRIDE;                          // staged halves between neighbouring output pixels
     constexpr int COUT = 8 * NT, STEM_OSTRIDE = COUT + 8;
     __shared__ __align__(16) __half srow[3][STEM_ROWLEN];
@@ -58,10 +62,11 @@ stem_conv3x3s2_mma_kernel(const TIn* __restrict__ img, const __half* __restrict_
         for (int j = 0; j < NT; ++j)
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
+                // weights OHWI [Cout][3][3][w_cin] (w_cin = 3, or 8 for the zero-padded layout of the tensor-map path)
                 const int k = 16 * s + 8 * r + 2 * t;
-                const __half* wr = w + (8 * j + g) * 27;
-                const __half lo = k < 27 ? wr[k] : __float2half(0.f);
-                const __half hi = k + 1 < 27 ? wr[k + 1] : __float2half(0.f);
+                const __half* wr = w + (8 * j + g) * 9 * w_cin;
+                const __half lo = k < 27 ? wr[(k / 3) * w_cin + k % 3] : __float2half(0.f);
+                const __half hi = k + 1 < 27 ? wr[((k + 1) / 3) * w_cin + (k + 1) % 3] : __float2half(0.f);
                 bf[s][j][r] = (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
             }
     pdl_wait();
@@ -76,10 +81,21 @@ stem_conv3x3s2_mma_kernel(const TIn* __restrict__ img, const __half* __restrict_
             for (int e = tid; e < STEM_ROWLEN; e += STEM_THREADS) dst[e] = __float2half(0.f);
             continue;
         }
-        const TIn* src = base + (size_t)iy * W * 3;           // element e of the staged row = src[ix_first * 3 + e]
         const int e_lo = max(0, -ix_first * 3), e_hi = min(need, (W - ix_first) * 3);     // valid range [e_lo, e_hi)
         for (int e = tid; e < e_lo; e += STEM_THREADS) dst[e] = __float2half(0.f);
         for (int e = e_hi + tid; e < STEM_ROWLEN; e += STEM_THREADS) dst[e] = __float2half(0.f);
+        if constexpr (sizeof(TIn) == 16) {                    // HalfC8: pixel px of the row -> staged halves 3 * (px - ix_first) ...
+            const HalfC8* srcp = reinterpret_cast<const HalfC8*>(img) + ((size_t)b * H + iy) * W;
+            const int p_lo = e_lo / 3, p_hi = (e_hi + 2) / 3;   // staged pixels [p_lo, p_hi)
+            for (int pp = p_lo + tid; pp < p_hi; pp += STEM_THREADS) {
+                const uint2 v = __ldg(reinterpret_cast<const uint2*>(srcp + ix_first + pp));
+                const __half* h = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    if (pp * 3 + c < e_hi) dst[pp * 3 + c] = h[c];
+            }
+        } else {
+        const TIn* src = base + (size_t)iy * W * 3;           // element e of the staged row = src[ix_first * 3 + e]
         const TIn* s0 = src + ix_first * 3 + e_lo;            // first valid source element
         const int n = e_hi - e_lo;
         constexpr int VEC = 4;                                // elements per vector: float4 (16 B) / uchar4 (4 B)
@@ -104,6 +120,7 @@ stem_conv3x3s2_mma_kernel(const TIn* __restrict__ img, const __half* __restrict_
             }
         }
         for (int e = head + nvec * VEC + tid; e < n; e += STEM_THREADS) dst[e_lo + e] = __float2half_rn(stem_to_float(s0[e]));
+        }
     }
     __syncthreads();
 
@@ -168,7 +185,8 @@ stem_conv3x3s2_mma_kernel(const TIn* __restrict__ img, const __half* __restrict_
 
 template <typename TIn>
 static int stem_launch(const TIn* d_img, const void* d_weight, const float* d_bias, void* d_out, int B, int H, int W,
-                       int Cout, int Ho, int Wo, int stride, int pad_top, int pad_left, int act, ssd_stream_t stream, const char* who) {
+                       int Cout, int Ho, int Wo, int stride, int pad_top, int pad_left, int act, ssd_stream_t stream, const char* who,
+                       int w_cin = 3) {
     SSD_REQUIRE_PTR(d_img); SSD_REQUIRE_PTR(d_weight); SSD_REQUIRE_PTR(d_out);
     SSD_REQUIRE(B >= 1 && H >= 1 && W >= 1 && Ho >= 1 && Wo >= 1 && act >= SSD_ACT_NONE && act <= SSD_ACT_RELU6 &&
                 pad_top >= 0 && pad_left >= 0 && pad_top <= 1 && pad_left <= 1 && B <= 65535,
@@ -181,7 +199,7 @@ static int stem_launch(const TIn* d_img, const void* d_weight, const float* d_bi
     auto kern = stride == 2 ? stem_conv3x3s2_mma_kernel<TIn, 2, 4> : stem_conv3x3s2_mma_kernel<TIn, 1, 8>;
     cudaError_t le = launch_pdl(kern, dim3(Ho * chunks, B), dim3(STEM_THREADS), 0, as_stream(stream),
                                 d_img, reinterpret_cast<const __half*>(d_weight), d_bias, reinterpret_cast<__half*>(d_out),
-                                H, W, Ho, Wo, pad_top, pad_left, act, chunks);
+                                H, W, Ho, Wo, pad_top, pad_left, act, chunks, w_cin);
     if (le != cudaSuccess) return cuda_fail(le, "stem_conv3x3s2_mma_kernel");
     return SSD_OK;
 }
@@ -229,6 +247,13 @@ extern "C" int ssd_stem_conv3x3s2_u8(const void* d_img_u8, const void* d_weight,
                                      ssd_stream_t stream) {
     return stem_launch<uint8_t>(static_cast<const uint8_t*>(d_img_u8), d_weight, d_bias, d_out, B, H, W, Cout, Ho, Wo,
                                 2, pad_top, pad_left, act, stream, "ssd_stem_conv3x3s2_u8");
+}
+
+extern "C" int ssd_stem_conv3x3_f16c8(const void* d_img_f16c8, const void* d_weight_ohwi8, const float* d_bias, void* d_out,
+                                      int B, int H, int W, int Cout, int Ho, int Wo, int stride, int pad_top, int pad_left, int act,
+                                      ssd_stream_t stream) {
+    return stem_launch<HalfC8>(static_cast<const HalfC8*>(d_img_f16c8), d_weight_ohwi8, d_bias, d_out, B, H, W, Cout, Ho, Wo,
+                               stride, pad_top, pad_left, act, stream, "ssd_stem_conv3x3_f16c8", 8);
 }
 
 extern "C" int ssd_image_u8_to_f16c8(const void* d_img_u8, void* d_out, int64_t n_pixels, ssd_stream_t stream) {

@@ -79,6 +79,7 @@ class Act:
     H: int
     W: int
     C: int
+    is_image: bool = False          # the fp16 copy of the input image (3 real channels padded to 8)
 
 
 def mobilenet_v2_graph(n: Any, x: Act, hp: Dict[str, Any]) -> List[Act]:
@@ -397,7 +398,7 @@ class _PlanBuilder:
                                     (_ffi.ptr(self.plan.image), _ffi.ptr(x), npx), 0.0, npx * (12 + 16), (x,)))
         self.plan.first_u8 = Step("input_cast_u8", "cast", self.lib.ssd_image_u8_to_f16c8,
                                   (_ffi.ptr(self.plan.image_u8), _ffi.ptr(x), npx), 0.0, npx * (3 + 16), (x,))
-        return Act(x, S, S, 8)
+        return Act(x, S, S, 8, is_image=True)
 
     def _stem(self, x, name, cout, stride, ph, pw, act, bn):
         """The first layer straight from the image (float32 or uint8): MobileNetV2's Conv1 (3x3 stride 2 -> 32) and
@@ -415,6 +416,9 @@ class _PlanBuilder:
                                   (_ffi.ptr(self.plan.image_u8),) + args[1:], 2.0 * self.B * Ho * Wo * 27 * cout,
                                   nbytes - self.B * x.H * x.W * 9, (w, b, out), dict(meta, x=self.plan.image_u8))
         return Act(out, Ho, Wo, cout)
+
+    # first layer of a training plan through the first-layer kernel ("1") or the generic tensor-map path ("0")
+    TRAIN_STEM = os.environ.get("SSD_B200_TRAIN_STEM", "1") not in ("0", "")
 
     def _emit_conv(self, name, x: Act, w: torch.Tensor, bias, cout, k, stride, dilation, ph, pw, act,
                    residual: Optional[Act], out0, out1=None, out_f32=0, split=None, strides=None, real_cin=None):
@@ -439,6 +443,16 @@ class _PlanBuilder:
         meta = dict(x=x.t, w=w, bias=bias, res=residual.t if residual is not None else None, out0=out0, out1=out1,
                     k=k, stride=stride, dilation=dilation, ph=ph, pw=pw, act=act, Ho=Ho, Wo=Wo, cout=cout,
                     split=d.split, out_f32=out_f32, strides=strides)
+        if (self.TRAIN_STEM and x.is_image and k == 3 and dilation == 1 and residual is None and not out_f32 and d.split == cout
+                and (stride, cout) in ((2, 32), (1, 64)) and ph[0] <= 1 and pw[0] <= 1 and isinstance(out0, torch.Tensor)):
+            # first layer of a TRAINING plan: same tensors as the tensor-map path (fp16 image padded to 8 channels, OHWI
+            # weights padded to 8 input channels -- what its filter gradient reads), computed by the first-layer kernel
+            # instead of nine 64-channel k-blocks for 3 real channels
+            args = (_ffi.ptr(x.t), _ffi.ptr(w), _ffi.ptr(bias) if bias is not None else None, _ffi.ptr(out0), self.B, x.H, x.W,
+                    cout, Ho, Wo, stride, ph[0], pw[0], act)
+            self.plan.steps.append(Step(name, "conv", self.lib.ssd_stem_conv3x3_f16c8, args, 2.0 * macs, nbytes,
+                                        (d, w, bias, x.t, out0), meta))
+            return Ho, Wo
         self.plan.steps.append(Step(name, "conv", self.lib.ssd_conv2d, (C.byref(d),), 2.0 * macs, nbytes,
                                     (d, w, bias, x.t, out0), meta))
         return Ho, Wo
