@@ -29,6 +29,14 @@ for what in "$@"; do
       python tools/ncu_traffic.py $OUT/conv_${tag}_raw.csv $OUT/traffic_$tag.json > /dev/null 2>&1
       rm -f $OUT/conv_$tag.ncu-rep
       ;;
+    vgg)
+      # one SSD300-VGG16 B=32 inference step: tensor-pipe evidence for the tcgen05 / CTA-pair convolutions
+      ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"conv_tcgen05|stem_conv|conv_chain|maxpool|l2norm|splitk" \
+          -o $OUT/vgg_$tag python tools/infer_bench.py --backbone vgg16 --batch 32 --profile-one-step > $OUT/vgg_$tag.log 2>&1
+      ncu -i $OUT/vgg_$tag.ncu-rep --page raw --csv > $OUT/vgg_${tag}_raw.csv 2>/dev/null
+      python tools/ncu_summary.py $OUT/vgg_${tag}_raw.csv > $OUT/vgg_${tag}_summary.csv 2>&1
+      rm -f $OUT/vgg_$tag.ncu-rep $OUT/vgg_${tag}_raw.csv
+      ;;
     train)
       # the training kernels of one MobileNetV2 step (BatchNorm fwd/bwd, depthwise gradients, tcgen05 wgrad, loss bwd, Adam);
       # one pass per kernel family so that each gets a sample from the middle of the network

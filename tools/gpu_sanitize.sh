@@ -5,7 +5,7 @@ set -u
 tag=$1
 OUT=gpurun_out
 mkdir -p $OUT
-SEL='irblock or dwproj or stem_kernel or conv2d_against or decoder_parity or decoder_integer or loss_forward or hard_negative or iou or match or prior or cuda_reproduces or cuda_priors or cuda_losses or cuda_decoder'
+SEL='irblock or dwproj or stem_kernel or conv2d_against or cta_pair or conv_chain or decoder_parity or decoder_integer or combined_nms or loss_forward or hard_negative or iou or match or prior or cuda_reproduces or cuda_priors or cuda_losses or cuda_decoder or cuda_augmentation'
 for tool in memcheck racecheck synccheck; do
   log=$OUT/sanitize_${tag}_${tool}.txt
   timeout 700 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 0 \

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--backbone", default="vgg16_512", choices=["mobilenet_v2", "vgg16", "vgg16_512"])
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--profile-one-step", action="store_true", help="ncu --profile-from-start off: one eager step between profiler start/stop")
     a = ap.parse_args()
     import torch
     from tf_ssd_b200 import synth
@@ -37,6 +38,12 @@ def main():
     for _ in range(5):
         dm.run_resident(a.batch, 0)
     torch.cuda.synchronize()
+    if a.profile_one_step:
+        torch.cuda.profiler.start()
+        st["plan"].run()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     for e0, e1 in evs:
         flush.zero_()
