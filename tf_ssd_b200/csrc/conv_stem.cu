@@ -41,8 +41,8 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 template <typename TIn, int STRIDE, int NT>
 __global__ void __launch_bounds__(STEM_THREADS)
 stem_conv3x3s2_mma_kernel(const TIn* __restrict__ img, const __half* __restrict__ w, const float* __restrict__ bias,
-                          __half* __restrict__ out, int H, int W, int Ho, int Wo, int pad_t, int pad_l, int act, int chunks,
-                          int w_cin) {
+                          __half* __restrict__ out, int H, int W, int Ho, int Wo, int pad_t, int pad_l, int act, int chunks) {
+    constexpr int WCIN = sizeof(TIn) == 16 ? 8 : 3;           // input channels per tap in the weight layout
     constexpr int STEP = 3 * STRIDE;                          // staged halves between neighbouring output pixels
     constexpr int COUT = 8 * NT, STEM_OSTRIDE = COUT + 8;
     __shared__ __align__(16) __half srow[3][STEM_ROWLEN];
@@ -64,9 +64,10 @@ stem_conv3x3s2_mma_kernel(const TIn* __restrict__ img, const __half* __restrict_
             for (int r = 0; r < 2; ++r) {
                 // weights OHWI [Cout][3][3][w_cin] (w_cin = 3, or 8 for the zero-padded layout of the tensor-map path)
                 const int k = 16 * s + 8 * r + 2 * t;
-                const __half* wr = w + (8 * j + g) * 9 * w_cin;
-                const __half lo = k < 27 ? wr[(k / 3) * w_cin + k % 3] : __float2half(0.f);
-                const __half hi = k + 1 < 27 ? wr[((k + 1) / 3) * w_cin + (k + 1) % 3] : __float2half(0.f);
+                const __half* wr = w + (8 * j + g) * 9 * WCIN;
+                const int i0 = WCIN == 3 ? k : (k / 3) * WCIN + k % 3, i1 = WCIN == 3 ? k + 1 : ((k + 1) / 3) * WCIN + (k + 1) % 3;
+                const __half lo = k < 27 ? wr[i0] : __float2half(0.f);
+                const __half hi = k + 1 < 27 ? wr[i1] : __float2half(0.f);
                 bf[s][j][r] = (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
             }
     pdl_wait();
@@ -185,8 +186,7 @@ stem_conv3x3s2_mma_kernel(const TIn* __restrict__ img, const __half* __restrict_
 
 template <typename TIn>
 static int stem_launch(const TIn* d_img, const void* d_weight, const float* d_bias, void* d_out, int B, int H, int W,
-                       int Cout, int Ho, int Wo, int stride, int pad_top, int pad_left, int act, ssd_stream_t stream, const char* who,
-                       int w_cin = 3) {
+                       int Cout, int Ho, int Wo, int stride, int pad_top, int pad_left, int act, ssd_stream_t stream, const char* who) {
     SSD_REQUIRE_PTR(d_img); SSD_REQUIRE_PTR(d_weight); SSD_REQUIRE_PTR(d_out);
     SSD_REQUIRE(B >= 1 && H >= 1 && W >= 1 && Ho >= 1 && Wo >= 1 && act >= SSD_ACT_NONE && act <= SSD_ACT_RELU6 &&
                 pad_top >= 0 && pad_left >= 0 && pad_top <= 1 && pad_left <= 1 && B <= 65535,
@@ -199,7 +199,7 @@ static int stem_launch(const TIn* d_img, const void* d_weight, const float* d_bi
     auto kern = stride == 2 ? stem_conv3x3s2_mma_kernel<TIn, 2, 4> : stem_conv3x3s2_mma_kernel<TIn, 1, 8>;
     cudaError_t le = launch_pdl(kern, dim3(Ho * chunks, B), dim3(STEM_THREADS), 0, as_stream(stream),
                                 d_img, reinterpret_cast<const __half*>(d_weight), d_bias, reinterpret_cast<__half*>(d_out),
-                                H, W, Ho, Wo, pad_top, pad_left, act, chunks, w_cin);
+                                H, W, Ho, Wo, pad_top, pad_left, act, chunks);
     if (le != cudaSuccess) return cuda_fail(le, "stem_conv3x3s2_mma_kernel");
     return SSD_OK;
 }
@@ -253,7 +253,7 @@ extern "C" int ssd_stem_conv3x3_f16c8(const void* d_img_f16c8, const void* d_wei
                                       int B, int H, int W, int Cout, int Ho, int Wo, int stride, int pad_top, int pad_left, int act,
                                       ssd_stream_t stream) {
     return stem_launch<HalfC8>(static_cast<const HalfC8*>(d_img_f16c8), d_weight_ohwi8, d_bias, d_out, B, H, W, Cout, Ho, Wo,
-                               stride, pad_top, pad_left, act, stream, "ssd_stem_conv3x3_f16c8", 8);
+                               stride, pad_top, pad_left, act, stream, "ssd_stem_conv3x3_f16c8");
 }
 
 extern "C" int ssd_image_u8_to_f16c8(const void* d_img_u8, void* d_out, int64_t n_pixels, ssd_stream_t stream) {

@@ -646,7 +646,11 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
         // ===================== depthwise 3x3 from the shared-memory patch =====================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_DW_REGS_DW));
         const int pt = (int)threadIdx.x - 32 * TC_DW_WARP0;
-        const int j = pt & 7, rg = pt >> 3;                      // 16-byte channel chunk, row group (0..31)
+        // pair mode (<= 32 channels, stride 1, even box width: MobileNetV2's block 0): only the 4 live 16-byte chunks are
+        // spread over the threads, each owns 2 horizontally adjacent pixels (12 patch loads and 72 HFMA2 instead of the
+        // quad mode's 18 / 144 with half of the threads on dead channels)
+        const int pairm = p.dw_pair;
+        const int j = pairm ? (pt & 3) : (pt & 7), rg = pairm ? (pt >> 2) : (pt >> 3);      // 16-byte channel chunk, row group
         const int C8 = p.dw_C8, st = p.dw_stride, pw = p.dw_pw, php = p.dw_ph;
         const float lo = p.dw_act == SSD_ACT_NONE ? -__int_as_float(0x7f800000) : 0.0f;
         const float hi = p.dw_act == SSD_ACT_RELU6 ? 6.0f : __int_as_float(0x7f800000);
@@ -656,7 +660,7 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
         int q0[TC_DW_ROWS];                                      // patch position of tap (0,0) per owned row; -1: padding row
 #pragma unroll
         for (int i = 0; i < TC_DW_ROWS; ++i) {
-            const int r = quad ? 4 * rg + i : rg + 4 * TC_DW_WARPS * i;
+            const int r = pairm ? (i < 2 ? 2 * rg + i : TC_BM) : quad ? 4 * rg + i : rg + 4 * TC_DW_WARPS * i;
             if (r < box_rows && r < TC_BM) {
                 const int dx = r % p.bw, qq = r / p.bw, dy = qq % p.bh, db = qq / p.bh;
                 q0[i] = dx * st + pw * (dy * st + php * db);
@@ -670,6 +674,11 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
         int s = 0, ps = 0, it = 0, tslot = 0;
         uint32_t ph = 0, pph = 0;
         const bool has_bias = p.dw_bias != nullptr;
+        if (pairm)       // logical chunks 4..7 of the A tiles are never written in pair mode: they must hold finite values
+            for (int i = pt; i < TC_DW_ASTAGES * TC_BM * 4; i += 32 * TC_DW_WARPS) {      // (they meet zero-filled weights)
+                const int stg = i / (TC_BM * 4), rr = (i >> 2) % TC_BM, c = 4 + (i & 3);
+                *reinterpret_cast<uint4*>(sA + (size_t)stg * a_stage + rr * 128 + ((c ^ (rr & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+            }
         auto load_bias = [&](int kb, __half2 (&b4)[4]) {
             const int c8 = kb * 8 + j;
             const bool okb = has_bias && c8 < C8;
@@ -696,7 +705,35 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
                 if (pt == 0) trace_stamp(p.trace, 2, tslot, 1);
                 const unsigned char* patch = sP + (size_t)ps * p.dw_patch_stage;
                 const unsigned char* wsm = patch + p.dw_patch_stage - 2048;
-                if (quad) {
+                if (pairm) {
+                    // 2 outputs share 4 input columns per filter row
+                    if (q0[0] >= 0) {
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            uint4 w3[3];
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const int tap = ky * 3 + kx;
+                                w3[kx] = *reinterpret_cast<const uint4*>(wsm + tap * 128 + ((j ^ (tap & 7)) << 4));
+                            }
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const int q = q0[0] + c + pw * ky;
+                                const uint4 xv = *reinterpret_cast<const uint4*>(patch + (size_t)q * 128 + ((j ^ (q & 7)) << 4));
+                                const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+                                for (int i = 0; i < 2; ++i) {
+                                    const int kx = c - i;
+                                    if (kx >= 0 && kx < 3) {
+                                        const __half2* wh = reinterpret_cast<const __half2*>(&w3[kx]);
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) acc[i][e] = __hfma2(xh[e], wh[e], acc[i][e]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                } else if (quad) {
                     // sliding window: the 4 outputs of a thread share 6 input columns per filter row (18 loads, not 36)
                     if (q0[0] >= 0) {
 #pragma unroll
@@ -749,7 +786,7 @@ conv_dwproj_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
                 unsigned char* a_tile = sA + (size_t)s * a_stage;
 #pragma unroll
                 for (int i = 0; i < TC_DW_ROWS; ++i) {
-                    const int r = quad ? 4 * rg + i : rg + 4 * TC_DW_WARPS * i;
+                    const int r = pairm ? (i < 2 ? 2 * rg + i : TC_BM) : quad ? 4 * rg + i : rg + 4 * TC_DW_WARPS * i;
                     if (r >= TC_BM) continue;
                     uint4 o = make_uint4(0u, 0u, 0u, 0u);
                     if (q0[i] >= 0 && cok) {
@@ -1287,6 +1324,7 @@ int conv_dwproj_launch(const ssd_dwproj_desc* d, cudaStream_t st) {
     p.dw_act = d->dw_act;
     p.splits = 1; p.tiles_m = p.n_tiles; p.tiles_n = 1; p.tma_store = 1; p.stages = TC_DW_ASTAGES;
     p.dw_quad = (d->stride == 1 && p.bw % 4 == 0) ? 1 : 0;
+    p.dw_pair = (d->stride == 1 && p.bw % 2 == 0 && d->C <= 32) ? 1 : 0;
 
     CUtensorMap map_x, map_w, map_b, map_o;
     {

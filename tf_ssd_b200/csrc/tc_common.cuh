@@ -63,6 +63,7 @@ struct TcParams {
     uint32_t dw_patch_stage;         // patch stage size in shared memory (1024-byte multiple)
     int dw_pstages;                  // patch ring depth
     int dw_quad;                     // stride 1 and bw % 4 == 0: a thread owns 4 horizontally adjacent pixels (sliding window)
+    int dw_pair;                     // <= 32 channels, stride 1, even bw: 4 live chunks x 2 adjacent pixels per thread
     unsigned long long* trace;       // debug (ssd_debug_trace): per-role stamps of CTA 0, else nullptr
 };
 
