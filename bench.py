@@ -571,7 +571,8 @@ def run_b200(args):
             roof.update({"traffic": _ncu_traffic(top, g["launches"]), "algorithmic_bytes_per_launch": g["bytes"] / max(g["launches"], 1), "kernel": {"conv": "ssd_conv2d launches: conv_tcgen05_kernel (+ conv_splitk_reduce_kernel for the multibox heads)",
                                                      "irblock": "conv_irblock_tcgen05_kernel (whole inverted-residual block: 1x1 expand -> depthwise 3x3 -> 1x1 project)",
                          "dw": "depthwise3x3_kernel", "dwproj": "conv_dwproj_tcgen05_kernel (fused depthwise 3x3 -> 1x1 projection)", "decode_nms": "nms_candidates+nms_image",
-                         "chain": "conv_chain_kernel (the small-map tail + its heads as one cluster launch)", "stem": "stem_conv3x3s2_mma_kernel"}.get(top, top),
+                         "chain": "conv_chain_kernel (the small-map tail + its heads as one cluster launch)", "stem": "stem_conv3x3s2_mma_kernel",
+                         "stemblock": "stem_dwproj_kernel (Conv1 3x3 s2 -> depthwise 3x3 -> 1x1 projection from the image, one launch)"}.get(top, top),
                          "launches_per_step": g["launches"], "ms_per_step": g["ms"], "share_of_step": g["ms"] / total,
                          "algorithmic_bytes_per_step": g["bytes"], "flops_per_step": g["flops"], "peak_source": peaks["source"],
                          "by_kind_ms": {k: round(v["ms"], 4) for k, v in groups.items()}})

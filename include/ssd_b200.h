@@ -277,6 +277,26 @@ int ssd_debug_trace(void* d_buf);
  * SM, full 128 / 256-wide N tiles, K >= 512), 0 never, 1 whenever the shape allows (small test shapes). */
 int ssd_debug_pair_mode(int mode);
 
+/* MobileNetV2's first three layers as ONE launch (models/ssd_mobilenet_v2.py:25 -> keras_applications Conv1_pad / Conv1 /
+ * bn_Conv1 / Conv1_relu, expanded_conv_depthwise (+BN, ReLU6), expanded_conv_project (+BN)): the 3x3 stride-2 stem
+ * straight from the NHWC image (float32 in [0,1], or the uint8 batch of utils/data_utils.py:33-37 with
+ * convert_image_dtype fused in), the stride-1 SAME depthwise 3x3 of block 0 and its 1x1 projection.  Neither the stem
+ * output [B,Hs,Ws,32] nor the depthwise output is written to global memory (one CTA per 30 x 10 output tile: staged image
+ * patch -> mma.sync stem -> packed-half2 depthwise -> mma.sync projection -> coalesced stores).
+ * stem_weight [32,3,3,3] fp16, dw_weight [3,3,32] fp16, proj_weight [Cout,32] fp16, biases fp32 (may be NULL),
+ * out [B,Hs,Ws,Cout] fp16 with Hs, Ws = the stem's output size.  Cmid == 32, Cout in {8,16,24,32}; returns
+ * SSD_ERR_UNSUPPORTED otherwise (ssd_stem_dwproj_supported tells beforehand). */
+typedef struct ssd_stem_dwproj_desc {
+    const void* image; const void* stem_weight; const float* stem_bias;
+    const void* dw_weight; const float* dw_bias; const void* proj_weight; const float* proj_bias; void* out;
+    int32_t image_u8;                 /* 0: float32 image, 1: uint8 image */
+    int32_t B, H, W, Hs, Ws, Cmid, Cout;
+    int32_t pad_top, pad_left, stem_act, dw_act, act;
+    int32_t reserved;
+} ssd_stem_dwproj_desc;
+int ssd_stem_dwproj(const ssd_stem_dwproj_desc* h_desc, ssd_stream_t stream);
+int ssd_stem_dwproj_supported(const ssd_stem_dwproj_desc* h_desc);
+
 /* MobileNetV2 stem: keras_applications Conv1_pad + Conv1 (3x3, stride 2, Cin = 3) + bn_Conv1 +
  * Conv1_relu (models/ssd_mobilenet_v2.py:25), computed straight from the fp32 NHWC image
  * [B,H,W,3] (the fp32->fp16 input rounding of the pipeline is fused in).

@@ -422,6 +422,17 @@ def test_every_layer_in_situ(backbone, B):
             x = f32(mt["x"]).numpy()
             y = x / np.sqrt(np.maximum((x * x).sum(-1, keepdims=True), 1e-12)) * f32(mt["scale"]).numpy()
             assert _rel(f32(mt["out"]).numpy(), y) < 2e-3, s.name
+        elif s.kind == "stemblock":
+            # Conv1 -> expanded_conv_depthwise -> expanded_conv_project as one launch (ssd_stem_dwproj)
+            x = mt["x"].half().float().cpu().permute(0, 3, 1, 2)
+            (pt, pb), (pl, pr) = mt["ph"], mt["pw"]
+            h = F.conv2d(F.pad(x, (pl, pr, pt, pb)), f32(mt["stem_w"]).permute(0, 3, 1, 2), f32(mt["stem_bias"]), stride=2)
+            h = _act(h, mt["stem_act"]).half().float()
+            wd = f32(mt["dw_w"]).permute(2, 0, 1).unsqueeze(1)
+            h = _act(F.conv2d(F.pad(h, (1, 1, 1, 1)), wd, f32(mt["dw_bias"]), groups=wd.shape[0]), mt["dw_act"]).half().float()
+            y = _act(F.conv2d(h, f32(mt["w"]).permute(0, 3, 1, 2), f32(mt["bias"])), mt["act"]).permute(0, 2, 3, 1)
+            assert y.shape[1:3] == (mt["Ho"], mt["Wo"])
+            assert _rel(f32(mt["out0"]).numpy(), y.numpy()) < 3e-3, f"{s.name}: {_rel(f32(mt['out0']).numpy(), y.numpy())}"
         elif s.kind == "stem":
             x = mt["x"].half().float().cpu().permute(0, 3, 1, 2)          # the kernel rounds the image to fp16 first
             w = f32(mt["w"]).permute(0, 3, 1, 2)
@@ -434,7 +445,7 @@ def test_every_layer_in_situ(backbone, B):
             continue
         checked += 1
     assert checked == plan.n_launches - sum(1 for s in plan.steps if s.kind == "cast")
-    assert any(s.kind == "stem" for s in plan.steps)          # Conv1 (MobileNetV2) / conv1_1 (VGG16) read the image directly
+    assert any(s.kind in ("stem", "stemblock") for s in plan.steps)   # Conv1 (MobileNetV2) / conv1_1 (VGG16) read the image directly
     assert any(s.kind == "chain" for s in plan.steps)
 
 
@@ -591,6 +602,60 @@ def test_stem_kernel_shapes(H, W, pad):
     y = torch.clamp(y, 0, 6).permute(0, 2, 3, 1).numpy()
     assert y.shape == (B, Ho, Wo, 32)
     assert _rel(outs[0].float().cpu().numpy(), y) < 2e-3
+
+
+@pytest.mark.parametrize("case", [
+    # B, H, W, pad (top, left), Cout, u8
+    (2, 300, 300, (0, 0), 16, True), (2, 300, 300, (0, 0), 16, False), (1, 67, 45, (1, 1), 8, False),
+    (3, 64, 122, (0, 1), 32, True), (2, 9, 7, (1, 0), 24, True), (1, 130, 25, (0, 0), 16, False),
+])
+def test_stem_dwproj_fused_against_torch(case):
+    """ssd_stem_dwproj (Conv1 3x3 s2 + ReLU6 -> depthwise 3x3 + ReLU6 -> 1x1 projection, one launch) against torch-CPU
+    with the same fp16 roundings: SSD300's shape, partial tiles in both directions, both paddings, row lengths that are
+    not multiples of four elements (scalar staging path), all output widths, float32 and uint8 images (bit-identical)."""
+    import ctypes as C
+    from tf_ssd_b200 import _ffi
+    from tf_ssd_b200._ffi_conv import StemDwProjDesc
+    B, H, W, (pt, pl), Cout, u8_in = case
+    lib = _ffi.lib()
+    rng = np.random.default_rng(H * W + Cout)
+    Hs, Ws = (H + pt - 2) // 2 + 1, (W + pl - 2) // 2 + 1
+    u8 = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    x32 = u8.astype(np.float32) * np.float32(1.0 / 255.0)
+    ws = (rng.standard_normal((32, 3, 3, 3)) * 0.5).astype(np.float16)
+    bs = rng.standard_normal(32).astype(np.float32)
+    wd = (rng.standard_normal((3, 3, 32)) * 0.4).astype(np.float16)
+    bd = (0.3 * rng.standard_normal(32)).astype(np.float32)
+    wp = (rng.standard_normal((Cout, 32)) * 0.25).astype(np.float16)
+    bp = (0.3 * rng.standard_normal(Cout)).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).cuda()
+    xt, ut, wst, bst, wdt, bdt, wpt, bpt = map(t, (x32, u8, ws, bs, wd, bd, wp, bp))
+    outs = []
+    for is_u8 in (False, True):
+        out = torch.full((B, Hs, Ws, Cout), float("nan"), dtype=torch.float16, device="cuda")
+        d = StemDwProjDesc()
+        d.image, d.image_u8 = (ut if is_u8 else xt).data_ptr(), int(is_u8)
+        d.stem_weight, d.stem_bias, d.dw_weight, d.dw_bias = wst.data_ptr(), bst.data_ptr(), wdt.data_ptr(), bdt.data_ptr()
+        d.proj_weight, d.proj_bias, d.out = wpt.data_ptr(), bpt.data_ptr(), out.data_ptr()
+        d.B, d.H, d.W, d.Hs, d.Ws, d.Cmid, d.Cout = B, H, W, Hs, Ws, 32, Cout
+        d.pad_top, d.pad_left, d.stem_act, d.dw_act, d.act = pt, pl, 2, 2, 0
+        assert lib.ssd_stem_dwproj_supported(C.byref(d)) == 1
+        _ffi.check(lib.ssd_stem_dwproj(C.byref(d), _ffi.stream()), "ssd_stem_dwproj")
+        outs.append(out)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])                       # convert_image_dtype fused into the load: bit-identical
+    xr = torch.from_numpy(x32).half().float().permute(0, 3, 1, 2)
+    pb, pr = max(0, (Hs - 1) * 2 + 3 - H - pt), max(0, (Ws - 1) * 2 + 3 - W - pl)
+    h = F.conv2d(F.pad(xr, (pl, pr, pt, pb)), torch.from_numpy(ws).float().permute(0, 3, 1, 2), torch.from_numpy(bs), stride=2)
+    h = torch.clamp(h, 0, 6).half().float()
+    h = F.conv2d(F.pad(h, (1, 1, 1, 1)), torch.from_numpy(wd).float().permute(2, 0, 1).unsqueeze(1), torch.from_numpy(bd), groups=32)
+    h = torch.clamp(h, 0, 6).half().float()
+    y = F.conv2d(h, torch.from_numpy(wp).float().view(Cout, 32, 1, 1), torch.from_numpy(bp)).permute(0, 2, 3, 1).numpy()
+    got = outs[1 if u8_in else 0].float().cpu().numpy()
+    assert y.shape == got.shape and np.isfinite(got).all()
+    assert _rel(got, y) < 3e-3, _rel(got, y)
+    d.Cmid = 64                                                 # another stem width: refused, not mis-computed
+    assert lib.ssd_stem_dwproj_supported(C.byref(d)) == 0 and lib.ssd_stem_dwproj(C.byref(d), _ffi.stream()) < 0
 
 
 @pytest.mark.parametrize("H,W", [(300, 300), (33, 47), (5, 200), (1, 1)])

@@ -44,6 +44,17 @@ class IrBlockDesc(C.Structure):
     ]
 
 
+class StemDwProjDesc(C.Structure):
+    """``struct ssd_stem_dwproj_desc`` (include/ssd_b200.h)."""
+    _fields_ = [
+        ("image", vp), ("stem_weight", vp), ("stem_bias", vp), ("dw_weight", vp), ("dw_bias", vp), ("proj_weight", vp),
+        ("proj_bias", vp), ("out", vp),
+        ("image_u8", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Hs", C.c_int32), ("Ws", C.c_int32),
+        ("Cmid", C.c_int32), ("Cout", C.c_int32), ("pad_top", C.c_int32), ("pad_left", C.c_int32),
+        ("stem_act", C.c_int32), ("dw_act", C.c_int32), ("act", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
 class AdamVar(C.Structure):
     """``struct ssd_adam_var`` (include/ssd_b200.h)."""
     _fields_ = [("w", vp), ("m", vp), ("v", vp), ("grad", vp), ("w16", vp), ("n", i64), ("l2", f), ("reserved", f)]
@@ -57,6 +68,8 @@ SIGNATURES = {
     "ssd_depthwise3x3": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),
     "ssd_dwproj": (i, [C.POINTER(DwProjDesc), vp]),
     "ssd_dwproj_supported": (i, [C.POINTER(DwProjDesc)]),
+    "ssd_stem_dwproj": (i, [C.POINTER(StemDwProjDesc), vp]),
+    "ssd_stem_dwproj_supported": (i, [C.POINTER(StemDwProjDesc)]),
     "ssd_irblock": (i, [C.POINTER(IrBlockDesc), vp]),
     "ssd_irblock_supported": (i, [C.POINTER(IrBlockDesc)]),
     "ssd_irblock_trace": (i, [vp]),

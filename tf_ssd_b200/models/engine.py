@@ -28,7 +28,7 @@ import numpy as np
 import torch
 
 from tf_ssd_b200 import _ffi
-from tf_ssd_b200._ffi_conv import ACT_NONE, ACT_RELU, ACT_RELU6, ConvDesc, DwProjDesc, IrBlockDesc
+from tf_ssd_b200._ffi_conv import ACT_NONE, ACT_RELU, ACT_RELU6, ConvDesc, DwProjDesc, IrBlockDesc, StemDwProjDesc
 
 BN_EPS = 1e-3        # keras_applications.mobilenet_v2: BatchNormalization(epsilon=1e-3, momentum=0.999)
 
@@ -475,6 +475,8 @@ class _PlanBuilder:
                 and dilation == 1 and cout <= 256 and cout % 8 == 0 and type(self) is _PlanBuilder):
             # depthwise 3x3 -> 1x1 projection as ONE launch (ssd_dwproj): the depthwise output stays on chip
             dm = last.meta
+            if self._try_stemblock(name, x, w, b, cout, act, residual, out, Ho, Wo):
+                return Act(out, Ho, Wo, cout)
             if self._try_irblock(name, x, w, b, cout, act, residual, out, Ho, Wo):
                 return Act(out, Ho, Wo, cout)
             d = DwProjDesc()
@@ -502,6 +504,51 @@ class _PlanBuilder:
         if tap:
             self.plan.steps[-1].meta["tap"] = True
         return Act(out, Ho, Wo, cout)
+
+    # first layer 3x3 s2 -> depthwise 3x3 -> project 1x1 (MobileNetV2 Conv1 + block 0) as ONE launch (ssd_stem_dwproj): "1" / "0"
+    FUSE_STEM = os.environ.get("SSD_B200_FUSE_STEM", "1")
+
+    def _try_stemblock(self, name, x, w, b, cout, act, residual, out, Ho, Wo) -> bool:
+        """Called while emitting a 1x1 projection with a depthwise step last in the plan: when that depthwise layer
+        (stride 1) reads the first-layer kernel's output and nothing else does, the three layers become one launch that
+        reads the image and writes the projection (the 32-channel stem output never reaches HBM)."""
+        steps = self.plan.steps
+        if self.FUSE_STEM in ("0", "") or len(steps) != 2 or type(self) is not _PlanBuilder or residual is not None:
+            return False
+        dws, stem = steps[-1], steps[-2]
+        dm, sm = dws.meta, stem.meta
+        if not (stem.kind == "stem" and sm["stride"] == 2 and sm["out"] is dm["x"] and dm["stride"] == 1
+                and tuple(dm["ph"]) == (1, 1) and tuple(dm["pw"]) == (1, 1)):
+            return False
+        Hs, Ws = dm["x"].shape[1], dm["x"].shape[2]
+        descs = []
+        for is_u8, img in ((0, self.plan.image), (1, self.plan.image_u8)):
+            d = StemDwProjDesc()
+            d.image, d.image_u8 = img.data_ptr(), is_u8
+            d.stem_weight, d.stem_bias = sm["w"].data_ptr(), sm["bias"].data_ptr()
+            d.dw_weight, d.dw_bias = dm["w"].data_ptr(), dm["bias"].data_ptr()
+            d.proj_weight, d.proj_bias, d.out = w.data_ptr(), b.data_ptr(), out.data_ptr()
+            d.B, d.H, d.W, d.Hs, d.Ws = self.B, img.shape[1], img.shape[2], Hs, Ws
+            d.Cmid, d.Cout = x.C, cout
+            d.pad_top, d.pad_left = sm["ph"][0], sm["pw"][0]
+            d.stem_act, d.dw_act, d.act = sm["act"], dm["act"], act
+            if not self.lib.ssd_stem_dwproj_supported(C.byref(d)):
+                return False
+            descs.append(d)
+        steps.pop(); steps.pop()
+        B, H, W = self.B, self.plan.image.shape[1], self.plan.image.shape[2]
+        flops = 2.0 * B * Hs * Ws * x.C * (27 + 9 + cout)
+        wbytes = (27 * x.C + 9 * x.C + x.C * cout) * 2
+        meta = dict(stem_w=sm["w"], stem_bias=sm["bias"], stem_act=sm["act"], ph=sm["ph"], pw=sm["pw"], stride=2,
+                    dw_w=dm["w"], dw_bias=dm["bias"], dw_act=dm["act"], w=w, bias=b, res=None, out0=out, act=act,
+                    Ho=Ho, Wo=Wo, cout=cout, stem_name=stem.name, dw_name=dws.name)
+        keep = (w, b, sm["w"], sm["bias"], dm["w"], dm["bias"], out)
+        steps.append(Step(name, "stemblock", self.lib.ssd_stem_dwproj, (C.byref(descs[0]),), flops,
+                          B * (H * W * 3 * 4 + Hs * Ws * cout * 2) + wbytes, keep + (descs[0],), dict(meta, x=self.plan.image)))
+        self.plan.first_u8 = Step(name + "_u8", "stemblock", self.lib.ssd_stem_dwproj, (C.byref(descs[1]),), flops,
+                                  B * (H * W * 3 + Hs * Ws * cout * 2) + wbytes, keep + (descs[1],),
+                                  dict(meta, x=self.plan.image_u8))
+        return True
 
     # expand 1x1 -> depthwise 3x3 -> project 1x1 as ONE launch (ssd_irblock): "1" / "0"
     FUSE_IR = os.environ.get("SSD_B200_FUSE_IR", "1")

@@ -22,7 +22,7 @@ def main(src, dst):
             continue
         nm = r[ki]
         kind = ("irblock" if "irblock" in nm else "dwproj" if "dwproj" in nm else "chain" if "conv_chain" in nm
-                else "stem" if "stem_conv" in nm else "decode_nms" if "nms_" in nm
+                else "stemblock" if "stem_dwproj" in nm else "stem" if "stem_conv" in nm else "decode_nms" if "nms_" in nm
                 else "conv" if ("conv_tcgen05" in nm or "conv_igemm" in nm or "splitk" in nm) else "dw" if "depthwise" in nm else None)
         if kind is None:
             continue

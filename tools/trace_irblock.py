@@ -47,7 +47,7 @@ def main():
     t = buf.cpu().numpy().astype(np.uint64).reshape(5, 512)
     ev = []
     names = {0: "tma", 1: "mma", 2: "dw", 3: "mid", 4: "epi"}
-    tags = {0: {1: "patch_issued", 2: "wexp_issued"}, 1: {1: "expand_go", 2: "project_go"},
+    tags = {0: {1: "patch_issued", 2: "wexp_issued", 3: "dwf_issued", 4: "wproj_issued"}, 1: {1: "expand_go", 2: "project_go", 3: "wexp_arrived", 4: "d1_free"},
             2: {1: "ep_full", 2: "dw_done", 3: "a2_written"}, 3: {1: "d1_full", 2: "ep_free", 3: "mid_done"}, 4: {4: "epi_wait", 5: "d2_full", 6: "epi_done"}}
     for role in range(5):
         for v in t[role]:
@@ -55,7 +55,7 @@ def main():
                 ev.append((int(v >> np.uint64(8)), role, int(v & np.uint64(0xff))))
     ev.sort()
     t0 = ev[0][0]
-    for ts, role, tag in ev[:160]:
+    for ts, role, tag in ev[:int(os.environ.get('TRACE_N', '160'))]:
         print(f"{(ts - t0) / 1000.0:9.2f} us  {names[role]:4s} {tags[role].get(tag, tag)}")
 
 
