@@ -23,6 +23,8 @@
 
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace ssd {
 
 constexpr int SB_TW = 30, SB_TH = 10;                 // output tile: 150 = 5 x 30 = 15 x 10 (no partial tiles at SSD300)
@@ -85,6 +87,7 @@ __global__ void __launch_bounds__(SB_THREADS, 2)
 stem_dwproj_kernel(const __grid_constant__ SbParams p) {
     extern __shared__ __align__(16) unsigned char sb_smem[];
     __half* sImg = reinterpret_cast<__half*>(sb_smem + SB_OFF_IMG);
+    const uint32_t sImg32 = (uint32_t)__cvta_generic_to_shared(sb_smem + SB_OFF_IMG);
     const uint32_t sMid = (uint32_t)__cvta_generic_to_shared(sb_smem + SB_OFF_MID);
     const uint32_t sDw = (uint32_t)__cvta_generic_to_shared(sb_smem + SB_OFF_DW);
     constexpr int COUT = 8 * NTP;
@@ -99,63 +102,86 @@ stem_dwproj_kernel(const __grid_constant__ SbParams p) {
     const int abase = ebase - shift;
     const int rowlen = p.W * 3;
 
-    // stem B fragments (weights OHWI [32][27] fp16, k = (ky * 3 + kx) * 3 + ci, zero for k >= 27): n = 8 j + g
+    // The stem's K axis (27 taps, padded to 32) is ordered in 16 PAIR SLOTS so that every A-fragment register is ONE
+    // aligned 32-bit shared-memory load: slot ky * 5 + i holds the staged elements (jstart, jstart + 1) of image row
+    // 2 pr + ky with jstart = 2 i - (shift & 1) (j = kx * 3 + ci in 0..8; the elements outside that range belong to
+    // the neighbouring pixel and meet a zero weight); slot 15 is all zero.  Thread t of a quad owns slots t, 4 + t,
+    // 8 + t, 12 + t (mma.sync's k = 2t, 2t+1 / 2t+8, 2t+9 of the two k16 steps).
+    const int sodd = shift & 1;
     uint32_t bf[2][4][2];
+    int soff[4];                                                  // staged offset (halves) of this thread's four slots
 #pragma unroll
     for (int s = 0; s < 2; ++s)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int r = 0; r < 2; ++r) {
+            const int slot = 8 * s + 4 * r + t;
+            const int sl = slot < 15 ? slot : 14;
+            const int ky = sl / 5, jstart = 2 * (sl - ky * 5) - sodd;
+            soff[2 * s + r] = ky * SB_IROWLEN + shift + jstart;
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int k = 16 * s + 8 * r + 2 * t;
-                const __half* wr = p.w_stem + (8 * j + g) * 27;
-                const __half lo = k < 27 ? wr[k] : __float2half(0.f);
-                const __half hi = k + 1 < 27 ? wr[k + 1] : __float2half(0.f);
+            for (int j = 0; j < 4; ++j) {
+                const __half* wr = p.w_stem + (8 * j + g) * 27 + ky * 9;
+                const __half lo = (slot < 15 && jstart >= 0) ? wr[jstart] : __float2half(0.f);
+                const __half hi = (slot < 15 && jstart + 1 <= 8) ? wr[jstart + 1] : __float2half(0.f);
                 bf[s][j][r] = (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
             }
+        }
     pdl_wait();
 
     // ---- 1. the image patch as fp16: staged element s of row r = image element abase + s of image row iy0 + r ----
     {
         const TIn* img = static_cast<const TIn*>(p.img) + (size_t)b * p.H * rowlen;
-        const bool vec_ok = (rowlen & 3) == 0;
-        for (int i = tid; i < SB_IROWS * (SB_IROWLEN / 4); i += SB_THREADS) {
-            const int r = i / (SB_IROWLEN / 4), v = i - r * (SB_IROWLEN / 4);
-            const int iy = iy0 + r, e0 = abase + 4 * v;
-            float x[4] = {0.f, 0.f, 0.f, 0.f};
-            if ((unsigned)iy < (unsigned)p.H) {
-                const TIn* src = img + (size_t)iy * rowlen;
-                if (vec_ok && e0 >= 0 && e0 + 3 < rowlen) {
-                    if constexpr (sizeof(TIn) == 4) {
-                        const float4 q = __ldg(reinterpret_cast<const float4*>(src + e0));
-                        x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
-                    } else {
-                        const uchar4 q = __ldg(reinterpret_cast<const uchar4*>(src + e0));
-                        x[0] = sb_to_float(q.x); x[1] = sb_to_float(q.y); x[2] = sb_to_float(q.z); x[3] = sb_to_float(q.w);
-                    }
-                } else {
+        constexpr int VPR = SB_IROWLEN / 4, NVEC = SB_IROWS * VPR;      // 50 four-element vectors per row, 1250 per patch
+        if ((rowlen & 3) == 0) {
+            // rows and abase are multiples of four elements: a vector is inside the image or outside, never across
+            // its edge.  All loads of a thread are issued before the first conversion.
+            constexpr int IT = (NVEC + SB_THREADS - 1) / SB_THREADS;
+            static_assert(SB_THREADS / VPR == 5 && SB_THREADS % VPR == 6, "incremental (row, vector) update below");
+            typedef typename std::conditional<sizeof(TIn) == 4, float4, uchar4>::type VecT;
+            VecT q[IT];
+            int r = tid / VPR, v = tid - r * VPR;
+#pragma unroll
+            for (int it = 0; it < IT; ++it) {
+                const int iy = iy0 + r, e0 = abase + 4 * v;
+                const bool ok = tid + it * SB_THREADS < NVEC && (unsigned)iy < (unsigned)p.H && (unsigned)e0 < (unsigned)rowlen;
+                if constexpr (sizeof(TIn) == 4) q[it] = make_float4(0.f, 0.f, 0.f, 0.f); else q[it] = make_uchar4(0, 0, 0, 0);
+                if (ok) q[it] = __ldg(reinterpret_cast<const VecT*>(img + (size_t)iy * rowlen + e0));
+                v += SB_THREADS % VPR; r += SB_THREADS / VPR;
+                if (v >= VPR) { v -= VPR; ++r; }
+            }
+            r = tid / VPR; v = tid - r * VPR;
+#pragma unroll
+            for (int it = 0; it < IT; ++it) {
+                uint2 o;
+                o.x = sb_pack(__floats2half2_rn(sb_to_float(q[it].x), sb_to_float(q[it].y)));
+                o.y = sb_pack(__floats2half2_rn(sb_to_float(q[it].z), sb_to_float(q[it].w)));
+                if (tid + it * SB_THREADS < NVEC) *reinterpret_cast<uint2*>(sImg + r * SB_IROWLEN + 4 * v) = o;
+                v += SB_THREADS % VPR; r += SB_THREADS / VPR;
+                if (v >= VPR) { v -= VPR; ++r; }
+            }
+        } else {
+            for (int i = tid; i < NVEC; i += SB_THREADS) {
+                const int r = i / VPR, v = i - r * VPR;
+                const int iy = iy0 + r, e0 = abase + 4 * v;
+                float x[4] = {0.f, 0.f, 0.f, 0.f};
+                if ((unsigned)iy < (unsigned)p.H) {
+                    const TIn* src = img + (size_t)iy * rowlen;
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
                         if (e0 + c >= 0 && e0 + c < rowlen) x[c] = sb_to_float(__ldg(src + e0 + c));
                 }
+                uint2 o;
+                o.x = sb_pack(__floats2half2_rn(x[0], x[1]));
+                o.y = sb_pack(__floats2half2_rn(x[2], x[3]));
+                *reinterpret_cast<uint2*>(sImg + r * SB_IROWLEN + 4 * v) = o;
             }
-            uint2 o;
-            o.x = sb_pack(__floats2half2_rn(x[0], x[1]));
-            o.y = sb_pack(__floats2half2_rn(x[2], x[3]));
-            *reinterpret_cast<uint2*>(sImg + r * SB_IROWLEN + 4 * v) = o;
         }
     }
     __syncthreads();
 
-    // ---- 2. stem: patch positions x 32 channels; position = pr * 32 + pc, A element (position, k) with k -> (ky = k / 9,
-    //         j = k % 9) lives at sImg[(2 pr + ky) * ROWLEN + 6 pc + j + shift] ----------------------------------------
+    // ---- 2. stem: patch positions x 32 channels; position = pr * 32 + pc, tap (ky, j = kx * 3 + ci) of a position lives at
+    //         sImg[(2 pr + ky) * ROWLEN + 6 pc + shift + j] ---------------------------------------------------------
     {
-        int koff[8];                                              // staged offset of this thread's 8 k values (-1: zero)
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int k = 16 * (q >> 2) + 8 * ((q >> 1) & 1) + 2 * t + (q & 1);
-            koff[q] = k < 27 ? (k / 9) * SB_IROWLEN + (k % 9) + shift : -1;
-        }
         const __half2 lo2 = __float2half2_rn(p.stem_act == SSD_ACT_NONE ? -65504.0f : 0.0f);
         const __half2 hi2 = __float2half2_rn(p.stem_act == SSD_ACT_RELU6 ? 6.0f : 65504.0f);
         float bias[4][2];
@@ -176,16 +202,10 @@ stem_dwproj_kernel(const __grid_constant__ SbParams p) {
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 uint32_t a[4];
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {                     // r: k half (k .. k+7 / k+8 .. k+15)
-                    const int q = s * 4 + r * 2;
-                    const uint16_t x00 = koff[q] >= 0 ? __half_as_ushort(sImg[koff[q] + p0]) : (uint16_t)0;
-                    const uint16_t x01 = koff[q + 1] >= 0 ? __half_as_ushort(sImg[koff[q + 1] + p0]) : (uint16_t)0;
-                    const uint16_t x10 = koff[q] >= 0 ? __half_as_ushort(sImg[koff[q] + p1]) : (uint16_t)0;
-                    const uint16_t x11 = koff[q + 1] >= 0 ? __half_as_ushort(sImg[koff[q + 1] + p1]) : (uint16_t)0;
-                    a[r * 2 + 0] = (uint32_t)x00 | ((uint32_t)x01 << 16);
-                    a[r * 2 + 1] = (uint32_t)x10 | ((uint32_t)x11 << 16);
-                }
+                a[0] = sb_lds32(sImg32 + (uint32_t)(p0 + soff[2 * s]) * 2u);
+                a[1] = sb_lds32(sImg32 + (uint32_t)(p1 + soff[2 * s]) * 2u);
+                a[2] = sb_lds32(sImg32 + (uint32_t)(p0 + soff[2 * s + 1]) * 2u);
+                a[3] = sb_lds32(sImg32 + (uint32_t)(p1 + soff[2 * s + 1]) * 2u);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) sb_mma16816(acc[j], a, bf[s][j][0], bf[s][j][1]);
             }
