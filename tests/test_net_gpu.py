@@ -295,9 +295,15 @@ IRBLOCK_CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", IRBLOCK_CASES)
-def test_irblock_fused_against_torch(case):
-    """ssd_irblock (whole inverted-residual block in one launch) against torch-CPU with the same fp16 roundings."""
+@pytest.mark.parametrize("mode", [-1, 0])
+@pytest.mark.parametrize("case", IRBLOCK_CASES + [
+    (1, 33, 41, 24, 144, 24, 1, True),        # mma.sync variant: partial tiles in both directions, odd sizes
+    (2, 31, 26, 16, 96, 24, 2, False), (1, 40, 17, 32, 192, 64, 2, False), (2, 21, 23, 32, 192, 32, 1, True),
+    (1, 20, 34, 24, 144, 32, 2, False),
+])
+def test_irblock_fused_against_torch(case, mode):
+    """ssd_irblock (whole inverted-residual block in one launch) against torch-CPU with the same fp16 roundings -- both
+    implementations: the tcgen05 pipeline (mode 0) and, for the large-map block shapes, the mma.sync kernel (mode -1)."""
     from tf_ssd_b200 import _ffi
     from tf_ssd_b200._ffi_conv import IrBlockDesc
     import ctypes as C
@@ -327,6 +333,7 @@ def test_irblock_fused_against_torch(case):
     d.B, d.H, d.W, d.Cin, d.Cexp, d.Ho, d.Wo, d.Cout = B, H, W, Cin, Cexp, Ho, Wo, Cout
     d.stride, d.pad_top, d.pad_left, d.exp_act, d.dw_act, d.act = stride, ph[0], pw[0], 2, 2, 0
     lib = _ffi.lib()
+    lib.ssd_debug_irblock_mode(mode)
     assert lib.ssd_irblock_supported(C.byref(d)) == 1
     runs = []
     for _ in range(6):          # repeated launches must agree bit for bit: the stages hand data over through mbarriers
@@ -334,6 +341,7 @@ def test_irblock_fused_against_torch(case):
         _ffi.check(lib.ssd_irblock(C.byref(d), _ffi.stream()), "ssd_irblock")
         runs.append(out.clone())
     torch.cuda.synchronize()
+    lib.ssd_debug_irblock_mode(-1)
     assert all(torch.equal(runs[0], r) for r in runs[1:])
     f = lambda a: torch.from_numpy(a).float() if a is not None else None
     y = _irblock_reference(f(x), f(we), f(be), 2, f(wd), f(bd), stride, ph, pw, 2, f(wp), f(bp), 0, f(res))

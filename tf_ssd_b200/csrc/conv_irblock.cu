@@ -766,6 +766,12 @@ int conv_irblock_launch(const ssd_irblock_desc* d, cudaStream_t st) {
 
 }  // namespace ssd
 
+namespace ssd {
+// conv_irblock_mma.cu: the mma.sync implementation of the large-map blocks (MobileNetV2 blocks 1-6)
+bool conv_irblock_mma_matches(const ssd_irblock_desc* d);
+int conv_irblock_mma_launch(const ssd_irblock_desc* d, cudaStream_t st);
+}  // namespace ssd
+
 extern "C" int ssd_irblock(const ssd_irblock_desc* d, ssd_stream_t stream) {
     SSD_REQUIRE_PTR(d);
     SSD_REQUIRE_PTR(d->in); SSD_REQUIRE_PTR(d->exp_weight); SSD_REQUIRE_PTR(d->dw_weight); SSD_REQUIRE_PTR(d->proj_weight);
@@ -778,6 +784,7 @@ extern "C" int ssd_irblock(const ssd_irblock_desc* d, ssd_stream_t stream) {
     SSD_REQUIRE(ssd::conv_irblock_supported(d), SSD_ERR_UNSUPPORTED,
                 "ssd_irblock: unsupported configuration (channels %% 8, Cin <= 256, Cexp <= 1024, Cout <= 256, stride 1|2, "
                 "16-byte aligned pointers)");
+    if (ssd::conv_irblock_mma_matches(d)) return ssd::conv_irblock_mma_launch(d, ssd::as_stream(stream));
     return ssd::conv_irblock_launch(d, ssd::as_stream(stream));
 }
 

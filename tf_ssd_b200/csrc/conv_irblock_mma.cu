@@ -1,0 +1,471 @@
+// The LARGE-MAP inverted-residual blocks of MobileNetV2 (blocks 1-6: 150x150 ... 38x38, Cin <= 32, Cexp <= 192) as one
+// launch each, on mma.sync -- second implementation behind ssd_irblock (keras_applications.mobilenet_v2.
+// _inverted_res_block under models/ssd_mobilenet_v2.py:25 of the reference):
+//
+//     1x1 expand (+ folded BN + ReLU6) -> depthwise 3x3 stride 1|2 (+ folded BN + ReLU6) -> 1x1 project (+ folded BN, + shortcut)
+//
+// Why not the tcgen05 pipeline of conv_irblock.cu here: these blocks have shallow contractions (K = 16..32 for the
+// expansion, N = 24..64 for the projection) and small weights, so the tensor pipe is idle either way; the tcgen05 kernel
+// is ONE CTA per SM whose five roles hand 64-channel slices over through mbarriers, and its slice period (~2 us) is a
+// latency chain (TMA -> MMA -> TMEM load -> shared memory -> depthwise -> MMA), not work.  Here a CTA owns one small
+// output tile with ALL expanded channels, phases are separated by plain __syncthreads(), and two CTAs per SM overlap each
+// other's phases; the cost is issue slots (the expansion's epilogue and the depthwise FMAs), nothing waits on a chain.
+//
+//   1. cp.async: input patch (tile + halo, zero outside the image), expansion / depthwise / projection weights, biases;
+//   2. expansion: [patch positions x Cin] x [Cin x Cexp] on mma.sync.m16n8k16 (ldmatrix operands), + bias, ReLU6 fused into
+//      the fp16 conversion (cvt.rn.relu) -> expanded patch in shared memory; edge tiles then zero the positions outside
+//      the image (the depthwise layer's zero padding);
+//   3. depthwise 3x3: a thread owns one 8-channel chunk (its 9 x 8 taps live in registers) and walks over tile pixels,
+//      packed half2 FMAs -> the projection's A operand in shared memory;
+//   4. projection: [pixels x Cexp] x [Cexp x Cout] on mma.sync, + bias -> fp32 staging tile;
+//   5. (+ residual) -> fp16 -> 16-byte coalesced stores.
+//
+// Shared-memory tiles are arrays of 16-channel SLICES: tile[slice][row][16 fp16] (32-byte rows, slice stride = one row
+// more than the row count so that the depthwise stage's 16-byte accesses -- 8 consecutive chunks of one position = 4
+// slices -- are bank-conflict free); a k16 step of either GEMM is one slice.  The ldmatrix operands (input patch, weights,
+// depthwise tile) XOR the 16-byte half of a row with (row >> 2) & 1 (conflict-free 8-row phases); the expanded patch is
+// linear, so that the nine depthwise taps of a pixel are compile-time offsets from one address.
+
+#include "common.cuh"
+
+namespace ssd {
+
+constexpr int IM_THREADS = 256;
+constexpr int IM_WARPS = IM_THREADS / 32;
+
+__host__ __device__ constexpr int im_up16(int v) { return (v + 15) / 16 * 16; }
+__host__ __device__ constexpr int im_max(int a, int b) { return a > b ? a : b; }
+
+template <int CIN_, int CEXP_, int COUT_, int STRIDE_, int TW_, int TH_>
+struct ImCfg {
+    static constexpr int CIN = CIN_, CEXP = CEXP_, COUT = COUT_, S = STRIDE_, TW = TW_, TH = TH_;
+    static constexpr int KIN = im_up16(CIN);                  // expansion K, zero-padded to whole k16 steps
+    static constexpr int KS = KIN / 16;                       // input slices = k16 steps of the expansion
+    static constexpr int ES = CEXP / 16;                      // expanded slices = n-tile pairs of the expansion = k16 steps of the projection
+    static constexpr int PW = (TW - 1) * S + 3, PH = (TH - 1) * S + 3;
+    static constexpr int P = PW * PH, PPOS = im_up16(P);      // patch positions (rows of the expansion GEMM)
+    static constexpr int NPX = TW * TH, MPX = im_up16(NPX);   // tile pixels (rows of the projection GEMM)
+    static constexpr int COUTP = im_up16(COUT);               // projection N, whole n-tile pairs
+    static constexpr int MT = PPOS / 16, MTP = MPX / 16, NP = COUTP / 16;
+    static constexpr int NCH = CEXP / 8;                      // 8-channel chunks of the expanded tensor
+    static constexpr int NPL = IM_THREADS / NCH;              // pixel lanes of the depthwise stage
+    // slice strides (bytes): one padding row per slice (see the header comment)
+    static constexpr int IN_SL = (PPOS + 1) * 32, MID_SL = (PPOS + 1) * 32, DW_SL = (MPX + 1) * 32;
+    static constexpr int WE_SL = (CEXP + 1) * 32, WP_SL = (COUTP + 1) * 32;
+    // layout: region A = [input patch | expansion weights] during phases 1-2, the depthwise tile during phases 3-4;
+    // the expanded patch (phases 2-3) is reused as the fp32 output staging tile (phases 4-5)
+    static constexpr int OFF_IN = 0;
+    static constexpr int OFF_WE = OFF_IN + KS * IN_SL;
+    static constexpr int A_BYTES = im_max(OFF_WE + KS * WE_SL, ES * DW_SL);
+    static constexpr int OFF_DW = 0;
+    static constexpr int OFF_MID = A_BYTES;
+    static constexpr int OFF_WP = OFF_MID + im_max(ES * MID_SL, NPX * COUT * 4);
+    static constexpr int OFF_WD = OFF_WP + ES * WP_SL;        // [9][CEXP] fp16
+    static constexpr int OFF_BE = OFF_WD + 9 * CEXP * 2;      // expansion bias [CEXP] f32
+    static constexpr int OFF_BD = OFF_BE + CEXP * 4;          // depthwise bias [CEXP] f32
+    static constexpr int OFF_BP = OFF_BD + CEXP * 4;          // projection bias [COUTP] f32
+    static constexpr int SMEM = OFF_BP + COUTP * 4;
+    static_assert(CIN % 8 == 0 && CEXP % 16 == 0 && COUT % 8 == 0, "channel granularity");
+    static_assert(OFF_MID % 16 == 0 && OFF_WP % 16 == 0 && OFF_WD % 16 == 0 && OFF_BE % 16 == 0 && OFF_BD % 16 == 0 && OFF_BP % 16 == 0, "alignment");
+    static_assert(2 * (SMEM + 1024) <= 227 * 1024, "two CTAs per SM");
+    static_assert(NCH <= IM_THREADS, "depthwise mapping");
+};
+
+struct ImParams {
+    const __half* in; const __half* we; const float* be; const __half* wd; const float* bd;
+    const __half* wp; const float* bp; const __half* res; __half* out;
+    int B, H, W, Ho, Wo, pad_t, pad_l, tiles_x;
+};
+
+// byte offset of (row, 16-byte half h) inside a slice
+__device__ __forceinline__ uint32_t im_row(int row, int h) { return (uint32_t)(row * 32 + ((h ^ ((row >> 2) & 1)) << 4)); }
+__device__ __forceinline__ void im_ldsm4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void im_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// first k-step of the expansion: the accumulator starts at the bias (C = {c0, c1, c0, c1}: rows g and g + 8 share the columns)
+__device__ __forceinline__ void im_mma_bias(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, float c0, float c1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%10,%11};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c0), "f"(c1));
+}
+// fp16x2(max(lo, 0), max(hi, 0)): the lower bound of ReLU6 fused into the conversion
+__device__ __forceinline__ uint32_t im_cvt_relu(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t im_min2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("min.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint4 im_lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void im_sts128(uint32_t a, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void im_sts64(uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void im_sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void im_sts64f(uint32_t a, float x, float y) {
+    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ float2 im_lds64f(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float4 im_lds128f(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void im_cp16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// 16 bytes when ok, else 16 bytes of zeros (src-size 0: nothing is read) -- no divergent zero-store path
+__device__ __forceinline__ void im_cp16_zfill(uint32_t dst, const void* src, bool ok) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(IM_THREADS, 2)
+irblock_mma_kernel(const __grid_constant__ ImParams p) {
+    extern __shared__ __align__(16) unsigned char im_smem[];
+    const uint32_t sm = (uint32_t)__cvta_generic_to_shared(im_smem);
+    const uint32_t sIn = sm + Cfg::OFF_IN, sWe = sm + Cfg::OFF_WE, sDw = sm + Cfg::OFF_DW, sMid = sm + Cfg::OFF_MID;
+    const uint32_t sWp = sm + Cfg::OFF_WP, sWd = sm + Cfg::OFF_WD, sBe = sm + Cfg::OFF_BE, sBd = sm + Cfg::OFF_BD, sBp = sm + Cfg::OFF_BP;
+    constexpr int S = Cfg::S, PW = Cfg::PW, P = Cfg::P, CIN = Cfg::CIN, CEXP = Cfg::CEXP, COUT = Cfg::COUT;
+    pdl_trigger();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x, b = blockIdx.y;
+    const int oy0 = ty * Cfg::TH, ox0 = tx * Cfg::TW;
+    const int iy0 = oy0 * S - p.pad_t, ix0 = ox0 * S - p.pad_l;          // image coordinates of patch position (0, 0)
+
+    // ---- 1a. weights and biases (never written by a predecessor of the plan: before the PDL wait) ----
+    for (int i = tid; i < CEXP * (Cfg::KIN / 8); i += IM_THREADS) {      // expansion weights [CEXP][CIN] -> slices of 16 k
+        const int n = i / (Cfg::KIN / 8), c = i - n * (Cfg::KIN / 8);
+        // Row order inside a 16-channel slice: MMA column (n-tile q, column j) computes channel 4 (j >> 1) + 2 q + (j & 1),
+        // so that a thread's four accumulator columns (2t, 2t+1 of both n-tiles) are the CONTIGUOUS channels 4t .. 4t+3
+        // (one 8-byte store per row; a warp's store instruction covers 8 whole 32-byte rows, conflict-free).
+        const int cl = n & 15, nrow = (n & ~15) + 8 * ((cl >> 1) & 1) + 2 * (cl >> 2) + (cl & 1);
+        const uint32_t dst = sWe + (uint32_t)((c >> 1) * Cfg::WE_SL) + im_row(nrow, c & 1);
+        if (c < CIN / 8) im_cp16(dst, p.we + (size_t)n * CIN + 8 * c);
+        else im_sts128(dst, make_uint4(0u, 0u, 0u, 0u));
+    }
+    for (int i = tid; i < Cfg::COUTP * Cfg::NCH; i += IM_THREADS) {      // projection weights [COUT][CEXP] -> slices of 16 k
+        const int n = i / Cfg::NCH, c = i - n * Cfg::NCH;
+        const uint32_t dst = sWp + (uint32_t)((c >> 1) * Cfg::WP_SL) + im_row(n, c & 1);
+        if (n < COUT) im_cp16(dst, p.wp + (size_t)n * CEXP + 8 * c);
+        else im_sts128(dst, make_uint4(0u, 0u, 0u, 0u));
+    }
+    for (int i = tid; i < 9 * Cfg::NCH; i += IM_THREADS) im_cp16(sWd + 16u * i, p.wd + 8 * i);
+    for (int i = tid; i < CEXP; i += IM_THREADS) {
+        reinterpret_cast<float*>(im_smem + Cfg::OFF_BE)[i] = p.be ? __ldg(p.be + i) : 0.f;
+        reinterpret_cast<float*>(im_smem + Cfg::OFF_BD)[i] = p.bd ? __ldg(p.bd + i) : 0.f;
+    }
+    for (int i = tid; i < Cfg::COUTP; i += IM_THREADS)
+        reinterpret_cast<float*>(im_smem + Cfg::OFF_BP)[i] = (p.bp && i < COUT) ? __ldg(p.bp + i) : 0.f;
+    pdl_wait();
+
+    // ---- 1b. input patch: positions x KIN channels, zero outside the image and in the K padding ----
+    {
+        const __half* img = p.in + (size_t)b * p.H * p.W * CIN;
+        for (int i = tid; i < Cfg::PPOS * (Cfg::KIN / 8); i += IM_THREADS) {
+            const int pos = i / (Cfg::KIN / 8), c = i - pos * (Cfg::KIN / 8);
+            const int py = pos / PW, px = pos - py * PW;
+            const int iy = iy0 + py, ix = ix0 + px;
+            const uint32_t dst = sIn + (uint32_t)((c >> 1) * Cfg::IN_SL) + im_row(pos, c & 1);
+            const bool ok = pos < P && c < CIN / 8 && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+            im_cp16_zfill(dst, ok ? img + ((size_t)iy * p.W + ix) * CIN + 8 * c : img, ok);
+        }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+
+    // ---- 2. expansion: units of (16-channel slice, m16 tile of positions) round-robin over the warps ----
+    {
+        const uint32_t six = 0x46004600u;                              // half2(6, 6)
+        const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lhalf = lane >> 4;         // A operand: ldmatrix lane -> (row, half)
+        const int brow = (lane & 7) + (lane >> 4) * 8, bhalf = (lane >> 3) & 1;         // B operand
+        // unit = (m16 tile of positions, group of JG slices): the A fragments are loaded once per unit, per slice one
+        // ldmatrix per k-step for the weights, one 16-byte bias load, 2 KS MMAs and two 8-byte stores (shared-memory
+        // wavefronts, not issue slots, bound this kernel)
+        constexpr int G = Cfg::MT % IM_WARPS == 0 ? 1 : (Cfg::ES % 3 == 0 ? 3 : (Cfg::ES % 2 == 0 ? 2 : 1));
+        constexpr int JG = Cfg::ES / G;
+        for (int u = warp; u < Cfg::MT * G; u += IM_WARPS) {
+            const int mt = u / G, gi = u - mt * G;
+            uint32_t a[Cfg::KS][4];
+#pragma unroll
+            for (int ks = 0; ks < Cfg::KS; ++ks)
+                im_ldsm4(a[ks], sIn + (uint32_t)(ks * Cfg::IN_SL) + im_row(mt * 16 + lrow, lhalf));
+            const uint32_t dst0 = sMid + (uint32_t)((mt * 16 + g) * 32 + 8 * t);
+#pragma unroll 2
+            for (int jj = 0; jj < JG; ++jj) {
+                const int jp = gi * JG + jj;
+                uint32_t bq[Cfg::KS][4];
+#pragma unroll
+                for (int ks = 0; ks < Cfg::KS; ++ks)
+                    im_ldsm4(bq[ks], sWe + (uint32_t)(ks * Cfg::WE_SL) + im_row(jp * 16 + brow, bhalf));
+                const float4 bias = im_lds128f(sBe + (uint32_t)(jp * 16 + 4 * t) * 4u);       // channels 4t .. 4t+3 of the slice
+                float acc[2][4];
+                im_mma_bias(acc[0], a[0], bq[0][0], bq[0][1], bias.x, bias.y);
+                im_mma_bias(acc[1], a[0], bq[0][2], bq[0][3], bias.z, bias.w);
+#pragma unroll
+                for (int ks = 1; ks < Cfg::KS; ++ks) {
+                    im_mma(acc[0], a[ks], bq[ks][0], bq[ks][1]);
+                    im_mma(acc[1], a[ks], bq[ks][2], bq[ks][3]);
+                }
+                // the expanded patch is LINEAR (row = 32 bytes = 16 channels in their true order)
+                const uint32_t dst = dst0 + (uint32_t)(jp * Cfg::MID_SL);
+                im_sts64(dst, im_min2(im_cvt_relu(acc[0][0], acc[0][1]), six), im_min2(im_cvt_relu(acc[1][0], acc[1][1]), six));
+                im_sts64(dst + 256, im_min2(im_cvt_relu(acc[0][2], acc[0][3]), six), im_min2(im_cvt_relu(acc[1][2], acc[1][3]), six));
+            }
+        }
+    }
+    __syncthreads();
+    // edge tiles: positions outside the image are the depthwise layer's zero padding, not ReLU6(bias)
+    if (iy0 < 0 || ix0 < 0 || iy0 + Cfg::PH > p.H || ix0 + PW > p.W) {
+        for (int i = tid; i < P * Cfg::ES; i += IM_THREADS) {
+            const int pos = i / Cfg::ES, sl = i - pos * Cfg::ES;
+            const int py = pos / PW, px = pos - py * PW;
+            if ((unsigned)(iy0 + py) >= (unsigned)p.H || (unsigned)(ix0 + px) >= (unsigned)p.W) {
+                const uint32_t a = sMid + (uint32_t)(sl * Cfg::MID_SL + pos * 32);
+                im_sts128(a, make_uint4(0u, 0u, 0u, 0u));
+                im_sts128(a + 16, make_uint4(0u, 0u, 0u, 0u));
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- 3. depthwise 3x3: thread = (8-channel chunk, pixel lane); packed half2 FMAs, fp16 accumulation from the fp16 bias ----
+    if (tid < Cfg::NCH * Cfg::NPL) {
+        const int c8 = tid % Cfg::NCH, pl = tid / Cfg::NCH;
+        uint4 w[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w[k] = im_lds128(sWd + (uint32_t)(k * CEXP + 8 * c8) * 2u);
+        __half2 bias4[4];
+        {
+            const float4 b0 = im_lds128f(sBd + (uint32_t)(8 * c8) * 4u), b1 = im_lds128f(sBd + (uint32_t)(8 * c8 + 4) * 4u);
+            bias4[0] = __floats2half2_rn(b0.x, b0.y); bias4[1] = __floats2half2_rn(b0.z, b0.w);
+            bias4[2] = __floats2half2_rn(b1.x, b1.y); bias4[3] = __floats2half2_rn(b1.z, b1.w);
+        }
+        const __half2 zero2 = __float2half2_rn(0.f), six2 = __float2half2_rn(6.f);
+        const int h = c8 & 1;
+        const uint32_t src = sMid + (uint32_t)((c8 >> 1) * Cfg::MID_SL + h * 16), dstb = sDw + (uint32_t)((c8 >> 1) * Cfg::DW_SL);
+        if constexpr (S == 1) {
+            // stride 1: runs of 3 horizontally adjacent pixels share their input columns (15 loads per 3 outputs instead
+            // of 27); columns past the tile's halo belong to discarded outputs and only read allocated shared memory
+            constexpr int RPR = (Cfg::TW + 2) / 3, NRUN = Cfg::TH * RPR;
+            int y = pl / RPR, xr = pl - y * RPR;
+            for (int run = pl; run < NRUN; run += Cfg::NPL) {
+                const int x0 = 3 * xr;
+                const uint32_t a0 = src + (uint32_t)((y * PW + x0) * 32);
+                __half2 acc[3][4];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int c2 = 0; c2 < 4; ++c2) acc[i][c2] = bias4[c2];
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) {
+                        const uint4 xv = im_lds128(a0 + (uint32_t)((ky * PW + c) * 32));
+                        const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const int kx = c - i;
+                            if (kx >= 0 && kx < 3) {
+                                const __half2* wh = reinterpret_cast<const __half2*>(&w[ky * 3 + kx]);
+#pragma unroll
+                                for (int c2 = 0; c2 < 4; ++c2) acc[i][c2] = __hfma2(xh[c2], wh[c2], acc[i][c2]);
+                            }
+                        }
+                    }
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    if (x0 + i < Cfg::TW) {
+                        uint4 o;
+                        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int c2 = 0; c2 < 4; ++c2) oh[c2] = __hmin2(__hmax2(acc[i][c2], zero2), six2);
+                        im_sts128(dstb + im_row(y * Cfg::TW + x0 + i, h), o);
+                    }
+                xr += Cfg::NPL % RPR; y += Cfg::NPL / RPR;
+                if (xr >= RPR) { xr -= RPR; ++y; }
+            }
+        } else {
+        // two pixels in flight per iteration (independent load -> FMA chains)
+            int y = pl / Cfg::TW, x = pl - y * Cfg::TW;
+            for (int px = pl; px < Cfg::NPX; px += 2 * Cfg::NPL) {
+                int yy[2], xx[2];
+                yy[0] = y; xx[0] = x;
+                x += Cfg::NPL % Cfg::TW; y += Cfg::NPL / Cfg::TW;
+                if (x >= Cfg::TW) { x -= Cfg::TW; ++y; }
+                const bool two = px + Cfg::NPL < Cfg::NPX;
+                yy[1] = two ? y : yy[0]; xx[1] = two ? x : xx[0];
+                x += Cfg::NPL % Cfg::TW; y += Cfg::NPL / Cfg::TW;
+                if (x >= Cfg::TW) { x -= Cfg::TW; ++y; }
+                uint32_t a0[2];
+                __half2 acc[2][4];
+    #pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    a0[q] = src + (uint32_t)((yy[q] * S * PW + xx[q] * S) * 32);
+    #pragma unroll
+                    for (int c2 = 0; c2 < 4; ++c2) acc[q][c2] = bias4[c2];
+                }
+    #pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+    #pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const __half2* wh = reinterpret_cast<const __half2*>(&w[ky * 3 + kx]);
+    #pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const uint4 xv = im_lds128(a0[q] + (uint32_t)((ky * PW + kx) * 32));
+                            const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+    #pragma unroll
+                            for (int c2 = 0; c2 < 4; ++c2) acc[q][c2] = __hfma2(xh[c2], wh[c2], acc[q][c2]);
+                        }
+                    }
+    #pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (q == 1 && !two) break;
+                    uint4 o;
+                    __half2* oh = reinterpret_cast<__half2*>(&o);
+    #pragma unroll
+                    for (int c2 = 0; c2 < 4; ++c2) oh[c2] = __hmin2(__hmax2(acc[q][c2], zero2), six2);
+                    im_sts128(dstb + im_row(px + q * Cfg::NPL, h), o);
+                }
+            }
+        }
+        }
+    __syncthreads();
+
+    // ---- 4. projection: units of (m16 tile of pixels, n-tile pair); fp32 results (+ bias) -> staging tile [pixel][COUT] ----
+    {
+        const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lhalf = lane >> 4;
+        const int brow = (lane & 7) + (lane >> 4) * 8, bhalf = (lane >> 3) & 1;
+        const uint32_t sOut = sMid;
+        for (int u = warp; u < Cfg::MTP * Cfg::NP; u += IM_WARPS) {
+            const int mt = u / Cfg::NP, np = u - mt * Cfg::NP;
+            float acc[2][4];
+#pragma unroll
+            for (int n = 0; n < 2; ++n)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[n][r] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < Cfg::ES; ++ks) {
+                uint32_t a[4], bq[4];
+                im_ldsm4(a, sDw + (uint32_t)(ks * Cfg::DW_SL) + im_row(mt * 16 + lrow, lhalf));
+                im_ldsm4(bq, sWp + (uint32_t)(ks * Cfg::WP_SL) + im_row(np * 16 + brow, bhalf));
+                im_mma(acc[0], a, bq[0], bq[1]);
+                im_mma(acc[1], a, bq[2], bq[3]);
+            }
+            const int r0 = mt * 16 + g;
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+                const int c = np * 16 + n * 8 + 2 * t;
+                if (c < COUT) {
+                    const float2 bias = im_lds64f(sBp + (uint32_t)c * 4u);
+                    if (r0 < Cfg::NPX) im_sts64f(sOut + (uint32_t)(r0 * COUT + c) * 4u, acc[n][0] + bias.x, acc[n][1] + bias.y);
+                    if (r0 + 8 < Cfg::NPX) im_sts64f(sOut + (uint32_t)((r0 + 8) * COUT + c) * 4u, acc[n][2] + bias.x, acc[n][3] + bias.y);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 5. (+ residual) -> fp16 -> 16-byte coalesced stores ----
+    {
+        constexpr int U = COUT / 8;
+        for (int i = tid; i < Cfg::NPX * U; i += IM_THREADS) {
+            const int px = i / U, u = i - px * U;
+            const int y = px / Cfg::TW, x = px - y * Cfg::TW;
+            const int oy = oy0 + y, ox = ox0 + x;
+            if (oy < p.Ho && ox < p.Wo) {
+                const float4 v0 = im_lds128f(sMid + (uint32_t)(px * COUT + 8 * u) * 4u);
+                const float4 v1 = im_lds128f(sMid + (uint32_t)(px * COUT + 8 * u + 4) * 4u);
+                float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                const size_t off = (((size_t)b * p.Ho + oy) * p.Wo + ox) * COUT + 8 * u;
+                if (p.res) {
+                    const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + off));
+                    const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float2 f = __half22float2(rh[c]);
+                        v[2 * c] += f.x; v[2 * c + 1] += f.y;
+                    }
+                }
+                uint4 o;
+                __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) oh[c] = __floats2half2_rn(v[2 * c], v[2 * c + 1]);
+                *reinterpret_cast<uint4*>(p.out + off) = o;
+            }
+        }
+    }
+}
+
+template <class Cfg>
+static int irblock_mma_launch_t(const ssd_irblock_desc* d, cudaStream_t st) {
+    ImParams p;
+    p.in = static_cast<const __half*>(d->in); p.we = static_cast<const __half*>(d->exp_weight); p.be = d->exp_bias;
+    p.wd = static_cast<const __half*>(d->dw_weight); p.bd = d->dw_bias;
+    p.wp = static_cast<const __half*>(d->proj_weight); p.bp = d->proj_bias;
+    p.res = static_cast<const __half*>(d->residual); p.out = static_cast<__half*>(d->out);
+    p.B = d->B; p.H = d->H; p.W = d->W; p.Ho = d->Ho; p.Wo = d->Wo; p.pad_t = d->pad_top; p.pad_l = d->pad_left;
+    p.tiles_x = ceil_div(d->Wo, Cfg::TW);
+    static thread_local int attr_dev = -1;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (attr_dev != cur) {
+        cudaError_t e = cudaFuncSetAttribute(irblock_mma_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        if (e != cudaSuccess) return cuda_fail(e, "ssd_irblock: cudaFuncSetAttribute (mma.sync variant)");
+        attr_dev = cur;
+    }
+    const dim3 grid(p.tiles_x * ceil_div(d->Ho, Cfg::TH), d->B);
+    cudaError_t le = launch_pdl(irblock_mma_kernel<Cfg>, grid, dim3(IM_THREADS), (size_t)Cfg::SMEM, st, p);
+    if (le != cudaSuccess) return cuda_fail(le, "irblock_mma_kernel");
+    return SSD_OK;
+}
+
+// MobileNetV2 blocks 1-6 at width 1.0 (t = 6): (Cin, Cexp, Cout, stride) and the output tile chosen for each
+typedef ImCfg<16, 96, 24, 2, 15, 5> ImBlock1;       // 150 -> 75: 5 x 15 tiles per image
+typedef ImCfg<24, 144, 24, 1, 15, 5> ImBlock2;      // 75 x 75
+typedef ImCfg<24, 144, 32, 2, 10, 4> ImBlock3;      // 75 -> 38
+typedef ImCfg<32, 192, 32, 1, 19, 4> ImBlock45;     // 38 x 38
+typedef ImCfg<32, 192, 64, 2, 19, 1> ImBlock6;      // 38 -> 19
+
+static int g_irblock_mode = -1;      // -1 automatic, 0 tcgen05 kernel only, 1 mma.sync variant whenever a configuration matches
+
+// 1 when the mma.sync variant has an instantiation for this block (and ReLU6 / ReLU6 / linear activations, B <= 65535)
+bool conv_irblock_mma_matches(const ssd_irblock_desc* d) {
+    if (g_irblock_mode == 0) return false;
+    if (!(d->exp_act == SSD_ACT_RELU6 && d->dw_act == SSD_ACT_RELU6 && d->act == SSD_ACT_NONE && d->B <= 65535)) return false;
+    auto is = [&](int ci, int ce, int co, int s) { return d->Cin == ci && d->Cexp == ce && d->Cout == co && d->stride == s; };
+    return is(16, 96, 24, 2) || is(24, 144, 24, 1) || is(24, 144, 32, 2) || is(32, 192, 32, 1) || is(32, 192, 64, 2);
+}
+
+int conv_irblock_mma_launch(const ssd_irblock_desc* d, cudaStream_t st) {
+    if (d->Cexp == 96) return irblock_mma_launch_t<ImBlock1>(d, st);
+    if (d->Cexp == 144) return d->stride == 1 ? irblock_mma_launch_t<ImBlock2>(d, st) : irblock_mma_launch_t<ImBlock3>(d, st);
+    return d->stride == 1 ? irblock_mma_launch_t<ImBlock45>(d, st) : irblock_mma_launch_t<ImBlock6>(d, st);
+}
+
+}  // namespace ssd
+
+extern "C" int ssd_debug_irblock_mode(int mode) {
+    ssd::g_irblock_mode = mode;
+    return SSD_OK;
+}
