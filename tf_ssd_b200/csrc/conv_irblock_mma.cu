@@ -26,7 +26,7 @@
 // depthwise tile) XOR the 16-byte half of a row with (row >> 2) & 1 (conflict-free 8-row phases); the expanded patch is
 // linear, so that the nine depthwise taps of a pixel are compile-time offsets from one address.
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace ssd {
 
@@ -35,6 +35,17 @@ constexpr int IM_WARPS = IM_THREADS / 32;
 
 __host__ __device__ constexpr int im_up16(int v) { return (v + 15) / 16 * 16; }
 __host__ __device__ constexpr int im_max(int a, int b) { return a > b ? a : b; }
+// expansion work split: units = m-tiles x G slice groups over 8 warps; G (a divisor of the slice count) minimising
+// rounds x slices per unit
+__host__ __device__ constexpr int im_best_groups(int mt, int es) {
+    int best = 1, cost = ((mt + 7) / 8) * es;
+    for (int gq = 2; gq <= es; ++gq)
+        if (es % gq == 0) {
+            const int c = ((mt * gq + 7) / 8) * (es / gq);
+            if (c < cost) { cost = c; best = gq; }
+        }
+    return best;
+}
 
 template <int CIN_, int CEXP_, int COUT_, int STRIDE_, int TW_, int TH_>
 struct ImCfg {
@@ -49,24 +60,31 @@ struct ImCfg {
     static constexpr int MT = PPOS / 16, MTP = MPX / 16, NP = COUTP / 16;
     static constexpr int NCH = CEXP / 8;                      // 8-channel chunks of the expanded tensor
     static constexpr int NPL = IM_THREADS / NCH;              // pixel lanes of the depthwise stage
-    // slice strides (bytes): one padding row per slice (see the header comment)
-    static constexpr int IN_SL = (PPOS + 1) * 32, MID_SL = (PPOS + 1) * 32, DW_SL = (MPX + 1) * 32;
-    static constexpr int WE_SL = (CEXP + 1) * 32, WP_SL = (COUTP + 1) * 32;
-    // layout: region A = [input patch | expansion weights] during phases 1-2, the depthwise tile during phases 3-4;
-    // the expanded patch (phases 2-3) is reused as the fp32 output staging tile (phases 4-5)
+    // slice strides (bytes).  TMA destinations (input patch, expansion / projection weights): whole rows, 128-byte aligned,
+    // so that the tensor map's 32-byte swizzle == im_row()'s XOR.  Expanded patch and depthwise tile: one padding row per
+    // slice (see the header comment).
+    static constexpr int IN_SL = PPOS * 32, WE_SL = CEXP * 32, WP_SL = COUTP * 32;
+    static constexpr int MID_SL = (PPOS + 1) * 32, DW_SL = (MPX + 1) * 32;
+    // layout (256-byte aligned TMA destinations so that the tensor map's 32-byte swizzle, which XORs address bit 7 into bit 4,
+    // equals im_row()'s XOR with (row >> 2) & 1).  The kernel is persistent: the weights are loaded once per CTA, and the
+    // input patch of the NEXT tile is requested as soon as the expansion of the current one has read the buffer, so it lands
+    // under the depthwise / projection / store phases.  The expanded patch is reused as the fp32 output staging tile.
     static constexpr int OFF_IN = 0;
     static constexpr int OFF_WE = OFF_IN + KS * IN_SL;
-    static constexpr int A_BYTES = im_max(OFF_WE + KS * WE_SL, ES * DW_SL);
-    static constexpr int OFF_DW = 0;
-    static constexpr int OFF_MID = A_BYTES;
-    static constexpr int OFF_WP = OFF_MID + im_max(ES * MID_SL, NPX * COUT * 4);
-    static constexpr int OFF_WD = OFF_WP + ES * WP_SL;        // [9][CEXP] fp16
-    static constexpr int OFF_BE = OFF_WD + 9 * CEXP * 2;      // expansion bias [CEXP] f32
+    static constexpr int OFF_WP = OFF_WE + KS * WE_SL;
+    static constexpr int OFF_DW = OFF_WP + ES * WP_SL;
+    static constexpr int OFF_MID = OFF_DW + (ES * DW_SL + 255) / 256 * 256;
+    static constexpr int OFF_WD = OFF_MID + (im_max(ES * MID_SL, NPX * COUT * 4) + 255) / 256 * 256;   // [9][CEXP] fp16
+    static constexpr int OFF_BE = OFF_WD + 9 * CEXP * 2;      // expansion bias [CEXP] f32, in the expanded patch's channel order
     static constexpr int OFF_BD = OFF_BE + CEXP * 4;          // depthwise bias [CEXP] f32
     static constexpr int OFF_BP = OFF_BD + CEXP * 4;          // projection bias [COUTP] f32
-    static constexpr int SMEM = OFF_BP + COUTP * 4;
+    static constexpr int OFF_BAR = OFF_BP + COUTP * 4;        // two mbarriers: weights (once), input patch (one phase per tile)
+    static constexpr int SMEM = OFF_BAR + 16 + 1024;          // + slack for the manual 1024-byte alignment of the base
+    static constexpr uint32_t W_BYTES = KS * WE_SL + ES * WP_SL, X_BYTES = KS * P * 32;
+    static_assert(OFF_WE % 256 == 0 && OFF_WP % 256 == 0 && IN_SL % 256 == 0 && WE_SL % 256 == 0 && WP_SL % 256 == 0, "TMA destinations");
+    static_assert(PW <= 256 && PH <= 256 && CEXP <= 256 && COUTP <= 256, "TMA box dimensions");
     static_assert(CIN % 8 == 0 && CEXP % 16 == 0 && COUT % 8 == 0, "channel granularity");
-    static_assert(OFF_MID % 16 == 0 && OFF_WP % 16 == 0 && OFF_WD % 16 == 0 && OFF_BE % 16 == 0 && OFF_BD % 16 == 0 && OFF_BP % 16 == 0, "alignment");
+    static_assert(OFF_DW % 16 == 0 && OFF_MID % 16 == 0 && OFF_WD % 16 == 0 && OFF_BE % 16 == 0 && OFF_BD % 16 == 0 && OFF_BP % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
     static_assert(2 * (SMEM + 1024) <= 227 * 1024, "two CTAs per SM");
     static_assert(NCH <= IM_THREADS, "depthwise mapping");
 };
@@ -74,7 +92,7 @@ struct ImCfg {
 struct ImParams {
     const __half* in; const __half* we; const float* be; const __half* wd; const float* bd;
     const __half* wp; const float* bp; const __half* res; __half* out;
-    int B, H, W, Ho, Wo, pad_t, pad_l, tiles_x;
+    int B, H, W, Ho, Wo, pad_t, pad_l, tiles_x, tiles_per_img, n_tiles;
 };
 
 // byte offset of (row, 16-byte half h) inside a slice
@@ -120,6 +138,11 @@ __device__ __forceinline__ void im_sts32(uint32_t a, uint32_t v) { asm volatile(
 __device__ __forceinline__ void im_sts64f(uint32_t a, float x, float y) {
     asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(x), "f"(y) : "memory");
 }
+__device__ __forceinline__ uint2 im_lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ float2 im_lds64f(uint32_t a) {
     float2 v;
     asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
@@ -140,59 +163,69 @@ __device__ __forceinline__ void im_cp16_zfill(uint32_t dst, const void* src, boo
 
 template <class Cfg>
 __global__ void __launch_bounds__(IM_THREADS, 2)
-irblock_mma_kernel(const __grid_constant__ ImParams p) {
-    extern __shared__ __align__(16) unsigned char im_smem[];
+irblock_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_we,
+                   const __grid_constant__ CUtensorMap map_wp, const __grid_constant__ ImParams p) {
+    extern __shared__ __align__(16) unsigned char im_smem_raw[];
+    unsigned char* im_smem = reinterpret_cast<unsigned char*>(((uintptr_t)im_smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sm = (uint32_t)__cvta_generic_to_shared(im_smem);
     const uint32_t sIn = sm + Cfg::OFF_IN, sWe = sm + Cfg::OFF_WE, sDw = sm + Cfg::OFF_DW, sMid = sm + Cfg::OFF_MID;
     const uint32_t sWp = sm + Cfg::OFF_WP, sWd = sm + Cfg::OFF_WD, sBe = sm + Cfg::OFF_BE, sBd = sm + Cfg::OFF_BD, sBp = sm + Cfg::OFF_BP;
-    constexpr int S = Cfg::S, PW = Cfg::PW, P = Cfg::P, CIN = Cfg::CIN, CEXP = Cfg::CEXP, COUT = Cfg::COUT;
+    const uint32_t bar_w = sm + Cfg::OFF_BAR, bar_x = bar_w + 8;
+    constexpr int S = Cfg::S, PW = Cfg::PW, P = Cfg::P, CEXP = Cfg::CEXP, COUT = Cfg::COUT;
     pdl_trigger();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x, b = blockIdx.y;
-    const int oy0 = ty * Cfg::TH, ox0 = tx * Cfg::TW;
-    const int iy0 = oy0 * S - p.pad_t, ix0 = ox0 * S - p.pad_l;          // image coordinates of patch position (0, 0)
 
-    // ---- 1a. weights and biases (never written by a predecessor of the plan: before the PDL wait) ----
-    for (int i = tid; i < CEXP * (Cfg::KIN / 8); i += IM_THREADS) {      // expansion weights [CEXP][CIN] -> slices of 16 k
-        const int n = i / (Cfg::KIN / 8), c = i - n * (Cfg::KIN / 8);
-        // Row order inside a 16-channel slice: MMA column (n-tile q, column j) computes channel 4 (j >> 1) + 2 q + (j & 1),
-        // so that a thread's four accumulator columns (2t, 2t+1 of both n-tiles) are the CONTIGUOUS channels 4t .. 4t+3
-        // (one 8-byte store per row; a warp's store instruction covers 8 whole 32-byte rows, conflict-free).
-        const int cl = n & 15, nrow = (n & ~15) + 8 * ((cl >> 1) & 1) + 2 * (cl >> 2) + (cl & 1);
-        const uint32_t dst = sWe + (uint32_t)((c >> 1) * Cfg::WE_SL) + im_row(nrow, c & 1);
-        if (c < CIN / 8) im_cp16(dst, p.we + (size_t)n * CIN + 8 * c);
-        else im_sts128(dst, make_uint4(0u, 0u, 0u, 0u));
-    }
-    for (int i = tid; i < Cfg::COUTP * Cfg::NCH; i += IM_THREADS) {      // projection weights [COUT][CEXP] -> slices of 16 k
-        const int n = i / Cfg::NCH, c = i - n * Cfg::NCH;
-        const uint32_t dst = sWp + (uint32_t)((c >> 1) * Cfg::WP_SL) + im_row(n, c & 1);
-        if (n < COUT) im_cp16(dst, p.wp + (size_t)n * CEXP + 8 * c);
-        else im_sts128(dst, make_uint4(0u, 0u, 0u, 0u));
+    // ---- 1. loads.  TMA (one thread): expansion weights [CEXP][CIN] and projection weights [COUT][CEXP] as 16-channel
+    //         slices (rows past COUT and channels past CIN are out of bounds = zero-filled), once per CTA; then -- after the
+    //         PDL wait -- the input patch of the first tile (tile + halo; positions outside the image zero-filled).  The
+    //         depthwise filter and the biases are loaded by the threads.
+    if (tid == 0) {
+        tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_we); tma_prefetch_desc(&map_wp);
+        mbar_init(bar_w, 1);
+        mbar_init(bar_x, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar_w, Cfg::W_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < Cfg::KS; ++ks) tma_load_2d(sWe + ks * Cfg::WE_SL, &map_we, bar_w, 16 * ks, 0);
+        for (int ks = 0; ks < Cfg::ES; ++ks) tma_load_2d(sWp + ks * Cfg::WP_SL, &map_wp, bar_w, 16 * ks, 0);
     }
     for (int i = tid; i < 9 * Cfg::NCH; i += IM_THREADS) im_cp16(sWd + 16u * i, p.wd + 8 * i);
     for (int i = tid; i < CEXP; i += IM_THREADS) {
-        reinterpret_cast<float*>(im_smem + Cfg::OFF_BE)[i] = p.be ? __ldg(p.be + i) : 0.f;
+        // expansion bias in the channel order of the expanded patch: position q of a slice holds channel
+        // 8 ((q >> 1) & 1) + 2 (q >> 2) + (q & 1) (see the expansion's epilogue)
+        const int q = i & 15, c = (i & ~15) + 8 * ((q >> 1) & 1) + 2 * (q >> 2) + (q & 1);
+        reinterpret_cast<float*>(im_smem + Cfg::OFF_BE)[i] = p.be ? __ldg(p.be + c) : 0.f;
         reinterpret_cast<float*>(im_smem + Cfg::OFF_BD)[i] = p.bd ? __ldg(p.bd + i) : 0.f;
     }
     for (int i = tid; i < Cfg::COUTP; i += IM_THREADS)
         reinterpret_cast<float*>(im_smem + Cfg::OFF_BP)[i] = (p.bp && i < COUT) ? __ldg(p.bp + i) : 0.f;
     pdl_wait();
-
-    // ---- 1b. input patch: positions x KIN channels, zero outside the image and in the K padding ----
-    {
-        const __half* img = p.in + (size_t)b * p.H * p.W * CIN;
-        for (int i = tid; i < Cfg::PPOS * (Cfg::KIN / 8); i += IM_THREADS) {
-            const int pos = i / (Cfg::KIN / 8), c = i - pos * (Cfg::KIN / 8);
-            const int py = pos / PW, px = pos - py * PW;
-            const int iy = iy0 + py, ix = ix0 + px;
-            const uint32_t dst = sIn + (uint32_t)((c >> 1) * Cfg::IN_SL) + im_row(pos, c & 1);
-            const bool ok = pos < P && c < CIN / 8 && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
-            im_cp16_zfill(dst, ok ? img + ((size_t)iy * p.W + ix) * CIN + 8 * c : img, ok);
-        }
-    }
+    // tile -> (image, tile row, tile column)
+    auto tile_origin = [&](int tile, int& b, int& oy0, int& ox0) {
+        b = tile / p.tiles_per_img;
+        const int r = tile - b * p.tiles_per_img, ty = r / p.tiles_x;
+        oy0 = ty * Cfg::TH; ox0 = (r - ty * p.tiles_x) * Cfg::TW;
+    };
+    auto request_patch = [&](int tile) {                              // thread 0 only
+        int b, oy0, ox0;
+        tile_origin(tile, b, oy0, ox0);
+        mbar_expect_tx(bar_x, Cfg::X_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < Cfg::KS; ++ks)
+            tma_load_4d(sIn + ks * Cfg::IN_SL, &map_x, bar_x, 16 * ks, ox0 * S - p.pad_l, oy0 * S - p.pad_t, b);
+    };
+    if (tid == 0 && (int)blockIdx.x < p.n_tiles) request_patch((int)blockIdx.x);
     asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();
+    __syncthreads();                        // barriers initialised, filter + biases visible
+    mbar_wait(bar_w, 0);
+
+    uint32_t it = 0;
+    for (int tile = (int)blockIdx.x; tile < p.n_tiles; tile += (int)gridDim.x, ++it) {
+    int b, oy0, ox0;
+    tile_origin(tile, b, oy0, ox0);
+    const int iy0 = oy0 * S - p.pad_t, ix0 = ox0 * S - p.pad_l;          // image coordinates of patch position (0, 0)
+    mbar_wait(bar_x, it & 1u);              // this tile's patch has landed
 
     // ---- 2. expansion: units of (16-channel slice, m16 tile of positions) round-robin over the warps ----
     {
@@ -202,7 +235,7 @@ irblock_mma_kernel(const __grid_constant__ ImParams p) {
         // unit = (m16 tile of positions, group of JG slices): the A fragments are loaded once per unit, per slice one
         // ldmatrix per k-step for the weights, one 16-byte bias load, 2 KS MMAs and two 8-byte stores (shared-memory
         // wavefronts, not issue slots, bound this kernel)
-        constexpr int G = Cfg::MT % IM_WARPS == 0 ? 1 : (Cfg::ES % 3 == 0 ? 3 : (Cfg::ES % 2 == 0 ? 2 : 1));
+        constexpr int G = im_best_groups(Cfg::MT, Cfg::ES);
         constexpr int JG = Cfg::ES / G;
         for (int u = warp; u < Cfg::MT * G; u += IM_WARPS) {
             const int mt = u / G, gi = u - mt * G;
@@ -227,7 +260,8 @@ irblock_mma_kernel(const __grid_constant__ ImParams p) {
                     im_mma(acc[0], a[ks], bq[ks][0], bq[ks][1]);
                     im_mma(acc[1], a[ks], bq[ks][2], bq[ks][3]);
                 }
-                // the expanded patch is LINEAR (row = 32 bytes = 16 channels in their true order)
+                // the expanded patch is LINEAR (row = 32 bytes); within a slice, position 4t + 2q + e holds channel 8q + 2t + e
+                // (accumulator columns 2t, 2t+1 of n-tiles q = 0, 1): one 8-byte store per row, 8 whole rows per instruction
                 const uint32_t dst = dst0 + (uint32_t)(jp * Cfg::MID_SL);
                 im_sts64(dst, im_min2(im_cvt_relu(acc[0][0], acc[0][1]), six), im_min2(im_cvt_relu(acc[1][0], acc[1][1]), six));
                 im_sts64(dst + 256, im_min2(im_cvt_relu(acc[0][2], acc[0][3]), six), im_min2(im_cvt_relu(acc[1][2], acc[1][3]), six));
@@ -235,6 +269,11 @@ irblock_mma_kernel(const __grid_constant__ ImParams p) {
         }
     }
     __syncthreads();
+    if (tid == 0 && tile + (int)gridDim.x < p.n_tiles) {
+        // every warp is done reading the patch buffer (generic proxy) -> the next tile's patch may overwrite it (async proxy)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        request_patch(tile + (int)gridDim.x);
+    }
     // edge tiles: positions outside the image are the depthwise layer's zero padding, not ReLU6(bias)
     if (iy0 < 0 || ix0 < 0 || iy0 + Cfg::PH > p.H || ix0 + PW > p.W) {
         for (int i = tid; i < P * Cfg::ES; i += IM_THREADS) {
@@ -252,18 +291,25 @@ irblock_mma_kernel(const __grid_constant__ ImParams p) {
     // ---- 3. depthwise 3x3: thread = (8-channel chunk, pixel lane); packed half2 FMAs, fp16 accumulation from the fp16 bias ----
     if (tid < Cfg::NCH * Cfg::NPL) {
         const int c8 = tid % Cfg::NCH, pl = tid / Cfg::NCH;
+        // The expanded patch stores a slice's 16 channels in the order of the expansion's accumulator fragments: the four
+        // half2 pairs of 16-byte chunk h are channels 4h (+0,1), 8 + 4h (+0,1), 4h + 2 (+0,1), 8 + 4h + 2 (+0,1) of the slice.
+        // Filter taps and bias are gathered in that order once per tile; the outputs go back in natural order.
+        const int sl = c8 >> 1, h = c8 & 1;
         uint4 w[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) w[k] = im_lds128(sWd + (uint32_t)(k * CEXP + 8 * c8) * 2u);
+        for (int k = 0; k < 9; ++k) {
+            const uint2 lo = im_lds64(sWd + (uint32_t)(k * CEXP + 16 * sl + 4 * h) * 2u);
+            const uint2 hi = im_lds64(sWd + (uint32_t)(k * CEXP + 16 * sl + 8 + 4 * h) * 2u);
+            w[k] = make_uint4(lo.x, hi.x, lo.y, hi.y);
+        }
         __half2 bias4[4];
         {
-            const float4 b0 = im_lds128f(sBd + (uint32_t)(8 * c8) * 4u), b1 = im_lds128f(sBd + (uint32_t)(8 * c8 + 4) * 4u);
-            bias4[0] = __floats2half2_rn(b0.x, b0.y); bias4[1] = __floats2half2_rn(b0.z, b0.w);
-            bias4[2] = __floats2half2_rn(b1.x, b1.y); bias4[3] = __floats2half2_rn(b1.z, b1.w);
+            const float4 b0 = im_lds128f(sBd + (uint32_t)(16 * sl + 4 * h) * 4u), b1 = im_lds128f(sBd + (uint32_t)(16 * sl + 8 + 4 * h) * 4u);
+            bias4[0] = __floats2half2_rn(b0.x, b0.y); bias4[1] = __floats2half2_rn(b1.x, b1.y);
+            bias4[2] = __floats2half2_rn(b0.z, b0.w); bias4[3] = __floats2half2_rn(b1.z, b1.w);
         }
         const __half2 zero2 = __float2half2_rn(0.f), six2 = __float2half2_rn(6.f);
-        const int h = c8 & 1;
-        const uint32_t src = sMid + (uint32_t)((c8 >> 1) * Cfg::MID_SL + h * 16), dstb = sDw + (uint32_t)((c8 >> 1) * Cfg::DW_SL);
+        const uint32_t src = sMid + (uint32_t)(sl * Cfg::MID_SL + h * 16), dstb = sDw + (uint32_t)(sl * Cfg::DW_SL + 8 * h);
         if constexpr (S == 1) {
             // stride 1: runs of 3 horizontally adjacent pixels share their input columns (15 loads per 3 outputs instead
             // of 27); columns past the tile's halo belong to discarded outputs and only read allocated shared memory
@@ -300,7 +346,8 @@ irblock_mma_kernel(const __grid_constant__ ImParams p) {
                         __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
                         for (int c2 = 0; c2 < 4; ++c2) oh[c2] = __hmin2(__hmax2(acc[i][c2], zero2), six2);
-                        im_sts128(dstb + im_row(y * Cfg::TW + x0 + i, h), o);
+                        im_sts64(dstb + im_row(y * Cfg::TW + x0 + i, 0), o.x, o.z);
+                        im_sts64(dstb + im_row(y * Cfg::TW + x0 + i, 1), o.y, o.w);
                     }
                 xr += Cfg::NPL % RPR; y += Cfg::NPL / RPR;
                 if (xr >= RPR) { xr -= RPR; ++y; }
@@ -345,7 +392,8 @@ irblock_mma_kernel(const __grid_constant__ ImParams p) {
                     __half2* oh = reinterpret_cast<__half2*>(&o);
     #pragma unroll
                     for (int c2 = 0; c2 < 4; ++c2) oh[c2] = __hmin2(__hmax2(acc[q][c2], zero2), six2);
-                    im_sts128(dstb + im_row(px + q * Cfg::NPL, h), o);
+                    im_sts64(dstb + im_row(px + q * Cfg::NPL, 0), o.x, o.z);
+                    im_sts64(dstb + im_row(px + q * Cfg::NPL, 1), o.y, o.w);
                 }
             }
         }
@@ -415,6 +463,8 @@ irblock_mma_kernel(const __grid_constant__ ImParams p) {
             }
         }
     }
+    __syncthreads();                        // the staging tile (= the expanded patch) is free for the next tile
+    }   // tile loop
 }
 
 template <class Cfg>
@@ -426,6 +476,30 @@ static int irblock_mma_launch_t(const ssd_irblock_desc* d, cudaStream_t st) {
     p.res = static_cast<const __half*>(d->residual); p.out = static_cast<__half*>(d->out);
     p.B = d->B; p.H = d->H; p.W = d->W; p.Ho = d->Ho; p.Wo = d->Wo; p.pad_t = d->pad_top; p.pad_l = d->pad_left;
     p.tiles_x = ceil_div(d->Wo, Cfg::TW);
+    p.tiles_per_img = p.tiles_x * ceil_div(d->Ho, Cfg::TH);
+    p.n_tiles = p.tiles_per_img * d->B;
+    CUtensorMap map_x, map_we, map_wp;
+    {
+        uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+        uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
+        uint32_t box[4] = {16, (uint32_t)Cfg::PW, (uint32_t)Cfg::PH, 1};
+        int rc = cached_map(&map_x, d->in, 4, dims, str, box, nullptr, 32);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)d->Cin, (uint64_t)d->Cexp};
+        uint64_t str[1] = {(uint64_t)d->Cin * 2};
+        uint32_t box[2] = {16, (uint32_t)Cfg::CEXP};
+        int rc = cached_map(&map_we, d->exp_weight, 2, dims, str, box, nullptr, 32);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)d->Cexp, (uint64_t)d->Cout};
+        uint64_t str[1] = {(uint64_t)d->Cexp * 2};
+        uint32_t box[2] = {16, (uint32_t)Cfg::COUTP};
+        int rc = cached_map(&map_wp, d->proj_weight, 2, dims, str, box, nullptr, 32);
+        if (rc) return rc;
+    }
     static thread_local int attr_dev = -1;
     int cur = 0;
     cudaGetDevice(&cur);
@@ -434,8 +508,8 @@ static int irblock_mma_launch_t(const ssd_irblock_desc* d, cudaStream_t st) {
         if (e != cudaSuccess) return cuda_fail(e, "ssd_irblock: cudaFuncSetAttribute (mma.sync variant)");
         attr_dev = cur;
     }
-    const dim3 grid(p.tiles_x * ceil_div(d->Ho, Cfg::TH), d->B);
-    cudaError_t le = launch_pdl(irblock_mma_kernel<Cfg>, grid, dim3(IM_THREADS), (size_t)Cfg::SMEM, st, p);
+    const dim3 grid(min(p.n_tiles, 2 * (sm_count() > 0 ? sm_count() : 148)));
+    cudaError_t le = launch_pdl(irblock_mma_kernel<Cfg>, grid, dim3(IM_THREADS), (size_t)Cfg::SMEM, st, map_x, map_we, map_wp, p);
     if (le != cudaSuccess) return cuda_fail(le, "irblock_mma_kernel");
     return SSD_OK;
 }
@@ -444,8 +518,8 @@ static int irblock_mma_launch_t(const ssd_irblock_desc* d, cudaStream_t st) {
 typedef ImCfg<16, 96, 24, 2, 15, 5> ImBlock1;       // 150 -> 75: 5 x 15 tiles per image
 typedef ImCfg<24, 144, 24, 1, 15, 5> ImBlock2;      // 75 x 75
 typedef ImCfg<24, 144, 32, 2, 10, 4> ImBlock3;      // 75 -> 38
-typedef ImCfg<32, 192, 32, 1, 19, 4> ImBlock45;     // 38 x 38
-typedef ImCfg<32, 192, 64, 2, 19, 1> ImBlock6;      // 38 -> 19
+typedef ImCfg<32, 192, 32, 1, 13, 4> ImBlock45;     // 38 x 38
+typedef ImCfg<32, 192, 64, 2, 10, 2> ImBlock6;      // 38 -> 19
 
 static int g_irblock_mode = -1;      // -1 automatic, 0 tcgen05 kernel only, 1 mma.sync variant whenever a configuration matches
 

@@ -932,7 +932,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
 }
 
 static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, const uint32_t* elem_strides = nullptr) {
+                    const uint32_t* box, const uint32_t* elem_strides = nullptr, int swizzle_bytes = 128) {
     auto enc = tensor_map_encoder();
     if (!enc) return fail(SSD_ERR_UNSUPPORTED, "conv_tcgen05: cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t gdim[4], gstr[3];
@@ -940,7 +940,9 @@ static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t
     for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SSD_ERR_UNSUPPORTED, "conv_tcgen05: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return SSD_OK;
@@ -949,7 +951,7 @@ static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t
 // Encoded tensor maps are cached per (pointer, geometry): cuTensorMapEncodeTiled costs a few
 // microseconds of host time, which would otherwise dominate eager launches of small layers.
 struct MapKey {
-    const void* base; uint64_t dims[4]; uint64_t strides[3]; uint32_t box[4]; uint32_t es[4]; int rank;
+    const void* base; uint64_t dims[4]; uint64_t strides[3]; uint32_t box[4]; uint32_t es[4]; int rank; int swizzle;
     bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
 };
 struct MapKeyHash {
@@ -964,16 +966,16 @@ static std::mutex g_map_mutex;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
 
 int cached_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box, const uint32_t* elem_strides) {
+               const uint32_t* box, const uint32_t* elem_strides, int swizzle_bytes) {
     MapKey k;
     memset(&k, 0, sizeof(k));
-    k.base = base; k.rank = rank;
+    k.base = base; k.rank = rank; k.swizzle = swizzle_bytes;
     for (int i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; k.es[i] = elem_strides ? elem_strides[i] : 1; }
     for (int i = 0; i + 1 < rank; ++i) k.strides[i] = strides_bytes[i];
     std::lock_guard<std::mutex> lock(g_map_mutex);
     auto it = g_map_cache.find(k);
     if (it != g_map_cache.end()) { *map = it->second; return SSD_OK; }
-    int rc = make_map(map, base, rank, dims, strides_bytes, box, elem_strides);
+    int rc = make_map(map, base, rank, dims, strides_bytes, box, elem_strides, swizzle_bytes);
     if (rc == SSD_OK) {
         if (g_map_cache.size() > 4096) g_map_cache.clear();
         g_map_cache.emplace(k, *map);

@@ -202,7 +202,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 
 // Encoded tensor maps, cached per (pointer, geometry) -- defined in conv_tcgen05.cu.
+// swizzle_bytes: 128 (the tcgen05 operand tiles), 64 or 32 (the 32-byte-row slices of conv_irblock_mma.cu).
 int cached_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box, const uint32_t* elem_strides = nullptr);
+               const uint32_t* box, const uint32_t* elem_strides = nullptr, int swizzle_bytes = 128);
 
 }  // namespace ssd
