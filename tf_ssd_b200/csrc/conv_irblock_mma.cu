@@ -35,17 +35,6 @@ constexpr int IM_WARPS = IM_THREADS / 32;
 
 __host__ __device__ constexpr int im_up16(int v) { return (v + 15) / 16 * 16; }
 __host__ __device__ constexpr int im_max(int a, int b) { return a > b ? a : b; }
-// expansion work split: units = m-tiles x G slice groups over 8 warps; G (a divisor of the slice count) minimising
-// rounds x slices per unit
-__host__ __device__ constexpr int im_best_groups(int mt, int es) {
-    int best = 1, cost = ((mt + 7) / 8) * es;
-    for (int gq = 2; gq <= es; ++gq)
-        if (es % gq == 0) {
-            const int c = ((mt * gq + 7) / 8) * (es / gq);
-            if (c < cost) { cost = c; best = gq; }
-        }
-    return best;
-}
 
 template <int CIN_, int CEXP_, int COUT_, int STRIDE_, int TW_, int TH_>
 struct ImCfg {
@@ -190,13 +179,18 @@ irblock_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         for (int ks = 0; ks < Cfg::KS; ++ks) tma_load_2d(sWe + ks * Cfg::WE_SL, &map_we, bar_w, 16 * ks, 0);
         for (int ks = 0; ks < Cfg::ES; ++ks) tma_load_2d(sWp + ks * Cfg::WP_SL, &map_wp, bar_w, 16 * ks, 0);
     }
-    for (int i = tid; i < 9 * Cfg::NCH; i += IM_THREADS) im_cp16(sWd + 16u * i, p.wd + 8 * i);
+    // Expansion bias, depthwise filter and depthwise bias in the channel order of the expanded patch: position q of a
+    // 16-channel slice holds channel 8 ((q >> 1) & 1) + 2 (q >> 2) + (q & 1) (see the expansion's epilogue); pairs (q even,
+    // q + 1) are pairs of adjacent channels, so the fp16 filter moves as 4-byte words.
+    for (int i = tid; i < 9 * CEXP / 2; i += IM_THREADS) {
+        const int k = i / (CEXP / 2), w2 = i - k * (CEXP / 2), q = (2 * w2) & 15;
+        const int c = ((2 * w2) & ~15) + 8 * ((q >> 1) & 1) + 2 * (q >> 2);
+        reinterpret_cast<uint32_t*>(im_smem + Cfg::OFF_WD)[i] = __ldg(reinterpret_cast<const uint32_t*>(p.wd + k * CEXP + c));
+    }
     for (int i = tid; i < CEXP; i += IM_THREADS) {
-        // expansion bias in the channel order of the expanded patch: position q of a slice holds channel
-        // 8 ((q >> 1) & 1) + 2 (q >> 2) + (q & 1) (see the expansion's epilogue)
         const int q = i & 15, c = (i & ~15) + 8 * ((q >> 1) & 1) + 2 * (q >> 2) + (q & 1);
         reinterpret_cast<float*>(im_smem + Cfg::OFF_BE)[i] = p.be ? __ldg(p.be + c) : 0.f;
-        reinterpret_cast<float*>(im_smem + Cfg::OFF_BD)[i] = p.bd ? __ldg(p.bd + i) : 0.f;
+        reinterpret_cast<float*>(im_smem + Cfg::OFF_BD)[i] = p.bd ? __ldg(p.bd + c) : 0.f;
     }
     for (int i = tid; i < Cfg::COUTP; i += IM_THREADS)
         reinterpret_cast<float*>(im_smem + Cfg::OFF_BP)[i] = (p.bp && i < COUT) ? __ldg(p.bp + i) : 0.f;
@@ -232,40 +226,41 @@ irblock_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const uint32_t six = 0x46004600u;                              // half2(6, 6)
         const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lhalf = lane >> 4;         // A operand: ldmatrix lane -> (row, half)
         const int brow = (lane & 7) + (lane >> 4) * 8, bhalf = (lane >> 3) & 1;         // B operand
-        // unit = (m16 tile of positions, group of JG slices): the A fragments are loaded once per unit, per slice one
-        // ldmatrix per k-step for the weights, one 16-byte bias load, 2 KS MMAs and two 8-byte stores (shared-memory
-        // wavefronts, not issue slots, bound this kernel)
-        constexpr int G = im_best_groups(Cfg::MT, Cfg::ES);
-        constexpr int JG = Cfg::ES / G;
-        for (int u = warp; u < Cfg::MT * G; u += IM_WARPS) {
-            const int mt = u / G, gi = u - mt * G;
+        // Every warp owns a contiguous range of the ES x MT (slice, m16 tile) pairs, slice-major: the weight fragments and
+        // the bias of a slice stay in registers while the warp walks over m-tiles (shared-memory wavefronts, not issue
+        // slots, bound this kernel: per pair one ldmatrix per k-step for the positions, 2 KS MMAs, two 8-byte stores).
+        constexpr int NPAIR = Cfg::ES * Cfg::MT;
+        const int q0 = warp * NPAIR / IM_WARPS, q1 = (warp + 1) * NPAIR / IM_WARPS;
+        int jp = q0 / Cfg::MT, mt = q0 - jp * Cfg::MT;
+        uint32_t bq[Cfg::KS][4];
+        float4 bias;
+        bool fresh = true;
+        for (int q = q0; q < q1; ++q) {
+            if (fresh) {
+#pragma unroll
+                for (int ks = 0; ks < Cfg::KS; ++ks)
+                    im_ldsm4(bq[ks], sWe + (uint32_t)(ks * Cfg::WE_SL) + im_row(jp * 16 + brow, bhalf));
+                bias = im_lds128f(sBe + (uint32_t)(jp * 16 + 4 * t) * 4u);           // channels 4t .. 4t+3 of the slice's order
+                fresh = false;
+            }
             uint32_t a[Cfg::KS][4];
 #pragma unroll
             for (int ks = 0; ks < Cfg::KS; ++ks)
                 im_ldsm4(a[ks], sIn + (uint32_t)(ks * Cfg::IN_SL) + im_row(mt * 16 + lrow, lhalf));
-            const uint32_t dst0 = sMid + (uint32_t)((mt * 16 + g) * 32 + 8 * t);
-#pragma unroll 2
-            for (int jj = 0; jj < JG; ++jj) {
-                const int jp = gi * JG + jj;
-                uint32_t bq[Cfg::KS][4];
+            float acc[2][4];
+            im_mma_bias(acc[0], a[0], bq[0][0], bq[0][1], bias.x, bias.y);
+            im_mma_bias(acc[1], a[0], bq[0][2], bq[0][3], bias.z, bias.w);
 #pragma unroll
-                for (int ks = 0; ks < Cfg::KS; ++ks)
-                    im_ldsm4(bq[ks], sWe + (uint32_t)(ks * Cfg::WE_SL) + im_row(jp * 16 + brow, bhalf));
-                const float4 bias = im_lds128f(sBe + (uint32_t)(jp * 16 + 4 * t) * 4u);       // channels 4t .. 4t+3 of the slice
-                float acc[2][4];
-                im_mma_bias(acc[0], a[0], bq[0][0], bq[0][1], bias.x, bias.y);
-                im_mma_bias(acc[1], a[0], bq[0][2], bq[0][3], bias.z, bias.w);
-#pragma unroll
-                for (int ks = 1; ks < Cfg::KS; ++ks) {
-                    im_mma(acc[0], a[ks], bq[ks][0], bq[ks][1]);
-                    im_mma(acc[1], a[ks], bq[ks][2], bq[ks][3]);
-                }
-                // the expanded patch is LINEAR (row = 32 bytes); within a slice, position 4t + 2q + e holds channel 8q + 2t + e
-                // (accumulator columns 2t, 2t+1 of n-tiles q = 0, 1): one 8-byte store per row, 8 whole rows per instruction
-                const uint32_t dst = dst0 + (uint32_t)(jp * Cfg::MID_SL);
-                im_sts64(dst, im_min2(im_cvt_relu(acc[0][0], acc[0][1]), six), im_min2(im_cvt_relu(acc[1][0], acc[1][1]), six));
-                im_sts64(dst + 256, im_min2(im_cvt_relu(acc[0][2], acc[0][3]), six), im_min2(im_cvt_relu(acc[1][2], acc[1][3]), six));
+            for (int ks = 1; ks < Cfg::KS; ++ks) {
+                im_mma(acc[0], a[ks], bq[ks][0], bq[ks][1]);
+                im_mma(acc[1], a[ks], bq[ks][2], bq[ks][3]);
             }
+            // the expanded patch is LINEAR (row = 32 bytes); within a slice, position 4t + 2n + e holds channel 8n + 2t + e
+            // (accumulator columns 2t, 2t+1 of n-tiles n = 0, 1): one 8-byte store per row, 8 whole rows per instruction
+            const uint32_t dst = sMid + (uint32_t)(jp * Cfg::MID_SL + (mt * 16 + g) * 32 + 8 * t);
+            im_sts64(dst, im_min2(im_cvt_relu(acc[0][0], acc[0][1]), six), im_min2(im_cvt_relu(acc[1][0], acc[1][1]), six));
+            im_sts64(dst + 256, im_min2(im_cvt_relu(acc[0][2], acc[0][3]), six), im_min2(im_cvt_relu(acc[1][2], acc[1][3]), six));
+            if (++mt == Cfg::MT) { mt = 0; ++jp; fresh = true; }
         }
     }
     __syncthreads();
@@ -293,20 +288,16 @@ irblock_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const int c8 = tid % Cfg::NCH, pl = tid / Cfg::NCH;
         // The expanded patch stores a slice's 16 channels in the order of the expansion's accumulator fragments: the four
         // half2 pairs of 16-byte chunk h are channels 4h (+0,1), 8 + 4h (+0,1), 4h + 2 (+0,1), 8 + 4h + 2 (+0,1) of the slice.
-        // Filter taps and bias are gathered in that order once per tile; the outputs go back in natural order.
+        // The filter taps and the bias were stored in that order by the prologue; the outputs go back in natural order.
         const int sl = c8 >> 1, h = c8 & 1;
         uint4 w[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const uint2 lo = im_lds64(sWd + (uint32_t)(k * CEXP + 16 * sl + 4 * h) * 2u);
-            const uint2 hi = im_lds64(sWd + (uint32_t)(k * CEXP + 16 * sl + 8 + 4 * h) * 2u);
-            w[k] = make_uint4(lo.x, hi.x, lo.y, hi.y);
-        }
+        for (int k = 0; k < 9; ++k) w[k] = im_lds128(sWd + (uint32_t)(k * CEXP + 8 * c8) * 2u);
         __half2 bias4[4];
         {
-            const float4 b0 = im_lds128f(sBd + (uint32_t)(16 * sl + 4 * h) * 4u), b1 = im_lds128f(sBd + (uint32_t)(16 * sl + 8 + 4 * h) * 4u);
-            bias4[0] = __floats2half2_rn(b0.x, b0.y); bias4[1] = __floats2half2_rn(b1.x, b1.y);
-            bias4[2] = __floats2half2_rn(b0.z, b0.w); bias4[3] = __floats2half2_rn(b1.z, b1.w);
+            const float4 b0 = im_lds128f(sBd + (uint32_t)(8 * c8) * 4u), b1 = im_lds128f(sBd + (uint32_t)(8 * c8 + 4) * 4u);
+            bias4[0] = __floats2half2_rn(b0.x, b0.y); bias4[1] = __floats2half2_rn(b0.z, b0.w);
+            bias4[2] = __floats2half2_rn(b1.x, b1.y); bias4[3] = __floats2half2_rn(b1.z, b1.w);
         }
         const __half2 zero2 = __float2half2_rn(0.f), six2 = __float2half2_rn(6.f);
         const uint32_t src = sMid + (uint32_t)(sl * Cfg::MID_SL + h * 16), dstb = sDw + (uint32_t)(sl * Cfg::DW_SL + 8 * h);
