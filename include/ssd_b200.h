@@ -265,8 +265,10 @@ int ssd_irblock(const ssd_irblock_desc* h_desc, ssd_stream_t stream);
 int ssd_irblock_supported(const ssd_irblock_desc* h_desc);
 /* ssd_irblock has two implementations: the tcgen05 / TMEM pipeline (any supported shape) and an mma.sync kernel with one
  * CTA per small output tile for MobileNetV2's large-map blocks 1-6 ((Cin, Cexp, Cout, stride) = (16,96,24,2), (24,144,24,1),
- * (24,144,32,2), (32,192,32,1), (32,192,64,2) with ReLU6 / ReLU6 / linear activations).  Test hook: -1 automatic (the
- * mma.sync kernel where it has an instantiation), 0 tcgen05 only. */
+ * (24,144,32,2), (32,192,32,1), (32,192,64,2) with ReLU6 / ReLU6 / linear activations), plus a channel-grouped mma.sync
+ * kernel for the small-map blocks 7-12, 14, 15 ((64,384,64,1), (64,384,96,1), (96,576,96,1), (160,960,160,1)).  Test hook:
+ * -1 automatic (mma.sync for blocks 1-6, tcgen05 otherwise), 0 tcgen05 only, 1 every mma.sync variant that has an
+ * instantiation, 2 the large-map variant only. */
 int ssd_debug_irblock_mode(int mode);
 /* Debug aid, not a reference interface: d_buf = device buffer of 5 x 512 uint64 that CTA 0 of later ssd_irblock
  * launches fills with per-role (globaltimer << 8 | tag) stamps (tools/trace_irblock.py); NULL switches it off. */

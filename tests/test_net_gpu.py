@@ -295,15 +295,18 @@ IRBLOCK_CASES = [
 ]
 
 
-@pytest.mark.parametrize("mode", [-1, 0])
+@pytest.mark.parametrize("mode", [1, 0])
 @pytest.mark.parametrize("case", IRBLOCK_CASES + [
     (1, 33, 41, 24, 144, 24, 1, True),        # mma.sync variant: partial tiles in both directions, odd sizes
     (2, 31, 26, 16, 96, 24, 2, False), (1, 40, 17, 32, 192, 64, 2, False), (2, 21, 23, 32, 192, 32, 1, True),
     (1, 20, 34, 24, 144, 32, 2, False),
+    (1, 23, 17, 64, 384, 96, 1, False),       # grouped mma.sync variant (small maps): partial tiles, block 10's shape
+    (2, 7, 12, 160, 960, 160, 1, True), (1, 19, 19, 96, 576, 96, 1, False),
 ])
 def test_irblock_fused_against_torch(case, mode):
     """ssd_irblock (whole inverted-residual block in one launch) against torch-CPU with the same fp16 roundings -- both
-    implementations: the tcgen05 pipeline (mode 0) and, for the large-map block shapes, the mma.sync kernel (mode -1)."""
+    implementations: the tcgen05 pipeline (mode 0) and, for the block shapes that have an instantiation, the mma.sync kernels
+    (mode 1: one CTA per small tile for the large maps, channel-grouped for the small maps)."""
     from tf_ssd_b200 import _ffi
     from tf_ssd_b200._ffi_conv import IrBlockDesc
     import ctypes as C

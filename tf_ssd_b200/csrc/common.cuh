@@ -53,8 +53,8 @@ __device__ __forceinline__ void trace_stamp(unsigned long long* trace, int role,
 // launched through launch_pdl() MUST call pdl_wait() before it touches global memory
 // written or read by its predecessors; pdl_trigger() (at kernel entry) lets the
 // successor be scheduled as soon as all CTAs of this grid have started.
-// Opt-in with SSD_B200_PDL=1 (default: plain stream order -- measured gain 1.3 % on the MobileNetV2
-// step, and Nsight Compute hangs when it tries to serialise a programmatic chain).
+// On by default (SSD_B200_PDL=0 switches it off; off automatically under Nsight Compute / compute-sanitizer): see
+// pdl_enabled() in common.cu.
 bool pdl_enabled();
 
 template <typename... KArgs, typename... Args>

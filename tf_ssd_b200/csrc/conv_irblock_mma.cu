@@ -28,6 +28,8 @@
 
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace ssd {
 
 constexpr int IM_THREADS = 256;
@@ -512,17 +514,373 @@ typedef ImCfg<24, 144, 32, 2, 10, 4> ImBlock3;      // 75 -> 38
 typedef ImCfg<32, 192, 32, 1, 13, 4> ImBlock45;     // 38 x 38
 typedef ImCfg<32, 192, 64, 2, 10, 2> ImBlock6;      // 38 -> 19
 
-static int g_irblock_mode = -1;      // -1 automatic, 0 tcgen05 kernel only, 1 mma.sync variant whenever a configuration matches
+// ------------------------------------------------------------------------------------------------------------------
+// The SMALL-MAP blocks (19x19 blocks 7-12, 10x10 blocks 14-15; stride 1, Cexp = 384 ... 960): the expanded tensor of a
+// tile no longer fits shared memory at once and the weights are 100-630 KB, so the expanded channels are processed in
+// GROUPS of 96 (6 slices): per group  expansion -> depthwise -> projection partial sums (accumulators stay in registers
+// across groups), with the group's weights streamed from L2 by TMA into a double buffer two groups ahead.  One CTA of 16
+// warps per SM, one tile per CTA (4 tiles per image = 128 CTAs at batch 32).
+template <int CIN_, int CEXP_, int COUT_, int TW_, int TH_>
+struct ImGCfg {
+    static constexpr int CIN = CIN_, CEXP = CEXP_, COUT = COUT_, TW = TW_, TH = TH_;
+    static constexpr int THREADS = 512, WARPS = THREADS / 32;
+    static constexpr int GS = 6, GCH = GS * 16, NG = CEXP / GCH;       // slices / channels per group, groups
+    static constexpr int KS = CIN / 16;
+    static constexpr int PW = TW + 2, PH = TH + 2, P = PW * PH, PPOS = im_up16(P);
+    static constexpr int NPX = TW * TH, MPX = im_up16(NPX);
+    static constexpr int COUTP = im_up16(COUT);
+    static constexpr int MT = PPOS / 16, MTP = MPX / 16, NP = COUTP / 16;
+    static constexpr int NUNIT = MTP * NP, UPW = (NUNIT + WARPS - 1) / WARPS;      // projection units (m-tile, n-tile pair) per warp
+    static constexpr int NCH = GS * 2, NPL = THREADS / NCH;
+    static constexpr int RPR = (TW + 2) / 3, NRUN = TH * RPR;
+    static constexpr int IN_SL = PPOS * 32, WE_SL = GCH * 32, WP_SL = COUTP * 32;
+    static constexpr int MID_SL = (PPOS + 1) * 32, DW_SL = (MPX + 1) * 32;
+    static constexpr int WB_BYTES = KS * WE_SL + GS * WP_SL;           // one group's weights: [expansion | projection]
+    static constexpr int OFF_IN = 0;
+    static constexpr int OFF_WB = OFF_IN + KS * IN_SL;                 // [2] weight buffers
+    static constexpr int OFF_MID = OFF_WB + 2 * WB_BYTES;
+    static constexpr int OFF_DW = OFF_MID + (GS * MID_SL + 255) / 256 * 256;
+    static constexpr int STAGE_BYTES = im_max(OFF_DW - OFF_MID + GS * DW_SL, NPX * COUT * 4);     // fp32 staging aliases [mid | dw]
+    static constexpr int OFF_WD = OFF_MID + (STAGE_BYTES + 255) / 256 * 256;                      // [9][CEXP] fp16, patch channel order
+    static constexpr int OFF_BE = OFF_WD + 9 * CEXP * 2;
+    static constexpr int OFF_BD = OFF_BE + CEXP * 4;
+    static constexpr int OFF_BP = OFF_BD + CEXP * 4;
+    static constexpr int OFF_BAR = OFF_BP + COUTP * 4;                 // mbarriers: patch, weight buffer 0, weight buffer 1
+    static constexpr int SMEM = OFF_BAR + 32 + 1024;
+    static constexpr uint32_t X_BYTES = KS * P * 32;
+    static_assert(CIN % 16 == 0 && CEXP % GCH == 0 && COUT % 8 == 0, "channel granularity");
+    static_assert(OFF_WB % 256 == 0 && WB_BYTES % 256 == 0 && IN_SL % 256 == 0 && WE_SL % 256 == 0 && WP_SL % 256 == 0, "TMA destinations");
+    static_assert(OFF_DW % 16 == 0 && OFF_WD % 16 == 0 && OFF_BE % 16 == 0 && OFF_BD % 16 == 0 && OFF_BP % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
+    static_assert(SMEM <= 227 * 1024, "shared memory");
+    static_assert(NRUN <= NPL, "one depthwise pass");
+    static_assert(PW <= 256 && PH <= 256 && GCH <= 256 && COUTP <= 256, "TMA box dimensions");
+};
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+irblock_mma_grouped_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_we,
+                           const __grid_constant__ CUtensorMap map_wp, const __grid_constant__ ImParams p) {
+    extern __shared__ __align__(16) unsigned char im_smem_raw[];
+    unsigned char* im_smem = reinterpret_cast<unsigned char*>(((uintptr_t)im_smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t sm = (uint32_t)__cvta_generic_to_shared(im_smem);
+    const uint32_t sIn = sm + Cfg::OFF_IN, sWB = sm + Cfg::OFF_WB, sMid = sm + Cfg::OFF_MID, sDw = sm + Cfg::OFF_DW;
+    const uint32_t sWd = sm + Cfg::OFF_WD, sBe = sm + Cfg::OFF_BE, sBd = sm + Cfg::OFF_BD, sBp = sm + Cfg::OFF_BP;
+    const uint32_t bar_x = sm + Cfg::OFF_BAR, bar_w = bar_x + 8;              // bar_w + 8 * buffer
+    constexpr int PW = Cfg::PW, P = Cfg::P, CEXP = Cfg::CEXP, COUT = Cfg::COUT, GS = Cfg::GS, KS = Cfg::KS;
+    pdl_trigger();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int tile = (int)blockIdx.x;
+    const int b = tile / p.tiles_per_img, tr = tile - b * p.tiles_per_img, ty = tr / p.tiles_x;
+    const int oy0 = ty * Cfg::TH, ox0 = (tr - ty * p.tiles_x) * Cfg::TW;
+    const int iy0 = oy0 - p.pad_t, ix0 = ox0 - p.pad_l;
+
+    auto request_weights = [&](int grp) {                               // thread 0 only
+        const uint32_t wb = sWB + (uint32_t)((grp & 1) * Cfg::WB_BYTES), bar = bar_w + 8u * (grp & 1);
+        mbar_expect_tx(bar, Cfg::WB_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) tma_load_2d(wb + ks * Cfg::WE_SL, &map_we, bar, 16 * ks, grp * Cfg::GCH);
+#pragma unroll
+        for (int j = 0; j < GS; ++j) tma_load_2d(wb + KS * Cfg::WE_SL + j * Cfg::WP_SL, &map_wp, bar, 16 * (grp * GS + j), 0);
+    };
+    if (tid == 0) {
+        tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_we); tma_prefetch_desc(&map_wp);
+        mbar_init(bar_x, 1); mbar_init(bar_w, 1); mbar_init(bar_w + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        request_weights(0);
+        if (Cfg::NG > 1) request_weights(1);
+    }
+    // depthwise filter and biases in the channel order of the expanded patch (see irblock_mma_kernel)
+    for (int i = tid; i < 9 * CEXP / 2; i += Cfg::THREADS) {
+        const int k = i / (CEXP / 2), w2 = i - k * (CEXP / 2), q = (2 * w2) & 15;
+        const int c = ((2 * w2) & ~15) + 8 * ((q >> 1) & 1) + 2 * (q >> 2);
+        reinterpret_cast<uint32_t*>(im_smem + Cfg::OFF_WD)[i] = __ldg(reinterpret_cast<const uint32_t*>(p.wd + k * CEXP + c));
+    }
+    for (int i = tid; i < CEXP; i += Cfg::THREADS) {
+        const int q = i & 15, c = (i & ~15) + 8 * ((q >> 1) & 1) + 2 * (q >> 2) + (q & 1);
+        reinterpret_cast<float*>(im_smem + Cfg::OFF_BE)[i] = p.be ? __ldg(p.be + c) : 0.f;
+        reinterpret_cast<float*>(im_smem + Cfg::OFF_BD)[i] = p.bd ? __ldg(p.bd + c) : 0.f;
+    }
+    for (int i = tid; i < Cfg::COUTP; i += Cfg::THREADS)
+        reinterpret_cast<float*>(im_smem + Cfg::OFF_BP)[i] = (p.bp && i < COUT) ? __ldg(p.bp + i) : 0.f;
+    pdl_wait();
+    if (tid == 0) {
+        mbar_expect_tx(bar_x, Cfg::X_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) tma_load_4d(sIn + ks * Cfg::IN_SL, &map_x, bar_x, 16 * ks, ix0, iy0, b);
+    }
+    __syncthreads();
+    mbar_wait(bar_x, 0);
+
+    const uint32_t six = 0x46004600u;
+    const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lhalf = lane >> 4;       // A operand: ldmatrix lane -> (row, half)
+    const int brow = (lane & 7) + (lane >> 4) * 8, bhalf = (lane >> 3) & 1;       // B operand
+    const bool edge = iy0 < 0 || ix0 < 0 || iy0 + Cfg::PH > p.H || ix0 + PW > p.W;
+    float pacc[Cfg::UPW][2][4];                                                   // projection partial sums of this warp's units
+#pragma unroll
+    for (int i = 0; i < Cfg::UPW; ++i)
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) pacc[i][n][r] = 0.f;
+
+    for (int grp = 0; grp < Cfg::NG; ++grp) {
+        const uint32_t sWe = sWB + (uint32_t)((grp & 1) * Cfg::WB_BYTES), sWp = sWe + KS * Cfg::WE_SL;
+        mbar_wait(bar_w + 8u * (grp & 1), (uint32_t)(grp >> 1) & 1u);
+        // ---- expansion of this group's 6 slices: contiguous (slice, m-tile) pairs per warp ----
+        {
+            constexpr int NPAIR = GS * Cfg::MT;
+            const int q0 = warp * NPAIR / Cfg::WARPS, q1 = (warp + 1) * NPAIR / Cfg::WARPS;
+            int jp = q0 / Cfg::MT, mt = q0 - jp * Cfg::MT;
+            uint32_t bq[KS][4];
+            float4 bias;
+            bool fresh = true;
+            for (int q = q0; q < q1; ++q) {
+                if (fresh) {
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks)
+                        im_ldsm4(bq[ks], sWe + (uint32_t)(ks * Cfg::WE_SL) + im_row(jp * 16 + brow, bhalf));
+                    bias = im_lds128f(sBe + (uint32_t)(grp * Cfg::GCH + jp * 16 + 4 * t) * 4u);
+                    fresh = false;
+                }
+                float acc[2][4];
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    uint32_t a[4];
+                    im_ldsm4(a, sIn + (uint32_t)(ks * Cfg::IN_SL) + im_row(mt * 16 + lrow, lhalf));
+                    if (ks == 0) {
+                        im_mma_bias(acc[0], a, bq[0][0], bq[0][1], bias.x, bias.y);
+                        im_mma_bias(acc[1], a, bq[0][2], bq[0][3], bias.z, bias.w);
+                    } else {
+                        im_mma(acc[0], a, bq[ks][0], bq[ks][1]);
+                        im_mma(acc[1], a, bq[ks][2], bq[ks][3]);
+                    }
+                }
+                const uint32_t dst = sMid + (uint32_t)(jp * Cfg::MID_SL + (mt * 16 + g) * 32 + 8 * t);
+                im_sts64(dst, im_min2(im_cvt_relu(acc[0][0], acc[0][1]), six), im_min2(im_cvt_relu(acc[1][0], acc[1][1]), six));
+                im_sts64(dst + 256, im_min2(im_cvt_relu(acc[0][2], acc[0][3]), six), im_min2(im_cvt_relu(acc[1][2], acc[1][3]), six));
+                if (++mt == Cfg::MT) { mt = 0; ++jp; fresh = true; }
+            }
+        }
+        __syncthreads();
+        if (edge) {                                   // CTA-uniform: zero the positions outside the image (depthwise padding)
+            for (int i = tid; i < P * GS; i += Cfg::THREADS) {
+                const int pos = i / GS, sl = i - pos * GS;
+                const int py = pos / PW, px = pos - py * PW;
+                if ((unsigned)(iy0 + py) >= (unsigned)p.H || (unsigned)(ix0 + px) >= (unsigned)p.W) {
+                    const uint32_t a = sMid + (uint32_t)(sl * Cfg::MID_SL + pos * 32);
+                    im_sts128(a, make_uint4(0u, 0u, 0u, 0u));
+                    im_sts128(a + 16, make_uint4(0u, 0u, 0u, 0u));
+                }
+            }
+            __syncthreads();
+        }
+        // ---- depthwise 3x3 (stride 1): thread = (8-channel chunk, run of 3 adjacent pixels) ----
+        if (tid < Cfg::NCH * Cfg::NPL) {
+            const int c8 = tid % Cfg::NCH, pl = tid / Cfg::NCH;
+            if (pl < Cfg::NRUN) {
+                const int sl = c8 >> 1, h = c8 & 1;
+                const int y = pl / Cfg::RPR, x0 = 3 * (pl - y * Cfg::RPR);
+                const uint32_t wsrc = sWd + (uint32_t)(grp * Cfg::GCH + 8 * c8) * 2u;
+                __half2 bias4[4];
+                {
+                    const float4 b0 = im_lds128f(sBd + (uint32_t)(grp * Cfg::GCH + 8 * c8) * 4u);
+                    const float4 b1 = im_lds128f(sBd + (uint32_t)(grp * Cfg::GCH + 8 * c8 + 4) * 4u);
+                    bias4[0] = __floats2half2_rn(b0.x, b0.y); bias4[1] = __floats2half2_rn(b0.z, b0.w);
+                    bias4[2] = __floats2half2_rn(b1.x, b1.y); bias4[3] = __floats2half2_rn(b1.z, b1.w);
+                }
+                const uint32_t a0 = sMid + (uint32_t)(sl * Cfg::MID_SL + h * 16 + (y * PW + x0) * 32);
+                __half2 acc[3][4];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int c2 = 0; c2 < 4; ++c2) acc[i][c2] = bias4[c2];
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    uint4 w3[3];
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) w3[kx] = im_lds128(wsrc + (uint32_t)((ky * 3 + kx) * CEXP) * 2u);
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) {
+                        const uint4 xv = im_lds128(a0 + (uint32_t)((ky * PW + c) * 32));
+                        const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const int kx = c - i;
+                            if (kx >= 0 && kx < 3) {
+                                const __half2* wh = reinterpret_cast<const __half2*>(&w3[kx]);
+#pragma unroll
+                                for (int c2 = 0; c2 < 4; ++c2) acc[i][c2] = __hfma2(xh[c2], wh[c2], acc[i][c2]);
+                            }
+                        }
+                    }
+                }
+                const __half2 zero2 = __float2half2_rn(0.f), six2 = __float2half2_rn(6.f);
+                const uint32_t dstb = sDw + (uint32_t)(sl * Cfg::DW_SL + 8 * h);
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    if (x0 + i < Cfg::TW) {
+                        uint4 o;
+                        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int c2 = 0; c2 < 4; ++c2) oh[c2] = __hmin2(__hmax2(acc[i][c2], zero2), six2);
+                        im_sts64(dstb + im_row(y * Cfg::TW + x0 + i, 0), o.x, o.z);
+                        im_sts64(dstb + im_row(y * Cfg::TW + x0 + i, 1), o.y, o.w);
+                    }
+            }
+        }
+        __syncthreads();
+        // ---- projection partial sums: this group's 6 k16 steps into the warp's units ----
+#pragma unroll
+        for (int i = 0; i < Cfg::UPW; ++i) {
+            const int u = warp + i * Cfg::WARPS;
+            if (u < Cfg::NUNIT) {
+                const int mt = u / Cfg::NP, np = u - mt * Cfg::NP;
+#pragma unroll
+                for (int ks = 0; ks < GS; ++ks) {
+                    uint32_t a[4], bq[4];
+                    im_ldsm4(a, sDw + (uint32_t)(ks * Cfg::DW_SL) + im_row(mt * 16 + lrow, lhalf));
+                    im_ldsm4(bq, sWp + (uint32_t)(ks * Cfg::WP_SL) + im_row(np * 16 + brow, bhalf));
+                    im_mma(pacc[i][0], a, bq[0], bq[1]);
+                    im_mma(pacc[i][1], a, bq[2], bq[3]);
+                }
+            }
+        }
+        __syncthreads();                              // weight buffer, expanded patch and depthwise tile of this group are free
+        if (tid == 0 && grp + 2 < Cfg::NG) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            request_weights(grp + 2);
+        }
+    }
+
+    // ---- projection results (+ bias) -> fp32 staging tile [pixel][COUT] (aliases the expanded patch / depthwise tile) ----
+    {
+        const uint32_t sOut = sMid;
+#pragma unroll
+        for (int i = 0; i < Cfg::UPW; ++i) {
+            const int u = warp + i * Cfg::WARPS;
+            if (u < Cfg::NUNIT) {
+                const int mt = u / Cfg::NP, np = u - mt * Cfg::NP;
+                const int r0 = mt * 16 + g;
+#pragma unroll
+                for (int n = 0; n < 2; ++n) {
+                    const int c = np * 16 + n * 8 + 2 * t;
+                    if (c < COUT) {
+                        const float2 bias = im_lds64f(sBp + (uint32_t)c * 4u);
+                        if (r0 < Cfg::NPX) im_sts64f(sOut + (uint32_t)(r0 * COUT + c) * 4u, pacc[i][n][0] + bias.x, pacc[i][n][1] + bias.y);
+                        if (r0 + 8 < Cfg::NPX) im_sts64f(sOut + (uint32_t)((r0 + 8) * COUT + c) * 4u, pacc[i][n][2] + bias.x, pacc[i][n][3] + bias.y);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    {
+        constexpr int U = COUT / 8;
+        for (int i = tid; i < Cfg::NPX * U; i += Cfg::THREADS) {
+            const int px = i / U, u = i - px * U;
+            const int y = px / Cfg::TW, x = px - y * Cfg::TW;
+            const int oy = oy0 + y, ox = ox0 + x;
+            if (oy < p.Ho && ox < p.Wo) {
+                const float4 v0 = im_lds128f(sMid + (uint32_t)(px * COUT + 8 * u) * 4u);
+                const float4 v1 = im_lds128f(sMid + (uint32_t)(px * COUT + 8 * u + 4) * 4u);
+                float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                const size_t off = (((size_t)b * p.Ho + oy) * p.Wo + ox) * COUT + 8 * u;
+                if (p.res) {
+                    const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + off));
+                    const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float2 f = __half22float2(rh[c]);
+                        v[2 * c] += f.x; v[2 * c + 1] += f.y;
+                    }
+                }
+                uint4 o;
+                __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) oh[c] = __floats2half2_rn(v[2 * c], v[2 * c + 1]);
+                *reinterpret_cast<uint4*>(p.out + off) = o;
+            }
+        }
+    }
+}
+
+template <class Cfg>
+static int irblock_mma_grouped_launch_t(const ssd_irblock_desc* d, cudaStream_t st) {
+    ImParams p;
+    p.in = static_cast<const __half*>(d->in); p.we = static_cast<const __half*>(d->exp_weight); p.be = d->exp_bias;
+    p.wd = static_cast<const __half*>(d->dw_weight); p.bd = d->dw_bias;
+    p.wp = static_cast<const __half*>(d->proj_weight); p.bp = d->proj_bias;
+    p.res = static_cast<const __half*>(d->residual); p.out = static_cast<__half*>(d->out);
+    p.B = d->B; p.H = d->H; p.W = d->W; p.Ho = d->Ho; p.Wo = d->Wo; p.pad_t = d->pad_top; p.pad_l = d->pad_left;
+    p.tiles_x = ceil_div(d->Wo, Cfg::TW);
+    p.tiles_per_img = p.tiles_x * ceil_div(d->Ho, Cfg::TH);
+    p.n_tiles = p.tiles_per_img * d->B;
+    CUtensorMap map_x, map_we, map_wp;
+    {
+        uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+        uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
+        uint32_t box[4] = {16, (uint32_t)Cfg::PW, (uint32_t)Cfg::PH, 1};
+        int rc = cached_map(&map_x, d->in, 4, dims, str, box, nullptr, 32);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)d->Cin, (uint64_t)d->Cexp};
+        uint64_t str[1] = {(uint64_t)d->Cin * 2};
+        uint32_t box[2] = {16, (uint32_t)Cfg::GCH};
+        int rc = cached_map(&map_we, d->exp_weight, 2, dims, str, box, nullptr, 32);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)d->Cexp, (uint64_t)d->Cout};
+        uint64_t str[1] = {(uint64_t)d->Cexp * 2};
+        uint32_t box[2] = {16, (uint32_t)Cfg::COUTP};
+        int rc = cached_map(&map_wp, d->proj_weight, 2, dims, str, box, nullptr, 32);
+        if (rc) return rc;
+    }
+    static thread_local int attr_dev = -1;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (attr_dev != cur) {
+        cudaError_t e = cudaFuncSetAttribute(irblock_mma_grouped_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        if (e != cudaSuccess) return cuda_fail(e, "ssd_irblock: cudaFuncSetAttribute (grouped mma.sync variant)");
+        attr_dev = cur;
+    }
+    cudaError_t le = launch_pdl(irblock_mma_grouped_kernel<Cfg>, dim3(p.n_tiles), dim3(Cfg::THREADS), (size_t)Cfg::SMEM, st,
+                                map_x, map_we, map_wp, p);
+    if (le != cudaSuccess) return cuda_fail(le, "irblock_mma_grouped_kernel");
+    return SSD_OK;
+}
+
+// MobileNetV2 blocks 7-12 (19 x 19: 4 tiles of 19 x 5 per image) and 14-15 (10 x 10: 4 tiles of 10 x 3)
+typedef ImGCfg<64, 384, 64, 19, 5> ImBlock7;
+typedef ImGCfg<64, 384, 96, 19, 5> ImBlock10;
+typedef ImGCfg<96, 576, 96, 19, 5> ImBlock11;
+typedef ImGCfg<160, 960, 160, 10, 3> ImBlock14;
+
+// -1 automatic (large-map variant always; the channel-grouped small-map variant when programmatic dependent launch is on:
+// its weight prologue then overlaps the predecessor, which is what makes it faster than the tcgen05 kernel), 0 tcgen05 kernel only, 1 every mma.sync variant that has an instantiation,
+// 2 the large-map mma.sync variant only (blocks 1-6); SSD_B200_IRBLOCK presets it
+static int irblock_mode_from_env() {
+    const char* e = getenv("SSD_B200_IRBLOCK");
+    return e ? atoi(e) : -1;
+}
+static int g_irblock_mode = irblock_mode_from_env();
 
 // 1 when the mma.sync variant has an instantiation for this block (and ReLU6 / ReLU6 / linear activations, B <= 65535)
 bool conv_irblock_mma_matches(const ssd_irblock_desc* d) {
     if (g_irblock_mode == 0) return false;
     if (!(d->exp_act == SSD_ACT_RELU6 && d->dw_act == SSD_ACT_RELU6 && d->act == SSD_ACT_NONE && d->B <= 65535)) return false;
     auto is = [&](int ci, int ce, int co, int s) { return d->Cin == ci && d->Cexp == ce && d->Cout == co && d->stride == s; };
-    return is(16, 96, 24, 2) || is(24, 144, 24, 1) || is(24, 144, 32, 2) || is(32, 192, 32, 1) || is(32, 192, 64, 2);
+    const bool large = is(16, 96, 24, 2) || is(24, 144, 24, 1) || is(24, 144, 32, 2) || is(32, 192, 32, 1) || is(32, 192, 64, 2);
+    const bool small = is(64, 384, 64, 1) || is(64, 384, 96, 1) || is(96, 576, 96, 1) || is(160, 960, 160, 1);
+    return large || (small && (g_irblock_mode == 1 || (g_irblock_mode == -1 && pdl_enabled())));
 }
 
 int conv_irblock_mma_launch(const ssd_irblock_desc* d, cudaStream_t st) {
+    if (d->Cexp == 384) return d->Cout == 64 ? irblock_mma_grouped_launch_t<ImBlock7>(d, st) : irblock_mma_grouped_launch_t<ImBlock10>(d, st);
+    if (d->Cexp == 576) return irblock_mma_grouped_launch_t<ImBlock11>(d, st);
+    if (d->Cexp == 960) return irblock_mma_grouped_launch_t<ImBlock14>(d, st);
     if (d->Cexp == 96) return irblock_mma_launch_t<ImBlock1>(d, st);
     if (d->Cexp == 144) return d->stride == 1 ? irblock_mma_launch_t<ImBlock2>(d, st) : irblock_mma_launch_t<ImBlock3>(d, st);
     return d->stride == 1 ? irblock_mma_launch_t<ImBlock45>(d, st) : irblock_mma_launch_t<ImBlock6>(d, st);
