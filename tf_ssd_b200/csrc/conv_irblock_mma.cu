@@ -228,41 +228,51 @@ irblock_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const uint32_t six = 0x46004600u;                              // half2(6, 6)
         const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lhalf = lane >> 4;         // A operand: ldmatrix lane -> (row, half)
         const int brow = (lane & 7) + (lane >> 4) * 8, bhalf = (lane >> 3) & 1;         // B operand
-        // Every warp owns a contiguous range of the ES x MT (slice, m16 tile) pairs, slice-major: the weight fragments and
-        // the bias of a slice stay in registers while the warp walks over m-tiles (shared-memory wavefronts, not issue
-        // slots, bound this kernel: per pair one ldmatrix per k-step for the positions, 2 KS MMAs, two 8-byte stores).
-        constexpr int NPAIR = Cfg::ES * Cfg::MT;
-        const int q0 = warp * NPAIR / IM_WARPS, q1 = (warp + 1) * NPAIR / IM_WARPS;
-        int jp = q0 / Cfg::MT, mt = q0 - jp * Cfg::MT;
-        uint32_t bq[Cfg::KS][4];
-        float4 bias;
-        bool fresh = true;
+        // Every warp owns a contiguous range of the (slice PAIR, m16 tile) work items, slice-major: the weight fragments
+        // and biases of two slices stay in registers while the warp walks over m-tiles, and one ldmatrix per k-step of the
+        // positions feeds 4 KS MMAs (shared-memory wavefronts, not issue slots, bound this kernel).
+        constexpr int ESP = (Cfg::ES + 1) / 2, NITEM = ESP * Cfg::MT;
+        const int q0 = warp * NITEM / IM_WARPS, q1 = (warp + 1) * NITEM / IM_WARPS;
+        int sp = q0 / Cfg::MT, mt = q0 - sp * Cfg::MT;
+        uint32_t bq[2][Cfg::KS][4];
+        float4 bias[2];
+        bool fresh = true, two = true;
         for (int q = q0; q < q1; ++q) {
             if (fresh) {
+                two = 2 * sp + 1 < Cfg::ES;                           // an odd slice count leaves the last pair half empty
 #pragma unroll
-                for (int ks = 0; ks < Cfg::KS; ++ks)
-                    im_ldsm4(bq[ks], sWe + (uint32_t)(ks * Cfg::WE_SL) + im_row(jp * 16 + brow, bhalf));
-                bias = im_lds128f(sBe + (uint32_t)(jp * 16 + 4 * t) * 4u);           // channels 4t .. 4t+3 of the slice's order
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int jp = (h2 == 1 && !two) ? 2 * sp : 2 * sp + h2;
+#pragma unroll
+                    for (int ks = 0; ks < Cfg::KS; ++ks)
+                        im_ldsm4(bq[h2][ks], sWe + (uint32_t)(ks * Cfg::WE_SL) + im_row(jp * 16 + brow, bhalf));
+                    bias[h2] = im_lds128f(sBe + (uint32_t)(jp * 16 + 4 * t) * 4u);   // channels 4t .. 4t+3 of the slice's order
+                }
                 fresh = false;
             }
             uint32_t a[Cfg::KS][4];
 #pragma unroll
             for (int ks = 0; ks < Cfg::KS; ++ks)
                 im_ldsm4(a[ks], sIn + (uint32_t)(ks * Cfg::IN_SL) + im_row(mt * 16 + lrow, lhalf));
-            float acc[2][4];
-            im_mma_bias(acc[0], a[0], bq[0][0], bq[0][1], bias.x, bias.y);
-            im_mma_bias(acc[1], a[0], bq[0][2], bq[0][3], bias.z, bias.w);
-#pragma unroll
-            for (int ks = 1; ks < Cfg::KS; ++ks) {
-                im_mma(acc[0], a[ks], bq[ks][0], bq[ks][1]);
-                im_mma(acc[1], a[ks], bq[ks][2], bq[ks][3]);
-            }
             // the expanded patch is LINEAR (row = 32 bytes); within a slice, position 4t + 2n + e holds channel 8n + 2t + e
             // (accumulator columns 2t, 2t+1 of n-tiles n = 0, 1): one 8-byte store per row, 8 whole rows per instruction
-            const uint32_t dst = sMid + (uint32_t)(jp * Cfg::MID_SL + (mt * 16 + g) * 32 + 8 * t);
-            im_sts64(dst, im_min2(im_cvt_relu(acc[0][0], acc[0][1]), six), im_min2(im_cvt_relu(acc[1][0], acc[1][1]), six));
-            im_sts64(dst + 256, im_min2(im_cvt_relu(acc[0][2], acc[0][3]), six), im_min2(im_cvt_relu(acc[1][2], acc[1][3]), six));
-            if (++mt == Cfg::MT) { mt = 0; ++jp; fresh = true; }
+            const uint32_t dst0 = sMid + (uint32_t)(2 * sp * Cfg::MID_SL + (mt * 16 + g) * 32 + 8 * t);
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                if (h2 == 1 && !two) break;
+                float acc[2][4];
+                im_mma_bias(acc[0], a[0], bq[h2][0][0], bq[h2][0][1], bias[h2].x, bias[h2].y);
+                im_mma_bias(acc[1], a[0], bq[h2][0][2], bq[h2][0][3], bias[h2].z, bias[h2].w);
+#pragma unroll
+                for (int ks = 1; ks < Cfg::KS; ++ks) {
+                    im_mma(acc[0], a[ks], bq[h2][ks][0], bq[h2][ks][1]);
+                    im_mma(acc[1], a[ks], bq[h2][ks][2], bq[h2][ks][3]);
+                }
+                const uint32_t dst = dst0 + (uint32_t)(h2 * Cfg::MID_SL);
+                im_sts64(dst, im_min2(im_cvt_relu(acc[0][0], acc[0][1]), six), im_min2(im_cvt_relu(acc[1][0], acc[1][1]), six));
+                im_sts64(dst + 256, im_min2(im_cvt_relu(acc[0][2], acc[0][3]), six), im_min2(im_cvt_relu(acc[1][2], acc[1][3]), six));
+            }
+            if (++mt == Cfg::MT) { mt = 0; ++sp; fresh = true; }
         }
     }
     __syncthreads();
