@@ -62,12 +62,16 @@ def _ncu_traffic(kind, launches_per_step):
     committed ``ncu --set full`` capture of one step of this same workload (profiles/r2_traffic.json, written by
     tools/ncu_traffic.py): the group's DRAM bytes per step / its launches per step, i.e. per launch like ``achieved``.
     None when no capture is committed for that group."""
+    e = _ncu_group(kind)
+    return None if e is None else float(e["dram_bytes"]) / max(int(launches_per_step), 1)
+
+
+def _ncu_group(kind):
     path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as f:
-        e = json.load(f).get(kind)
-    return None if e is None else float(e["dram_bytes"]) / max(int(launches_per_step), 1)
+        return json.load(f).get(kind)
 
 
 def _hyper_params():
@@ -569,13 +573,19 @@ def run_b200(args):
                 ach = g["bytes"] / (g["ms"] * 1e-3) / 1e9
                 roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]}
             roof.update({"traffic": _ncu_traffic(top, g["launches"]), "algorithmic_bytes_per_launch": g["bytes"] / max(g["launches"], 1), "kernel": {"conv": "ssd_conv2d launches: conv_tcgen05_kernel (+ conv_splitk_reduce_kernel for the multibox heads)",
-                                                     "irblock": "conv_irblock_tcgen05_kernel (whole inverted-residual block: 1x1 expand -> depthwise 3x3 -> 1x1 project)",
+                                                     "irblock": "ssd_irblock launches (whole inverted-residual block: 1x1 expand -> depthwise 3x3 -> 1x1 project): irblock_mma_kernel "
+                                    "(blocks 1-6) + irblock_mma_grouped_kernel (blocks 7-12, 14, 15; conv_irblock_tcgen05_kernel when PDL is off)",
                          "dw": "depthwise3x3_kernel", "dwproj": "conv_dwproj_tcgen05_kernel (fused depthwise 3x3 -> 1x1 projection)", "decode_nms": "nms_candidates+nms_image",
                          "chain": "conv_chain_kernel (the small-map tail + its heads as one cluster launch)", "stem": "stem_conv3x3s2_mma_kernel",
                          "stemblock": "stem_dwproj_kernel (Conv1 3x3 s2 -> depthwise 3x3 -> 1x1 projection from the image, one launch)"}.get(top, top),
                          "launches_per_step": g["launches"], "ms_per_step": g["ms"], "share_of_step": g["ms"] / total,
                          "algorithmic_bytes_per_step": g["bytes"], "flops_per_step": g["flops"], "peak_source": peaks["source"],
                          "by_kind_ms": {k: round(v["ms"], 4) for k, v in groups.items()}})
+            grp = _ncu_group(top)
+            if grp is not None and grp.get("l1tex_throughput_pct") is not None:
+                # what actually bounds the block kernels: the shared-memory (L1/TEX) pipe, from the committed ncu capture
+                roof["on_chip"] = {"l1tex_throughput_pct_of_peak": round(float(grp["l1tex_throughput_pct"]), 1),
+                                   "source": grp.get("source"), "note": "time-weighted l1tex__throughput of the group's launches"}
             if top == "irblock":
                 # context for the fraction above: the fused kernel's algorithmic bytes exclude the 6x expanded tensors it
                 # keeps on chip; the layer-by-layer path (expand -> depthwise -> project as three launches) would move these
@@ -590,8 +600,8 @@ def run_b200(args):
                     "bytes_per_step": unfused, "gbs": unfused / (g["ms"] * 1e-3) / 1e9,
                     "frac": unfused / (g["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
                     "note": "bytes the unfused expand / depthwise / project launches of the same blocks would move; the fused "
-                            "kernel is bound by its on-chip mid + depthwise pipeline (shared-memory wavefronts, issue slots), "
-                            "not by HBM or the tensor pipe"}
+                            "kernels are bound by the shared-memory pipe (expanded patch written once and read by the nine "
+                            "depthwise taps, ldmatrix operands), not by HBM or the tensor pipe: see on_chip"}
             line["roofline"] = roof
             worst = sorted(zip(per[:-1], steps), key=lambda t: -t[0])[:8]
             line["top_launches"] = [{"name": s.name, "kind": s.kind, "ms": round(float(ms), 4),

@@ -3,6 +3,7 @@
 # usage: tools/gpu_profile.sh <tag> [box] [launches] [conv]
 set -u
 export SSD_B200_PDL=0
+export SSD_B200_IRBLOCK=1      # the block kernels of the production path (automatic mode keys on PDL, which is off under ncu)
 tag=$1; shift
 OUT=gpurun_out
 mkdir -p $OUT
@@ -22,7 +23,7 @@ for what in "$@"; do
           python bench.py --profile-one-step > $OUT/launches_$tag.log 2>&1
       ;;
     conv)
-      ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"conv_tcgen05_kernel|conv_dwproj|conv_irblock|conv_chain|stem_conv|conv_igemm|splitk|nms_|depthwise3x3" \
+      ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"conv_tcgen05_kernel|conv_dwproj|conv_irblock|irblock_mma|stem_dwproj|conv_chain|stem_conv|conv_igemm|splitk|nms_|depthwise3x3" \
           -o $OUT/conv_$tag python bench.py --profile-one-step > $OUT/conv_$tag.log 2>&1
       ncu -i $OUT/conv_$tag.ncu-rep --page raw --csv > $OUT/conv_${tag}_raw.csv 2>/dev/null
       python tools/ncu_summary.py $OUT/conv_${tag}_raw.csv > $OUT/conv_${tag}_summary.csv 2>&1

@@ -1,14 +1,14 @@
 #!/bin/bash
 # compute-sanitizer over the parity tests of the hand-written kernels (runs on the GPU box via gpurun).
-#   tools/gpu_sanitize.sh <tag>      -> gpurun_out/sanitize_<tag>_{memcheck,racecheck,synccheck}.txt (+ .summary)
+#   tools/gpu_sanitize.sh <tag> [pytest -k expression]      -> gpurun_out/sanitize_<tag>_{memcheck,racecheck,synccheck}.txt (+ .summary)
 set -u
 tag=$1
 OUT=gpurun_out
 mkdir -p $OUT
-SEL='irblock or dwproj or stem_kernel or conv2d_against or cta_pair or conv_chain or decoder_parity or decoder_integer or combined_nms or loss_forward or hard_negative or iou or match or prior or cuda_reproduces or cuda_priors or cuda_losses or cuda_decoder or cuda_augmentation'
+SEL=${2:-'irblock or dwproj or stem_kernel or conv2d_against or cta_pair or conv_chain or decoder_parity or decoder_integer or combined_nms or loss_forward or hard_negative or iou or match or prior or cuda_reproduces or cuda_priors or cuda_losses or cuda_decoder or cuda_augmentation'}
 for tool in memcheck racecheck synccheck; do
   log=$OUT/sanitize_${tag}_${tool}.txt
-  timeout 700 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 0 \
+  timeout ${SAN_TIMEOUT:-700} compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 0 \
       python -m pytest tests/test_net_gpu.py tests/test_box_gpu.py tests/test_nms_gpu.py tests/test_loss_gpu.py tests/test_golden.py tests/test_ref_golden.py \
       -m gpu -q -x -k "$SEL" -p no:cacheprovider > $log 2>&1
   echo "exit=$?" >> $log

@@ -17,6 +17,8 @@ KEYS = [
     ("launch__block_size", "block"),
     ("smsp__inst_executed.sum", "inst"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_conflicts"),
+    ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex_pct"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem_wavefronts"),
 ]
 
 
