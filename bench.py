@@ -543,7 +543,7 @@ def run_b200(args):
                                "images_per_step": B, "peaks": peaks["source"], "numa_bound": numa_bound},
             "clocks": clocks,
             "e2e": {"value": total_images / (e2e_ms / 1e3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(B * S * S * 3), "d2h_bytes_per_step": int(B * 200 * 6 * 4),
+                    "h2d_bytes_per_step": int(B * S * S * 3), "d2h_bytes_per_step": int(B * 200 * 6 * 4 + B * 4),
                     "api": "get_decoder_model(...).predict(uint8 host batches): pinned H2D + graph replay + D2H, 2 slots in flight"},
             "gpu_launches": K * dm.launches_per_batch(B),
         }
@@ -633,7 +633,7 @@ def _decode_only(dm, st, B):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")

@@ -1037,15 +1037,13 @@ class DecoderModel(object):
         st: Dict[str, Any] = {
             "plan": plan,
             # one packed result buffer so a single D2H brings everything back:
-            # [B, T, 6] = boxes(4) | labels | scores, then the int32 valid counts
-            "boxes": torch.empty((B, T, 4), dtype=torch.float32, device=dev),
-            "labels": torch.empty((B, T), dtype=torch.float32, device=dev),
-            "scores": torch.empty((B, T), dtype=torch.float32, device=dev),
-            "valid": torch.empty((B,), dtype=torch.int32, device=dev),
+            # boxes [B,T,4] | labels [B,T] | scores [B,T] | int32 valid counts [B] (views of ``packed``)
+            "packed": torch.empty((B * T * 6 + B,), dtype=torch.float32, device=dev),
             "graph": {},                      # input dtype (False: float32, True: uint8) -> captured CUDA graph
             "ws": _ffi.workspace(_ffi.lib().ssd_decode_nms_workspace_bytes(B, self.base_model.n_anchors,
                                                                             self.base_model.total_labels, T, 0)),
         }
+        st.update(self._unpack(st["packed"], B, T))
         dec, lib = self.decoder, _ffi.lib()
         var = _ffi.f32_array(dec.variances)
         priors = dec._priors()
@@ -1061,6 +1059,13 @@ class DecoderModel(object):
         st["enqueue"] = enqueue
         self._state[(B, slot)] = st
         return st
+
+    @staticmethod
+    def _unpack(packed: torch.Tensor, B: int, T: int) -> Dict[str, torch.Tensor]:
+        """The four result tensors as views of one packed buffer (device or pinned host)."""
+        n = B * T
+        return {"boxes": packed[:4 * n].view(B, T, 4), "labels": packed[4 * n:5 * n].view(B, T),
+                "scores": packed[5 * n:6 * n].view(B, T), "valid": packed[6 * n:].view(torch.int32)}
 
     def _graph(self, st: Dict[str, Any], u8: bool):
         """The captured forward + decode + NMS graph of one slot for one input dtype (captured on first use)."""
@@ -1112,20 +1117,31 @@ class DecoderModel(object):
         ob, ol, os_ = [], [], []
         pending: List[Tuple[Dict[str, Any], torch.cuda.Event]] = []
         host: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}
+        out: Dict[str, Any] = {"rows": 0, "cap": 0}    # preallocated result arrays when ``steps`` is given (no concatenation)
 
         def drain(entry):
             st, hb, done = entry
             done.synchronize()
             if int(hb["valid"].min()) < 0:               # cannot happen for softmax outputs (at most one class per anchor > 0.5)
                 raise _ffi.SsdB200Error("ssd_decode_nms reported a candidate overflow (valid = -1)")
-            ob.append(hb["boxes"].numpy().copy()); ol.append(hb["labels"].numpy().copy())
-            os_.append(hb["scores"].numpy().copy())
+            n = hb["boxes"].shape[0]
+            if out["rows"] + n <= out["cap"]:          # known number of batches: results land in the final arrays directly
+                r0 = out["rows"]
+                out["b"][r0:r0 + n] = hb["boxes"].numpy(); out["l"][r0:r0 + n] = hb["labels"].numpy()
+                out["s"][r0:r0 + n] = hb["scores"].numpy()
+                out["rows"] = r0 + n
+            else:
+                res = self._unpack(hb["packed"].clone(), n, T)                         # one host copy, then views
+                ob.append(res["boxes"].numpy()); ol.append(res["labels"].numpy()); os_.append(res["scores"].numpy())
 
         for i, batch in enumerate(data):
             if steps is not None and i >= steps:
                 break
             img = batch[0] if isinstance(batch, (tuple, list)) else batch
             B = int(img.shape[0])
+            if i == 0 and steps is not None:
+                out.update(cap=steps * B, b=np.empty((steps * B, T, 4), np.float32), l=np.empty((steps * B, T), np.float32),
+                           s=np.empty((steps * B, T), np.float32))
             slot = i % self.N_SLOTS
             st = self._prepare(B, slot)
             if len(pending) >= self.N_SLOTS:           # the slot's previous user must be fully drained
@@ -1135,10 +1151,8 @@ class DecoderModel(object):
             hb = host.get((B, slot, u8))
             if hb is None:
                 hb = {"img": torch.empty(tuple(dst_img.shape), dtype=dst_img.dtype, pin_memory=True),
-                      "boxes": torch.empty((B, T, 4), dtype=torch.float32, pin_memory=True),
-                      "labels": torch.empty((B, T), dtype=torch.float32, pin_memory=True),
-                      "scores": torch.empty((B, T), dtype=torch.float32, pin_memory=True),
-                      "valid": torch.empty((B,), dtype=torch.int32, pin_memory=True)}
+                      "packed": torch.empty((B * T * 6 + B,), dtype=torch.float32, pin_memory=True)}
+                hb.update(self._unpack(hb["packed"], B, T))
                 host[(B, slot, u8)] = hb
             if isinstance(img, torch.Tensor) and img.is_cuda:
                 with torch.cuda.stream(cs):
@@ -1160,15 +1174,17 @@ class DecoderModel(object):
             self.run_resident(B, slot, u8)
             ds.wait_stream(ms)
             with torch.cuda.stream(ds):
-                hb["boxes"].copy_(st["boxes"], non_blocking=True)
-                hb["labels"].copy_(st["labels"], non_blocking=True)
-                hb["scores"].copy_(st["scores"], non_blocking=True)
-                hb["valid"].copy_(st["valid"], non_blocking=True)
+                hb["packed"].copy_(st["packed"], non_blocking=True)        # boxes | labels | scores | valid in ONE copy
                 done = torch.cuda.Event()
                 done.record(ds)
             pending.append((st, hb, done))
         while pending:
             drain(pending.pop(0))
+        if out["rows"]:
+            head = (out["b"][:out["rows"]], out["l"][:out["rows"]], out["s"][:out["rows"]])
+            if not ob:
+                return head
+            return (np.concatenate([head[0]] + ob, 0), np.concatenate([head[1]] + ol, 0), np.concatenate([head[2]] + os_, 0))
         if not ob:
             z = np.zeros((0, T), np.float32)
             return np.zeros((0, T, 4), np.float32), z, z.copy()
