@@ -376,7 +376,66 @@ def _box_kernel_rooflines(peaks, hp, iters=10, warmup=3):
                                               0, _ffi.ptr(ob), _ffi.ptr(ol), _ffi.ptr(os_), _ffi.ptr(ov), _ffi.ptr(ws2),
                                               ws2.numel(), _ffi.stream())),
         B * N * (16 + 4 * L) + 16 * N + 24 * B * T)
+    # the same four kernels at the BASELINE shapes (launch-latency bound: 5-56 MB per launch = 1-9 us at the HBM peak) and
+    # over the batch size at N = 24 564: where each launch stops being latency-bound
+    del deltas, onehot, pd_d, z_d, ws, ws2
+    torch.cuda.empty_cache()
+    out["baseline_shapes"] = {}
+    for tag, backbone, b_ in (("cfg2_mobilenet_v2_B32_N2268", "mobilenet_v2", 32), ("cfg3_vgg16_B32_N8732", "vgg16", 32),
+                              ("cfg5_vgg16_512_B16_N24564", "vgg16_512", 16)):
+        out["baseline_shapes"][tag] = _box_kernels_at(lib, timeit, var, backbone, b_, 16, L)
+    sweep_all = {}
+    for b_ in (8, 32, 128, 256):
+        r = _box_kernels_at(lib, timeit, var, "vgg16_512", b_, 16, L)
+        for k, v in r.items():
+            sweep_all.setdefault(k, {})[str(b_)] = {"ms": v["ms"], "frac": v["frac"]}
+    out["batch_sweep_N24564_G16"] = sweep_all
     return {"shape": {"B": B, "N": N, "G": G, "L": L}, "peak_gbs": peaks["hbm_gbs"], "kernels": out}
+
+
+def _box_kernels_at(lib, timeit, var, backbone, B, G, L):
+    """generate_iou_map / match_encode / ssd_loss_fwd / decode_nms at one (network, batch) shape: ms and HBM fraction."""
+    import torch
+    from tf_ssd_b200 import _ffi, synth
+    from tf_ssd_b200.utils import bbox_utils, train_utils
+    hp = train_utils.get_hyper_params(backbone)
+    hp["total_labels"] = L
+    priors = bbox_utils.generate_prior_boxes(hp["feature_map_shapes"], hp["aspect_ratios"])
+    N, dev = priors.shape[0], priors.device
+    gt, lab = synth.make_ground_truth(B, padded=G, max_boxes=8, seed=5)
+    gt_d, lab_d = _ffi.to_dev(gt), _ffi.to_dev(lab, dtype=torch.int32)
+    res = {}
+    iou = torch.empty((B, N, G), dtype=torch.float32, device=dev)
+    res["generate_iou_map"] = timeit(
+        lambda: _ffi.check(lib.ssd_iou_map(_ffi.ptr(priors), _ffi.ptr(gt_d), B, N, G, 0, _ffi.ptr(iou), _ffi.stream())),
+        4 * B * N * G + 16 * N + 16 * B * G)
+    deltas = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
+    onehot = torch.empty((B, N, L), dtype=torch.float32, device=dev)
+    res["match_encode"] = timeit(
+        lambda: _ffi.check(lib.ssd_match_encode(_ffi.ptr(priors), _ffi.ptr(gt_d), _ffi.ptr(lab_d), B, N, G, L, 0.5, var,
+                                                _ffi.ptr(deltas), _ffi.ptr(onehot), None, None, _ffi.stream())),
+        16 * N + 20 * B * G + B * N * (16 + 4 * L))
+    pd, logits = synth.make_head_outputs(B, N, L, seed=6, background_bias=10.0)
+    pd_d, z_d = _ffi.to_dev(pd), _ffi.to_dev(logits)
+    ws = _ffi.workspace(lib.ssd_loss_workspace_bytes(B, N, L))
+    loc = torch.empty(B, dtype=torch.float32, device=dev)
+    conf = torch.empty(B, dtype=torch.float32, device=dev)
+    res["ssd_loss_fwd"] = timeit(
+        lambda: _ffi.check(lib.ssd_loss_fwd(_ffi.ptr(deltas), _ffi.ptr(pd_d), _ffi.ptr(onehot), _ffi.ptr(z_d), B, N, L, 3.0,
+                                            1.0, 1, _ffi.ptr(loc), _ffi.ptr(conf), _ffi.ptr(ws), ws.numel(), _ffi.stream())),
+        B * N * (16 + 16 + 4 * L + 4 * L) + 8 * B)
+    T = 200
+    ws2 = _ffi.workspace(lib.ssd_decode_nms_workspace_bytes(B, N, L, T, 0))
+    ob = torch.empty((B, T, 4), dtype=torch.float32, device=dev)
+    ol = torch.empty((B, T), dtype=torch.float32, device=dev)
+    os_ = torch.empty((B, T), dtype=torch.float32, device=dev)
+    ov = torch.empty((B,), dtype=torch.int32, device=dev)
+    res["decode_nms"] = timeit(
+        lambda: _ffi.check(lib.ssd_decode_nms(_ffi.ptr(priors), _ffi.ptr(pd_d), _ffi.ptr(z_d), B, N, L, var, 1, 0.5, 0.5, T,
+                                              0, _ffi.ptr(ob), _ffi.ptr(ol), _ffi.ptr(os_), _ffi.ptr(ov), _ffi.ptr(ws2),
+                                              ws2.numel(), _ffi.stream())),
+        B * N * (16 + 4 * L) + 16 * N + 24 * B * T)
+    return {k: {"ms": round(v["ms"], 5), "MB": round(v["bytes"] / 1e6, 2), "frac": round(v["frac"], 4)} for k, v in res.items()}
 
 
 def _other_inference_configs(steps=10, warmup=3):
