@@ -263,6 +263,11 @@ typedef struct ssd_irblock_desc {
 } ssd_irblock_desc;
 int ssd_irblock(const ssd_irblock_desc* h_desc, ssd_stream_t stream);
 int ssd_irblock_supported(const ssd_irblock_desc* h_desc);
+/* Programmatic dependent launch between consecutive kernels of a plan: -1 the default policy (on, unless SSD_B200_PDL=0 or a
+ * CUDA injection library -- Nsight Compute, compute-sanitizer -- is attached), 0 off, 1 on.  Takes effect for launches (and
+ * graph captures) made after the call; the training driver switches it off while it records its step (the many mid-size
+ * kernels of a training step lose ~3 % when their successors' CTAs are scheduled early). */
+int ssd_set_pdl(int mode);
 /* ssd_irblock has two implementations: the tcgen05 / TMEM pipeline (any supported shape) and an mma.sync kernel with one
  * CTA per small output tile for MobileNetV2's large-map blocks 1-6 ((Cin, Cexp, Cout, stride) = (16,96,24,2), (24,144,24,1),
  * (24,144,32,2), (32,192,32,1), (32,192,64,2) with ReLU6 / ReLU6 / linear activations), plus a channel-grouped mma.sync

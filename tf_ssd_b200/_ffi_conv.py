@@ -74,6 +74,7 @@ SIGNATURES = {
     "ssd_irblock_supported": (i, [C.POINTER(IrBlockDesc)]),
     "ssd_irblock_trace": (i, [vp]),
     "ssd_debug_irblock_mode": (i, [i]),
+    "ssd_set_pdl": (i, [i]),
     "ssd_irblock_plan": (i, [C.POINTER(IrBlockDesc), C.POINTER(C.c_int32)]),
     "ssd_debug_trace": (i, [vp]),
     "ssd_debug_pair_mode": (i, [i]),

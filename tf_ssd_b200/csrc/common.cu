@@ -23,7 +23,10 @@ int cuda_fail(cudaError_t e, const char* what) {
     return (int)e;
 }
 
+static int g_pdl_mode = -1;         // ssd_set_pdl: -1 the default policy below, 0 off, 1 on
+
 bool pdl_enabled() {
+    if (g_pdl_mode >= 0) return g_pdl_mode == 1;
     // Default ON (measured -4.6 % on the MobileNetV2 step, -6 % with the channel-grouped block kernels whose weight
     // prologue then runs under the predecessor's tail).  SSD_B200_PDL=0 switches it off, =1 forces it on; without the
     // variable it is switched off when a CUDA injection library is attached (Nsight Compute, compute-sanitizer): their
@@ -79,5 +82,10 @@ extern "C" int ssd_device_info(char* h_name, int name_len, int* h_sm_count, int*
     }
     if (h_sm_count) *h_sm_count = prop.multiProcessorCount;
     if (h_cc) *h_cc = prop.major * 10 + prop.minor;
+    return SSD_OK;
+}
+
+extern "C" int ssd_set_pdl(int mode) {
+    ssd::g_pdl_mode = mode < 0 ? -1 : (mode ? 1 : 0);
     return SSD_OK;
 }

@@ -425,6 +425,15 @@ class Trainer(object):
                 self._enqueue_launches(st, first, last)
 
         key = "graphs_dist" if distributed else "graphs"
+        # launches recorded (or run eagerly) below carry no programmatic-dependent-launch edges: measured 7.85 vs 8.11 ms
+        # per MobileNetV2 step (the inference plans keep them)
+        self.lib.ssd_set_pdl(0)
+        try:
+            return self._forward_backward_recorded(st, B, key, segments, run_segment, distributed)
+        finally:
+            self.lib.ssd_set_pdl(-1)
+
+    def _forward_backward_recorded(self, st, B, key, segments, run_segment, distributed) -> Dict[str, torch.Tensor]:
         if self.use_cuda_graph and st.get(key) is None:
             # the first step runs eagerly (workspaces, function attributes, split-K regions) ...
             for i in range(len(segments)):
