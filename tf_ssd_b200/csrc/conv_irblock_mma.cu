@@ -11,20 +11,27 @@
 // output tile with ALL expanded channels, phases are separated by plain __syncthreads(), and two CTAs per SM overlap each
 // other's phases; the cost is issue slots (the expansion's epilogue and the depthwise FMAs), nothing waits on a chain.
 //
-//   1. cp.async: input patch (tile + halo, zero outside the image), expansion / depthwise / projection weights, biases;
-//   2. expansion: [patch positions x Cin] x [Cin x Cexp] on mma.sync.m16n8k16 (ldmatrix operands), + bias, ReLU6 fused into
-//      the fp16 conversion (cvt.rn.relu) -> expanded patch in shared memory; edge tiles then zero the positions outside
-//      the image (the depthwise layer's zero padding);
-//   3. depthwise 3x3: a thread owns one 8-channel chunk (its 9 x 8 taps live in registers) and walks over tile pixels,
-//      packed half2 FMAs -> the projection's A operand in shared memory;
+//   1. TMA: expansion / projection weights once per (persistent) CTA, the input patch (tile + halo, zero outside the image)
+//      per tile -- the NEXT tile's patch is requested as soon as the expansion has read the buffer; depthwise filter and
+//      biases by the threads, once per CTA;
+//   2. expansion: [patch positions x Cin] x [Cin x Cexp] on mma.sync.m16n8k16 (ldmatrix operands; the bias enters as the C
+//      operand of the first MMA), ReLU6 fused into the fp16 conversion (cvt.rn.relu + one min) -> expanded patch in shared
+//      memory; edge tiles then zero the positions outside the image (the depthwise layer's zero padding);
+//   3. depthwise 3x3: a thread owns one 8-channel chunk (its 9 x 8 taps live in registers) and walks over tile pixels
+//      (runs of three adjacent pixels at stride 1), packed half2 FMAs -> the projection's A operand in shared memory;
 //   4. projection: [pixels x Cexp] x [Cexp x Cout] on mma.sync, + bias -> fp32 staging tile;
 //   5. (+ residual) -> fp16 -> 16-byte coalesced stores.
 //
-// Shared-memory tiles are arrays of 16-channel SLICES: tile[slice][row][16 fp16] (32-byte rows, slice stride = one row
-// more than the row count so that the depthwise stage's 16-byte accesses -- 8 consecutive chunks of one position = 4
-// slices -- are bank-conflict free); a k16 step of either GEMM is one slice.  The ldmatrix operands (input patch, weights,
-// depthwise tile) XOR the 16-byte half of a row with (row >> 2) & 1 (conflict-free 8-row phases); the expanded patch is
-// linear, so that the nine depthwise taps of a pixel are compile-time offsets from one address.
+// Shared-memory tiles are arrays of 16-channel SLICES: tile[slice][row][16 fp16] (32-byte rows); a k16 step of either GEMM
+// is one slice.  The ldmatrix operands (input patch, weights, depthwise tile) XOR the 16-byte half of a row with
+// (row >> 2) & 1 -- conflict-free 8-row phases, and exactly the tensor map's 32-byte swizzle, so TMA writes them directly.
+// The expanded patch is linear (the nine depthwise taps of a pixel are compile-time offsets from one address) with one
+// padding row per slice (the depthwise stage's 16-byte accesses to 8 consecutive chunks of a position = 4 slices are then
+// bank-conflict free); inside a slice its 16 channels are stored in the order of the accumulator fragments (a thread's four
+// values are contiguous: one 8-byte store per row), and the depthwise filter / biases are kept in that order too.
+//
+// The second kernel of this file (irblock_mma_grouped_kernel) runs the SMALL-MAP blocks 7-12, 14, 15 with the expanded
+// channels in groups of 96 and the weights streamed through a TMA double buffer.
 
 #include "tc_common.cuh"
 
@@ -356,7 +363,7 @@ irblock_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 if (xr >= RPR) { xr -= RPR; ++y; }
             }
         } else {
-        // two pixels in flight per iteration (independent load -> FMA chains)
+            // stride 2: two pixels in flight per iteration (independent load -> FMA chains)
             int y = pl / Cfg::TW, x = pl - y * Cfg::TW;
             for (int px = pl; px < Cfg::NPX; px += 2 * Cfg::NPL) {
                 int yy[2], xx[2];
@@ -369,38 +376,38 @@ irblock_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 if (x >= Cfg::TW) { x -= Cfg::TW; ++y; }
                 uint32_t a0[2];
                 __half2 acc[2][4];
-    #pragma unroll
+#pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     a0[q] = src + (uint32_t)((yy[q] * S * PW + xx[q] * S) * 32);
-    #pragma unroll
+#pragma unroll
                     for (int c2 = 0; c2 < 4; ++c2) acc[q][c2] = bias4[c2];
                 }
-    #pragma unroll
+#pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
-    #pragma unroll
+#pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
                         const __half2* wh = reinterpret_cast<const __half2*>(&w[ky * 3 + kx]);
-    #pragma unroll
+#pragma unroll
                         for (int q = 0; q < 2; ++q) {
                             const uint4 xv = im_lds128(a0[q] + (uint32_t)((ky * PW + kx) * 32));
                             const __half2* xh = reinterpret_cast<const __half2*>(&xv);
-    #pragma unroll
+#pragma unroll
                             for (int c2 = 0; c2 < 4; ++c2) acc[q][c2] = __hfma2(xh[c2], wh[c2], acc[q][c2]);
                         }
                     }
-    #pragma unroll
+#pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     if (q == 1 && !two) break;
                     uint4 o;
                     __half2* oh = reinterpret_cast<__half2*>(&o);
-    #pragma unroll
+#pragma unroll
                     for (int c2 = 0; c2 < 4; ++c2) oh[c2] = __hmin2(__hmax2(acc[q][c2], zero2), six2);
                     im_sts64(dstb + im_row(px + q * Cfg::NPL, 0), o.x, o.z);
                     im_sts64(dstb + im_row(px + q * Cfg::NPL, 1), o.y, o.w);
                 }
             }
         }
-        }
+    }
     __syncthreads();
 
     // ---- 4. projection: units of (m16 tile of pixels, n-tile pair); fp32 results (+ bias) -> staging tile [pixel][COUT] ----
