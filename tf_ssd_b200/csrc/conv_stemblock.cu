@@ -83,7 +83,7 @@ struct SbParams {
 };
 
 template <typename TIn, int NTP>
-__global__ void __launch_bounds__(SB_THREADS, 2)
+__global__ void __launch_bounds__(SB_THREADS, 4)
 stem_dwproj_kernel(const __grid_constant__ SbParams p) {
     extern __shared__ __align__(16) unsigned char sb_smem[];
     __half* sImg = reinterpret_cast<__half*>(sb_smem + SB_OFF_IMG);
