@@ -7,7 +7,7 @@
 // As separate launches the 150x150x32 stem output (46 MB per batch of 32) is written, evicted from L2 and read back,
 // and block 0 runs the tcgen05 depthwise->projection pipeline at one 128-pixel tile per ~2 us (86 us + 40 us for the
 // stem).  None of the three layers has a deep contraction (K = 27, 9, 32), so this kernel keeps them on mma.sync / packed
-// half2 FMAs inside ONE CTA per 30 x 10 output tile, with plain __syncthreads() between phases and two to three CTAs
+// half2 FMAs inside ONE CTA per 30 x 10 output tile, with plain __syncthreads() between phases and four CTAs (54 KB, 64 registers)
 // per SM overlapping each other's phases:
 //
 //   1. the 25 x 65 image patch (u8 or f32) is staged in shared memory as fp16 (convert_image_dtype fused in);
