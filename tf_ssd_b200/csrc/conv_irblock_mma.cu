@@ -537,10 +537,10 @@ typedef ImCfg<32, 192, 64, 2, 10, 2> ImBlock6;      // 38 -> 19
 // GROUPS of 96 (6 slices): per group  expansion -> depthwise -> projection partial sums (accumulators stay in registers
 // across groups), with the group's weights streamed from L2 by TMA into a double buffer two groups ahead.  One CTA of 16
 // warps per SM, one tile per CTA (4 tiles per image = 128 CTAs at batch 32).
-template <int CIN_, int CEXP_, int COUT_, int TW_, int TH_>
+template <int CIN_, int CEXP_, int COUT_, int TW_, int TH_, int THREADS_ = 512>
 struct ImGCfg {
     static constexpr int CIN = CIN_, CEXP = CEXP_, COUT = COUT_, TW = TW_, TH = TH_;
-    static constexpr int THREADS = 512, WARPS = THREADS / 32;
+    static constexpr int THREADS = THREADS_, WARPS = THREADS / 32;
     static constexpr int GS = 6, GCH = GS * 16, NG = CEXP / GCH;       // slices / channels per group, groups
     static constexpr int KS = CIN / 16;
     static constexpr int PW = TW + 2, PH = TH + 2, P = PW * PH, PPOS = im_up16(P);
@@ -873,7 +873,7 @@ static int irblock_mma_grouped_launch_t(const ssd_irblock_desc* d, cudaStream_t 
 typedef ImGCfg<64, 384, 64, 19, 5> ImBlock7;
 typedef ImGCfg<64, 384, 96, 19, 5> ImBlock10;
 typedef ImGCfg<96, 576, 96, 19, 5> ImBlock11;
-typedef ImGCfg<160, 960, 160, 10, 3> ImBlock14;
+typedef ImGCfg<160, 960, 160, 10, 3, 768> ImBlock14;      // 24 warps: 39 vs 41 us (the 19 x 19 configurations lose with more warps)
 
 // -1 automatic (large-map variant always; the channel-grouped small-map variant when programmatic dependent launch is on:
 // its weight prologue then overlaps the predecessor, which is what makes it faster than the tcgen05 kernel), 0 tcgen05 kernel only, 1 every mma.sync variant that has an instantiation,
