@@ -132,14 +132,8 @@ __device__ __forceinline__ void im_sts128(uint32_t a, const uint4& v) {
 __device__ __forceinline__ void im_sts64(uint32_t a, uint32_t x, uint32_t y) {
     asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
-__device__ __forceinline__ void im_sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void im_sts64f(uint32_t a, float x, float y) {
     asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(x), "f"(y) : "memory");
-}
-__device__ __forceinline__ uint2 im_lds64(uint32_t a) {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
-    return v;
 }
 __device__ __forceinline__ float2 im_lds64f(uint32_t a) {
     float2 v;
@@ -150,13 +144,6 @@ __device__ __forceinline__ float4 im_lds128f(uint32_t a) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
-}
-__device__ __forceinline__ void im_cp16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-// 16 bytes when ok, else 16 bytes of zeros (src-size 0: nothing is read) -- no divergent zero-store path
-__device__ __forceinline__ void im_cp16_zfill(uint32_t dst, const void* src, bool ok) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
 }
 
 template <class Cfg>
@@ -219,7 +206,6 @@ irblock_mma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             tma_load_4d(sIn + ks * Cfg::IN_SL, &map_x, bar_x, 16 * ks, ox0 * S - p.pad_l, oy0 * S - p.pad_t, b);
     };
     if (tid == 0 && (int)blockIdx.x < p.n_tiles) request_patch((int)blockIdx.x);
-    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();                        // barriers initialised, filter + biases visible
     mbar_wait(bar_w, 0);
 
