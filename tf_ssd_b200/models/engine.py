@@ -18,7 +18,9 @@ torch is used for device buffers, streams and graph capture only -- no
 
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import gc
 import math
 import os
 from dataclasses import dataclass
@@ -213,6 +215,22 @@ class _ParamTracer:
                 self.weights[nm + "/kernel"] = self._kernel((3, 3, t.C, c), 9 * t.C, 9 * c, "glorot_uniform")
                 self.weights[nm + "/bias"] = np.zeros(c, np.float32)
                 self.macs += t.H * t.W * 9 * t.C * c
+
+
+@contextlib.contextmanager
+def _no_gc_during_capture():
+    """Stream capture (global mode) is invalidated by any "unsafe" CUDA call of the process -- including the
+    cudaGraphExecDestroy / cudaFree that Python's cyclic garbage collector issues when it happens to reclaim an older
+    DecoderModel / trainer (their graphs and buffers sit in reference cycles with the enqueue closures).  Collect now,
+    and keep the collector off until the capture has ended."""
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was_enabled:
+            gc.enable()
 
 
 # ------------------------------------------------------------------ the plan --
@@ -1079,8 +1097,9 @@ class DecoderModel(object):
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                st["enqueue"](u8)
+            with _no_gc_during_capture():
+                with torch.cuda.graph(g):
+                    st["enqueue"](u8)
             st["graph"][u8] = g
         return g
 

@@ -27,7 +27,7 @@ import torch
 
 from tf_ssd_b200 import _ffi, dist_utils
 from tf_ssd_b200._ffi_conv import ACT_NONE, ConvDesc
-from tf_ssd_b200.models.engine import SSDModel, Step
+from tf_ssd_b200.models.engine import SSDModel, Step, _no_gc_during_capture
 
 L2_REG = 5e-4                  # models/ssd_vgg16.py:76  reg_factor
 
@@ -442,8 +442,9 @@ class Trainer(object):
             graphs = []
             for i in range(len(segments)):           # ... and is then recorded, without executing, for every later step
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    run_segment(i)
+                with _no_gc_during_capture():
+                    with torch.cuda.graph(g):
+                        run_segment(i)
                 graphs.append(g)
             st[key] = graphs
         for i, (_, _, done) in enumerate(segments):
